@@ -13,6 +13,7 @@
  * Each function cites the reference lines it follows. Written from the behaviour, with index
  * arrays instead of pointer-linked nodes; not a copy.
  */
+#define _POSIX_C_SOURCE 200809L
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
