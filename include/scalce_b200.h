@@ -1,0 +1,142 @@
+/*
+ * scalce_b200.h - C ABI of the B200-native SCALCE boosting transform
+ * (core scan -> stateful bucket pick -> bucket histogram -> stable reorder of sequence,
+ * quality and name payloads).
+ *
+ * The reference (sfu-compbio/scalce) has no plugin or FFI layer; its seam is the set of free
+ * functions in reads.h:87-94 driven per read from compress.cpp:600-717 and flushed by
+ * dump_trie (compress.cpp:524-552). This header is the batch form of that seam: plain
+ * pointers and sizes, no C++/torch types. Each entry point names what it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SCB_E* code on failure; the text of the
+ *     last failure is available from scb_last_error(). The reference's convention is
+ *     ERROR() -> "(ERROR) ..." on stderr + exit(1) (const.h:77-81); the CLI glue maps a non-zero
+ *     return to that.
+ *   - there is NO CPU fallback: if no sm_100 device is usable, scb_create fails with
+ *     SCB_ENODEVICE.
+ *   - bit-exactness contract: results equal the reference run with -T 1 (its only deterministic
+ *     mode): per-read bucket, end marker, flush chunk, final permutation and every stream byte.
+ *   - one submitting thread per handle.
+ */
+#ifndef SCALCE_B200_H_
+#define SCALCE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_ABI_VERSION 1
+
+#define SCB_OK 0
+#define SCB_EINVAL -1    /* bad argument / unsupported configuration */
+#define SCB_ENODEVICE -2 /* no usable CUDA device (no fallback exists) */
+#define SCB_ECUDA -3     /* CUDA runtime error, see scb_last_error() */
+#define SCB_ENOMEM -4    /* host or device allocation failed */
+#define SCB_ESTATE -5    /* call order violated */
+#define SCB_EIO -6       /* core-set file could not be read */
+
+/* id/core written for the "no core" (root) bucket: MAXBIN-1, const.h:94, reads.cpp:161-164 */
+#define SCB_ROOT_ID ((1 << 30) - 1)
+
+/* stream numbering = temp-file numbering t_%03d_<k>.tmp (compress.cpp:527-533, reads.cpp:91-180) */
+enum { SCB_S_NAMES = 0, SCB_S_READS = 1, SCB_S_QUALS = 2, SCB_S_META = 3, SCB_S_READS2 = 4, SCB_S_QUALS2 = 5, SCB_N_STREAMS = 6 };
+
+typedef struct scb_handle scb_handle;
+
+/* Replaces the globals the path reads: read_length[2], _use_names, _use_second_file,
+ * _compress_qualities, _max_bucket_set_size (const.h:100-119, main.cpp:62-80). */
+typedef struct scb_config {
+    int32_t read_length[2];    /* L of mate 1, mate 2 (0 when single-end); fixed-length build only */
+    int32_t use_names;         /* 1: names are payload (stream 0); 0: -n mode, one 0 byte per read in size accounting */
+    int32_t paired;            /* _use_second_file */
+    int32_t use_quals;         /* _compress_qualities (0 with -Q / -f) */
+    int32_t device;            /* CUDA device ordinal */
+    uint64_t bucket_set_bytes; /* -B, flush threshold of compress.cpp:708 (default 4 GiB) */
+    int32_t emit_merged;       /* 1: additionally produce the post-merge order (merge(), compress.cpp:488-522) */
+    int32_t reserved;
+} scb_config;
+
+/* One batch of parsed reads in input order: what thread() holds per read after the parse and
+ * after output_name / output_quality (compress.cpp:614-699), as a structure of arrays.
+ *   seq*   ASCII bases, n rows of read_length[m] bytes, no terminator (any case; N and anything
+ *          that is not C/G/T maps to A, const.cpp:47-49)
+ *   qual*  the bytes output_quality produced (q - offset, 0 under 'N'; qualities.cpp:177-204);
+ *          opaque payload to this library. NULL when use_quals == 0.
+ *   names  concatenated name characters as output_name keeps them (after '@', up to the first
+ *          space; names.cpp:48-62) WITHOUT the length byte; name_off[n+1] byte offsets into it.
+ *          A name longer than 255 bytes is an error (the reference's length byte wraps).
+ *          NULL when use_names == 0.
+ * location: 0 = host memory (pageable or pinned), 1 = device memory on cfg.device. */
+typedef struct scb_batch {
+    int64_t n;
+    const uint8_t *seq1, *qual1;
+    const uint8_t *names;
+    const int64_t *name_off;
+    const uint8_t *seq2, *qual2;
+    int32_t location;
+    int32_t reserved;
+} scb_batch;
+
+/* Result of a flush. Streams are byte-identical to what bin_dump writes into the temp files:
+ * stream k of flush chunk c is data[k][chunk_off[k][c] .. chunk_off[k][c+1]).
+ * Pointers are DEVICE pointers owned by the handle, valid until the next submit/flush/destroy;
+ * chunk_off arrays are host memory owned by the handle. Use scb_copy_stream for host copies. */
+typedef struct scb_result {
+    int64_t n_reads;
+    int32_t n_chunks;
+    int32_t n_buckets_nonempty;       /* distinct non-empty buckets over the whole flush */
+    const uint8_t *data[SCB_N_STREAMS];
+    const int64_t *chunk_off[SCB_N_STREAMS];
+    /* post-merge order (emit_merged): one set of streams, meta already merged */
+    const uint8_t *merged[SCB_N_STREAMS];
+    int64_t merged_size[SCB_N_STREAMS];
+    /* per-read arrays in INPUT order (device): bucket id as written to meta (BFS node id,
+     * SCB_ROOT_ID for none), core index (-1 for none), end marker, flush chunk; and the final
+     * permutation in OUTPUT order (perm[j] = input index of the j-th emitted read). */
+    const int32_t *bucket_id, *core_idx, *end, *chunk;
+    const uint32_t *perm;
+    /* device-side time of the last flush in milliseconds (CUDA events on the handle's stream) */
+    float device_ms;
+} scb_result;
+
+/* Replaces read_patterns_from_file + prepare_aho_automata (reads.cpp:379-410, 270-324) for a
+ * core set given as strings; core index = position in the array. */
+int scb_create(const char *const *cores, int32_t n_cores, const scb_config *cfg, scb_handle **out);
+/* Same, loading the set from disk: text (one core per whitespace-separated token, -P file,
+ * reads.cpp:388-394) or patterns.bin records (reads.cpp:338-369); format is sniffed. */
+int scb_create_from_file(const char *path, const scb_config *cfg, scb_handle **out);
+/* Number of cores / automaton states / whether the transition table is shared-memory resident. */
+int scb_table_info(const scb_handle *h, int32_t *n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *smem_resident);
+/* patterns[i] (reads.h:48): NUL-terminated core string by index, owned by the handle. */
+const char *scb_core(const scb_handle *h, int32_t idx);
+
+/* Replaces the per-read calls aho_search / output_read / aho_trie_bucket and the size accounting
+ * (compress.cpp:673-706): appends the batch, in order, to the pending set. */
+int scb_submit(scb_handle *h, const scb_batch *batch);
+/* Replaces dump_trie / aho_output / bin_prepare / bin_dump (compress.cpp:524-552,
+ * reads.cpp:466-499, 600-634, 91-180) for everything pending; lifetime bucket counts
+ * (aho_trie::bin_size, reads.h:82) persist in the handle across flushes. */
+int scb_flush(scb_handle *h, scb_result *out);
+/* Device-to-host copy of one stream slice (chunk >= 0) or of the merged stream (chunk = -1). */
+int scb_copy_stream(scb_handle *h, int32_t stream, int32_t chunk, void *dst, int64_t dst_bytes);
+/* Copies per-read arrays of the last flush to host; any pointer may be NULL. */
+int scb_copy_debug(scb_handle *h, int32_t *bucket_id, int32_t *core_idx, int32_t *end, int32_t *chunk, uint32_t *perm);
+/* unbuck() (reads.cpp:502): reads flushed from the root bucket so far. */
+int64_t scb_unbucketed(const scb_handle *h);
+/* Lifetime count of a core's bucket (bin_size), -1 = root. */
+int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx);
+/* Number of this library's kernel launches since creation (bench.py's gpu_launches). */
+int64_t scb_kernel_launches(const scb_handle *h);
+/* aho_trie_free (reads.cpp:505-535). */
+void scb_destroy(scb_handle *h);
+
+const char *scb_last_error(void);
+int scb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCALCE_B200_H_ */

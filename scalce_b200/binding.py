@@ -1,0 +1,209 @@
+"""ctypes binding of the C ABI (include/scalce_b200.h) and a small host-side wrapper.
+
+The product path is libscalce_b200.so (hand-written sm_100a CUDA). There is no CPU fallback: if
+the library cannot be loaded or no B200-class device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscalce_b200.so")
+
+N_STREAMS = 6
+S_NAMES, S_READS, S_QUALS, S_META, S_READS2, S_QUALS2 = range(6)
+ROOT_ID = (1 << 30) - 1
+
+EXPORTS = [
+    "scb_abi_version", "scb_last_error", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
+    "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
+    "scb_kernel_launches", "scb_destroy",
+]
+
+
+class ScbConfig(C.Structure):
+    _fields_ = [("read_length", C.c_int32 * 2), ("use_names", C.c_int32), ("paired", C.c_int32), ("use_quals", C.c_int32),
+                ("device", C.c_int32), ("bucket_set_bytes", C.c_uint64), ("emit_merged", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ScbBatch(C.Structure):
+    _fields_ = [("n", C.c_int64), ("seq1", C.c_void_p), ("qual1", C.c_void_p), ("names", C.c_void_p), ("name_off", C.c_void_p),
+                ("seq2", C.c_void_p), ("qual2", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ScbResult(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_chunks", C.c_int32), ("n_buckets_nonempty", C.c_int32),
+                ("data", C.c_void_p * N_STREAMS), ("chunk_off", C.POINTER(C.c_int64) * N_STREAMS),
+                ("merged", C.c_void_p * N_STREAMS), ("merged_size", C.c_int64 * N_STREAMS),
+                ("bucket_id", C.c_void_p), ("core_idx", C.c_void_p), ("end", C.c_void_p), ("chunk", C.c_void_p),
+                ("perm", C.c_void_p), ("device_ms", C.c_float)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Loads the shared library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} not found: build it with `python -m scalce_b200.build` (nvcc, sm_100a). "
+                           "scalce_b200 has no CPU fallback.")
+    L = C.CDLL(p)
+    L.scb_abi_version.restype = C.c_int
+    L.scb_last_error.restype = C.c_char_p
+    L.scb_create.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.POINTER(ScbConfig), C.POINTER(C.c_void_p)]
+    L.scb_create_from_file.argtypes = [C.c_char_p, C.POINTER(ScbConfig), C.POINTER(C.c_void_p)]
+    L.scb_table_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    L.scb_core.restype = C.c_char_p
+    L.scb_core.argtypes = [C.c_void_p, C.c_int32]
+    L.scb_submit.argtypes = [C.c_void_p, C.POINTER(ScbBatch)]
+    L.scb_flush.argtypes = [C.c_void_p, C.POINTER(ScbResult)]
+    L.scb_copy_stream.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+    L.scb_copy_debug.argtypes = [C.c_void_p] * 6
+    L.scb_unbucketed.restype = C.c_int64
+    L.scb_unbucketed.argtypes = [C.c_void_p]
+    L.scb_lifetime_count.restype = C.c_int64
+    L.scb_lifetime_count.argtypes = [C.c_void_p, C.c_int32]
+    L.scb_kernel_launches.restype = C.c_int64
+    L.scb_kernel_launches.argtypes = [C.c_void_p]
+    L.scb_destroy.argtypes = [C.c_void_p]
+    if path is None:
+        _lib = L
+    return L
+
+
+class ScbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"scalce_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise ScbError(rc, load_library().scb_last_error().decode(errors="replace"))
+
+
+class FlushResult:
+    """Host-side view of one scb_flush."""
+
+    def __init__(self, tr, res: ScbResult):
+        self._tr = tr
+        self.n_reads = res.n_reads
+        self.n_chunks = res.n_chunks
+        self.n_buckets_nonempty = res.n_buckets_nonempty
+        self.device_ms = res.device_ms
+        self.chunk_off = [[res.chunk_off[k][c] for c in range(res.n_chunks + 1)] for k in range(N_STREAMS)]
+        self.merged_size = [res.merged_size[k] for k in range(N_STREAMS)]
+        self.data_ptr = [res.data[k] for k in range(N_STREAMS)]
+        self.merged_ptr = [res.merged[k] for k in range(N_STREAMS)]
+
+    def stream(self, k, chunk=-1) -> bytes:
+        """Bytes of stream k for a flush chunk (the t_%03d_k.tmp contents) or merged (chunk=-1)."""
+        if chunk < 0:
+            n = self.merged_size[k]
+        else:
+            n = self.chunk_off[k][chunk + 1] - self.chunk_off[k][chunk]
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        _check(load_library().scb_copy_stream(self._tr._h, k, chunk, buf.ctypes.data_as(C.c_void_p), n))
+        return buf[:n].tobytes()
+
+    def debug(self):
+        n = self.n_reads
+        arrs = [np.empty(n, dtype=np.int32) for _ in range(4)] + [np.empty(n, dtype=np.uint32)]
+        _check(load_library().scb_copy_debug(self._tr._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+        return dict(node_id=arrs[0], core=arrs[1], end=arrs[2], chunk=arrs[3], perm=arrs[4])
+
+
+class BoostTransform:
+    """Host-side mirror of the reference's seam for this path (reads.h:87-94 in batch form).
+
+    create  <- read_patterns[_from_file] + prepare_aho_automata
+    submit  <- per-read aho_search / output_read / aho_trie_bucket + size accounting
+    flush   <- dump_trie / aho_output (+ merge() when emit_merged)
+    """
+
+    def __init__(self, cores=None, L1=0, L2=0, *, core_file=None, use_names=True, paired=False, use_quals=True,
+                 bucket_set_bytes=4 << 30, device=0, emit_merged=True):
+        L = load_library()
+        cfg = ScbConfig()
+        cfg.read_length[0] = L1
+        cfg.read_length[1] = L2 if paired else 0
+        cfg.use_names, cfg.paired, cfg.use_quals = int(use_names), int(paired), int(use_quals)
+        cfg.device, cfg.bucket_set_bytes, cfg.emit_merged = device, bucket_set_bytes, int(emit_merged)
+        self.cfg = cfg
+        h = C.c_void_p()
+        if core_file is not None:
+            _check(L.scb_create_from_file(os.fsencode(core_file), C.byref(cfg), C.byref(h)))
+        else:
+            enc = [c.encode() if isinstance(c, str) else c for c in cores]
+            arr = (C.c_char_p * len(enc))(*enc)
+            _check(L.scb_create(arr, len(enc), C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    # -- info ---------------------------------------------------------------------------------
+    def table_info(self):
+        v = [C.c_int32() for _ in range(4)]
+        _check(load_library().scb_table_info(self._h, *[C.byref(x) for x in v]))
+        return dict(n_cores=v[0].value, n_states=v[1].value, n_buckets=v[2].value, smem_resident=bool(v[3].value))
+
+    def core(self, idx):
+        s = load_library().scb_core(self._h, idx)
+        return None if s is None else s.decode()
+
+    # -- data ---------------------------------------------------------------------------------
+    def submit(self, seq, qual=None, names=None, name_off=None, seq2=None, qual2=None):
+        """Host numpy arrays (uint8 [n,L]; names uint8, name_off int64 [n+1])."""
+        def prep(a, dt=np.uint8):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=dt)
+            return a, a.ctypes.data_as(C.c_void_p)
+        keep = []
+        b = ScbBatch()
+        seq, b.seq1 = prep(seq); b.n = seq.shape[0]
+        qual, b.qual1 = prep(qual); names, b.names = prep(names); name_off, b.name_off = prep(name_off, np.int64)
+        seq2, b.seq2 = prep(seq2); qual2, b.qual2 = prep(qual2)
+        keep += [seq, qual, names, name_off, seq2, qual2]
+        b.location = 0
+        _check(load_library().scb_submit(self._h, C.byref(b)))
+
+    def submit_device(self, n, seq, qual=None, names=None, name_off=None, seq2=None, qual2=None):
+        """Raw device pointers (ints), e.g. torch tensors' data_ptr(); buffers must outlive flush()."""
+        b = ScbBatch()
+        b.n = n
+        b.seq1, b.qual1, b.names, b.name_off, b.seq2, b.qual2 = seq, qual, names, name_off, seq2, qual2
+        b.location = 1
+        _check(load_library().scb_submit(self._h, C.byref(b)))
+
+    def flush(self) -> FlushResult:
+        res = ScbResult()
+        _check(load_library().scb_flush(self._h, C.byref(res)))
+        return FlushResult(self, res)
+
+    @property
+    def unbucketed(self):
+        return load_library().scb_unbucketed(self._h)
+
+    def lifetime_count(self, core_idx):
+        return load_library().scb_lifetime_count(self._h, core_idx)
+
+    @property
+    def kernel_launches(self):
+        return load_library().scb_kernel_launches(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().scb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,639 @@
+// api.cu - handle, memory management and the C ABI (include/scalce_b200.h).
+#include "../../include/scalce_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "core_table.h"
+#include "pipeline.cuh"
+#include "prims.cuh"
+
+namespace scb {
+long long g_launches = 0;
+static thread_local std::string g_last_error;
+
+// stream-ordered device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+    DevBuf() {}
+    DevBuf(size_t b, cudaStream_t s) { alloc(b, s); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept { *this = std::move(o); }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; st = o.st; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    void alloc(size_t b, cudaStream_t s) {
+        release();
+        st = s; bytes = b;
+        if (b == 0) b = 16;
+        SCB_CUDA(cudaMallocAsync(&p, b, s));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, st); p = nullptr; bytes = 0; }
+    }
+    ~DevBuf() { release(); }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+static int ceil_log2(uint64_t x) {  // bits needed to represent values in [0, x)
+    int b = 0;
+    while (b < 64 && (1ull << b) < x) b++;
+    return b;
+}
+
+struct Pending {
+    int64_t n = 0;
+    bool borrowed = false;  // device pointers owned by the caller (location = 1)
+    const uint8_t *seq1 = nullptr, *qual1 = nullptr, *names = nullptr, *seq2 = nullptr, *qual2 = nullptr;
+    const int64_t *name_off = nullptr;
+    int64_t name_bytes = 0;
+    DevBuf b_seq1, b_qual1, b_names, b_off, b_seq2, b_qual2;
+};
+
+struct EmitOut {
+    DevBuf data[SCB_N_STREAMS];
+    int64_t size[SCB_N_STREAMS] = {0, 0, 0, 0, 0, 0};
+    std::vector<int64_t> chunk_off[SCB_N_STREAMS];
+    int64_t n_seg = 0;
+};
+
+}  // namespace scb
+
+using namespace scb;
+
+struct scb_handle {
+    scb_config cfg;
+    CoreTable tab;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device tables
+    DevBuf d_next, d_nto, d_rank_level, d_rank_node_id, d_rank_core;
+    DevBuf d_life, d_claim;
+    std::vector<Pending> pending;
+    // last flush
+    Pending cur;
+    DevBuf lvl, ncand, cand_off, cand_rank, cand_pos, asg, endv, chunk, perm_keys, perm, perm_m;
+    DevBuf dbg_bucket, dbg_core, dbg_end, dbg_chunk;
+    EmitOut chunked, merged;
+    int32_t n_chunks = 0;
+    int64_t n_last = 0;
+    int64_t unbucketed = 0;
+    bool smem_resident = false;
+};
+
+namespace scb {
+
+static DfaDev dfa_of(scb_handle *h) {
+    return DfaDev{h->d_next.as<uint32_t>(), h->d_nto.as<int32_t>(), h->d_rank_level.as<uint8_t>(), h->tab.n_states, h->tab.n_buckets};
+}
+
+template <typename T>
+static void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+    b.alloc(v.size() * sizeof(T), st);
+    if (!v.empty()) SCB_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+static int create_common(const std::vector<std::string> &cores, const scb_config *cfg, scb_handle **out) {
+    if (!cfg || !out) { g_last_error = "null argument"; return SCB_EINVAL; }
+    int L1 = cfg->read_length[0], L2 = cfg->read_length[1];
+    if (L1 <= 0 || L1 > 2047 || (cfg->paired && (L2 <= 0 || L2 > 2047))) { g_last_error = "read length out of range (1..2047)"; return SCB_EINVAL; }
+    if (cfg->bucket_set_bytes == 0) { g_last_error = "bucket_set_bytes must be > 0"; return SCB_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        g_last_error = "no usable CUDA device (this library has no CPU path)";
+        return SCB_ENODEVICE;
+    }
+    std::unique_ptr<scb_handle> h(new scb_handle());
+    h->cfg = *cfg;
+    if (!cfg->paired) h->cfg.read_length[1] = 0;
+    std::string err = build_core_table(cores, h->tab);
+    if (!err.empty()) { g_last_error = err; return SCB_EINVAL; }
+    try {
+        SCB_CUDA(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        SCB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 10) { g_last_error = "device is not sm_100 class"; return SCB_ENODEVICE; }
+        SCB_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        SCB_CUDA(cudaEventCreate(&h->ev0));
+        SCB_CUDA(cudaEventCreate(&h->ev1));
+        cudaMemPool_t pool;
+        SCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+        uint64_t thr = ~0ull;
+        SCB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        upload(h->d_next, h->tab.next, h->st);
+        upload(h->d_nto, h->tab.nto_rank, h->st);
+        upload(h->d_rank_level, h->tab.rank_level, h->st);
+        upload(h->d_rank_node_id, h->tab.rank_node_id, h->st);
+        upload(h->d_rank_core, h->tab.rank_core, h->st);
+        size_t nb1 = (size_t)h->tab.n_buckets + 1;
+        h->d_life.alloc(nb1 * 8, h->st);
+        h->d_claim.alloc(nb1 * 4, h->st);
+        SCB_CUDA(cudaMemsetAsync(h->d_life.p, 0, nb1 * 8, h->st));
+        SCB_CUDA(cudaMemsetAsync(h->d_claim.p, 0xff, nb1 * 4, h->st));
+        SCB_CUDA(cudaStreamSynchronize(h->st));
+    } catch (CudaError &e) {
+        g_last_error = e.msg;
+        return SCB_ECUDA;
+    }
+    *out = h.release();
+    return SCB_OK;
+}
+
+// ---- concatenate pending batches into h->cur -------------------------------------------------------
+static void gather_pending(scb_handle *h) {
+    auto &pv = h->pending;
+    cudaStream_t st = h->st;
+    const int L1 = h->cfg.read_length[0], L2 = h->cfg.read_length[1];
+    if (pv.size() == 1) { h->cur = std::move(pv[0]); pv.clear(); return; }
+    Pending c;
+    for (auto &p : pv) { c.n += p.n; c.name_bytes += p.name_bytes; }
+    c.b_seq1.alloc((size_t)c.n * L1, st);
+    if (h->cfg.use_quals) c.b_qual1.alloc((size_t)c.n * L1, st);
+    if (h->cfg.paired) { c.b_seq2.alloc((size_t)c.n * L2, st); if (h->cfg.use_quals) c.b_qual2.alloc((size_t)c.n * L2, st); }
+    if (h->cfg.use_names) { c.b_names.alloc((size_t)c.name_bytes, st); c.b_off.alloc((size_t)(c.n + 1) * 8, st); }
+    int64_t r0 = 0, nb0 = 0;
+    std::vector<int64_t> host_off;
+    for (auto &p : pv) {
+        SCB_CUDA(cudaMemcpyAsync(c.b_seq1.as<uint8_t>() + r0 * L1, p.seq1, (size_t)p.n * L1, cudaMemcpyDeviceToDevice, st));
+        if (h->cfg.use_quals) SCB_CUDA(cudaMemcpyAsync(c.b_qual1.as<uint8_t>() + r0 * L1, p.qual1, (size_t)p.n * L1, cudaMemcpyDeviceToDevice, st));
+        if (h->cfg.paired) {
+            SCB_CUDA(cudaMemcpyAsync(c.b_seq2.as<uint8_t>() + r0 * L2, p.seq2, (size_t)p.n * L2, cudaMemcpyDeviceToDevice, st));
+            if (h->cfg.use_quals) SCB_CUDA(cudaMemcpyAsync(c.b_qual2.as<uint8_t>() + r0 * L2, p.qual2, (size_t)p.n * L2, cudaMemcpyDeviceToDevice, st));
+        }
+        if (h->cfg.use_names) {
+            SCB_CUDA(cudaMemcpyAsync(c.b_names.as<uint8_t>() + nb0, p.names, (size_t)p.name_bytes, cudaMemcpyDeviceToDevice, st));
+            // offsets were rebased to 0 per batch at submit; shift by nb0 on the host copy
+            host_off.resize((size_t)p.n + 1);
+            SCB_CUDA(cudaMemcpyAsync(host_off.data(), p.name_off, (size_t)(p.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            for (auto &o : host_off) o += nb0;
+            SCB_CUDA(cudaMemcpyAsync(c.b_off.as<int64_t>() + r0, host_off.data(), (size_t)(p.n + 1) * 8, cudaMemcpyHostToDevice, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+        }
+        r0 += p.n; nb0 += p.name_bytes;
+    }
+    c.seq1 = c.b_seq1.as<uint8_t>(); c.qual1 = c.b_qual1.as<uint8_t>(); c.seq2 = c.b_seq2.as<uint8_t>(); c.qual2 = c.b_qual2.as<uint8_t>();
+    c.names = c.b_names.as<uint8_t>(); c.name_off = c.b_off.as<int64_t>();
+    pv.clear();
+    h->cur = std::move(c);
+}
+
+// ---- emit one ordering ----------------------------------------------------------------------------------
+static void emit_order(scb_handle *h, const uint32_t *perm, bool merged, EmitOut &o) {
+    cudaStream_t st = h->st;
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    EmitParams e;
+    e.seq1 = c.seq1; e.qual1 = c.qual1; e.names = c.names; e.seq2 = c.seq2; e.qual2 = c.qual2; e.name_off = c.name_off;
+    e.asg = h->asg.as<uint32_t>(); e.endv = h->endv.as<uint16_t>(); e.lvl = h->lvl.as<uint8_t>();
+    e.chunk = h->n_chunks > 1 ? h->chunk.as<uint32_t>() : nullptr;
+    e.perm = perm; e.n = n; e.L1 = L1; e.L2 = L2; e.use_names = cfg.use_names; e.use_quals = cfg.use_quals; e.paired = cfg.paired;
+    e.sz_meta = L1 > 255 ? 2 : 1; e.nb = h->tab.n_buckets; e.root_pos = h->tab.root_order_pos;
+
+    DevBuf offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st), hsum((size_t)(n + 1) * 4, st);
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st), ws32((size_t)scan_tiles(n) * 4, st);
+    exclusive_scan<uint64_t>(NameRec{e}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    exclusive_scan<uint64_t>(ReadRec{e}, n, offR.as<uint64_t>(), offR.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    SegOf seg{e, h->n_chunks, merged ? 1 : 0};
+    exclusive_scan<uint32_t>(SegHead{seg}, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
+    uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
+    SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(&totR, offR.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    const int nlen = 3 + 2 * cfg.paired;
+    const int64_t rsz = 8 + 8 * nlen;
+    o.n_seg = nseg;
+    o.size[SCB_S_NAMES] = (int64_t)totN;
+    o.size[SCB_S_READS] = (int64_t)totR;
+    o.size[SCB_S_QUALS] = cfg.use_quals ? n * L1 : 0;
+    o.size[SCB_S_META] = (int64_t)nseg * rsz;
+    o.size[SCB_S_READS2] = cfg.paired ? n * sz_read(L2) : 0;
+    o.size[SCB_S_QUALS2] = (cfg.paired && cfg.use_quals) ? n * L2 : 0;
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc((size_t)o.size[k], st);
+    if (n > 0)
+        SCB_LAUNCH(emit_k, (unsigned)cdiv(n * 32, 256), 256, 0, st, e, offN.as<uint64_t>(), offR.as<uint64_t>(),
+                   o.data[0].as<uint8_t>(), o.data[1].as<uint8_t>(), o.data[2].as<uint8_t>(), o.data[4].as<uint8_t>(), o.data[5].as<uint8_t>());
+    DevBuf hpos((size_t)(nseg + 1) * 4, st);
+    const int nch = merged ? 1 : h->n_chunks;
+    DevBuf cfirst((size_t)2 * nch * 8, st);
+    if (n > 0) {
+        SCB_LAUNCH(seg_heads_k, (unsigned)cdiv(n, 256), 256, 0, st, seg, hsum.as<uint32_t>(), n, hpos.as<uint32_t>());
+        SCB_LAUNCH(meta_k, (unsigned)cdiv(nseg, 128), 128, 0, st, seg, hpos.as<uint32_t>(), (int64_t)nseg, offN.as<uint64_t>(),
+                   offR.as<uint64_t>(), h->d_rank_node_id.as<int32_t>(), h->d_rank_core.as<int32_t>(), o.data[3].as<uint8_t>(),
+                   merged ? (int64_t *)nullptr : cfirst.as<int64_t>());
+    }
+    // per-chunk offsets of every stream
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.chunk_off[k].assign((size_t)nch + 1, 0);
+    if (!merged && n > 0) {
+        std::vector<int64_t> cf((size_t)2 * nch);
+        SCB_CUDA(cudaMemcpyAsync(cf.data(), cfirst.p, cf.size() * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint64_t> on((size_t)nch), orr((size_t)nch);
+        for (int cidx = 0; cidx < nch; cidx++) {
+            SCB_CUDA(cudaMemcpyAsync(&on[cidx], offN.as<uint64_t>() + cf[cidx], 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&orr[cidx], offR.as<uint64_t>() + cf[cidx], 8, cudaMemcpyDeviceToHost, st));
+        }
+        SCB_CUDA(cudaStreamSynchronize(st));
+        for (int cidx = 0; cidx < nch; cidx++) {
+            int64_t p0 = cf[cidx], m0 = cf[nch + cidx];
+            o.chunk_off[SCB_S_NAMES][cidx] = (int64_t)on[cidx];
+            o.chunk_off[SCB_S_READS][cidx] = (int64_t)orr[cidx];
+            o.chunk_off[SCB_S_QUALS][cidx] = cfg.use_quals ? p0 * L1 : 0;
+            o.chunk_off[SCB_S_META][cidx] = m0 * rsz;
+            o.chunk_off[SCB_S_READS2][cidx] = cfg.paired ? p0 * sz_read(L2) : 0;
+            o.chunk_off[SCB_S_QUALS2][cidx] = (cfg.paired && cfg.use_quals) ? p0 * L2 : 0;
+        }
+    }
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.chunk_off[k][nch] = o.size[k];
+}
+
+// ---- the transform ---------------------------------------------------------------------------------------
+static void run_flush(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    gather_pending(h);
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    h->n_last = n;
+    const int nb = h->tab.n_buckets;
+    SCB_CUDA(cudaEventRecord(h->ev0, st));
+
+    // 1. scan: level + candidate counts, then candidates
+    h->lvl.alloc((size_t)n, st);
+    h->ncand.alloc((size_t)n * 2, st);
+    h->cand_off.alloc((size_t)(n + 1) * 8, st);
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+    DfaDev dfa = dfa_of(h);
+    if (n > 0)
+        SCB_LAUNCH((scan_k<false>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
+                   h->ncand.as<uint16_t>(), (const uint64_t *)nullptr, (uint32_t *)nullptr, (uint16_t *)nullptr);
+    exclusive_scan<uint64_t>(LoadAs<uint16_t, uint64_t>{h->ncand.as<uint16_t>()}, n, h->cand_off.as<uint64_t>(),
+                             h->cand_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    uint64_t M = 0;
+    SCB_CUDA(cudaMemcpyAsync(&M, h->cand_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->cand_rank.alloc((size_t)M * 4, st);
+    h->cand_pos.alloc((size_t)M * 2, st);
+    if (n > 0)
+        SCB_LAUNCH((scan_k<true>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
+                   h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>());
+
+    // 2. resolve
+    h->asg.alloc((size_t)n * 4, st);
+    h->endv.alloc((size_t)n * 2, st);
+    unsigned long long root_before = 0, root_after = 0;
+    SCB_CUDA(cudaMemcpyAsync(&root_before, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    {
+        size_t smem = ((size_t)nb + 1) * 12;
+        if (smem <= 200 * 1024) {
+            SCB_CUDA(cudaFuncSetAttribute(resolve_seq_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCB_LAUNCH((resolve_seq_k<true>), 1, 32, smem, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
+                       h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), h->d_life.as<unsigned long long>(),
+                       h->d_claim.as<uint32_t>(), h->asg.as<uint32_t>(), h->endv.as<uint16_t>(), nb);
+        } else {
+            SCB_LAUNCH((resolve_seq_k<false>), 1, 32, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
+                       h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), h->d_life.as<unsigned long long>(),
+                       h->d_claim.as<uint32_t>(), h->asg.as<uint32_t>(), h->endv.as<uint16_t>(), nb);
+        }
+    }
+    SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+
+    // 3. sizes -> flush chunks
+    {
+        int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
+        RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
+        DevBuf S((size_t)(n + 1) * 8, st);
+        exclusive_scan<uint64_t>(rs, n, S.as<uint64_t>(), S.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        // upper bound on chunks: every read adds at most 256 + sz_read(L1) + L1 + mate 2 + 40 bytes
+        uint64_t max_rd = 256 + (uint64_t)sz_read(L1) + L1 + sz_read(L2) + L2 + 40;
+        uint64_t cap64 = (uint64_t)n * max_rd / cfg.bucket_set_bytes + 2;
+        if (cap64 > (uint64_t)n + 1) cap64 = (uint64_t)n + 1;
+        if (cap64 > (1u << 24)) throw CudaError{"bucket_set_bytes too small for this many reads (more than 2^24 flush chunks)"};
+        int cap = (int)cap64;
+        DevBuf cstart((size_t)cap * 4, st), dn(4, st);
+        SCB_LAUNCH(chunk_bounds_k, 1, 1, 0, st, S.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, cstart.as<uint32_t>(), cap, dn.as<int>());
+        int nch = 0;
+        SCB_CUDA(cudaMemcpyAsync(&nch, dn.p, 4, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        if (nch > cap) throw CudaError{"internal: chunk capacity exceeded"};
+        h->n_chunks = nch;
+        if (nch > 1) {
+            h->chunk.alloc((size_t)n * 4, st);
+            SCB_LAUNCH(chunk_ids_k, (unsigned)cdiv(n, 256), 256, 0, st, cstart.as<uint32_t>(), nch, n, h->chunk.as<uint32_t>());
+        } else {
+            h->chunk.release();
+        }
+    }
+    if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
+
+    // 4. sort by (chunk, bucket order, key prefix), stable in input order
+    const int nch = h->n_chunks > 0 ? h->n_chunks : 1;
+    const int seg_bits = ceil_log2((uint64_t)nch * (uint64_t)(nb + 1));
+    if (seg_bits > 40) throw CudaError{"too many (chunk, bucket) segments"};
+    int pb = std::min(L1, (64 - seg_bits) / 2);
+    DevBuf k0((size_t)n * 8, st), k1((size_t)n * 8, st), v1((size_t)n * 4, st);
+    h->perm.alloc((size_t)n * 4, st);
+    SortWs ws;
+    DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
+    ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
+    uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
+    uint32_t *va = h->perm.as<uint32_t>(), *vb = v1.as<uint32_t>();
+    if (n > 0) {
+        SCB_LAUNCH(build_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, c.seq1, n, L1, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+                   h->n_chunks > 1 ? h->chunk.as<uint32_t>() : (const uint32_t *)nullptr, nb, h->tab.root_order_pos, seg_bits, pb, ka, va);
+        radix_sort_pairs(&ka, &va, &kb, &vb, n, 64 - seg_bits - 2 * pb, 64, ws, st);
+        if (va != h->perm.as<uint32_t>()) {  // result landed in the alternate buffer
+            SCB_CUDA(cudaMemcpyAsync(h->perm.p, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            va = h->perm.as<uint32_t>();
+        }
+    }
+
+    // 5. refine ties with further key bases until unique or the key is exhausted
+    {
+        const uint64_t *cur_keys = ka;
+        const uint32_t *cur_idx = h->perm.as<uint32_t>();
+        const uint32_t *cur_pos = nullptr;
+        int64_t m = n;
+        int consumed = pb;
+        DevBuf keep_keys, keep_idx, keep_pos;  // own the current compact state across rounds
+        while (consumed < L1 && m > 1) {
+            DevBuf flag((size_t)m, st), cpos((size_t)(m + 1) * 4, st), hsum((size_t)(m + 1) * 4, st), w32((size_t)scan_tiles(m) * 4, st);
+            SCB_LAUNCH(tie_flags_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, m, flag.as<uint8_t>());
+            exclusive_scan<uint32_t>(LoadAs<uint8_t, uint32_t>{flag.as<uint8_t>()}, m, cpos.as<uint32_t>(), cpos.as<uint32_t>() + m, w32.as<uint32_t>(), st);
+            exclusive_scan<uint32_t>(HeadFlag{cur_keys, flag.as<uint8_t>()}, m, hsum.as<uint32_t>(), hsum.as<uint32_t>() + m, w32.as<uint32_t>(), st);
+            uint32_t t = 0, G = 0;
+            SCB_CUDA(cudaMemcpyAsync(&t, cpos.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&G, hsum.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            if (t == 0) break;
+            DevBuf c_pos((size_t)t * 4, st), c_idx((size_t)t * 4, st), c_grp((size_t)t * 4, st);
+            SCB_LAUNCH(tie_compact_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, flag.as<uint8_t>(), cpos.as<uint32_t>(),
+                       hsum.as<uint32_t>(), cur_pos, cur_idx, m, c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), c_grp.as<uint32_t>());
+            int grp_bits = ceil_log2(G);
+            int nbases = std::min(std::min(32, (64 - grp_bits) / 2), L1 - consumed);
+            DevBuf nk0((size_t)t * 8, st), nk1((size_t)t * 8, st), nv0((size_t)t * 4, st), nv1((size_t)t * 4, st);
+            uint64_t *a = nk0.as<uint64_t>(), *b = nk1.as<uint64_t>();
+            uint32_t *x = nv0.as<uint32_t>(), *y = nv1.as<uint32_t>();
+            SCB_LAUNCH(tie_rekey_k, (unsigned)cdiv(t, 256), 256, 0, st, c.seq1, L1, h->endv.as<uint16_t>(), c_idx.as<uint32_t>(),
+                       c_grp.as<uint32_t>(), (int64_t)t, grp_bits, consumed, nbases, a, x);
+            radix_sort_pairs(&a, &x, &b, &y, t, 64 - grp_bits - 2 * nbases, 64, ws, st);
+            SCB_LAUNCH(tie_writeback_k, (unsigned)cdiv(t, 256), 256, 0, st, c_pos.as<uint32_t>(), x, (int64_t)t, h->perm.as<uint32_t>());
+            // next round works on the compact state
+            bool in0 = (a == nk0.as<uint64_t>());
+            keep_keys = in0 ? std::move(nk0) : std::move(nk1);
+            keep_idx = (x == nv0.as<uint32_t>()) ? std::move(nv0) : std::move(nv1);
+            keep_pos = std::move(c_pos);
+            cur_keys = keep_keys.as<uint64_t>(); cur_idx = keep_idx.as<uint32_t>(); cur_pos = keep_pos.as<uint32_t>();
+            m = t; consumed += nbases;
+        }
+    }
+
+    // 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
+    emit_order(h, h->perm.as<uint32_t>(), false, h->chunked);
+    if (cfg.emit_merged && h->n_chunks > 1) {
+        // merge() concatenates a bucket's pieces in chunk order (compress.cpp:104-112): a stable sort of the
+        // chunk-major order by bucket order gives exactly that
+        const int ob = ceil_log2((uint64_t)nb + 1);
+        h->perm_m.alloc((size_t)n * 4, st);
+        uint64_t *a = k0.as<uint64_t>(), *b = k1.as<uint64_t>();
+        uint32_t *x = h->perm_m.as<uint32_t>(), *y = v1.as<uint32_t>();
+        SCB_LAUNCH(merged_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), h->perm.as<uint32_t>(), n, nb,
+                   h->tab.root_order_pos, a, x);
+        radix_sort_pairs(&a, &x, &b, &y, n, 0, ob, ws, st);
+        if (x != h->perm_m.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->perm_m.p, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        emit_order(h, h->perm_m.as<uint32_t>(), true, h->merged);
+    }
+
+    // 7. per-read arrays in input order
+    h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
+    if (n > 0) {
+        SCB_LAUNCH(debug_arrays_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->asg.as<uint32_t>(), nb, h->d_rank_node_id.as<int32_t>(),
+                   h->d_rank_core.as<int32_t>(), h->dbg_bucket.as<int32_t>(), h->dbg_core.as<int32_t>());
+        SCB_LAUNCH(widen_u16_k, (unsigned)cdiv(n, 256), 256, 0, st, h->endv.as<uint16_t>(), n, h->dbg_end.as<int32_t>());
+        if (h->n_chunks > 1) SCB_CUDA(cudaMemcpyAsync(h->dbg_chunk.p, h->chunk.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        else SCB_CUDA(cudaMemsetAsync(h->dbg_chunk.p, 0, (size_t)n * 4, st));
+    }
+    SCB_CUDA(cudaEventRecord(h->ev1, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace scb
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define SCB_TRY try {
+#define SCB_CATCH                                                          \
+    }                                                                      \
+    catch (scb::CudaError & e) { scb::g_last_error = e.msg; return SCB_ECUDA; } \
+    catch (std::bad_alloc &) { scb::g_last_error = "host allocation failed"; return SCB_ENOMEM; }
+
+extern "C" {
+
+int scb_abi_version(void) { return SCB_ABI_VERSION; }
+const char *scb_last_error(void) { return scb::g_last_error.c_str(); }
+
+int scb_create(const char *const *cores, int32_t n_cores, const scb_config *cfg, scb_handle **out) {
+    if (n_cores < 0 || (n_cores > 0 && !cores)) { scb::g_last_error = "bad core array"; return SCB_EINVAL; }
+    std::vector<std::string> v;
+    v.reserve((size_t)n_cores);
+    for (int32_t i = 0; i < n_cores; i++) {
+        if (!cores[i]) { scb::g_last_error = "null core string"; return SCB_EINVAL; }
+        v.emplace_back(cores[i]);
+    }
+    return scb::create_common(v, cfg, out);
+}
+
+int scb_create_from_file(const char *path, const scb_config *cfg, scb_handle **out) {
+    if (!path) { scb::g_last_error = "null path"; return SCB_EINVAL; }
+    std::vector<std::string> v;
+    std::string err = scb::load_core_file(path, v);
+    if (!err.empty()) { scb::g_last_error = err; return SCB_EIO; }
+    return scb::create_common(v, cfg, out);
+}
+
+int scb_table_info(const scb_handle *h, int32_t *n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *smem_resident) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    if (n_cores) *n_cores = (int32_t)h->tab.cores.size();
+    if (n_states) *n_states = h->tab.n_states;
+    if (n_buckets) *n_buckets = h->tab.n_buckets;
+    if (smem_resident) *smem_resident = h->smem_resident ? 1 : 0;
+    return SCB_OK;
+}
+
+const char *scb_core(const scb_handle *h, int32_t idx) {
+    if (!h || idx < 0 || idx >= (int32_t)h->tab.cores.size()) return nullptr;
+    return h->tab.cores[(size_t)idx].c_str();
+}
+
+int scb_submit(scb_handle *h, const scb_batch *b) {
+    if (!h || !b) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    const scb_config &cfg = h->cfg;
+    if (b->n < 0 || (!b->seq1 && b->n > 0)) { scb::g_last_error = "bad batch"; return SCB_EINVAL; }
+    if (b->n == 0) return SCB_OK;
+    if ((cfg.use_quals && !b->qual1) || (cfg.use_names && (!b->names || !b->name_off)) ||
+        (cfg.paired && (!b->seq2 || (cfg.use_quals && !b->qual2)))) { scb::g_last_error = "batch is missing an array the configuration requires"; return SCB_EINVAL; }
+    int64_t total = b->n;
+    for (auto &p : h->pending) total += p.n;
+    if (total >= (1ll << 31)) { scb::g_last_error = "more than 2^31-1 reads pending; flush first"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(cfg.device));
+    cudaStream_t st = h->st;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    scb::Pending p;
+    p.n = b->n;
+    if (b->location == 1) {
+        p.borrowed = true;
+        p.seq1 = b->seq1; p.qual1 = b->qual1; p.seq2 = b->seq2; p.qual2 = b->qual2; p.names = b->names; p.name_off = b->name_off;
+        if (cfg.use_names) {
+            int64_t o[2];
+            SCB_CUDA(cudaMemcpyAsync(&o[0], b->name_off, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&o[1], b->name_off + b->n, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            if (o[0] != 0) { scb::g_last_error = "device batches must have name_off[0] == 0"; return SCB_EINVAL; }
+            p.name_bytes = o[1];
+        }
+    } else {
+        auto up = [&](scb::DevBuf &d, const void *src, size_t bytes) {
+            d.alloc(bytes, st);
+            SCB_CUDA(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
+        };
+        up(p.b_seq1, b->seq1, (size_t)b->n * L1);
+        if (cfg.use_quals) up(p.b_qual1, b->qual1, (size_t)b->n * L1);
+        if (cfg.paired) { up(p.b_seq2, b->seq2, (size_t)b->n * L2); if (cfg.use_quals) up(p.b_qual2, b->qual2, (size_t)b->n * L2); }
+        if (cfg.use_names) {
+            int64_t o0 = b->name_off[0];
+            p.name_bytes = b->name_off[b->n] - o0;
+            for (int64_t i = 0; i < b->n; i++) {
+                int64_t len = b->name_off[i + 1] - b->name_off[i];
+                if (len < 0 || len > 255) { scb::g_last_error = "name length outside 0..255"; return SCB_EINVAL; }
+            }
+            up(p.b_names, b->names + o0, (size_t)p.name_bytes);
+            if (o0 == 0) up(p.b_off, b->name_off, (size_t)(b->n + 1) * 8);
+            else {
+                std::vector<int64_t> tmp((size_t)b->n + 1);
+                for (int64_t i = 0; i <= b->n; i++) tmp[(size_t)i] = b->name_off[i] - o0;
+                up(p.b_off, tmp.data(), tmp.size() * 8);
+                SCB_CUDA(cudaStreamSynchronize(st));
+            }
+        }
+        p.seq1 = p.b_seq1.as<uint8_t>(); p.qual1 = p.b_qual1.as<uint8_t>(); p.seq2 = p.b_seq2.as<uint8_t>(); p.qual2 = p.b_qual2.as<uint8_t>();
+        p.names = p.b_names.as<uint8_t>(); p.name_off = p.b_off.as<int64_t>();
+        // pageable sources must not be reused by the caller before the copy is done
+        SCB_CUDA(cudaStreamSynchronize(st));
+    }
+    h->pending.push_back(std::move(p));
+    SCB_CATCH
+    return SCB_OK;
+}
+
+int scb_flush(scb_handle *h, scb_result *out) {
+    if (!h || !out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (h->pending.empty()) h->pending.emplace_back();
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::run_flush(h);
+    float ms = 0;
+    SCB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    out->device_ms = ms;
+    SCB_CATCH
+    out->n_reads = h->n_last;
+    out->n_chunks = h->n_chunks;
+    out->n_buckets_nonempty = (int32_t)(h->cfg.emit_merged && h->n_chunks > 1 ? h->merged.n_seg : (h->n_chunks <= 1 ? h->chunked.n_seg : 0));
+    const bool alias = !(h->cfg.emit_merged && h->n_chunks > 1);
+    for (int k = 0; k < SCB_N_STREAMS; k++) {
+        out->data[k] = h->chunked.data[k].as<uint8_t>();
+        out->chunk_off[k] = h->chunked.chunk_off[k].data();
+        if (h->cfg.emit_merged) {
+            const scb::EmitOut &m = alias ? h->chunked : h->merged;
+            out->merged[k] = m.data[k].as<uint8_t>();
+            out->merged_size[k] = m.size[k];
+        }
+    }
+    out->bucket_id = h->dbg_bucket.as<int32_t>(); out->core_idx = h->dbg_core.as<int32_t>();
+    out->end = h->dbg_end.as<int32_t>(); out->chunk = h->dbg_chunk.as<int32_t>();
+    out->perm = h->perm.as<uint32_t>();
+    return SCB_OK;
+}
+
+int scb_copy_stream(scb_handle *h, int32_t stream, int32_t chunk, void *dst, int64_t dst_bytes) {
+    if (!h || stream < 0 || stream >= SCB_N_STREAMS || (!dst && dst_bytes > 0)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    const uint8_t *src; int64_t bytes;
+    if (chunk < 0) {
+        if (!h->cfg.emit_merged) { scb::g_last_error = "merged output was not requested (emit_merged = 0)"; return SCB_ESTATE; }
+        const scb::EmitOut &m = (h->n_chunks > 1) ? h->merged : h->chunked;
+        src = m.data[stream].as<uint8_t>(); bytes = m.size[stream];
+    } else {
+        if (chunk >= h->n_chunks) { scb::g_last_error = "chunk out of range"; return SCB_EINVAL; }
+        const auto &co = h->chunked.chunk_off[stream];
+        src = h->chunked.data[stream].as<uint8_t>() + co[(size_t)chunk]; bytes = co[(size_t)chunk + 1] - co[(size_t)chunk];
+    }
+    if (dst_bytes < bytes) { scb::g_last_error = "destination too small"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    if (bytes > 0) SCB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->st));
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    SCB_CATCH
+    return SCB_OK;
+}
+
+int scb_copy_debug(scb_handle *h, int32_t *bucket_id, int32_t *core_idx, int32_t *end, int32_t *chunk, uint32_t *perm) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    size_t b = (size_t)h->n_last * 4;
+    if (b) {
+        if (bucket_id) SCB_CUDA(cudaMemcpyAsync(bucket_id, h->dbg_bucket.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (core_idx) SCB_CUDA(cudaMemcpyAsync(core_idx, h->dbg_core.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (end) SCB_CUDA(cudaMemcpyAsync(end, h->dbg_end.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (chunk) SCB_CUDA(cudaMemcpyAsync(chunk, h->dbg_chunk.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (perm) SCB_CUDA(cudaMemcpyAsync(perm, h->perm.p, b, cudaMemcpyDeviceToHost, h->st));
+    }
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    SCB_CATCH
+    return SCB_OK;
+}
+
+int64_t scb_unbucketed(const scb_handle *h) { return h ? h->unbucketed : -1; }
+
+int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx) {
+    if (!h) return -1;
+    int32_t r = h->tab.n_buckets;
+    if (core_idx >= 0) {
+        if (core_idx >= (int32_t)h->tab.core_to_rank.size()) return -1;
+        r = h->tab.core_to_rank[(size_t)core_idx];
+    }
+    unsigned long long v = 0;
+    cudaSetDevice(h->cfg.device);
+    if (cudaMemcpy(&v, h->d_life.as<unsigned long long>() + r, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+
+int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches; }
+
+void scb_destroy(scb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    cudaStream_t st = h->st;
+    cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+    delete h;  // DevBufs free stream-ordered
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+}
+
+}  // extern "C"

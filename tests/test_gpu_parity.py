@@ -1,0 +1,120 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(n, L, **kw):
+    run_kw = {k: kw.pop(k) for k in list(kw) if k in ("use_names", "use_quals", "bucket_set_bytes", "splits")}
+    paired = kw.get("paired", False)
+    cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, **run_kw)
+    t, r = util.run_cuda(cores, b, q1, q2, paired=paired, **run_kw)
+    util.assert_same(o, t, r, paired=paired)
+    return o, t, r
+
+
+def test_single_end_100():
+    _case(20000, 100, seed=1)
+
+
+def test_multi_chunk():
+    o, t, r = _case(20000, 100, seed=2, bucket_set_bytes=1 << 20)
+    assert r.n_chunks > 2
+
+
+def test_paired():
+    _case(20000, 100, seed=3, paired=True)
+
+
+def test_paired_multi_chunk_l2():
+    _case(20000, 100, seed=4, paired=True, L2=75, bucket_set_bytes=1 << 20)
+
+
+def test_no_names():
+    _case(20000, 100, seed=5, use_names=False)
+
+
+def test_no_quals():
+    _case(5000, 100, seed=15, use_quals=False)
+
+
+def test_long_reads_two_byte_end():
+    _case(5000, 300, seed=6, bucket_set_bytes=1 << 20)
+
+
+def test_short_reads_lowercase():
+    _case(20000, 36, seed=7, lower=0.05)
+
+
+def test_long_cores():
+    _case(20000, 100, seed=8, spec=[(8, 100), (14, 50), (20, 30), (32, 10)])
+
+
+def test_many_n_and_duplicates():
+    # heavy N content makes many identical keys -> exercises tie refinement on long runs
+    cores, b, q1, q2, _ = util.make_case(4000, 100, seed=9, n_frac=0.3)
+    b.seq[1000:1400] = b.seq[0]          # 400 identical reads
+    b.seq[2000:2200, :60] = b.seq[1, :60]  # long common prefixes
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
+
+
+def test_all_identical_reads():
+    cores, b, q1, q2, _ = util.make_case(3000, 64, seed=10)
+    b.seq[:] = b.seq[0]
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
+
+
+def test_split_submits_and_second_flush_keeps_lifetime_counts():
+    cores, b, q1, q2, _ = util.make_case(12000, 100, seed=11)
+    o = util.run_oracle(cores, b, q1, q2, splits=[5000])
+    t, r = util.run_cuda(cores, b, q1, q2, splits=[100, 5000])
+    util.assert_same(o, t, r)
+    for ci in (0, 5, 17):
+        assert o.lifetime_count(ci) == t.lifetime_count(ci)
+
+
+def test_tiny_inputs():
+    for n in (1, 2, 31, 33):
+        _case(n, 50, seed=12 + n)
+
+
+def test_no_core_starting_with_some_base():
+    # aho_output meets the root early when a base starts no core (reads.cpp:473-476)
+    spec_cores = ["CCGTAGGT", "GGATTACA", "TTTTGGGA", "CGCGCGAT"]  # nothing starts with A
+    from scalce_b200 import synth
+    b = synth.make_batch(3000, 60, seed=21)
+    synth.plant_cores(b, spec_cores, seed=22, frac=0.6)
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(spec_cores, b, q1, None)
+    t, r = util.run_cuda(spec_cores, b, q1, None)
+    util.assert_same(o, t, r)
+
+
+def test_dense_core_set_many_candidates():
+    # every 4-mer is a core -> every position hits, dozens of distinct candidates per read
+    import itertools
+    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]
+    from scalce_b200 import synth
+    b = synth.make_batch(2000, 80, seed=23)
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, None)
+    t, r = util.run_cuda(cores, b, q1, None)
+    util.assert_same(o, t, r)
+
+
+def test_million_reads_bucket_ids():
+    cores, b, q1, q2, _ = util.make_case(300000, 100, seed=31, plant=0.0,
+                                         spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)

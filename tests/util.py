@@ -1,0 +1,78 @@
+"""Shared helpers for the parity tests: one seeded case -> oracle result and CUDA result."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle as orc
+from oracle.gen_cores import make_cores
+from scalce_b200 import synth
+
+DEFAULT_SPEC = [(8, 256), (9, 128), (10, 128), (11, 64), (12, 64)]
+
+
+def make_case(n, L, spec=DEFAULT_SPEC, seed=1, paired=False, L2=None, plant=0.5, lower=0.0, n_frac=0.001, high_entropy=False):
+    cores = make_cores(seed, spec)
+    b = synth.make_batch(n, L, seed=seed, paired=paired, L2=L2, lower_frac=lower, n_frac=n_frac, high_entropy=high_entropy)
+    if plant:
+        synth.plant_cores(b, cores, seed=seed + 1, frac=plant)
+    off = orc.detect_phred_offset(b.qual)
+    q1 = orc.quality_payload(b.qual, b.seq, off)
+    q2 = orc.quality_payload(b.qual2, b.seq2, orc.detect_phred_offset(b.qual2)) if paired else None
+    return cores, b, q1, q2, off
+
+
+def run_oracle(cores, b, q1, q2, *, use_names=True, paired=False, use_quals=True, bucket_set_bytes=4 << 30, splits=None):
+    L1 = b.seq.shape[1]
+    L2 = b.seq2.shape[1] if paired else 0
+    o = orc.Oracle(cores, L1, L2, use_names=use_names, paired=paired, use_quals=use_quals, bucket_set_bytes=bucket_set_bytes)
+    _submit_split(o.submit, b, q1, q2, paired, splits)
+    o.finish()
+    return o
+
+
+def _submit_split(submit, b, q1, q2, paired, splits):
+    n = b.seq.shape[0]
+    cuts = [0] + list(splits or []) + [n]
+    for a, z in zip(cuts[:-1], cuts[1:]):
+        if z <= a:
+            continue
+        no = b.name_off[a:z + 1]
+        submit(b.seq[a:z], q1[a:z] if q1 is not None else None, b.names, no,
+               b.seq2[a:z] if paired else None, q2[a:z] if (paired and q2 is not None) else None)
+
+
+def run_cuda(cores, b, q1, q2, *, use_names=True, paired=False, use_quals=True, bucket_set_bytes=4 << 30, splits=None,
+             emit_merged=True):
+    from scalce_b200.binding import BoostTransform
+    L1 = b.seq.shape[1]
+    L2 = b.seq2.shape[1] if paired else 0
+    t = BoostTransform(cores, L1, L2, use_names=use_names, paired=paired, use_quals=use_quals,
+                       bucket_set_bytes=bucket_set_bytes, emit_merged=emit_merged)
+    _submit_split(t.submit, b, q1 if use_quals else None, q2 if use_quals else None, paired, splits)
+    r = t.flush()
+    return t, r
+
+
+def assert_same(o, t, r, paired=False, check_merged=True):
+    dbg_o, dbg_c = o.debug(), r.debug()
+    for k in ("node_id", "core", "end", "chunk"):
+        bad = np.nonzero(dbg_o[k] != dbg_c[k])[0]
+        assert bad.size == 0, f"per-read {k} differs at {bad[:5]}: oracle {dbg_o[k][bad[:5]]} cuda {dbg_c[k][bad[:5]]}"
+    assert o.n_chunks == r.n_chunks
+    streams = [0, 1, 2, 3] + ([4, 5] if paired else [])
+    for c in range(o.n_chunks):
+        for k in streams:
+            a, b = o.stream(k, c), r.stream(k, c)
+            assert a == b, f"chunk {c} stream {k}: oracle {len(a)} B, cuda {len(b)} B, first diff {_first_diff(a, b)}"
+    if check_merged:
+        for k in streams:
+            a, b = o.stream(k, -1), r.stream(k, -1)
+            assert a == b, f"merged stream {k}: oracle {len(a)} B, cuda {len(b)} B, first diff {_first_diff(a, b)}"
+    assert o.unbucketed == t.unbucketed
+
+
+def _first_diff(a, b):
+    n = min(len(a), len(b))
+    x = np.frombuffer(a[:n], dtype=np.uint8) != np.frombuffer(b[:n], dtype=np.uint8)
+    nz = np.nonzero(x)[0]
+    return int(nz[0]) if nz.size else n
