@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py - throughput of the boosting transform (core scan + bucket + reorder) on B200.
+
+A step = one pass of the hot path (scb_submit + scb_flush through the C ABI) over one batch of
+synthetic fixed-length reads. Workload at 1 GPU = BASELINE.json configs[1]: 50M x 150 bp
+single-end; under torchrun every rank runs the same per-GPU workload on its own shard (weak
+scaling, no data-path collective yet: bucket order is shard-local, see DESIGN.md "multi-GPU").
+
+  value  reads/s with inputs resident in HBM when the timed region starts (CUDA events on the
+         library's stream, max over ranks)
+  e2e    reads/s through the same C ABI with HOST (pinned) buffers: H2D of all inputs and D2H
+         of every output stream inside the timed region
+  --impl reference : the reference's own CPU transform (oracle/_ref, unmodified objects)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEADLINE_SPEC = [(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)]  # 2048 synthetic cores, seed 7
+CORE_SEED = 7
+NAME_BYTES = 13  # "SYN.%09d"
+
+
+def algorithmic_bytes_per_read(L, name_len, mean_core, paired=False, L2=0):
+    """read seq L + qual L + name; write name + packed + end marker + qual L."""
+    b = 3 * L + 2 * (name_len + 1) + (L - mean_core + 3) // 4 + (2 if L > 255 else 1)
+    if paired:
+        b += 3 * L2 + (L2 + 3) // 4
+    return b
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def headline_cores():
+    # same generator as oracle/gen_cores.py, duplicated here because the product bench must not
+    # import oracle/ outside the cpu_baseline / reference legs
+    rng = np.random.default_rng(CORE_SEED)
+    out = []
+    for ln, cnt in HEADLINE_SPEC:
+        seen = set()
+        while len(seen) < cnt:
+            codes = rng.integers(0, 4, size=((cnt - len(seen)) * 2 + 8, ln), dtype=np.uint8)
+            for row in codes:
+                s = "".join("ACGT"[c] for c in row)
+                if s not in seen:
+                    seen.add(s); out.append(s)
+                    if len(seen) == cnt:
+                        break
+    return out
+
+
+def run_reference_harness(cores, seq, qual, names, name_off, L, threads_note="1"):
+    """Times the unmodified reference objects (oracle/_ref/libref_harness.so) or, if that was not
+    built, the oracle port, on host arrays. Returns (reads_per_s, kind, seconds)."""
+    n = seq.shape[0]
+    harness = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+    d = tempfile.mkdtemp(prefix="scb_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        if os.path.exists(harness):
+            with open(os.path.join(d, "cores.txt"), "w") as f:
+                f.write("\n".join(cores) + "\n")
+            H = C.CDLL(harness)
+            H.refh_init.restype = C.c_double
+            H.refh_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
+            H.refh_run.restype = C.c_double
+            H.refh_run.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            # the harness prints the reference's own LOG lines to stderr
+            H.refh_init(os.path.join(d, "cores.txt").encode(), L, 0, 0, 1, 4 << 30)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            nch = C.c_int()
+            secs = H.refh_run(n, p(seq), p(qual), p(names), p(name_off), None, None, 33, d.encode(), C.byref(nch), None, None)
+            return n / secs, "reference", secs
+        from oracle import oracle as orc
+        q1 = orc.quality_payload(qual, seq, 33)
+        t0 = time.perf_counter()
+        o = orc.Oracle(cores, L)
+        o.submit(seq, q1, names, name_off)
+        o.finish()
+        secs = time.perf_counter() - t0
+        return n / secs, "port", secs
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def synth_host_sample(n, L, seed):
+    from scalce_b200 import synth
+    b = synth.make_batch(n, L, seed=seed)
+    W = NAME_BYTES
+    names = np.frombuffer(b"".join(b"SYN.%09d" % i for i in range(n)), dtype=np.uint8).copy()
+    name_off = np.arange(n + 1, dtype=np.int64) * W
+    return b.seq, b.qual, names, name_off
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU per step (configs[1]: 50M)")
+    ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    N, L = a.reads, a.length
+    cores = headline_cores()
+    workload = f"synthetic {N // 1_000_000}M x {L}bp single-end FASTQ per GPU (BASELINE configs[1]), {len(cores)} synthetic cores 8-12bp seed {CORE_SEED}"
+    mean_core = 8
+    bpr = algorithmic_bytes_per_read(L, NAME_BYTES, mean_core)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        ns = min(a.cpu_sample, N)
+        seq, qual, names, name_off = synth_host_sample(ns, L, seed=1)
+        vals = []
+        for s in range(a.warmup + a.steps):
+            rps, kind, secs = run_reference_harness(cores, seq, qual, names, name_off, L)
+            if s >= a.warmup:
+                vals.append((rps, secs))
+            if s == 0 and secs * (a.warmup + a.steps) > 240:  # keep the run within a few minutes
+                vals = [(rps, secs)]
+                break
+        rps = float(np.mean([v[0] for v in vals]))
+        ms = float(np.mean([v[1] for v in vals])) * 1e3
+        sample = f"first {ns} reads of the workload per step, in-memory, 1 thread (the reference is only deterministic at -T 1)"
+        print(json.dumps({
+            "impl": "reference", "metric": "reads/s of core-scan+bucket+reorder", "value": rps, "unit": "reads/s", "n_gpus": a.gpus,
+            "steps": len(vals), "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "bases_per_s": rps * L,
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": rps, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ native arm (B200)
+    import torch
+    from scalce_b200 import synth
+    from scalce_b200.binding import BoostTransform, load_library
+
+    load_library()  # fails loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    d = synth.make_batch_cuda(N, L, seed=1 + rank, device=f"cuda:{local}")
+    seq, qual, names, name_off = d["seq"], d["qual"], d["names"], d["name_off"]
+    # host side of the boundary prepares quality payload (output_quality: q - 33, 0 under N)
+    qual = torch.where(seq == ord("N"), torch.zeros_like(qual), qual - 33)
+    torch.cuda.synchronize()
+
+    def one_step():
+        t = BoostTransform(cores, L, device=local, emit_merged=False)
+        t.submit_device(N, seq.data_ptr(), qual.data_ptr(), names.data_ptr(), name_off.data_ptr())
+        r = t.flush()
+        st = t.stage_ms()
+        launches = t.kernel_launches
+        t.close()
+        return r.device_ms, st, launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib = load_library()
+    launches0 = lib.scb_kernel_launches(None)
+    t0 = time.perf_counter()
+    dev_ms, stages = [], []
+    for _ in range(a.steps):
+        ms, st, _ = one_step()
+        dev_ms.append(ms); stages.append(st)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    launches = lib.scb_kernel_launches(None) - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = float(np.mean(dev_ms))
+    if dist is not None:
+        tt = torch.tensor([ms_step, wall_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, wall_ms = float(tt[0]), float(tt[1])
+    value = N * world / (ms_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        hs = [x.cpu().pin_memory() for x in (seq, qual, names, name_off)]
+        h_seq, h_qual, h_names, h_off = [x.numpy() for x in hs]
+        outbuf = None
+        e_steps = min(a.steps, 2)
+        e_ms = []
+        for s in range(1 + e_steps):
+            barrier()
+            t1 = time.perf_counter()
+            t = BoostTransform(cores, L, device=local, emit_merged=False)
+            t.submit(h_seq.reshape(N, L), h_qual.reshape(N, L), h_names, h_off)
+            r = t.flush()
+            sizes = [r.chunk_off[k][-1] for k in range(6)]
+            if outbuf is None:
+                outbuf = [torch.empty(max(sz, 1), dtype=torch.uint8).pin_memory() for sz in sizes]
+            for k in range(4):
+                for c in range(r.n_chunks):
+                    o0, o1 = r.chunk_off[k][c], r.chunk_off[k][c + 1]
+                    lib.scb_copy_stream(t._h, k, c, C.c_void_p(outbuf[k].data_ptr() + o0), o1 - o0)
+            t.close()
+            torch.cuda.synchronize()
+            if s >= 1:
+                e_ms.append((time.perf_counter() - t1) * 1e3)
+        e_ms_step = float(np.mean(e_ms))
+        if dist is not None:
+            tt = torch.tensor([e_ms_step], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms_step = float(tt[0])
+        h2d = int(sum(x.numel() * x.element_size() for x in hs))
+        d2h = int(sum(sizes[:4]))
+        e2e = {"value": N * world / (e_ms_step * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e_ms_step, "steps": e_steps, "note": "pinned host buffers -> scb_submit (H2D) -> scb_flush -> scb_copy_stream of every stream (D2H)"}
+        del hs, outbuf
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage + whole-path figure --------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    mean_st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    dom = max(mean_st, key=mean_st.get)
+    stage_bytes = {  # algorithmic bytes per read of each stage (DESIGN.md "kernels")
+        "scan": L + 8, "resolve": 16, "chunks": 8, "sort": 24, "ties": 0,
+        "emit": 2 * L + 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + L + 4, "merged": 0, "arrays": 16,
+    }
+    ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "bytes_per_read": stage_bytes[dom], "stage_ms": mean_st}
+    pipe = N * bpr / (ms_step * 1e-3) / 1e9
+    pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
+
+    cpu = None
+    if not a.no_cpu:
+        ns = min(a.cpu_sample, N)
+        s_seq = seq[:ns].cpu().numpy(); s_qual = (qual[:ns] + 33).cpu().numpy()
+        s_names = names[:ns * NAME_BYTES].cpu().numpy(); s_off = name_off[:ns + 1].cpu().numpy()
+        rps, kind, secs = run_reference_harness(cores, s_seq, s_qual, s_names, s_off, L)
+        cpu = {"value": rps, "unit": "reads/s", "cores": 1, "kind": kind,
+               "sample": f"first {ns} reads of rank 0's batch, in-memory, single thread ({secs:.1f} s)", "host_cores_available": os.cpu_count()}
+
+    out = {
+        "metric": "reads/s of core-scan+bucket+reorder", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "bases_per_s": value * L,
+        "config": {"workload": workload, "reads_per_gpu": N, "read_length": L, "l2": "inputs (>= 15 GB per step) far exceed the 126 MB L2",
+                   "timing": "CUDA events on the library stream around scb_flush, fresh handle per step", "multi_gpu": "independent shards, no exchange"},
+        "roofline": roof, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

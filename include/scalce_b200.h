@@ -130,6 +130,11 @@ int64_t scb_unbucketed(const scb_handle *h);
 int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx);
 /* Number of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t scb_kernel_launches(const scb_handle *h);
+/* Device time of each stage of the last flush, CUDA events on the handle's stream, milliseconds:
+ * 0 scan, 1 resolve, 2 size accounting + chunk ids, 3 key build + sort, 4 tie refinement,
+ * 5 emit (per-chunk streams), 6 merged order + emit, 7 per-read arrays. Returns SCB_N_STAGES. */
+#define SCB_N_STAGES 8
+int scb_stage_ms(const scb_handle *h, float *out, int32_t cap);
 /* aho_trie_free (reads.cpp:505-535). */
 void scb_destroy(scb_handle *h);
 

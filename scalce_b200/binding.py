@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_destroy",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library(path: str | None = None):
     L.scb_lifetime_count.argtypes = [C.c_void_p, C.c_int32]
     L.scb_kernel_launches.restype = C.c_int64
     L.scb_kernel_launches.argtypes = [C.c_void_p]
+    L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_destroy.argtypes = [C.c_void_p]
     if path is None:
         _lib = L
@@ -192,6 +193,13 @@ class BoostTransform:
 
     def lifetime_count(self, core_idx):
         return load_library().scb_lifetime_count(self._h, core_idx)
+
+    STAGES = ("scan", "resolve", "chunks", "sort", "ties", "emit", "merged", "arrays")
+
+    def stage_ms(self):
+        buf = (C.c_float * 8)()
+        load_library().scb_stage_ms(self._h, buf, 8)
+        return dict(zip(self.STAGES, [float(x) for x in buf]))
 
     @property
     def kernel_launches(self):

@@ -73,6 +73,8 @@ struct scb_handle {
     CoreTable tab;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t stage_ev[SCB_N_STAGES + 1] = {};
+    float stage_ms[SCB_N_STAGES] = {};
     // device tables
     DevBuf d_next, d_nto, d_rank_level, d_rank_node_id, d_rank_core;
     DevBuf d_life, d_claim;
@@ -124,6 +126,7 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         SCB_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
         SCB_CUDA(cudaEventCreate(&h->ev0));
         SCB_CUDA(cudaEventCreate(&h->ev1));
+        for (auto &e : h->stage_ev) SCB_CUDA(cudaEventCreate(&e));
         cudaMemPool_t pool;
         SCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
         uint64_t thr = ~0ull;
@@ -269,6 +272,7 @@ static void run_flush(scb_handle *h) {
     h->n_last = n;
     const int nb = h->tab.n_buckets;
     SCB_CUDA(cudaEventRecord(h->ev0, st));
+    SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
 
     // 1. scan: level + candidate counts, then candidates
     h->lvl.alloc((size_t)n, st);
@@ -290,6 +294,7 @@ static void run_flush(scb_handle *h) {
         SCB_LAUNCH((scan_k<true>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
                    h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>());
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
     // 2. resolve
     h->asg.alloc((size_t)n * 4, st);
     h->endv.alloc((size_t)n * 2, st);
@@ -310,6 +315,7 @@ static void run_flush(scb_handle *h) {
     }
     SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
     // 3. sizes -> flush chunks
     {
         int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
@@ -338,6 +344,7 @@ static void run_flush(scb_handle *h) {
     }
     if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[3], st));
     // 4. sort by (chunk, bucket order, key prefix), stable in input order
     const int nch = h->n_chunks > 0 ? h->n_chunks : 1;
     const int seg_bits = ceil_log2((uint64_t)nch * (uint64_t)(nb + 1));
@@ -360,6 +367,7 @@ static void run_flush(scb_handle *h) {
         }
     }
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[4], st));
     // 5. refine ties with further key bases until unique or the key is exhausted
     {
         const uint64_t *cur_keys = ka;
@@ -400,8 +408,10 @@ static void run_flush(scb_handle *h) {
         }
     }
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[5], st));
     // 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
     emit_order(h, h->perm.as<uint32_t>(), false, h->chunked);
+    SCB_CUDA(cudaEventRecord(h->stage_ev[6], st));
     if (cfg.emit_merged && h->n_chunks > 1) {
         // merge() concatenates a bucket's pieces in chunk order (compress.cpp:104-112): a stable sort of the
         // chunk-major order by bucket order gives exactly that
@@ -416,6 +426,7 @@ static void run_flush(scb_handle *h) {
         emit_order(h, h->perm_m.as<uint32_t>(), true, h->merged);
     }
 
+    SCB_CUDA(cudaEventRecord(h->stage_ev[7], st));
     // 7. per-read arrays in input order
     h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
     if (n > 0) {
@@ -425,8 +436,10 @@ static void run_flush(scb_handle *h) {
         if (h->n_chunks > 1) SCB_CUDA(cudaMemcpyAsync(h->dbg_chunk.p, h->chunk.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         else SCB_CUDA(cudaMemsetAsync(h->dbg_chunk.p, 0, (size_t)n * 4, st));
     }
+    SCB_CUDA(cudaEventRecord(h->stage_ev[8], st));
     SCB_CUDA(cudaEventRecord(h->ev1, st));
     SCB_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < SCB_N_STAGES; k++) SCB_CUDA(cudaEventElapsedTime(&h->stage_ms[k], h->stage_ev[k], h->stage_ev[k + 1]));
 }
 
 }  // namespace scb
@@ -624,12 +637,19 @@ int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx) {
 
 int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches; }
 
+int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
+    if (!h || !out) return SCB_EINVAL;
+    for (int k = 0; k < SCB_N_STAGES && k < cap; k++) out[k] = h->stage_ms[k];
+    return SCB_N_STAGES;
+}
+
 void scb_destroy(scb_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
     cudaStream_t st = h->st;
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+    for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
     delete h;  // DevBufs free stream-ordered
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (e0) cudaEventDestroy(e0);
