@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_stage_ms", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_destroy",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library(path: str | None = None):
     L.scb_kernel_launches.restype = C.c_int64
     L.scb_kernel_launches.argtypes = [C.c_void_p]
     L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
+    L.scb_resolve_rounds.argtypes = [C.c_void_p]
     L.scb_destroy.argtypes = [C.c_void_p]
     if path is None:
         _lib = L
@@ -200,6 +201,10 @@ class BoostTransform:
         buf = (C.c_float * 8)()
         load_library().scb_stage_ms(self._h, buf, 8)
         return dict(zip(self.STAGES, [float(x) for x in buf]))
+
+    @property
+    def resolve_rounds(self):
+        return load_library().scb_resolve_rounds(self._h)
 
     @property
     def kernel_launches(self):

@@ -2,6 +2,7 @@
 #include "../../include/scalce_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -10,6 +11,7 @@
 #include "core_table.h"
 #include "pipeline.cuh"
 #include "prims.cuh"
+#include "resolve_dense.cuh"
 
 namespace scb {
 long long g_launches = 0;
@@ -88,6 +90,8 @@ struct scb_handle {
     int64_t n_last = 0;
     int64_t unbucketed = 0;
     bool smem_resident = false;
+    uint64_t life_total = 0;   // reads ever submitted (bound on any lifetime count)
+    int last_rounds = 0;       // fixed-point rounds of the last dense resolve
 };
 
 namespace scb {
@@ -300,7 +304,59 @@ static void run_flush(scb_handle *h) {
     h->endv.alloc((size_t)n * 2, st);
     unsigned long long root_before = 0, root_after = 0;
     SCB_CUDA(cudaMemcpyAsync(&root_before, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    bool dense_done = false;
     {
+        // dense engine: one u32 population counter per bucket per warp in shared memory
+        const int nb1 = nb + 1;
+        int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 4));
+        const char *force = getenv("SCB_RESOLVE");
+        bool want_dense = W >= 1 && n > 0 && (h->life_total + (uint64_t)n) < 0xffffffffull && !(force && !strcmp(force, "seq"));
+        if (want_dense) {
+            int dev_sms = 0;
+            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+            size_t smem = (size_t)W * nb1 * 4;
+            SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0;
+            SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
+            if (occ >= 1) {
+                const int grid = dev_sms;
+                std::vector<int64_t> blk;
+                blk.push_back(0);
+                const int64_t first = 4096;
+                while (blk.back() < n) { int64_t n0 = blk.back(); blk.push_back(std::min<int64_t>(n, std::max<int64_t>(2 * n0, n0 + first))); }
+                const int nblk = (int)blk.size() - 1;
+                const size_t max_sub = (size_t)grid * W;
+                DevBuf sel((size_t)n * 2, st), base((size_t)nb1 * 4, st), H(max_sub * nb1 * 4, st), S(max_sub * nb1 * 4, st),
+                    Csum((size_t)grid * nb1 * 4, st), Cpre((size_t)grid * nb1 * 4, st), changed((size_t)kRdMaxRounds * 4, st),
+                    dblk(blk.size() * 8, st), dstat(8, st);
+                SCB_CUDA(cudaMemsetAsync(sel.p, 0xff, (size_t)n * 2, st));
+                SCB_CUDA(cudaMemsetAsync(changed.p, 0, (size_t)kRdMaxRounds * 4, st));
+                SCB_CUDA(cudaMemsetAsync(dstat.p, 0, 8, st));
+                SCB_CUDA(cudaMemcpyAsync(dblk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
+                SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), base.as<uint32_t>(), nb1);
+                RdParams rp;
+                rp.n = n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
+                rp.sel = sel.as<uint16_t>(); rp.base = base.as<uint32_t>(); rp.H = H.as<uint32_t>(); rp.S = S.as<uint32_t>();
+                rp.Csum = Csum.as<uint32_t>(); rp.Cpre = Cpre.as<uint32_t>(); rp.changed = changed.as<uint32_t>(); rp.blk = dblk.as<int64_t>();
+                rp.nblk = nblk; rp.nb1 = nb1; rp.W = W; rp.status = dstat.as<int>(); rp.rounds_out = dstat.as<int>() + 1;
+                void *args[] = {&rp};
+                SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
+                g_launches++;
+                int stat[2] = {0, 0};
+                SCB_CUDA(cudaMemcpyAsync(stat, dstat.p, 8, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                h->last_rounds = stat[1];
+                if (stat[0] == 0) {
+                    SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
+                    SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
+                               h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), sel.as<uint16_t>(), nb, h->asg.as<uint32_t>(),
+                               h->endv.as<uint16_t>(), h->d_life.as<unsigned long long>() + nb);
+                    dense_done = true;
+                }
+            }
+        }
+    }
+    if (!dense_done) {
         size_t smem = ((size_t)nb + 1) * 12;
         if (smem <= 200 * 1024) {
             SCB_CUDA(cudaFuncSetAttribute(resolve_seq_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -313,6 +369,7 @@ static void run_flush(scb_handle *h) {
                        h->d_claim.as<uint32_t>(), h->asg.as<uint32_t>(), h->endv.as<uint16_t>(), nb);
         }
     }
+    h->life_total += (uint64_t)n;
     SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
 
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
@@ -636,6 +693,8 @@ int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx) {
 }
 
 int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches; }
+
+int scb_resolve_rounds(const scb_handle *h) { return h ? h->last_rounds : -1; }
 
 int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
     if (!h || !out) return SCB_EINVAL;

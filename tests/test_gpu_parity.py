@@ -118,3 +118,15 @@ def test_million_reads_bucket_ids():
     o = util.run_oracle(cores, b, q1, q2)
     t, r = util.run_cuda(cores, b, q1, q2)
     util.assert_same(o, t, r)
+
+
+def test_sequential_resolve_engine(monkeypatch):
+    # the fallback engine for bucket counts too large for shared memory, forced on a small case
+    monkeypatch.setenv("SCB_RESOLVE", "seq")
+    o, t, r = _case(20000, 100, seed=41)
+    assert t.resolve_rounds == 0
+
+
+def test_dense_resolve_used_by_default():
+    o, t, r = _case(50000, 100, seed=42)
+    assert t.resolve_rounds > 0
