@@ -12,6 +12,7 @@
 #include "pipeline.cuh"
 #include "prims.cuh"
 #include "resolve_dense.cuh"
+#include "scan_smem.cuh"
 
 namespace scb {
 long long g_launches = 0;
@@ -80,6 +81,9 @@ struct scb_handle {
     // device tables
     DevBuf d_next, d_nto, d_rank_level, d_rank_node_id, d_rank_core;
     DevBuf d_life, d_claim;
+    DevBuf d_trans16, d_hit_rank;   // shared-memory form of the automaton (scan_smem.cuh)
+    int H0 = 0, n_hit = 0;
+    size_t smem_table_bytes = 0;
     std::vector<Pending> pending;
     // last flush
     Pending cur;
@@ -140,6 +144,28 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         upload(h->d_rank_level, h->tab.rank_level, h->st);
         upload(h->d_rank_node_id, h->tab.rank_node_id, h->st);
         upload(h->d_rank_core, h->tab.rank_core, h->st);
+        {   // shared-memory form: states renumbered so that states where some core ends come last
+            const CoreTable &t = h->tab;
+            const int ns = t.n_states;
+            size_t nhit = 0;
+            for (int u = 0; u < ns; u++) nhit += t.nto_rank[u] >= 0;
+            size_t bytes = (size_t)ns * 8 + nhit * 4 + (size_t)t.n_buckets;
+            if (ns <= 65535 && bytes <= 160 * 1024) {
+                std::vector<uint32_t> newid(ns);
+                uint32_t a = 0, b = (uint32_t)(ns - nhit);
+                for (int u = 0; u < ns; u++) newid[u] = t.nto_rank[u] >= 0 ? b++ : a++;
+                std::vector<uint16_t> tr((size_t)ns * 4);
+                std::vector<uint32_t> hr(nhit);
+                for (int u = 0; u < ns; u++) {
+                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + c] = (uint16_t)newid[t.next[(size_t)u * 4 + c]];
+                    if (t.nto_rank[u] >= 0) hr[newid[u] - (ns - nhit)] = (uint32_t)t.nto_rank[u];
+                }
+                upload(h->d_trans16, tr, h->st);
+                upload(h->d_hit_rank, hr, h->st);
+                h->H0 = (int)(ns - nhit); h->n_hit = (int)nhit; h->smem_table_bytes = bytes;
+                h->smem_resident = true;
+            }
+        }
         size_t nb1 = (size_t)h->tab.n_buckets + 1;
         h->d_life.alloc(nb1 * 8, h->st);
         h->d_claim.alloc(nb1 * 4, h->st);
@@ -278,25 +304,60 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->ev0, st));
     SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
 
-    // 1. scan: level + candidate counts, then candidates
+    // 1. scan: max level + ordered distinct candidates per read
     h->lvl.alloc((size_t)n, st);
     h->ncand.alloc((size_t)n * 2, st);
     h->cand_off.alloc((size_t)(n + 1) * 8, st);
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     DfaDev dfa = dfa_of(h);
-    if (n > 0)
-        SCB_LAUNCH((scan_k<false>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
-                   h->ncand.as<uint16_t>(), (const uint64_t *)nullptr, (uint32_t *)nullptr, (uint16_t *)nullptr);
-    exclusive_scan<uint64_t>(LoadAs<uint16_t, uint64_t>{h->ncand.as<uint16_t>()}, n, h->cand_off.as<uint64_t>(),
-                             h->cand_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
     uint64_t M = 0;
-    SCB_CUDA(cudaMemcpyAsync(&M, h->cand_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaStreamSynchronize(st));
-    h->cand_rank.alloc((size_t)M * 4, st);
-    h->cand_pos.alloc((size_t)M * 2, st);
-    if (n > 0)
-        SCB_LAUNCH((scan_k<true>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
-                   h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>());
+    bool scanned = false;
+    {
+        const char *force = getenv("SCB_SCAN");
+        const size_t toff = (h->smem_table_bytes + 15) & ~(size_t)15;
+        const size_t budget = 225 * 1024;
+        int R = 0;
+        if (h->smem_resident && toff + 512 < budget) R = (int)std::min<size_t>(1024, ((budget - toff - 256) / 2 / (size_t)L1) / 32 * 32);
+        if (R >= 64 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
+            const size_t tile_bytes = (((size_t)R * L1) + 15) & ~(size_t)15;
+            const size_t smem = toff + 2 * tile_bytes + 256;
+            SCB_CUDA(cudaFuncSetAttribute(scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int dev_sms = 0;
+            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+            DevBuf dtot(8, st);
+            uint64_t cap = std::max<uint64_t>((uint64_t)n * 8, 1u << 20);
+            for (int attempt = 0; attempt < 2 && !scanned; attempt++) {
+                h->cand_rank.alloc((size_t)cap * 4, st);
+                h->cand_pos.alloc((size_t)cap * 2, st);
+                SCB_CUDA(cudaMemsetAsync(dtot.p, 0, 8, st));
+                ScanSmemParams sp;
+                sp.seq = c.seq1; sp.n = n; sp.L = L1; sp.trans = h->d_trans16.as<uint16_t>(); sp.hit_rank = h->d_hit_rank.as<uint32_t>();
+                sp.rank_level = h->d_rank_level.as<uint8_t>(); sp.ns = h->tab.n_states; sp.n_hit = h->n_hit; sp.nb = nb; sp.H0 = h->H0; sp.R = R;
+                sp.lvl = h->lvl.as<uint8_t>(); sp.ncand = h->ncand.as<uint16_t>(); sp.cand_off = h->cand_off.as<uint64_t>();
+                sp.cand_rank = h->cand_rank.as<uint32_t>(); sp.cand_pos = h->cand_pos.as<uint16_t>();
+                sp.cand_total = dtot.as<unsigned long long>(); sp.cand_cap = cap; sp.n_tiles = cdiv(n, R);
+                int grid = (int)std::min<int64_t>(dev_sms, sp.n_tiles);
+                SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
+                SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                if (M <= cap) scanned = true; else cap = M;   // list space was short: rerun with the exact size
+            }
+        }
+    }
+    if (!scanned) {
+        if (n > 0)
+            SCB_LAUNCH((scan_k<false>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
+                       h->ncand.as<uint16_t>(), (const uint64_t *)nullptr, (uint32_t *)nullptr, (uint16_t *)nullptr);
+        exclusive_scan<uint64_t>(LoadAs<uint16_t, uint64_t>{h->ncand.as<uint16_t>()}, n, h->cand_off.as<uint64_t>(),
+                                 h->cand_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        SCB_CUDA(cudaMemcpyAsync(&M, h->cand_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        h->cand_rank.alloc((size_t)M * 4, st);
+        h->cand_pos.alloc((size_t)M * 2, st);
+        if (n > 0)
+            SCB_LAUNCH((scan_k<true>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
+                       h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>());
+    }
 
     SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
     // 2. resolve

@@ -1,0 +1,160 @@
+// scan_smem.cuh - core scan with the automaton resident in shared memory.
+//
+// Persistent kernel, one CTA per SM, one thread per read of a tile. The tile's ASCII rows are
+// staged into shared memory with 16-byte cp.async (coalesced, double buffered: the next tile
+// streams in while the current one is walked); the DFA is a u16 transition table
+// trans[state][4] whose states are renumbered so that "some core ends here" is a single compare
+// (state >= H0); only then are the rank / level tables consulted.
+// Per read it emits, in ONE pass: the maximum core level, the ordered list of distinct
+// candidates of that level (bucket rank, position) and their count - everything aho_search
+// (reads.cpp:413-429) needs except the running populations. Candidate space is handed out per
+// tile with one atomicAdd; cand_off[i] records where read i's list starts.
+#pragma once
+#include "common.cuh"
+#include "pipeline.cuh"
+
+namespace scb {
+
+struct ScanSmemParams {
+    const uint8_t *seq; int64_t n; int L;
+    const uint16_t *trans; const uint32_t *hit_rank; const uint8_t *rank_level;
+    int ns, n_hit, nb, H0, R;
+    uint8_t *lvl; uint16_t *ncand; uint64_t *cand_off; uint32_t *cand_rank; uint16_t *cand_pos;
+    unsigned long long *cand_total; uint64_t cand_cap;
+    int64_t n_tiles;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct SmemDfa {
+    const uint16_t *trans; const uint32_t *hit_rank; const uint8_t *rank_level; int H0;
+};
+
+__device__ __forceinline__ bool seen_before_smem(const uint8_t *s, int p, uint32_t r, const SmemDfa &d) {
+    uint32_t st = 0;
+    for (int q = 0; q < p; q++) {
+        st = d.trans[(st << 2) | base_code(s[q])];
+        if (st >= (uint32_t)d.H0 && d.hit_rank[st - d.H0] == r) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void stage_tile(const ScanSmemParams &p, int64_t tile, uint8_t *buf) {
+    const int64_t row0 = tile * p.R;
+    int64_t rows = p.n - row0;
+    if (rows > p.R) rows = p.R;
+    if (rows <= 0) return;
+    const int64_t bytes = rows * p.L;
+    const uint8_t *src = p.seq + row0 * p.L;
+    const int64_t n16 = bytes >> 4;
+    for (int64_t k = threadIdx.x; k < n16; k += blockDim.x) cp_async16(buf + (k << 4), src + (k << 4));
+    for (int64_t k = (n16 << 4) + threadIdx.x; k < bytes; k += blockDim.x) buf[k] = src[k];
+}
+
+__global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    // layout: trans | hit_rank | rank_level | pad16 | tile0 | tile1 | scan scratch
+    uint16_t *s_trans = (uint16_t *)sm;
+    uint32_t *s_hit = (uint32_t *)(sm + (size_t)p.ns * 8);
+    uint8_t *s_lvl = (uint8_t *)(s_hit + p.n_hit);
+    size_t off = ((size_t)p.ns * 8 + (size_t)p.n_hit * 4 + (size_t)p.nb + 15) & ~(size_t)15;
+    const size_t tile_bytes = (((size_t)p.R * p.L) + 15) & ~(size_t)15;
+    uint8_t *tile_buf[2] = {sm + off, sm + off + tile_bytes};
+    uint32_t *s_scan = (uint32_t *)(sm + off + 2 * tile_bytes);   // [33]
+    __shared__ unsigned long long s_base;
+
+    for (int k = threadIdx.x; k < p.ns * 2; k += blockDim.x) ((uint32_t *)s_trans)[k] = ((const uint32_t *)p.trans)[k];
+    for (int k = threadIdx.x; k < p.n_hit; k += blockDim.x) s_hit[k] = p.hit_rank[k];
+    for (int k = threadIdx.x; k < p.nb; k += blockDim.x) s_lvl[k] = p.rank_level[k];
+    SmemDfa d{s_trans, s_hit, s_lvl, p.H0};
+
+    int cur = 0;
+    int64_t tile = blockIdx.x;
+    if (tile < p.n_tiles) stage_tile(p, tile, tile_buf[0]);
+    cp_async_commit();
+    for (; tile < p.n_tiles; tile += gridDim.x, cur ^= 1) {
+        const int64_t nxt = tile + gridDim.x;
+        if (nxt < p.n_tiles) stage_tile(p, nxt, tile_buf[cur ^ 1]);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const int64_t i = tile * p.R + threadIdx.x;
+        const bool live = i < p.n;
+        uint32_t list_r[kScanListCap];
+        uint16_t list_p[kScanListCap];
+        int best = 0, cnt = 0;
+        if (live) {
+            const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
+            uint32_t st = 0;
+            for (int q = 0; q < p.L; q++) {
+                st = s_trans[(st << 2) | base_code(s[q])];
+                if (st >= (uint32_t)p.H0) {
+                    uint32_t r = s_hit[st - p.H0];
+                    int lv = s_lvl[r];
+                    if (lv > best) { best = lv; cnt = 0; }
+                    if (lv == best) {
+                        bool dup = false;
+                        int lim = cnt < kScanListCap ? cnt : kScanListCap;
+                        for (int k = 0; k < lim; k++) dup |= (list_r[k] == r);
+                        if (!dup && cnt >= kScanListCap) dup = seen_before_smem(s, q, r, d);
+                        if (!dup) {
+                            if (cnt < kScanListCap) { list_r[cnt] = r; list_p[cnt] = (uint16_t)q; }
+                            cnt++;
+                        }
+                    }
+                }
+            }
+        }
+        // candidate space for the tile: block scan of counts + one atomicAdd
+        uint32_t v = live ? (uint32_t)cnt : 0u;
+        uint32_t inc = warp_incl_scan(v);
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane_id() == 31) s_scan[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t x = (int)lane_id() < nw ? s_scan[lane_id()] : 0u;
+            uint32_t xi = warp_incl_scan(x);
+            s_scan[lane_id()] = xi - x;
+            if (lane_id() == 31) {
+                s_scan[32] = xi;
+                s_base = xi ? atomicAdd(p.cand_total, (unsigned long long)xi) : 0ull;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const uint64_t o = s_base + s_scan[w] + (inc - v);
+            p.lvl[i] = (uint8_t)best;
+            p.ncand[i] = (uint16_t)cnt;
+            p.cand_off[i] = o;
+            if (o + (uint64_t)cnt <= p.cand_cap) {
+                int lim = cnt < kScanListCap ? cnt : kScanListCap;
+                for (int k = 0; k < lim; k++) { p.cand_rank[o + k] = list_r[k]; p.cand_pos[o + k] = list_p[k]; }
+                if (cnt > kScanListCap) {   // rare: regenerate the tail of the list by a second walk
+                    const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
+                    uint32_t st = 0; int c2 = 0;
+                    for (int q = 0; q < p.L; q++) {
+                        st = s_trans[(st << 2) | base_code(s[q])];
+                        if (st >= (uint32_t)p.H0) {
+                            uint32_t r = s_hit[st - p.H0];
+                            if ((int)s_lvl[r] == best && !seen_before_smem(s, q, r, d)) {
+                                if (c2 >= kScanListCap) { p.cand_rank[o + c2] = r; p.cand_pos[o + c2] = (uint16_t)q; }
+                                c2++;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // tile_buf[cur] and s_scan are reused next iteration
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace scb

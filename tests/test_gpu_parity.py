@@ -130,3 +130,9 @@ def test_sequential_resolve_engine(monkeypatch):
 def test_dense_resolve_used_by_default():
     o, t, r = _case(50000, 100, seed=42)
     assert t.resolve_rounds > 0
+
+
+def test_global_table_scan_engine(monkeypatch):
+    # the scan path for automata too large for shared memory, forced on a small case
+    monkeypatch.setenv("SCB_SCAN", "global")
+    _case(20000, 100, seed=43)
