@@ -233,6 +233,7 @@ def main():
         r = t.flush()
         st = t.stage_ms()
         launches = t.kernel_launches
+        st["_rounds"] = t.resolve_rounds
         t.close()
         return r.device_ms, st, launches
 
@@ -308,6 +309,7 @@ def main():
     # ---- roofline of the dominant stage + whole-path figure --------------------------------------
     peak, peak_src = measured_peak_gbs()
     mean_st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    resolve_rounds = mean_st.pop("_rounds", None)
     dom = max(mean_st, key=mean_st.get)
     stage_bytes = {  # algorithmic bytes per read of each stage (DESIGN.md "kernels")
         "scan": L + 8, "resolve": 16, "chunks": 8, "sort": 24, "ties": 0,
@@ -315,7 +317,7 @@ def main():
     }
     ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "peak_source": peak_src, "bytes_per_read": stage_bytes[dom], "stage_ms": mean_st}
+            "peak_source": peak_src, "bytes_per_read": stage_bytes[dom], "stage_ms": mean_st, "resolve_rounds": resolve_rounds}
     pipe = N * bpr / (ms_step * 1e-3) / 1e9
     pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
 

@@ -369,18 +369,18 @@ static void run_flush(scb_handle *h) {
     {
         // dense engine: one u32 population counter per bucket per warp in shared memory
         const int nb1 = nb + 1;
-        int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 4));
+        int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 8));
         const char *force = getenv("SCB_RESOLVE");
         bool want_dense = W >= 1 && n > 0 && (h->life_total + (uint64_t)n) < 0xffffffffull && !(force && !strcmp(force, "seq"));
         if (want_dense) {
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
-            size_t smem = (size_t)W * nb1 * 4;
+            size_t smem = (size_t)W * nb1 * 8;
             SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 0;
             SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
             if (occ >= 1) {
-                const int grid = dev_sms;
+                const int grid = std::min(dev_sms, 160);
                 std::vector<int64_t> blk;
                 blk.push_back(0);
                 const int64_t first = 4096;
@@ -400,6 +400,10 @@ static void run_flush(scb_handle *h) {
                 rp.sel = sel.as<uint16_t>(); rp.base = base.as<uint32_t>(); rp.H = H.as<uint32_t>(); rp.S = S.as<uint32_t>();
                 rp.Csum = Csum.as<uint32_t>(); rp.Cpre = Cpre.as<uint32_t>(); rp.changed = changed.as<uint32_t>(); rp.blk = dblk.as<int64_t>();
                 rp.nblk = nblk; rp.nb1 = nb1; rp.W = W; rp.status = dstat.as<int>(); rp.rounds_out = dstat.as<int>() + 1;
+                DevBuf dts;
+                const bool prof = getenv("SCB_RESOLVE_PROF") != nullptr;
+                if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
+                rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
                 void *args[] = {&rp};
                 SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
                 g_launches++;
@@ -407,6 +411,18 @@ static void run_flush(scb_handle *h) {
                 SCB_CUDA(cudaMemcpyAsync(stat, dstat.p, 8, cudaMemcpyDeviceToHost, st));
                 SCB_CUDA(cudaStreamSynchronize(st));
                 h->last_rounds = stat[1];
+                if (prof) {
+                    std::vector<unsigned long long> ts(4096 * 8);
+                    SCB_CUDA(cudaMemcpy(ts.data(), dts.p, ts.size() * 8, cudaMemcpyDeviceToHost));
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    for (int r = 0; r < stat[1] && r < 4096; r++) {
+                        for (int k = 0; k < 6; k++) acc[k] += (double)(ts[r * 8 + k + 1] - ts[r * 8 + k]) * 1e-3;
+                        fprintf(stderr, "round %3d len %9llu: P %.1f D %.1f E %.1f sync1 %.1f scan %.1f sync2 %.1f us\n", r, ts[r * 8 + 7],
+                                (ts[r * 8 + 1] - ts[r * 8]) * 1e-3, (ts[r * 8 + 2] - ts[r * 8 + 1]) * 1e-3, (ts[r * 8 + 3] - ts[r * 8 + 2]) * 1e-3,
+                                (ts[r * 8 + 4] - ts[r * 8 + 3]) * 1e-3, (ts[r * 8 + 5] - ts[r * 8 + 4]) * 1e-3, (ts[r * 8 + 6] - ts[r * 8 + 5]) * 1e-3);
+                    }
+                    fprintf(stderr, "resolve totals (us): P %.0f D %.0f E %.0f sync1 %.0f scan %.0f sync2 %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
+                }
                 if (stat[0] == 0) {
                     SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
                     SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),

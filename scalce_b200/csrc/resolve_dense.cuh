@@ -12,11 +12,13 @@
 //   D  each warp sweeps one subtile in input order, 32 reads per step, with the bucket populations
 //      of "everything before" in shared memory (cnt[nb+1], u32)
 //   --grid sync--  column scan of the chunk totals  --grid sync--  converged?
-// Dense = one u32 counter per bucket per warp in shared memory, so it needs 4*(nb+1)*W <= ~200 KB.
+// Dense = two u32 words per bucket per warp in shared memory (population + lane tags), so it needs
+// 8*(nb+1)*W <= ~200 KB.
 #pragma once
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "prims.cuh"
 
 namespace scb {
 namespace cg = cooperative_groups;
@@ -38,6 +40,7 @@ struct RdParams {
     int nblk, nb1, W;
     int *status;                  // 0 ok, 1 round cap hit
     int *rounds_out;
+    unsigned long long *tstamps;  // optional [rounds][8] globaltimer stamps of CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t lanemask_ge() {
@@ -46,22 +49,26 @@ __device__ __forceinline__ uint32_t lanemask_ge() {
     return m;
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RD_STAMP(k) do { if (p.tstamps && blockIdx.x == 0 && threadIdx.x == 0 && round < 4096) p.tstamps[round * 8 + (k)] = gtimer(); } while (0)
+
 struct RdLane {   // one read's state held by one lane
     int nc; uint64_t off; uint32_t so; uint32_t r[kRdRegCands];
 };
 
-__device__ __forceinline__ void rd_load(const RdParams &p, int64_t i, int64_t hi, RdLane &x) {
+// meta (count, list offset, old slot) is fetched two steps ahead, the candidates one step ahead, so
+// neither dependent global load stalls the step being decided
+__device__ __forceinline__ void rd_load_meta(const RdParams &p, int64_t i, int64_t hi, RdLane &x) {
     x.nc = 0; x.off = 0; x.so = kNoSel;
+    if (i < hi) { x.nc = p.ncand[i]; x.off = p.cand_off[i]; x.so = p.sel[i]; }
+}
+__device__ __forceinline__ void rd_load_cands(const RdParams &p, RdLane &x) {
 #pragma unroll
-    for (int k = 0; k < kRdRegCands; k++) x.r[k] = 0;
-    if (i < hi) {
-        x.nc = p.ncand[i];
-        x.off = p.cand_off[i];
-        x.so = p.sel[i];
-#pragma unroll
-        for (int k = 0; k < kRdRegCands; k++)
-            if (k < x.nc) x.r[k] = p.cand_rank[x.off + k];
-    }
+    for (int k = 0; k < kRdRegCands; k++) x.r[k] = (k < x.nc) ? p.cand_rank[x.off + k] : 0u;
 }
 __device__ __forceinline__ uint32_t rd_rank(const RdParams &p, const RdLane &x, int k) {
     uint32_t v = 0;
@@ -71,70 +78,88 @@ __device__ __forceinline__ uint32_t rd_rank(const RdParams &p, const RdLane &x, 
     return v;
 }
 
-// sweep reads [lo, hi) in order with populations cnt[] (shared memory, one array per warp)
-__device__ __forceinline__ uint32_t rd_sweep(const RdParams &p, int64_t lo, int64_t hi, uint32_t *cnt) {
+// proportional extrapolation of a bucket population `off` reads into a block that starts at n0
+__device__ __forceinline__ uint32_t rd_guess(uint32_t b0, int64_t off, int64_t n0) {
+    return n0 > 0 ? (uint32_t)(((unsigned long long)b0 * (unsigned long long)off) / (unsigned long long)n0) : 0u;
+}
+
+// one step: decide the 32 reads held in `cur` (one per lane) exactly as if they were processed in
+// lane order, while the candidate lists of the next step and the meta of the one after stream in
+__device__ __forceinline__ void rd_step(const RdParams &p, int64_t g, int64_t hi, RdLane &cur, RdLane &nxt, RdLane &nn,
+                                        uint32_t *cnt, uint32_t *tag, uint32_t &changed) {
+    const uint32_t l = lane_id();
+    const uint32_t lt = lanemask_lt();
+    const uint32_t bit = 1u << l;
+    rd_load_cands(p, nxt);                       // candidates of step g+1 (its meta arrived a step ago)
+    rd_load_meta(p, g + 64 + l, hi, nn);         // meta of step g+2
+    const int nc = cur.nc;
+    int my_k = (nc > 0 && cur.so != kNoSel) ? (int)cur.so : -1;
+    uint32_t a_cur = my_k >= 0 ? rd_rank(p, cur, my_k) : 0u;
+    if (my_k >= 0) atomicOr(&tag[a_cur], bit);
+    __syncwarp();
+    // iterate inside the step until no lane changes: lane j is final after at most j+1 passes, in
+    // practice after one or two
+    while (true) {
+        uint32_t best_c = 0; int best_k = 0;
+#pragma unroll
+        for (int k = 0; k < kRdRegCands; k++)
+            if (k < nc) {
+                uint32_t c = cnt[cur.r[k]] + __popc(tag[cur.r[k]] & lt);
+                if (k == 0 || c > best_c) { best_c = c; best_k = k; }   // first arg-max, strict > (reads.cpp:420-421)
+            }
+        for (int k = kRdRegCands; k < nc; k++) {
+            uint32_t rk = p.cand_rank[cur.off + k];
+            uint32_t c = cnt[rk] + __popc(tag[rk] & lt);
+            if (c > best_c) { best_c = c; best_k = k; }
+        }
+        const bool chg = nc > 0 && best_k != my_k;
+        __syncwarp();
+        if (chg) {
+            if (my_k >= 0) atomicAnd(&tag[a_cur], ~bit);
+            my_k = best_k;
+            a_cur = rd_rank(p, cur, best_k);
+            atomicOr(&tag[a_cur], bit);
+        }
+        if (!__any_sync(0xffffffffu, chg)) break;
+    }
+    if (nc > 0) {
+        atomicAdd(&cnt[a_cur], 1u);              // reads.cpp:246
+        tag[a_cur] = 0;
+        if ((uint32_t)my_k != cur.so) { p.sel[g + l] = (uint16_t)my_k; changed++; }
+    }
+    __syncwarp();
+}
+
+// sweep reads [lo, hi) in order with populations cnt[] and lane tags tag[] (shared memory, one pair
+// of arrays per warp): cnt[b] = population of b before the current step; tag[b] = bit set of the
+// lanes of the current step assigned to b, so read i sees cnt[b] + popc(tag[b] & lanes_below(i)).
+__device__ __forceinline__ uint32_t rd_sweep(const RdParams &p, int64_t lo, int64_t hi, uint32_t *cnt, uint32_t *tag) {
     const uint32_t l = lane_id();
     uint32_t changed = 0;
-    RdLane cur, nxt;
-    rd_load(p, lo + l, hi, cur);
-    for (int64_t g = lo; g < hi; g += 32) {
-        rd_load(p, g + 32 + l, hi, nxt);   // prefetch the next step while this one is decided
-        const int64_t i = g + l;
-        const int nc = cur.nc;
-        const bool has_old = nc > 0 && cur.so != kNoSel;
-        const uint32_t a_old = has_old ? rd_rank(p, cur, (int)cur.so) : 0xffffffffu;
-        // pass 1: first arg-max on the populations before this step
-        uint32_t best_c = 0, sum1 = 0; int best_k = 0;
-#pragma unroll
-        for (int k = 0; k < kRdRegCands; k++)
-            if (k < nc) { uint32_t c = cnt[cur.r[k]]; sum1 += c; if (k == 0 || c > best_c) { best_c = c; best_k = k; } }
-        for (int k = kRdRegCands; k < nc; k++) { uint32_t c = cnt[p.cand_rank[cur.off + k]]; sum1 += c; if (c > best_c) { best_c = c; best_k = k; } }
-        __syncwarp();
-        if (has_old) atomicAdd(&cnt[a_old], 1u);      // old assignments of this step become visible
-        __syncwarp();
-        uint32_t sum2 = 0;
-#pragma unroll
-        for (int k = 0; k < kRdRegCands; k++)
-            if (k < nc) sum2 += cnt[cur.r[k]];
-        for (int k = kRdRegCands; k < nc; k++) sum2 += cnt[p.cand_rank[cur.off + k]];
-        // somebody else in this step sits in one of my candidate buckets -> count only the earlier lanes
-        bool flagged = nc > 0 && (sum2 - sum1) != (has_old ? 1u : 0u);
-        uint32_t m = __ballot_sync(0xffffffffu, flagged);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int nk = __shfl_sync(0xffffffffu, nc, src);
-            uint32_t bc = 0; int bk = 0;
-            for (int k = 0; k < nk; k++) {
-                uint32_t mine = (l == (uint32_t)src) ? rd_rank(p, cur, k) : 0u;
-                uint32_t rk = __shfl_sync(0xffffffffu, mine, src);
-                uint32_t bal = __ballot_sync(0xffffffffu, has_old && a_old == rk);
-                if (l == (uint32_t)src) {
-                    uint32_t c = cnt[rk] - __popc(bal & lanemask_ge());
-                    if (k == 0 || c > bc) { bc = c; bk = k; }
-                }
-            }
-            if (l == (uint32_t)src) best_k = bk;
-        }
-        __syncwarp();
-        if (nc > 0) {
-            uint32_t a_new = rd_rank(p, cur, best_k);
-            if (!has_old) { atomicAdd(&cnt[a_new], 1u); p.sel[i] = (uint16_t)best_k; changed++; }
-            else if ((uint32_t)best_k != cur.so) { atomicSub(&cnt[a_old], 1u); atomicAdd(&cnt[a_new], 1u); p.sel[i] = (uint16_t)best_k; changed++; }
-        }
-        __syncwarp();
-        cur = nxt;
+    RdLane x0, x1, x2;
+    rd_load_meta(p, lo + l, hi, x0);
+    rd_load_cands(p, x0);
+    rd_load_meta(p, lo + 32 + l, hi, x1);
+    // three register sets rotate roles (deciding / candidates in flight / meta in flight) so that no
+    // register is copied while its load is outstanding
+    for (int64_t g = lo; g < hi; g += 96) {
+        rd_step(p, g, hi, x0, x1, x2, cnt, tag, changed);
+        if (g + 32 < hi) rd_step(p, g + 32, hi, x1, x2, x0, cnt, tag, changed);
+        if (g + 64 < hi) rd_step(p, g + 64, hi, x2, x0, x1, cnt, tag, changed);
     }
     return changed;
 }
 
 __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams p) {
-    extern __shared__ uint32_t sm_cnt[];   // [W][nb1]
+    extern __shared__ uint32_t sm_cnt[];   // [W][nb1] populations, then [W][nb1] per-step lane tags
+    uint32_t *sm_tag = sm_cnt + (size_t)p.W * p.nb1;
     cg::grid_group grid = cg::this_grid();
     const int W = p.W, nb1 = p.nb1;
     const int w = threadIdx.x >> 5, l = lane_id();
     const int ncta = gridDim.x, c = blockIdx.x;
     const int total_warps = ncta * W;
+    for (int k = threadIdx.x; k < W * nb1; k += blockDim.x) sm_tag[k] = 0;
+    __syncthreads();
     int round = 0;
     for (int b = 0; b < p.nblk; b++) {
         const int64_t n0 = p.blk[b], n1 = p.blk[b + 1];
@@ -148,55 +173,94 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
         const int t_lo = c * k, t_hi = min(ns, t_lo + k);
         bool first = true;
         while (true) {
-            // ---- P: start counts of my subtiles -------------------------------------------------
-            if (c < nact) {
-                for (int col = threadIdx.x; col < nb1; col += blockDim.x) {
-                    uint32_t run = p.base[col] + (first ? 0u : p.Cpre[(size_t)c * nb1 + col]);
-                    for (int t = t_lo; t < t_hi; t++) {
-                        p.S[(size_t)t * nb1 + col] = run;
-                        if (!first) run += p.H[(size_t)t * nb1 + col];
-                    }
+            // ---- P: start counts of my subtiles, straight into the warps' shared-memory counters ----
+            // first round of a block: no histogram of the block exists yet; start from the populations
+            // before the block, extrapolated proportionally to the subtile's position (only a guess:
+            // it shortens convergence, the fixed point does not depend on it)
+            RD_STAMP(0);
+            const int kl = (c < nact) ? (t_hi - t_lo) : 0;
+            for (int col = threadIdx.x; col < nb1 && kl > 0; col += blockDim.x) {
+                const uint32_t b0 = p.base[col];
+                if (first) {
+                    for (int tl = 0; tl < kl; tl++) sm_cnt[(size_t)tl * nb1 + col] = b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, n0);
+                } else {
+                    uint32_t hv[kRdMaxWarps];
+#pragma unroll
+                    for (int tl = 0; tl < kRdMaxWarps; tl++) hv[tl] = tl < kl ? p.H[(size_t)(t_lo + tl) * nb1 + col] : 0u;
+                    uint32_t run = b0 + p.Cpre[(size_t)c * nb1 + col];
+#pragma unroll
+                    for (int tl = 0; tl < kRdMaxWarps; tl++)
+                        if (tl < kl) { sm_cnt[(size_t)tl * nb1 + col] = run; run += hv[tl]; }
                 }
             }
             __syncthreads();
+            RD_STAMP(1);
             // ---- D: sweep ------------------------------------------------------------------------------
             uint32_t ch = 0;
-            const int t = t_lo + w;
-            if (c < nact && w < k && t < t_hi) {
-                uint32_t *cnt = sm_cnt + (size_t)w * nb1;
-                for (int col = l; col < nb1; col += 32) cnt[col] = p.S[(size_t)t * nb1 + col];
-                __syncwarp();
+            if (w < kl) {
+                const int t = t_lo + w;
                 const int64_t lo = n0 + (int64_t)t * ts, hi = min(n1, lo + ts);
-                ch = rd_sweep(p, lo, hi, cnt);
-                __syncwarp();
-                for (int col = l; col < nb1; col += 32) p.H[(size_t)t * nb1 + col] = cnt[col] - p.S[(size_t)t * nb1 + col];
+                ch = rd_sweep(p, lo, hi, sm_cnt + (size_t)w * nb1, sm_tag + (size_t)w * nb1);
             }
             ch = __reduce_add_sync(0xffffffffu, ch);
             if (l == 0 && ch) atomicAdd(&p.changed[round], ch);
             __syncthreads();
-            if (c < nact) {
-                for (int col = threadIdx.x; col < nb1; col += blockDim.x) {
-                    uint32_t s = 0;
-                    for (int tt = t_lo; tt < t_hi; tt++) s += p.H[(size_t)tt * nb1 + col];
-                    p.Csum[(size_t)c * nb1 + col] = s;
+            RD_STAMP(2);
+            // ---- new subtile histograms = final counters - start counts; chunk total ------------------
+            for (int col = threadIdx.x; col < nb1 && kl > 0; col += blockDim.x) {
+                const uint32_t b0 = p.base[col];
+                uint32_t tot = 0;
+                if (first) {
+                    for (int tl = 0; tl < kl; tl++) {
+                        const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - (b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, n0));
+                        p.H[(size_t)(t_lo + tl) * nb1 + col] = hn;
+                        tot += hn;
+                    }
+                } else {
+                    uint32_t hv[kRdMaxWarps];
+#pragma unroll
+                    for (int tl = 0; tl < kRdMaxWarps; tl++) hv[tl] = tl < kl ? p.H[(size_t)(t_lo + tl) * nb1 + col] : 0u;
+                    uint32_t run = b0 + p.Cpre[(size_t)c * nb1 + col];
+#pragma unroll
+                    for (int tl = 0; tl < kRdMaxWarps; tl++)
+                        if (tl < kl) {
+                            const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - run;
+                            run += hv[tl];
+                            p.H[(size_t)(t_lo + tl) * nb1 + col] = hn;
+                            tot += hn;
+                        }
                 }
+                p.Csum[(size_t)c * nb1 + col] = tot;
             }
+            RD_STAMP(3);
             __threadfence();
             grid.sync();
+            RD_STAMP(4);
             // ---- column scan over chunk totals; on convergence fold the block into base ---------------
             const uint32_t chg = *((volatile uint32_t *)&p.changed[round]);
             const bool done = (chg == 0);
-            for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < nb1; col += (int64_t)gridDim.x * blockDim.x) {
-                uint32_t run = 0;
-                for (int cc = 0; cc < nact; cc++) {
-                    uint32_t v = p.Csum[(size_t)cc * nb1 + col];
-                    p.Cpre[(size_t)cc * nb1 + col] = run;
-                    run += v;
+            {   // one warp per column; lanes stride over the chunks, shuffle scan across lanes
+                const int gw = blockIdx.x * W + w, tw = gridDim.x * W;
+                for (int col = gw; col < nb1; col += tw) {
+                    uint32_t v[5];   // grid <= 160 CTAs
+#pragma unroll
+                    for (int q = 0; q < 5; q++) { const int cc = q * 32 + l; v[q] = cc < nact ? p.Csum[(size_t)cc * nb1 + col] : 0u; }
+                    uint32_t carry = 0;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) {
+                        const int cc = q * 32 + l;
+                        uint32_t inc = warp_incl_scan(v[q]);
+                        if (cc < nact) p.Cpre[(size_t)cc * nb1 + col] = carry + inc - v[q];
+                        carry += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                    if (done && l == 0) p.base[col] += carry;
                 }
-                if (done) p.base[col] += run;
             }
+            RD_STAMP(5);
             __threadfence();
             grid.sync();
+            RD_STAMP(6);
+            if (p.tstamps && blockIdx.x == 0 && threadIdx.x == 0 && round < 4096) p.tstamps[round * 8 + 7] = (unsigned long long)len;
             round++;
             first = false;
             if (done) break;

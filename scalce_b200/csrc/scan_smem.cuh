@@ -15,6 +15,8 @@
 
 namespace scb {
 
+constexpr int kHitCap = 40;   // queued hits per read before the slow path
+
 struct ScanSmemParams {
     const uint8_t *seq; int64_t n; int L;
     const uint16_t *trans; const uint32_t *hit_rank; const uint8_t *rank_level;
@@ -87,27 +89,44 @@ __global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
 
         const int64_t i = tile * p.R + threadIdx.x;
         const bool live = i < p.n;
-        uint32_t list_r[kScanListCap];
-        uint16_t list_p[kScanListCap];
-        int best = 0, cnt = 0;
+        // hot loop: one table lookup per base; a hit (some core ends here) only queues (state, pos)
+        uint32_t hits[kHitCap];
+        int nh = 0, best = 0, cnt = 0;
+        const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
         if (live) {
-            const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
             uint32_t st = 0;
+#pragma unroll 4
             for (int q = 0; q < p.L; q++) {
                 st = s_trans[(st << 2) | base_code(s[q])];
                 if (st >= (uint32_t)p.H0) {
-                    uint32_t r = s_hit[st - p.H0];
+                    if (nh < kHitCap) hits[nh] = (st << 16) | (uint32_t)q;
+                    nh++;
+                }
+            }
+            if (nh <= kHitCap) {
+                // max level, then keep the first occurrence of each bucket of that level
+                for (int j = 0; j < nh; j++) {
+                    uint32_t r = s_hit[(hits[j] >> 16) - p.H0];
                     int lv = s_lvl[r];
-                    if (lv > best) { best = lv; cnt = 0; }
-                    if (lv == best) {
-                        bool dup = false;
-                        int lim = cnt < kScanListCap ? cnt : kScanListCap;
-                        for (int k = 0; k < lim; k++) dup |= (list_r[k] == r);
-                        if (!dup && cnt >= kScanListCap) dup = seen_before_smem(s, q, r, d);
-                        if (!dup) {
-                            if (cnt < kScanListCap) { list_r[cnt] = r; list_p[cnt] = (uint16_t)q; }
-                            cnt++;
-                        }
+                    best = lv > best ? lv : best;
+                    hits[j] = (r << 16) | (hits[j] & 0xffffu);
+                }
+                for (int j = 0; j < nh; j++) {
+                    uint32_t r = hits[j] >> 16;
+                    bool drop = (int)s_lvl[r] != best;
+                    for (int k = 0; k < j && !drop; k++) drop = (hits[k] != 0xffffffffu) && ((hits[k] >> 16) == r);
+                    if (drop) hits[j] = 0xffffffffu; else cnt++;
+                }
+            } else {
+                // more hits than the queue holds (very dense core sets): full walk with inline dedupe
+                uint32_t st2 = 0;
+                for (int q = 0; q < p.L; q++) {
+                    st2 = s_trans[(st2 << 2) | base_code(s[q])];
+                    if (st2 >= (uint32_t)p.H0) {
+                        uint32_t r = s_hit[st2 - p.H0];
+                        int lv = s_lvl[r];
+                        if (lv > best) { best = lv; cnt = 0; }
+                        if (lv == best && !seen_before_smem(s, q, r, d)) cnt++;
                     }
                 }
             }
@@ -134,19 +153,17 @@ __global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
             p.ncand[i] = (uint16_t)cnt;
             p.cand_off[i] = o;
             if (o + (uint64_t)cnt <= p.cand_cap) {
-                int lim = cnt < kScanListCap ? cnt : kScanListCap;
-                for (int k = 0; k < lim; k++) { p.cand_rank[o + k] = list_r[k]; p.cand_pos[o + k] = list_p[k]; }
-                if (cnt > kScanListCap) {   // rare: regenerate the tail of the list by a second walk
-                    const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
-                    uint32_t st = 0; int c2 = 0;
+                if (nh <= kHitCap) {
+                    int c2 = 0;
+                    for (int j = 0; j < nh; j++)
+                        if (hits[j] != 0xffffffffu) { p.cand_rank[o + c2] = hits[j] >> 16; p.cand_pos[o + c2] = (uint16_t)(hits[j] & 0xffffu); c2++; }
+                } else {
+                    uint32_t st2 = 0; int c2 = 0;
                     for (int q = 0; q < p.L; q++) {
-                        st = s_trans[(st << 2) | base_code(s[q])];
-                        if (st >= (uint32_t)p.H0) {
-                            uint32_t r = s_hit[st - p.H0];
-                            if ((int)s_lvl[r] == best && !seen_before_smem(s, q, r, d)) {
-                                if (c2 >= kScanListCap) { p.cand_rank[o + c2] = r; p.cand_pos[o + c2] = (uint16_t)q; }
-                                c2++;
-                            }
+                        st2 = s_trans[(st2 << 2) | base_code(s[q])];
+                        if (st2 >= (uint32_t)p.H0) {
+                            uint32_t r = s_hit[st2 - p.H0];
+                            if ((int)s_lvl[r] == best && !seen_before_smem(s, q, r, d)) { p.cand_rank[o + c2] = r; p.cand_pos[o + c2] = (uint16_t)q; c2++; }
                         }
                     }
                 }
