@@ -13,6 +13,7 @@
 #include "prims.cuh"
 #include "resolve_dense.cuh"
 #include "scan_smem.cuh"
+#include "emit2.cuh"
 
 namespace scb {
 long long g_launches = 0;
@@ -87,6 +88,7 @@ struct scb_handle {
     std::vector<Pending> pending;
     // last flush
     Pending cur;
+    DevBuf packed; int PW = 0;   // 2-bit packed mate-1 reads, PW words per read
     DevBuf lvl, ncand, cand_off, cand_rank, cand_pos, asg, endv, chunk, perm_keys, perm, perm_m;
     DevBuf dbg_bucket, dbg_core, dbg_end, dbg_chunk;
     EmitOut chunked, merged;
@@ -220,75 +222,84 @@ static void gather_pending(scb_handle *h) {
 }
 
 // ---- emit one ordering ----------------------------------------------------------------------------------
-static void emit_order(scb_handle *h, const uint32_t *perm, bool merged, EmitOut &o) {
+// keys: the sorted keys of this ordering; the segment id (chunk, bucket order) is their top seg_bits bits
+static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys, int seg_shift, int seg_bits, bool merged, EmitOut &o) {
     cudaStream_t st = h->st;
     const Pending &c = h->cur;
     const int64_t n = c.n;
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
-    EmitParams e;
-    e.seq1 = c.seq1; e.qual1 = c.qual1; e.names = c.names; e.seq2 = c.seq2; e.qual2 = c.qual2; e.name_off = c.name_off;
-    e.asg = h->asg.as<uint32_t>(); e.endv = h->endv.as<uint16_t>(); e.lvl = h->lvl.as<uint8_t>();
-    e.chunk = h->n_chunks > 1 ? h->chunk.as<uint32_t>() : nullptr;
-    e.perm = perm; e.n = n; e.L1 = L1; e.L2 = L2; e.use_names = cfg.use_names; e.use_quals = cfg.use_quals; e.paired = cfg.paired;
-    e.sz_meta = L1 > 255 ? 2 : 1; e.nb = h->tab.n_buckets; e.root_pos = h->tab.root_order_pos;
-
-    DevBuf offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st), hsum((size_t)(n + 1) * 4, st);
-    DevBuf ws64((size_t)scan_tiles(n) * 8, st), ws32((size_t)scan_tiles(n) * 4, st);
-    exclusive_scan<uint64_t>(NameRec{e}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
-    exclusive_scan<uint64_t>(ReadRec{e}, n, offR.as<uint64_t>(), offR.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
-    SegOf seg{e, h->n_chunks, merged ? 1 : 0};
-    exclusive_scan<uint32_t>(SegHead{seg}, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
-    uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
-    SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaMemcpyAsync(&totR, offR.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaStreamSynchronize(st));
+    const int nb = h->tab.n_buckets;
+    const int sz_meta = L1 > 255 ? 2 : 1;
     const int nlen = 3 + 2 * cfg.paired;
     const int64_t rsz = 8 + 8 * nlen;
+    const int nch = merged ? 1 : h->n_chunks;
+    for (int k = 0; k < SCB_N_STREAMS; k++) { o.size[k] = 0; o.chunk_off[k].assign((size_t)std::max(nch, 0) + 1, 0); }
+    o.n_seg = 0;
+    if (n == 0) { for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc(0, st); return; }
+
+    DevBuf hsum((size_t)(n + 1) * 4, st), ws32((size_t)scan_tiles(n) * 4, st), ws64((size_t)scan_tiles(n) * 8, st), offN;
+    KeyHead kh{keys, seg_shift, seg_bits};
+    exclusive_scan<uint32_t>(kh, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
+    uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
+    if (cfg.use_names) {
+        offN.alloc((size_t)(n + 1) * 8, st);
+        exclusive_scan<uint64_t>(NameRec2{perm, c.name_off}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    }
+    SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
     o.n_seg = nseg;
+    DevBuf spos((size_t)(nseg + 1) * 4, st), srank((size_t)nseg * 4, st), schunk((size_t)nseg * 4, st), srec((size_t)nseg * 4, st),
+        soff((size_t)(nseg + 1) * 8, st), wsS((size_t)scan_tiles(nseg) * 8, st);
+    SegTab tab{spos.as<uint32_t>(), srank.as<uint32_t>(), schunk.as<uint32_t>(), srec.as<uint32_t>()};
+    SCB_LAUNCH(seg_table_k, (unsigned)cdiv(n, 256), 256, 0, st, kh, hsum.as<uint32_t>(), n, perm, h->asg.as<uint32_t>(),
+               (!merged && h->n_chunks > 1) ? h->chunk.as<uint32_t>() : (const uint32_t *)nullptr, h->d_rank_level.as<uint8_t>(), nb, L1, sz_meta, tab, nseg);
+    exclusive_scan<uint64_t>(SegBytes{spos.as<uint32_t>(), srec.as<uint32_t>()}, (int64_t)nseg, soff.as<uint64_t>(), soff.as<uint64_t>() + nseg, wsS.as<uint64_t>(), st);
+    SCB_CUDA(cudaMemcpyAsync(&totR, soff.as<uint64_t>() + nseg, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
     o.size[SCB_S_NAMES] = (int64_t)totN;
     o.size[SCB_S_READS] = (int64_t)totR;
     o.size[SCB_S_QUALS] = cfg.use_quals ? n * L1 : 0;
     o.size[SCB_S_META] = (int64_t)nseg * rsz;
     o.size[SCB_S_READS2] = cfg.paired ? n * sz_read(L2) : 0;
     o.size[SCB_S_QUALS2] = (cfg.paired && cfg.use_quals) ? n * L2 : 0;
-    for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc((size_t)o.size[k], st);
-    if (n > 0)
-        SCB_LAUNCH(emit_k, (unsigned)cdiv(n * 32, 256), 256, 0, st, e, offN.as<uint64_t>(), offR.as<uint64_t>(),
-                   o.data[0].as<uint8_t>(), o.data[1].as<uint8_t>(), o.data[2].as<uint8_t>(), o.data[4].as<uint8_t>(), o.data[5].as<uint8_t>());
-    DevBuf hpos((size_t)(nseg + 1) * 4, st);
-    const int nch = merged ? 1 : h->n_chunks;
-    DevBuf cfirst((size_t)2 * nch * 8, st);
-    if (n > 0) {
-        SCB_LAUNCH(seg_heads_k, (unsigned)cdiv(n, 256), 256, 0, st, seg, hsum.as<uint32_t>(), n, hpos.as<uint32_t>());
-        SCB_LAUNCH(meta_k, (unsigned)cdiv(nseg, 128), 128, 0, st, seg, hpos.as<uint32_t>(), (int64_t)nseg, offN.as<uint64_t>(),
-                   offR.as<uint64_t>(), h->d_rank_node_id.as<int32_t>(), h->d_rank_core.as<int32_t>(), o.data[3].as<uint8_t>(),
-                   merged ? (int64_t *)nullptr : cfirst.as<int64_t>());
-    }
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc((size_t)o.size[k] + 8, st);
+
+    Emit2Params e;
+    e.qual1 = c.qual1; e.names = c.names; e.seq2 = c.seq2; e.qual2 = c.qual2; e.name_off = c.name_off;
+    e.packed = h->packed.as<uint32_t>(); e.PW = h->PW; e.endv = h->endv.as<uint16_t>(); e.perm = perm; e.hsum = hsum.as<uint32_t>();
+    e.seg_pos = spos.as<uint32_t>(); e.seg_recsz = srec.as<uint32_t>(); e.seg_rank = srank.as<uint32_t>(); e.seg_off = soff.as<uint64_t>();
+    e.rank_level = h->d_rank_level.as<uint8_t>(); e.offN = offN.as<uint64_t>(); e.n = n; e.L1 = L1; e.L2 = L2;
+    e.use_names = cfg.use_names; e.use_quals = cfg.use_quals; e.paired = cfg.paired; e.sz_meta = sz_meta; e.nb = nb;
+    e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>(); e.oQ = o.data[2].as<uint8_t>(); e.oR2 = o.data[4].as<uint8_t>(); e.oQ2 = o.data[5].as<uint8_t>();
+    SCB_LAUNCH(emit2_k, (unsigned)cdiv(n * 16, 256), 256, 0, st, e);
+    DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
+    SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), h->d_rank_node_id.as<int32_t>(),
+               h->d_rank_core.as<int32_t>(), nb, L1, L2, cfg.use_names, cfg.use_quals, cfg.paired, o.data[3].as<uint8_t>(),
+               merged ? (int64_t *)nullptr : cfirst.as<int64_t>(), nch);
     // per-chunk offsets of every stream
-    for (int k = 0; k < SCB_N_STREAMS; k++) o.chunk_off[k].assign((size_t)nch + 1, 0);
-    if (!merged && n > 0) {
+    if (!merged) {
         std::vector<int64_t> cf((size_t)2 * nch);
         SCB_CUDA(cudaMemcpyAsync(cf.data(), cfirst.p, cf.size() * 8, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));
-        std::vector<uint64_t> on((size_t)nch), orr((size_t)nch);
-        for (int cidx = 0; cidx < nch; cidx++) {
-            SCB_CUDA(cudaMemcpyAsync(&on[cidx], offN.as<uint64_t>() + cf[cidx], 8, cudaMemcpyDeviceToHost, st));
-            SCB_CUDA(cudaMemcpyAsync(&orr[cidx], offR.as<uint64_t>() + cf[cidx], 8, cudaMemcpyDeviceToHost, st));
+        std::vector<uint64_t> on((size_t)nch, 0), orr((size_t)nch, 0);
+        for (int ci = 0; ci < nch; ci++) {
+            if (cfg.use_names) SCB_CUDA(cudaMemcpyAsync(&on[ci], offN.as<uint64_t>() + cf[ci], 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&orr[ci], soff.as<uint64_t>() + cf[nch + ci], 8, cudaMemcpyDeviceToHost, st));
         }
         SCB_CUDA(cudaStreamSynchronize(st));
-        for (int cidx = 0; cidx < nch; cidx++) {
-            int64_t p0 = cf[cidx], m0 = cf[nch + cidx];
-            o.chunk_off[SCB_S_NAMES][cidx] = (int64_t)on[cidx];
-            o.chunk_off[SCB_S_READS][cidx] = (int64_t)orr[cidx];
-            o.chunk_off[SCB_S_QUALS][cidx] = cfg.use_quals ? p0 * L1 : 0;
-            o.chunk_off[SCB_S_META][cidx] = m0 * rsz;
-            o.chunk_off[SCB_S_READS2][cidx] = cfg.paired ? p0 * sz_read(L2) : 0;
-            o.chunk_off[SCB_S_QUALS2][cidx] = (cfg.paired && cfg.use_quals) ? p0 * L2 : 0;
+        for (int ci = 0; ci < nch; ci++) {
+            int64_t p0 = cf[ci], m0 = cf[nch + ci];
+            o.chunk_off[SCB_S_NAMES][ci] = (int64_t)on[ci];
+            o.chunk_off[SCB_S_READS][ci] = (int64_t)orr[ci];
+            o.chunk_off[SCB_S_QUALS][ci] = cfg.use_quals ? p0 * L1 : 0;
+            o.chunk_off[SCB_S_META][ci] = m0 * rsz;
+            o.chunk_off[SCB_S_READS2][ci] = cfg.paired ? p0 * sz_read(L2) : 0;
+            o.chunk_off[SCB_S_QUALS2][ci] = (cfg.paired && cfg.use_quals) ? p0 * L2 : 0;
         }
     }
-    for (int k = 0; k < SCB_N_STREAMS; k++) o.chunk_off[k][nch] = o.size[k];
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.chunk_off[k][(size_t)nch] = o.size[k];
 }
 
 // ---- the transform ---------------------------------------------------------------------------------------
@@ -304,7 +315,9 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->ev0, st));
     SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
 
-    // 1. scan: max level + ordered distinct candidates per read
+    // 1. scan: max level + ordered distinct candidates per read (+ the 2-bit packed copy of the reads)
+    h->PW = (L1 + 15) / 16;
+    h->packed.alloc((size_t)n * h->PW * 4, st);
     h->lvl.alloc((size_t)n, st);
     h->ncand.alloc((size_t)n * 2, st);
     h->cand_off.alloc((size_t)(n + 1) * 8, st);
@@ -336,6 +349,7 @@ static void run_flush(scb_handle *h) {
                 sp.lvl = h->lvl.as<uint8_t>(); sp.ncand = h->ncand.as<uint16_t>(); sp.cand_off = h->cand_off.as<uint64_t>();
                 sp.cand_rank = h->cand_rank.as<uint32_t>(); sp.cand_pos = h->cand_pos.as<uint16_t>();
                 sp.cand_total = dtot.as<unsigned long long>(); sp.cand_cap = cap; sp.n_tiles = cdiv(n, R);
+                sp.packed = h->packed.as<uint32_t>(); sp.PW = h->PW;
                 int grid = (int)std::min<int64_t>(dev_sms, sp.n_tiles);
                 SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
                 SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
@@ -354,9 +368,11 @@ static void run_flush(scb_handle *h) {
         SCB_CUDA(cudaStreamSynchronize(st));
         h->cand_rank.alloc((size_t)M * 4, st);
         h->cand_pos.alloc((size_t)M * 2, st);
-        if (n > 0)
+        if (n > 0) {
             SCB_LAUNCH((scan_k<true>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
                        h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>());
+            SCB_LAUNCH(pack_reads_k, (unsigned)cdiv(n * h->PW, 256), 256, 0, st, c.seq1, n, L1, h->PW, h->packed.as<uint32_t>());
+        }
     }
 
     SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
@@ -492,7 +508,7 @@ static void run_flush(scb_handle *h) {
     uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
     uint32_t *va = h->perm.as<uint32_t>(), *vb = v1.as<uint32_t>();
     if (n > 0) {
-        SCB_LAUNCH(build_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, c.seq1, n, L1, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+        SCB_LAUNCH(build_keys_pk_k, (unsigned)cdiv(n, 256), 256, 0, st, h->packed.as<uint32_t>(), h->PW, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
                    h->n_chunks > 1 ? h->chunk.as<uint32_t>() : (const uint32_t *)nullptr, nb, h->tab.root_order_pos, seg_bits, pb, ka, va);
         radix_sort_pairs(&ka, &va, &kb, &vb, n, 64 - seg_bits - 2 * pb, 64, ws, st);
         if (va != h->perm.as<uint32_t>()) {  // result landed in the alternate buffer
@@ -528,7 +544,7 @@ static void run_flush(scb_handle *h) {
             DevBuf nk0((size_t)t * 8, st), nk1((size_t)t * 8, st), nv0((size_t)t * 4, st), nv1((size_t)t * 4, st);
             uint64_t *a = nk0.as<uint64_t>(), *b = nk1.as<uint64_t>();
             uint32_t *x = nv0.as<uint32_t>(), *y = nv1.as<uint32_t>();
-            SCB_LAUNCH(tie_rekey_k, (unsigned)cdiv(t, 256), 256, 0, st, c.seq1, L1, h->endv.as<uint16_t>(), c_idx.as<uint32_t>(),
+            SCB_LAUNCH(tie_rekey_pk_k, (unsigned)cdiv(t, 256), 256, 0, st, h->packed.as<uint32_t>(), h->PW, h->endv.as<uint16_t>(), c_idx.as<uint32_t>(),
                        c_grp.as<uint32_t>(), (int64_t)t, grp_bits, consumed, nbases, a, x);
             radix_sort_pairs(&a, &x, &b, &y, t, 64 - grp_bits - 2 * nbases, 64, ws, st);
             SCB_LAUNCH(tie_writeback_k, (unsigned)cdiv(t, 256), 256, 0, st, c_pos.as<uint32_t>(), x, (int64_t)t, h->perm.as<uint32_t>());
@@ -544,7 +560,7 @@ static void run_flush(scb_handle *h) {
 
     SCB_CUDA(cudaEventRecord(h->stage_ev[5], st));
     // 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
-    emit_order(h, h->perm.as<uint32_t>(), false, h->chunked);
+    emit_order(h, h->perm.as<uint32_t>(), ka, 64 - seg_bits, seg_bits, false, h->chunked);
     SCB_CUDA(cudaEventRecord(h->stage_ev[6], st));
     if (cfg.emit_merged && h->n_chunks > 1) {
         // merge() concatenates a bucket's pieces in chunk order (compress.cpp:104-112): a stable sort of the
@@ -557,7 +573,7 @@ static void run_flush(scb_handle *h) {
                    h->tab.root_order_pos, a, x);
         radix_sort_pairs(&a, &x, &b, &y, n, 0, ob, ws, st);
         if (x != h->perm_m.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->perm_m.p, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        emit_order(h, h->perm_m.as<uint32_t>(), true, h->merged);
+        emit_order(h, h->perm_m.as<uint32_t>(), a, 0, ob, true, h->merged);
     }
 
     SCB_CUDA(cudaEventRecord(h->stage_ev[7], st));

@@ -1,0 +1,235 @@
+// emit2.cuh - output side of the transform on 2-bit packed reads.
+//   packed row: PW = ceil(L/16) u32 words per read, base 16k+j of word k at bits 31-2j (MSB first),
+//   zero filled past L - written by the scan kernel (or pack_reads_k on the fallback path).
+//   keys      : prefix of the in-bucket sort key straight from the packed row
+//   segments  : runs of equal (chunk, bucket) in the sorted order -> per-segment table
+//   emit      : 16 lanes per read: names, rotated packed read + end marker, qualities (word copies
+//               with funnel-shifted sources), mate 2
+//   meta      : one record per segment (reads.cpp:160-176)
+#pragma once
+#include "common.cuh"
+#include "pipeline.cuh"
+
+namespace scb {
+
+__device__ __forceinline__ uint32_t pk_word(const uint32_t *__restrict__ row, int k, int PW) { return (k >= 0 && k < PW) ? row[k] : 0u; }
+// 32 bases (64 bits, MSB first) starting at base offset b0; zero past the row
+__device__ __forceinline__ uint64_t pk_bits64(const uint32_t *__restrict__ row, int PW, int b0) {
+    const int k = b0 >> 4, sh = (b0 & 15) * 2;
+    const uint32_t w0 = pk_word(row, k, PW), w1 = pk_word(row, k + 1, PW), w2 = pk_word(row, k + 2, PW);
+    const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+// `nbases` (1..32) bases of the in-bucket sort key of a read from key offset `from`:
+// key = s[end..L) right-padded with A (reads.cpp:547-559)
+__device__ __forceinline__ uint64_t pk_key_bits(const uint32_t *__restrict__ row, int PW, int end, int from, int nbases) {
+    return pk_bits64(row, PW, end + from) >> (64 - 2 * nbases);
+}
+
+// fallback packer (global-table scan path): one thread per (read, word)
+__global__ void pack_reads_k(const uint8_t *__restrict__ seq, int64_t n, int L, int PW, uint32_t *__restrict__ packed) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * PW) return;
+    int64_t i = t / PW;
+    int k = (int)(t - i * PW);
+    const uint8_t *s = seq + i * (int64_t)L;
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        int q = 16 * k + j;
+        w = (w << 2) | (q < L ? base_code(s[q]) : 0u);
+    }
+    packed[t] = w;
+}
+
+__global__ void build_keys_pk_k(const uint32_t *__restrict__ packed, int PW, int64_t n, const uint32_t *__restrict__ asg,
+                                const uint16_t *__restrict__ endv, const uint32_t *__restrict__ chunk, int nb, int root_pos,
+                                int seg_bits, int pb, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t seg = (uint64_t)(chunk ? chunk[i] : 0u) * (uint64_t)(nb + 1) + bucket_ord(asg[i], nb, root_pos);
+    uint64_t kb = pk_key_bits(packed + i * (int64_t)PW, PW, endv[i], 0, pb);
+    keys[i] = (seg_bits ? (seg << (64 - seg_bits)) : 0ull) | (kb << (64 - seg_bits - 2 * pb));
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void tie_rekey_pk_k(const uint32_t *__restrict__ packed, int PW, const uint16_t *__restrict__ endv,
+                               const uint32_t *__restrict__ c_idx, const uint32_t *__restrict__ c_grp, int64_t m, int grp_bits,
+                               int from, int nbases, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    uint32_t i = c_idx[c];
+    uint64_t kb = pk_key_bits(packed + (int64_t)i * PW, PW, endv[i], from, nbases);
+    keys[c] = (grp_bits ? ((uint64_t)c_grp[c] << (64 - grp_bits)) : 0ull) | (kb << (64 - grp_bits - 2 * nbases));
+    vals[c] = i;
+}
+
+// ---- segments ----------------------------------------------------------------------------------------
+struct KeyHead {   // 1 where the segment id (top `bits` bits of the sorted key, 0 bits = one segment) changes
+    const uint64_t *keys; int shift, bits;
+    __device__ __forceinline__ uint32_t operator()(int64_t p) const {
+        if (p == 0) return 1u;
+        if (bits == 0) return 0u;
+        return ((keys[p] >> shift) != (keys[p - 1] >> shift)) ? 1u : 0u;
+    }
+};
+struct NameRec2 {  // bytes of stream 0 for the p-th emitted read
+    const uint32_t *perm; const int64_t *name_off;
+    __device__ __forceinline__ uint64_t operator()(int64_t p) const {
+        uint32_t i = perm[p];
+        return (uint64_t)(name_off[i + 1] - name_off[i]) + 1;
+    }
+};
+struct SegTab {
+    uint32_t *pos;      // [n_seg+1] first output position (pos[n_seg] = n)
+    uint32_t *rank;     // [n_seg] bucket rank (nb = root)
+    uint32_t *chunk;    // [n_seg]
+    uint32_t *recsz;    // [n_seg] bytes per read in stream 1
+};
+__global__ void seg_table_k(KeyHead kh, const uint32_t *__restrict__ hsum, int64_t n, const uint32_t *__restrict__ perm,
+                            const uint32_t *__restrict__ asg, const uint32_t *__restrict__ chunk, const uint8_t *__restrict__ rank_level,
+                            int nb, int L1, int sz_meta, SegTab t, uint32_t n_seg) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) t.pos[n_seg] = (uint32_t)n;
+    if (p >= n || !kh(p)) return;
+    uint32_t m = hsum[p];
+    uint32_t i = perm[p];
+    uint32_t r = asg[i];
+    t.pos[m] = (uint32_t)p;
+    t.rank[m] = r;
+    t.chunk[m] = chunk ? chunk[i] : 0u;
+    int lv = r == (uint32_t)nb ? 0 : rank_level[r];
+    t.recsz[m] = (uint32_t)(sz_read(L1 - lv) + sz_meta);
+}
+struct SegBytes {   // stream-1 bytes of a segment
+    const uint32_t *pos, *recsz;
+    __device__ __forceinline__ uint64_t operator()(int64_t m) const { return (uint64_t)(pos[m + 1] - pos[m]) * recsz[m]; }
+};
+
+// ---- emit ---------------------------------------------------------------------------------------------
+struct Emit2Params {
+    const uint8_t *qual1, *names, *seq2, *qual2;
+    const int64_t *name_off;
+    const uint32_t *packed; int PW;
+    const uint16_t *endv;
+    const uint32_t *perm;
+    const uint32_t *hsum;              // [n] segment index of position p = hsum[p] + head(p) - 1 -> stored as sidx
+    const uint32_t *seg_pos, *seg_recsz, *seg_rank;
+    const uint64_t *seg_off;           // [n_seg] stream-1 byte offset of the segment
+    const uint8_t *rank_level;
+    const uint64_t *offN;              // [n+1]
+    int64_t n;
+    int L1, L2, use_names, use_quals, paired, sz_meta, nb;
+    uint8_t *oN, *oR, *oQ, *oR2, *oQ2;
+};
+
+// copy `len` bytes src -> dst (arbitrary alignments) with 4-byte stores; lanes h, h+16, ... of a half warp
+__device__ __forceinline__ void copy_bytes16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int len, int h) {
+    const uintptr_t d0 = (uintptr_t)dst;
+    const int head = (int)((4 - (d0 & 3)) & 3);              // bytes before the first aligned dst word
+    if (len <= 8 + head) { for (int k = h; k < len; k += 16) dst[k] = src[k]; return; }
+    if (h < head) dst[h] = src[h];
+    const int nw = (len - head) >> 2;                         // full aligned dst words
+    const uint8_t *s0 = src + head;
+    const int sh = (int)(((uintptr_t)s0 & 3) * 8);
+    const uint32_t *sa = (const uint32_t *)((uintptr_t)s0 & ~(uintptr_t)3);
+    uint32_t *da = (uint32_t *)(dst + head);
+    for (int k = h; k < nw; k += 16) {
+        uint32_t lo = sa[k];
+        uint32_t v = lo;
+        if (sh) { uint32_t hi = sa[k + 1]; v = __funnelshift_r(lo, hi, sh); }
+        da[k] = v;
+    }
+    const int done = head + (nw << 2);
+    if (h < len - done) dst[done + h] = src[done + h];
+}
+
+__global__ void __launch_bounds__(256) emit2_k(Emit2Params e) {
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (p >= e.n) return;
+    const int h = threadIdx.x & 15;
+    const uint32_t i = e.perm[p];
+    if (e.use_names) {
+        const int64_t a = e.name_off[i];
+        const int nl = (int)(e.name_off[i + 1] - a);
+        uint8_t *d = e.oN + e.offN[p];
+        if (h == 0) d[0] = (uint8_t)nl;                                        // names.cpp:58
+        for (int k = h; k < nl; k += 16) d[1 + k] = e.names[a + k];
+    }
+    {   // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
+        uint32_t m = e.hsum[p];                              // exclusive head count: a head's own index, else one past
+        if (e.seg_pos[m] != (uint32_t)p) m -= 1;             // seg_pos has n_seg+1 entries (last = n)
+        const uint32_t r = e.seg_rank[m];
+        const int lv = r == (uint32_t)e.nb ? 0 : e.rank_level[r];
+        const int end = e.endv[i];
+        const int tail = e.L1 - end, total = e.L1 - lv;
+        const int nbytes = sz_read(total);
+        uint8_t *d = e.oR + e.seg_off[m] + (uint64_t)((uint32_t)p - e.seg_pos[m]) * e.seg_recsz[m];
+        const uint32_t *row = e.packed + (int64_t)i * e.PW;
+        for (int b = h; b < nbytes; b += 16) {
+            const int j0 = 4 * b;
+            uint32_t v;
+            if (j0 + 4 <= tail) {                       // entirely after the core
+                v = (uint32_t)(pk_bits64(row, e.PW, end + j0) >> 56);
+            } else if (j0 >= tail && j0 + 4 <= total) { // entirely before the core
+                v = (uint32_t)(pk_bits64(row, e.PW, j0 - tail) >> 56);
+            } else {                                    // straddles the wrap point or the end: base by base
+                v = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int j = j0 + t;
+                    uint32_t c = 0;
+                    if (j < total) { const int q = j < tail ? end + j : j - tail; c = (row[q >> 4] >> (30 - 2 * (q & 15))) & 3u; }
+                    v = (v << 2) | c;
+                }
+            }
+            d[b] = (uint8_t)v;
+        }
+        if (h < e.sz_meta) d[nbytes + h] = (uint8_t)((uint32_t)end >> (8 * h));   // low bytes of int16 end, reads.cpp:130
+    }
+    if (e.use_quals) copy_bytes16(e.oQ + p * (int64_t)e.L1, e.qual1 + (int64_t)i * e.L1, e.L1, h);
+    if (e.paired) {
+        const uint8_t *s = e.seq2 + (int64_t)i * e.L2;
+        const int nbytes = sz_read(e.L2);
+        uint8_t *d = e.oR2 + p * (int64_t)nbytes;
+        for (int b = h; b < nbytes; b += 16) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int j = 4 * b + t;
+                v = (v << 2) | (j < e.L2 ? base_code(s[j]) : 0u);
+            }
+            d[b] = (uint8_t)v;
+        }
+        if (e.use_quals) copy_bytes16(e.oQ2 + p * (int64_t)e.L2, e.qual2 + (int64_t)i * e.L2, e.L2, h);
+    }
+}
+
+// one meta record per segment: int32 id, int32 core, int64 tN, tR, tQ [, tR2, tQ2]   reads.cpp:160-176
+__global__ void meta2_k(SegTab t, int64_t n_seg, const uint64_t *__restrict__ offN, const int32_t *__restrict__ rank_node_id,
+                        const int32_t *__restrict__ rank_core, int nb, int L1, int L2, int use_names, int use_quals, int paired,
+                        uint8_t *__restrict__ meta, int64_t *__restrict__ chunk_first /*[2][n_chunks] or null*/, int n_chunks) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_seg) return;
+    const int64_t p0 = t.pos[m], p1 = t.pos[m + 1];
+    const uint32_t r = t.rank[m];
+    const int32_t id = r == (uint32_t)nb ? SCB_ROOT_ID_DEV : rank_node_id[r];
+    const int32_t core = r == (uint32_t)nb ? SCB_ROOT_ID_DEV : rank_core[r];
+    const int64_t cnt = p1 - p0;
+    const int nlen = 3 + 2 * paired;
+    uint8_t *d = meta + m * (int64_t)(8 + 8 * nlen);
+    int64_t v[5];
+    v[0] = use_names ? (int64_t)(offN[p1] - offN[p0]) : 0;
+    v[1] = cnt * (int64_t)t.recsz[m];
+    v[2] = use_quals ? cnt * L1 : 0;
+    v[3] = cnt * sz_read(L2);
+    v[4] = use_quals ? cnt * L2 : 0;
+    memcpy(d, &id, 4); memcpy(d + 4, &core, 4);
+    for (int k = 0; k < nlen; k++) memcpy(d + 8 + 8 * k, &v[k], 8);
+    if (chunk_first) {
+        const uint32_t c = t.chunk[m];
+        if (m == 0 || t.chunk[m - 1] != c) { chunk_first[c] = p0; chunk_first[n_chunks + c] = m; }
+    }
+}
+
+}  // namespace scb

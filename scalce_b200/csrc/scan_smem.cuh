@@ -24,6 +24,7 @@ struct ScanSmemParams {
     uint8_t *lvl; uint16_t *ncand; uint64_t *cand_off; uint32_t *cand_rank; uint16_t *cand_pos;
     unsigned long long *cand_total; uint64_t cand_cap;
     int64_t n_tiles;
+    uint32_t *packed; int PW;     // 2-bit packed copy of every read, PW = ceil(L/16) words
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -95,13 +96,35 @@ __global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
         const uint8_t *s = tile_buf[cur] + (size_t)threadIdx.x * p.L;
         if (live) {
             uint32_t st = 0;
-#pragma unroll 4
-            for (int q = 0; q < p.L; q++) {
-                st = s_trans[(st << 2) | base_code(s[q])];
-                if (st >= (uint32_t)p.H0) {
-                    if (nh < kHitCap) hits[nh] = (st << 16) | (uint32_t)q;
-                    nh++;
+            uint32_t *prow = p.packed + i * (int64_t)p.PW;
+            const int full = p.L >> 4;
+            for (int k = 0; k < full; k++) {          // 16 bases per packed word
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int q = 16 * k + j;
+                    const uint32_t c = base_code(s[q]);
+                    acc = (acc << 2) | c;
+                    st = s_trans[(st << 2) | c];
+                    if (st >= (uint32_t)p.H0) {
+                        if (nh < kHitCap) hits[nh] = (st << 16) | (uint32_t)q;
+                        nh++;
+                    }
                 }
+                prow[k] = acc;
+            }
+            if (p.L & 15) {
+                uint32_t acc = 0;
+                for (int q = full << 4; q < p.L; q++) {
+                    const uint32_t c = base_code(s[q]);
+                    acc = (acc << 2) | c;
+                    st = s_trans[(st << 2) | c];
+                    if (st >= (uint32_t)p.H0) {
+                        if (nh < kHitCap) hits[nh] = (st << 16) | (uint32_t)q;
+                        nh++;
+                    }
+                }
+                prow[full] = acc << (2 * (16 - (p.L & 15)));
             }
             if (nh <= kHitCap) {
                 // max level, then keep the first occurrence of each bucket of that level
