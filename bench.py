@@ -254,6 +254,8 @@ def main():
     for _ in range(a.steps):
         ms, st, _ = one_step()
         dev_ms.append(ms); stages.append(st)
+        if os.environ.get("SCB_BENCH_VERBOSE"):
+            print("step", ms, st, file=sys.stderr)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
     launches = lib.scb_kernel_launches(None) - launches0

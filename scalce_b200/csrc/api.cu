@@ -152,14 +152,15 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
             size_t nhit = 0;
             for (int u = 0; u < ns; u++) nhit += t.nto_rank[u] >= 0;
             size_t bytes = (size_t)ns * 8 + nhit * 4 + (size_t)t.n_buckets;
-            if (ns <= 65535 && bytes <= 160 * 1024) {
+            if (ns <= 16383 && bytes <= 160 * 1024) {   // u16 entries hold next-state * 4
                 std::vector<uint32_t> newid(ns);
                 uint32_t a = 0, b = (uint32_t)(ns - nhit);
                 for (int u = 0; u < ns; u++) newid[u] = t.nto_rank[u] >= 0 ? b++ : a++;
                 std::vector<uint16_t> tr((size_t)ns * 4);
                 std::vector<uint32_t> hr(nhit);
                 for (int u = 0; u < ns; u++) {
-                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + c] = (uint16_t)newid[t.next[(size_t)u * 4 + c]];
+                    // columns in the permuted base order the kernel reads off ASCII bits 1-2 (A0 C1 T2 G3)
+                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + (c ^ (c >> 1))] = (uint16_t)(newid[t.next[(size_t)u * 4 + c]] * 4u);
                     if (t.nto_rank[u] >= 0) hr[newid[u] - (ns - nhit)] = (uint32_t)t.nto_rank[u];
                 }
                 upload(h->d_trans16, tr, h->st);
@@ -317,7 +318,7 @@ static void run_flush(scb_handle *h) {
 
     // 1. scan: max level + ordered distinct candidates per read (+ the 2-bit packed copy of the reads)
     h->PW = (L1 + 15) / 16;
-    h->packed.alloc((size_t)n * h->PW * 4, st);
+    h->packed.alloc((size_t)n * h->PW * 4 + 64, st);   // slack: emit reads up to 2 words past a row
     h->lvl.alloc((size_t)n, st);
     h->ncand.alloc((size_t)n * 2, st);
     h->cand_off.alloc((size_t)(n + 1) * 8, st);

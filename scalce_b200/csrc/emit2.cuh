@@ -20,6 +20,12 @@ __device__ __forceinline__ uint64_t pk_bits64(const uint32_t *__restrict__ row, 
     const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
     return ((uint64_t)hi << 32) | lo;
 }
+// 16 bases (32 bits, MSB first) starting at base offset b0 >= 0; unguarded: the caller masks what lies
+// past the logical end, and every row is followed by readable words
+__device__ __forceinline__ uint32_t pk_bits32(const uint32_t *__restrict__ row, int b0) {
+    const int k = b0 >> 4, sh = (b0 & 15) * 2;
+    return __funnelshift_l(row[k + 1], row[k], sh);
+}
 // `nbases` (1..32) bases of the in-bucket sort key of a read from key offset `from`:
 // key = s[end..L) right-padded with A (reads.cpp:547-559)
 __device__ __forceinline__ uint64_t pk_key_bits(const uint32_t *__restrict__ row, int PW, int end, int from, int nbases) {
@@ -165,25 +171,23 @@ __global__ void __launch_bounds__(256) emit2_k(Emit2Params e) {
         const int tail = e.L1 - end, total = e.L1 - lv;
         const int nbytes = sz_read(total);
         uint8_t *d = e.oR + e.seg_off[m] + (uint64_t)((uint32_t)p - e.seg_pos[m]) * e.seg_recsz[m];
-        const uint32_t *row = e.packed + (int64_t)i * e.PW;
-        for (int b = h; b < nbytes; b += 16) {
-            const int j0 = 4 * b;
-            uint32_t v;
-            if (j0 + 4 <= tail) {                       // entirely after the core
-                v = (uint32_t)(pk_bits64(row, e.PW, end + j0) >> 56);
-            } else if (j0 >= tail && j0 + 4 <= total) { // entirely before the core
-                v = (uint32_t)(pk_bits64(row, e.PW, j0 - tail) >> 56);
-            } else {                                    // straddles the wrap point or the end: base by base
-                v = 0;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int j = j0 + t;
-                    uint32_t c = 0;
-                    if (j < total) { const int q = j < tail ? end + j : j - tail; c = (row[q >> 4] >> (30 - 2 * (q & 15))) & 3u; }
-                    v = (v << 2) | c;
-                }
-            }
-            d[b] = (uint8_t)v;
+        const uint32_t *row = e.packed + (int64_t)i * e.PW;   // rows have 2 words of slack behind the last one
+        // one lane builds 16 rotated bases (4 output bytes): `a` of them come from behind the core, the
+        // rest from the front of the read; whatever lies past `total` is zero fill
+        for (int w = h; 4 * w < nbytes; w += 16) {
+            const int j0 = 16 * w;
+            int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
+            int nv = total - j0; nv = nv > 16 ? 16 : nv;
+            uint32_t v = 0;
+            if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
+            if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
+            if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
+            const int nbw = nbytes - 4 * w;                   // bytes of this word that belong to the record
+            uint8_t *dw = d + 4 * w;
+            dw[0] = (uint8_t)(v >> 24);
+            if (nbw > 1) dw[1] = (uint8_t)(v >> 16);
+            if (nbw > 2) dw[2] = (uint8_t)(v >> 8);
+            if (nbw > 3) dw[3] = (uint8_t)v;
         }
         if (h < e.sz_meta) d[nbytes + h] = (uint8_t)((uint32_t)end >> (8 * h));   // low bytes of int16 end, reads.cpp:130
     }
