@@ -135,6 +135,9 @@ int64_t scb_kernel_launches(const scb_handle *h);
  * 5 emit (per-chunk streams), 6 merged order + emit, 7 per-read arrays. Returns SCB_N_STAGES. */
 #define SCB_N_STAGES 8
 int scb_stage_ms(const scb_handle *h, float *out, int32_t cap);
+/* Forgets all lifetime bucket populations and the unbucketed count (a new compression job with the
+ * same core set); keeps the automaton and the device workspace. */
+int scb_reset_counts(scb_handle *h);
 /* Fixed-point rounds the parallel tie-break needed in the last flush (0 = sequential engine used). */
 int scb_resolve_rounds(const scb_handle *h);
 /* aho_trie_free (reads.cpp:505-535). */

@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_reset_counts", "scb_destroy",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library(path: str | None = None):
     L.scb_kernel_launches.argtypes = [C.c_void_p]
     L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_resolve_rounds.argtypes = [C.c_void_p]
+    L.scb_reset_counts.argtypes = [C.c_void_p]
     L.scb_destroy.argtypes = [C.c_void_p]
     if path is None:
         _lib = L
@@ -201,6 +202,9 @@ class BoostTransform:
         buf = (C.c_float * 8)()
         load_library().scb_stage_ms(self._h, buf, 8)
         return dict(zip(self.STAGES, [float(x) for x in buf]))
+
+    def reset_counts(self):
+        _check(load_library().scb_reset_counts(self._h))
 
     @property
     def resolve_rounds(self):

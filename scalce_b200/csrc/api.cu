@@ -2,6 +2,7 @@
 #include "../../include/scalce_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -19,28 +20,69 @@ namespace scb {
 long long g_launches = 0;
 static thread_local std::string g_last_error;
 
-// stream-ordered device buffer
+// Flush-scoped device memory: one slab (grown on demand, kept across flushes) with bump allocation.
+// The transform allocates ~40 temporaries and 6 output streams per flush; going through the driver's
+// pool for each of them costs milliseconds and occasionally stalls for hundreds, a slab costs nothing.
+struct Arena {
+    struct Slab { char *p; size_t cap; };
+    std::vector<Slab> slabs;
+    size_t cur = 0, off = 0;
+    void reset() { cur = 0; off = 0; }
+    void reserve(size_t bytes) {   // make the first slab at least this large (only ever called between flushes)
+        if (!slabs.empty() && slabs[0].cap >= bytes) return;
+        for (auto &s : slabs) cudaFree(s.p);
+        slabs.clear();
+        Slab s{nullptr, bytes};
+        SCB_CUDA(cudaMalloc((void **)&s.p, bytes));
+        slabs.push_back(s);
+        reset();
+    }
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        if (bytes == 0) bytes = 512;
+        while (true) {
+            if (cur < slabs.size() && off + bytes <= slabs[cur].cap) { void *r = slabs[cur].p + off; off += bytes; return r; }
+            if (cur + 1 < slabs.size()) { cur++; off = 0; continue; }
+            Slab s{nullptr, std::max(bytes, (size_t)1 << 30)};
+            SCB_CUDA(cudaMalloc((void **)&s.p, s.cap));
+            slabs.push_back(s);
+            cur = slabs.size() - 1; off = 0;
+        }
+    }
+    struct Mark { size_t cur, off; };
+    Mark mark() const { return Mark{cur, off}; }
+    void rewind(Mark m) { cur = m.cur; off = m.off; }
+    void destroy() { for (auto &s : slabs) cudaFree(s.p); slabs.clear(); reset(); }
+};
+static thread_local Arena *g_arena = nullptr;   // set while a flush runs
+
+// device buffer: from the flush arena while a flush runs (never freed individually), otherwise from the
+// stream-ordered pool
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     cudaStream_t st = nullptr;
+    bool pooled = false;
     DevBuf() {}
     DevBuf(size_t b, cudaStream_t s) { alloc(b, s); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     DevBuf(DevBuf &&o) noexcept { *this = std::move(o); }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; st = o.st; o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; st = o.st; pooled = o.pooled; o.p = nullptr; o.bytes = 0; }
         return *this;
     }
     void alloc(size_t b, cudaStream_t s) {
         release();
         st = s; bytes = b;
+        if (g_arena) { p = g_arena->alloc(b); pooled = false; return; }
         if (b == 0) b = 16;
         SCB_CUDA(cudaMallocAsync(&p, b, s));
+        pooled = true;
     }
     void release() {
-        if (p) { cudaFreeAsync(p, st); p = nullptr; bytes = 0; }
+        if (p && pooled) cudaFreeAsync(p, st);
+        p = nullptr; bytes = 0; pooled = false;
     }
     ~DevBuf() { release(); }
     template <typename T> T *as() const { return (T *)p; }
@@ -86,6 +128,7 @@ struct scb_handle {
     int H0 = 0, n_hit = 0;
     size_t smem_table_bytes = 0;
     std::vector<Pending> pending;
+    Arena arena;
     // last flush
     Pending cur;
     DevBuf packed; int PW = 0;   // 2-bit packed mate-1 reads, PW words per read
@@ -274,7 +317,17 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     e.rank_level = h->d_rank_level.as<uint8_t>(); e.offN = offN.as<uint64_t>(); e.n = n; e.L1 = L1; e.L2 = L2;
     e.use_names = cfg.use_names; e.use_quals = cfg.use_quals; e.paired = cfg.paired; e.sz_meta = sz_meta; e.nb = nb;
     e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>(); e.oQ = o.data[2].as<uint8_t>(); e.oR2 = o.data[4].as<uint8_t>(); e.oQ2 = o.data[5].as<uint8_t>();
-    SCB_LAUNCH(emit2_k, (unsigned)cdiv(n * 16, 256), 256, 0, st, e);
+    auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) {
+        if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256), 256, 0, st, src, dst, perm, n, L);
+        else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
+    };
+    if (cfg.use_names) SCB_LAUNCH(emit_names_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
+    SCB_LAUNCH(emit_reads_k, (unsigned)cdiv(n * 16, 256), 256, 0, st, e);
+    if (cfg.use_quals) gather_rows(c.qual1, e.oQ, L1);
+    if (cfg.paired) {
+        SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, e.oR2);
+        if (cfg.use_quals) gather_rows(c.qual2, e.oQ2, L2);
+    }
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
     SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), h->d_rank_node_id.as<int32_t>(),
                h->d_rank_core.as<int32_t>(), nb, L1, L2, cfg.use_names, cfg.use_quals, cfg.paired, o.data[3].as<uint8_t>(),
@@ -308,6 +361,19 @@ static void run_flush(scb_handle *h) {
     cudaStream_t st = h->st;
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    struct ArenaScope { ArenaScope(Arena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } };
+    {   // size the slab for this flush before anything is carved from it
+        int64_t n_est = 0, name_est = 0;
+        for (auto &p : h->pending) { n_est += p.n; name_est += p.name_bytes; }
+        const size_t per_read = (size_t)((L1 + 15) / 16 * 4) + 1 + 2 + 8 + 8 * 6 + 4 + 2 + 4 + 3 * (8 + 4) + 8 + 4 +
+                                (size_t)(sz_read(L1) + 3) + (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 16 + 64;
+        size_t est = (size_t)n_est * per_read + (size_t)name_est + (size_t)n_est + ((size_t)256 << 20);
+        if (h->pending.size() > 1) est += (size_t)n_est * ((size_t)L1 * 2 + (size_t)L2 * 2 + 8) + (size_t)name_est;
+        if (cfg.emit_merged) est += est / 2;
+        h->arena.reserve(est);
+        h->arena.reset();
+    }
+    ArenaScope arena_scope(&h->arena);
     gather_pending(h);
     const Pending &c = h->cur;
     const int64_t n = c.n;
@@ -500,7 +566,18 @@ static void run_flush(scb_handle *h) {
     const int nch = h->n_chunks > 0 ? h->n_chunks : 1;
     const int seg_bits = ceil_log2((uint64_t)nch * (uint64_t)(nb + 1));
     if (seg_bits > 40) throw CudaError{"too many (chunk, bucket) segments"};
-    int pb = std::min(L1, (64 - seg_bits) / 2);
+    // key prefix: enough bases that equal prefixes are rare inside a bucket of the expected size, then
+    // rounded up so that the sorted bit range is a whole number of 8-bit passes; equal prefixes that do
+    // occur are refined afterwards (step 5), so this only trades radix passes against refinement work
+    int pb;
+    {
+        double per_bucket = (double)std::max<int64_t>(n, 1) / (double)(nb + 1);
+        int need = 6;
+        while (need < 32 && std::pow(4.0, need - 6) < per_bucket) need++;
+        int total_bits = std::min(64, ((seg_bits + 2 * need + 7) / 8) * 8);
+        pb = std::min(L1, (total_bits - seg_bits) / 2);
+        if (getenv("SCB_SORT_FULLKEY")) pb = std::min(L1, (64 - seg_bits) / 2);
+    }
     DevBuf k0((size_t)n * 8, st), k1((size_t)n * 8, st), v1((size_t)n * 4, st);
     h->perm.alloc((size_t)n * 4, st);
     SortWs ws;
@@ -788,6 +865,18 @@ int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx) {
 
 int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches; }
 
+int scb_reset_counts(scb_handle *h) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    SCB_CUDA(cudaMemsetAsync(h->d_life.p, 0, ((size_t)h->tab.n_buckets + 1) * 8, h->st));
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    SCB_CATCH
+    h->life_total = 0;
+    h->unbucketed = 0;
+    return SCB_OK;
+}
+
 int scb_resolve_rounds(const scb_handle *h) { return h ? h->last_rounds : -1; }
 
 int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
@@ -803,7 +892,8 @@ void scb_destroy(scb_handle *h) {
     cudaStream_t st = h->st;
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
-    delete h;  // DevBufs free stream-ordered
+    h->arena.destroy();
+    delete h;  // pooled DevBufs free stream-ordered
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);

@@ -150,63 +150,144 @@ __device__ __forceinline__ void copy_bytes16(uint8_t *__restrict__ dst, const ui
     if (h < len - done) dst[done + h] = src[done + h];
 }
 
-__global__ void __launch_bounds__(256) emit2_k(Emit2Params e) {
+// ---- stream 2 / 5: qualities are a pure row gather: out row p <- in row perm[p] -----------------------
+// One thread per 16 output bytes (the output is dense, so stores are aligned STG.128 and fully
+// coalesced); a chunk may straddle two rows. Sources are unaligned: two aligned 16-byte loads and a
+// byte shift. Requires L >= 16.
+__device__ __forceinline__ uint4 load16_unaligned(const uint8_t *__restrict__ a, int nbytes) {
+    const uintptr_t A = (uintptr_t)a;
+    const uint4 *a0 = (const uint4 *)(A & ~(uintptr_t)15);
+    const int sh = (int)(A & 15);
+    uint4 v0 = a0[0], v1 = make_uint4(0, 0, 0, 0);
+    if (sh + nbytes > 16) v1 = a0[1];               // only when it holds a needed byte (never past the buffer's last granule)
+    const int bs = (sh & 3) * 8;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (sh >> 2) {
+        case 0: w0 = v0.x; w1 = v0.y; w2 = v0.z; w3 = v0.w; w4 = v1.x; break;
+        case 1: w0 = v0.y; w1 = v0.z; w2 = v0.w; w3 = v1.x; w4 = v1.y; break;
+        case 2: w0 = v0.z; w1 = v0.w; w2 = v1.x; w3 = v1.y; w4 = v1.z; break;
+        default: w0 = v0.w; w1 = v1.x; w2 = v1.y; w3 = v1.z; w4 = v1.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+}
+// dst bytes [0, k) from x, bytes [k, 16) from y shifted up by k (k in 1..15)
+__device__ __forceinline__ uint4 splice16(uint4 x, uint4 y, int k) {
+    uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int lo = 4 * j;                                   // first byte of output word j
+        uint32_t v;
+        if (lo + 4 <= k) v = xs[j];
+        else if (lo >= k) {                                     // bytes lo-k .. lo-k+3 of y
+            const int s = lo - k, ws = s >> 2, bs = (s & 3) * 8;
+            uint32_t a = 0, b2 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { a = (ws == q) ? ys[q] : a; b2 = (ws + 1 == q) ? ys[q] : b2; }
+            v = __funnelshift_r(a, b2, bs);
+        } else {                                                // mixed word: k - lo bytes of x, rest from y[0..]
+            const int nx = k - lo;
+            v = (xs[j] & (0xffffffffu >> (8 * (4 - nx)))) | (ys[0] << (8 * nx));
+        }
+        o[j] = v;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void __launch_bounds__(256) gather_rows16_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                       const uint32_t *__restrict__ perm, int64_t n, int L) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t o = c << 4, total = n * (int64_t)L;
+    if (o >= total) return;
+    const int64_t p0 = o / L;
+    const int r0 = (int)(o - p0 * L);
+    const int n0 = min(16, L - r0);
+    uint4 v = load16_unaligned(src + (int64_t)perm[p0] * L + r0, n0);
+    if (n0 < 16 && p0 + 1 < n) {
+        const uint4 y = load16_unaligned(src + (int64_t)perm[p0 + 1] * L, 16 - n0);
+        v = splice16(v, y, n0);
+    }
+    if (o + 16 <= total) *(uint4 *)(dst + o) = v;               // dst is 16-byte aligned (allocation base)
+    else {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int k = 0; k < (int)(total - o); k++) dst[o + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+__global__ void gather_rows_small_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint32_t *__restrict__ perm,
+                                    int64_t n, int L) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n * (int64_t)L) return;
+    const int64_t p = o / L;
+    dst[o] = src[(int64_t)perm[p] * L + (o - p * L)];
+}
+
+// ---- stream 0: names, one thread per read --------------------------------------------------------------
+__global__ void emit_names_k(Emit2Params e) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= e.n) return;
+    const uint32_t i = e.perm[p];
+    const int64_t a = e.name_off[i];
+    const int nl = (int)(e.offN[p + 1] - e.offN[p]) - 1;
+    uint8_t *d = e.oN + e.offN[p];
+    d[0] = (uint8_t)nl;                                                           // names.cpp:58
+    for (int k = 0; k < nl; k++) d[1 + k] = e.names[a + k];
+}
+
+// ---- stream 1: rotated 2-bit reads + end marker, 16 lanes per read -------------------------------------
+__global__ void __launch_bounds__(256) emit_reads_k(Emit2Params e) {
     const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     if (p >= e.n) return;
     const int h = threadIdx.x & 15;
     const uint32_t i = e.perm[p];
-    if (e.use_names) {
-        const int64_t a = e.name_off[i];
-        const int nl = (int)(e.name_off[i + 1] - a);
-        uint8_t *d = e.oN + e.offN[p];
-        if (h == 0) d[0] = (uint8_t)nl;                                        // names.cpp:58
-        for (int k = h; k < nl; k += 16) d[1 + k] = e.names[a + k];
+    // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
+    uint32_t m = e.hsum[p];                              // exclusive head count: a head's own index, else one past
+    if (e.seg_pos[m] != (uint32_t)p) m -= 1;             // seg_pos has n_seg+1 entries (last = n)
+    const uint32_t r = e.seg_rank[m];
+    const int lv = r == (uint32_t)e.nb ? 0 : e.rank_level[r];
+    const int end = e.endv[i];
+    const int tail = e.L1 - end, total = e.L1 - lv;
+    const int nbytes = sz_read(total);
+    uint8_t *d = e.oR + e.seg_off[m] + (uint64_t)((uint32_t)p - e.seg_pos[m]) * e.seg_recsz[m];
+    const uint32_t *row = e.packed + (int64_t)i * e.PW;   // rows have 2 words of slack behind the last one
+    // one lane builds 16 rotated bases (4 output bytes): `a` of them come from behind the core, the
+    // rest from the front of the read; whatever lies past `total` is zero fill
+    for (int w = h; 4 * w < nbytes; w += 16) {
+        const int j0 = 16 * w;
+        int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
+        int nv = total - j0; nv = nv > 16 ? 16 : nv;
+        uint32_t v = 0;
+        if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
+        if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
+        if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
+        const int nbw = nbytes - 4 * w;                   // bytes of this word that belong to the record
+        uint8_t *dw = d + 4 * w;
+        dw[0] = (uint8_t)(v >> 24);
+        if (nbw > 1) dw[1] = (uint8_t)(v >> 16);
+        if (nbw > 2) dw[2] = (uint8_t)(v >> 8);
+        if (nbw > 3) dw[3] = (uint8_t)v;
     }
-    {   // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
-        uint32_t m = e.hsum[p];                              // exclusive head count: a head's own index, else one past
-        if (e.seg_pos[m] != (uint32_t)p) m -= 1;             // seg_pos has n_seg+1 entries (last = n)
-        const uint32_t r = e.seg_rank[m];
-        const int lv = r == (uint32_t)e.nb ? 0 : e.rank_level[r];
-        const int end = e.endv[i];
-        const int tail = e.L1 - end, total = e.L1 - lv;
-        const int nbytes = sz_read(total);
-        uint8_t *d = e.oR + e.seg_off[m] + (uint64_t)((uint32_t)p - e.seg_pos[m]) * e.seg_recsz[m];
-        const uint32_t *row = e.packed + (int64_t)i * e.PW;   // rows have 2 words of slack behind the last one
-        // one lane builds 16 rotated bases (4 output bytes): `a` of them come from behind the core, the
-        // rest from the front of the read; whatever lies past `total` is zero fill
-        for (int w = h; 4 * w < nbytes; w += 16) {
-            const int j0 = 16 * w;
-            int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
-            int nv = total - j0; nv = nv > 16 ? 16 : nv;
-            uint32_t v = 0;
-            if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
-            if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
-            if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
-            const int nbw = nbytes - 4 * w;                   // bytes of this word that belong to the record
-            uint8_t *dw = d + 4 * w;
-            dw[0] = (uint8_t)(v >> 24);
-            if (nbw > 1) dw[1] = (uint8_t)(v >> 16);
-            if (nbw > 2) dw[2] = (uint8_t)(v >> 8);
-            if (nbw > 3) dw[3] = (uint8_t)v;
-        }
-        if (h < e.sz_meta) d[nbytes + h] = (uint8_t)((uint32_t)end >> (8 * h));   // low bytes of int16 end, reads.cpp:130
-    }
-    if (e.use_quals) copy_bytes16(e.oQ + p * (int64_t)e.L1, e.qual1 + (int64_t)i * e.L1, e.L1, h);
-    if (e.paired) {
-        const uint8_t *s = e.seq2 + (int64_t)i * e.L2;
-        const int nbytes = sz_read(e.L2);
-        uint8_t *d = e.oR2 + p * (int64_t)nbytes;
-        for (int b = h; b < nbytes; b += 16) {
-            uint32_t v = 0;
+    if (h < e.sz_meta) d[nbytes + h] = (uint8_t)((uint32_t)end >> (8 * h));   // low bytes of int16 end, reads.cpp:130
+}
+
+// ---- stream 4: mate 2 is packed without rotation (output_read(read2, dest, 0, 0), compress.cpp:696) ----
+__global__ void emit_reads2_k(const uint8_t *__restrict__ seq2, const uint32_t *__restrict__ perm, int64_t n, int L2,
+                              uint8_t *__restrict__ oR2) {
+    const int nb2 = sz_read(L2), nw = (nb2 + 3) >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nw) return;
+    const int64_t p = t / nw;
+    const int w = (int)(t - p * nw);
+    const uint8_t *s = seq2 + (int64_t)perm[p] * L2;
+    uint32_t v = 0;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int j = 4 * b + t;
-                v = (v << 2) | (j < e.L2 ? base_code(s[j]) : 0u);
-            }
-            d[b] = (uint8_t)v;
-        }
-        if (e.use_quals) copy_bytes16(e.oQ2 + p * (int64_t)e.L2, e.qual2 + (int64_t)i * e.L2, e.L2, h);
+    for (int j = 0; j < 16; j++) {
+        const int q = 16 * w + j;
+        v = (v << 2) | (q < L2 ? base_code(s[q]) : 0u);
     }
+    uint8_t *d = oR2 + p * (int64_t)nb2 + 4 * w;
+    const int nbw = nb2 - 4 * w;
+    d[0] = (uint8_t)(v >> 24);
+    if (nbw > 1) d[1] = (uint8_t)(v >> 16);
+    if (nbw > 2) d[2] = (uint8_t)(v >> 8);
+    if (nbw > 3) d[3] = (uint8_t)v;
 }
 
 // one meta record per segment: int32 id, int32 core, int64 tN, tR, tQ [, tR2, tQ2]   reads.cpp:160-176

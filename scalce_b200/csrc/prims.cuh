@@ -119,7 +119,7 @@ struct LoadAs {
 // =================================================================================================
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;
+constexpr int kSortItems = 12;   // tile = 3072 elements: 36 KB of staging + 10 KB of counters stays under 48 KB static smem
 constexpr int kSortTile = kSortThreads * kSortItems;
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys, int64_t n, int shift, uint32_t mask,
@@ -137,23 +137,36 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys
     hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *keys, const uint32_t *vals, uint64_t *keys_out,
-                                                               uint32_t *vals_out, int64_t n, int shift, uint32_t mask,
-                                                               const uint32_t *hist_scanned, int64_t tiles) {
+// Scatter pass. Ranks are computed per warp with match.any (stable), the tile is first reordered by
+// digit in shared memory, then written out so that each digit's elements leave as one contiguous run.
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                               uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
+                                                               int shift, uint32_t mask, const uint32_t *__restrict__ hist_scanned, int64_t tiles) {
     __shared__ uint32_t cnt[kSortWarps][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gbase[256];     // global start of this tile's run of digit d, minus its start inside the tile
+    __shared__ uint32_t tbase[256];     // start of digit d inside the digit-ordered tile
+    __shared__ uint32_t sc[kSortThreads / 32 + 1];
+    __shared__ uint64_t skey[kSortTile];
+    __shared__ uint32_t sval[kSortTile];
     const int w = threadIdx.x >> 5, l = lane_id();
     for (int d = l; d < 256; d += 32) cnt[w][d] = 0;
-    gbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * tiles + blockIdx.x];
     __syncwarp();
-    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortItems * 32);
+    const int64_t tbeg = (int64_t)blockIdx.x * kSortTile;
+    const int64_t wbase = tbeg + (int64_t)w * (kSortItems * 32);
     uint64_t key[kSortItems];
+    uint32_t val[kSortItems];
     uint32_t rank[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
         int64_t i = wbase + k * 32 + l;
         bool ok = i < n;
         key[k] = ok ? keys[i] : ~0ull;
+        val[k] = ok ? vals[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        int64_t i = wbase + k * 32 + l;
+        bool ok = i < n;
         uint32_t d = ok ? ((uint32_t)(key[k] >> shift) & mask) : 0xffffffffu;  // invalid lanes never match valid ones
         uint32_t m = __match_any_sync(0xffffffffu, d);
         uint32_t leader = __ffs(m) - 1;
@@ -167,14 +180,17 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *k
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive scan over warps for digit = threadIdx.x
-        uint32_t run = gbase[threadIdx.x];
+    {   // digit = threadIdx.x: exclusive scan over warps, then over digits
+        uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < kSortWarps; ww++) {
             uint32_t c = cnt[ww][threadIdx.x];
             cnt[ww][threadIdx.x] = run;
             run += c;
         }
+        uint32_t tb = block_excl_scan<uint32_t, kSortThreads>(run, sc, (uint32_t *)nullptr);
+        tbase[threadIdx.x] = tb;
+        gbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * tiles + blockIdx.x] - tb;
     }
     __syncthreads();
 #pragma unroll
@@ -182,10 +198,20 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *k
         int64_t i = wbase + k * 32 + l;
         if (i < n) {
             uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-            uint32_t p = cnt[w][d] + rank[k];
-            keys_out[p] = key[k];
-            vals_out[p] = vals[i];
+            uint32_t t = tbase[d] + cnt[w][d] + rank[k];
+            skey[t] = key[k];
+            sval[t] = val[k];
         }
+    }
+    __syncthreads();
+    const int64_t rem = n - tbeg;
+    const int cntTile = (int)(rem < (int64_t)kSortTile ? rem : (int64_t)kSortTile);
+    for (int t = threadIdx.x; t < cntTile; t += kSortThreads) {
+        uint64_t kk = skey[t];
+        uint32_t d = (uint32_t)(kk >> shift) & mask;
+        uint32_t p = gbase[d] + (uint32_t)t;
+        keys_out[p] = kk;
+        vals_out[p] = sval[t];
     }
 }
 
