@@ -131,6 +131,7 @@ struct scb_handle {
     Arena arena;
     // last flush
     Pending cur;
+    DevBuf meta_in;               // per-read metadata word (emit2.cuh), input order
     DevBuf packed; int PW = 0;   // 2-bit packed mate-1 reads, PW words per read
     DevBuf lvl, ncand, cand_off, cand_rank, cand_pos, asg, endv, chunk, perm_keys, perm, perm_m;
     DevBuf dbg_bucket, dbg_core, dbg_end, dbg_chunk;
@@ -282,56 +283,59 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     o.n_seg = 0;
     if (n == 0) { for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc(0, st); return; }
 
-    DevBuf hsum((size_t)(n + 1) * 4, st), ws32((size_t)scan_tiles(n) * 4, st), ws64((size_t)scan_tiles(n) * 8, st), offN;
+    DevBuf hsum((size_t)(n + 1) * 4, st), ws32((size_t)scan_tiles(n) * 4, st), ws64((size_t)scan_tiles(n) * 8, st);
+    DevBuf ms((size_t)n * 8, st), offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st);
+    // the one random small gather of the output side: per-read metadata into output order
+    SCB_LAUNCH(gather_meta_k, (unsigned)cdiv(n, 256), 256, 0, st, h->meta_in.as<uint64_t>(), perm, n, ms.as<uint64_t>());
     KeyHead kh{keys, seg_shift, seg_bits};
     exclusive_scan<uint32_t>(kh, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
     uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
     if (cfg.use_names) {
-        offN.alloc((size_t)(n + 1) * 8, st);
-        exclusive_scan<uint64_t>(NameRec2{perm, c.name_off}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        exclusive_scan<uint64_t>(NameRecM{ms.as<uint64_t>()}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
         SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     }
+    exclusive_scan<uint64_t>(ReadRecM{ms.as<uint64_t>(), L1, sz_meta}, n, offR.as<uint64_t>(), offR.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    SCB_CUDA(cudaMemcpyAsync(&totR, offR.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     o.n_seg = nseg;
-    DevBuf spos((size_t)(nseg + 1) * 4, st), srank((size_t)nseg * 4, st), schunk((size_t)nseg * 4, st), srec((size_t)nseg * 4, st),
-        soff((size_t)(nseg + 1) * 8, st), wsS((size_t)scan_tiles(nseg) * 8, st);
+    DevBuf spos((size_t)(nseg + 1) * 4, st), srank((size_t)nseg * 4, st), schunk((size_t)nseg * 4, st), srec((size_t)nseg * 4, st);
     SegTab tab{spos.as<uint32_t>(), srank.as<uint32_t>(), schunk.as<uint32_t>(), srec.as<uint32_t>()};
     SCB_LAUNCH(seg_table_k, (unsigned)cdiv(n, 256), 256, 0, st, kh, hsum.as<uint32_t>(), n, perm, h->asg.as<uint32_t>(),
                (!merged && h->n_chunks > 1) ? h->chunk.as<uint32_t>() : (const uint32_t *)nullptr, h->d_rank_level.as<uint8_t>(), nb, L1, sz_meta, tab, nseg);
-    exclusive_scan<uint64_t>(SegBytes{spos.as<uint32_t>(), srec.as<uint32_t>()}, (int64_t)nseg, soff.as<uint64_t>(), soff.as<uint64_t>() + nseg, wsS.as<uint64_t>(), st);
-    SCB_CUDA(cudaMemcpyAsync(&totR, soff.as<uint64_t>() + nseg, 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaStreamSynchronize(st));
     o.size[SCB_S_NAMES] = (int64_t)totN;
     o.size[SCB_S_READS] = (int64_t)totR;
     o.size[SCB_S_QUALS] = cfg.use_quals ? n * L1 : 0;
     o.size[SCB_S_META] = (int64_t)nseg * rsz;
     o.size[SCB_S_READS2] = cfg.paired ? n * sz_read(L2) : 0;
     o.size[SCB_S_QUALS2] = (cfg.paired && cfg.use_quals) ? n * L2 : 0;
-    for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc((size_t)o.size[k] + 8, st);
+    for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc((size_t)o.size[k] + 16, st);
 
-    Emit2Params e;
-    e.qual1 = c.qual1; e.names = c.names; e.seq2 = c.seq2; e.qual2 = c.qual2; e.name_off = c.name_off;
-    e.packed = h->packed.as<uint32_t>(); e.PW = h->PW; e.endv = h->endv.as<uint16_t>(); e.perm = perm; e.hsum = hsum.as<uint32_t>();
-    e.seg_pos = spos.as<uint32_t>(); e.seg_recsz = srec.as<uint32_t>(); e.seg_rank = srank.as<uint32_t>(); e.seg_off = soff.as<uint64_t>();
-    e.rank_level = h->d_rank_level.as<uint8_t>(); e.offN = offN.as<uint64_t>(); e.n = n; e.L1 = L1; e.L2 = L2;
-    e.use_names = cfg.use_names; e.use_quals = cfg.use_quals; e.paired = cfg.paired; e.sz_meta = sz_meta; e.nb = nb;
-    e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>(); e.oQ = o.data[2].as<uint8_t>(); e.oR2 = o.data[4].as<uint8_t>(); e.oQ2 = o.data[5].as<uint8_t>();
+    EmitMParams e;
+    e.names = c.names; e.packed = h->packed.as<uint32_t>(); e.PW = h->PW; e.perm = perm; e.ms = ms.as<uint64_t>();
+    e.offN = offN.as<uint64_t>(); e.offR = offR.as<uint64_t>(); e.n = n; e.L1 = L1; e.sz_meta = sz_meta;
+    e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>();
+    uint8_t *oQ = o.data[2].as<uint8_t>(), *oR2 = o.data[4].as<uint8_t>(), *oQ2 = o.data[5].as<uint8_t>();
     auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) {
-        if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256), 256, 0, st, src, dst, perm, n, L);
+        if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
         else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
     };
-    if (cfg.use_names) SCB_LAUNCH(emit_names_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
-    SCB_LAUNCH(emit_reads_k, (unsigned)cdiv(n * 16, 256), 256, 0, st, e);
-    if (cfg.use_quals) gather_rows(c.qual1, e.oQ, L1);
+    if (cfg.use_names) SCB_LAUNCH(emit_names_m_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
+    {
+        const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
+        const int64_t nthr = n * (int64_t)NW;
+        if (nthr >= (1ll << 32)) throw CudaError{"flush too large for the stream-1 kernel's 32-bit indexing (n * record words >= 2^32)"};
+        SCB_LAUNCH(emit_reads_m_k, (unsigned)cdiv(nthr, 256), 256, 0, st, e, NW, nthr);
+    }
+    if (cfg.use_quals) gather_rows(c.qual1, oQ, L1);
     if (cfg.paired) {
-        SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, e.oR2);
-        if (cfg.use_quals) gather_rows(c.qual2, e.oQ2, L2);
+        SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, oR2);
+        if (cfg.use_quals) gather_rows(c.qual2, oQ2, L2);
     }
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
-    SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), h->d_rank_node_id.as<int32_t>(),
-               h->d_rank_core.as<int32_t>(), nb, L1, L2, cfg.use_names, cfg.use_quals, cfg.paired, o.data[3].as<uint8_t>(),
-               merged ? (int64_t *)nullptr : cfirst.as<int64_t>(), nch);
+    SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), offR.as<uint64_t>(),
+               h->d_rank_node_id.as<int32_t>(), h->d_rank_core.as<int32_t>(), nb, L1, L2, cfg.use_names, cfg.use_quals, cfg.paired,
+               o.data[3].as<uint8_t>(), merged ? (int64_t *)nullptr : cfirst.as<int64_t>(), nch);
     // per-chunk offsets of every stream
     if (!merged) {
         std::vector<int64_t> cf((size_t)2 * nch);
@@ -340,7 +344,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         std::vector<uint64_t> on((size_t)nch, 0), orr((size_t)nch, 0);
         for (int ci = 0; ci < nch; ci++) {
             if (cfg.use_names) SCB_CUDA(cudaMemcpyAsync(&on[ci], offN.as<uint64_t>() + cf[ci], 8, cudaMemcpyDeviceToHost, st));
-            SCB_CUDA(cudaMemcpyAsync(&orr[ci], soff.as<uint64_t>() + cf[nch + ci], 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&orr[ci], offR.as<uint64_t>() + cf[ci], 8, cudaMemcpyDeviceToHost, st));
         }
         SCB_CUDA(cudaStreamSynchronize(st));
         for (int ci = 0; ci < nch; ci++) {
@@ -532,6 +536,10 @@ static void run_flush(scb_handle *h) {
     h->life_total += (uint64_t)n;
     SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
 
+    h->meta_in.alloc((size_t)n * 8, st);
+    if (n > 0)
+        SCB_LAUNCH(build_meta_k, (unsigned)cdiv(n, 256), 256, 0, st, n, cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->lvl.as<uint8_t>(),
+                   h->endv.as<uint16_t>(), h->meta_in.as<uint64_t>());
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
     // 3. sizes -> flush chunks
     {

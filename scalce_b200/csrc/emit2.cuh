@@ -24,7 +24,7 @@ __device__ __forceinline__ uint64_t pk_bits64(const uint32_t *__restrict__ row, 
 // past the logical end, and every row is followed by readable words
 __device__ __forceinline__ uint32_t pk_bits32(const uint32_t *__restrict__ row, int b0) {
     const int k = b0 >> 4, sh = (b0 & 15) * 2;
-    return __funnelshift_l(row[k + 1], row[k], sh);
+    return __funnelshift_l(ldg_g64(row + k + 1), ldg_g64(row + k), sh);
 }
 // `nbases` (1..32) bases of the in-bucket sort key of a read from key offset `from`:
 // key = s[end..L) right-padded with A (reads.cpp:547-559)
@@ -83,7 +83,7 @@ struct NameRec2 {  // bytes of stream 0 for the p-th emitted read
     const uint32_t *perm; const int64_t *name_off;
     __device__ __forceinline__ uint64_t operator()(int64_t p) const {
         uint32_t i = perm[p];
-        return (uint64_t)(name_off[i + 1] - name_off[i]) + 1;
+        return (uint64_t)(ldg_g64(name_off + i + 1) - ldg_g64(name_off + i)) + 1;
     }
 };
 struct SegTab {
@@ -158,8 +158,8 @@ __device__ __forceinline__ uint4 load16_unaligned(const uint8_t *__restrict__ a,
     const uintptr_t A = (uintptr_t)a;
     const uint4 *a0 = (const uint4 *)(A & ~(uintptr_t)15);
     const int sh = (int)(A & 15);
-    uint4 v0 = a0[0], v1 = make_uint4(0, 0, 0, 0);
-    if (sh + nbytes > 16) v1 = a0[1];               // only when it holds a needed byte (never past the buffer's last granule)
+    uint4 v0 = ldg_g64(a0), v1 = make_uint4(0, 0, 0, 0);
+    if (sh + nbytes > 16) v1 = ldg_g64(a0 + 1);               // only when it holds a needed byte (never past the buffer's last granule)
     const int bs = (sh & 3) * 8;
     uint32_t w0, w1, w2, w3, w4;
     switch (sh >> 2) {
@@ -192,23 +192,45 @@ __device__ __forceinline__ uint4 splice16(uint4 x, uint4 y, int k) {
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
+constexpr int kGatherChunks = 4;   // independent 16-byte chunks per thread (memory-level parallelism)
 __global__ void __launch_bounds__(256) gather_rows16_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                        const uint32_t *__restrict__ perm, int64_t n, int L) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t o = c << 4, total = n * (int64_t)L;
-    if (o >= total) return;
-    const int64_t p0 = o / L;
-    const int r0 = (int)(o - p0 * L);
-    const int n0 = min(16, L - r0);
-    uint4 v = load16_unaligned(src + (int64_t)perm[p0] * L + r0, n0);
-    if (n0 < 16 && p0 + 1 < n) {
-        const uint4 y = load16_unaligned(src + (int64_t)perm[p0 + 1] * L, 16 - n0);
-        v = splice16(v, y, n0);
+    const int64_t total = n * (int64_t)L;
+    // one 64-bit division per thread (the block's first byte), 32-bit arithmetic after that
+    const int64_t blk0 = (int64_t)blockIdx.x * (256 * kGatherChunks * 16);
+    const int64_t pblk = blk0 / L;
+    const uint32_t rblk = (uint32_t)(blk0 - pblk * L);
+    const uint8_t *a0[kGatherChunks], *a1[kGatherChunks];
+    int n0[kGatherChunks];
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++) {     // all row lookups first ...
+        const uint32_t lo = (uint32_t)(q * 256 + threadIdx.x) << 4;   // byte offset inside the block's range
+        a0[q] = a1[q] = nullptr; n0[q] = 16;
+        if (blk0 + lo < total) {
+            const uint32_t x = rblk + lo, dp = x / (uint32_t)L;
+            const int64_t p0 = pblk + dp;
+            const int r0 = (int)(x - dp * (uint32_t)L);
+            n0[q] = min(16, L - r0);
+            a0[q] = src + (int64_t)perm[p0] * L + r0;
+            if (n0[q] < 16 && p0 + 1 < n) a1[q] = src + (int64_t)perm[p0 + 1] * L;
+        }
     }
-    if (o + 16 <= total) *(uint4 *)(dst + o) = v;               // dst is 16-byte aligned (allocation base)
-    else {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        for (int k = 0; k < (int)(total - o); k++) dst[o + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    uint4 v[kGatherChunks];
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++)       // ... then all row loads ...
+        if (a0[q]) {
+            v[q] = load16_unaligned(a0[q], n0[q]);
+            if (a1[q]) v[q] = splice16(v[q], load16_unaligned(a1[q], 16 - n0[q]), n0[q]);
+        }
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++) {     // ... then the stores
+        const int64_t o = blk0 + ((int64_t)(q * 256 + threadIdx.x) << 4);
+        if (!a0[q]) continue;
+        if (o + 16 <= total) *(uint4 *)(dst + o) = v[q];        // dst is 16-byte aligned (allocation base)
+        else {
+            const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            for (int k = 0; k < (int)(total - o); k++) dst[o + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        }
     }
 }
 __global__ void gather_rows_small_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint32_t *__restrict__ perm,
@@ -219,52 +241,90 @@ __global__ void gather_rows_small_k(const uint8_t *__restrict__ src, uint8_t *__
     dst[o] = src[(int64_t)perm[p] * L + (o - p * L)];
 }
 
+// ---- per-read metadata word ---------------------------------------------------------------------------
+// Everything small the output side needs about a read, in one u64 so that output order costs ONE random
+// 8-byte gather per read: bits 0-36 name offset, 37-44 name length, 45-52 core level, 53-63 end marker.
+__host__ __device__ __forceinline__ uint64_t meta_pack(uint64_t name_off, uint32_t namelen, uint32_t lvl, uint32_t end) {
+    return (name_off & ((1ull << 37) - 1)) | ((uint64_t)(namelen & 0xffu) << 37) | ((uint64_t)(lvl & 0xffu) << 45) | ((uint64_t)(end & 0x7ffu) << 53);
+}
+__device__ __forceinline__ int64_t meta_name_off(uint64_t m) { return (int64_t)(m & ((1ull << 37) - 1)); }
+__device__ __forceinline__ int meta_namelen(uint64_t m) { return (int)((m >> 37) & 0xffu); }
+__device__ __forceinline__ int meta_lvl(uint64_t m) { return (int)((m >> 45) & 0xffu); }
+__device__ __forceinline__ int meta_end(uint64_t m) { return (int)(m >> 53); }
+
+__global__ void build_meta_k(int64_t n, const int64_t *__restrict__ name_off, const uint8_t *__restrict__ lvl,
+                             const uint16_t *__restrict__ endv, uint64_t *__restrict__ meta_in) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t a = 0; uint32_t nl = 0;
+    if (name_off) { a = (uint64_t)name_off[i]; nl = (uint32_t)(name_off[i + 1] - name_off[i]); }
+    meta_in[i] = meta_pack(a, nl, lvl[i], endv[i]);
+}
+__global__ void gather_meta_k(const uint64_t *__restrict__ meta_in, const uint32_t *__restrict__ perm, int64_t n,
+                              uint64_t *__restrict__ meta_s) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) meta_s[p] = (uint64_t)ldg_g64((const int64_t *)meta_in + perm[p]);
+}
+struct NameRecM {  // bytes of stream 0 for the p-th emitted read
+    const uint64_t *ms;
+    __device__ __forceinline__ uint64_t operator()(int64_t p) const { return (uint64_t)meta_namelen(ms[p]) + 1; }
+};
+struct ReadRecM {  // bytes of stream 1: packed rotated read + end marker (reads.cpp:128-130)
+    const uint64_t *ms; int L1, sz_meta;
+    __device__ __forceinline__ uint64_t operator()(int64_t p) const { return (uint64_t)(sz_read(L1 - meta_lvl(ms[p])) + sz_meta); }
+};
+
+struct EmitMParams {
+    const uint8_t *names; const uint32_t *packed; int PW;
+    const uint32_t *perm; const uint64_t *ms; const uint64_t *offN, *offR;
+    int64_t n; int L1, sz_meta;
+    uint8_t *oN, *oR;
+};
+
 // ---- stream 0: names, one thread per read --------------------------------------------------------------
-__global__ void emit_names_k(Emit2Params e) {
+__global__ void emit_names_m_k(EmitMParams e) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= e.n) return;
-    const uint32_t i = e.perm[p];
-    const int64_t a = e.name_off[i];
-    const int nl = (int)(e.offN[p + 1] - e.offN[p]) - 1;
+    const uint64_t m = e.ms[p];
+    const int64_t a = meta_name_off(m);
+    const int nl = meta_namelen(m);
     uint8_t *d = e.oN + e.offN[p];
     d[0] = (uint8_t)nl;                                                           // names.cpp:58
-    for (int k = 0; k < nl; k++) d[1 + k] = e.names[a + k];
+    for (int k = 0; k < nl; k++) d[1 + k] = (uint8_t)ldg_g64(e.names + a + k);
 }
 
-// ---- stream 1: rotated 2-bit reads + end marker, 16 lanes per read -------------------------------------
-__global__ void __launch_bounds__(256) emit_reads_k(Emit2Params e) {
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    if (p >= e.n) return;
-    const int h = threadIdx.x & 15;
-    const uint32_t i = e.perm[p];
+// ---- stream 1: rotated 2-bit reads + end marker, one thread per (read, 4 output bytes) ------------------
+__global__ void __launch_bounds__(256) emit_reads_m_k(EmitMParams e, uint32_t NW /* words per record, max */, int64_t n_threads) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    // t < 2^32 is guaranteed by the launcher when this 32-bit division is used
+    const uint32_t p = (uint32_t)t / NW, w = (uint32_t)t - p * NW;
+    const uint64_t m = e.ms[p];
     // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
-    uint32_t m = e.hsum[p];                              // exclusive head count: a head's own index, else one past
-    if (e.seg_pos[m] != (uint32_t)p) m -= 1;             // seg_pos has n_seg+1 entries (last = n)
-    const uint32_t r = e.seg_rank[m];
-    const int lv = r == (uint32_t)e.nb ? 0 : e.rank_level[r];
-    const int end = e.endv[i];
+    const int lv = meta_lvl(m), end = meta_end(m);
     const int tail = e.L1 - end, total = e.L1 - lv;
     const int nbytes = sz_read(total);
-    uint8_t *d = e.oR + e.seg_off[m] + (uint64_t)((uint32_t)p - e.seg_pos[m]) * e.seg_recsz[m];
-    const uint32_t *row = e.packed + (int64_t)i * e.PW;   // rows have 2 words of slack behind the last one
-    // one lane builds 16 rotated bases (4 output bytes): `a` of them come from behind the core, the
-    // rest from the front of the read; whatever lies past `total` is zero fill
-    for (int w = h; 4 * w < nbytes; w += 16) {
-        const int j0 = 16 * w;
+    const int recsz = nbytes + e.sz_meta;
+    if ((int)(4 * w) >= recsz) return;
+    uint8_t *d = e.oR + e.offR[p] + 4 * w;
+    uint32_t v = 0;
+    if ((int)(4 * w) < nbytes) {
+        // 16 rotated bases: `a` of them come from behind the core, the rest from the front of the read;
+        // whatever lies past `total` is zero fill
+        const uint32_t *row = e.packed + (int64_t)e.perm[p] * e.PW;   // rows have 2 words of slack behind the last one
+        const int j0 = 16 * (int)w;
         int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
         int nv = total - j0; nv = nv > 16 ? 16 : nv;
-        uint32_t v = 0;
         if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
         if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
         if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
-        const int nbw = nbytes - 4 * w;                   // bytes of this word that belong to the record
-        uint8_t *dw = d + 4 * w;
-        dw[0] = (uint8_t)(v >> 24);
-        if (nbw > 1) dw[1] = (uint8_t)(v >> 16);
-        if (nbw > 2) dw[2] = (uint8_t)(v >> 8);
-        if (nbw > 3) dw[3] = (uint8_t)v;
     }
-    if (h < e.sz_meta) d[nbytes + h] = (uint8_t)((uint32_t)end >> (8 * h));   // low bytes of int16 end, reads.cpp:130
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int b = 4 * (int)w + k;                          // byte index inside the record
+        if (b < nbytes) d[k] = (uint8_t)(v >> (24 - 8 * k));
+        else if (b < recsz) d[k] = (uint8_t)((uint32_t)end >> (8 * (b - nbytes)));   // low bytes of int16 end, reads.cpp:130
+    }
 }
 
 // ---- stream 4: mate 2 is packed without rotation (output_read(read2, dest, 0, 0), compress.cpp:696) ----
@@ -291,7 +351,7 @@ __global__ void emit_reads2_k(const uint8_t *__restrict__ seq2, const uint32_t *
 }
 
 // one meta record per segment: int32 id, int32 core, int64 tN, tR, tQ [, tR2, tQ2]   reads.cpp:160-176
-__global__ void meta2_k(SegTab t, int64_t n_seg, const uint64_t *__restrict__ offN, const int32_t *__restrict__ rank_node_id,
+__global__ void meta2_k(SegTab t, int64_t n_seg, const uint64_t *__restrict__ offN, const uint64_t *__restrict__ offR, const int32_t *__restrict__ rank_node_id,
                         const int32_t *__restrict__ rank_core, int nb, int L1, int L2, int use_names, int use_quals, int paired,
                         uint8_t *__restrict__ meta, int64_t *__restrict__ chunk_first /*[2][n_chunks] or null*/, int n_chunks) {
     int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,7 +365,7 @@ __global__ void meta2_k(SegTab t, int64_t n_seg, const uint64_t *__restrict__ of
     uint8_t *d = meta + m * (int64_t)(8 + 8 * nlen);
     int64_t v[5];
     v[0] = use_names ? (int64_t)(offN[p1] - offN[p0]) : 0;
-    v[1] = cnt * (int64_t)t.recsz[m];
+    v[1] = (int64_t)(offR[p1] - offR[p0]);
     v[2] = use_quals ? cnt * L1 : 0;
     v[3] = cnt * sz_read(L2);
     v[4] = use_quals ? cnt * L2 : 0;
