@@ -108,6 +108,12 @@ int scb_create(const char *const *cores, int32_t n_cores, const scb_config *cfg,
 /* Same, loading the set from disk: text (one core per whitespace-separated token, -P file,
  * reads.cpp:388-394) or patterns.bin records (reads.cpp:338-369); format is sniffed. */
 int scb_create_from_file(const char *path, const scb_config *cfg, scb_handle **out);
+/* Host-only: compiles the core set into the automaton tables without touching a device and reports
+ * their shape: states (trie nodes incl. root), buckets (distinct cores), where aho_output would emit
+ * the root bucket (== n_buckets unless some base starts no core), and each core's BFS node id - the
+ * "id" bin_dump writes (reads.cpp:166, 296). Needs no GPU; used by the CPU-side tests. */
+int scb_table_dryrun(const char *const *cores, int32_t n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *root_order_pos,
+                     int32_t *core_node_id);
 /* Number of cores / automaton states / whether the transition table is shared-memory resident. */
 int scb_table_info(const scb_handle *h, int32_t *n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *smem_resident);
 /* patterns[i] (reads.h:48): NUL-terminated core string by index, owned by the handle. */

@@ -58,6 +58,8 @@ def lib():
         L.orc_lifetime_count.restype = C.c_uint64
         L.orc_lifetime_count.argtypes = [C.c_void_p, C.c_int32]
         L.orc_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_core_node_id.restype = C.c_int32
+        L.orc_core_node_id.argtypes = [C.c_void_p, C.c_int32]
         L.orc_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -118,6 +120,9 @@ class Oracle:
         text = np.ascontiguousarray(text, dtype=np.uint8)
         n = lib().orc_candidates(self.h, _ptr(text), text.size, cap, _ptr(cc), _ptr(cp), _ptr(lv))
         return int(lv[0]), cc[:min(n, cap)].copy(), cp[:min(n, cap)].copy(), n
+
+    def core_node_id(self, core):
+        return lib().orc_core_node_id(self.h, core)
 
     @property
     def unbucketed(self):

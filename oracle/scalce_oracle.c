@@ -384,6 +384,16 @@ uint64_t orc_lifetime_count(orc *o, int32_t core) {
     return 0;
 }
 
+/* BFS node id (reads.cpp:296) of the node a core ends at - the "id" written to meta. */
+int32_t orc_core_node_id(orc *o, int32_t core) {
+    int32_t n = 0;
+    for (const char *c = o->cores[core]; *c != 0 && *c != '\n'; c++) {
+        /* the DFA is complete by now; walking a core from the root follows its own trie path */
+        n = o->nd[n].child[orc_getval((unsigned char)*c)];
+    }
+    return o->nd[n].id;
+}
+
 /* Helper for design experiments and scan-kernel unit parity (derived from reads.cpp:413-429, not a
  * reference function): the count-independent part of aho_search - the maximum level reached and
  * the distinct nodes of that level in order of first occurrence, with that first position.

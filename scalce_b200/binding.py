@@ -17,7 +17,7 @@ S_NAMES, S_READS, S_QUALS, S_META, S_READS2, S_QUALS2 = range(6)
 ROOT_ID = (1 << 30) - 1
 
 EXPORTS = [
-    "scb_abi_version", "scb_last_error", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
+    "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
     "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_reset_counts", "scb_destroy",
 ]
@@ -59,6 +59,7 @@ def load_library(path: str | None = None):
     L.scb_create.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.POINTER(ScbConfig), C.POINTER(C.c_void_p)]
     L.scb_create_from_file.argtypes = [C.c_char_p, C.POINTER(ScbConfig), C.POINTER(C.c_void_p)]
     L.scb_table_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    L.scb_table_dryrun.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]
     L.scb_core.restype = C.c_char_p
     L.scb_core.argtypes = [C.c_void_p, C.c_int32]
     L.scb_submit.argtypes = [C.c_void_p, C.POINTER(ScbBatch)]
@@ -89,6 +90,16 @@ class ScbError(RuntimeError):
 def _check(rc):
     if rc != 0:
         raise ScbError(rc, load_library().scb_last_error().decode(errors="replace"))
+
+
+def table_dryrun(cores):
+    """Host-only compile of a core set (no device needed): shape of the automaton and per-core node ids."""
+    enc = [c.encode() if isinstance(c, str) else c for c in cores]
+    arr = (C.c_char_p * len(enc))(*enc)
+    ns, nb, rp = C.c_int32(), C.c_int32(), C.c_int32()
+    ids = np.empty(len(enc), dtype=np.int32)
+    _check(load_library().scb_table_dryrun(arr, len(enc), C.byref(ns), C.byref(nb), C.byref(rp), ids.ctypes.data_as(C.c_void_p)))
+    return dict(n_states=ns.value, n_buckets=nb.value, root_order_pos=rp.value, core_node_id=ids)
 
 
 class FlushResult:

@@ -713,6 +713,22 @@ int scb_create_from_file(const char *path, const scb_config *cfg, scb_handle **o
     return scb::create_common(v, cfg, out);
 }
 
+int scb_table_dryrun(const char *const *cores, int32_t n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *root_order_pos,
+                     int32_t *core_node_id /* [n_cores] or NULL */) {
+    if (n_cores < 0 || (n_cores > 0 && !cores)) { scb::g_last_error = "bad core array"; return SCB_EINVAL; }
+    std::vector<std::string> v;
+    for (int32_t i = 0; i < n_cores; i++) v.emplace_back(cores[i] ? cores[i] : "");
+    scb::CoreTable t;
+    std::string err = scb::build_core_table(v, t);
+    if (!err.empty()) { scb::g_last_error = err; return SCB_EINVAL; }
+    if (n_states) *n_states = t.n_states;
+    if (n_buckets) *n_buckets = t.n_buckets;
+    if (root_order_pos) *root_order_pos = t.root_order_pos;
+    if (core_node_id)
+        for (int32_t i = 0; i < n_cores; i++) core_node_id[i] = t.rank_node_id[(size_t)t.core_to_rank[(size_t)i]];
+    return SCB_OK;
+}
+
 int scb_table_info(const scb_handle *h, int32_t *n_cores, int32_t *n_states, int32_t *n_buckets, int32_t *smem_resident) {
     if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
     if (n_cores) *n_cores = (int32_t)h->tab.cores.size();

@@ -96,6 +96,9 @@ def plant_cores(batch: FastqBatch, cores, seed=3, frac=0.5):
             continue
         p = rng.integers(0, L - c.size + 1)
         batch.seq[r, p:p + c.size] = c
+        # a planted base over a former 'N' must not keep quality 0 (the decompressor restores 'N' there)
+        q = batch.qual[r, p:p + c.size]
+        q[q == 33] = 35
     return batch
 
 
