@@ -1,0 +1,95 @@
+"""CPU suite, part 1: the oracle (oracle/scalce_oracle.c) against fixtures the UNMODIFIED reference
+CLI produced (tests/golden/*.npz, generator tests/make_golden.py), byte for byte."""
+import ast
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.gen_cores import make_cores
+from scalce_b200 import synth
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    meta = ast.literal_eval(z["meta"].tobytes().decode())
+    return z, meta
+
+
+def _inputs(z, meta):
+    if meta["store"] == "full":
+        cores = z["cores"].tobytes().decode().split("\n")
+        b = synth.FastqBatch(z["seq"], z["qual"], z["names"], z["name_off"],
+                             z["seq2"] if meta["paired"] else None, z["qual2"] if meta["paired"] else None)
+        return cores, b
+    cores = make_cores(meta["seed"], [tuple(x) for x in meta["spec"]])
+    b = synth.make_batch(meta["n"], meta["L"], seed=meta["seed"], paired=meta["paired"], L2=meta["L2"] or None, lower_frac=meta["lower"])
+    synth.plant_cores(b, cores, seed=meta["seed"] + 1, frac=0.5)
+    h = hashlib.sha256()
+    h.update("\n".join(cores).encode())
+    for a in (b.seq, b.qual, b.names, b.name_off, b.seq2, b.qual2):
+        if a is not None:
+            h.update(np.ascontiguousarray(a).tobytes())
+    if h.hexdigest() != meta["input_sha"]:
+        pytest.skip("numpy generator stream differs from the one the fixture was made with")
+    return cores, b
+
+
+def oracle_files(cores, b, meta):
+    off = orc.detect_phred_offset(b.qual)
+    q1 = orc.quality_payload(b.qual, b.seq, off)
+    q2 = orc.quality_payload(b.qual2, b.seq2, orc.detect_phred_offset(b.qual2)) if meta["paired"] else None
+    bucket = {"4G": 4 << 30, "1M": 1 << 20}[meta["bucket"]]
+    o = orc.Oracle(cores, meta["L"], meta["L2"], use_names=meta["use_names"], paired=meta["paired"], bucket_set_bytes=bucket)
+    o.submit(b.seq, q1, b.names, b.name_off, b.seq2, q2)
+    o.finish()
+    out = {}
+    for mate in range(1 + int(meta["paired"])):
+        fn, fr, fq = orc.assemble_container(o.stream(3), o.stream(0), o.stream(1), o.stream(2), cores, meta["L"], off,
+                                            use_names=meta["use_names"], library=b"lib", paired=meta["paired"], mate=mate,
+                                            reads2=o.stream(4), quals2=o.stream(5), L2=meta["L2"])
+        out[f"{mate + 1}n"], out[f"{mate + 1}r"], out[f"{mate + 1}q"] = fn, fr, fq
+    return o, out
+
+
+def test_fixtures_present():
+    assert len(GOLD) >= 7
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_matches_reference_cli(path, oracle_lib):
+    z, meta = _load(path)
+    assert meta["roundtrip_ok"], "fixture was not round-tripped by the reference decompressor"
+    cores, b = _inputs(z, meta)
+    o, files = oracle_files(cores, b, meta)
+    for k, data in files.items():
+        assert len(data) == meta["sizes"][k], f"{k}: size {len(data)} != reference {meta['sizes'][k]}"
+        assert hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{k}: bytes differ from the reference CLI output"
+        if meta["store"] == "full":
+            assert data == z["out_" + k].tobytes()
+    if meta["bucket"] == "1M":
+        assert o.n_chunks > 1   # the multi-chunk merge path (compress.cpp:68-198) is what these fixtures pin
+
+
+def test_oracle_against_live_reference_cli(tmp_path, oracle_lib):
+    """When oracle/_ref/scalce exists (build container), run it now on a fresh seed."""
+    if not os.path.exists(orc.REF_CLI):
+        pytest.skip("reference CLI not built here")
+    from oracle.gen_cores import write_text
+    spec = [(8, 128), (9, 64), (11, 32)]
+    cores = make_cores(911, spec)
+    b = synth.make_batch(3000, 80, seed=911, lower_frac=0.02)
+    synth.plant_cores(b, cores, seed=912, frac=0.5)
+    d = str(tmp_path)
+    write_text(d + "/cores.txt", cores)
+    synth.write_fastq(b, d + "/in_1.fastq")
+    orc.run_reference_cli(d + "/in_1.fastq", d + "/ref", d + "/cores.txt", tmpdir=d + "/tmp")
+    meta = dict(L=80, L2=0, paired=False, use_names=True, bucket="4G")
+    _, files = oracle_files(cores, b, meta)
+    for ext in "nrq":
+        assert files["1" + ext] == open(f"{d}/ref_1.scalce{ext}", "rb").read()
