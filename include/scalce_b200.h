@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SCB_ABI_VERSION 1
+#define SCB_ABI_VERSION 2
 
 #define SCB_OK 0
 #define SCB_EINVAL -1    /* bad argument / unsupported configuration */
@@ -146,6 +146,79 @@ int scb_stage_ms(const scb_handle *h, float *out, int32_t cap);
 int scb_reset_counts(scb_handle *h);
 /* Fixed-point rounds the parallel tie-break needed in the last flush (0 = sequential engine used). */
 int scb_resolve_rounds(const scb_handle *h);
+
+/* =====================================================================================================
+ * Sharded run: ONE flush whose input is the concatenation of the ranks' submissions in rank order
+ * (one handle per GPU, one process per GPU). The reference has no counterpart (single process); the
+ * contract is that concatenating the ranks' outputs in rank order gives, per flush chunk and per
+ * stream, exactly what ONE handle fed the whole input would have produced (= the reference at -T 1).
+ * The library does the per-GPU work; the caller moves bytes between ranks (NCCL all-gather of a few
+ * KB per resolve round, one all-to-all of the payload) - scalce_b200/shard.py is that caller.
+ * Call order on every rank:
+ *   scb_submit...                                    this rank's shard, in input order
+ *   scb_shard_scan                                   core scan (aho_search minus the populations)
+ *   scb_shard_sizes                                  rd.sz accounting; ranks in order, each passing
+ *                                                    (carry, chunk) on to the next (compress.cpp:702-713)
+ *   scb_shard_resolve_local  (first rank)            tie-break over its own shard, then
+ *   scb_shard_resolve_round  (the others, repeated)  one global fixed-point round per call, until a round
+ *                                                    other than the first changes nothing on any rank
+ *   scb_shard_finalize                               bucket / end marker per read, lifetime counts
+ *   scb_shard_bucket_hist -> all-reduce -> split of the bucket emission order into contiguous slices
+ *   scb_shard_pack -> all-to-all -> scb_shard_import
+ *   scb_shard_finish                                 stable sort + emit of the owned bucket slice
+ * Restrictions: the shared-memory resolve engine must apply (<= ~25k buckets). Every rank owns ALL
+ * flush chunks of its buckets, so emit_merged works per rank.
+ * ===================================================================================================== */
+
+/* Device arrays of one side of the exchange, destination-major (send) or source-major (receive); rows keep
+ * input order inside a destination/source. aux: one u64 per read (bucket rank | end << 24 | name length
+ * << 35 | flush chunk << 43); packed: 2-bit rows of packed_row_bytes; names: name bytes without length
+ * bytes. cnt_* are host arrays [n_ranks] owned by the handle (send side only). */
+typedef struct scb_shard_xfer {
+    int64_t n;
+    int64_t name_bytes;
+    const uint64_t *aux;
+    const uint8_t *packed, *qual1, *names, *seq2, *qual2;
+    const int64_t *cnt_reads, *cnt_name_bytes;
+    int32_t packed_row_bytes;
+    int32_t reserved;
+} scb_shard_xfer;
+
+/* enable = 1: runs the handle's work on the caller's CUDA stream (cudaStream_t; NULL = the legacy default
+ * stream) instead of its own, so that the caller's events and collectives order with it.
+ * enable = 0: back to the handle's own stream. */
+int scb_set_stream(scb_handle *h, void *cuda_stream, int32_t enable);
+/* Number of bucket columns a resolve histogram has: n_buckets + 1 (root last); tot arrays hold one more
+ * word (the changed count). Emission position of the root bucket in *root_order_pos. */
+int scb_shard_info(const scb_handle *h, int32_t *n_cols, int32_t *root_order_pos);
+/* Scan of everything pending (aho_search's walk, reads.cpp:413-429, without the population compare). */
+int scb_shard_scan(scb_handle *h, int64_t *n_local);
+/* rd.sz + sizeof(bin_node) accounting and flush-chunk ids numbered along the global order. */
+int scb_shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint64_t *carry_out, int32_t *chunk_out);
+/* Tie-break of a shard that starts the input order (populations = lifetime counts). tot_dev: device
+ * u32[n_cols + 1], receives the shard's bucket histogram (rank order) and 0 in the last word. */
+int scb_shard_resolve_local(scb_handle *h, uint32_t *tot_dev);
+/* One global round for a later shard. before_dev: device u32[n_cols] populations of all lower ranks'
+ * shards under the current global assignment (a guess in the first round); reads_before: their read
+ * count; first: 1 for the first round. tot_dev as above, last word = decisions that changed. */
+int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t reads_before, int32_t first, uint32_t *tot_dev);
+/* Commits the converged assignment. global_tot_dev: device u32[n_cols], bucket histogram summed over all
+ * ranks (adds to the lifetime counts of EVERY rank's handle); n_global: reads of the whole flush. */
+int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global);
+/* Local bucket histogram in emission order, device u32[n_cols] (overwritten). */
+int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev);
+/* Stable partition of the local reads by owner; split[g] = first emission position owned by rank g,
+ * split[0] = 0, split[n_ranks] = n_cols (host array). Fills *out with the send arrays. */
+int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
+/* Adopts the received arrays (caller-owned device memory, must stay valid until the next submit; the
+ * packed array needs 64 readable bytes past its last row). */
+int scb_shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global);
+/* Sort + emit of the owned slice; result as scb_flush (per-read arrays refer to the rank's INPUT shard,
+ * perm to the received order). */
+int scb_shard_finish(scb_handle *h, scb_result *out);
+/* Device milliseconds of the last scb_shard_* call (CUDA events on the handle's stream). */
+float scb_shard_last_ms(const scb_handle *h);
+
 /* aho_trie_free (reads.cpp:505-535). */
 void scb_destroy(scb_handle *h);
 

@@ -20,6 +20,8 @@ EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
     "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_reset_counts", "scb_destroy",
+    "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
+    "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
 ]
 
 
@@ -39,6 +41,12 @@ class ScbResult(C.Structure):
                 ("merged", C.c_void_p * N_STREAMS), ("merged_size", C.c_int64 * N_STREAMS),
                 ("bucket_id", C.c_void_p), ("core_idx", C.c_void_p), ("end", C.c_void_p), ("chunk", C.c_void_p),
                 ("perm", C.c_void_p), ("device_ms", C.c_float)]
+
+
+class ScbShardXfer(C.Structure):
+    _fields_ = [("n", C.c_int64), ("name_bytes", C.c_int64), ("aux", C.c_void_p), ("packed", C.c_void_p), ("qual1", C.c_void_p),
+                ("names", C.c_void_p), ("seq2", C.c_void_p), ("qual2", C.c_void_p), ("cnt_reads", C.POINTER(C.c_int64)),
+                ("cnt_name_bytes", C.POINTER(C.c_int64)), ("packed_row_bytes", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -76,6 +84,19 @@ def load_library(path: str | None = None):
     L.scb_resolve_rounds.argtypes = [C.c_void_p]
     L.scb_reset_counts.argtypes = [C.c_void_p]
     L.scb_destroy.argtypes = [C.c_void_p]
+    L.scb_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.scb_shard_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.scb_shard_scan.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.scb_shard_sizes.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    L.scb_shard_resolve_local.argtypes = [C.c_void_p, C.c_void_p]
+    L.scb_shard_resolve_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.scb_shard_finalize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.scb_shard_bucket_hist.argtypes = [C.c_void_p, C.c_void_p]
+    L.scb_shard_pack.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(ScbShardXfer)]
+    L.scb_shard_import.argtypes = [C.c_void_p, C.POINTER(ScbShardXfer), C.c_int32]
+    L.scb_shard_finish.argtypes = [C.c_void_p, C.POINTER(ScbResult)]
+    L.scb_shard_last_ms.restype = C.c_float
+    L.scb_shard_last_ms.argtypes = [C.c_void_p]
     if path is None:
         _lib = L
     return L
@@ -126,9 +147,10 @@ class FlushResult:
         _check(load_library().scb_copy_stream(self._tr._h, k, chunk, buf.ctypes.data_as(C.c_void_p), n))
         return buf[:n].tobytes()
 
-    def debug(self):
-        n = self.n_reads
-        arrs = [np.empty(n, dtype=np.int32) for _ in range(4)] + [np.empty(n, dtype=np.uint32)]
+    def debug(self, n_local=None):
+        """Per-read arrays in input order (of the rank's own shard after a sharded run: pass n_local) and perm."""
+        n = self.n_reads if n_local is None else n_local
+        arrs = [np.empty(n, dtype=np.int32) for _ in range(4)] + [np.empty(self.n_reads, dtype=np.uint32)]
         _check(load_library().scb_copy_debug(self._tr._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
         return dict(node_id=arrs[0], core=arrs[1], end=arrs[2], chunk=arrs[3], perm=arrs[4])
 

@@ -15,6 +15,7 @@
 #include "resolve_dense.cuh"
 #include "scan_smem.cuh"
 #include "emit2.cuh"
+#include "shard.cuh"
 
 namespace scb {
 long long g_launches = 0;
@@ -80,6 +81,7 @@ struct DevBuf {
         SCB_CUDA(cudaMallocAsync(&p, b, s));
         pooled = true;
     }
+    void borrow(void *ptr, size_t b) { release(); p = ptr; bytes = b; pooled = false; }   // caller-owned memory
     void release() {
         if (p && pooled) cudaFreeAsync(p, st);
         p = nullptr; bytes = 0; pooled = false;
@@ -117,7 +119,7 @@ using namespace scb;
 struct scb_handle {
     scb_config cfg;
     CoreTable tab;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_own = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t stage_ev[SCB_N_STAGES + 1] = {};
     float stage_ms[SCB_N_STAGES] = {};
@@ -142,6 +144,18 @@ struct scb_handle {
     bool smem_resident = false;
     uint64_t life_total = 0;   // reads ever submitted (bound on any lifetime count)
     int last_rounds = 0;       // fixed-point rounds of the last dense resolve
+    int64_t n_perm = 0;        // entries of perm (== n_last except after a sharded run)
+    // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
+    int sh_phase = 0;          // 0 idle, 1 scanned, 2 resolved (finalized), 3 sized, 4 packed, 5 imported
+    Arena::Mark sh_mark{0, 0}; // arena position after the arrays that survive the exchange
+    int64_t sh_n_local = 0;    // reads of this rank's input shard
+    int sh_W = 0, sh_grid = 0; // dense-resolve geometry
+    DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
+    DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
+    DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
+    std::vector<int64_t> sh_cnt_reads, sh_cnt_name_bytes;
+    DevBuf sh_name_off;        // import side: name offsets rebuilt from the lengths
+    float sh_ms = 0;           // device time of the last scb_shard_* call
 };
 
 namespace scb {
@@ -177,7 +191,8 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         cudaDeviceProp prop;
         SCB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
         if (prop.major < 10) { g_last_error = "device is not sm_100 class"; return SCB_ENODEVICE; }
-        SCB_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        SCB_CUDA(cudaStreamCreateWithFlags(&h->st_own, cudaStreamNonBlocking));
+        h->st = h->st_own;
         SCB_CUDA(cudaEventCreate(&h->ev0));
         SCB_CUDA(cudaEventCreate(&h->ev1));
         for (auto &e : h->stage_ev) SCB_CUDA(cudaEventCreate(&e));
@@ -266,6 +281,13 @@ static void gather_pending(scb_handle *h) {
     h->cur = std::move(c);
 }
 
+// dst row p <- src row perm[p], rows of L bytes (dst dense and 16-byte aligned)
+static void gather_rows_any(cudaStream_t st, const uint8_t *src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
+    if (n <= 0 || L <= 0) return;
+    if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
+    else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
+}
+
 // ---- emit one ordering ----------------------------------------------------------------------------------
 // keys: the sorted keys of this ordering; the segment id (chunk, bucket order) is their top seg_bits bits
 static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys, int seg_shift, int seg_bits, bool merged, EmitOut &o) {
@@ -316,10 +338,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     e.offN = offN.as<uint64_t>(); e.offR = offR.as<uint64_t>(); e.n = n; e.L1 = L1; e.sz_meta = sz_meta;
     e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>();
     uint8_t *oQ = o.data[2].as<uint8_t>(), *oR2 = o.data[4].as<uint8_t>(), *oQ2 = o.data[5].as<uint8_t>();
-    auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) {
-        if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
-        else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
-    };
+    auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) { gather_rows_any(st, src, dst, perm, n, L); };
     if (cfg.use_names) SCB_LAUNCH(emit_names_m_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
     {
         const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
@@ -333,6 +352,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         if (cfg.use_quals) gather_rows(c.qual2, oQ2, L2);
     }
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
+    SCB_CUDA(cudaMemsetAsync(cfirst.p, 0xff, (size_t)2 * std::max(nch, 1) * 8, st));   // -1 = chunk has no read here
     SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), offR.as<uint64_t>(),
                h->d_rank_node_id.as<int32_t>(), h->d_rank_core.as<int32_t>(), nb, L1, L2, cfg.use_names, cfg.use_quals, cfg.paired,
                o.data[3].as<uint8_t>(), merged ? (int64_t *)nullptr : cfirst.as<int64_t>(), nch);
@@ -341,6 +361,9 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         std::vector<int64_t> cf((size_t)2 * nch);
         SCB_CUDA(cudaMemcpyAsync(cf.data(), cfirst.p, cf.size() * 8, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));
+        // a chunk without reads (possible for a rank's bucket slice in a sharded run) is an empty slice
+        for (int ci = nch - 1; ci >= 0; ci--)
+            if (cf[ci] < 0) { cf[ci] = ci + 1 < nch ? cf[ci + 1] : n; cf[nch + ci] = ci + 1 < nch ? cf[nch + ci + 1] : (int64_t)nseg; }
         std::vector<uint64_t> on((size_t)nch, 0), orr((size_t)nch, 0);
         for (int ci = 0; ci < nch; ci++) {
             if (cfg.use_names) SCB_CUDA(cudaMemcpyAsync(&on[ci], offN.as<uint64_t>() + cf[ci], 8, cudaMemcpyDeviceToHost, st));
@@ -361,11 +384,13 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
 }
 
 // ---- the transform ---------------------------------------------------------------------------------------
-static void run_flush(scb_handle *h) {
+struct ArenaScope { ArenaScope(Arena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } };
+
+// sizes the flush slab and concatenates the pending batches into h->cur (call with the arena scope open)
+static void flush_begin(scb_handle *h, double extra_factor) {
     cudaStream_t st = h->st;
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
-    struct ArenaScope { ArenaScope(Arena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } };
     {   // size the slab for this flush before anything is carved from it
         int64_t n_est = 0, name_est = 0;
         for (auto &p : h->pending) { n_est += p.n; name_est += p.name_bytes; }
@@ -374,19 +399,25 @@ static void run_flush(scb_handle *h) {
         size_t est = (size_t)n_est * per_read + (size_t)name_est + (size_t)n_est + ((size_t)256 << 20);
         if (h->pending.size() > 1) est += (size_t)n_est * ((size_t)L1 * 2 + (size_t)L2 * 2 + 8) + (size_t)name_est;
         if (cfg.emit_merged) est += est / 2;
+        est = (size_t)((double)est * extra_factor);
         h->arena.reserve(est);
         h->arena.reset();
     }
-    ArenaScope arena_scope(&h->arena);
     gather_pending(h);
     const Pending &c = h->cur;
     const int64_t n = c.n;
     h->n_last = n;
-    const int nb = h->tab.n_buckets;
-    SCB_CUDA(cudaEventRecord(h->ev0, st));
-    SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
+}
 
-    // 1. scan: max level + ordered distinct candidates per read (+ the 2-bit packed copy of the reads)
+// 1. scan: max level + ordered distinct candidates per read (+ the 2-bit packed copy of the reads)
+static void stage_scan(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
     h->PW = (L1 + 15) / 16;
     h->packed.alloc((size_t)n * h->PW * 4 + 64, st);   // slack: emit reads up to 2 words past a row
     h->lvl.alloc((size_t)n, st);
@@ -446,81 +477,122 @@ static void run_flush(scb_handle *h) {
         }
     }
 
-    SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
-    // 2. resolve
+}
+
+// ---- dense resolve engine (resolve_dense.cuh): geometry, buffers, launches --------------------------------
+// Buffers live in the flush arena and are kept in the handle so that a sharded run can launch the kernel
+// once per global round. Returns false when the engine does not apply (too many buckets for shared
+// memory, counts that would overflow u32, or forced off).
+static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on any population after this flush */) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n;
+    const int nb1 = h->tab.n_buckets + 1;
+    int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 8));
+    const char *force = getenv("SCB_RESOLVE");
+    if (!(W >= 1 && n > 0 && reads_in_job < 0xffffffffull && !(force && !strcmp(force, "seq")))) return false;
+    int dev_sms = 0;
+    SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    const size_t smem = (size_t)W * nb1 * 8;
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
+    if (occ < 1) return false;
+    const int grid = std::min(dev_sms, 160);
+    const size_t max_sub = (size_t)grid * W;
+    h->sh_W = W; h->sh_grid = grid;
+    h->sh_sel.alloc((size_t)n * 2, st); h->sh_base.alloc((size_t)nb1 * 4, st);
+    h->sh_H.alloc(max_sub * nb1 * 4, st); h->sh_S.alloc(max_sub * nb1 * 4, st);
+    h->sh_Csum.alloc((size_t)grid * nb1 * 4, st); h->sh_Cpre.alloc((size_t)grid * nb1 * 4, st);
+    h->sh_changed.alloc((size_t)kRdMaxRounds * 4, st); h->sh_stat.alloc(8, st);
+    h->sh_tot.alloc((size_t)(nb1 + 1) * 4, st);
+    SCB_CUDA(cudaMemsetAsync(h->sh_sel.p, 0xff, (size_t)n * 2, st));
+    return true;
+}
+
+// one launch of the engine over blocks `blk` of the local reads; returns status (0 ok)
+static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<int64_t> &blk, uint32_t *tot_out) {
+    cudaStream_t st = h->st;
+    const int nb1 = h->tab.n_buckets + 1;
+    const int W = h->sh_W, grid = h->sh_grid;
+    const size_t smem = (size_t)W * nb1 * 8;
+    h->sh_blk.alloc(blk.size() * 8, st);
+    SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)(mode == 0 ? kRdMaxRounds : 1) * 4, st));
+    SCB_CUDA(cudaMemsetAsync(h->sh_stat.p, 0, 8, st));
+    RdParams rp;
+    rp.n = h->cur.n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
+    rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = h->sh_S.as<uint32_t>();
+    rp.Csum = h->sh_Csum.as<uint32_t>(); rp.Cpre = h->sh_Cpre.as<uint32_t>(); rp.changed = h->sh_changed.as<uint32_t>(); rp.blk = h->sh_blk.as<int64_t>();
+    rp.nblk = (int)blk.size() - 1; rp.nb1 = nb1; rp.W = W; rp.status = h->sh_stat.as<int>(); rp.rounds_out = h->sh_stat.as<int>() + 1;
+    rp.g0 = g0; rp.mode = mode; rp.tot_out = tot_out;
+    DevBuf dts;
+    const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
+    if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
+    rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
+    void *args[] = {&rp};
+    SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
+    g_launches++;
+    int stat[2] = {0, 0};
+    SCB_CUDA(cudaMemcpyAsync(stat, h->sh_stat.p, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->last_rounds = mode == 0 ? stat[1] : h->last_rounds + stat[1];
+    if (prof) {
+        std::vector<unsigned long long> ts(4096 * 8);
+        SCB_CUDA(cudaMemcpy(ts.data(), dts.p, ts.size() * 8, cudaMemcpyDeviceToHost));
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < stat[1] && r < 4096; r++) {
+            for (int k = 0; k < 6; k++) acc[k] += (double)(ts[r * 8 + k + 1] - ts[r * 8 + k]) * 1e-3;
+            fprintf(stderr, "round %3d len %9llu: P %.1f D %.1f E %.1f sync1 %.1f scan %.1f sync2 %.1f us\n", r, ts[r * 8 + 7],
+                    (ts[r * 8 + 1] - ts[r * 8]) * 1e-3, (ts[r * 8 + 2] - ts[r * 8 + 1]) * 1e-3, (ts[r * 8 + 3] - ts[r * 8 + 2]) * 1e-3,
+                    (ts[r * 8 + 4] - ts[r * 8 + 3]) * 1e-3, (ts[r * 8 + 5] - ts[r * 8 + 4]) * 1e-3, (ts[r * 8 + 6] - ts[r * 8 + 5]) * 1e-3);
+        }
+        fprintf(stderr, "resolve totals (us): P %.0f D %.0f E %.0f sync1 %.0f scan %.0f sync2 %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
+    }
+    return stat[0];
+}
+
+// geometric block schedule: block k+1 is as long as everything before it, earlier reads of the job included
+static std::vector<int64_t> dense_blocks(int64_t n, int64_t g0) {
+    std::vector<int64_t> blk;
+    blk.push_back(0);
+    const int64_t first = 4096;
+    while (blk.back() < n) { int64_t n0 = blk.back(); blk.push_back(std::min<int64_t>(n, std::max<int64_t>(2 * n0 + g0, n0 + first))); }
+    return blk;
+}
+
+// asg / end marker from the converged slots; counts the reads without a candidate into the root population
+static void dense_finalize(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n;
+    const int nb = h->tab.n_buckets;
+    SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
+               h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), h->sh_sel.as<uint16_t>(), nb, h->asg.as<uint32_t>(),
+               h->endv.as<uint16_t>(), h->d_life.as<unsigned long long>() + nb);
+}
+
+// 2. resolve: the stateful tie-break over the whole flush, this GPU owning the whole input order
+static void stage_resolve(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n;
+    const int nb = h->tab.n_buckets;
+    const int nb1 = nb + 1;
     h->asg.alloc((size_t)n * 4, st);
     h->endv.alloc((size_t)n * 2, st);
     unsigned long long root_before = 0, root_after = 0;
     SCB_CUDA(cudaMemcpyAsync(&root_before, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
     bool dense_done = false;
-    {
-        // dense engine: one u32 population counter per bucket per warp in shared memory
-        const int nb1 = nb + 1;
-        int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 8));
-        const char *force = getenv("SCB_RESOLVE");
-        bool want_dense = W >= 1 && n > 0 && (h->life_total + (uint64_t)n) < 0xffffffffull && !(force && !strcmp(force, "seq"));
-        if (want_dense) {
-            int dev_sms = 0;
-            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
-            size_t smem = (size_t)W * nb1 * 8;
-            SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int occ = 0;
-            SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
-            if (occ >= 1) {
-                const int grid = std::min(dev_sms, 160);
-                std::vector<int64_t> blk;
-                blk.push_back(0);
-                const int64_t first = 4096;
-                while (blk.back() < n) { int64_t n0 = blk.back(); blk.push_back(std::min<int64_t>(n, std::max<int64_t>(2 * n0, n0 + first))); }
-                const int nblk = (int)blk.size() - 1;
-                const size_t max_sub = (size_t)grid * W;
-                DevBuf sel((size_t)n * 2, st), base((size_t)nb1 * 4, st), H(max_sub * nb1 * 4, st), S(max_sub * nb1 * 4, st),
-                    Csum((size_t)grid * nb1 * 4, st), Cpre((size_t)grid * nb1 * 4, st), changed((size_t)kRdMaxRounds * 4, st),
-                    dblk(blk.size() * 8, st), dstat(8, st);
-                SCB_CUDA(cudaMemsetAsync(sel.p, 0xff, (size_t)n * 2, st));
-                SCB_CUDA(cudaMemsetAsync(changed.p, 0, (size_t)kRdMaxRounds * 4, st));
-                SCB_CUDA(cudaMemsetAsync(dstat.p, 0, 8, st));
-                SCB_CUDA(cudaMemcpyAsync(dblk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
-                SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), base.as<uint32_t>(), nb1);
-                RdParams rp;
-                rp.n = n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
-                rp.sel = sel.as<uint16_t>(); rp.base = base.as<uint32_t>(); rp.H = H.as<uint32_t>(); rp.S = S.as<uint32_t>();
-                rp.Csum = Csum.as<uint32_t>(); rp.Cpre = Cpre.as<uint32_t>(); rp.changed = changed.as<uint32_t>(); rp.blk = dblk.as<int64_t>();
-                rp.nblk = nblk; rp.nb1 = nb1; rp.W = W; rp.status = dstat.as<int>(); rp.rounds_out = dstat.as<int>() + 1;
-                DevBuf dts;
-                const bool prof = getenv("SCB_RESOLVE_PROF") != nullptr;
-                if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
-                rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
-                void *args[] = {&rp};
-                SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
-                g_launches++;
-                int stat[2] = {0, 0};
-                SCB_CUDA(cudaMemcpyAsync(stat, dstat.p, 8, cudaMemcpyDeviceToHost, st));
-                SCB_CUDA(cudaStreamSynchronize(st));
-                h->last_rounds = stat[1];
-                if (prof) {
-                    std::vector<unsigned long long> ts(4096 * 8);
-                    SCB_CUDA(cudaMemcpy(ts.data(), dts.p, ts.size() * 8, cudaMemcpyDeviceToHost));
-                    double acc[6] = {0, 0, 0, 0, 0, 0};
-                    for (int r = 0; r < stat[1] && r < 4096; r++) {
-                        for (int k = 0; k < 6; k++) acc[k] += (double)(ts[r * 8 + k + 1] - ts[r * 8 + k]) * 1e-3;
-                        fprintf(stderr, "round %3d len %9llu: P %.1f D %.1f E %.1f sync1 %.1f scan %.1f sync2 %.1f us\n", r, ts[r * 8 + 7],
-                                (ts[r * 8 + 1] - ts[r * 8]) * 1e-3, (ts[r * 8 + 2] - ts[r * 8 + 1]) * 1e-3, (ts[r * 8 + 3] - ts[r * 8 + 2]) * 1e-3,
-                                (ts[r * 8 + 4] - ts[r * 8 + 3]) * 1e-3, (ts[r * 8 + 5] - ts[r * 8 + 4]) * 1e-3, (ts[r * 8 + 6] - ts[r * 8 + 5]) * 1e-3);
-                    }
-                    fprintf(stderr, "resolve totals (us): P %.0f D %.0f E %.0f sync1 %.0f scan %.0f sync2 %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
-                }
-                if (stat[0] == 0) {
-                    SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
-                    SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
-                               h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), sel.as<uint16_t>(), nb, h->asg.as<uint32_t>(),
-                               h->endv.as<uint16_t>(), h->d_life.as<unsigned long long>() + nb);
-                    dense_done = true;
-                }
-            }
+    h->last_rounds = 0;
+    if (dense_setup(h, h->life_total + (uint64_t)n)) {
+        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40);
+        SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
+        if (dense_launch(h, 0, g0, dense_blocks(n, g0), nullptr) == 0) {
+            SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->sh_base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
+            dense_finalize(h);
+            dense_done = true;
         }
     }
     if (!dense_done) {
+        h->last_rounds = 0;
         size_t smem = ((size_t)nb + 1) * 12;
         if (smem <= 200 * 1024) {
             SCB_CUDA(cudaFuncSetAttribute(resolve_seq_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -535,13 +607,36 @@ static void run_flush(scb_handle *h) {
     }
     h->life_total += (uint64_t)n;
     SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
+}
 
+// per-read metadata word for the output side (needs lvl, endv, name offsets)
+static void stage_meta(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
     h->meta_in.alloc((size_t)n * 8, st);
     if (n > 0)
         SCB_LAUNCH(build_meta_k, (unsigned)cdiv(n, 256), 256, 0, st, n, cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->lvl.as<uint8_t>(),
                    h->endv.as<uint16_t>(), h->meta_in.as<uint64_t>());
-    SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
-    // 3. sizes -> flush chunks
+
+}
+
+// 3. sizes -> flush chunks (compress.cpp:702, 708-713)
+static void stage_chunks(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     {
         int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
         RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
@@ -567,9 +662,18 @@ static void run_flush(scb_handle *h) {
             h->chunk.release();
         }
     }
-    if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
 
-    SCB_CUDA(cudaEventRecord(h->stage_ev[3], st));
+}
+
+// 4-6. sort by (chunk, bucket order, suffix key), refine ties, emit the streams
+static void stage_sort_emit(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
     // 4. sort by (chunk, bucket order, key prefix), stable in input order
     const int nch = h->n_chunks > 0 ? h->n_chunks : 1;
     const int seg_bits = ceil_log2((uint64_t)nch * (uint64_t)(nb + 1));
@@ -662,20 +766,326 @@ static void run_flush(scb_handle *h) {
         emit_order(h, h->perm_m.as<uint32_t>(), a, 0, ob, true, h->merged);
     }
 
-    SCB_CUDA(cudaEventRecord(h->stage_ev[7], st));
-    // 7. per-read arrays in input order
-    h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
+}
+
+// 7. per-read arrays in input order
+static void stage_debug(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
+    if (h->sh_phase == 0) { h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st); }
     if (n > 0) {
         SCB_LAUNCH(debug_arrays_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->asg.as<uint32_t>(), nb, h->d_rank_node_id.as<int32_t>(),
                    h->d_rank_core.as<int32_t>(), h->dbg_bucket.as<int32_t>(), h->dbg_core.as<int32_t>());
         SCB_LAUNCH(widen_u16_k, (unsigned)cdiv(n, 256), 256, 0, st, h->endv.as<uint16_t>(), n, h->dbg_end.as<int32_t>());
-        if (h->n_chunks > 1) SCB_CUDA(cudaMemcpyAsync(h->dbg_chunk.p, h->chunk.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        if (h->chunk.p) SCB_CUDA(cudaMemcpyAsync(h->dbg_chunk.p, h->chunk.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         else SCB_CUDA(cudaMemsetAsync(h->dbg_chunk.p, 0, (size_t)n * 4, st));
     }
+
+}
+
+// =====================================================================================================
+// sharded run (include/scalce_b200.h "Sharded run")
+// =====================================================================================================
+struct ShardTimer {   // device time of one scb_shard_* call
+    scb_handle *h;
+    explicit ShardTimer(scb_handle *hh) : h(hh) { cudaEventRecord(h->ev0, h->st); }
+    void stop() {
+        SCB_CUDA(cudaEventRecord(h->ev1, h->st));
+        SCB_CUDA(cudaStreamSynchronize(h->st));
+        SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev0, h->ev1));
+    }
+};
+
+static void shard_scan(scb_handle *h) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    h->sh_phase = 0;
+    flush_begin(h, 2.0);   // room for the send arrays; the receive side reuses the slab after the exchange
+    const int64_t n = h->cur.n;
+    h->sh_n_local = n;
+    h->n_perm = 0;
+    // per-read arrays of the INPUT shard survive the exchange: carve them first and remember the mark
+    h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
+    h->sh_mark = h->arena.mark();
+    ShardTimer tm(h);
+    stage_scan(h);
+    h->asg.alloc((size_t)n * 4, st);
+    h->endv.alloc((size_t)n * 2, st);
+    tm.stop();
+    h->last_rounds = 0;
+    h->sh_phase = 1;
+}
+
+static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint64_t *carry_out, int32_t *chunk_out) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    ShardTimer tm(h);
+    const int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
+    RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+    h->sh_sizes.alloc((size_t)(n + 1) * 8, st);
+    exclusive_scan<uint64_t>(rs, n, h->sh_sizes.as<uint64_t>(), h->sh_sizes.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    const uint64_t max_rd = 256 + (uint64_t)sz_read(L1) + L1 + sz_read(L2) + L2 + 40;
+    uint64_t cap64 = (uint64_t)n * max_rd / cfg.bucket_set_bytes + 2;
+    if (cap64 > (uint64_t)n + 1) cap64 = (uint64_t)n + 1;
+    if (cap64 > (1u << 24)) throw CudaError{"bucket_set_bytes too small for this many reads (more than 2^24 flush chunks)"};
+    const int cap = (int)cap64;
+    DevBuf bounds((size_t)cap * 4, st), dout(16, st);
+    SCB_LAUNCH(chunk_bounds_carry_k, 1, 1, 0, st, h->sh_sizes.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, carry_in,
+               bounds.as<uint32_t>(), cap, dout.as<unsigned long long>());
+    unsigned long long o[2] = {0, 0};
+    SCB_CUDA(cudaMemcpyAsync(o, dout.p, 16, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)o[0] > cap) throw CudaError{"internal: chunk capacity exceeded"};
+    if ((uint64_t)chunk_in + o[0] >= kAuxMaxChunks) throw CudaError{"too many flush chunks for the sharded run (>= 2^21)"};
+    h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
+    if (n > 0) SCB_LAUNCH(chunk_ids_global_k, (unsigned)cdiv(n, 256), 256, 0, st, bounds.as<uint32_t>(), (int)o[0], (uint32_t)chunk_in, n, h->chunk.as<uint32_t>());
+    tm.stop();
+    *carry_out = o[1];
+    *chunk_out = chunk_in + (int32_t)o[0];
+}
+
+static void shard_need_dense(scb_handle *h) {
+    if (!dense_setup(h, h->life_total + (uint64_t)h->cur.n))
+        throw CudaError{"the sharded run needs the shared-memory resolve engine (core set too large, or SCB_RESOLVE=seq)"};
+}
+
+static void shard_resolve_local(scb_handle *h, uint32_t *tot_dev) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const int64_t n = h->cur.n;
+    const int nb1 = h->tab.n_buckets + 1;
+    ShardTimer tm(h);
+    if (n == 0) {
+        SCB_CUDA(cudaMemsetAsync(tot_dev, 0, (size_t)(nb1 + 1) * 4, st));
+    } else {
+        shard_need_dense(h);
+        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40);
+        SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
+        if (dense_launch(h, 0, g0, dense_blocks(n, g0), nullptr) != 0) throw CudaError{"resolve: round cap hit"};
+        SCB_LAUNCH(sub_life_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sh_base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb1, tot_dev);
+    }
+    tm.stop();
+}
+
+static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t reads_before, int first, uint32_t *tot_dev) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const int64_t n = h->cur.n;
+    const int nb1 = h->tab.n_buckets + 1;
+    ShardTimer tm(h);
+    if (n == 0) {
+        SCB_CUDA(cudaMemsetAsync(tot_dev, 0, (size_t)(nb1 + 1) * 4, st));
+    } else {
+        if (first) shard_need_dense(h);
+        if ((h->life_total + (uint64_t)reads_before + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
+        SCB_LAUNCH(add_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), before_dev, nb1, h->sh_base.as<uint32_t>());
+        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40) + reads_before;
+        std::vector<int64_t> blk{0, n};
+        if (dense_launch(h, first ? 1 : 2, g0, blk, tot_dev) != 0) throw CudaError{"resolve: round cap hit"};
+    }
+    tm.stop();
+}
+
+static void shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const int64_t n = h->cur.n;
+    const int nb = h->tab.n_buckets;
+    ShardTimer tm(h);
+    unsigned long long root_before = 0, root_after = 0;
+    SCB_CUDA(cudaMemcpyAsync(&root_before, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    if (n > 0) dense_finalize(h);
+    SCB_LAUNCH(life_add_k, (unsigned)cdiv(nb + 1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), global_tot_dev, nb);
+    SCB_CUDA(cudaMemcpyAsync(&root_after, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    h->life_total += (uint64_t)n_global;
+    stage_debug(h);   // per-read arrays of the input shard (chunk ids are the global ones)
+    tm.stop();
+    if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
+    h->sh_phase = 2;
+}
+
+static void shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n;
+    const int nb = h->tab.n_buckets;
+    ShardTimer tm(h);
+    SCB_CUDA(cudaMemsetAsync(hist_dev, 0, (size_t)(nb + 1) * 4, st));
+    if (n > 0) {
+        const size_t smem = (size_t)(nb + 1) * 4;
+        const int grid = (int)std::min<int64_t>(cdiv(n, 512 * 8), 148 * 4);
+        if (smem <= 160 * 1024) {
+            SCB_CUDA(cudaFuncSetAttribute(bucket_hist_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCB_LAUNCH((bucket_hist_k<true>), grid, 512, smem, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, hist_dev);
+        } else {
+            SCB_LAUNCH((bucket_hist_k<false>), grid, 512, 0, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, hist_dev);
+        }
+    }
+    tm.stop();
+}
+
+static void shard_pack(scb_handle *h, const int64_t *split, int G, scb_shard_xfer *out) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const int nb = h->tab.n_buckets;
+    ShardTimer tm(h);
+    SplitTab t;
+    t.G = G;
+    for (int g = 0; g <= G; g++) t.s[g] = (uint32_t)split[g];
+    // stable partition by owner: one 8-bit radix pass over the destination
+    DevBuf k0((size_t)std::max<int64_t>(n, 1) * 8, st), k1((size_t)std::max<int64_t>(n, 1) * 8, st), v1((size_t)std::max<int64_t>(n, 1) * 4, st);
+    h->sh_perm.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
+    DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
+    SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
+    uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
+    uint32_t *va = h->sh_perm.as<uint32_t>(), *vb = v1.as<uint32_t>();
+    if (n > 0) {
+        SCB_LAUNCH(dest_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, t, ka, va);
+        radix_sort_pairs(&ka, &va, &kb, &vb, n, 0, std::max(1, ceil_log2((uint64_t)G)), ws, st);
+    }
+    const uint32_t *perm = va;
+    DevBuf dfirst((size_t)(G + 1) * 8, st), dnb((size_t)(G + 1) * 8, st);
+    SCB_LAUNCH(dest_bounds_k, 1, kMaxRanks + 1, 0, st, ka, n, G, dfirst.as<int64_t>());
+    // aux words, then everything else in the same order
+    h->sh_aux.alloc((size_t)std::max<int64_t>(n, 1) * 8, st);
+    if (n > 0)
+        SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+                   cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
+    h->sh_noff.alloc((size_t)(n + 1) * 8, st);
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+    exclusive_scan<uint64_t>(AuxNameLen{h->sh_aux.as<uint64_t>()}, n, h->sh_noff.as<uint64_t>(), h->sh_noff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, h->sh_noff.as<uint64_t>(), dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
+    std::vector<int64_t> first((size_t)G + 1), nbytes((size_t)G + 1);
+    SCB_CUDA(cudaMemcpyAsync(first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->sh_cnt_reads.assign((size_t)G, 0); h->sh_cnt_name_bytes.assign((size_t)G, 0);
+    for (int g = 0; g < G; g++) { h->sh_cnt_reads[g] = first[g + 1] - first[g]; h->sh_cnt_name_bytes[g] = nbytes[g + 1] - nbytes[g]; }
+    const int64_t name_bytes = nbytes[(size_t)G];
+    const int prow = h->PW * 4;
+    h->sh_packed.alloc((size_t)n * prow + 64, st);
+    gather_rows_any(st, h->packed.as<uint8_t>(), h->sh_packed.as<uint8_t>(), perm, n, prow);
+    if (cfg.use_quals) { h->sh_qual1.alloc((size_t)n * L1 + 16, st); gather_rows_any(st, c.qual1, h->sh_qual1.as<uint8_t>(), perm, n, L1); }
+    if (cfg.use_names) {
+        h->sh_names.alloc((size_t)name_bytes + 16, st);
+        if (n > 0) SCB_LAUNCH(pack_names_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, c.name_off, c.names, h->sh_noff.as<uint64_t>(), h->sh_names.as<uint8_t>());
+    }
+    if (cfg.paired) {
+        h->sh_seq2.alloc((size_t)n * L2 + 16, st); gather_rows_any(st, c.seq2, h->sh_seq2.as<uint8_t>(), perm, n, L2);
+        if (cfg.use_quals) { h->sh_qual2.alloc((size_t)n * L2 + 16, st); gather_rows_any(st, c.qual2, h->sh_qual2.as<uint8_t>(), perm, n, L2); }
+    }
+    tm.stop();
+    memset(out, 0, sizeof *out);
+    out->n = n; out->name_bytes = cfg.use_names ? name_bytes : 0;
+    out->aux = h->sh_aux.as<uint64_t>(); out->packed = h->sh_packed.as<uint8_t>();
+    out->qual1 = cfg.use_quals ? h->sh_qual1.as<uint8_t>() : nullptr;
+    out->names = cfg.use_names ? h->sh_names.as<uint8_t>() : nullptr;
+    out->seq2 = cfg.paired ? h->sh_seq2.as<uint8_t>() : nullptr;
+    out->qual2 = (cfg.paired && cfg.use_quals) ? h->sh_qual2.as<uint8_t>() : nullptr;
+    out->cnt_reads = h->sh_cnt_reads.data(); out->cnt_name_bytes = h->sh_cnt_name_bytes.data();
+    out->packed_row_bytes = prow;
+    h->sh_phase = 4;
+}
+
+static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0];
+    const int nb = h->tab.n_buckets;
+    const int64_t n = in->n;
+    h->PW = (L1 + 15) / 16;
+    if (in->packed_row_bytes != h->PW * 4) throw CudaError{"import: packed row size does not match the read length"};
+    if (n >= (1ll << 31)) throw CudaError{"import: more than 2^31-1 reads on one rank"};
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->arena.rewind(h->sh_mark);   // everything of the scan/resolve side is dead now (the send arrays were delivered)
+    ShardTimer tm(h);
+    Pending imp;
+    imp.n = n; imp.borrowed = true;
+    imp.qual1 = in->qual1; imp.names = in->names; imp.seq2 = in->seq2; imp.qual2 = in->qual2; imp.name_bytes = in->name_bytes;
+    h->packed.borrow((void *)in->packed, (size_t)n * h->PW * 4);
+    h->asg.alloc((size_t)std::max<int64_t>(n, 1) * 4, st); h->endv.alloc((size_t)std::max<int64_t>(n, 1) * 2, st); h->lvl.alloc((size_t)std::max<int64_t>(n, 1), st);
+    h->n_chunks = n_chunks_global;
+    if (n_chunks_global > 1) h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st); else h->chunk.release();
+    if (n > 0)
+        SCB_LAUNCH(unpack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, in->aux, n, nb, h->d_rank_level.as<uint8_t>(), h->asg.as<uint32_t>(),
+                   h->endv.as<uint16_t>(), h->lvl.as<uint8_t>(), n_chunks_global > 1 ? h->chunk.as<uint32_t>() : (uint32_t *)nullptr);
+    if (cfg.use_names) {
+        h->sh_name_off.alloc((size_t)(n + 1) * 8, st);
+        DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+        exclusive_scan<uint64_t>(AuxNameLen{in->aux}, n, h->sh_name_off.as<uint64_t>(), h->sh_name_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        imp.name_off = h->sh_name_off.as<int64_t>();
+    }
+    h->cur = std::move(imp);
+    h->n_perm = n;
+    tm.stop();
+    h->sh_phase = 5;
+}
+
+static void shard_finish(scb_handle *h) {
+    ArenaScope arena_scope(&h->arena);
+    ShardTimer tm(h);
+    stage_meta(h);
+    stage_sort_emit(h);
+    tm.stop();
+    h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
+}
+
+// ---- the transform on one GPU ------------------------------------------------------------------------------
+static void run_flush(scb_handle *h) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    h->sh_phase = 0;
+    flush_begin(h, 1.0);
+    h->n_perm = h->cur.n;
+    SCB_CUDA(cudaEventRecord(h->ev0, st));
+    SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
+    stage_scan(h);
+    SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
+    stage_resolve(h);
+    stage_meta(h);
+    SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
+    stage_chunks(h);
+    SCB_CUDA(cudaEventRecord(h->stage_ev[3], st));
+    stage_sort_emit(h);
+    SCB_CUDA(cudaEventRecord(h->stage_ev[7], st));
+    stage_debug(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[8], st));
     SCB_CUDA(cudaEventRecord(h->ev1, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k < SCB_N_STAGES; k++) SCB_CUDA(cudaEventElapsedTime(&h->stage_ms[k], h->stage_ev[k], h->stage_ev[k + 1]));
+}
+
+static void fill_result(scb_handle *h, scb_result *out) {
+    out->n_reads = h->cur.n;
+    out->n_chunks = h->n_chunks;
+    out->n_buckets_nonempty = (int32_t)(h->cfg.emit_merged && h->n_chunks > 1 ? h->merged.n_seg : (h->n_chunks <= 1 ? h->chunked.n_seg : 0));
+    const bool alias = !(h->cfg.emit_merged && h->n_chunks > 1);
+    for (int k = 0; k < SCB_N_STREAMS; k++) {
+        out->data[k] = h->chunked.data[k].as<uint8_t>();
+        out->chunk_off[k] = h->chunked.chunk_off[k].data();
+        if (h->cfg.emit_merged) {
+            const EmitOut &m = alias ? h->chunked : h->merged;
+            out->merged[k] = m.data[k].as<uint8_t>();
+            out->merged_size[k] = m.size[k];
+        }
+    }
+    out->bucket_id = h->dbg_bucket.as<int32_t>(); out->core_idx = h->dbg_core.as<int32_t>();
+    out->end = h->dbg_end.as<int32_t>(); out->chunk = h->dbg_chunk.as<int32_t>();
+    out->perm = h->perm.as<uint32_t>();
 }
 
 }  // namespace scb
@@ -815,24 +1225,101 @@ int scb_flush(scb_handle *h, scb_result *out) {
     SCB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     out->device_ms = ms;
     SCB_CATCH
-    out->n_reads = h->n_last;
-    out->n_chunks = h->n_chunks;
-    out->n_buckets_nonempty = (int32_t)(h->cfg.emit_merged && h->n_chunks > 1 ? h->merged.n_seg : (h->n_chunks <= 1 ? h->chunked.n_seg : 0));
-    const bool alias = !(h->cfg.emit_merged && h->n_chunks > 1);
-    for (int k = 0; k < SCB_N_STREAMS; k++) {
-        out->data[k] = h->chunked.data[k].as<uint8_t>();
-        out->chunk_off[k] = h->chunked.chunk_off[k].data();
-        if (h->cfg.emit_merged) {
-            const scb::EmitOut &m = alias ? h->chunked : h->merged;
-            out->merged[k] = m.data[k].as<uint8_t>();
-            out->merged_size[k] = m.size[k];
-        }
-    }
-    out->bucket_id = h->dbg_bucket.as<int32_t>(); out->core_idx = h->dbg_core.as<int32_t>();
-    out->end = h->dbg_end.as<int32_t>(); out->chunk = h->dbg_chunk.as<int32_t>();
-    out->perm = h->perm.as<uint32_t>();
+    scb::fill_result(h, out);
     return SCB_OK;
 }
+
+int scb_set_stream(scb_handle *h, void *cuda_stream, int32_t enable) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->st);
+    h->st = enable ? (cudaStream_t)cuda_stream : h->st_own;
+    return SCB_OK;
+}
+
+int scb_shard_info(const scb_handle *h, int32_t *n_cols, int32_t *root_order_pos) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    if (n_cols) *n_cols = h->tab.n_buckets + 1;
+    if (root_order_pos) *root_order_pos = h->tab.root_order_pos;
+    return SCB_OK;
+}
+
+#define SCB_SHARD_ENTER(min_phase)                                                                         \
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }                                     \
+    if (h->sh_phase < (min_phase)) { scb::g_last_error = "sharded run: call order violated"; return SCB_ESTATE; } \
+    SCB_TRY                                                                                                \
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+
+int scb_shard_scan(scb_handle *h, int64_t *n_local) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    if ((uint32_t)h->tab.n_buckets + 1 >= scb::kAuxMaxBuckets) { scb::g_last_error = "sharded run: more than 2^24-2 buckets"; return SCB_EINVAL; }
+    if (h->pending.empty()) h->pending.emplace_back();
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::shard_scan(h);
+    SCB_CATCH
+    if (n_local) *n_local = h->sh_n_local;
+    return SCB_OK;
+}
+int scb_shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint64_t *carry_out, int32_t *chunk_out) {
+    if (!carry_out || !chunk_out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(1)
+    scb::shard_sizes(h, carry_in, chunk_in, carry_out, chunk_out);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_resolve_local(scb_handle *h, uint32_t *tot_dev) {
+    SCB_SHARD_ENTER(1)
+    scb::shard_resolve_local(h, tot_dev);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t reads_before, int32_t first, uint32_t *tot_dev) {
+    SCB_SHARD_ENTER(1)
+    scb::shard_resolve_round(h, before_dev, reads_before, first, tot_dev);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
+    SCB_SHARD_ENTER(1)
+    if (!h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_finalize"; return SCB_ESTATE; }
+    scb::shard_finalize(h, global_tot_dev, n_global);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
+    SCB_SHARD_ENTER(2)
+    scb::shard_bucket_hist(h, hist_dev);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
+    if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(2)
+    if (split[0] != 0 || split[n_ranks] != h->tab.n_buckets + 1) { scb::g_last_error = "split must cover [0, n_cols]"; return SCB_EINVAL; }
+    for (int g = 0; g < n_ranks; g++) if (split[g] > split[g + 1]) { scb::g_last_error = "split must be non-decreasing"; return SCB_EINVAL; }
+    scb::shard_pack(h, split, n_ranks, out);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global) {
+    if (!in || in->n < 0 || n_chunks_global < 0) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(4)
+    scb::shard_import(h, in, n_chunks_global);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_finish(scb_handle *h, scb_result *out) {
+    if (!out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    memset(out, 0, sizeof *out);
+    SCB_SHARD_ENTER(5)
+    scb::shard_finish(h);
+    out->device_ms = h->sh_ms;
+    SCB_CATCH
+    scb::fill_result(h, out);
+    return SCB_OK;
+}
+float scb_shard_last_ms(const scb_handle *h) { return h ? h->sh_ms : 0.f; }
 
 int scb_copy_stream(scb_handle *h, int32_t stream, int32_t chunk, void *dst, int64_t dst_bytes) {
     if (!h || stream < 0 || stream >= SCB_N_STREAMS || (!dst && dst_bytes > 0)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
@@ -859,13 +1346,13 @@ int scb_copy_debug(scb_handle *h, int32_t *bucket_id, int32_t *core_idx, int32_t
     if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
     SCB_TRY
     SCB_CUDA(cudaSetDevice(h->cfg.device));
-    size_t b = (size_t)h->n_last * 4;
-    if (b) {
-        if (bucket_id) SCB_CUDA(cudaMemcpyAsync(bucket_id, h->dbg_bucket.p, b, cudaMemcpyDeviceToHost, h->st));
-        if (core_idx) SCB_CUDA(cudaMemcpyAsync(core_idx, h->dbg_core.p, b, cudaMemcpyDeviceToHost, h->st));
-        if (end) SCB_CUDA(cudaMemcpyAsync(end, h->dbg_end.p, b, cudaMemcpyDeviceToHost, h->st));
-        if (chunk) SCB_CUDA(cudaMemcpyAsync(chunk, h->dbg_chunk.p, b, cudaMemcpyDeviceToHost, h->st));
-        if (perm) SCB_CUDA(cudaMemcpyAsync(perm, h->perm.p, b, cudaMemcpyDeviceToHost, h->st));
+    const size_t b = (size_t)h->n_last * 4, bp = (size_t)h->n_perm * 4;
+    {
+        if (bucket_id && b) SCB_CUDA(cudaMemcpyAsync(bucket_id, h->dbg_bucket.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (core_idx && b) SCB_CUDA(cudaMemcpyAsync(core_idx, h->dbg_core.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (end && b) SCB_CUDA(cudaMemcpyAsync(end, h->dbg_end.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (chunk && b) SCB_CUDA(cudaMemcpyAsync(chunk, h->dbg_chunk.p, b, cudaMemcpyDeviceToHost, h->st));
+        if (perm && bp) SCB_CUDA(cudaMemcpyAsync(perm, h->perm.p, bp, cudaMemcpyDeviceToHost, h->st));
     }
     SCB_CUDA(cudaStreamSynchronize(h->st));
     SCB_CATCH
@@ -913,7 +1400,7 @@ void scb_destroy(scb_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
-    cudaStream_t st = h->st;
+    cudaStream_t st = h->st_own;
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
     h->arena.destroy();

@@ -41,6 +41,16 @@ struct RdParams {
     int *status;                  // 0 ok, 1 round cap hit
     int *rounds_out;
     unsigned long long *tstamps;  // optional [rounds][8] globaltimer stamps of CTA 0 (profiling aid)
+    // reads that precede blk[0] in the job (earlier flushes, and in a sharded run the lower ranks' shards):
+    // only the first-round extrapolation looks at it
+    int64_t g0;
+    // 0: all blocks, each iterated to its fixed point (one GPU owns the whole input order)
+    // 1: ONE round over block 0 from extrapolated start counts; 2: ONE round from the histograms the previous
+    //    launch left in H / Cpre. Modes 1-2 are the sharded run: `base` is supplied per round by the caller
+    //    (populations of everything before this shard under the current global assignment) and is not
+    //    modified; tot_out[0..nb1) receives this shard's bucket histogram, tot_out[nb1] the changed count.
+    int mode;
+    uint32_t *tot_out;
 };
 
 __device__ __forceinline__ uint32_t lanemask_ge() {
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
         const int k = (ns + ncta - 1) / ncta;                 // subtiles per CTA (<= W)
         const int nact = (ns + k - 1) / k;                    // CTAs with work
         const int t_lo = c * k, t_hi = min(ns, t_lo + k);
-        bool first = true;
+        bool first = p.mode != 2;
         while (true) {
             // ---- P: start counts of my subtiles, straight into the warps' shared-memory counters ----
             // first round of a block: no histogram of the block exists yet; start from the populations
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             for (int col = threadIdx.x; col < nb1 && kl > 0; col += blockDim.x) {
                 const uint32_t b0 = p.base[col];
                 if (first) {
-                    for (int tl = 0; tl < kl; tl++) sm_cnt[(size_t)tl * nb1 + col] = b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, n0);
+                    for (int tl = 0; tl < kl; tl++) sm_cnt[(size_t)tl * nb1 + col] = b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0);
                 } else {
                     uint32_t hv[kRdMaxWarps];
 #pragma unroll
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                 uint32_t tot = 0;
                 if (first) {
                     for (int tl = 0; tl < kl; tl++) {
-                        const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - (b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, n0));
+                        const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - (b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0));
                         p.H[(size_t)(t_lo + tl) * nb1 + col] = hn;
                         tot += hn;
                     }
@@ -253,7 +263,10 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                         if (cc < nact) p.Cpre[(size_t)cc * nb1 + col] = carry + inc - v[q];
                         carry += __shfl_sync(0xffffffffu, inc, 31);
                     }
-                    if (done && l == 0) p.base[col] += carry;
+                    if (l == 0) {
+                        if (p.mode != 0) p.tot_out[col] = carry;
+                        else if (done) p.base[col] += carry;
+                    }
                 }
             }
             RD_STAMP(5);
@@ -261,6 +274,10 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             grid.sync();
             RD_STAMP(6);
             if (p.tstamps && blockIdx.x == 0 && threadIdx.x == 0 && round < 4096) p.tstamps[round * 8 + 7] = (unsigned long long)len;
+            if (p.mode != 0) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) { p.tot_out[nb1] = chg; *p.rounds_out = 1; }
+                return;
+            }
             round++;
             first = false;
             if (done) break;

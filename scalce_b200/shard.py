@@ -1,10 +1,29 @@
-"""Host-side sharding helpers for the one-process-per-GPU launch (torchrun).
+"""Sharded (multi-GPU) run of the boosting transform: one process per GPU, reads sharded as
+contiguous input slices, results bit-identical to one GPU fed the whole input.
 
-Reads shard across ranks as contiguous input slices: rank g owns
-[bounds[g], bounds[g+1]); mates travel with mate 1. Timing is reported as the maximum over
-ranks, throughput as total units / that maximum.
+The library (include/scalce_b200.h, "Sharded run") does all per-GPU work; this module is the
+plumbing between ranks:
+  * flush-chunk numbering: a (carry, chunk) pair handed from rank to rank,
+  * tie-break: rank 0 resolves its shard alone, then all later shards iterate ONE global fixed
+    point together - per round each rank re-decides its reads from the populations of everything
+    before it under the current global assignment and the ranks all-gather their bucket histograms
+    (n_buckets+2 words each); the run stops at the first round (other than the first) in which no
+    read on any rank changed, which proves the assignment is the sequential one,
+  * exchange: all-reduce of the bucket histogram, split of the bucket emission order into
+    contiguous slices balanced by reads, one all-to-all per payload array over NCCL,
+  * each rank then sorts and emits its slice: rank-order concatenation of the ranks' streams is,
+    per flush chunk, the single-GPU (= reference -T 1) stream.
+
+Comm back-ends: TorchComm (torch.distributed: NCCL on GPUs, gloo for the CPU tests of the host
+logic) and LoopbackComm (ranks are threads of one process sharing one GPU; used to test the
+whole sharded path on a single-GPU box).
 """
 from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
 
 
 def shard_bounds(n: int, world: int):
@@ -33,3 +52,312 @@ def sum_over_ranks(values, dist=None, device=None):
     t = torch.tensor(list(values), dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [float(x) for x in t]
+
+
+def balanced_split(hist, world: int):
+    """Splits the bucket emission order [0, len(hist)) into `world` contiguous slices with about equal
+    read counts. Returns split[world+1], split[0] = 0, split[world] = len(hist); rank g owns
+    [split[g], split[g+1]). A bucket is never divided (its reads must be sorted together)."""
+    hist = np.asarray(hist, dtype=np.int64)
+    ncols = int(hist.shape[0])
+    total = int(hist.sum())
+    cum = np.cumsum(hist)
+    split = [0]
+    for g in range(1, world):
+        target = (total * g) // world
+        # first bucket whose inclusive cumulative count exceeds the target starts rank g's slice ... unless the
+        # previous slice would then be empty while this bucket alone overshoots: keep boundaries monotone
+        k = int(np.searchsorted(cum, target, side="right"))
+        k = min(max(k, split[-1]), ncols)
+        split.append(k)
+    split.append(ncols)
+    return split
+
+
+def chain_chunks(sizes_fn, comm):
+    """Flush-chunk numbering along the global order: ranks take turns, each passing (carry, chunk) on.
+    sizes_fn(carry_in, chunk_in) -> (carry_out, chunk_out) is this rank's scb_shard_sizes.
+    Returns the global number of flush chunks."""
+    carry, chunk = 0, 0
+    for g in range(comm.world):
+        if g == comm.rank:
+            carry, chunk = sizes_fn(carry, chunk)
+        carry, chunk = comm.bcast_host([int(carry), int(chunk)], src=g)
+    return chunk + (1 if carry > 0 else 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# communication back-ends
+# ---------------------------------------------------------------------------------------------
+class TorchComm:
+    """torch.distributed plumbing (NCCL for device tensors; works on gloo/CPU for the host-logic tests)."""
+
+    def __init__(self, dist, device):
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.device = device
+
+    def allgather(self, t):
+        import torch
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def allgather_host(self, ints):
+        import torch
+        t = torch.tensor(list(ints), dtype=torch.int64, device=self.device)
+        return self.allgather(t).cpu().tolist()
+
+    def bcast_host(self, ints, src):
+        import torch
+        t = torch.tensor(list(ints), dtype=torch.int64, device=self.device)
+        self.dist.broadcast(t, src=src)
+        return t.cpu().tolist()
+
+    def all_to_all_bytes(self, send, send_counts, recv_counts, slack=0):
+        """send: uint8 tensor laid out destination-major; counts in bytes. Returns the receive tensor
+        (source-major) with `slack` extra bytes allocated past the end."""
+        import torch
+        total = int(sum(recv_counts))
+        buf = torch.empty(total + slack, dtype=torch.uint8, device=send.device)
+        self.dist.all_to_all_single(buf[:total], send[: int(sum(send_counts))], [int(x) for x in recv_counts], [int(x) for x in send_counts])
+        return buf
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+class _LoopbackShared:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class LoopbackComm:
+    """`world` ranks as threads of ONE process (one GPU): collectives are shared-memory hand-offs and
+    device-to-device copies. Same interface as TorchComm, so the orchestration code is the same."""
+
+    def __init__(self, shared: _LoopbackShared, rank: int, device):
+        self.s = shared
+        self.rank = rank
+        self.world = shared.world
+        self.device = device
+
+    @staticmethod
+    def make(world, device):
+        sh = _LoopbackShared(world)
+        return [LoopbackComm(sh, r, device) for r in range(world)]
+
+    def _exchange(self, obj):
+        self.s.slots[self.rank] = obj
+        self.s.barrier.wait()
+        got = list(self.s.slots)
+        self.s.barrier.wait()
+        return got
+
+    def allgather(self, t):
+        import torch
+        torch.cuda.synchronize() if t.is_cuda else None
+        return torch.stack(self._exchange(t.clone()))
+
+    def allgather_host(self, ints):
+        return [list(x) for x in self._exchange(list(ints))]
+
+    def bcast_host(self, ints, src):
+        return list(self._exchange(list(ints))[src])
+
+    def all_to_all_bytes(self, send, send_counts, recv_counts, slack=0):
+        import torch
+        if send.is_cuda:
+            torch.cuda.synchronize()
+        self.s.slots[self.rank] = (send, [int(x) for x in send_counts])
+        self.s.barrier.wait()
+        total = int(sum(recv_counts))
+        buf = torch.empty(total + slack, dtype=torch.uint8, device=send.device)
+        o = 0
+        for src in range(self.world):
+            t, cnts = self.s.slots[src]
+            a = int(sum(cnts[: self.rank]))
+            n = cnts[self.rank]
+            assert n == int(recv_counts[src])
+            buf[o:o + n] = t[a:a + n]
+            o += n
+        if send.is_cuda:
+            torch.cuda.synchronize()
+        self.s.barrier.wait()   # senders may release their buffers only after every receiver copied
+        return buf
+
+    def barrier(self):
+        self.s.barrier.wait()
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded transform
+# ---------------------------------------------------------------------------------------------
+class _DevPtr:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _dev_bytes(ptr, nbytes, device):
+    import torch
+    if nbytes <= 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
+
+
+class ShardedTransform:
+    """One rank of a sharded run. `transform` is this rank's BoostTransform (its device = this rank's GPU);
+    submit this rank's slice of the input to it as usual, then call flush() on every rank."""
+
+    def __init__(self, transform, comm, use_torch_stream=True):
+        self.t = transform
+        self.comm = comm
+        self.stats = {}
+        self._keep = None
+        if use_torch_stream:
+            import torch
+            from .binding import _check, load_library
+            with torch.cuda.device(transform.cfg.device):
+                s = torch.cuda.current_stream().cuda_stream
+            _check(load_library().scb_set_stream(transform._h, C.c_void_p(s), 1))
+
+    def flush(self):
+        import torch
+        from .binding import FlushResult, ScbResult, ScbShardXfer, _check, load_library
+        L = load_library()
+        h = self.t._h
+        cfg = self.t.cfg
+        comm = self.comm
+        G, r = comm.world, comm.rank
+        dev = torch.device("cuda", cfg.device)
+        L1, L2 = cfg.read_length[0], cfg.read_length[1]
+        ms = {}
+
+        def lap(name):
+            ms[name] = ms.get(name, 0.0) + float(L.scb_shard_last_ms(h))
+
+        ncols_c, rootpos_c = C.c_int32(), C.c_int32()
+        _check(L.scb_shard_info(h, C.byref(ncols_c), C.byref(rootpos_c)))
+        ncols = ncols_c.value
+
+        # ---- scan -------------------------------------------------------------------------------------
+        n_local = C.c_int64()
+        _check(L.scb_shard_scan(h, C.byref(n_local)))
+        lap("scan")
+        ns = [x[0] for x in comm.allgather_host([n_local.value])]
+        before = [0]
+        for x in ns:
+            before.append(before[-1] + x)
+        n_global = before[-1]
+
+        # ---- flush chunks along the global order ------------------------------------------------------------
+        def sizes(carry, chunk):
+            co, ko = C.c_uint64(), C.c_int32()
+            _check(L.scb_shard_sizes(h, carry, chunk, C.byref(co), C.byref(ko)))
+            lap("chunks")
+            return co.value, ko.value
+        n_chunks = chain_chunks(sizes, comm)
+
+        # ---- tie-break -------------------------------------------------------------------------------------
+        tot = torch.zeros(ncols + 1, dtype=torch.int32, device=dev)   # u32 bit patterns
+        if r == 0:
+            _check(L.scb_shard_resolve_local(h, C.c_void_p(tot.data_ptr())))
+            lap("resolve")
+        torch.cuda.synchronize(dev)
+        allt = comm.allgather(tot)
+        rounds = 0
+        if G > 1:
+            first = True
+            while True:
+                if r > 0:
+                    if first:   # guess: rank 0's histogram scaled to the reads before this shard (exact for rank 1)
+                        if ns[0] > 0:
+                            bf = (allt[0, :ncols].to(torch.int64) * before[r] // ns[0]).to(torch.int32)
+                        else:
+                            bf = torch.zeros(ncols, dtype=torch.int32, device=dev)
+                    else:
+                        bf = allt[:r, :ncols].sum(0, dtype=torch.int64).to(torch.int32)
+                    bf = bf.contiguous()
+                    torch.cuda.synchronize(dev)
+                    _check(L.scb_shard_resolve_round(h, C.c_void_p(bf.data_ptr()), before[r], 1 if first else 0, C.c_void_p(tot.data_ptr())))
+                    lap("resolve")
+                torch.cuda.synchronize(dev)
+                allt = comm.allgather(tot)
+                rounds += 1
+                changed = int(allt[1:, ncols].to(torch.int64).sum().item())
+                if not first and changed == 0:
+                    break
+                first = False
+        gtot = allt[:, :ncols].sum(0, dtype=torch.int64).to(torch.int32).contiguous()
+        torch.cuda.synchronize(dev)
+        _check(L.scb_shard_finalize(h, C.c_void_p(gtot.data_ptr()), n_global))
+        lap("finalize")
+
+        # ---- bucket-range split ----------------------------------------------------------------------------
+        hist = torch.zeros(ncols, dtype=torch.int32, device=dev)
+        _check(L.scb_shard_bucket_hist(h, C.c_void_p(hist.data_ptr())))
+        lap("hist")
+        torch.cuda.synchronize(dev)
+        ghist = comm.allgather(hist).to(torch.int64).sum(0).cpu().numpy()
+        split = balanced_split(ghist, G)
+        split_c = (C.c_int64 * (G + 1))(*split)
+        x = ScbShardXfer()
+        _check(L.scb_shard_pack(h, split_c, G, C.byref(x)))
+        lap("pack")
+
+        # ---- exchange ---------------------------------------------------------------------------------------
+        cr = [int(x.cnt_reads[g]) for g in range(G)]
+        cn = [int(x.cnt_name_bytes[g]) for g in range(G)]
+        mat = comm.allgather_host(cr + cn)
+        rr = [mat[s][r] for s in range(G)]
+        rn = [mat[s][G + r] for s in range(G)]
+        n_recv, nb_recv = sum(rr), sum(rn)
+        prow = x.packed_row_bytes
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        keep = {}
+
+        def xchg(name, ptr, row, slack=0):
+            send = _dev_bytes(ptr, x.n * row, dev)
+            keep[name] = comm.all_to_all_bytes(send, [c * row for c in cr], [c * row for c in rr], slack=slack)
+        xchg("aux", x.aux, 8)
+        xchg("packed", x.packed, prow, slack=64)
+        if cfg.use_quals:
+            xchg("qual1", x.qual1, L1)
+        if cfg.use_names:
+            send = _dev_bytes(x.names, x.name_bytes, dev)
+            keep["names"] = comm.all_to_all_bytes(send, cn, rn, slack=16)
+        if cfg.paired:
+            xchg("seq2", x.seq2, L2)
+            if cfg.use_quals:
+                xchg("qual2", x.qual2, L2)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms["exchange"] = ev0.elapsed_time(ev1)
+
+        # ---- sort + emit of the owned slice --------------------------------------------------------------------
+        y = ScbShardXfer()
+        y.n, y.name_bytes, y.packed_row_bytes = n_recv, nb_recv, prow
+        y.aux = keep["aux"].data_ptr()
+        y.packed = keep["packed"].data_ptr()
+        y.qual1 = keep["qual1"].data_ptr() if "qual1" in keep else None
+        y.names = keep["names"].data_ptr() if "names" in keep else None
+        y.seq2 = keep["seq2"].data_ptr() if "seq2" in keep else None
+        y.qual2 = keep["qual2"].data_ptr() if "qual2" in keep else None
+        _check(L.scb_shard_import(h, C.byref(y), n_chunks))
+        lap("import")
+        res = ScbResult()
+        _check(L.scb_shard_finish(h, C.byref(res)))
+        lap("emit")
+        self._keep = keep   # the received arrays back the result until the next flush
+        self.stats = dict(ms=ms, rounds=rounds, n_local=n_local.value, n_recv=n_recv, n_global=n_global, n_chunks=n_chunks,
+                          split=split, sent_bytes=int(sum((8 + prow + (L1 if cfg.use_quals else 0) + ((L2 + (L2 if cfg.use_quals else 0)) if cfg.paired else 0)) * c
+                                                          for g, c in enumerate(cr) if g != r) + sum(c for g, c in enumerate(cn) if g != r)))
+        out = FlushResult(self.t, res)
+        out.n_local = n_local.value
+        return out

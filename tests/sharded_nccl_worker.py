@@ -1,0 +1,61 @@
+"""torchrun worker: the sharded path over NCCL, checked on rank 0 against the oracle over the whole input.
+Launched by tests/test_gpu_sharded_nccl.py (and usable by hand under gpurun --gpus N)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from tests import util
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+    L = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    bsb = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 21)
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from scalce_b200.binding import BoostTransform
+    from scalce_b200.shard import ShardedTransform, TorchComm, shard_bounds
+    cores, b, q1, q2, _ = util.make_case(n, L, seed=77)
+    bd = shard_bounds(n, world)
+    a, z = bd[rank], bd[rank + 1]
+    t = BoostTransform(cores, L, 0, bucket_set_bytes=bsb, device=local, emit_merged=True)
+    t.submit(b.seq[a:z], q1[a:z], b.names, b.name_off[a:z + 1])
+    st = ShardedTransform(t, TorchComm(dist, torch.device("cuda", local)))
+    res = st.flush()
+    mine = dict(dbg=res.debug(res.n_local), n_chunks=res.n_chunks, unb=t.unbucketed, stats=st.stats,
+                streams={(k, c): res.stream(k, c) for k in range(4) for c in list(range(res.n_chunks)) + [-1]})
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=bsb)
+        dbg_o = o.debug()
+        for k in ("node_id", "core", "end", "chunk"):
+            got = np.concatenate([g["dbg"][k] for g in gathered])
+            if not np.array_equal(dbg_o[k], got):
+                print(f"MISMATCH per-read {k}"); ok = False
+        for g in gathered:
+            ok &= g["n_chunks"] == o.n_chunks
+        for c in list(range(o.n_chunks)) + [-1]:
+            for k in range(4):
+                want = o.stream(k, c)
+                got = b"".join(g["streams"][(k, c)] for g in gathered)
+                if want != got:
+                    print(f"MISMATCH chunk {c} stream {k}: {len(want)} vs {len(got)}"); ok = False
+        ok &= o.unbucketed == sum(g["unb"] for g in gathered)
+        print("rounds", gathered[0]["stats"]["rounds"], "chunks", o.n_chunks, "split", gathered[0]["stats"]["split"])
+        print("SHARDED_NCCL_OK" if ok else "SHARDED_NCCL_FAIL")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

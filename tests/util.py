@@ -76,3 +76,67 @@ def _first_diff(a, b):
     x = np.frombuffer(a[:n], dtype=np.uint8) != np.frombuffer(b[:n], dtype=np.uint8)
     nz = np.nonzero(x)[0]
     return int(nz[0]) if nz.size else n
+
+
+def run_sharded_loopback(cores, b, q1, q2, world, *, use_names=True, paired=False, use_quals=True, bucket_set_bytes=4 << 30,
+                         emit_merged=True, bounds=None, device=0):
+    """The sharded path with `world` ranks as threads of this process on ONE GPU (LoopbackComm).
+    Returns [(transform, sharded, result)] per rank."""
+    import threading
+    from scalce_b200.binding import BoostTransform
+    from scalce_b200.shard import LoopbackComm, ShardedTransform, shard_bounds
+    n = b.seq.shape[0]
+    L1 = b.seq.shape[1]
+    L2 = b.seq2.shape[1] if paired else 0
+    bounds = bounds or shard_bounds(n, world)
+    comms = LoopbackComm.make(world, device)
+    out = [None] * world
+    errs = []
+
+    def worker(r):
+        try:
+            t = BoostTransform(cores, L1, L2, use_names=use_names, paired=paired, use_quals=use_quals,
+                               bucket_set_bytes=bucket_set_bytes, emit_merged=emit_merged, device=device)
+            a, z = bounds[r], bounds[r + 1]
+            if z > a:
+                t.submit(b.seq[a:z], q1[a:z] if (use_quals and q1 is not None) else None, b.names, b.name_off[a:z + 1],
+                         b.seq2[a:z] if paired else None, q2[a:z] if (paired and use_quals and q2 is not None) else None)
+            st = ShardedTransform(t, comms[r])
+            out[r] = (t, st, st.flush())
+        except BaseException as e:   # noqa: BLE001 - unblock the other ranks, then re-raise in the caller
+            errs.append(e)
+            comms[r].s.barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    if errs:
+        real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    return out
+
+
+def assert_sharded_same(o, ranks, paired=False, check_merged=True):
+    """Rank-order concatenation of the ranks' outputs == the oracle over the whole input."""
+    dbg_o = o.debug()
+    dbg = [res.debug(res.n_local) for _, _, res in ranks]
+    for k in ("node_id", "core", "end", "chunk"):
+        got = np.concatenate([d[k] for d in dbg])
+        bad = np.nonzero(dbg_o[k] != got)[0]
+        assert bad.size == 0, f"per-read {k} differs at {bad[:5]}: oracle {dbg_o[k][bad[:5]]} sharded {got[bad[:5]]}"
+    for _, _, res in ranks:
+        assert res.n_chunks == o.n_chunks, (res.n_chunks, o.n_chunks)
+    streams = [0, 1, 2, 3] + ([4, 5] if paired else [])
+    for c in range(o.n_chunks):
+        for k in streams:
+            a = o.stream(k, c)
+            g = b"".join(res.stream(k, c) for _, _, res in ranks)
+            assert a == g, f"chunk {c} stream {k}: oracle {len(a)} B, sharded {len(g)} B, first diff {_first_diff(a, g)}"
+    if check_merged:
+        for k in streams:
+            a = o.stream(k, -1)
+            g = b"".join(res.stream(k, -1) for _, _, res in ranks)
+            assert a == g, f"merged stream {k}: oracle {len(a)} B, sharded {len(g)} B, first diff {_first_diff(a, g)}"
+    assert o.unbucketed == sum(t.unbucketed for t, _, _ in ranks)
