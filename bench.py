@@ -228,8 +228,28 @@ def main():
     torch.cuda.synchronize()
 
     tr = BoostTransform(cores, L, device=local, emit_merged=False)
+    sharded = None
+    if world > 1:
+        # the global input is the concatenation of the ranks' batches in rank order; results are the single-GPU
+        # (= reference -T 1) order of that input, each rank emitting a contiguous slice of the bucket order
+        from scalce_b200.shard import ShardedTransform, TorchComm
+        sharded = ShardedTransform(tr, TorchComm(dist, torch.device("cuda", local)))
+
+    def one_step_sharded():
+        tr.reset_counts()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.submit_device(N, seq.data_ptr(), qual.data_ptr(), names.data_ptr(), name_off.data_ptr())
+        sharded.flush()
+        e1.record()
+        torch.cuda.synchronize()
+        st = dict(sharded.stats["ms"])
+        st["_rounds"] = sharded.stats["rounds"]
+        return e0.elapsed_time(e1), st, tr.kernel_launches
 
     def one_step():
+        if sharded is not None:
+            return one_step_sharded()
         # one compression job per step: same handle (automaton + device workspace), populations reset
         tr.reset_counts()
         tr.submit_device(N, seq.data_ptr(), qual.data_ptr(), names.data_ptr(), name_off.data_ptr())
@@ -283,7 +303,11 @@ def main():
             t1 = time.perf_counter()
             t = BoostTransform(cores, L, device=local, emit_merged=False)
             t.submit(h_seq.reshape(N, L), h_qual.reshape(N, L), h_names, h_off)
-            r = t.flush()
+            if world > 1:
+                from scalce_b200.shard import ShardedTransform, TorchComm
+                r = ShardedTransform(t, TorchComm(dist, torch.device("cuda", local))).flush()
+            else:
+                r = t.flush()
             sizes = [r.chunk_off[k][-1] for k in range(6)]
             if outbuf is None:
                 outbuf = [torch.empty(max(sz, 1), dtype=torch.uint8).pin_memory() for sz in sizes]
@@ -319,6 +343,8 @@ def main():
     stage_bytes = {  # algorithmic bytes per read of each stage (DESIGN.md "kernels")
         "scan": L + 8, "resolve": 16, "chunks": 8, "sort": 24, "ties": 0,
         "emit": 2 * L + 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + L + 4, "merged": 0, "arrays": 16,
+        # sharded run: pack + exchange move the payload once each (aux word, packed row, quality row, name)
+        "finalize": 8, "hist": 4, "pack": 2 * (8 + 40 + L + NAME_BYTES), "exchange": 2 * (8 + 40 + L + NAME_BYTES), "import": 16,
     }
     ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
@@ -340,7 +366,10 @@ def main():
         "warmup": a.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "bases_per_s": value * L,
         "config": {"workload": workload, "reads_per_gpu": N, "read_length": L, "l2": "inputs (>= 15 GB per step) far exceed the 126 MB L2",
-                   "timing": "CUDA events on the library stream around scb_flush; one handle, bucket populations reset between steps", "multi_gpu": "independent shards, no exchange"},
+                   "timing": ("CUDA events on the library stream around scb_flush; one handle, bucket populations reset between steps" if world == 1 else
+                              "CUDA events on the rank's stream (library work and NCCL collectives are ordered on it) around submit + sharded flush, max over ranks"),
+                   "multi_gpu": ("n/a" if world == 1 else "contiguous input shards; joint exact tie-break (all-gather of bucket histograms per round), "
+                                 "bucket-range all-to-all of packed reads + qualities + names over NCCL; output = single-GPU order of the concatenated input")},
         "roofline": roof, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(out))

@@ -210,6 +210,29 @@ int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev);
 /* Stable partition of the local reads by owner; split[g] = first emission position owned by rank g,
  * split[0] = 0, split[n_ranks] = n_cols (host array). Fills *out with the send arrays. */
 int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
+/* Fused pack + exchange over peer memory (the production path; scb_shard_pack + a caller-side all-to-all is the
+ * staged alternative):
+ *   scb_shard_partition   owner of every local read, per-owner counts (out->cnt_*), aux words and names staged
+ *   (ranks all-gather the counts; every rank sizes its receive arrays and publishes them)
+ *   scb_shard_recv_reserve  persistent receive arrays of this rank (cudaMalloc; grown with headroom). need_bytes
+ *                         / ptrs are indexed 0 aux, 1 packed, 2 qual1, 3 names, 4 seq2, 5 qual2; *changed = 1 when
+ *                         any array moved (its IPC handle must be re-published)
+ *   scb_ipc_export / scb_ipc_open / scb_ipc_close   CUDA IPC plumbing for those arrays (64-byte handles)
+ *   scb_shard_send        row gathers that write straight into the owners' receive arrays: peers[g] holds owner
+ *                         g's arrays as mapped in THIS process and the row / name-byte offset at which this
+ *                         rank's reads start there. Returns when this rank's writes are complete; a barrier over
+ *                         the ranks then makes every receive array complete.
+ * followed by scb_shard_import of the rank's own receive arrays. */
+typedef struct scb_shard_peer {
+    void *aux, *packed, *qual1, *names, *seq2, *qual2;
+    int64_t row_off, name_off;
+} scb_shard_peer;
+int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
+int scb_shard_recv_reserve(scb_handle *h, const int64_t *need_bytes, void **ptrs, int32_t *changed);
+int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers);
+int scb_ipc_export(scb_handle *h, const void *dev_ptr, uint8_t *handle64);
+int scb_ipc_open(scb_handle *h, const uint8_t *handle64, void **out);
+int scb_ipc_close(scb_handle *h, void *peer_ptr);
 /* Adopts the received arrays (caller-owned device memory, must stay valid until the next submit; the
  * packed array needs 64 readable bytes past its last row). */
 int scb_shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global);

@@ -153,7 +153,11 @@ struct scb_handle {
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
-    std::vector<int64_t> sh_cnt_reads, sh_cnt_name_bytes;
+    std::vector<int64_t> sh_cnt_reads, sh_cnt_name_bytes, sh_first, sh_nbytes;
+    int sh_G = 0;
+    void *rx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // receive buffers: aux, packed, qual1, names, seq2, qual2
+    size_t rx_cap[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<void *> rx_retired;
     DevBuf sh_name_off;        // import side: name offsets rebuilt from the lengths
     float sh_ms = 0;           // device time of the last scb_shard_* call
 };
@@ -759,8 +763,9 @@ static void stage_sort_emit(scb_handle *h) {
         h->perm_m.alloc((size_t)n * 4, st);
         uint64_t *a = k0.as<uint64_t>(), *b = k1.as<uint64_t>();
         uint32_t *x = h->perm_m.as<uint32_t>(), *y = v1.as<uint32_t>();
-        SCB_LAUNCH(merged_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), h->perm.as<uint32_t>(), n, nb,
-                   h->tab.root_order_pos, a, x);
+        if (n > 0)
+            SCB_LAUNCH(merged_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), h->perm.as<uint32_t>(), n, nb,
+                       h->tab.root_order_pos, a, x);
         radix_sort_pairs(&a, &x, &b, &y, n, 0, ob, ws, st);
         if (x != h->perm_m.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->perm_m.p, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         emit_order(h, h->perm_m.as<uint32_t>(), a, 0, ob, true, h->merged);
@@ -933,34 +938,47 @@ static void shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
     tm.stop();
 }
 
-static void shard_pack(scb_handle *h, const int64_t *split, int G, scb_shard_xfer *out) {
+// dst row p <- src row perm[p] where dst is any byte address (peer memory over NVLink or local)
+static void gather_rows_to(cudaStream_t st, const uint8_t *src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
+    if (n <= 0 || L <= 0) return;
+    if (L >= 16) {
+        const int64_t nchunks = (n * (int64_t)L + 15 + 15) >> 4;
+        SCB_LAUNCH(gather_rows16_to_k, (unsigned)cdiv(nchunks, 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
+    } else if ((L & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+        SCB_LAUNCH(gather_words_to_k, (unsigned)cdiv(n * (L / 4), 256), 256, 0, st, (const uint32_t *)src, (uint32_t *)dst, perm, n, L / 4);
+    } else {
+        SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
+    }
+}
+
+// stable partition of the local reads by owner + what the owners need to size their receive buffers
+static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shard_xfer *out) {
     cudaStream_t st = h->st;
     ArenaScope arena_scope(&h->arena);
     const scb_config &cfg = h->cfg;
-    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
     const Pending &c = h->cur;
     const int64_t n = c.n;
     const int nb = h->tab.n_buckets;
+    const int64_t n1 = std::max<int64_t>(n, 1);
     ShardTimer tm(h);
     SplitTab t;
     t.G = G;
     for (int g = 0; g <= G; g++) t.s[g] = (uint32_t)split[g];
-    // stable partition by owner: one 8-bit radix pass over the destination
-    DevBuf k0((size_t)std::max<int64_t>(n, 1) * 8, st), k1((size_t)std::max<int64_t>(n, 1) * 8, st), v1((size_t)std::max<int64_t>(n, 1) * 4, st);
-    h->sh_perm.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
+    // one 8-bit radix pass over the destination keeps input order inside every destination
+    DevBuf k0((size_t)n1 * 8, st), k1((size_t)n1 * 8, st), v1((size_t)n1 * 4, st), v0((size_t)n1 * 4, st);
     DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
     SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
     uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
-    uint32_t *va = h->sh_perm.as<uint32_t>(), *vb = v1.as<uint32_t>();
+    uint32_t *va = v0.as<uint32_t>(), *vb = v1.as<uint32_t>();
     if (n > 0) {
         SCB_LAUNCH(dest_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, t, ka, va);
         radix_sort_pairs(&ka, &va, &kb, &vb, n, 0, std::max(1, ceil_log2((uint64_t)G)), ws, st);
     }
-    const uint32_t *perm = va;
+    h->sh_perm = (va == v0.as<uint32_t>()) ? std::move(v0) : std::move(v1);
+    const uint32_t *perm = h->sh_perm.as<uint32_t>();
     DevBuf dfirst((size_t)(G + 1) * 8, st), dnb((size_t)(G + 1) * 8, st);
     SCB_LAUNCH(dest_bounds_k, 1, kMaxRanks + 1, 0, st, ka, n, G, dfirst.as<int64_t>());
-    // aux words, then everything else in the same order
-    h->sh_aux.alloc((size_t)std::max<int64_t>(n, 1) * 8, st);
+    h->sh_aux.alloc((size_t)n1 * 8, st);
     if (n > 0)
         SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
                    cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
@@ -968,36 +986,105 @@ static void shard_pack(scb_handle *h, const int64_t *split, int G, scb_shard_xfe
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     exclusive_scan<uint64_t>(AuxNameLen{h->sh_aux.as<uint64_t>()}, n, h->sh_noff.as<uint64_t>(), h->sh_noff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
     SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, h->sh_noff.as<uint64_t>(), dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
-    std::vector<int64_t> first((size_t)G + 1), nbytes((size_t)G + 1);
-    SCB_CUDA(cudaMemcpyAsync(first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaMemcpyAsync(nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    h->sh_first.assign((size_t)G + 1, 0); h->sh_nbytes.assign((size_t)G + 1, 0);
+    SCB_CUDA(cudaMemcpyAsync(h->sh_first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(h->sh_nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     h->sh_cnt_reads.assign((size_t)G, 0); h->sh_cnt_name_bytes.assign((size_t)G, 0);
-    for (int g = 0; g < G; g++) { h->sh_cnt_reads[g] = first[g + 1] - first[g]; h->sh_cnt_name_bytes[g] = nbytes[g + 1] - nbytes[g]; }
-    const int64_t name_bytes = nbytes[(size_t)G];
-    const int prow = h->PW * 4;
-    h->sh_packed.alloc((size_t)n * prow + 64, st);
-    gather_rows_any(st, h->packed.as<uint8_t>(), h->sh_packed.as<uint8_t>(), perm, n, prow);
-    if (cfg.use_quals) { h->sh_qual1.alloc((size_t)n * L1 + 16, st); gather_rows_any(st, c.qual1, h->sh_qual1.as<uint8_t>(), perm, n, L1); }
-    if (cfg.use_names) {
+    for (int g = 0; g < G; g++) { h->sh_cnt_reads[g] = h->sh_first[g + 1] - h->sh_first[g]; h->sh_cnt_name_bytes[g] = h->sh_nbytes[g + 1] - h->sh_nbytes[g]; }
+    const int64_t name_bytes = h->sh_nbytes[(size_t)G];
+    if (cfg.use_names) {   // names are staged contiguously per destination (variable length: bulk copies move them)
         h->sh_names.alloc((size_t)name_bytes + 16, st);
         if (n > 0) SCB_LAUNCH(pack_names_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, c.name_off, c.names, h->sh_noff.as<uint64_t>(), h->sh_names.as<uint8_t>());
-    }
-    if (cfg.paired) {
-        h->sh_seq2.alloc((size_t)n * L2 + 16, st); gather_rows_any(st, c.seq2, h->sh_seq2.as<uint8_t>(), perm, n, L2);
-        if (cfg.use_quals) { h->sh_qual2.alloc((size_t)n * L2 + 16, st); gather_rows_any(st, c.qual2, h->sh_qual2.as<uint8_t>(), perm, n, L2); }
     }
     tm.stop();
     memset(out, 0, sizeof *out);
     out->n = n; out->name_bytes = cfg.use_names ? name_bytes : 0;
-    out->aux = h->sh_aux.as<uint64_t>(); out->packed = h->sh_packed.as<uint8_t>();
-    out->qual1 = cfg.use_quals ? h->sh_qual1.as<uint8_t>() : nullptr;
+    out->aux = h->sh_aux.as<uint64_t>();
     out->names = cfg.use_names ? h->sh_names.as<uint8_t>() : nullptr;
+    out->cnt_reads = h->sh_cnt_reads.data(); out->cnt_name_bytes = h->sh_cnt_name_bytes.data();
+    out->packed_row_bytes = h->PW * 4;
+    h->sh_G = G;
+    h->sh_phase = 3;
+}
+
+// staged variant: rows gathered into local send arrays (the caller moves them, e.g. NCCL all-to-all)
+static void shard_stage(scb_handle *h, scb_shard_xfer *out) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    const uint32_t *perm = h->sh_perm.as<uint32_t>();
+    const int prow = h->PW * 4;
+    ShardTimer tm(h);
+    h->sh_packed.alloc((size_t)n * prow + 64, st);
+    gather_rows_to(st, h->packed.as<uint8_t>(), h->sh_packed.as<uint8_t>(), perm, n, prow);
+    if (cfg.use_quals) { h->sh_qual1.alloc((size_t)n * L1 + 16, st); gather_rows_to(st, c.qual1, h->sh_qual1.as<uint8_t>(), perm, n, L1); }
+    if (cfg.paired) {
+        h->sh_seq2.alloc((size_t)n * L2 + 16, st); gather_rows_to(st, c.seq2, h->sh_seq2.as<uint8_t>(), perm, n, L2);
+        if (cfg.use_quals) { h->sh_qual2.alloc((size_t)n * L2 + 16, st); gather_rows_to(st, c.qual2, h->sh_qual2.as<uint8_t>(), perm, n, L2); }
+    }
+    tm.stop();
+    out->packed = h->sh_packed.as<uint8_t>();
+    out->qual1 = cfg.use_quals ? h->sh_qual1.as<uint8_t>() : nullptr;
     out->seq2 = cfg.paired ? h->sh_seq2.as<uint8_t>() : nullptr;
     out->qual2 = (cfg.paired && cfg.use_quals) ? h->sh_qual2.as<uint8_t>() : nullptr;
-    out->cnt_reads = h->sh_cnt_reads.data(); out->cnt_name_bytes = h->sh_cnt_name_bytes.data();
-    out->packed_row_bytes = prow;
     h->sh_phase = 4;
+}
+
+// fused pack + send: every row gather writes straight into its owner's receive buffer (peer memory over
+// NVLink, or this rank's own buffer). Destinations are visited in rotated order (rank+1, rank+2, ...) so that at
+// any moment the ranks target different owners.
+static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int G = h->sh_G;
+    const int prow = h->PW * 4;
+    ShardTimer tm(h);
+    for (int k = 1; k <= G; k++) {
+        const int g = (rank + k) % G;
+        const int64_t ng = h->sh_cnt_reads[g];
+        if (ng == 0) continue;
+        const scb_shard_peer &pp = peers[g];
+        const int64_t f = h->sh_first[g];
+        const uint32_t *perm = h->sh_perm.as<uint32_t>() + f;
+        SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.aux + pp.row_off * 8, h->sh_aux.as<uint64_t>() + f, (size_t)ng * 8, cudaMemcpyDeviceToDevice, st));
+        gather_rows_to(st, h->packed.as<uint8_t>(), (uint8_t *)pp.packed + pp.row_off * prow, perm, ng, prow);
+        if (cfg.use_quals) gather_rows_to(st, c.qual1, (uint8_t *)pp.qual1 + pp.row_off * L1, perm, ng, L1);
+        if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)
+            SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names.as<uint8_t>() + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
+                                     cudaMemcpyDeviceToDevice, st));
+        if (cfg.paired) {
+            gather_rows_to(st, c.seq2, (uint8_t *)pp.seq2 + pp.row_off * L2, perm, ng, L2);
+            if (cfg.use_quals) gather_rows_to(st, c.qual2, (uint8_t *)pp.qual2 + pp.row_off * L2, perm, ng, L2);
+        }
+    }
+    tm.stop();
+    h->sh_phase = 4;
+}
+
+// persistent receive buffers (plain cudaMalloc so that they can be exported over CUDA IPC), grown with headroom
+static void shard_recv_reserve(scb_handle *h, const int64_t *need, void **ptrs, int32_t *changed) {
+    *changed = 0;
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    for (int k = 0; k < 6; k++) {
+        const size_t want = (size_t)std::max<int64_t>(need[k], 0) + 256;
+        if (need[k] > 0 && h->rx_cap[k] < want) {
+            // peers may still hold an IPC mapping of the old array: it is freed at the next import, after they
+            // have re-mapped (CUDA leaves freeing an array that is still imported elsewhere undefined)
+            if (h->rx[k]) h->rx_retired.push_back(h->rx[k]);
+            h->rx[k] = nullptr; h->rx_cap[k] = 0;
+            const size_t cap = want + want / 8;
+            SCB_CUDA(cudaMalloc(&h->rx[k], cap));
+            h->rx_cap[k] = cap;
+            *changed = 1;
+        }
+        ptrs[k] = h->rx[k];
+    }
 }
 
 static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global) {
@@ -1011,6 +1098,8 @@ static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chun
     if (in->packed_row_bytes != h->PW * 4) throw CudaError{"import: packed row size does not match the read length"};
     if (n >= (1ll << 31)) throw CudaError{"import: more than 2^31-1 reads on one rank"};
     SCB_CUDA(cudaStreamSynchronize(st));
+    for (void *r : h->rx_retired) cudaFree(r);
+    h->rx_retired.clear();
     h->arena.rewind(h->sh_mark);   // everything of the scan/resolve side is dead now (the send arrays were delivered)
     ShardTimer tm(h);
     Pending imp;
@@ -1293,12 +1382,72 @@ int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
     SCB_CATCH
     return SCB_OK;
 }
+static int shard_split_ok(const scb_handle *h, const int64_t *split, int32_t n_ranks) {
+    if (split[0] != 0 || split[n_ranks] != h->tab.n_buckets + 1) { scb::g_last_error = "split must cover [0, n_cols]"; return 0; }
+    for (int g = 0; g < n_ranks; g++) if (split[g] > split[g + 1]) { scb::g_last_error = "split must be non-decreasing"; return 0; }
+    return 1;
+}
+int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
+    if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(2)
+    if (!shard_split_ok(h, split, n_ranks)) return SCB_EINVAL;
+    scb::shard_partition(h, split, n_ranks, out);
+    SCB_CATCH
+    return SCB_OK;
+}
 int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
     if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(2)
-    if (split[0] != 0 || split[n_ranks] != h->tab.n_buckets + 1) { scb::g_last_error = "split must cover [0, n_cols]"; return SCB_EINVAL; }
-    for (int g = 0; g < n_ranks; g++) if (split[g] > split[g + 1]) { scb::g_last_error = "split must be non-decreasing"; return SCB_EINVAL; }
-    scb::shard_pack(h, split, n_ranks, out);
+    if (!shard_split_ok(h, split, n_ranks)) return SCB_EINVAL;
+    scb::shard_partition(h, split, n_ranks, out);
+    const float ms = h->sh_ms;
+    scb::shard_stage(h, out);
+    h->sh_ms += ms;
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers) {
+    if (!peers) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(3)
+    if (n_ranks != h->sh_G || rank < 0 || rank >= n_ranks) { scb::g_last_error = "rank / n_ranks do not match scb_shard_partition"; return SCB_EINVAL; }
+    scb::shard_send(h, rank, peers);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_recv_reserve(scb_handle *h, const int64_t *need_bytes, void **ptrs, int32_t *changed) {
+    if (!h || !need_bytes || !ptrs || !changed) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::shard_recv_reserve(h, need_bytes, ptrs, changed);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_ipc_export(scb_handle *h, const void *dev_ptr, uint8_t *handle64) {
+    if (!h || !dev_ptr || !handle64) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t mh;
+    SCB_CUDA(cudaIpcGetMemHandle(&mh, (void *)dev_ptr));
+    memcpy(handle64, &mh, 64);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_ipc_open(scb_handle *h, const uint8_t *handle64, void **out) {
+    if (!h || !handle64 || !out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handle64, 64);
+    SCB_CUDA(cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess));
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_ipc_close(scb_handle *h, void *peer_ptr) {
+    if (!h || !peer_ptr) return SCB_OK;
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    SCB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
     SCB_CATCH
     return SCB_OK;
 }
@@ -1403,6 +1552,8 @@ void scb_destroy(scb_handle *h) {
     cudaStream_t st = h->st_own;
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
+    for (auto &r : h->rx) if (r) cudaFree(r);
+    for (void *r : h->rx_retired) cudaFree(r);
     h->arena.destroy();
     delete h;  // pooled DevBufs free stream-ordered
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }

@@ -137,6 +137,65 @@ __global__ void gather_u64_k(const uint64_t *__restrict__ src, const int64_t *__
     if (k < m) out[k] = (int64_t)src[idx[k]];
 }
 
+// ---- fused pack + send: row gathers that write straight into the owner's receive buffer ---------------------
+// dst is peer memory mapped over NVLink (or this GPU's own receive buffer) at an arbitrary byte offset, so the
+// 16-byte chunks are aligned in DESTINATION address space: chunk c covers stream bytes [16c - mis, 16c - mis + 16)
+// with mis = dst & 15; the (at most two) partial chunks at the ends use byte stores. Requires L >= 16.
+__global__ void __launch_bounds__(256) gather_rows16_to_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                          const uint32_t *__restrict__ perm, int64_t n, int L) {
+    const int mis = (int)((uintptr_t)dst & 15);
+    const int64_t total = n * (int64_t)L;
+    const int64_t nchunks = (total + mis + 15) >> 4;
+    const int64_t cblk = (int64_t)blockIdx.x * (256 * kGatherChunks);
+    const int64_t s_blk = cblk * 16 - mis;
+    const int64_t sb = s_blk < 0 ? 0 : s_blk;          // first stream byte of the block, clamped for the division
+    const int64_t pblk = sb / L;
+    const uint32_t rblk = (uint32_t)(sb - pblk * L);
+    const uint8_t *a0[kGatherChunks], *a1[kGatherChunks];
+    int n0[kGatherChunks];
+    int64_t s0[kGatherChunks];
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++) {
+        const int64_t c = cblk + q * 256 + threadIdx.x;
+        a0[q] = a1[q] = nullptr; n0[q] = 16;
+        s0[q] = c * 16 - mis;
+        if (c < nchunks && s0[q] >= 0 && s0[q] + 16 <= total) {
+            const uint32_t x = rblk + (uint32_t)(s0[q] - sb), dp = x / (uint32_t)L;
+            const int64_t p0 = pblk + dp;
+            const int r0 = (int)(x - dp * (uint32_t)L);
+            n0[q] = min(16, L - r0);
+            a0[q] = src + (int64_t)perm[p0] * L + r0;
+            if (n0[q] < 16) a1[q] = src + (int64_t)perm[p0 + 1] * L;   // p0 + 1 < n: the chunk lies inside the stream
+        }
+    }
+    uint4 v[kGatherChunks];
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++)
+        if (a0[q]) {
+            v[q] = load16_unaligned(a0[q], n0[q]);
+            if (a1[q]) v[q] = splice16(v[q], load16_unaligned(a1[q], 16 - n0[q]), n0[q]);
+        }
+#pragma unroll
+    for (int q = 0; q < kGatherChunks; q++) {
+        const int64_t c = cblk + q * 256 + threadIdx.x;
+        if (c >= nchunks) continue;
+        if (a0[q]) { *(uint4 *)(dst + s0[q]) = v[q]; continue; }
+        for (int k = 0; k < 16; k++) {                 // partial chunk at either end of the stream
+            const int64_t sx = s0[q] + k;
+            if (sx < 0 || sx >= total) continue;
+            const int64_t pr = sx / L;
+            dst[sx] = src[(int64_t)perm[pr] * L + (sx - pr * L)];
+        }
+    }
+}
+// rows of W 32-bit words (packed reads of short inputs): one thread per word
+__global__ void gather_words_to_k(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint32_t *__restrict__ perm, int64_t n, int W) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n * (int64_t)W) return;
+    const int64_t pr = o / W;
+    dst[o] = src[(int64_t)perm[pr] * W + (o - pr * W)];
+}
+
 // ---- receive side ------------------------------------------------------------------------------------------
 __global__ void unpack_aux_k(const uint64_t *__restrict__ aux, int64_t n, int nb, const uint8_t *__restrict__ rank_level,
                              uint32_t *__restrict__ asg, uint16_t *__restrict__ endv, uint8_t *__restrict__ lvl, uint32_t *__restrict__ chunk) {

@@ -124,6 +124,53 @@ class TorchComm:
         self.dist.all_to_all_single(buf[:total], send[: int(sum(send_counts))], [int(x) for x in recv_counts], [int(x) for x in send_counts])
         return buf
 
+    def map_peers(self, transform, ptrs, changed):
+        """Publishes this rank's receive arrays (device pointers, 0 = unused) and returns table[g][k]: rank g's
+        array k as mapped into THIS process (CUDA IPC over NVLink peer access; own rank: the local pointer).
+        Handles are exchanged only when some rank's arrays moved; mappings are cached."""
+        import torch
+        from .binding import _check, load_library
+        L = load_library()
+        if not hasattr(self, "_ipc"):
+            self._ipc = {}        # (g, k) -> (handle bytes, mapped pointer)
+            self._table = None
+        any_changed = max(x[0] for x in self.allgather_host([1 if (changed or self._table is None) else 0]))
+        if any_changed:
+            nk = len(ptrs)
+            hb = np.zeros((nk, 65), dtype=np.uint8)
+            for k, p in enumerate(ptrs):
+                if p:
+                    buf = (C.c_uint8 * 64)()
+                    _check(L.scb_ipc_export(transform._h, C.c_void_p(p), buf))
+                    hb[k, :64] = np.frombuffer(buf, dtype=np.uint8)
+                    hb[k, 64] = 1
+            allh = self.allgather(torch.from_numpy(hb).to(self.device)).cpu().numpy()
+            table = []
+            for g in range(self.world):
+                row = []
+                for k in range(nk):
+                    if g == self.rank:
+                        row.append(int(ptrs[k] or 0))
+                        continue
+                    if not allh[g, k, 64]:
+                        row.append(0)
+                        continue
+                    hbytes = allh[g, k, :64].tobytes()
+                    old = self._ipc.get((g, k))
+                    if old is None or old[0] != hbytes:
+                        if old is not None:
+                            _check(L.scb_ipc_close(transform._h, C.c_void_p(old[1])))
+                        out = C.c_void_p()
+                        hbuf = (C.c_uint8 * 64).from_buffer_copy(hbytes)
+                        _check(L.scb_ipc_open(transform._h, hbuf, C.byref(out)))
+                        self._ipc[(g, k)] = (hbytes, out.value)
+                    row.append(self._ipc[(g, k)][1])
+                table.append(row)
+            self._table = table
+        else:
+            self._table[self.rank] = [int(p or 0) for p in ptrs]
+        return self._table
+
     def barrier(self):
         self.dist.barrier()
 
@@ -189,6 +236,9 @@ class LoopbackComm:
         self.s.barrier.wait()   # senders may release their buffers only after every receiver copied
         return buf
 
+    def map_peers(self, transform, ptrs, changed):
+        return [[int(p or 0) for p in row] for row in self._exchange(list(ptrs))]   # one address space
+
     def barrier(self):
         self.s.barrier.wait()
 
@@ -214,9 +264,12 @@ class ShardedTransform:
     """One rank of a sharded run. `transform` is this rank's BoostTransform (its device = this rank's GPU);
     submit this rank's slice of the input to it as usual, then call flush() on every rank."""
 
-    def __init__(self, transform, comm, use_torch_stream=True):
+    def __init__(self, transform, comm, use_torch_stream=True, p2p=True):
+        """p2p=True: fused pack + send over peer memory (CUDA IPC / NVLink stores from the gather kernels);
+        p2p=False: rows are staged locally and moved by the comm's all-to-all (NCCL)."""
         self.t = transform
         self.comm = comm
+        self.p2p = p2p and hasattr(comm, "map_peers")
         self.stats = {}
         self._keep = None
         if use_torch_stream:
@@ -228,7 +281,7 @@ class ShardedTransform:
 
     def flush(self):
         import torch
-        from .binding import FlushResult, ScbResult, ScbShardXfer, _check, load_library
+        from .binding import FlushResult, ScbResult, ScbShardPeer, ScbShardXfer, _check, load_library
         L = load_library()
         h = self.t._h
         cfg = self.t.cfg
@@ -307,7 +360,10 @@ class ShardedTransform:
         split = balanced_split(ghist, G)
         split_c = (C.c_int64 * (G + 1))(*split)
         x = ScbShardXfer()
-        _check(L.scb_shard_pack(h, split_c, G, C.byref(x)))
+        if self.p2p:
+            _check(L.scb_shard_partition(h, split_c, G, C.byref(x)))
+        else:
+            _check(L.scb_shard_pack(h, split_c, G, C.byref(x)))
         lap("pack")
 
         # ---- exchange ---------------------------------------------------------------------------------------
@@ -318,37 +374,56 @@ class ShardedTransform:
         rn = [mat[s][G + r] for s in range(G)]
         n_recv, nb_recv = sum(rr), sum(rn)
         prow = x.packed_row_bytes
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        keep = {}
-
-        def xchg(name, ptr, row, slack=0):
-            send = _dev_bytes(ptr, x.n * row, dev)
-            keep[name] = comm.all_to_all_bytes(send, [c * row for c in cr], [c * row for c in rr], slack=slack)
-        xchg("aux", x.aux, 8)
-        xchg("packed", x.packed, prow, slack=64)
-        if cfg.use_quals:
-            xchg("qual1", x.qual1, L1)
-        if cfg.use_names:
-            send = _dev_bytes(x.names, x.name_bytes, dev)
-            keep["names"] = comm.all_to_all_bytes(send, cn, rn, slack=16)
-        if cfg.paired:
-            xchg("seq2", x.seq2, L2)
-            if cfg.use_quals:
-                xchg("qual2", x.qual2, L2)
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        ms["exchange"] = ev0.elapsed_time(ev1)
-
-        # ---- sort + emit of the owned slice --------------------------------------------------------------------
         y = ScbShardXfer()
         y.n, y.name_bytes, y.packed_row_bytes = n_recv, nb_recv, prow
-        y.aux = keep["aux"].data_ptr()
-        y.packed = keep["packed"].data_ptr()
-        y.qual1 = keep["qual1"].data_ptr() if "qual1" in keep else None
-        y.names = keep["names"].data_ptr() if "names" in keep else None
-        y.seq2 = keep["seq2"].data_ptr() if "seq2" in keep else None
-        y.qual2 = keep["qual2"].data_ptr() if "qual2" in keep else None
+        keep = {}
+        if self.p2p:
+            # fused pack + send: the row gathers write straight into the owners' receive arrays over NVLink
+            need = [n_recv * 8, n_recv * prow + 64, n_recv * L1 if cfg.use_quals else 0, nb_recv + 16 if cfg.use_names else 0,
+                    n_recv * L2 if cfg.paired else 0, n_recv * L2 if (cfg.paired and cfg.use_quals) else 0]
+            ptrs = (C.c_void_p * 6)()
+            chg = C.c_int32()
+            _check(L.scb_shard_recv_reserve(h, (C.c_int64 * 6)(*need), ptrs, C.byref(chg)))
+            table = comm.map_peers(self.t, [ptrs[k] for k in range(6)], bool(chg.value))
+            peers = (ScbShardPeer * G)()
+            for g in range(G):
+                pg = peers[g]
+                pg.aux, pg.packed, pg.qual1, pg.names, pg.seq2, pg.qual2 = [table[g][k] or None for k in range(6)]
+                pg.row_off = sum(mat[s][g] for s in range(r))
+                pg.name_off = sum(mat[s][G + g] for s in range(r))
+            _check(L.scb_shard_send(h, r, G, peers))
+            lap("exchange")
+            comm.barrier()   # every rank's writes have landed
+            y.aux, y.packed, y.qual1, y.names, y.seq2, y.qual2 = [ptrs[k] for k in range(6)]
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+
+            def xchg(name, ptr, row, slack=0):
+                send = _dev_bytes(ptr, x.n * row, dev)
+                keep[name] = comm.all_to_all_bytes(send, [c * row for c in cr], [c * row for c in rr], slack=slack)
+            xchg("aux", x.aux, 8)
+            xchg("packed", x.packed, prow, slack=64)
+            if cfg.use_quals:
+                xchg("qual1", x.qual1, L1)
+            if cfg.use_names:
+                send = _dev_bytes(x.names, x.name_bytes, dev)
+                keep["names"] = comm.all_to_all_bytes(send, cn, rn, slack=16)
+            if cfg.paired:
+                xchg("seq2", x.seq2, L2)
+                if cfg.use_quals:
+                    xchg("qual2", x.qual2, L2)
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            ms["exchange"] = ev0.elapsed_time(ev1)
+            y.aux = keep["aux"].data_ptr()
+            y.packed = keep["packed"].data_ptr()
+            y.qual1 = keep["qual1"].data_ptr() if "qual1" in keep else None
+            y.names = keep["names"].data_ptr() if "names" in keep else None
+            y.seq2 = keep["seq2"].data_ptr() if "seq2" in keep else None
+            y.qual2 = keep["qual2"].data_ptr() if "qual2" in keep else None
+
+        # ---- sort + emit of the owned slice --------------------------------------------------------------------
         _check(L.scb_shard_import(h, C.byref(y), n_chunks))
         lap("import")
         res = ScbResult()

@@ -92,3 +92,26 @@ def test_larger_three_ranks_bucket_ids():
     o = util.run_oracle(cores, b, q1, q2)
     ranks = util.run_sharded_loopback(cores, b, q1, q2, 3)
     util.assert_sharded_same(o, ranks)
+
+
+def test_eight_ranks_empty_bucket_slice():
+    # the root bucket holds more than 1/8 of the reads: one rank owns an empty slice of the bucket order
+    o, ranks = _case(20000, 100, 8, seed=77, bucket_set_bytes=1 << 21)
+    assert any(r[1].stats["n_recv"] == 0 for r in ranks)
+
+
+def test_staged_exchange_path():
+    # scb_shard_pack + all-to-all of local send arrays (the NCCL-style path) instead of the fused peer writes
+    from scalce_b200 import shard
+    cores, b, q1, q2, _ = util.make_case(15000, 100, seed=60)
+    o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    orig = shard.ShardedTransform.__init__
+
+    def staged(self, transform, comm, use_torch_stream=True, p2p=True):
+        orig(self, transform, comm, use_torch_stream, p2p=False)
+    shard.ShardedTransform.__init__ = staged
+    try:
+        ranks = util.run_sharded_loopback(cores, b, q1, q2, 3, bucket_set_bytes=1 << 20)
+    finally:
+        shard.ShardedTransform.__init__ = orig
+    util.assert_sharded_same(o, ranks)
