@@ -519,10 +519,12 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     const int nb1 = h->tab.n_buckets + 1;
     const int W = h->sh_W, grid = h->sh_grid;
     const size_t smem = (size_t)W * nb1 * 8;
-    h->sh_blk.alloc(blk.size() * 8, st);
-    SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
+    if (mode != 2) {   // a warm round reuses the block list of the round before
+        h->sh_blk.alloc(blk.size() * 8, st);
+        SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
+        SCB_CUDA(cudaMemsetAsync(h->sh_stat.p, 0, 8, st));
+    }
     SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)(mode == 0 ? kRdMaxRounds : 1) * 4, st));
-    SCB_CUDA(cudaMemsetAsync(h->sh_stat.p, 0, 8, st));
     RdParams rp;
     rp.n = h->cur.n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
     rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = h->sh_S.as<uint32_t>();
@@ -536,10 +538,11 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     void *args[] = {&rp};
     SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
+    if (mode != 0) { h->last_rounds++; return 0; }   // single round: nothing to read back, the stream orders the rest
     int stat[2] = {0, 0};
     SCB_CUDA(cudaMemcpyAsync(stat, h->sh_stat.p, 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
-    h->last_rounds = mode == 0 ? stat[1] : h->last_rounds + stat[1];
+    h->last_rounds = stat[1];
     if (prof) {
         std::vector<unsigned long long> ts(4096 * 8);
         SCB_CUDA(cudaMemcpy(ts.data(), dts.p, ts.size() * 8, cudaMemcpyDeviceToHost));
@@ -887,7 +890,6 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
     ArenaScope arena_scope(&h->arena);
     const int64_t n = h->cur.n;
     const int nb1 = h->tab.n_buckets + 1;
-    ShardTimer tm(h);
     if (n == 0) {
         SCB_CUDA(cudaMemsetAsync(tot_dev, 0, (size_t)(nb1 + 1) * 4, st));
     } else {
@@ -898,7 +900,7 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
         std::vector<int64_t> blk{0, n};
         if (dense_launch(h, first ? 1 : 2, g0, blk, tot_dev) != 0) throw CudaError{"resolve: round cap hit"};
     }
-    tm.stop();
+    h->sh_ms = 0;   // asynchronous: the caller times the round loop on its stream
 }
 
 static void shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {

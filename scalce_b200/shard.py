@@ -270,6 +270,7 @@ class ShardedTransform:
         self.t = transform
         self.comm = comm
         self.p2p = p2p and hasattr(comm, "map_peers")
+        self.on_torch_stream = bool(use_torch_stream)
         self.stats = {}
         self._keep = None
         if use_torch_stream:
@@ -318,13 +319,16 @@ class ShardedTransform:
 
         # ---- tie-break -------------------------------------------------------------------------------------
         tot = torch.zeros(ncols + 1, dtype=torch.int32, device=dev)   # u32 bit patterns
+        sync = (lambda: None) if self.on_torch_stream else (lambda: torch.cuda.synchronize(dev))   # one stream orders everything
         if r == 0:
             _check(L.scb_shard_resolve_local(h, C.c_void_p(tot.data_ptr())))
             lap("resolve")
-        torch.cuda.synchronize(dev)
+        sync()
         allt = comm.allgather(tot)
         rounds = 0
         if G > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             first = True
             while True:
                 if r > 0:
@@ -336,16 +340,18 @@ class ShardedTransform:
                     else:
                         bf = allt[:r, :ncols].sum(0, dtype=torch.int64).to(torch.int32)
                     bf = bf.contiguous()
-                    torch.cuda.synchronize(dev)
+                    sync()
                     _check(L.scb_shard_resolve_round(h, C.c_void_p(bf.data_ptr()), before[r], 1 if first else 0, C.c_void_p(tot.data_ptr())))
-                    lap("resolve")
-                torch.cuda.synchronize(dev)
+                    sync()
                 allt = comm.allgather(tot)
                 rounds += 1
                 changed = int(allt[1:, ncols].to(torch.int64).sum().item())
                 if not first and changed == 0:
                     break
                 first = False
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms["resolve_rounds"] = e0.elapsed_time(e1)
         gtot = allt[:, :ncols].sum(0, dtype=torch.int64).to(torch.int32).contiguous()
         torch.cuda.synchronize(dev)
         _check(L.scb_shard_finalize(h, C.c_void_p(gtot.data_ptr()), n_global))
