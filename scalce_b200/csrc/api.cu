@@ -222,8 +222,7 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
                 std::vector<uint16_t> tr((size_t)ns * 4);
                 std::vector<uint32_t> hr(nhit);
                 for (int u = 0; u < ns; u++) {
-                    // columns in the permuted base order the kernel reads off ASCII bits 1-2 (A0 C1 T2 G3)
-                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + (c ^ (c >> 1))] = (uint16_t)(newid[t.next[(size_t)u * 4 + c]] * 4u);
+                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + c] = (uint16_t)(newid[t.next[(size_t)u * 4 + c]] * 4u);
                     if (t.nto_rank[u] >= 0) hr[newid[u] - (ns - nhit)] = (uint32_t)t.nto_rank[u];
                 }
                 upload(h->d_trans16, tr, h->st);
@@ -433,18 +432,22 @@ static void stage_scan(scb_handle *h) {
     bool scanned = false;
     {
         const char *force = getenv("SCB_SCAN");
-        const size_t toff = (h->smem_table_bytes + 15) & ~(size_t)15;
-        const size_t budget = 225 * 1024;
-        int R = 0;
-        if (h->smem_resident && toff + 512 < budget) R = (int)std::min<size_t>(1024, ((budget - toff - 256) / 2 / (size_t)L1) / 32 * 32);
-        if (R >= 64 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
-            const size_t tile_bytes = (((size_t)R * L1) + 15) & ~(size_t)15;
-            const size_t smem = toff + 2 * tile_bytes + 256;
+        const size_t budget = 227 * 1024 - 64;
+        const int PW = h->PW, pitch = scan_smem_pitch(PW);
+        const size_t per_warp = scan_smem_warp_bytes(L1, PW);
+        const size_t fixed = h->smem_resident ? scan_smem_table_bytes(h->tab.n_states, h->n_hit, nb) : budget;
+        int W = 0;
+        if (h->smem_resident && fixed + 2 * per_warp <= budget) W = (int)std::min<size_t>(32, (budget - fixed) / per_warp);
+        const int R = W * 32;
+        if (W >= 2 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
+            const size_t smem = scan_smem_total(h->tab.n_states, h->n_hit, nb, W, L1, PW);
             SCB_CUDA(cudaFuncSetAttribute(scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
             DevBuf dtot(8, st);
-            uint64_t cap = std::max<uint64_t>((uint64_t)n * 8, 1u << 20);
+            // candidate space is handed to warps in chunks, so the arrays have holes: up to one chunk per warp
+            const uint64_t holes = (uint64_t)dev_sms * W * kCandChunk;
+            uint64_t cap = std::max<uint64_t>((uint64_t)n * 8, 1u << 20) + holes;
             for (int attempt = 0; attempt < 2 && !scanned; attempt++) {
                 h->cand_rank.alloc((size_t)cap * 4, st);
                 h->cand_pos.alloc((size_t)cap * 2, st);
@@ -454,9 +457,10 @@ static void stage_scan(scb_handle *h) {
                 sp.rank_level = h->d_rank_level.as<uint8_t>(); sp.ns = h->tab.n_states; sp.n_hit = h->n_hit; sp.nb = nb; sp.H0 = h->H0; sp.R = R;
                 sp.lvl = h->lvl.as<uint8_t>(); sp.ncand = h->ncand.as<uint16_t>(); sp.cand_off = h->cand_off.as<uint64_t>();
                 sp.cand_rank = h->cand_rank.as<uint32_t>(); sp.cand_pos = h->cand_pos.as<uint16_t>();
-                sp.cand_total = dtot.as<unsigned long long>(); sp.cand_cap = cap; sp.n_tiles = cdiv(n, R);
-                sp.packed = h->packed.as<uint32_t>(); sp.PW = h->PW;
-                int grid = (int)std::min<int64_t>(dev_sms, sp.n_tiles);
+                sp.cand_total = dtot.as<unsigned long long>(); sp.cand_cap = cap; sp.n_tiles = cdiv(n, 32);
+                sp.packed = h->packed.as<uint32_t>(); sp.PW = PW;
+                sp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); sp.pitch = pitch;
+                int grid = (int)std::min<int64_t>(dev_sms, cdiv(sp.n_tiles, W));
                 SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
                 SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
                 SCB_CUDA(cudaStreamSynchronize(st));
