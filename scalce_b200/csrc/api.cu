@@ -342,12 +342,14 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>();
     uint8_t *oQ = o.data[2].as<uint8_t>(), *oR2 = o.data[4].as<uint8_t>(), *oQ2 = o.data[5].as<uint8_t>();
     auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) { gather_rows_any(st, src, dst, perm, n, L); };
-    if (cfg.use_names) SCB_LAUNCH(emit_names_m_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
+    if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
     {
         const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
-        const int64_t nthr = n * (int64_t)NW;
-        if (nthr >= (1ll << 32)) throw CudaError{"flush too large for the stream-1 kernel's 32-bit indexing (n * record words >= 2^32)"};
-        SCB_LAUNCH(emit_reads_m_k, (unsigned)cdiv(nthr, 256), 256, 0, st, e, NW, nthr);
+        const int recmax = sz_read(L1) + sz_meta;
+        const int RPB = std::max(1, std::min(64, (32 * 1024) / recmax));
+        const size_t smem = (size_t)RPB * recmax + 48;
+        const uint32_t inv_nw = (uint32_t)(((1ull << 32) + NW - 1) / NW);
+        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, st, e, RPB, NW, inv_nw);
     }
     if (cfg.use_quals) gather_rows(c.qual1, oQ, L1);
     if (cfg.paired) {

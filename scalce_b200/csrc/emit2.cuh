@@ -154,43 +154,37 @@ __device__ __forceinline__ void copy_bytes16(uint8_t *__restrict__ dst, const ui
 // One thread per 16 output bytes (the output is dense, so stores are aligned STG.128 and fully
 // coalesced); a chunk may straddle two rows. Sources are unaligned: two aligned 16-byte loads and a
 // byte shift. Requires L >= 16.
+// 16 bytes starting `sh` (0..15) bytes into the 32-byte window (v0, v1): word select in two predicated levels,
+// then four funnel shifts - branch free, so lanes of a warp that copy different rows do not diverge
+__device__ __forceinline__ uint4 window16(uint4 v0, uint4 v1, int sh) {
+    const bool b0 = (sh & 4) != 0, b1 = (sh & 8) != 0;
+    // level 1: skip one word if bit 2 of sh is set
+    const uint32_t u0 = b0 ? v0.y : v0.x, u1 = b0 ? v0.z : v0.y, u2 = b0 ? v0.w : v0.z, u3 = b0 ? v1.x : v0.w,
+                   u4 = b0 ? v1.y : v1.x, u5 = b0 ? v1.z : v1.y, u6 = b0 ? v1.w : v1.z;
+    // level 2: skip two words if bit 3 is set
+    const uint32_t w0 = b1 ? u2 : u0, w1 = b1 ? u3 : u1, w2 = b1 ? u4 : u2, w3 = b1 ? u5 : u3, w4 = b1 ? u6 : u4;
+    const int bs = (sh & 3) * 8;
+    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+}
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t *__restrict__ a, int nbytes) {
     const uintptr_t A = (uintptr_t)a;
     const uint4 *a0 = (const uint4 *)(A & ~(uintptr_t)15);
     const int sh = (int)(A & 15);
     uint4 v0 = ldg_g64(a0), v1 = make_uint4(0, 0, 0, 0);
     if (sh + nbytes > 16) v1 = ldg_g64(a0 + 1);               // only when it holds a needed byte (never past the buffer's last granule)
-    const int bs = (sh & 3) * 8;
-    uint32_t w0, w1, w2, w3, w4;
-    switch (sh >> 2) {
-        case 0: w0 = v0.x; w1 = v0.y; w2 = v0.z; w3 = v0.w; w4 = v1.x; break;
-        case 1: w0 = v0.y; w1 = v0.z; w2 = v0.w; w3 = v1.x; w4 = v1.y; break;
-        case 2: w0 = v0.z; w1 = v0.w; w2 = v1.x; w3 = v1.y; w4 = v1.z; break;
-        default: w0 = v0.w; w1 = v1.x; w2 = v1.y; w3 = v1.z; w4 = v1.w; break;
-    }
-    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+    return window16(v0, v1, sh);
 }
-// dst bytes [0, k) from x, bytes [k, 16) from y shifted up by k (k in 1..15)
+// dst bytes [0, k) from x, bytes [k, 16) from the first 16-k bytes of y (k in 1..15): y is moved up by k bytes
+// with the same window trick (32-byte window = 16 zero bytes, then y; start 16-k), then merged under a byte mask
 __device__ __forceinline__ uint4 splice16(uint4 x, uint4 y, int k) {
-    uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, o[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int lo = 4 * j;                                   // first byte of output word j
-        uint32_t v;
-        if (lo + 4 <= k) v = xs[j];
-        else if (lo >= k) {                                     // bytes lo-k .. lo-k+3 of y
-            const int s = lo - k, ws = s >> 2, bs = (s & 3) * 8;
-            uint32_t a = 0, b2 = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { a = (ws == q) ? ys[q] : a; b2 = (ws + 1 == q) ? ys[q] : b2; }
-            v = __funnelshift_r(a, b2, bs);
-        } else {                                                // mixed word: k - lo bytes of x, rest from y[0..]
-            const int nx = k - lo;
-            v = (xs[j] & (0xffffffffu >> (8 * (4 - nx)))) | (ys[0] << (8 * nx));
-        }
-        o[j] = v;
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
+    const uint4 ys = window16(make_uint4(0, 0, 0, 0), y, 16 - k);
+    // mask of the bytes taken from x: the low k bytes of the 16
+    const int kb = k * 8;                                       // 8..120 bits
+    const uint32_t m0 = kb >= 32 ? 0xffffffffu : (0xffffffffu >> (32 - kb));
+    const uint32_t m1 = kb >= 64 ? 0xffffffffu : (kb <= 32 ? 0u : (0xffffffffu >> (64 - kb)));
+    const uint32_t m2 = kb >= 96 ? 0xffffffffu : (kb <= 64 ? 0u : (0xffffffffu >> (96 - kb)));
+    const uint32_t m3 = kb <= 96 ? 0u : (0xffffffffu >> (128 - kb));
+    return make_uint4((x.x & m0) | (ys.x & ~m0), (x.y & m1) | (ys.y & ~m1), (x.z & m2) | (ys.z & ~m2), (x.w & m3) | (ys.w & ~m3));
 }
 constexpr int kGatherChunks = 4;   // independent 16-byte chunks per thread (memory-level parallelism)
 __global__ void __launch_bounds__(256) gather_rows16_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
@@ -325,6 +319,95 @@ __global__ void __launch_bounds__(256) emit_reads_m_k(EmitMParams e, uint32_t NW
         if (b < nbytes) d[k] = (uint8_t)(v >> (24 - 8 * k));
         else if (b < recsz) d[k] = (uint8_t)((uint32_t)end >> (8 * (b - nbytes)));   // low bytes of int16 end, reads.cpp:130
     }
+}
+
+// ---- dense writers: records of a CTA are assembled in shared memory, then leave as aligned 16-byte stores ----
+// sbuf[(g0 & 15) + i] holds stream byte g0 + i for i in [0, len); gbase is the (16-byte aligned) start of the stream
+__device__ __forceinline__ void flush_staged(uint8_t *__restrict__ gbase, uint64_t g0, int len, const uint8_t *sbuf) {
+    const int mis = (int)(g0 & 15);
+    const int nch = (mis + len + 15) >> 4;
+    uint8_t *ga = gbase + (g0 - mis);
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        const int lo = c * 16 - mis;
+        if (lo >= 0 && lo + 16 <= len) *(uint4 *)(ga + 16 * c) = *(const uint4 *)(sbuf + 16 * c);
+        else
+            for (int k = 0; k < 16; k++) { const int i = lo + k; if (i >= 0 && i < len) ga[16 * c + k] = sbuf[16 * c + k]; }
+    }
+}
+
+// stream 0: [len:u8][name] per read (names.cpp:48-62), 256 reads per CTA
+constexpr int kNamesCap = 24 * 1024;
+__global__ void __launch_bounds__(256) emit_names_st_k(EmitMParams e) {
+    __shared__ __align__(16) uint8_t sb[kNamesCap + 32];
+    const int64_t p0 = (int64_t)blockIdx.x * 256, p1 = (p0 + 256 < e.n) ? p0 + 256 : e.n;
+    const uint64_t g0 = e.offN[p0];
+    const int64_t len64 = (int64_t)(e.offN[p1] - g0);
+    const bool staged = len64 <= kNamesCap;
+    const int64_t p = p0 + threadIdx.x;
+    if (p < p1) {
+        const uint64_t m = e.ms[p];
+        const int64_t a = meta_name_off(m);
+        const int nl = meta_namelen(m);
+        const uint64_t o = e.offN[p];
+        if (staged) {
+            uint8_t *d = sb + (int)(g0 & 15) + (int)(o - g0);
+            d[0] = (uint8_t)nl;                                                   // names.cpp:58
+            for (int k = 0; k < nl; k += 16) {
+                const int nbv = nl - k < 16 ? nl - k : 16;
+                const uint4 v = load16_unaligned(e.names + a + k, nbv);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (j < nbv) d[1 + k + j] = (uint8_t)(wv[j >> 2] >> (8 * (j & 3)));
+            }
+        } else {
+            uint8_t *d = e.oN + o;
+            d[0] = (uint8_t)nl;
+            for (int k = 0; k < nl; k++) d[1 + k] = (uint8_t)ldg_g64(e.names + a + k);
+        }
+    }
+    __syncthreads();
+    if (staged) flush_staged(e.oN, g0, (int)len64, sb);
+}
+
+// stream 1: rotated 2-bit reads + end marker; RPB reads per CTA, one work item per (read, 4 record bytes)
+__global__ void __launch_bounds__(256) emit_reads_st_k(EmitMParams e, int RPB, uint32_t NW, uint32_t inv_nw) {
+    extern __shared__ __align__(16) uint8_t sbd[];
+    const int64_t p0 = (int64_t)blockIdx.x * RPB, p1 = (p0 + RPB < e.n) ? p0 + RPB : e.n;
+    const uint64_t g0 = e.offR[p0];
+    const int len = (int)(e.offR[p1] - g0);
+    uint8_t *sb = sbd + (int)(g0 & 15);
+    const uint32_t items = (uint32_t)(p1 - p0) * NW;
+    for (uint32_t t = threadIdx.x; t < items; t += 256) {
+        const uint32_t pl = __umulhi(t, inv_nw), w = t - pl * NW;
+        const int64_t p = p0 + pl;
+        const uint64_t m = e.ms[p];
+        // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
+        const int lv = meta_lvl(m), end = meta_end(m);
+        const int tail = e.L1 - end, total = e.L1 - lv;
+        const int nbytes = sz_read(total);
+        const int recsz = nbytes + e.sz_meta;
+        if ((int)(4 * w) >= recsz) continue;
+        uint8_t *d = sb + (int)(e.offR[p] - g0) + 4 * w;
+        uint32_t v = 0;
+        if ((int)(4 * w) < nbytes) {
+            const uint32_t *row = e.packed + (int64_t)e.perm[p] * e.PW;   // rows have 2 words of slack behind the last one
+            const int j0 = 16 * (int)w;
+            int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
+            int nv = total - j0; nv = nv > 16 ? 16 : nv;
+            if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
+            if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
+            if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = 4 * (int)w + k;                          // byte index inside the record
+            if (b < nbytes) d[k] = (uint8_t)(v >> (24 - 8 * k));
+            else if (b < recsz) d[k] = (uint8_t)((uint32_t)end >> (8 * (b - nbytes)));   // low bytes of int16 end, reads.cpp:130
+        }
+    }
+    __syncthreads();
+    flush_staged(e.oR, g0, len, sbd);
 }
 
 // ---- stream 4: mate 2 is packed without rotation (output_read(read2, dest, 0, 0), compress.cpp:696) ----
