@@ -346,10 +346,13 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     {
         const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
         const int recmax = sz_read(L1) + sz_meta;
-        const int RPB = std::max(1, std::min(64, (32 * 1024) / recmax));
-        const size_t smem = (size_t)RPB * recmax + 48;
-        const uint32_t inv_nw = (uint32_t)(((1ull << 32) + NW - 1) / NW);
-        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, st, e, RPB, NW, inv_nw);
+        const int PWs = (h->PW + kEmitRowPad) | 1;
+        const int per_read = recmax + PWs * 4;
+        const int RPB = std::max(1, std::min(256, (40 * 1024) / per_read));
+        const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
+        const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
+        SCB_CUDA(cudaFuncSetAttribute(emit_reads_st_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, st, e, RPB, NW, inv_pws, recmax);
     }
     if (cfg.use_quals) gather_rows(c.qual1, oQ, L1);
     if (cfg.paired) {
@@ -578,7 +581,7 @@ static void dense_finalize(scb_handle *h) {
     cudaStream_t st = h->st;
     const int64_t n = h->cur.n;
     const int nb = h->tab.n_buckets;
-    SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
+    SCB_LAUNCH(resolve_finalize_k, (unsigned)cdiv(n, 256 * kFinPer), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(),
                h->cand_rank.as<uint32_t>(), h->cand_pos.as<uint16_t>(), h->sh_sel.as<uint16_t>(), nb, h->asg.as<uint32_t>(),
                h->endv.as<uint16_t>(), h->d_life.as<unsigned long long>() + nb);
 }
@@ -730,18 +733,47 @@ static void stage_sort_emit(scb_handle *h) {
         int consumed = pb;
         DevBuf keep_keys, keep_idx, keep_pos;  // own the current compact state across rounds
         while (consumed < L1 && m > 1) {
-            DevBuf flag((size_t)m, st), cpos((size_t)(m + 1) * 4, st), hsum((size_t)(m + 1) * 4, st), w32((size_t)scan_tiles(m) * 4, st);
-            SCB_LAUNCH(tie_flags_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, m, flag.as<uint8_t>());
-            exclusive_scan<uint32_t>(LoadAs<uint8_t, uint32_t>{flag.as<uint8_t>()}, m, cpos.as<uint32_t>(), cpos.as<uint32_t>() + m, w32.as<uint32_t>(), st);
-            exclusive_scan<uint32_t>(HeadFlag{cur_keys, flag.as<uint8_t>()}, m, hsum.as<uint32_t>(), hsum.as<uint32_t>() + m, w32.as<uint32_t>(), st);
             uint32_t t = 0, G = 0;
-            SCB_CUDA(cudaMemcpyAsync(&t, cpos.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
-            SCB_CUDA(cudaMemcpyAsync(&G, hsum.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
-            SCB_CUDA(cudaStreamSynchronize(st));
-            if (t == 0) break;
-            DevBuf c_pos((size_t)t * 4, st), c_idx((size_t)t * 4, st), c_grp((size_t)t * 4, st);
-            SCB_LAUNCH(tie_compact_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, flag.as<uint8_t>(), cpos.as<uint32_t>(),
-                       hsum.as<uint32_t>(), cur_pos, cur_idx, m, c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), c_grp.as<uint32_t>());
+            DevBuf c_pos, c_idx, c_grp;
+            bool have = false;
+            if (cur_pos == nullptr && m >= (1 << 16)) {
+                // first round over the whole flush: tied elements are rare, so instead of two full prefix sums
+                // collect their positions with warp-aggregated appends (unordered), then order the short list
+                DevBuf lk0((size_t)m * 8 / 4 + 64, st), lk1((size_t)m * 8 / 4 + 64, st), lv0((size_t)m + 64, st), lv1((size_t)m + 64, st), dcnt(4, st);
+                const uint32_t cap = (uint32_t)(m / 4);
+                SCB_CUDA(cudaMemsetAsync(dcnt.p, 0, 4, st));
+                SCB_LAUNCH(tie_find_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, m, lk0.as<uint64_t>(), lv0.as<uint32_t>(), cap, dcnt.as<uint32_t>());
+                SCB_CUDA(cudaMemcpyAsync(&t, dcnt.p, 4, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                if (t == 0) break;
+                if (t <= cap) {
+                    uint64_t *a = lk0.as<uint64_t>(), *b = lk1.as<uint64_t>();
+                    uint32_t *x = lv0.as<uint32_t>(), *y = lv1.as<uint32_t>();
+                    radix_sort_pairs(&a, &x, &b, &y, t, 0, ceil_log2((uint64_t)m), ws, st);
+                    c_pos.alloc((size_t)t * 4, st); c_idx.alloc((size_t)t * 4, st); c_grp.alloc((size_t)t * 4, st);
+                    DevBuf hs((size_t)(t + 1) * 4, st), w32((size_t)scan_tiles(t) * 4, st);
+                    HeadAtPos hp{cur_keys, x};
+                    exclusive_scan<uint32_t>(hp, t, hs.as<uint32_t>(), hs.as<uint32_t>() + t, w32.as<uint32_t>(), st);
+                    SCB_CUDA(cudaMemcpyAsync(&G, hs.as<uint32_t>() + t, 4, cudaMemcpyDeviceToHost, st));
+                    SCB_LAUNCH(tie_gather_sparse_k, (unsigned)cdiv(t, 256), 256, 0, st, hp, hs.as<uint32_t>(), cur_idx, (int64_t)t,
+                               c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), c_grp.as<uint32_t>());
+                    SCB_CUDA(cudaStreamSynchronize(st));
+                    have = true;
+                }
+            }
+            if (!have) {
+                DevBuf flag((size_t)m, st), cpos((size_t)(m + 1) * 4, st), hsum((size_t)(m + 1) * 4, st), w32((size_t)scan_tiles(m) * 4, st);
+                SCB_LAUNCH(tie_flags_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, m, flag.as<uint8_t>());
+                exclusive_scan<uint32_t>(LoadAs<uint8_t, uint32_t>{flag.as<uint8_t>()}, m, cpos.as<uint32_t>(), cpos.as<uint32_t>() + m, w32.as<uint32_t>(), st);
+                exclusive_scan<uint32_t>(HeadFlag{cur_keys, flag.as<uint8_t>()}, m, hsum.as<uint32_t>(), hsum.as<uint32_t>() + m, w32.as<uint32_t>(), st);
+                SCB_CUDA(cudaMemcpyAsync(&t, cpos.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaMemcpyAsync(&G, hsum.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                if (t == 0) break;
+                c_pos.alloc((size_t)t * 4, st); c_idx.alloc((size_t)t * 4, st); c_grp.alloc((size_t)t * 4, st);
+                SCB_LAUNCH(tie_compact_k, (unsigned)cdiv(m, 256), 256, 0, st, cur_keys, flag.as<uint8_t>(), cpos.as<uint32_t>(),
+                           hsum.as<uint32_t>(), cur_pos, cur_idx, m, c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), c_grp.as<uint32_t>());
+            }
             int grp_bits = ceil_log2(G);
             int nbases = std::min(std::min(32, (64 - grp_bits) / 2), L1 - consumed);
             DevBuf nk0((size_t)t * 8, st), nk1((size_t)t * 8, st), nv0((size_t)t * 4, st), nv1((size_t)t * 4, st);

@@ -233,6 +233,42 @@ __global__ void tie_compact_k(const uint64_t *__restrict__ k, const uint8_t *__r
     c_idx[c] = idx_in[p];
     c_grp[c] = hsum[p] + (head ? 1u : 0u) - 1u;  // hsum exclusive
 }
+// sparse variant of the first round: positions of tied elements appended in no particular order
+// (warp-aggregated), keys[] = position for the short sort that orders them
+__global__ void tie_find_k(const uint64_t *__restrict__ k, int64_t n, uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_val,
+                           uint32_t cap, uint32_t *__restrict__ counter) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool t = false;
+    if (p < n) {
+        const uint64_t v = k[p];
+        t = (p > 0 && k[p - 1] == v) || (p + 1 < n && k[p + 1] == v);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, t);
+    if (!m) return;
+    uint32_t base = 0;
+    if (lane_id() == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (t) {
+        const uint32_t o = base + __popc(m & lanemask_lt());
+        if (o < cap) { out_key[o] = (uint64_t)p; out_val[o] = (uint32_t)p; }
+    }
+}
+struct HeadAtPos {  // 1 where the c-th tied position (ascending) starts a run of equal keys
+    const uint64_t *k; const uint32_t *pos;
+    __device__ __forceinline__ uint32_t operator()(int64_t c) const {
+        const uint32_t p = pos[c];
+        return (p == 0 || k[p - 1] != k[p]) ? 1u : 0u;
+    }
+};
+__global__ void tie_gather_sparse_k(HeadAtPos hp, const uint32_t *__restrict__ hsum, const uint32_t *__restrict__ idx_in, int64_t t,
+                                    uint32_t *__restrict__ c_pos, uint32_t *__restrict__ c_idx, uint32_t *__restrict__ c_grp) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t) return;
+    const uint32_t p = hp.pos[c];
+    c_pos[c] = p;
+    c_idx[c] = idx_in[p];
+    c_grp[c] = hsum[c] + hp(c) - 1u;   // hsum exclusive
+}
 __global__ void tie_rekey_k(const uint8_t *__restrict__ seq, int L, const uint16_t *__restrict__ endv,
                             const uint32_t *__restrict__ c_idx, const uint32_t *__restrict__ c_grp, int64_t m, int grp_bits,
                             int from, int nbases, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {

@@ -288,23 +288,32 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
 }
 
 // asg / end from the converged slots; base -> lifetime counts
-__global__ void resolve_finalize_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
+constexpr int kFinPer = 4;   // reads per thread: the dependent loads of four reads are in flight together
+__global__ void __launch_bounds__(256) resolve_finalize_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
                                    const uint32_t *__restrict__ cand_rank, const uint16_t *__restrict__ cand_pos,
                                    const uint16_t *__restrict__ sel, int nb, uint32_t *__restrict__ asg, uint16_t *__restrict__ endv,
                                    unsigned long long *root_count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool root = false;
-    if (i < n) {
-        int nc = ncand[i];
-        if (nc == 0) { asg[i] = (uint32_t)nb; endv[i] = 0; root = true; }
-        else {
-            uint64_t o = cand_off[i] + sel[i];
-            asg[i] = cand_rank[o];
-            endv[i] = (uint16_t)(cand_pos[o] + 1);
-        }
+    const int64_t i0 = (int64_t)blockIdx.x * (256 * kFinPer) + threadIdx.x;
+    int nc[kFinPer]; uint64_t o[kFinPer];
+#pragma unroll
+    for (int q = 0; q < kFinPer; q++) {
+        const int64_t i = i0 + q * 256;
+        nc[q] = -1; o[q] = 0;
+        if (i < n) { nc[q] = ncand[i]; if (nc[q] > 0) o[q] = cand_off[i] + sel[i]; }
     }
-    uint32_t m = __ballot_sync(0xffffffffu, root);
-    if (lane_id() == 0 && m) atomicAdd(root_count, (unsigned long long)__popc(m));
+    uint32_t r[kFinPer]; uint32_t ps[kFinPer];
+#pragma unroll
+    for (int q = 0; q < kFinPer; q++) { r[q] = 0; ps[q] = 0; if (nc[q] > 0) { r[q] = cand_rank[o[q]]; ps[q] = cand_pos[o[q]]; } }
+    uint32_t roots = 0;
+#pragma unroll
+    for (int q = 0; q < kFinPer; q++) {
+        const int64_t i = i0 + q * 256;
+        if (nc[q] < 0) continue;
+        if (nc[q] == 0) { asg[i] = (uint32_t)nb; endv[i] = 0; roots++; }
+        else { asg[i] = r[q]; endv[i] = (uint16_t)(ps[q] + 1); }
+    }
+    roots = __reduce_add_sync(0xffffffffu, roots);
+    if (lane_id() == 0 && roots) atomicAdd(root_count, (unsigned long long)roots);
 }
 __global__ void life_to_base_k(const unsigned long long *life, uint32_t *base, int nb1) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

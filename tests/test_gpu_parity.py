@@ -136,3 +136,24 @@ def test_global_table_scan_engine(monkeypatch):
     # the scan path for automata too large for shared memory, forced on a small case
     monkeypatch.setenv("SCB_SCAN", "global")
     _case(20000, 100, seed=43)
+
+
+def test_sparse_first_tie_round():
+    # >= 65536 reads: the first tie-refinement round collects the (rare) tied positions sparsely
+    cores, b, q1, q2, _ = util.make_case(70000, 100, seed=61, n_frac=0.01)
+    b.seq[5000:5300] = b.seq[17]            # 300 identical reads
+    b.seq[40000:40100, :70] = b.seq[3, :70]  # long common prefixes
+    b.seq[69990:70000] = b.seq[69989]
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
+
+
+def test_mostly_tied_falls_back_to_dense_round():
+    cores, b, q1, q2, _ = util.make_case(70000, 64, seed=62)
+    b.seq[:] = b.seq[:7].repeat(10000, axis=0)   # 7 distinct reads
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
