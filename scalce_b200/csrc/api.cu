@@ -759,6 +759,29 @@ static void stage_sort_emit(scb_handle *h) {
                                c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), c_grp.as<uint32_t>());
                     SCB_CUDA(cudaStreamSynchronize(st));
                     have = true;
+                    // groups of up to 32 members (all of them on ordinary data) are finished by one warp each, on the
+                    // whole remaining key; only larger groups go through the iterative rounds below
+                    DevBuf gstart((size_t)(G + 1) * 4, st), big((size_t)t, st), bpos((size_t)(t + 1) * 4, st), w32b((size_t)scan_tiles(t) * 4, st);
+                    DevBuf mid_list((size_t)(t / 33 + 1) * 4, st), mid_count(4, st);
+                    SCB_CUDA(cudaMemsetAsync(mid_count.p, 0, 4, st));
+                    SCB_LAUNCH(tie_group_starts_k, (unsigned)cdiv(t, 256), 256, 0, st, c_grp.as<uint32_t>(), (int64_t)t, G, gstart.as<uint32_t>());
+                    SCB_LAUNCH(tie_small_groups_k, (unsigned)cdiv((int64_t)G * 32, 256), 256, 0, st, h->packed.as<uint32_t>(), h->PW, L1, h->endv.as<uint16_t>(),
+                               gstart.as<uint32_t>(), G, c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), consumed, h->perm.as<uint32_t>(), big.as<uint8_t>(),
+                               mid_list.as<uint32_t>(), mid_count.as<uint32_t>(), (uint32_t)kTieMidMax);
+                    SCB_LAUNCH(tie_mid_groups_k, 148 * 4, 256, 0, st, h->packed.as<uint32_t>(), h->PW, L1, h->endv.as<uint16_t>(), gstart.as<uint32_t>(),
+                               mid_list.as<uint32_t>(), mid_count.as<uint32_t>(), c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), consumed, h->perm.as<uint32_t>());
+                    exclusive_scan<uint32_t>(LoadAs<uint8_t, uint32_t>{big.as<uint8_t>()}, t, bpos.as<uint32_t>(), bpos.as<uint32_t>() + t, w32b.as<uint32_t>(), st);
+                    uint32_t t2 = 0;
+                    SCB_CUDA(cudaMemcpyAsync(&t2, bpos.as<uint32_t>() + t, 4, cudaMemcpyDeviceToHost, st));
+                    SCB_CUDA(cudaStreamSynchronize(st));
+                    if (t2 == 0) break;
+                    DevBuf bk((size_t)t2 * 8, st), bi((size_t)t2 * 4, st), bp((size_t)t2 * 4, st);
+                    SCB_LAUNCH(tie_big_compact_k, (unsigned)cdiv(t, 256), 256, 0, st, big.as<uint8_t>(), bpos.as<uint32_t>(), c_pos.as<uint32_t>(),
+                               c_idx.as<uint32_t>(), c_grp.as<uint32_t>(), (int64_t)t, bk.as<uint64_t>(), bi.as<uint32_t>(), bp.as<uint32_t>());
+                    keep_keys = std::move(bk); keep_idx = std::move(bi); keep_pos = std::move(bp);
+                    cur_keys = keep_keys.as<uint64_t>(); cur_idx = keep_idx.as<uint32_t>(); cur_pos = keep_pos.as<uint32_t>();
+                    m = t2;
+                    continue;   // `consumed` is unchanged: the large groups start their rounds from the same key offset
                 }
             }
             if (!have) {

@@ -70,6 +70,142 @@ __global__ void tie_rekey_pk_k(const uint32_t *__restrict__ packed, int PW, cons
     vals[c] = i;
 }
 
+// ---- tie groups of up to 32 elements: one warp orders a whole group on the full remaining key -----------------
+// The compact tie list is in position order, so a group (run of equal sorted keys) is a contiguous range of it and
+// its members are already in input-index order. Each lane holds one member; 32 key bases at a time every lane
+// compares its chunk with every other member's (shuffles) until all pairs are decided or the key is exhausted;
+// fully equal keys keep input order (the reference's radix sort is stable, reads.cpp:571-587).
+__global__ void tie_group_starts_k(const uint32_t *__restrict__ c_grp, int64_t t, uint32_t G, uint32_t *__restrict__ gstart) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) gstart[G] = (uint32_t)t;
+    if (c >= t) return;
+    if (c == 0 || c_grp[c] != c_grp[c - 1]) gstart[c_grp[c]] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(256) tie_small_groups_k(const uint32_t *__restrict__ packed, int PW, int L1, const uint16_t *__restrict__ endv,
+                                                          const uint32_t *__restrict__ gstart, uint32_t G, const uint32_t *__restrict__ c_pos,
+                                                          const uint32_t *__restrict__ c_idx, int consumed, uint32_t *__restrict__ perm,
+                                                          uint8_t *__restrict__ big /* [t]: 1 = member of a group left to the iterative rounds */,
+                                                          uint32_t *__restrict__ mid_list, uint32_t *__restrict__ mid_count, uint32_t mid_max) {
+    const uint32_t g = (uint32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= G) return;
+    const uint32_t l = lane_id();
+    const uint32_t gs = gstart[g], size = gstart[g + 1] - gs;
+    if (size > 32) {
+        // 33..mid_max members: queued for one CTA each (tie_mid_groups_k); beyond that: iterative radix rounds
+        const uint8_t b = size > mid_max ? 1 : 0;
+        for (uint32_t k = l; k < size; k += 32) big[gs + k] = b;
+        if (!b && l == 0) mid_list[atomicAdd(mid_count, 1u)] = g;
+        return;
+    }
+    const bool on = l < size;
+    const uint32_t idx = on ? c_idx[gs + l] : 0u, pos = on ? c_pos[gs + l] : 0u;
+    if (on) big[gs + l] = 0;
+    const uint32_t *row = packed + (int64_t)idx * PW;
+    const int end = on ? (int)endv[idx] : 0;
+    const uint32_t members = size == 32 ? 0xffffffffu : ((1u << size) - 1u);
+    uint32_t undecided = on ? (members & ~(1u << l)) : 0u, less = 0;   // less: members that sort before this lane's
+    for (int from = consumed; from < L1; from += 32) {
+        if (!__any_sync(0xffffffffu, undecided != 0)) break;
+        const uint64_t mine = on ? pk_key_bits(row, PW, end, from, 32) : 0ull;
+        for (uint32_t k = 0; k < size; k++) {
+            const uint64_t other = __shfl_sync(0xffffffffu, mine, (int)k);
+            if (undecided & (1u << k)) {
+                if (other < mine) { less |= 1u << k; undecided &= ~(1u << k); }
+                else if (other > mine) undecided &= ~(1u << k);
+            }
+        }
+    }
+    less |= undecided & lanemask_lt();                 // equal keys: input order
+    const uint32_t rank = __popc(less);
+    const uint32_t dst = __shfl_sync(0xffffffffu, pos, (int)rank);   // the group's positions are ascending along the lanes
+    if (on) perm[dst] = idx;
+}
+// groups of 33..kTieMidMax members: one CTA refines the whole group in shared memory, 32 key bases per round:
+// rank = number of members with a smaller (label, chunk) plus equal ones that come earlier; label = the rank of the
+// first equal member, so members that are still tied share a label in the next round.
+constexpr int kTieMidMax = 1024;
+__global__ void __launch_bounds__(256) tie_mid_groups_k(const uint32_t *__restrict__ packed, int PW, int L1, const uint16_t *__restrict__ endv,
+                                                        const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ mid_list,
+                                                        const uint32_t *__restrict__ mid_count, const uint32_t *__restrict__ c_pos,
+                                                        const uint32_t *__restrict__ c_idx, int consumed, uint32_t *__restrict__ perm) {
+    __shared__ uint64_t s_key[kTieMidMax];
+    __shared__ uint32_t s_lab[kTieMidMax], s_new[kTieMidMax];
+    __shared__ int s_tied;
+    constexpr int PER = kTieMidMax / 256;
+    const uint32_t count = *mid_count;
+    for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+        const uint32_t g = mid_list[q];
+        const uint32_t gs = gstart[g], size = gstart[g + 1] - gs;
+        uint32_t idx[PER], rank[PER];
+        int end[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const uint32_t j = threadIdx.x + 256 * u;
+            idx[u] = j < size ? c_idx[gs + j] : 0u;
+            end[u] = j < size ? (int)endv[idx[u]] : 0;
+            rank[u] = j;
+            if (j < size) s_lab[j] = 0;
+        }
+        for (int from = consumed; from < L1; from += 32) {
+            if (threadIdx.x == 0) s_tied = 0;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t j = threadIdx.x + 256 * u;
+                if (j < size) s_key[j] = pk_key_bits(packed + (int64_t)idx[u] * PW, PW, end[u], from, 32);
+            }
+            __syncthreads();
+            bool tied = false;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t j = threadIdx.x + 256 * u;
+                if (j >= size) continue;
+                const uint32_t lj = s_lab[j];
+                const uint64_t kj = s_key[j];
+                uint32_t less = 0, eqb = 0, eqa = 0;
+                for (uint32_t k = 0; k < size; k++) {
+                    const uint32_t lk = s_lab[k];
+                    const uint64_t kk = s_key[k];
+                    const bool eq = lk == lj && kk == kj;
+                    less += (lk < lj || (lk == lj && kk < kj)) ? 1u : 0u;
+                    eqb += (eq && k < j) ? 1u : 0u;
+                    eqa += (eq && k > j) ? 1u : 0u;
+                }
+                s_new[j] = less;
+                rank[u] = less + eqb;
+                tied |= (eqb + eqa) != 0;
+            }
+            if (tied) s_tied = 1;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t j = threadIdx.x + 256 * u;
+                if (j < size) s_lab[j] = s_new[j];
+            }
+            const bool more = s_tied != 0;
+            __syncthreads();
+            if (!more) break;
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const uint32_t j = threadIdx.x + 256 * u;
+            if (j < size) perm[c_pos[gs + rank[u]]] = idx[u];   // the group's positions are ascending along the compact list
+        }
+        __syncthreads();
+    }
+}
+
+// what is left for the iterative rounds: members of large groups, keyed by their group number
+__global__ void tie_big_compact_k(const uint8_t *__restrict__ big, const uint32_t *__restrict__ bpos, const uint32_t *__restrict__ c_pos,
+                                  const uint32_t *__restrict__ c_idx, const uint32_t *__restrict__ c_grp, int64_t t,
+                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint32_t *__restrict__ pos) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t || !big[c]) return;
+    const uint32_t o = bpos[c];
+    keys[o] = (uint64_t)c_grp[c];
+    idx[o] = c_idx[c];
+    pos[o] = c_pos[c];
+}
+
 // ---- segments ----------------------------------------------------------------------------------------
 struct KeyHead {   // 1 where the segment id (top `bits` bits of the sorted key, 0 bits = one segment) changes
     const uint64_t *keys; int shift, bits;

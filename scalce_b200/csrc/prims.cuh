@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys
 
 // Scatter pass. Ranks are computed per warp with match.any (stable), the tile is first reordered by
 // digit in shared memory, then written out so that each digit's elements leave as one contiguous run.
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(kSortThreads, 3) sort_scatter_k(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
                                                                int shift, uint32_t mask, const uint32_t *__restrict__ hist_scanned, int64_t tiles) {
     __shared__ uint32_t cnt[kSortWarps][256];
@@ -154,14 +154,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *_
     const int64_t tbeg = (int64_t)blockIdx.x * kSortTile;
     const int64_t wbase = tbeg + (int64_t)w * (kSortItems * 32);
     uint64_t key[kSortItems];
-    uint32_t val[kSortItems];
     uint32_t rank[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
         int64_t i = wbase + k * 32 + l;
-        bool ok = i < n;
-        key[k] = ok ? keys[i] : ~0ull;
-        val[k] = ok ? vals[i] : 0u;
+        key[k] = i < n ? keys[i] : ~0ull;
     }
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_k(const uint64_t *_
             uint32_t d = (uint32_t)(key[k] >> shift) & mask;
             uint32_t t = tbase[d] + cnt[w][d] + rank[k];
             skey[t] = key[k];
-            sval[t] = val[k];
+            sval[t] = vals[i];          // loaded late: keeps the values out of the registers while ranks are computed
         }
     }
     __syncthreads();

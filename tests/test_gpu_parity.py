@@ -157,3 +157,15 @@ def test_mostly_tied_falls_back_to_dense_round():
     o = util.run_oracle(cores, b, q1, q2)
     t, r = util.run_cuda(cores, b, q1, q2)
     util.assert_same(o, t, r)
+
+
+def test_mid_size_tie_groups():
+    # groups of 33..1024 tied reads (short suffixes after the core, duplicates) take the CTA-per-group path
+    cores, b, q1, q2, _ = util.make_case(80000, 100, seed=63)
+    for k, (lo, n_dup) in enumerate(((1000, 40), (3000, 300), (9000, 1000), (20000, 1500))):
+        b.seq[lo:lo + n_dup] = b.seq[lo]
+        b.seq[lo:lo + n_dup:3, 90:] = b.seq[lo + n_dup + 1, 90:]   # every third differs late in the read
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
