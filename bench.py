@@ -3,11 +3,12 @@
 
 A step = one pass of the hot path (scb_submit + scb_flush through the C ABI) over one batch of
 synthetic fixed-length reads. Workload at 1 GPU = BASELINE.json configs[1]: 50M x 150 bp
-single-end; under torchrun every rank runs the same per-GPU workload on its own shard (weak
-scaling, no data-path collective yet: bucket order is shard-local, see DESIGN.md "multi-GPU").
+single-end; under torchrun every rank holds the same per-GPU workload (weak scaling), the global
+input is the ranks' batches concatenated in rank order, and the sharded run (joint
+exact tie-break, bucket-range exchange over NVLink peer memory) produces the single-GPU order of it.
 
   value  reads/s with inputs resident in HBM when the timed region starts (CUDA events on the
-         library's stream, max over ranks)
+         stream the library runs on, max over ranks)
   e2e    reads/s through the same C ABI with HOST (pinned) buffers: H2D of all inputs and D2H
          of every output stream inside the timed region
   --impl reference : the reference's own CPU transform (oracle/_ref, unmodified objects)

@@ -100,9 +100,10 @@ class TorchComm:
 
     def allgather(self, t):
         import torch
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous())
-        return out
+        flat = t.contiguous().view(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat)
+        return out.view((self.world,) + tuple(t.shape))
 
     def allgather_host(self, ints):
         import torch

@@ -165,3 +165,134 @@ def test_two_rank_gloo_aggregation(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+# ---- host logic of the sharded run (scalce_b200/shard.py) -------------------------------------------
+def test_balanced_split_properties():
+    from scalce_b200.shard import balanced_split
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 8):
+        for _ in range(20):
+            ncols = int(rng.integers(1, 400))
+            hist = rng.integers(0, 1000, size=ncols)
+            if rng.random() < 0.3:
+                hist[int(rng.integers(0, ncols))] += 10 ** 6        # one dominant bucket (e.g. the root)
+            s = balanced_split(hist, world)
+            assert len(s) == world + 1 and s[0] == 0 and s[-1] == ncols
+            assert all(a <= b for a, b in zip(s[:-1], s[1:]))
+    # even histogram splits evenly; a bucket is never divided
+    assert balanced_split([10] * 8, 4) == [0, 2, 4, 6, 8]
+    assert balanced_split([0, 0, 100, 0], 2) in ([0, 2, 4], [0, 3, 4])
+
+
+def _ref_chunk_ids(sizes, B):
+    """compress.cpp:702, 708-713 over the whole input: chunk id of every read."""
+    out, tot, c = [], 0, 0
+    for s in sizes:
+        out.append(c)
+        tot += s
+        if tot >= B:
+            c += 1
+            tot = 0
+    return out, c + (1 if tot > 0 else 0)
+
+
+def _shard_sizes_host(sizes, B, carry, chunk):
+    """Host restatement of scb_shard_sizes (chunk_bounds_carry_k): returns ids, carry_out, chunk_out."""
+    ids = []
+    for s in sizes:
+        ids.append(chunk)
+        carry += s
+        if carry >= B:
+            chunk += 1
+            carry = 0
+    return ids, carry, chunk
+
+
+def test_chunk_chain_equals_global_numbering():
+    from scalce_b200.shard import chain_chunks, shard_bounds
+
+    class FakeComm:
+        def __init__(self, world):
+            self.world, self.rank, self.box = world, 0, None
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 5):
+        sizes = rng.integers(100, 400, size=1000).tolist()
+        B = 7000
+        want_ids, want_n = _ref_chunk_ids(sizes, B)
+        bd = shard_bounds(len(sizes), world)
+        # ranks take turns in rank order: emulate the chain sequentially
+        carry, chunk, got = 0, 0, []
+        for g in range(world):
+            ids, carry, chunk = _shard_sizes_host(sizes[bd[g]:bd[g + 1]], B, carry, chunk)
+            got += ids
+        assert got == want_ids
+        assert chunk + (1 if carry > 0 else 0) == want_n
+
+
+_GLOO_SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from scalce_b200.shard import TorchComm, chain_chunks, balanced_split, shard_bounds
+rank = int(sys.argv[1]); world = 2
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+comm = TorchComm(dist, torch.device("cpu"))
+# host metadata collectives
+assert comm.allgather_host([rank, 10 + rank]) == [[0, 10], [1, 11]]
+assert comm.bcast_host([7 * (rank + 1), 3], src=1) == [14, 3]
+# chunk chain: rank-order hand-off of (carry, chunk)
+rng = np.random.default_rng(11)
+sizes = rng.integers(100, 400, size=600).tolist(); B = 5000
+bd = shard_bounds(len(sizes), world)
+def sizes_fn(carry, chunk):
+    for s in sizes[bd[rank]:bd[rank + 1]]:
+        carry += s
+        if carry >= B: chunk += 1; carry = 0
+    return carry, chunk
+n_chunks = chain_chunks(sizes_fn, comm)
+tot, c = 0, 0
+for s in sizes:
+    tot += s
+    if tot >= B: c += 1; tot = 0
+assert n_chunks == c + (1 if tot > 0 else 0), (n_chunks, c, tot)
+# histogram all-gather -> identical split on every rank
+hist = torch.tensor([5, 0, 9, 1] if rank == 0 else [1, 2, 3, 40], dtype=torch.int32)
+g = comm.allgather(hist).to(torch.int64).sum(0).numpy()
+split = balanced_split(g, world)
+assert split[0] == 0 and split[-1] == 4
+# payload all-to-all (bytes, destination-major) with slack
+send = torch.arange(10, dtype=torch.uint8) + 100 * rank
+cnt = [3, 7] if rank == 0 else [6, 4]
+mat = comm.allgather_host(cnt)
+recv_cnt = [mat[s][rank] for s in range(world)]
+buf = comm.all_to_all_bytes(send, cnt, recv_cnt, slack=8)
+got = buf[:sum(recv_cnt)].tolist()
+want = (list(range(0, 3)) + list(range(100, 106))) if rank == 0 else (list(range(3, 10)) + list(range(106, 110)))
+assert got == want, (got, want)
+assert buf.numel() == sum(recv_cnt) + 8
+comm.barrier()
+dist.destroy_process_group()
+print("ok", rank, split)
+'''
+
+
+def test_two_rank_gloo_shard_plumbing(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "ws.py"
+    script.write_text(_GLOO_SHARD_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+    assert outs[0].split("ok 0")[1].strip() == outs[1].split("ok 1")[1].strip()   # same split everywhere
+
+
+def test_aux_word_layout_matches_header():
+    # include/scalce_b200.h documents the exchange word: rank | end << 24 | name length << 35 | chunk << 43
+    hdr = open(os.path.join(ROOT, "include", "scalce_b200.h")).read()
+    cuh = open(os.path.join(ROOT, "scalce_b200", "csrc", "shard.cuh")).read()
+    assert "end << 24" in hdr and "<< 35" in hdr and "<< 43" in hdr
+    assert "<< 24" in cuh and "<< 35" in cuh and "<< 43" in cuh
