@@ -345,7 +345,7 @@ def main():
         "scan": L + 8, "resolve": 16, "chunks": 8, "sort": 24, "ties": 0,
         "emit": 2 * L + 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + L + 4, "merged": 0, "arrays": 16,
         # sharded run: pack + exchange move the payload once each (aux word, packed row, quality row, name)
-        "finalize": 8, "hist": 4, "resolve_rounds": 16, "pack": 2 * (8 + 40 + L + NAME_BYTES), "exchange": 2 * (8 + 40 + L + NAME_BYTES), "import": 16,
+        "finalize": 8, "hist": 4, "resolve_rounds": 16, "pack": 2 * (8 + 40 + L + NAME_BYTES), "exchange": 2 * (8 + 40 + NAME_BYTES), "exchange_rows": 2 * L, "import": 16, "sort": 24,
     }
     ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,

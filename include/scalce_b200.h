@@ -229,7 +229,16 @@ typedef struct scb_shard_peer {
 } scb_shard_peer;
 int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
 int scb_shard_recv_reserve(scb_handle *h, const int64_t *need_bytes, void **ptrs, int32_t *changed);
-int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers);
+/* what: 1 = aux words + 2-bit rows + names (all the receive side needs to SORT), 2 = quality / mate-2 rows, 3 = both.
+ * async = 0: returns when this rank's writes are complete. async = 1: the writes run on a side stream with a small
+ * grid and the call returns at once - so that, after a first synchronous send of `what = 1`, a barrier and
+ * scb_shard_import, the row exchange overlaps scb_shard_finish_sort; scb_shard_send_wait joins it (then a barrier,
+ * then scb_shard_finish emits). */
+int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers, int32_t what, int32_t async);
+int scb_shard_send_wait(scb_handle *h);
+/* Sort + tie refinement of the imported reads (needs aux, 2-bit rows and names only); optional: scb_shard_finish
+ * runs it if it was not called. */
+int scb_shard_finish_sort(scb_handle *h);
 int scb_ipc_export(scb_handle *h, const void *dev_ptr, uint8_t *handle64);
 int scb_ipc_open(scb_handle *h, const uint8_t *handle64, void **out);
 int scb_ipc_close(scb_handle *h, void *peer_ptr);

@@ -120,6 +120,9 @@ struct scb_handle {
     scb_config cfg;
     CoreTable tab;
     cudaStream_t st = nullptr, st_own = nullptr;
+    cudaStream_t st_aux[2] = {nullptr, nullptr};   // side streams: independent output kernels run next to the quality gather
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;   // around the rows of a sharded send (possibly on the side stream)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t stage_ev[SCB_N_STAGES + 1] = {};
     float stage_ms[SCB_N_STAGES] = {};
@@ -145,6 +148,11 @@ struct scb_handle {
     uint64_t life_total = 0;   // reads ever submitted (bound on any lifetime count)
     int last_rounds = 0;       // fixed-point rounds of the last dense resolve
     int64_t n_perm = 0;        // entries of perm (== n_last except after a sharded run)
+    DevBuf srt_k0, srt_k1, srt_v1, srt_hist, srt_histws;   // sort buffers (shared by stage_sort and stage_emit's merged order)
+    const uint64_t *srt_keys = nullptr;                    // sorted keys of the chunk-major order
+    int srt_seg_bits = 0;
+    bool srt_keys_valid = false;   // scb_shard_finish_sort ran: scb_shard_finish only emits
+    Pending sh_local;          // the rank's own input after scb_shard_import replaced `cur` (phase-2 sends still read it)
     // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
     int sh_phase = 0;          // 0 idle, 1 scanned, 2 resolved (finalized), 3 sized, 4 packed, 5 imported
     Arena::Mark sh_mark{0, 0}; // arena position after the arrays that survive the exchange
@@ -197,6 +205,11 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         if (prop.major < 10) { g_last_error = "device is not sm_100 class"; return SCB_ENODEVICE; }
         SCB_CUDA(cudaStreamCreateWithFlags(&h->st_own, cudaStreamNonBlocking));
         h->st = h->st_own;
+        for (auto &a : h->st_aux) SCB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        SCB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (auto &e : h->ev_join) SCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        SCB_CUDA(cudaEventCreate(&h->ev_s0));
+        SCB_CUDA(cudaEventCreate(&h->ev_s1));
         SCB_CUDA(cudaEventCreate(&h->ev0));
         SCB_CUDA(cudaEventCreate(&h->ev1));
         for (auto &e : h->stage_ev) SCB_CUDA(cudaEventCreate(&e));
@@ -342,7 +355,13 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>();
     uint8_t *oQ = o.data[2].as<uint8_t>(), *oR2 = o.data[4].as<uint8_t>(), *oQ2 = o.data[5].as<uint8_t>();
     auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) { gather_rows_any(st, src, dst, perm, n, L); };
-    if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, st, e);
+    // The output kernels are independent of each other: names and packed reads (latency / issue bound) run on side
+    // streams next to the quality-row gather (HBM bound) instead of one after the other.
+    SCB_CUDA(cudaEventRecord(h->ev_fork, st));
+    cudaStream_t sN = h->st_aux[0], sR = h->st_aux[1];
+    SCB_CUDA(cudaStreamWaitEvent(sN, h->ev_fork, 0));
+    SCB_CUDA(cudaStreamWaitEvent(sR, h->ev_fork, 0));
+    if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
     {
         const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
         const int recmax = sz_read(L1) + sz_meta;
@@ -352,13 +371,15 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
         const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
         SCB_CUDA(cudaFuncSetAttribute(emit_reads_st_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, st, e, RPB, NW, inv_pws, recmax);
+        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, sR, e, RPB, NW, inv_pws, recmax);
     }
+    if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
+    SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
+    SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
     if (cfg.use_quals) gather_rows(c.qual1, oQ, L1);
-    if (cfg.paired) {
-        SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, oR2);
-        if (cfg.use_quals) gather_rows(c.qual2, oQ2, L2);
-    }
+    if (cfg.paired && cfg.use_quals) gather_rows(c.qual2, oQ2, L2);
+    SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+    SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
     SCB_CUDA(cudaMemsetAsync(cfirst.p, 0xff, (size_t)2 * std::max(nch, 1) * 8, st));   // -1 = chunk has no read here
     SCB_LAUNCH(meta2_k, (unsigned)cdiv(nseg, 128), 128, 0, st, tab, (int64_t)nseg, offN.as<uint64_t>(), offR.as<uint64_t>(),
@@ -681,8 +702,8 @@ static void stage_chunks(scb_handle *h) {
 
 }
 
-// 4-6. sort by (chunk, bucket order, suffix key), refine ties, emit the streams
-static void stage_sort_emit(scb_handle *h) {
+// 4-5. sort by (chunk, bucket order, suffix key), refine ties
+static void stage_sort(scb_handle *h) {
     cudaStream_t st = h->st;
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
@@ -706,10 +727,11 @@ static void stage_sort_emit(scb_handle *h) {
         pb = std::min(L1, (total_bits - seg_bits) / 2);
         if (getenv("SCB_SORT_FULLKEY")) pb = std::min(L1, (64 - seg_bits) / 2);
     }
-    DevBuf k0((size_t)n * 8, st), k1((size_t)n * 8, st), v1((size_t)n * 4, st);
+    DevBuf &k0 = h->srt_k0, &k1 = h->srt_k1, &v1 = h->srt_v1, &hist = h->srt_hist, &histws = h->srt_histws;
+    k0.alloc((size_t)n * 8, st); k1.alloc((size_t)n * 8, st); v1.alloc((size_t)n * 4, st);
     h->perm.alloc((size_t)n * 4, st);
     SortWs ws;
-    DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
+    hist.alloc((size_t)SortWs::hist_elems(n) * 4, st); histws.alloc((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
     ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
     uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
     uint32_t *va = h->perm.as<uint32_t>(), *vb = v1.as<uint32_t>();
@@ -816,8 +838,22 @@ static void stage_sort_emit(scb_handle *h) {
         }
     }
 
+    h->srt_keys = ka;
+    h->srt_seg_bits = seg_bits;
+}
+
+// 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
+static void stage_emit(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int64_t n = h->cur.n;
+    const int nb = h->tab.n_buckets;
+    const int seg_bits = h->srt_seg_bits;
+    const uint64_t *ka = h->srt_keys;
+    DevBuf &k0 = h->srt_k0, &k1 = h->srt_k1, &v1 = h->srt_v1;
+    SortWs ws;
+    ws.hist = h->srt_hist.as<uint32_t>(); ws.tile_ws = h->srt_histws.as<uint32_t>();
     SCB_CUDA(cudaEventRecord(h->stage_ev[5], st));
-    // 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
     emit_order(h, h->perm.as<uint32_t>(), ka, 64 - seg_bits, seg_bits, false, h->chunked);
     SCB_CUDA(cudaEventRecord(h->stage_ev[6], st));
     if (cfg.emit_merged && h->n_chunks > 1) {
@@ -880,6 +916,8 @@ static void shard_scan(scb_handle *h) {
     h->n_perm = 0;
     // per-read arrays of the INPUT shard survive the exchange: carve them first and remember the mark
     h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
+    h->sh_perm.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);   // send order: read by the row sends that overlap the receive side
+    h->sh_local = Pending();
     h->sh_mark = h->arena.mark();
     ShardTimer tm(h);
     stage_scan(h);
@@ -1002,11 +1040,13 @@ static void shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
 }
 
 // dst row p <- src row perm[p] where dst is any byte address (peer memory over NVLink or local)
-static void gather_rows_to(cudaStream_t st, const uint8_t *src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
+static void gather_rows_to(cudaStream_t st, const uint8_t *src, uint8_t *dst, const uint32_t *perm, int64_t n, int L, int grid_cap = 0) {
     if (n <= 0 || L <= 0) return;
     if (L >= 16) {
         const int64_t nchunks = (n * (int64_t)L + 15 + 15) >> 4;
-        SCB_LAUNCH(gather_rows16_to_k, (unsigned)cdiv(nchunks, 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
+        int64_t grid = cdiv(nchunks, 256 * kGatherChunks);
+        if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+        SCB_LAUNCH(gather_rows16_to_k, (unsigned)grid, 256, 0, st, src, dst, perm, n, L);
     } else if ((L & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
         SCB_LAUNCH(gather_words_to_k, (unsigned)cdiv(n * (L / 4), 256), 256, 0, st, (const uint32_t *)src, (uint32_t *)dst, perm, n, L / 4);
     } else {
@@ -1028,16 +1068,16 @@ static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shar
     t.G = G;
     for (int g = 0; g <= G; g++) t.s[g] = (uint32_t)split[g];
     // one 8-bit radix pass over the destination keeps input order inside every destination
-    DevBuf k0((size_t)n1 * 8, st), k1((size_t)n1 * 8, st), v1((size_t)n1 * 4, st), v0((size_t)n1 * 4, st);
+    DevBuf k0((size_t)n1 * 8, st), k1((size_t)n1 * 8, st), v0((size_t)n1 * 4, st);
     DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
     SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
     uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
-    uint32_t *va = v0.as<uint32_t>(), *vb = v1.as<uint32_t>();
+    uint32_t *va = v0.as<uint32_t>(), *vb = h->sh_perm.as<uint32_t>();   // one pass: the result lands in sh_perm
     if (n > 0) {
         SCB_LAUNCH(dest_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, t, ka, va);
         radix_sort_pairs(&ka, &va, &kb, &vb, n, 0, std::max(1, ceil_log2((uint64_t)G)), ws, st);
+        if (va != h->sh_perm.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->sh_perm.p, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     }
-    h->sh_perm = (va == v0.as<uint32_t>()) ? std::move(v0) : std::move(v1);
     const uint32_t *perm = h->sh_perm.as<uint32_t>();
     DevBuf dfirst((size_t)(G + 1) * 8, st), dnb((size_t)(G + 1) * 8, st);
     SCB_LAUNCH(dest_bounds_k, 1, kMaxRanks + 1, 0, st, ka, n, G, dfirst.as<int64_t>());
@@ -1100,14 +1140,18 @@ static void shard_stage(scb_handle *h, scb_shard_xfer *out) {
 // fused pack + send: every row gather writes straight into its owner's receive buffer (peer memory over
 // NVLink, or this rank's own buffer). Destinations are visited in rotated order (rank+1, rank+2, ...) so that at
 // any moment the ranks target different owners.
-static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers) {
-    cudaStream_t st = h->st;
+static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int what /* 1 small arrays, 2 rows, 3 both */, bool async) {
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
-    const Pending &c = h->cur;
+    const Pending &c = h->sh_phase >= 5 ? h->sh_local : h->cur;   // after import `cur` is the received set
     const int G = h->sh_G;
     const int prow = h->PW * 4;
-    ShardTimer tm(h);
+    // async: on a side stream with a capped grid (NVLink-bound work needs few SMs), so that the receive side's sort
+    // runs next to it; scb_shard_send_wait joins
+    cudaStream_t st = async ? h->st_aux[0] : h->st;
+    const int cap = async ? 148 * 2 : 0;
+    if (async) { SCB_CUDA(cudaEventRecord(h->ev_fork, h->st)); SCB_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0)); }
+    cudaEventRecord(h->ev_s0, st);
     for (int k = 1; k <= G; k++) {
         const int g = (rank + k) % G;
         const int64_t ng = h->sh_cnt_reads[g];
@@ -1115,19 +1159,32 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers) {
         const scb_shard_peer &pp = peers[g];
         const int64_t f = h->sh_first[g];
         const uint32_t *perm = h->sh_perm.as<uint32_t>() + f;
-        SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.aux + pp.row_off * 8, h->sh_aux.as<uint64_t>() + f, (size_t)ng * 8, cudaMemcpyDeviceToDevice, st));
-        gather_rows_to(st, h->packed.as<uint8_t>(), (uint8_t *)pp.packed + pp.row_off * prow, perm, ng, prow);
-        if (cfg.use_quals) gather_rows_to(st, c.qual1, (uint8_t *)pp.qual1 + pp.row_off * L1, perm, ng, L1);
-        if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)
-            SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names.as<uint8_t>() + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
-                                     cudaMemcpyDeviceToDevice, st));
-        if (cfg.paired) {
-            gather_rows_to(st, c.seq2, (uint8_t *)pp.seq2 + pp.row_off * L2, perm, ng, L2);
-            if (cfg.use_quals) gather_rows_to(st, c.qual2, (uint8_t *)pp.qual2 + pp.row_off * L2, perm, ng, L2);
+        if (what & 1) {
+            SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.aux + pp.row_off * 8, h->sh_aux.as<uint64_t>() + f, (size_t)ng * 8, cudaMemcpyDeviceToDevice, st));
+            gather_rows_to(st, h->packed.as<uint8_t>(), (uint8_t *)pp.packed + pp.row_off * prow, perm, ng, prow, cap);
+            if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)
+                SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names.as<uint8_t>() + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+        if (what & 2) {
+            if (cfg.use_quals) gather_rows_to(st, c.qual1, (uint8_t *)pp.qual1 + pp.row_off * L1, perm, ng, L1, cap);
+            if (cfg.paired) {
+                gather_rows_to(st, c.seq2, (uint8_t *)pp.seq2 + pp.row_off * L2, perm, ng, L2, cap);
+                if (cfg.use_quals) gather_rows_to(st, c.qual2, (uint8_t *)pp.qual2 + pp.row_off * L2, perm, ng, L2, cap);
+            }
         }
     }
-    tm.stop();
-    h->sh_phase = 4;
+    SCB_CUDA(cudaEventRecord(h->ev_s1, st));
+    if (!async) {
+        SCB_CUDA(cudaStreamSynchronize(st));
+        SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_s0, h->ev_s1));
+    }
+    if (h->sh_phase < 4) h->sh_phase = 4;
+}
+static void shard_send_wait(scb_handle *h) {
+    SCB_CUDA(cudaStreamSynchronize(h->st_aux[0]));
+    SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_s0, h->ev_s1));
+    h->sh_local = Pending();
 }
 
 // persistent receive buffers (plain cudaMalloc so that they can be exported over CUDA IPC), grown with headroom
@@ -1181,19 +1238,20 @@ static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chun
         exclusive_scan<uint64_t>(AuxNameLen{in->aux}, n, h->sh_name_off.as<uint64_t>(), h->sh_name_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
         imp.name_off = h->sh_name_off.as<int64_t>();
     }
+    h->sh_local = std::move(h->cur);   // the rank's own input: overlapping row sends still read it
     h->cur = std::move(imp);
     h->n_perm = n;
     tm.stop();
     h->sh_phase = 5;
 }
 
-static void shard_finish(scb_handle *h) {
+static void shard_finish(scb_handle *h, int what /* 1 = sort, 2 = emit, 3 = both */) {
     ArenaScope arena_scope(&h->arena);
     ShardTimer tm(h);
-    stage_meta(h);
-    stage_sort_emit(h);
+    if (what & 1) { stage_meta(h); stage_sort(h); h->srt_keys_valid = true; }
+    if (what & 2) stage_emit(h);
     tm.stop();
-    h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
+    if (what & 2) h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
 }
 
 // ---- the transform on one GPU ------------------------------------------------------------------------------
@@ -1212,7 +1270,8 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
     stage_chunks(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[3], st));
-    stage_sort_emit(h);
+    stage_sort(h);
+    stage_emit(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[7], st));
     stage_debug(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[8], st));
@@ -1469,11 +1528,17 @@ int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_sha
     SCB_CATCH
     return SCB_OK;
 }
-int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers) {
-    if (!peers) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+int scb_shard_send(scb_handle *h, int32_t rank, int32_t n_ranks, const scb_shard_peer *peers, int32_t what, int32_t async) {
+    if (!peers || (what & ~3) || what == 0) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(3)
     if (n_ranks != h->sh_G || rank < 0 || rank >= n_ranks) { scb::g_last_error = "rank / n_ranks do not match scb_shard_partition"; return SCB_EINVAL; }
-    scb::shard_send(h, rank, peers);
+    scb::shard_send(h, rank, peers, what, async != 0);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_send_wait(scb_handle *h) {
+    SCB_SHARD_ENTER(3)
+    scb::shard_send_wait(h);
     SCB_CATCH
     return SCB_OK;
 }
@@ -1521,11 +1586,18 @@ int scb_shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_g
     SCB_CATCH
     return SCB_OK;
 }
+int scb_shard_finish_sort(scb_handle *h) {
+    SCB_SHARD_ENTER(5)
+    scb::shard_finish(h, 1);
+    SCB_CATCH
+    return SCB_OK;
+}
 int scb_shard_finish(scb_handle *h, scb_result *out) {
     if (!out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
     memset(out, 0, sizeof *out);
     SCB_SHARD_ENTER(5)
-    scb::shard_finish(h);
+    scb::shard_finish(h, h->srt_keys_valid ? 2 : 3);
+    h->srt_keys_valid = false;
     out->device_ms = h->sh_ms;
     SCB_CATCH
     scb::fill_result(h, out);
@@ -1615,6 +1687,11 @@ void scb_destroy(scb_handle *h) {
     cudaStream_t st = h->st_own;
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
+    for (auto &a : h->st_aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
+    if (h->ev_s0) cudaEventDestroy(h->ev_s0);
+    if (h->ev_s1) cudaEventDestroy(h->ev_s1);
     for (auto &r : h->rx) if (r) cudaFree(r);
     for (void *r : h->rx_retired) cudaFree(r);
     h->arena.destroy();

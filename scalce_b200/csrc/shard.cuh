@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) gather_rows16_to_k(const uint8_t *__restr
     const int mis = (int)((uintptr_t)dst & 15);
     const int64_t total = n * (int64_t)L;
     const int64_t nchunks = (total + mis + 15) >> 4;
-    const int64_t cblk = (int64_t)blockIdx.x * (256 * kGatherChunks);
+    for (int64_t cblk = (int64_t)blockIdx.x * (256 * kGatherChunks); cblk < nchunks; cblk += (int64_t)gridDim.x * (256 * kGatherChunks)) {
     const int64_t s_blk = cblk * 16 - mis;
     const int64_t sb = s_blk < 0 ? 0 : s_blk;          // first stream byte of the block, clamped for the division
     const int64_t pblk = sb / L;
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256) gather_rows16_to_k(const uint8_t *__restr
             dst[sx] = src[(int64_t)perm[pr] * L + (sx - pr * L)];
         }
     }
+    }   // grid-stride loop (the grid is capped when the send overlaps the receive side's sort)
 }
 // rows of W 32-bit words (packed reads of short inputs): one thread per word
 __global__ void gather_words_to_k(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint32_t *__restrict__ perm, int64_t n, int W) {

@@ -265,13 +265,14 @@ class ShardedTransform:
     """One rank of a sharded run. `transform` is this rank's BoostTransform (its device = this rank's GPU);
     submit this rank's slice of the input to it as usual, then call flush() on every rank."""
 
-    def __init__(self, transform, comm, use_torch_stream=True, p2p=True):
+    def __init__(self, transform, comm, use_torch_stream=True, p2p=True, overlap=True):
         """p2p=True: fused pack + send over peer memory (CUDA IPC / NVLink stores from the gather kernels);
         p2p=False: rows are staged locally and moved by the comm's all-to-all (NCCL)."""
         self.t = transform
         self.comm = comm
         self.p2p = p2p and hasattr(comm, "map_peers")
         self.on_torch_stream = bool(use_torch_stream)
+        self.overlap = overlap      # row exchange overlapped with the receive side's sort (p2p only)
         self.stats = {}
         self._keep = None
         if use_torch_stream:
@@ -398,10 +399,25 @@ class ShardedTransform:
                 pg.aux, pg.packed, pg.qual1, pg.names, pg.seq2, pg.qual2 = [table[g][k] or None for k in range(6)]
                 pg.row_off = sum(mat[s][g] for s in range(r))
                 pg.name_off = sum(mat[s][G + g] for s in range(r))
-            _check(L.scb_shard_send(h, r, G, peers))
-            lap("exchange")
-            comm.barrier()   # every rank's writes have landed
             y.aux, y.packed, y.qual1, y.names, y.seq2, y.qual2 = [ptrs[k] for k in range(6)]
+            if self.overlap:
+                # what the receive side needs to SORT goes first; the quality / mate-2 rows then cross NVLink on a
+                # side stream while the received reads are sorted, and are only awaited before the emit
+                _check(L.scb_shard_send(h, r, G, peers, 1, 0))
+                lap("exchange")
+                comm.barrier()
+                _check(L.scb_shard_import(h, C.byref(y), n_chunks))
+                lap("import")
+                _check(L.scb_shard_send(h, r, G, peers, 2, 1))
+                _check(L.scb_shard_finish_sort(h))
+                lap("sort")
+                _check(L.scb_shard_send_wait(h))
+                lap("exchange_rows")
+                comm.barrier()   # every rank's row writes have landed
+            else:
+                _check(L.scb_shard_send(h, r, G, peers, 3, 0))
+                lap("exchange")
+                comm.barrier()   # every rank's writes have landed
         else:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -431,8 +447,9 @@ class ShardedTransform:
             y.qual2 = keep["qual2"].data_ptr() if "qual2" in keep else None
 
         # ---- sort + emit of the owned slice --------------------------------------------------------------------
-        _check(L.scb_shard_import(h, C.byref(y), n_chunks))
-        lap("import")
+        if not (self.p2p and self.overlap):
+            _check(L.scb_shard_import(h, C.byref(y), n_chunks))
+            lap("import")
         res = ScbResult()
         _check(L.scb_shard_finish(h, C.byref(res)))
         lap("emit")

@@ -107,7 +107,7 @@ def test_staged_exchange_path():
     o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
     orig = shard.ShardedTransform.__init__
 
-    def staged(self, transform, comm, use_torch_stream=True, p2p=True):
+    def staged(self, transform, comm, use_torch_stream=True, p2p=True, overlap=True):
         orig(self, transform, comm, use_torch_stream, p2p=False)
     shard.ShardedTransform.__init__ = staged
     try:
@@ -115,3 +115,20 @@ def test_staged_exchange_path():
     finally:
         shard.ShardedTransform.__init__ = orig
     util.assert_sharded_same(o, ranks)
+
+
+def test_unoverlapped_p2p_exchange_path():
+    # fused peer writes in one synchronous send (overlap=False)
+    from scalce_b200 import shard
+    cores, b, q1, q2, _ = util.make_case(15000, 100, seed=64, paired=True, L2=60)
+    o = util.run_oracle(cores, b, q1, q2, paired=True, bucket_set_bytes=1 << 20)
+    orig = shard.ShardedTransform.__init__
+
+    def plain(self, transform, comm, use_torch_stream=True, p2p=True, overlap=True):
+        orig(self, transform, comm, use_torch_stream, p2p=True, overlap=False)
+    shard.ShardedTransform.__init__ = plain
+    try:
+        ranks = util.run_sharded_loopback(cores, b, q1, q2, 3, paired=True, bucket_set_bytes=1 << 20)
+    finally:
+        shard.ShardedTransform.__init__ = orig
+    util.assert_sharded_same(o, ranks, paired=True)
