@@ -521,12 +521,13 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     cudaStream_t st = h->st;
     const int64_t n = h->cur.n;
     const int nb1 = h->tab.n_buckets + 1;
-    int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)nb1 * 8));
+    const int P = (nb1 + 3) & ~3;   // row pitch: 128-bit rows
+    int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)P * 8));
     const char *force = getenv("SCB_RESOLVE");
     if (!(W >= 1 && n > 0 && reads_in_job < 0xffffffffull && !(force && !strcmp(force, "seq")))) return false;
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-    const size_t smem = (size_t)W * nb1 * 8;
+    const size_t smem = (size_t)W * P * 8;
     SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
@@ -534,11 +535,12 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
     h->sh_W = W; h->sh_grid = grid;
-    h->sh_sel.alloc((size_t)n * 2, st); h->sh_base.alloc((size_t)nb1 * 4, st);
-    h->sh_H.alloc(max_sub * nb1 * 4, st); h->sh_S.alloc(max_sub * nb1 * 4, st);
-    h->sh_Csum.alloc((size_t)grid * nb1 * 4, st); h->sh_Cpre.alloc((size_t)grid * nb1 * 4, st);
+    h->sh_sel.alloc((size_t)n * 2, st); h->sh_base.alloc((size_t)P * 4, st);
+    h->sh_H.alloc(max_sub * P * 4, st);
+    h->sh_Csum.alloc((size_t)grid * P * 4, st); h->sh_Cpre.alloc((size_t)grid * P * 4, st);
     h->sh_changed.alloc((size_t)kRdMaxRounds * 4, st); h->sh_stat.alloc(8, st);
     h->sh_tot.alloc((size_t)(nb1 + 1) * 4, st);
+    SCB_CUDA(cudaMemsetAsync(h->sh_base.p, 0, (size_t)P * 4, st));
     SCB_CUDA(cudaMemsetAsync(h->sh_sel.p, 0xff, (size_t)n * 2, st));
     return true;
 }
@@ -548,7 +550,8 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     cudaStream_t st = h->st;
     const int nb1 = h->tab.n_buckets + 1;
     const int W = h->sh_W, grid = h->sh_grid;
-    const size_t smem = (size_t)W * nb1 * 8;
+    const int P = (nb1 + 3) & ~3;
+    const size_t smem = (size_t)W * P * 8;
     if (mode != 2) {   // a warm round reuses the block list of the round before
         h->sh_blk.alloc(blk.size() * 8, st);
         SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
@@ -557,10 +560,10 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)(mode == 0 ? kRdMaxRounds : 1) * 4, st));
     RdParams rp;
     rp.n = h->cur.n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
-    rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = h->sh_S.as<uint32_t>();
+    rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = nullptr;
     rp.Csum = h->sh_Csum.as<uint32_t>(); rp.Cpre = h->sh_Cpre.as<uint32_t>(); rp.changed = h->sh_changed.as<uint32_t>(); rp.blk = h->sh_blk.as<int64_t>();
     rp.nblk = (int)blk.size() - 1; rp.nb1 = nb1; rp.W = W; rp.status = h->sh_stat.as<int>(); rp.rounds_out = h->sh_stat.as<int>() + 1;
-    rp.g0 = g0; rp.mode = mode; rp.tot_out = tot_out;
+    rp.g0 = g0; rp.mode = mode; rp.tot_out = tot_out; rp.pitch = P;
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }

@@ -27,6 +27,7 @@ constexpr int kRdMaxWarps = 16;
 constexpr int kRdRegCands = 8;          // candidates kept in registers per read
 constexpr uint32_t kNoSel = 0xffffu;
 constexpr int kRdMaxRounds = 1 << 16;
+constexpr int kRdBatch = 6;             // 128-bit histogram rows fetched together in the P / E phases
 
 struct RdParams {
     int64_t n;
@@ -38,6 +39,7 @@ struct RdParams {
     uint32_t *changed;            // [kRdMaxRounds]
     const int64_t *blk;           // [nblk+1] block boundaries
     int nblk, nb1, W;
+    int pitch;                    // row pitch of every [..][nb1] array here and in shared memory: nb1 rounded up to 4 (128-bit rows)
     int *status;                  // 0 ok, 1 round cap hit
     int *rounds_out;
     unsigned long long *tstamps;  // optional [rounds][8] globaltimer stamps of CTA 0 (profiling aid)
@@ -160,15 +162,24 @@ __device__ __forceinline__ uint32_t rd_sweep(const RdParams &p, int64_t lo, int6
     return changed;
 }
 
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ uint4 sub4(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ uint4 guess4(uint4 b0, int64_t off, int64_t n0) {
+    return make_uint4(rd_guess(b0.x, off, n0), rd_guess(b0.y, off, n0), rd_guess(b0.z, off, n0), rd_guess(b0.w, off, n0));
+}
+
 __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams p) {
-    extern __shared__ uint32_t sm_cnt[];   // [W][nb1] populations, then [W][nb1] per-step lane tags
-    uint32_t *sm_tag = sm_cnt + (size_t)p.W * p.nb1;
+    extern __shared__ __align__(16) uint32_t sm_cnt[];   // [W][pitch] populations, then [W][pitch] per-step lane tags
+    const int W = p.W, nb1 = p.nb1, P = p.pitch, Q = p.pitch >> 2;   // Q = 128-bit quads per row
+    uint32_t *sm_tag = sm_cnt + (size_t)W * P;
     cg::grid_group grid = cg::this_grid();
-    const int W = p.W, nb1 = p.nb1;
     const int w = threadIdx.x >> 5, l = lane_id();
     const int ncta = gridDim.x, c = blockIdx.x;
     const int total_warps = ncta * W;
-    for (int k = threadIdx.x; k < W * nb1; k += blockDim.x) sm_tag[k] = 0;
+    uint4 *sm_cnt4 = (uint4 *)sm_cnt;
+    const uint4 *base4 = (const uint4 *)p.base;
+    uint4 *H4 = (uint4 *)p.H, *Csum4 = (uint4 *)p.Csum, *Cpre4 = (uint4 *)p.Cpre;
+    for (int k = threadIdx.x; k < W * P; k += blockDim.x) sm_tag[k] = 0;
     __syncthreads();
     int round = 0;
     for (int b = 0; b < p.nblk; b++) {
@@ -186,21 +197,24 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             // ---- P: start counts of my subtiles, straight into the warps' shared-memory counters ----
             // first round of a block: no histogram of the block exists yet; start from the populations
             // before the block, extrapolated proportionally to the subtile's position (only a guess:
-            // it shortens convergence, the fixed point does not depend on it)
+            // it shortens convergence, the fixed point does not depend on it). Four buckets per thread
+            // and 128-bit loads / stores: the phase is bound by the number of memory requests.
             RD_STAMP(0);
             const int kl = (c < nact) ? (t_hi - t_lo) : 0;
-            for (int col = threadIdx.x; col < nb1 && kl > 0; col += blockDim.x) {
-                const uint32_t b0 = p.base[col];
+            for (int q = threadIdx.x; q < Q && kl > 0; q += blockDim.x) {
+                const uint4 b0 = base4[q];
                 if (first) {
-                    for (int tl = 0; tl < kl; tl++) sm_cnt[(size_t)tl * nb1 + col] = b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0);
+                    for (int tl = 0; tl < kl; tl++) sm_cnt4[(size_t)tl * Q + q] = add4(b0, guess4(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0));
                 } else {
-                    uint32_t hv[kRdMaxWarps];
+                    uint4 run = add4(b0, Cpre4[(size_t)c * Q + q]);
+                    for (int tb = 0; tb < kl; tb += kRdBatch) {   // loads of a batch are in flight together
+                        uint4 hv[kRdBatch];
 #pragma unroll
-                    for (int tl = 0; tl < kRdMaxWarps; tl++) hv[tl] = tl < kl ? p.H[(size_t)(t_lo + tl) * nb1 + col] : 0u;
-                    uint32_t run = b0 + p.Cpre[(size_t)c * nb1 + col];
+                        for (int u = 0; u < kRdBatch; u++) hv[u] = tb + u < kl ? H4[(size_t)(t_lo + tb + u) * Q + q] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int tl = 0; tl < kRdMaxWarps; tl++)
-                        if (tl < kl) { sm_cnt[(size_t)tl * nb1 + col] = run; run += hv[tl]; }
+                        for (int u = 0; u < kRdBatch; u++)
+                            if (tb + u < kl) { sm_cnt4[(size_t)(tb + u) * Q + q] = run; run = add4(run, hv[u]); }
+                    }
                 }
             }
             __syncthreads();
@@ -210,37 +224,39 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             if (w < kl) {
                 const int t = t_lo + w;
                 const int64_t lo = n0 + (int64_t)t * ts, hi = min(n1, lo + ts);
-                ch = rd_sweep(p, lo, hi, sm_cnt + (size_t)w * nb1, sm_tag + (size_t)w * nb1);
+                ch = rd_sweep(p, lo, hi, sm_cnt + (size_t)w * P, sm_tag + (size_t)w * P);
             }
             ch = __reduce_add_sync(0xffffffffu, ch);
             if (l == 0 && ch) atomicAdd(&p.changed[round], ch);
             __syncthreads();
             RD_STAMP(2);
             // ---- new subtile histograms = final counters - start counts; chunk total ------------------
-            for (int col = threadIdx.x; col < nb1 && kl > 0; col += blockDim.x) {
-                const uint32_t b0 = p.base[col];
-                uint32_t tot = 0;
+            for (int q = threadIdx.x; q < Q && kl > 0; q += blockDim.x) {
+                const uint4 b0 = base4[q];
+                uint4 tot = make_uint4(0, 0, 0, 0);
                 if (first) {
                     for (int tl = 0; tl < kl; tl++) {
-                        const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - (b0 + rd_guess(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0));
-                        p.H[(size_t)(t_lo + tl) * nb1 + col] = hn;
-                        tot += hn;
+                        const uint4 hn = sub4(sm_cnt4[(size_t)tl * Q + q], add4(b0, guess4(b0, (int64_t)(t_lo + tl) * ts, p.g0 + n0)));
+                        H4[(size_t)(t_lo + tl) * Q + q] = hn;
+                        tot = add4(tot, hn);
                     }
                 } else {
-                    uint32_t hv[kRdMaxWarps];
+                    uint4 run = add4(b0, Cpre4[(size_t)c * Q + q]);
+                    for (int tb = 0; tb < kl; tb += kRdBatch) {
+                        uint4 hv[kRdBatch];
 #pragma unroll
-                    for (int tl = 0; tl < kRdMaxWarps; tl++) hv[tl] = tl < kl ? p.H[(size_t)(t_lo + tl) * nb1 + col] : 0u;
-                    uint32_t run = b0 + p.Cpre[(size_t)c * nb1 + col];
+                        for (int u = 0; u < kRdBatch; u++) hv[u] = tb + u < kl ? H4[(size_t)(t_lo + tb + u) * Q + q] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int tl = 0; tl < kRdMaxWarps; tl++)
-                        if (tl < kl) {
-                            const uint32_t hn = sm_cnt[(size_t)tl * nb1 + col] - run;
-                            run += hv[tl];
-                            p.H[(size_t)(t_lo + tl) * nb1 + col] = hn;
-                            tot += hn;
-                        }
+                        for (int u = 0; u < kRdBatch; u++)
+                            if (tb + u < kl) {
+                                const uint4 hn = sub4(sm_cnt4[(size_t)(tb + u) * Q + q], run);
+                                run = add4(run, hv[u]);
+                                H4[(size_t)(t_lo + tb + u) * Q + q] = hn;
+                                tot = add4(tot, hn);
+                            }
+                    }
                 }
-                p.Csum[(size_t)c * nb1 + col] = tot;
+                Csum4[(size_t)c * Q + q] = tot;
             }
             RD_STAMP(3);
             __threadfence();
@@ -249,23 +265,32 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             // ---- column scan over chunk totals; on convergence fold the block into base ---------------
             const uint32_t chg = *((volatile uint32_t *)&p.changed[round]);
             const bool done = (chg == 0);
-            {   // one warp per column; lanes stride over the chunks, shuffle scan across lanes
+            {   // one warp per quad of columns; lanes stride over the chunks, shuffle scan across lanes
                 const int gw = blockIdx.x * W + w, tw = gridDim.x * W;
-                for (int col = gw; col < nb1; col += tw) {
-                    uint32_t v[5];   // grid <= 160 CTAs
+                for (int q = gw; q < Q; q += tw) {
+                    // lane l owns chunks 5l .. 5l+4 (grid <= 160 CTAs): serial prefix inside the lane, one shuffle
+                    // scan of the lane totals across the warp
+                    uint4 v[5];
 #pragma unroll
-                    for (int q = 0; q < 5; q++) { const int cc = q * 32 + l; v[q] = cc < nact ? p.Csum[(size_t)cc * nb1 + col] : 0u; }
-                    uint32_t carry = 0;
+                    for (int u = 0; u < 5; u++) { const int cc = l * 5 + u; v[u] = cc < nact ? Csum4[(size_t)cc * Q + q] : make_uint4(0, 0, 0, 0); }
+                    uint4 mine = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int q = 0; q < 5; q++) {
-                        const int cc = q * 32 + l;
-                        uint32_t inc = warp_incl_scan(v[q]);
-                        if (cc < nact) p.Cpre[(size_t)cc * nb1 + col] = carry + inc - v[q];
-                        carry += __shfl_sync(0xffffffffu, inc, 31);
-                    }
+                    for (int u = 0; u < 5; u++) { const uint4 t = v[u]; v[u] = mine; mine = add4(mine, t); }   // v[u] = exclusive inside the lane
+                    const uint4 inc = make_uint4(warp_incl_scan(mine.x), warp_incl_scan(mine.y), warp_incl_scan(mine.z), warp_incl_scan(mine.w));
+                    const uint4 ex = sub4(inc, mine);
+#pragma unroll
+                    for (int u = 0; u < 5; u++) { const int cc = l * 5 + u; if (cc < nact) Cpre4[(size_t)cc * Q + q] = add4(ex, v[u]); }
+                    uint4 carry;
+                    carry.x = __shfl_sync(0xffffffffu, inc.x, 31); carry.y = __shfl_sync(0xffffffffu, inc.y, 31);
+                    carry.z = __shfl_sync(0xffffffffu, inc.z, 31); carry.w = __shfl_sync(0xffffffffu, inc.w, 31);
                     if (l == 0) {
-                        if (p.mode != 0) p.tot_out[col] = carry;
-                        else if (done) p.base[col] += carry;
+                        const uint32_t cv[4] = {carry.x, carry.y, carry.z, carry.w};
+                        for (int j = 0; j < 4; j++) {
+                            const int col = 4 * q + j;
+                            if (col >= nb1) break;
+                            if (p.mode != 0) p.tot_out[col] = cv[j];
+                            else if (done) p.base[col] += cv[j];
+                        }
                     }
                 }
             }
