@@ -151,6 +151,8 @@ class FlushResult:
         self.merged_size = [res.merged_size[k] for k in range(N_STREAMS)]
         self.data_ptr = [res.data[k] for k in range(N_STREAMS)]
         self.merged_ptr = [res.merged[k] for k in range(N_STREAMS)]
+        # device pointers of the per-read arrays (int32, input order) and of perm (uint32, output order)
+        self.array_ptr = dict(node_id=res.bucket_id, core=res.core_idx, end=res.end, chunk=res.chunk, perm=res.perm)
 
     def stream(self, k, chunk=-1) -> bytes:
         """Bytes of stream k for a flush chunk (the t_%03d_k.tmp contents) or merged (chunk=-1)."""
@@ -161,6 +163,23 @@ class FlushResult:
         buf = np.empty(max(n, 1), dtype=np.uint8)
         _check(load_library().scb_copy_stream(self._tr._h, k, chunk, buf.ctypes.data_as(C.c_void_p), n))
         return buf[:n].tobytes()
+
+    def torch_view(self, what, n=None):
+        """Zero-copy torch view of a device-resident result: 'perm' / 'node_id' / 'core' / 'end' / 'chunk' (int32; perm's
+        uint32 bit patterns) or a stream number (uint8, all chunks). Valid until the next submit / flush."""
+        import torch
+
+        class _P:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        dev = torch.device("cuda", self._tr.cfg.device)
+        if isinstance(what, int):
+            nb = self.chunk_off[what][-1]
+            return torch.as_tensor(_P(self.data_ptr[what], nb), device=dev) if nb else torch.empty(0, dtype=torch.uint8, device=dev)
+        cnt = self.n_reads if n is None else n
+        if cnt == 0:
+            return torch.empty(0, dtype=torch.int32, device=dev)
+        return torch.as_tensor(_P(self.array_ptr[what], cnt * 4), device=dev).view(torch.int32)
 
     def debug(self, n_local=None):
         """Per-read arrays in input order (of the rank's own shard after a sharded run: pass n_local) and perm."""
