@@ -215,13 +215,6 @@ struct KeyHead {   // 1 where the segment id (top `bits` bits of the sorted key,
         return ((keys[p] >> shift) != (keys[p - 1] >> shift)) ? 1u : 0u;
     }
 };
-struct NameRec2 {  // bytes of stream 0 for the p-th emitted read
-    const uint32_t *perm; const int64_t *name_off;
-    __device__ __forceinline__ uint64_t operator()(int64_t p) const {
-        uint32_t i = perm[p];
-        return (uint64_t)(ldg_g64(name_off + i + 1) - ldg_g64(name_off + i)) + 1;
-    }
-};
 struct SegTab {
     uint32_t *pos;      // [n_seg+1] first output position (pos[n_seg] = n)
     uint32_t *rank;     // [n_seg] bucket rank (nb = root)
@@ -243,49 +236,7 @@ __global__ void seg_table_k(KeyHead kh, const uint32_t *__restrict__ hsum, int64
     int lv = r == (uint32_t)nb ? 0 : rank_level[r];
     t.recsz[m] = (uint32_t)(sz_read(L1 - lv) + sz_meta);
 }
-struct SegBytes {   // stream-1 bytes of a segment
-    const uint32_t *pos, *recsz;
-    __device__ __forceinline__ uint64_t operator()(int64_t m) const { return (uint64_t)(pos[m + 1] - pos[m]) * recsz[m]; }
-};
-
 // ---- emit ---------------------------------------------------------------------------------------------
-struct Emit2Params {
-    const uint8_t *qual1, *names, *seq2, *qual2;
-    const int64_t *name_off;
-    const uint32_t *packed; int PW;
-    const uint16_t *endv;
-    const uint32_t *perm;
-    const uint32_t *hsum;              // [n] segment index of position p = hsum[p] + head(p) - 1 -> stored as sidx
-    const uint32_t *seg_pos, *seg_recsz, *seg_rank;
-    const uint64_t *seg_off;           // [n_seg] stream-1 byte offset of the segment
-    const uint8_t *rank_level;
-    const uint64_t *offN;              // [n+1]
-    int64_t n;
-    int L1, L2, use_names, use_quals, paired, sz_meta, nb;
-    uint8_t *oN, *oR, *oQ, *oR2, *oQ2;
-};
-
-// copy `len` bytes src -> dst (arbitrary alignments) with 4-byte stores; lanes h, h+16, ... of a half warp
-__device__ __forceinline__ void copy_bytes16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int len, int h) {
-    const uintptr_t d0 = (uintptr_t)dst;
-    const int head = (int)((4 - (d0 & 3)) & 3);              // bytes before the first aligned dst word
-    if (len <= 8 + head) { for (int k = h; k < len; k += 16) dst[k] = src[k]; return; }
-    if (h < head) dst[h] = src[h];
-    const int nw = (len - head) >> 2;                         // full aligned dst words
-    const uint8_t *s0 = src + head;
-    const int sh = (int)(((uintptr_t)s0 & 3) * 8);
-    const uint32_t *sa = (const uint32_t *)((uintptr_t)s0 & ~(uintptr_t)3);
-    uint32_t *da = (uint32_t *)(dst + head);
-    for (int k = h; k < nw; k += 16) {
-        uint32_t lo = sa[k];
-        uint32_t v = lo;
-        if (sh) { uint32_t hi = sa[k + 1]; v = __funnelshift_r(lo, hi, sh); }
-        da[k] = v;
-    }
-    const int done = head + (nw << 2);
-    if (h < len - done) dst[done + h] = src[done + h];
-}
-
 // ---- stream 2 / 5: qualities are a pure row gather: out row p <- in row perm[p] -----------------------
 // One thread per 16 output bytes (the output is dense, so stores are aligned STG.128 and fully
 // coalesced); a chunk may straddle two rows. Sources are unaligned: two aligned 16-byte loads and a
@@ -410,52 +361,6 @@ struct EmitMParams {
     int64_t n; int L1, sz_meta;
     uint8_t *oN, *oR;
 };
-
-// ---- stream 0: names, one thread per read --------------------------------------------------------------
-__global__ void emit_names_m_k(EmitMParams e) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= e.n) return;
-    const uint64_t m = e.ms[p];
-    const int64_t a = meta_name_off(m);
-    const int nl = meta_namelen(m);
-    uint8_t *d = e.oN + e.offN[p];
-    d[0] = (uint8_t)nl;                                                           // names.cpp:58
-    for (int k = 0; k < nl; k++) d[1 + k] = (uint8_t)ldg_g64(e.names + a + k);
-}
-
-// ---- stream 1: rotated 2-bit reads + end marker, one thread per (read, 4 output bytes) ------------------
-__global__ void __launch_bounds__(256) emit_reads_m_k(EmitMParams e, uint32_t NW /* words per record, max */, int64_t n_threads) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_threads) return;
-    // t < 2^32 is guaranteed by the launcher when this 32-bit division is used
-    const uint32_t p = (uint32_t)t / NW, w = (uint32_t)t - p * NW;
-    const uint64_t m = e.ms[p];
-    // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
-    const int lv = meta_lvl(m), end = meta_end(m);
-    const int tail = e.L1 - end, total = e.L1 - lv;
-    const int nbytes = sz_read(total);
-    const int recsz = nbytes + e.sz_meta;
-    if ((int)(4 * w) >= recsz) return;
-    uint8_t *d = e.oR + e.offR[p] + 4 * w;
-    uint32_t v = 0;
-    if ((int)(4 * w) < nbytes) {
-        // 16 rotated bases: `a` of them come from behind the core, the rest from the front of the read;
-        // whatever lies past `total` is zero fill
-        const uint32_t *row = e.packed + (int64_t)e.perm[p] * e.PW;   // rows have 2 words of slack behind the last one
-        const int j0 = 16 * (int)w;
-        int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
-        int nv = total - j0; nv = nv > 16 ? 16 : nv;
-        if (a > 0) v = pk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
-        if (a < 16) v |= pk_bits32(row, j0 + a - tail) >> (2 * a);
-        if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int b = 4 * (int)w + k;                          // byte index inside the record
-        if (b < nbytes) d[k] = (uint8_t)(v >> (24 - 8 * k));
-        else if (b < recsz) d[k] = (uint8_t)((uint32_t)end >> (8 * (b - nbytes)));   // low bytes of int16 end, reads.cpp:130
-    }
-}
 
 // ---- dense writers: records of a CTA are assembled in shared memory, then leave as aligned 16-byte stores ----
 // sbuf[(g0 & 15) + i] holds stream byte g0 + i for i in [0, len); gbase is the (16-byte aligned) start of the stream

@@ -1,10 +1,10 @@
-// pipeline.cuh - kernels of the boosting transform (v1: straightforward, every stage on the GPU).
-//   scan     : DFA walk per read -> max core level + ordered distinct candidates   (aho_search minus the counts)
-//   resolve  : the stateful tie-break on running bucket populations               (reads.cpp:420-421,246)
-//   sizes    : rd.sz + sizeof(bin_node) accounting and flush-chunk ids            (compress.cpp:675-715)
-//   keys     : (segment, suffix-key prefix) sort keys                              (reads.cpp:547-634 order)
-//   ties     : refinement of equal-prefix runs with further key bases
-//   emit     : rotate + 2-bit pack, gather of names / qualities / mate 2, meta     (reads.cpp:432-461, 91-180)
+// pipeline.cuh - the general-case kernels of the boosting transform and small helpers shared by all stages.
+//   scan_k        : DFA walk per read with the table in global memory (automata too large for shared memory)
+//   resolve_seq_k : the stateful tie-break, one warp in input order (bucket sets too large for the dense engine)
+//   sizes         : rd.sz + sizeof(bin_node) accounting and flush-chunk ids            (compress.cpp:675-715)
+//   ties          : detection / compaction of equal-prefix runs for the iterative refinement rounds
+//   debug arrays  : per-read bucket id / core index as the reference writes them to meta
+// The shared-memory scan is scan_smem.cuh, the dense tie-break resolve_dense.cuh, the output side emit2.cuh.
 #pragma once
 #include "common.cuh"
 #include "prims.cuh"
@@ -177,31 +177,8 @@ __global__ void chunk_ids_k(const uint32_t *__restrict__ chunk_start, int n_chun
 // -------------------------------------------------------------------------------------------------
 // sort keys
 // -------------------------------------------------------------------------------------------------
-// `nbases` bases of the in-bucket sort key of read i starting at key offset `from`:
-// key = s[end..L) right-padded with A (reads.cpp:547-559); MSB-first 2 bits per base.
-__device__ __forceinline__ uint64_t key_bits(const uint8_t *__restrict__ s, int L, int end, int from, int nbases) {
-    uint64_t v = 0;
-    for (int j = 0; j < nbases; j++) {
-        int q = end + from + j;
-        v = (v << 2) | (q < L ? base_code(s[q]) : 0u);
-    }
-    return v;
-}
-
 __device__ __forceinline__ uint32_t bucket_ord(uint32_t rank, int nb, int root_pos) {
     return rank == (uint32_t)nb ? (uint32_t)root_pos : rank + (rank >= (uint32_t)root_pos ? 1u : 0u);
-}
-
-// key = [seg : seg_bits][first pb key bases : 2*pb][zero fill]
-__global__ void build_keys_k(const uint8_t *__restrict__ seq, int64_t n, int L, const uint32_t *__restrict__ asg,
-                             const uint16_t *__restrict__ endv, const uint32_t *__restrict__ chunk, int nb, int root_pos,
-                             int seg_bits, int pb, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t seg = (uint64_t)(chunk ? chunk[i] : 0u) * (uint64_t)(nb + 1) + bucket_ord(asg[i], nb, root_pos);
-    uint64_t kb = key_bits(seq + i * (int64_t)L, L, endv[i], 0, pb);
-    keys[i] = (seg_bits ? (seg << (64 - seg_bits)) : 0ull) | (pb ? (kb << (64 - seg_bits - 2 * pb)) : 0ull);
-    vals[i] = (uint32_t)i;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -269,157 +246,10 @@ __global__ void tie_gather_sparse_k(HeadAtPos hp, const uint32_t *__restrict__ h
     c_idx[c] = idx_in[p];
     c_grp[c] = hsum[c] + hp(c) - 1u;   // hsum exclusive
 }
-__global__ void tie_rekey_k(const uint8_t *__restrict__ seq, int L, const uint16_t *__restrict__ endv,
-                            const uint32_t *__restrict__ c_idx, const uint32_t *__restrict__ c_grp, int64_t m, int grp_bits,
-                            int from, int nbases, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m) return;
-    uint32_t i = c_idx[c];
-    uint64_t kb = key_bits(seq + (int64_t)i * L, L, endv[i], from, nbases);
-    keys[c] = (grp_bits ? ((uint64_t)c_grp[c] << (64 - grp_bits)) : 0ull) | (kb << (64 - grp_bits - 2 * nbases));
-    vals[c] = i;
-}
 __global__ void tie_writeback_k(const uint32_t *__restrict__ c_pos, const uint32_t *__restrict__ sorted_idx, int64_t m,
                                 uint32_t *__restrict__ perm) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < m) perm[c_pos[c]] = sorted_idx[c];
-}
-
-// -------------------------------------------------------------------------------------------------
-// emit
-// -------------------------------------------------------------------------------------------------
-struct EmitParams {
-    const uint8_t *seq1, *qual1, *names, *seq2, *qual2;
-    const int64_t *name_off;
-    const uint32_t *asg; const uint16_t *endv; const uint8_t *lvl; const uint32_t *chunk;
-    const uint32_t *perm;
-    int64_t n;
-    int L1, L2, use_names, use_quals, paired, sz_meta, nb, root_pos;
-};
-struct NameRec {  // bytes of stream 0 for the p-th emitted read
-    EmitParams e;
-    __device__ __forceinline__ uint64_t operator()(int64_t p) const {
-        if (!e.use_names) return 0;
-        uint32_t i = e.perm[p];
-        return (uint64_t)(e.name_off[i + 1] - e.name_off[i]) + 1;
-    }
-};
-struct ReadRec {  // bytes of stream 1: packed rotated read + end marker (reads.cpp:128-130)
-    EmitParams e;
-    __device__ __forceinline__ uint64_t operator()(int64_t p) const {
-        uint32_t i = e.perm[p];
-        return (uint64_t)(sz_read(e.L1 - (int)e.lvl[i]) + e.sz_meta);
-    }
-};
-
-// one warp per emitted read; byte-granular copies (v1)
-__global__ void __launch_bounds__(256) emit_k(EmitParams e, const uint64_t *__restrict__ offN, const uint64_t *__restrict__ offR,
-                                              uint8_t *__restrict__ oN, uint8_t *__restrict__ oR, uint8_t *__restrict__ oQ,
-                                              uint8_t *__restrict__ oR2, uint8_t *__restrict__ oQ2) {
-    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (p >= e.n) return;
-    const int l = lane_id();
-    const uint32_t i = e.perm[p];
-    if (e.use_names) {
-        int64_t a = e.name_off[i];
-        int nl = (int)(e.name_off[i + 1] - a);
-        uint8_t *d = oN + offN[p];
-        if (l == 0) d[0] = (uint8_t)nl;                    // names.cpp:58
-        for (int k = l; k < nl; k += 32) d[1 + k] = e.names[a + k];
-    }
-    {   // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level)   reads.cpp:432-461
-        const uint8_t *s = e.seq1 + (int64_t)i * e.L1;
-        int lv = e.lvl[i], end = e.endv[i];
-        int tail = e.L1 - end;         // bases after the core
-        int total = e.L1 - lv;
-        int nbytes = sz_read(total);
-        uint8_t *d = oR + offR[p];
-        for (int b = l; b < nbytes; b += 32) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                int j = 4 * b + t;
-                uint32_t c = 0;
-                if (j < total) c = base_code(s[j < tail ? end + j : j - tail]);
-                v = (v << 2) | c;
-            }
-            d[b] = (uint8_t)v;
-        }
-        if (l < e.sz_meta) d[nbytes + l] = (uint8_t)((uint32_t)end >> (8 * l));   // low bytes of int16 end
-    }
-    if (e.use_quals) {
-        const uint8_t *q = e.qual1 + (int64_t)i * e.L1;
-        uint8_t *d = oQ + p * (int64_t)e.L1;
-        for (int k = l; k < e.L1; k += 32) d[k] = q[k];
-    }
-    if (e.paired) {
-        const uint8_t *s = e.seq2 + (int64_t)i * e.L2;
-        int nbytes = sz_read(e.L2);
-        uint8_t *d = oR2 + p * (int64_t)nbytes;
-        for (int b = l; b < nbytes; b += 32) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                int j = 4 * b + t;
-                v = (v << 2) | (j < e.L2 ? base_code(s[j]) : 0u);
-            }
-            d[b] = (uint8_t)v;
-        }
-        if (e.use_quals) {
-            const uint8_t *q = e.qual2 + (int64_t)i * e.L2;
-            uint8_t *dq = oQ2 + p * (int64_t)e.L2;
-            for (int k = l; k < e.L2; k += 32) dq[k] = q[k];
-        }
-    }
-}
-
-// segment of the p-th emitted read: chunk-major (per-flush files) or bucket-major (merged)
-struct SegOf {
-    EmitParams e; int n_chunks; int merged;
-    __device__ __forceinline__ uint64_t operator()(int64_t p) const {
-        uint32_t i = e.perm[p];
-        uint64_t o = bucket_ord(e.asg[i], e.nb, e.root_pos), c = e.chunk ? e.chunk[i] : 0u;
-        return merged ? o : c * (uint64_t)(e.nb + 1) + o;
-    }
-};
-struct SegHead {
-    SegOf s;
-    __device__ __forceinline__ uint32_t operator()(int64_t p) const { return (p == 0 || s(p) != s(p - 1)) ? 1u : 0u; }
-};
-__global__ void seg_heads_k(SegOf s, const uint32_t *__restrict__ hsum, int64_t n, uint32_t *__restrict__ hpos) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (p == 0 || s(p) != s(p - 1)) hpos[hsum[p]] = (uint32_t)p;
-}
-// one meta record per segment: int32 id, int32 core, int64 tN, tR, tQ [, tR2, tQ2]   reads.cpp:160-176
-__global__ void meta_k(SegOf s, const uint32_t *__restrict__ hpos, int64_t n_seg, const uint64_t *__restrict__ offN,
-                       const uint64_t *__restrict__ offR, const int32_t *__restrict__ rank_node_id,
-                       const int32_t *__restrict__ rank_core, uint8_t *__restrict__ meta, int64_t *__restrict__ chunk_first /*[2][n_chunks]: pos, meta idx*/) {
-    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_seg) return;
-    const EmitParams &e = s.e;
-    int64_t p0 = hpos[m], p1 = (m + 1 < n_seg) ? (int64_t)hpos[m + 1] : e.n;
-    uint32_t i = e.perm[p0];
-    uint32_t r = e.asg[i];
-    int32_t id = r == (uint32_t)e.nb ? SCB_ROOT_ID_DEV : rank_node_id[r];
-    int32_t core = r == (uint32_t)e.nb ? SCB_ROOT_ID_DEV : rank_core[r];
-    int64_t cnt = p1 - p0;
-    int nlen = 3 + 2 * e.paired;
-    uint8_t *d = meta + m * (int64_t)(8 + 8 * nlen);
-    int64_t v[5];
-    v[0] = e.use_names ? (int64_t)(offN[p1] - offN[p0]) : 0;
-    v[1] = (int64_t)(offR[p1] - offR[p0]);
-    v[2] = e.use_quals ? cnt * e.L1 : 0;
-    v[3] = cnt * sz_read(e.L2);
-    v[4] = e.use_quals ? cnt * e.L2 : 0;
-    memcpy(d, &id, 4); memcpy(d + 4, &core, 4);
-    for (int k = 0; k < nlen; k++) memcpy(d + 8 + 8 * k, &v[k], 8);
-    if (chunk_first) {
-        uint32_t c = e.chunk ? e.chunk[i] : 0u;
-        bool first = (m == 0);
-        if (!first) { uint32_t ip = e.perm[hpos[m - 1]]; first = (e.chunk ? e.chunk[ip] : 0u) != c; }
-        if (first) { chunk_first[c] = p0; chunk_first[s.n_chunks + c] = m; }
-    }
 }
 
 // per-read arrays the reference exposes through meta / debugging
@@ -444,9 +274,4 @@ __global__ void widen_u16_k(const uint16_t *__restrict__ a, int64_t n, int32_t *
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i];
 }
-__global__ void fill_u32_k(uint32_t *a, int64_t n, uint32_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = v;
-}
-
 }  // namespace scb
