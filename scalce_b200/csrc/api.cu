@@ -159,6 +159,7 @@ struct scb_handle {
     int64_t sh_n_local = 0;    // reads of this rank's input shard
     int sh_W = 0, sh_grid = 0; // dense-resolve geometry
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
+    DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
     std::vector<int64_t> sh_cnt_reads, sh_cnt_name_bytes, sh_first, sh_nbytes;
@@ -537,6 +538,13 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     h->sh_W = W; h->sh_grid = grid;
     h->sh_sel.alloc((size_t)n * 2, st); h->sh_base.alloc((size_t)P * 4, st);
     h->sh_H.alloc(max_sub * P * 4, st);
+    h->sh_S0.alloc(max_sub * P * 4, st); h->sh_H0.alloc(max_sub * P * 4, st);
+    h->sh_frused.alloc(max_sub * 4, st);
+    h->sh_frbuf.alloc((size_t)n * 8 + 64, st);
+    h->sh_fridx.alloc((size_t)n * 4 + 64, st);
+    h->sh_incr_stat.alloc(32, st);
+    SCB_CUDA(cudaMemsetAsync(h->sh_frused.p, 0xff, max_sub * 4, st));
+    SCB_CUDA(cudaMemsetAsync(h->sh_incr_stat.p, 0, 32, st));
     h->sh_Csum.alloc((size_t)grid * P * 4, st); h->sh_Cpre.alloc((size_t)grid * P * 4, st);
     h->sh_changed.alloc((size_t)kRdMaxRounds * 4, st); h->sh_stat.alloc(8, st);
     h->sh_tot.alloc((size_t)(nb1 + 1) * 4, st);
@@ -564,6 +572,13 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     rp.Csum = h->sh_Csum.as<uint32_t>(); rp.Cpre = h->sh_Cpre.as<uint32_t>(); rp.changed = h->sh_changed.as<uint32_t>(); rp.blk = h->sh_blk.as<int64_t>();
     rp.nblk = (int)blk.size() - 1; rp.nb1 = nb1; rp.W = W; rp.status = h->sh_stat.as<int>(); rp.rounds_out = h->sh_stat.as<int>() + 1;
     rp.g0 = g0; rp.mode = mode; rp.tot_out = tot_out; rp.pitch = P;
+    rp.S0 = h->sh_S0.as<uint32_t>(); rp.H0 = h->sh_H0.as<uint32_t>(); rp.fr_buf = h->sh_frbuf.as<uint32_t>(); rp.fr_idx = h->sh_fridx.as<uint32_t>(); rp.fr_used = h->sh_frused.as<uint32_t>();
+    {
+        const char *e = getenv("SCB_RESOLVE_INCR");      // decision-margin threshold of the incremental rounds; 0 = every round sweeps in full
+        rp.incr_T = e ? atoi(e) : 1024;
+        if (nb1 > 0xffff) rp.incr_T = 0;                 // records hold bucket ranks in 16 bits
+    }
+    rp.incr_stat = getenv("SCB_RESOLVE_PROF") ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
@@ -587,6 +602,9 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
                     (ts[r * 8 + 4] - ts[r * 8 + 3]) * 1e-3, (ts[r * 8 + 5] - ts[r * 8 + 4]) * 1e-3, (ts[r * 8 + 6] - ts[r * 8 + 5]) * 1e-3);
         }
         fprintf(stderr, "resolve totals (us): P %.0f D %.0f E %.0f sync1 %.0f scan %.0f sync2 %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
+        unsigned long long is[4] = {0, 0, 0, 0};
+        SCB_CUDA(cudaMemcpy(is, h->sh_incr_stat.p, 32, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "resolve subtile sweeps: %llu full, %llu incremental, %llu incremental redone in full, %llu records replayed (T = %d)\n", is[0], is[1], is[2], is[3], rp.incr_T);
     }
     return stat[0];
 }

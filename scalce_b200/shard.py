@@ -331,8 +331,16 @@ class ShardedTransform:
         if G > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            # Rounds are enqueued one ahead of the convergence check: the "changed" count of round k is read back
+            # (pinned buffer + event) while round k+1 is already running, so the device never waits for the host. A round
+            # launched after the fixed point re-decides everything from the same inputs and changes nothing.
+            pipelined = self.on_torch_stream and not isinstance(comm, LoopbackComm)
+            inflight = []          # (event, pinned changed count, was_first)
+            if pipelined and not hasattr(self, "_pin"):
+                self._pin = [torch.empty(1, dtype=torch.int64, pin_memory=True) for _ in range(4)]   # allocated once: pinning is slow
             first = True
-            while True:
+            done = False
+            while not done:
                 if r > 0:
                     if first:   # guess: rank 0's histogram scaled to the reads before this shard (exact for rank 1)
                         if ns[0] > 0:
@@ -340,16 +348,25 @@ class ShardedTransform:
                         else:
                             bf = torch.zeros(ncols, dtype=torch.int32, device=dev)
                     else:
-                        bf = allt[:r, :ncols].sum(0, dtype=torch.int64).to(torch.int32)
-                    bf = bf.contiguous()
+                        bf = allt[:r, :ncols].sum(0, dtype=torch.int32)    # u32 bit patterns: wrap-around sum is the u32 sum
                     sync()
                     _check(L.scb_shard_resolve_round(h, C.c_void_p(bf.data_ptr()), before[r], 1 if first else 0, C.c_void_p(tot.data_ptr())))
                     sync()
                 allt = comm.allgather(tot)
                 rounds += 1
-                changed = int(allt[1:, ncols].to(torch.int64).sum().item())
-                if not first and changed == 0:
-                    break
+                chg = allt[1:, ncols].sum(dtype=torch.int64)
+                if pipelined:
+                    hb = self._pin[rounds % 4]
+                    hb.copy_(chg.view(1), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    inflight.append((ev, hb, first, bf if r > 0 else None))   # keeps bf alive until its round has run
+                    if len(inflight) == 2:
+                        ev0, hb0, f0, _ = inflight.pop(0)
+                        ev0.synchronize()
+                        done = (not f0) and int(hb0[0]) == 0
+                else:
+                    done = (not first) and int(chg.item()) == 0
                 first = False
             e1.record()
             torch.cuda.synchronize(dev)
