@@ -578,7 +578,7 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
         rp.incr_T = e ? atoi(e) : 1024;
         if (nb1 > 0xffff) rp.incr_T = 0;                 // records hold bucket ranks in 16 bits
     }
-    rp.incr_stat = getenv("SCB_RESOLVE_PROF") ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
+    rp.incr_stat = (getenv("SCB_RESOLVE_PROF") || getenv("SCB_RESOLVE_STAT")) ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
@@ -586,7 +586,17 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     void *args[] = {&rp};
     SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
-    if (mode != 0) { h->last_rounds++; return 0; }   // single round: nothing to read back, the stream orders the rest
+    if (mode != 0) {
+        h->last_rounds++;
+        if (getenv("SCB_RESOLVE_STAT")) {   // debugging aid: subtile sweeps of this round (synchronises)
+            unsigned long long is[4] = {0, 0, 0, 0};
+            SCB_CUDA(cudaStreamSynchronize(st));
+            SCB_CUDA(cudaMemcpy(is, h->sh_incr_stat.p, 32, cudaMemcpyDeviceToHost));
+            SCB_CUDA(cudaMemset(h->sh_incr_stat.p, 0, 32));
+            fprintf(stderr, "round %d (device %d): %llu full, %llu incremental, %llu redone, %llu records\n", h->last_rounds, h->cfg.device, is[0], is[1], is[2], is[3]);
+        }
+        return 0;   // single round: nothing to read back, the stream orders the rest
+    }
     int stat[2] = {0, 0};
     SCB_CUDA(cudaMemcpyAsync(stat, h->sh_stat.p, 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));

@@ -21,6 +21,7 @@ whole sharded path on a single-GPU box).
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import threading
 
 import numpy as np
