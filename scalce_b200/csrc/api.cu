@@ -624,7 +624,15 @@ static std::vector<int64_t> dense_blocks(int64_t n, int64_t g0) {
     std::vector<int64_t> blk;
     blk.push_back(0);
     const int64_t first = 4096;
-    while (blk.back() < n) { int64_t n0 = blk.back(); blk.push_back(std::min<int64_t>(n, std::max<int64_t>(2 * n0 + g0, n0 + first))); }
+    // early blocks are bound by the fixed cost of a round, not by their sweeps: they grow faster (x growth_small)
+    // until the input before them reaches `small`
+    const char *e1 = getenv("SCB_RESOLVE_GROWTH"), *e2 = getenv("SCB_RESOLVE_SMALL");
+    const int64_t growth_small = e1 ? std::max(2, atoi(e1)) : 4, small = e2 ? atoll(e2) : (1 << 20);
+    while (blk.back() < n) {
+        const int64_t n0 = blk.back(), before = n0 + g0;
+        const int64_t len = before < small ? (growth_small - 1) * before : before;
+        blk.push_back(std::min<int64_t>(n, n0 + std::max<int64_t>(len, first)));
+    }
     return blk;
 }
 
