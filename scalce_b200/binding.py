@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscalce_b200.so")
+LIB_PATH = os.environ.get("SCB_LIB") or os.path.join(HERE, "libscalce_b200.so")   # SCB_LIB: an alternative build (tuning experiments)
 
 N_STREAMS = 6
 S_NAMES, S_READS, S_QUALS, S_META, S_READS2, S_QUALS2 = range(6)

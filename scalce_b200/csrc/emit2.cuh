@@ -273,7 +273,10 @@ __device__ __forceinline__ uint4 splice16(uint4 x, uint4 y, int k) {
     const uint32_t m3 = kb <= 96 ? 0u : (0xffffffffu >> (128 - kb));
     return make_uint4((x.x & m0) | (ys.x & ~m0), (x.y & m1) | (ys.y & ~m1), (x.z & m2) | (ys.z & ~m2), (x.w & m3) | (ys.w & ~m3));
 }
-constexpr int kGatherChunks = 4;   // independent 16-byte chunks per thread (memory-level parallelism)
+#ifndef SCB_GATHER_CHUNKS
+#define SCB_GATHER_CHUNKS 3
+#endif
+constexpr int kGatherChunks = SCB_GATHER_CHUNKS;   // independent 16-byte chunks per thread; 3 measured best (4: 11.7 ms emit, 3: 10.6, 2: 10.8)   // independent 16-byte chunks per thread (memory-level parallelism)
 __global__ void __launch_bounds__(256) gather_rows16_k(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                        const uint32_t *__restrict__ perm, int64_t n, int L) {
     const int64_t total = n * (int64_t)L;
