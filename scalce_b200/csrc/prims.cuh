@@ -119,7 +119,10 @@ struct LoadAs {
 // =================================================================================================
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 12;   // tile = 3072 elements: 36 KB of staging + 10 KB of counters stays under 48 KB static smem
+#ifndef SCB_SORT_ITEMS
+#define SCB_SORT_ITEMS 12
+#endif
+constexpr int kSortItems = SCB_SORT_ITEMS;   // tile = 3072 elements: 36 KB of staging + 10 KB of counters stays under 48 KB static smem
 constexpr int kSortTile = kSortThreads * kSortItems;
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys, int64_t n, int shift, uint32_t mask,
