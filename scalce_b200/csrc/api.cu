@@ -424,7 +424,7 @@ static void flush_begin(scb_handle *h, double extra_factor) {
     {   // size the slab for this flush before anything is carved from it
         int64_t n_est = 0, name_est = 0;
         for (auto &p : h->pending) { n_est += p.n; name_est += p.name_bytes; }
-        const size_t per_read = (size_t)((L1 + 15) / 16 * 4) + 1 + 2 + 8 + 8 * 6 + 4 + 2 + 4 + 3 * (8 + 4) + 8 + 4 +
+        const size_t per_read = (size_t)((L1 + 15) / 16 * 4) + 1 + 2 + 8 + 8 * 6 + 4 + 2 + 4 + 3 * (8 + 4) + 8 + 4 + 12 /* fragile-read lists */ +
                                 (size_t)(sz_read(L1) + 3) + (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 16 + 64;
         size_t est = (size_t)n_est * per_read + (size_t)name_est + (size_t)n_est + ((size_t)256 << 20);
         if (h->pending.size() > 1) est += (size_t)n_est * ((size_t)L1 * 2 + (size_t)L2 * 2 + 8) + (size_t)name_est;

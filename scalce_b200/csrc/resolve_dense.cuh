@@ -12,6 +12,8 @@
 //   D  each warp sweeps one subtile in input order, 32 reads per step, with the bucket populations
 //      of "everything before" in shared memory (cnt[nb+1], u32)
 //   --grid sync--  column scan of the chunk totals  --grid sync--  converged?
+// After the second round of a block most subtiles only REPLAY the short list of reads whose decision margin is
+// small ("fragile reads" below); everything else provably keeps its decision.
 // Dense = two u32 words per bucket per warp in shared memory (population + lane tags), so it needs
 // 8*(nb+1)*W <= ~200 KB.
 #pragma once
