@@ -350,7 +350,7 @@ def main():
     ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
     # DRAM bytes per read of each stage's kernels (dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list of this
     # workload: profiles/r01_launches_summary.txt); only valid for the headline shape
-    ncu_traffic_per_read = {"emit": 732, "resolve": 264, "scan": 212, "sort": 226, "ties": 22, "chunks": 28, "arrays": 22}
+    ncu_traffic_per_read = {"emit": 732, "resolve": 100, "scan": 212, "sort": 226, "ties": 22, "chunks": 28, "arrays": 22}
     stage_kernels = {"emit": "gather_rows16_k + emit_reads_st_k + emit_names_st_k + gather_meta_k + offset scans", "resolve": "resolve_dense_k + resolve_finalize_k",
                      "scan": "scan_smem_k", "sort": "build_keys_pk_k + 5 x (sort_hist_k, sort_scatter_k)", "exchange_rows": "gather_rows16_to_k (peer stores)"}
     traffic = float(ncu_traffic_per_read[dom]) * N if (L == 150 and world == 1 and dom in ncu_traffic_per_read) else None
