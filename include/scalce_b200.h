@@ -229,7 +229,7 @@ typedef struct scb_shard_peer {
 } scb_shard_peer;
 int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
 int scb_shard_recv_reserve(scb_handle *h, const int64_t *need_bytes, void **ptrs, int32_t *changed);
-/* what: 1 = aux words + 2-bit rows (all the receive side needs to SORT), 2 = names + quality / mate-2 rows, 3 = both.
+/* what: 1 = aux words + 2-bit rows + names (all the receive side needs to SORT), 2 = quality / mate-2 rows, 3 = both.
  * async = 0: returns when this rank's writes are complete. async = 1: the writes run on a side stream with a small
  * grid and the call returns at once - so that, after a first synchronous send of `what = 1`, a barrier and
  * scb_shard_import, the row exchange overlaps scb_shard_finish_sort; scb_shard_send_wait joins it (then a barrier,

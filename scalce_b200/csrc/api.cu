@@ -957,10 +957,6 @@ static void shard_scan(scb_handle *h) {
     h->dbg_bucket.alloc((size_t)n * 4, st); h->dbg_core.alloc((size_t)n * 4, st); h->dbg_end.alloc((size_t)n * 4, st); h->dbg_chunk.alloc((size_t)n * 4, st);
     h->sh_perm.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);   // send order: read by the row sends that overlap the receive side
     h->sh_local = Pending();
-    if (h->cfg.use_names) {   // name staging in send order: filled and sent while the receive side already sorts
-        h->sh_names.alloc((size_t)h->cur.name_bytes + 16, st);
-        h->sh_noff.alloc((size_t)(n + 1) * 8, st);
-    }
     h->sh_mark = h->arena.mark();
     ShardTimer tm(h);
     stage_scan(h);
@@ -1128,7 +1124,7 @@ static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shar
     if (n > 0)
         SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
                    cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
-    if (!cfg.use_names) h->sh_noff.alloc((size_t)(n + 1) * 8, st);   // (with names it was carved in scb_shard_scan, ahead of the arena mark)
+    h->sh_noff.alloc((size_t)(n + 1) * 8, st);
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     exclusive_scan<uint64_t>(AuxNameLen{h->sh_aux.as<uint64_t>()}, n, h->sh_noff.as<uint64_t>(), h->sh_noff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
     SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, h->sh_noff.as<uint64_t>(), dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
@@ -1139,6 +1135,10 @@ static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shar
     h->sh_cnt_reads.assign((size_t)G, 0); h->sh_cnt_name_bytes.assign((size_t)G, 0);
     for (int g = 0; g < G; g++) { h->sh_cnt_reads[g] = h->sh_first[g + 1] - h->sh_first[g]; h->sh_cnt_name_bytes[g] = h->sh_nbytes[g + 1] - h->sh_nbytes[g]; }
     const int64_t name_bytes = h->sh_nbytes[(size_t)G];
+    if (cfg.use_names) {   // names are staged contiguously per destination (variable length: bulk copies move them)
+        h->sh_names.alloc((size_t)name_bytes + 16, st);
+        if (n > 0) SCB_LAUNCH(pack_names_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, c.name_off, c.names, h->sh_noff.as<uint64_t>(), h->sh_names.as<uint8_t>());
+    }
     tm.stop();
     memset(out, 0, sizeof *out);
     out->n = n; out->name_bytes = cfg.use_names ? name_bytes : 0;
@@ -1163,8 +1163,6 @@ static void shard_stage(scb_handle *h, scb_shard_xfer *out) {
     ShardTimer tm(h);
     h->sh_packed.alloc((size_t)n * prow + 64, st);
     gather_rows_to(st, h->packed.as<uint8_t>(), h->sh_packed.as<uint8_t>(), perm, n, prow);
-    if (cfg.use_names && n > 0)
-        SCB_LAUNCH(pack_names_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, c.name_off, c.names, h->sh_noff.as<uint64_t>(), h->sh_names.as<uint8_t>());
     if (cfg.use_quals) { h->sh_qual1.alloc((size_t)n * L1 + 16, st); gather_rows_to(st, c.qual1, h->sh_qual1.as<uint8_t>(), perm, n, L1); }
     if (cfg.paired) {
         h->sh_seq2.alloc((size_t)n * L2 + 16, st); gather_rows_to(st, c.seq2, h->sh_seq2.as<uint8_t>(), perm, n, L2);
@@ -1193,9 +1191,6 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
     const int cap = async ? 148 * 2 : 0;
     if (async) { SCB_CUDA(cudaEventRecord(h->ev_fork, h->st)); SCB_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0)); }
     cudaEventRecord(h->ev_s0, st);
-    if ((what & 2) && cfg.use_names && c.n > 0)   // name bytes in send order (contiguous per owner), staged once
-        SCB_LAUNCH(pack_names_k, (unsigned)cdiv(c.n, 256), 256, 0, st, h->sh_perm.as<uint32_t>(), c.n, c.name_off, c.names, h->sh_noff.as<uint64_t>(),
-                   h->sh_names.as<uint8_t>());
     for (int k = 1; k <= G; k++) {
         const int g = (rank + k) % G;
         const int64_t ng = h->sh_cnt_reads[g];
@@ -1206,11 +1201,11 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
         if (what & 1) {
             SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.aux + pp.row_off * 8, h->sh_aux.as<uint64_t>() + f, (size_t)ng * 8, cudaMemcpyDeviceToDevice, st));
             gather_rows_to(st, h->packed.as<uint8_t>(), (uint8_t *)pp.packed + pp.row_off * prow, perm, ng, prow, cap);
-        }
-        if (what & 2) {
-            if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)   // names are only needed by the emit: they travel with the rows
+            if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)
                 SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names.as<uint8_t>() + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
                                          cudaMemcpyDeviceToDevice, st));
+        }
+        if (what & 2) {
             if (cfg.use_quals) gather_rows_to(st, c.qual1, (uint8_t *)pp.qual1 + pp.row_off * L1, perm, ng, L1, cap);
             if (cfg.paired) {
                 gather_rows_to(st, c.seq2, (uint8_t *)pp.seq2 + pp.row_off * L2, perm, ng, L2, cap);

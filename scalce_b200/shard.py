@@ -419,7 +419,7 @@ class ShardedTransform:
                 pg.name_off = sum(mat[s][G + g] for s in range(r))
             y.aux, y.packed, y.qual1, y.names, y.seq2, y.qual2 = [ptrs[k] for k in range(6)]
             if self.overlap:
-                # what the receive side needs to SORT (aux words, 2-bit rows) goes first; names and quality / mate-2 rows then cross NVLink on a
+                # what the receive side needs to SORT goes first; the quality / mate-2 rows then cross NVLink on a
                 # side stream while the received reads are sorted, and are only awaited before the emit
                 _check(L.scb_shard_send(h, r, G, peers, 1, 0))
                 lap("exchange")
