@@ -296,3 +296,35 @@ def test_aux_word_layout_matches_header():
     cuh = open(os.path.join(ROOT, "scalce_b200", "csrc", "shard.cuh")).read()
     assert "end << 24" in hdr and "<< 35" in hdr and "<< 43" in hdr
     assert "<< 24" in cuh and "<< 35" in cuh and "<< 43" in cuh
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in scalce_b200/binding.py against the C compiler's view of include/scalce_b200.h."""
+    import ctypes as C
+    from scalce_b200 import binding as B
+    structs = {"scb_config": B.ScbConfig, "scb_batch": B.ScbBatch, "scb_result": B.ScbResult,
+               "scb_shard_xfer": B.ScbShardXfer, "scb_shard_peer": B.ScbShardPeer}
+    fields = {"scb_config": ["read_length", "use_names", "paired", "use_quals", "device", "bucket_set_bytes", "emit_merged"],
+              "scb_batch": ["n", "seq1", "qual1", "names", "name_off", "seq2", "qual2", "location"],
+              "scb_result": ["n_reads", "n_chunks", "n_buckets_nonempty", "data", "chunk_off", "merged", "merged_size", "bucket_id", "core_idx",
+                             "end", "chunk", "perm", "device_ms"],
+              "scb_shard_xfer": ["n", "name_bytes", "aux", "packed", "qual1", "names", "seq2", "qual2", "cnt_reads", "cnt_name_bytes", "packed_row_bytes"],
+              "scb_shard_peer": ["aux", "packed", "qual1", "names", "seq2", "qual2", "row_off", "name_off"]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "scalce_b200.h")}"', 'int main(void) {']
+    for s, fl in fields.items():
+        src.append(f'  printf("{s} %zu\\n", sizeof({s}));')
+        for f in fl:
+            src.append(f'  printf("{s}.{f} %zu\\n", offsetof({s}, {f}));')
+    src += ['  printf("SCB_N_STREAMS %d\\n", (int)SCB_N_STREAMS);', '  printf("SCB_ABI_VERSION %d\\n", (int)SCB_ABI_VERSION);', '  return 0;', '}']
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(c), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines())
+    for s, cls in structs.items():
+        assert int(out[s]) == C.sizeof(cls), f"sizeof({s}): C {out[s]} vs ctypes {C.sizeof(cls)}"
+        for f in fields[s]:
+            assert int(out[f"{s}.{f}"]) == getattr(cls, f).offset, f"offsetof({s}, {f})"
+    assert int(out["SCB_N_STREAMS"]) == B.N_STREAMS
+    from scalce_b200.binding import load_library
+    assert int(out["SCB_ABI_VERSION"]) == load_library().scb_abi_version()
