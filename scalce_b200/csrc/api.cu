@@ -1441,9 +1441,16 @@ int scb_submit(scb_handle *h, const scb_batch *b) {
         if (cfg.use_names) {
             int64_t o0 = b->name_off[0];
             p.name_bytes = b->name_off[b->n] - o0;
-            for (int64_t i = 0; i < b->n; i++) {
+            // host-side validation of the offsets runs while the sequence / quality copies above are in flight (pinned sources)
+            bool bad = p.name_bytes < 0;
+            for (int64_t i = 0; i < b->n && !bad; i++) {
                 int64_t len = b->name_off[i + 1] - b->name_off[i];
-                if (len < 0 || len > 255) { scb::g_last_error = "name length outside 0..255"; return SCB_EINVAL; }
+                bad = len < 0 || len > 255;
+            }
+            if (bad) {
+                SCB_CUDA(cudaStreamSynchronize(st));   // the copies read the caller's buffers: finish them before returning
+                scb::g_last_error = "name length outside 0..255";
+                return SCB_EINVAL;
             }
             up(p.b_names, b->names + o0, (size_t)p.name_bytes);
             if (o0 == 0) up(p.b_off, b->name_off, (size_t)(b->n + 1) * 8);
