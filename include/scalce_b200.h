@@ -239,6 +239,11 @@ int scb_shard_send_wait(scb_handle *h);
 /* Sort + tie refinement of the imported reads (needs aux, 2-bit rows and names only); optional: scb_shard_finish
  * runs it if it was not called. */
 int scb_shard_finish_sort(scb_handle *h);
+/* Optional, after scb_shard_finish_sort and BEFORE the row exchange has been awaited: emits everything that does not
+ * read quality / mate-2 rows (stream offsets, names, packed reads, meta records = what bin_dump, reads.cpp:91-180,
+ * writes to files 0, 1, 3), so that this work overlaps the tail of the row exchange; scb_shard_finish then only runs
+ * the row gathers (files 2, 4, 5). */
+int scb_shard_finish_early(scb_handle *h);
 int scb_ipc_export(scb_handle *h, const void *dev_ptr, uint8_t *handle64);
 int scb_ipc_open(scb_handle *h, const uint8_t *handle64, void **out);
 int scb_ipc_close(scb_handle *h, void *peer_ptr);

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscalce_b200.so")
 SOURCES = ["api.cu", "core_table.cpp"]
-HEADERS = ["common.cuh", "prims.cuh", "pipeline.cuh", "resolve_dense.cuh", "scan_smem.cuh", "emit2.cuh", "core_table.h", os.path.join("..", "..", "include", "scalce_b200.h")]
+# every header under csrc/ is a dependency of the one translation unit (api.cu includes them all)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "scalce_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "--expt-relaxed-constexpr",

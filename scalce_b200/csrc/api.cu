@@ -15,6 +15,7 @@
 #include "resolve_dense.cuh"
 #include "scan_smem.cuh"
 #include "emit2.cuh"
+#include "emit_offsets.cuh"
 #include "shard.cuh"
 
 namespace scb {
@@ -152,6 +153,7 @@ struct scb_handle {
     const uint64_t *srt_keys = nullptr;                    // sorted keys of the chunk-major order
     int srt_seg_bits = 0;
     bool srt_keys_valid = false;   // scb_shard_finish_sort ran: scb_shard_finish only emits
+    bool emit_early_done = false;  // scb_shard_finish_early ran: scb_shard_finish only runs the kernels that read quality / mate-2 rows
     Pending sh_local;          // the rank's own input after scb_shard_import replaced `cur` (phase-2 sends still read it)
     // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
     int sh_phase = 0;          // 0 idle, 1 scanned, 2 resolved (finalized), 3 sized, 4 packed, 5 imported
@@ -307,7 +309,10 @@ static void gather_rows_any(cudaStream_t st, const uint8_t *src, uint8_t *dst, c
 
 // ---- emit one ordering ----------------------------------------------------------------------------------
 // keys: the sorted keys of this ordering; the segment id (chunk, bucket order) is their top seg_bits bits
-static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys, int seg_shift, int seg_bits, bool merged, EmitOut &o) {
+// part: 1 = everything that does not read the quality / mate-2 rows (offsets, names, packed reads, meta records, per-chunk
+// offsets; allocates all six streams), 2 = only the kernels that read those rows (streams 2, 4, 5), 3 = both, in the order
+// the one-GPU flush has always used. The sharded run calls 1 while the rows are still crossing NVLink and 2 once they landed.
+static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys, int seg_shift, int seg_bits, bool merged, EmitOut &o, int part = 3) {
     cudaStream_t st = h->st;
     const Pending &c = h->cur;
     const int64_t n = c.n;
@@ -318,22 +323,44 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     const int nlen = 3 + 2 * cfg.paired;
     const int64_t rsz = 8 + 8 * nlen;
     const int nch = merged ? 1 : h->n_chunks;
+    if (part == 2) {   // the row-dependent kernels alone, into the streams part 1 allocated
+        if (n == 0) return;
+        if (cfg.use_quals) gather_rows_any(st, c.qual1, o.data[2].as<uint8_t>(), perm, n, L1);
+        if (cfg.paired && cfg.use_quals) gather_rows_any(st, c.qual2, o.data[5].as<uint8_t>(), perm, n, L2);
+        if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, o.data[4].as<uint8_t>());
+        return;
+    }
+    const bool rows_now = (part & 2) != 0;
     for (int k = 0; k < SCB_N_STREAMS; k++) { o.size[k] = 0; o.chunk_off[k].assign((size_t)std::max(nch, 0) + 1, 0); }
     o.n_seg = 0;
     if (n == 0) { for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc(0, st); return; }
 
     DevBuf hsum((size_t)(n + 1) * 4, st), ws32((size_t)scan_tiles(n) * 4, st), ws64((size_t)scan_tiles(n) * 8, st);
     DevBuf ms((size_t)n * 8, st), offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st);
+    KeyHead kh{keys, seg_shift, seg_bits};
+    uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
+    const char *fs_env = getenv("SCB_EMIT_FUSED_SCAN");
+    const bool fused_scan = fs_env && atoi(fs_env) != 0;
+    if (fused_scan) {
+        // opt-in (not yet measured on a B200): metadata gather + the three prefix sums in 3 launches (emit_offsets.cuh)
+        const int64_t nt = scan_tiles(n);
+        DevBuf ts((size_t)3 * nt * 8, st), tot3(32, st);
+        SCB_LAUNCH(emit_off_reduce_k, (unsigned)nt, kScanThreads, 0, st, h->meta_in.as<uint64_t>(), perm, kh, n, L1, sz_meta, (int)cfg.use_names,
+                   ms.as<uint64_t>(), ts.as<uint64_t>(), nt);
+        SCB_LAUNCH(emit_off_sums_k, 3, 1024, 0, st, ts.as<uint64_t>(), nt, tot3.as<uint64_t>());
+        SCB_LAUNCH(emit_off_apply_k, (unsigned)nt, kScanThreads, 0, st, ms.as<uint64_t>(), kh, n, L1, sz_meta, (int)cfg.use_names, ts.as<uint64_t>(), nt,
+                   tot3.as<uint64_t>(), hsum.as<uint32_t>(), offN.as<uint64_t>(), offR.as<uint64_t>());
+        if (cfg.use_names) SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    } else {
     // the one random small gather of the output side: per-read metadata into output order
     SCB_LAUNCH(gather_meta_k, (unsigned)cdiv(n, 256), 256, 0, st, h->meta_in.as<uint64_t>(), perm, n, ms.as<uint64_t>());
-    KeyHead kh{keys, seg_shift, seg_bits};
     exclusive_scan<uint32_t>(kh, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
-    uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
     if (cfg.use_names) {
         exclusive_scan<uint64_t>(NameRecM{ms.as<uint64_t>()}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
         SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     }
     exclusive_scan<uint64_t>(ReadRecM{ms.as<uint64_t>(), L1, sz_meta}, n, offR.as<uint64_t>(), offR.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    }
     SCB_CUDA(cudaMemcpyAsync(&totR, offR.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
@@ -359,8 +386,9 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     // The output kernels are independent of each other: names and packed reads (latency / issue bound) run on side
     // streams next to the quality-row gather (HBM bound) instead of one after the other.
     SCB_CUDA(cudaEventRecord(h->ev_fork, st));
-    cudaStream_t sN = h->st_aux[0], sR = h->st_aux[1];
-    SCB_CUDA(cudaStreamWaitEvent(sN, h->ev_fork, 0));
+    // part 1 alone: side stream 0 is carrying the sharded run's row sends, so the names stay on the main stream
+    cudaStream_t sN = rows_now ? h->st_aux[0] : st, sR = h->st_aux[1];
+    if (sN != st) SCB_CUDA(cudaStreamWaitEvent(sN, h->ev_fork, 0));
     SCB_CUDA(cudaStreamWaitEvent(sR, h->ev_fork, 0));
     if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
     {
@@ -374,12 +402,12 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         SCB_CUDA(cudaFuncSetAttribute(emit_reads_st_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, sR, e, RPB, NW, inv_pws, recmax);
     }
-    if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
-    SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
+    if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
+    if (sN != st) SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
     SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
-    if (cfg.use_quals) gather_rows(c.qual1, oQ, L1);
-    if (cfg.paired && cfg.use_quals) gather_rows(c.qual2, oQ2, L2);
-    SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+    if (cfg.use_quals && rows_now) gather_rows(c.qual1, oQ, L1);
+    if (cfg.paired && cfg.use_quals && rows_now) gather_rows(c.qual2, oQ2, L2);
+    if (sN != st) SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
     SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
     SCB_CUDA(cudaMemsetAsync(cfirst.p, 0xff, (size_t)2 * std::max(nch, 1) * 8, st));   // -1 = chunk has no read here
@@ -754,12 +782,15 @@ static void stage_sort(scb_handle *h) {
     const int nch = h->n_chunks > 0 ? h->n_chunks : 1;
     const int seg_bits = ceil_log2((uint64_t)nch * (uint64_t)(nb + 1));
     if (seg_bits > 40) throw CudaError{"too many (chunk, bucket) segments"};
-    // key prefix: enough bases that equal prefixes are rare inside a bucket of the expected size, then
-    // rounded up so that the sorted bit range is a whole number of 8-bit passes; equal prefixes that do
-    // occur are refined afterwards (step 5), so this only trades radix passes against refinement work
+    // key prefix: enough bases that equal prefixes are rare inside a SEGMENT (one bucket of one flush chunk: the
+    // unit inside which the prefix has to discriminate) of the expected size, then rounded up so that the
+    // sorted bit range is a whole number of 8-bit passes; equal prefixes that do occur are refined afterwards
+    // (step 5), so this only trades radix passes against refinement work. Headline shape (50M x 150, 3 flush
+    // chunks, 2049 buckets): 13 + 2*13 = 39 -> 40 bits, 5 passes (sizing per bucket instead gave 48 bits, 6 passes).
     int pb;
     {
-        double per_bucket = (double)std::max<int64_t>(n, 1) / (double)(nb + 1);
+        double per_bucket = (double)std::max<int64_t>(n, 1) / ((double)(nb + 1) * (double)nch);
+        if (getenv("SCB_SORT_PER_BUCKET")) per_bucket *= (double)nch;   // the old sizing, for A/B runs
         int need = 6;
         while (need < 32 && std::pow(4.0, need - 6) < per_bucket) need++;
         int total_bits = std::min(64, ((seg_bits + 2 * need + 7) / 8) * 8);
@@ -882,7 +913,7 @@ static void stage_sort(scb_handle *h) {
 }
 
 // 6. emit streams per flush chunk (the t_%03d_k.tmp contents), then the merged order if asked
-static void stage_emit(scb_handle *h) {
+static void stage_emit(scb_handle *h, int part = 3) {
     cudaStream_t st = h->st;
     const scb_config &cfg = h->cfg;
     const int64_t n = h->cur.n;
@@ -892,8 +923,13 @@ static void stage_emit(scb_handle *h) {
     DevBuf &k0 = h->srt_k0, &k1 = h->srt_k1, &v1 = h->srt_v1;
     SortWs ws;
     ws.hist = h->srt_hist.as<uint32_t>(); ws.tile_ws = h->srt_histws.as<uint32_t>();
+    if (part == 2) {   // row-dependent kernels of both orderings (the sorts and everything else ran in part 1)
+        emit_order(h, h->perm.as<uint32_t>(), ka, 64 - seg_bits, seg_bits, false, h->chunked, 2);
+        if (cfg.emit_merged && h->n_chunks > 1) emit_order(h, h->perm_m.as<uint32_t>(), nullptr, 0, 0, true, h->merged, 2);
+        return;
+    }
     SCB_CUDA(cudaEventRecord(h->stage_ev[5], st));
-    emit_order(h, h->perm.as<uint32_t>(), ka, 64 - seg_bits, seg_bits, false, h->chunked);
+    emit_order(h, h->perm.as<uint32_t>(), ka, 64 - seg_bits, seg_bits, false, h->chunked, part);
     SCB_CUDA(cudaEventRecord(h->stage_ev[6], st));
     if (cfg.emit_merged && h->n_chunks > 1) {
         // merge() concatenates a bucket's pieces in chunk order (compress.cpp:104-112): a stable sort of the
@@ -907,7 +943,7 @@ static void stage_emit(scb_handle *h) {
                        h->tab.root_order_pos, a, x);
         radix_sort_pairs(&a, &x, &b, &y, n, 0, ob, ws, st);
         if (x != h->perm_m.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->perm_m.p, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        emit_order(h, h->perm_m.as<uint32_t>(), a, 0, ob, true, h->merged);
+        emit_order(h, h->perm_m.as<uint32_t>(), a, 0, ob, true, h->merged, part);
     }
 
 }
@@ -949,6 +985,7 @@ static void shard_scan(scb_handle *h) {
     cudaStream_t st = h->st;
     ArenaScope arena_scope(&h->arena);
     h->sh_phase = 0;
+    h->emit_early_done = false;
     flush_begin(h, 2.0);   // room for the send arrays; the receive side reuses the slab after the exchange
     const int64_t n = h->cur.n;
     h->sh_n_local = n;
@@ -1284,13 +1321,15 @@ static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chun
     h->sh_phase = 5;
 }
 
-static void shard_finish(scb_handle *h, int what /* 1 = sort, 2 = emit, 3 = both */) {
+static void shard_finish(scb_handle *h, int what /* 1 = sort, 2 = emit, 3 = both; 4 / 8 = the emit in two parts (emit_order) */) {
     ArenaScope arena_scope(&h->arena);
     ShardTimer tm(h);
     if (what & 1) { stage_meta(h); stage_sort(h); h->srt_keys_valid = true; }
     if (what & 2) stage_emit(h);
+    if (what & 4) stage_emit(h, 1);
+    if (what & 8) stage_emit(h, 2);
     tm.stop();
-    if (what & 2) h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
+    if (what & (2 | 8)) h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
 }
 
 // ---- the transform on one GPU ------------------------------------------------------------------------------
@@ -1638,12 +1677,22 @@ int scb_shard_finish_sort(scb_handle *h) {
     SCB_CATCH
     return SCB_OK;
 }
+int scb_shard_finish_early(scb_handle *h) {
+    SCB_SHARD_ENTER(5)
+    if (!h->srt_keys_valid) { scb::g_last_error = "sharded run: scb_shard_finish_early needs scb_shard_finish_sort first"; return SCB_ESTATE; }
+    if (h->emit_early_done) { scb::g_last_error = "sharded run: scb_shard_finish_early called twice"; return SCB_ESTATE; }
+    scb::shard_finish(h, 4);
+    h->emit_early_done = true;
+    SCB_CATCH
+    return SCB_OK;
+}
 int scb_shard_finish(scb_handle *h, scb_result *out) {
     if (!out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
     memset(out, 0, sizeof *out);
     SCB_SHARD_ENTER(5)
-    scb::shard_finish(h, h->srt_keys_valid ? 2 : 3);
+    scb::shard_finish(h, h->emit_early_done ? 8 : (h->srt_keys_valid ? 2 : 3));
     h->srt_keys_valid = false;
+    h->emit_early_done = false;
     out->device_ms = h->sh_ms;
     SCB_CATCH
     scb::fill_result(h, out);

@@ -274,6 +274,9 @@ class ShardedTransform:
         self.p2p = p2p and hasattr(comm, "map_peers")
         self.on_torch_stream = bool(use_torch_stream)
         self.overlap = overlap      # row exchange overlapped with the receive side's sort (p2p only)
+        import os
+        self.prerounds = int(os.environ.get("SCB_SHARD_PREROUNDS", "0") or 0)   # see flush(): 0 = off (default)
+        self.early_emit = os.environ.get("SCB_SHARD_EARLY_EMIT", "0") not in ("", "0")
         self.stats = {}
         self._keep = None
         if use_torch_stream:
@@ -323,9 +326,30 @@ class ShardedTransform:
         # ---- tie-break -------------------------------------------------------------------------------------
         tot = torch.zeros(ncols + 1, dtype=torch.int32, device=dev)   # u32 bit patterns
         sync = (lambda: None) if self.on_torch_stream else (lambda: torch.cuda.synchronize(dev))   # one stream orders everything
+        warm = self.prerounds > 0 and G > 1   # the switch must be the same on every rank
+        pre_ev = None
         if r == 0:
             _check(L.scb_shard_resolve_local(h, C.c_void_p(tot.data_ptr())))
             lap("resolve")
+        elif warm:
+            # Opt-in (SCB_SHARD_PREROUNDS=k): while rank 0 resolves its shard alone the later ranks would only wait, so
+            # they iterate their own shard from an ESTIMATE of what precedes it - first from nothing, then from their own
+            # bucket histogram scaled to the reads before the shard (shards of one input are statistically alike). The
+            # joint rounds then start from an almost converged assignment with fragile-read lists in place. Exactness is
+            # untouched: the estimate only picks the starting point of the fixed-point iteration below.
+            pre_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            pre_ev[0].record()
+            pre_keep = []
+            for k in range(self.prerounds):
+                if k == 0:
+                    bf = torch.zeros(ncols, dtype=torch.int32, device=dev)
+                else:
+                    bf = (tot[:ncols].to(torch.int64) * before[r] // max(ns[r], 1)).clamp_(max=0x7fffffff).to(torch.int32)
+                pre_keep.append(bf)   # referenced until the stream has run the round that reads it
+                sync()
+                _check(L.scb_shard_resolve_round(h, C.c_void_p(bf.data_ptr()), before[r], 1 if k == 0 else 0, C.c_void_p(tot.data_ptr())))
+                sync()
+            pre_ev[1].record()
         sync()
         allt = comm.allgather(tot)
         rounds = 0
@@ -339,7 +363,10 @@ class ShardedTransform:
             inflight = []          # (event, pinned changed count, was_first)
             if pipelined and not hasattr(self, "_pin"):
                 self._pin = [torch.empty(1, dtype=torch.int64, pin_memory=True) for _ in range(4)]   # allocated once: pinning is slow
-            first = True
+            # after pre-rounds every rank already holds an assignment and its histogram: the first joint round is an
+            # ordinary one (prefix counts of the current global assignment), so "nothing changed" already proves the
+            # fixed point and the kernel continues from the histograms the pre-rounds left
+            first = not warm
             done = False
             while not done:
                 if r > 0:
@@ -372,6 +399,8 @@ class ShardedTransform:
             e1.record()
             torch.cuda.synchronize(dev)
             ms["resolve_rounds"] = e0.elapsed_time(e1)
+            if pre_ev is not None:
+                ms["prerounds"] = pre_ev[0].elapsed_time(pre_ev[1])
         gtot = allt[:, :ncols].sum(0, dtype=torch.int64).to(torch.int32).contiguous()
         torch.cuda.synchronize(dev)
         _check(L.scb_shard_finalize(h, C.c_void_p(gtot.data_ptr()), n_global))
@@ -429,6 +458,9 @@ class ShardedTransform:
                 _check(L.scb_shard_send(h, r, G, peers, 2, 1))
                 _check(L.scb_shard_finish_sort(h))
                 lap("sort")
+                if self.early_emit:   # opt-in (SCB_SHARD_EARLY_EMIT=1): names / packed reads / meta records while the rows still travel
+                    _check(L.scb_shard_finish_early(h))
+                    lap("emit_early")
                 _check(L.scb_shard_send_wait(h))
                 lap("exchange_rows")
                 comm.barrier()   # every rank's row writes have landed

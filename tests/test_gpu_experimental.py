@@ -1,0 +1,83 @@
+"""Opt-in variants that were written without GPU access (end of round 1) and have NOT been measured or
+run on a B200 yet. They are off by default in the product path; these parity tests only run when
+SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GPU suite red.
+
+  SCB_SHARD_PREROUNDS=k    later ranks iterate their shard from an estimate while rank 0 resolves alone
+  SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
+  SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
+
+Same bar as everywhere else: bit-exact against the oracle.
+"""
+import os
+
+import pytest
+
+from tests import util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SCB_TEST_EXPERIMENTAL", "0") in ("", "0"),
+                                                   reason="experimental variants: set SCB_TEST_EXPERIMENTAL=1")]
+
+
+def _sharded(n, L, world, **kw):
+    run_kw = {k: kw.pop(k) for k in list(kw) if k in ("use_names", "use_quals", "bucket_set_bytes", "bounds")}
+    paired = kw.get("paired", False)
+    cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, **{k: v for k, v in run_kw.items() if k != "bounds"})
+    ranks = util.run_sharded_loopback(cores, b, q1, q2, world, paired=paired, **run_kw)
+    util.assert_sharded_same(o, ranks, paired=paired)
+    return o, ranks
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_prerounds_two_ranks(monkeypatch, k):
+    monkeypatch.setenv("SCB_SHARD_PREROUNDS", str(k))
+    _sharded(30000, 100, 2, seed=151)
+
+
+def test_prerounds_four_ranks_multi_chunk(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
+    _sharded(40000, 100, 4, seed=153, bucket_set_bytes=1 << 20)
+
+
+def test_prerounds_empty_ranks(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "2")
+    _sharded(9000, 64, 4, seed=156, bounds=[0, 0, 5000, 5000, 9000])
+
+
+def test_prerounds_larger_headline_cores(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
+    cores, b, q1, q2, _ = util.make_case(300000, 100, seed=159, plant=0.0,
+                                         spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2)
+    ranks = util.run_sharded_loopback(cores, b, q1, q2, 3)
+    util.assert_sharded_same(o, ranks)
+
+
+def test_early_emit_paired_multi_chunk(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_EARLY_EMIT", "1")
+    _sharded(20000, 100, 3, seed=154, paired=True, L2=75, bucket_set_bytes=1 << 20, bounds=[0, 1000, 13000, 20000])
+
+
+def test_early_emit_no_names_short(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_EARLY_EMIT", "1")
+    _sharded(40000, 36, 8, seed=155, use_names=False)
+
+
+def test_early_emit_and_prerounds(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_EARLY_EMIT", "1")
+    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
+    _sharded(30000, 100, 4, seed=157)
+
+
+@pytest.mark.parametrize("var", ["SCB_EMIT_FUSED_SCAN", "SCB_SORT_PER_BUCKET"])
+def test_single_gpu_variants(monkeypatch, var):
+    monkeypatch.setenv(var, "1")
+    for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
+               dict(n=8000, L=36, seed=163, lower=0.3), dict(n=3000, L=300, seed=164), dict(n=10000, L=100, seed=165, paired=True, L2=75)):
+        run_kw = {k: kw.pop(k) for k in list(kw) if k in ("bucket_set_bytes",)}
+        n, L = kw.pop("n"), kw.pop("L")
+        paired = kw.get("paired", False)
+        cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+        o = util.run_oracle(cores, b, q1, q2, paired=paired, **run_kw)
+        t, r = util.run_cuda(cores, b, q1, q2, paired=paired, **run_kw)
+        util.assert_same(o, t, r, paired=paired)
