@@ -93,3 +93,44 @@ def test_oracle_against_live_reference_cli(tmp_path, oracle_lib):
     _, files = oracle_files(cores, b, meta)
     for ext in "nrq":
         assert files["1" + ext] == open(f"{d}/ref_1.scalce{ext}", "rb").read()
+
+
+def test_reference_harness_thread_loop_conserves_payload(tmp_path):
+    """oracle/_ref/libref_harness.so (bench.py's CPU arm): the -T loop (refh_run_mt) must move the same reads as the
+    single-threaded loop - its order is not deterministic, but the bytes of the names and quality files and the
+    number of reads per file set are."""
+    import ctypes as C
+    import numpy as np
+    import bench
+    harness = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_harness.so")
+    if not os.path.exists(harness):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cores = bench.headline_cores()
+    n, L = 20000, 100
+    seq, qual, names, off = bench.synth_host_sample(n, L, seed=3)
+    H = C.CDLL(harness)
+    H.refh_init.restype = C.c_double
+    H.refh_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
+    H.refh_run.restype = C.c_double
+    H.refh_run.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    H.refh_run_mt.restype = C.c_double
+    H.refh_run_mt.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+    cf = tmp_path / "cores.txt"
+    cf.write_text("\n".join(cores) + "\n")
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    sizes = []
+    for mode, threads in (("st", 1), ("mt", 4)):
+        d = tmp_path / mode
+        d.mkdir()
+        H.refh_init(str(cf).encode(), L, 0, 0, 1, 4 << 30)
+        nch = C.c_int()
+        if mode == "st":
+            H.refh_run(n, p(seq), p(qual), p(names), p(off), None, None, 33, str(d).encode(), C.byref(nch), None, None)
+        else:
+            H.refh_run_mt(n, p(seq), p(qual), p(names), p(off), None, None, 33, str(d).encode(), C.byref(nch), threads)
+        assert nch.value == 1
+        sizes.append([os.path.getsize(d / f"t_000_{k}.tmp") for k in range(4)])
+    st, mt = sizes
+    assert st[0] == mt[0] == int(off[n]) + n          # names: length byte + name per read
+    assert st[2] == mt[2] == n * L                    # qualities
+    assert st[1] == mt[1]                             # packed reads: the chosen core's LENGTH does not depend on the tie-break
