@@ -14,6 +14,7 @@
 #include "prims.cuh"
 #include "resolve_dense.cuh"
 #include "scan_smem.cuh"
+#include "scan_smem2.cuh"
 #include "emit2.cuh"
 #include "emit_offsets.cuh"
 #include "shard.cuh"
@@ -496,7 +497,9 @@ static void stage_scan(scb_handle *h) {
         const int R = W * 32;
         if (W >= 2 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
             const size_t smem = scan_smem_total(h->tab.n_states, h->n_hit, nb, W, L1, PW);
-            SCB_CUDA(cudaFuncSetAttribute(scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const char *v2e = getenv("SCB_SCAN_V2");      // opt-in variant: pick + emit merged (scan_smem2.cuh), not yet measured
+            const bool scan_v2 = v2e && atoi(v2e) != 0;
+            SCB_CUDA(cudaFuncSetAttribute(scan_v2 ? scan_smem2_k : scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
             DevBuf dtot(8, st);
@@ -516,7 +519,8 @@ static void stage_scan(scb_handle *h) {
                 sp.packed = h->packed.as<uint32_t>(); sp.PW = PW;
                 sp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); sp.pitch = pitch;
                 int grid = (int)std::min<int64_t>(dev_sms, cdiv(sp.n_tiles, W));
-                SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
+                if (scan_v2) SCB_LAUNCH(scan_smem2_k, grid, R, smem, st, sp);
+                else SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
                 SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
                 SCB_CUDA(cudaStreamSynchronize(st));
                 if (M <= cap) scanned = true; else cap = M;   // list space was short: rerun with the exact size

@@ -4,6 +4,7 @@ SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GP
 
   SCB_SHARD_PREROUNDS=k    later ranks iterate their shard from an estimate while rank 0 resolves alone
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
+  SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
 
 Same bar as everywhere else: bit-exact against the oracle.
@@ -69,7 +70,7 @@ def test_early_emit_and_prerounds(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_EMIT_FUSED_SCAN", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -81,3 +82,25 @@ def test_single_gpu_variants(monkeypatch, var):
         o = util.run_oracle(cores, b, q1, q2, paired=paired, **run_kw)
         t, r = util.run_cuda(cores, b, q1, q2, paired=paired, **run_kw)
         util.assert_same(o, t, r, paired=paired)
+
+
+def test_scan_v2_dense_core_set_and_queue_overflow(monkeypatch):
+    # many hits per read: the queue overflows on some reads (slow path, L slots reserved) and the candidate arrays are
+    # re-sized by the second attempt
+    monkeypatch.setenv("SCB_SCAN_V2", "1")
+    import itertools
+    from scalce_b200 import synth
+    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]   # every position hits (tests/test_gpu_parity.py)
+    b = synth.make_batch(2000, 80, seed=171)
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, None)
+    t, r = util.run_cuda(cores, b, q1, None)
+    util.assert_same(o, t, r)
+
+
+def test_scan_v2_million_reads(monkeypatch):
+    monkeypatch.setenv("SCB_SCAN_V2", "1")
+    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=172, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2)
+    t, r = util.run_cuda(cores, b, q1, q2)
+    util.assert_same(o, t, r)
