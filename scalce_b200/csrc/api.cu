@@ -17,6 +17,7 @@
 #include "scan_smem2.cuh"
 #include "emit2.cuh"
 #include "emit_offsets.cuh"
+#include "emit_coresident.cuh"
 #include "shard.cuh"
 
 namespace scb {
@@ -391,7 +392,15 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     cudaStream_t sN = rows_now ? h->st_aux[0] : st, sR = h->st_aux[1];
     if (sN != st) SCB_CUDA(cudaStreamWaitEvent(sN, h->ev_fork, 0));
     SCB_CUDA(cudaStreamWaitEvent(sR, h->ev_fork, 0));
-    if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
+    // opt-in (not yet measured): the three output kernels as co-resident persistent grids (emit_coresident.cuh)
+    const char *cr_env = getenv("SCB_EMIT_CORESIDENT");
+    const bool cores_mode = cr_env && atoi(cr_env) != 0 && rows_now && cfg.use_quals && L1 >= 16;
+    int dev_sms = kSMs;
+    if (cores_mode) SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+    if (cfg.use_names) {
+        if (cores_mode) SCB_LAUNCH(emit_names_loop_k, (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)dev_sms * 2), 256, 0, sN, e, cdiv(n, 256));
+        else SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
+    }
     {
         const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
         const int recmax = sz_read(L1) + sz_meta;
@@ -400,14 +409,23 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         const int RPB = std::max(1, std::min(256, (40 * 1024) / per_read));
         const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
         const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
+        if (cores_mode) {
+            SCB_CUDA(cudaFuncSetAttribute(emit_reads_loop_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCB_LAUNCH(emit_reads_loop_k, (unsigned)std::min<int64_t>(cdiv(n, RPB), (int64_t)dev_sms * 2), 256, smem, sR, e, RPB, NW, inv_pws, recmax, cdiv(n, RPB));
+        } else {
         SCB_CUDA(cudaFuncSetAttribute(emit_reads_st_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, sR, e, RPB, NW, inv_pws, recmax);
+        }
     }
     if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
     if (sN != st) SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
     SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
-    if (cfg.use_quals && rows_now) gather_rows(c.qual1, oQ, L1);
-    if (cfg.paired && cfg.use_quals && rows_now) gather_rows(c.qual2, oQ2, L2);
+    auto gather_rows_loop = [&](const uint8_t *src, uint8_t *dst, int L) {
+        const int64_t n_blk = cdiv(cdiv(n * L, 16), 256 * kGatherChunks);   // < 2^31: n < 2^31 rows of <= 2047 bytes, 12 KB per block
+        SCB_LAUNCH(gather_rows16_loop_k, (unsigned)std::min<int64_t>(n_blk, (int64_t)dev_sms * 3), 256, 0, st, src, dst, perm, n, L, (int)n_blk);
+    };
+    if (cfg.use_quals && rows_now) { if (cores_mode) gather_rows_loop(c.qual1, oQ, L1); else gather_rows(c.qual1, oQ, L1); }
+    if (cfg.paired && cfg.use_quals && rows_now) { if (cores_mode && L2 >= 16) gather_rows_loop(c.qual2, oQ2, L2); else gather_rows(c.qual2, oQ2, L2); }
     if (sN != st) SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
     SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);

@@ -5,6 +5,7 @@ SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GP
   SCB_SHARD_PREROUNDS=k    later ranks iterate their shard from an estimate while rank 0 resolves alone
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
+  SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
   SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
 
 Same bar as everywhere else: bit-exact against the oracle.
@@ -70,7 +71,7 @@ def test_early_emit_and_prerounds(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -104,3 +105,13 @@ def test_scan_v2_million_reads(monkeypatch):
     o = util.run_oracle(cores, b, q1, q2)
     t, r = util.run_cuda(cores, b, q1, q2)
     util.assert_same(o, t, r)
+
+
+def test_all_single_gpu_variants_together_million_reads(monkeypatch):
+    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT"):
+        monkeypatch.setenv(var, "1")
+    cores, b, q1, q2, _ = util.make_case(1000000, 150, seed=173, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)],
+                                         paired=True, L2=100)
+    o = util.run_oracle(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
+    t, r = util.run_cuda(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
+    util.assert_same(o, t, r, paired=True)
