@@ -39,5 +39,26 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = os.path.join(HERE, "host", "scb_boost.cpp")
+HOST_BIN = os.path.join(HERE, "host", "scb_boost")
+
+
+def build_host_tool(force: bool = False) -> str:
+    """g++ -> scalce_b200/host/scb_boost: the C++ host side (FASTQ -> C ABI -> the reference's temp files), linked
+    against libscalce_b200.so through an rpath relative to the binary."""
+    build_lib()
+    deps = [HOST_SRC, LIB, os.path.join(HERE, "..", "include", "scalce_b200.h")]
+    if not force and os.path.exists(HOST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_BIN) for d in deps):
+        return HOST_BIN
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, HOST_SRC, "-L" + HERE, "-lscalce_b200", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("host tool build failed")
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host_tool(force="--force" in sys.argv))

@@ -115,3 +115,29 @@ def test_all_single_gpu_variants_together_million_reads(monkeypatch):
     o = util.run_oracle(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
     t, r = util.run_cuda(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
     util.assert_same(o, t, r, paired=True)
+
+
+# ---- the C++ host tool end to end (scalce_b200/host/scb_boost.cpp): FASTQ -> temp files == the oracle's chunk streams ----
+@pytest.mark.parametrize("paired", [False, True])
+def test_host_tool_temp_files_match_oracle(tmp_path, paired):
+    import subprocess
+    from scalce_b200 import build as bld, synth
+    tool = bld.build_host_tool()
+    cores, b, q1, q2, _ = util.make_case(30000, 100, seed=181, paired=paired, L2=75 if paired else None)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, bucket_set_bytes=1 << 21)
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(b, f1, f2 if paired else None)
+    (tmp_path / "cores.txt").write_text("\n".join(cores) + "\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    cmd = [tool, f1] + (["-r", f2] if paired else []) + ["-P", str(tmp_path / "cores.txt"), "-o", str(out), "-B", str(1 << 21), "--merged", "--batch", "7001"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    nf = 6 if paired else 4
+    assert o.n_chunks > 1
+    for c in range(o.n_chunks):
+        for k in range(nf):
+            assert (out / f"t_{c:03d}_{k}.tmp").read_bytes() == o.stream(k, c), f"chunk {c} stream {k}"
+    assert not (out / f"t_{o.n_chunks:03d}_0.tmp").exists()
+    for k in range(nf):
+        assert (out / f"merged_{k}.tmp").read_bytes() == o.stream(k, -1), f"merged stream {k}"

@@ -328,3 +328,69 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert int(out["SCB_N_STREAMS"]) == B.N_STREAMS
     from scalce_b200.binding import load_library
     assert int(out["SCB_ABI_VERSION"]) == load_library().scb_abi_version()
+
+
+# ---- C++ host side (scalce_b200/host/scb_boost.cpp): parse + payload preparation, no GPU involved -------------------
+def _run_host_tool_dump(tmp_path, b, paired=False, extra=()):
+    import subprocess
+    from scalce_b200 import build as bld, synth
+    tool = bld.build_host_tool()
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(b, f1, f2 if paired else None)
+    d = tmp_path / "soa"
+    d.mkdir()
+    cmd = [tool, f1] + (["-r", f2] if paired else []) + ["--dump-soa", str(d)] + list(extra)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    meta = dict(line.split() for line in (d / "meta.txt").read_text().splitlines())
+    arr = {k: np.fromfile(d / f"{k}.bin", dtype=np.uint8) for k in ("seq1", "qual1", "names", "seq2", "qual2")}
+    arr["name_off"] = np.fromfile(d / "name_off.bin", dtype=np.int64)
+    return {k: int(v) for k, v in meta.items()}, arr
+
+
+def test_host_tool_parse_and_payload_single_end(tmp_path):
+    """FASTQ -> SoA exactly as the Python host side builds it: names without '@', q - offset with 0 under 'N'
+    (qualities.cpp:177-204 as restated by oracle.quality_payload), several batches concatenated."""
+    from oracle import oracle as orc
+    from scalce_b200 import synth
+    b = synth.make_batch(5000, 100, seed=11, n_frac=0.01, lower_frac=0.05)
+    meta, a = _run_host_tool_dump(tmp_path, b, extra=("--batch", "777"))
+    assert meta == {"n": 5000, "L1": 100, "L2": 0, "offset1": 33, "offset2": 0}
+    assert np.array_equal(a["seq1"].reshape(5000, 100), b.seq)
+    assert np.array_equal(a["qual1"].reshape(5000, 100), orc.quality_payload(b.qual, b.seq, orc.detect_phred_offset(b.qual)))
+    assert np.array_equal(a["names"], b.names) and np.array_equal(a["name_off"], b.name_off)
+
+
+def test_host_tool_paired_phred64_and_name_truncation(tmp_path):
+    from oracle import oracle as orc
+    from scalce_b200 import synth
+    b = synth.make_batch(1200, 75, seed=12, paired=True, L2=50)
+    # phred+64 qualities on mate 2 only: the offsets are detected per file (compress.cpp:561-574)
+    b.qual2 = (b.qual2 - 33 + 64).astype(np.uint8)
+    # names with a description after a space: only the part before it is kept (names.cpp:48-62)
+    full = []
+    for i in range(b.n):
+        nm = b.names[b.name_off[i]:b.name_off[i + 1]].tobytes()
+        full.append(nm + (b" extra field %d" % i if i % 3 == 0 else b""))
+    kept_names, kept_off = b.names.copy(), b.name_off.copy()
+    b.names = np.frombuffer(b"".join(full), dtype=np.uint8).copy()
+    off = np.zeros(b.n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in full], out=off[1:])
+    b.name_off = off
+    meta, a = _run_host_tool_dump(tmp_path, b, paired=True)
+    assert meta == {"n": 1200, "L1": 75, "L2": 50, "offset1": 33, "offset2": 64}
+    assert np.array_equal(a["names"], kept_names) and np.array_equal(a["name_off"], kept_off)
+    assert np.array_equal(a["seq2"].reshape(1200, 50), b.seq2)
+    assert np.array_equal(a["qual1"].reshape(1200, 75), orc.quality_payload(b.qual, b.seq, 33))
+    assert np.array_equal(a["qual2"].reshape(1200, 50), orc.quality_payload(b.qual2, b.seq2, 64))
+
+
+def test_host_tool_rejects_ragged_reads(tmp_path):
+    import subprocess
+    from scalce_b200 import build as bld
+    tool = bld.build_host_tool()
+    f = tmp_path / "bad.fastq"
+    f.write_bytes(b"@a\nACGTACGT\n+\nIIIIIIII\n@b\nACGT\n+\nIIII\n@c\nACGTACGT\n+\nIIIIIIII\n")
+    (tmp_path / "o").mkdir()
+    r = subprocess.run([tool, str(f), "--dump-soa", str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"(ERROR)" in r.stderr          # the reference's convention: message + exit(1)
