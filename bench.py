@@ -510,16 +510,22 @@ def main():
         "emit": 2 * L + 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + L + 4, "merged": 0, "arrays": 16,
         # sharded run: pack + exchange move the payload once each (aux word, packed row, quality row, name)
         "finalize": 8, "hist": 4, "resolve_rounds": 16, "pack": 2 * (8 + 40 + L + NAME_BYTES), "exchange": 2 * (8 + 40 + NAME_BYTES), "exchange_rows": 2 * L, "import": 16, "sort": 24,
+        "prerounds": 16, "emit_early": 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + 40 + 8,   # opt-in stages of the sharded run
     }
-    ach = N * stage_bytes[dom] / (mean_st[dom] * 1e-3) / 1e9
+    ach = N * stage_bytes.get(dom, 0) / (mean_st[dom] * 1e-3) / 1e9
     # DRAM bytes per read of each stage's kernels (dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list of this
     # workload: profiles/r01_launches_summary.txt); only valid for the headline shape
     ncu_traffic_per_read = {"emit": 732, "resolve": 100, "scan": 212, "sort": 226, "ties": 22, "chunks": 28, "arrays": 22}
     stage_kernels = {"emit": "gather_rows16_k + emit_reads_st_k + emit_names_st_k + gather_meta_k + offset scans", "resolve": "resolve_dense_k + resolve_finalize_k",
                      "scan": "scan_smem_k", "sort": "build_keys_pk_k + 5 x (sort_hist_k, sort_scatter_k)", "exchange_rows": "gather_rows16_to_k (peer stores)"}
     traffic = float(ncu_traffic_per_read[dom]) * N if (L == 150 and world == 1 and dom in ncu_traffic_per_read) else None
+    # every stage's own figure beside the dominant one (same definition: algorithmic bytes of the stage / its device time)
+    per_stage = {k: {"ms": v, "bytes_per_read": stage_bytes.get(k), "achieved_gbs": (N * stage_bytes[k] / (v * 1e-3) / 1e9) if (v > 0 and stage_bytes.get(k)) else None}
+                 for k, v in mean_st.items()}
+    for k, d_ in per_stage.items():
+        d_["frac"] = (d_["achieved_gbs"] / peak) if d_["achieved_gbs"] else None
     roof = {"bound": "hbm", "kernel": dom, "kernels": stage_kernels.get(dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "peak_source": peak_src, "bytes_per_read": stage_bytes[dom], "stage_ms": mean_st, "resolve_rounds": resolve_rounds}
+            "peak_source": peak_src, "bytes_per_read": stage_bytes.get(dom), "stage_ms": mean_st, "per_stage": per_stage, "resolve_rounds": resolve_rounds}
     pipe = N * bpr / (ms_step * 1e-3) / 1e9
     pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
 
