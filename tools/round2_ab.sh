@@ -1,0 +1,22 @@
+#!/bin/bash
+# ONE gpurun call (one GPU, ~6 min) that answers every open question the end of round 1 left behind:
+#   1. do the opt-in variants pass parity (tests/test_gpu_experimental.py)?
+#   2. what does each switch do to the headline step (50M x 150 bp, stage times from bench.py)?
+#   3. the pipelined end-to-end arm.
+# Usage:  gpurun --timeout 900 -- 'bash tools/round2_ab.sh'      results: gpurun_out/ab/ + a table on stdout
+mkdir -p gpurun_out/ab
+export PYTHONUNBUFFERED=1
+SCB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/ab/tests.log 2>&1
+tail -n 15 gpurun_out/ab/tests.log
+run() {  # name ENV=... : kernel-only bench line of one configuration
+  local name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/ab/$name.json 2> gpurun_out/ab/$name.err
+}
+run default
+run sort_per_bucket SCB_SORT_PER_BUCKET=1
+run fused_scan SCB_EMIT_FUSED_SCAN=1
+run coresident SCB_EMIT_CORESIDENT=1
+run scan_v2 SCB_SCAN_V2=1
+run all_on SCB_EMIT_FUSED_SCAN=1 SCB_EMIT_CORESIDENT=1 SCB_SCAN_V2=1
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-depth 2 > gpurun_out/ab/e2e_depth2.json 2> gpurun_out/ab/e2e_depth2.err
+python tools/ab_summary.py gpurun_out/ab

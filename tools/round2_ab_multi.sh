@@ -1,0 +1,16 @@
+#!/bin/bash
+# The sharded run's opt-in switches at N GPUs (gpurun --gpus N): default, pre-rounds, early emit, both.
+# Usage:  gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_ab_multi.sh 8'
+N=${1:-2}
+mkdir -p gpurun_out/ab
+export PYTHONUNBUFFERED=1
+run() {
+  local name=$1; shift
+  env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --steps 3 --warmup 2 --no-e2e --no-cpu > gpurun_out/ab/n${N}_$name.json 2> gpurun_out/ab/n${N}_$name.err
+}
+run default
+run prerounds SCB_SHARD_PREROUNDS=3
+run early_emit SCB_SHARD_EARLY_EMIT=1
+run both SCB_SHARD_PREROUNDS=3 SCB_SHARD_EARLY_EMIT=1
+python tools/ab_summary.py gpurun_out/ab n${N}_
