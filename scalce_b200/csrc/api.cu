@@ -18,6 +18,7 @@
 #include "emit2.cuh"
 #include "emit_offsets.cuh"
 #include "emit_coresident.cuh"
+#include "emit_reads_fast.cuh"
 #include "shard.cuh"
 
 namespace scb {
@@ -409,7 +410,14 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         const int RPB = std::max(1, std::min(256, (40 * 1024) / per_read));
         const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
         const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
-        if (cores_mode) {
+        const char *rv2 = getenv("SCB_EMIT_READS_V2");   // opt-in (not yet measured): emit_reads_fast.cuh
+        if (rv2 && atoi(rv2) != 0) {
+            const uint32_t half = (uint32_t)((h->PW & 1) == 0 && (((uintptr_t)h->packed.p) & 7) == 0 ? h->PW / 2 : h->PW);
+            const uint32_t inv_half = (uint32_t)(((1ull << 32) + half - 1) / half);
+            const int64_t n_blk = cdiv(n, RPB);
+            SCB_CUDA(cudaFuncSetAttribute(emit_reads_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCB_LAUNCH(emit_reads_fast_k, (unsigned)(cores_mode ? std::min<int64_t>(n_blk, (int64_t)dev_sms * 2) : n_blk), 256, smem, sR, e, RPB, inv_half, recmax, n_blk);
+        } else if (cores_mode) {
             SCB_CUDA(cudaFuncSetAttribute(emit_reads_loop_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SCB_LAUNCH(emit_reads_loop_k, (unsigned)std::min<int64_t>(cdiv(n, RPB), (int64_t)dev_sms * 2), 256, smem, sR, e, RPB, NW, inv_pws, recmax, cdiv(n, RPB));
         } else {

@@ -6,6 +6,7 @@ SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GP
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
+  SCB_EMIT_READS_V2=1      stream-1 writer with 8-byte row staging and branch-free record assembly (emit_reads_fast.cuh)
   SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
 
 Same bar as everywhere else: bit-exact against the oracle.
@@ -71,7 +72,7 @@ def test_early_emit_and_prerounds(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -108,7 +109,7 @@ def test_scan_v2_million_reads(monkeypatch):
 
 
 def test_all_single_gpu_variants_together_million_reads(monkeypatch):
-    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT"):
+    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2"):
         monkeypatch.setenv(var, "1")
     cores, b, q1, q2, _ = util.make_case(1000000, 150, seed=173, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)],
                                          paired=True, L2=100)
@@ -141,3 +142,14 @@ def test_host_tool_temp_files_match_oracle(tmp_path, paired):
     assert not (out / f"t_{o.n_chunks:03d}_0.tmp").exists()
     for k in range(nf):
         assert (out / f"merged_{k}.tmp").read_bytes() == o.stream(k, -1), f"merged stream {k}"
+
+
+def test_emit_reads_v2_odd_row_words_and_long_reads(monkeypatch):
+    # PW odd (4-byte staging path), 2-byte end markers, cores at the very start / end of reads (planted)
+    monkeypatch.setenv("SCB_EMIT_READS_V2", "1")
+    for kw in (dict(n=9000, L=40, seed=191), dict(n=5000, L=300, seed=192), dict(n=7000, L=17, seed=193), dict(n=4000, L=272, seed=194, plant=0.9)):
+        n, L = kw.pop("n"), kw.pop("L")
+        cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+        o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+        t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+        util.assert_same(o, t, r)

@@ -394,3 +394,57 @@ def test_host_tool_rejects_ragged_reads(tmp_path):
     (tmp_path / "o").mkdir()
     r = subprocess.run([tool, str(f), "--dump-soa", str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"(ERROR)" in r.stderr          # the reference's convention: message + exit(1)
+
+
+def test_emit_record_host_device_code_against_per_base_reference(tmp_path):
+    """scalce_b200/csrc/emit_record.h is compiled into the (opt-in) stream-1 kernel AND is plain C++: check the record it
+    writes (rotation around the core, zero padding, 1- or 2-byte end marker, any byte alignment) base by base, under
+    the address and undefined-behaviour sanitizers, for read lengths around every word boundary."""
+    import subprocess
+    src = tmp_path / "er_test.cpp"
+    hdr = os.path.join(ROOT, "scalce_b200", "csrc", "emit_record.h")
+    src.write_text(r'''
+#include "%s"
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+using namespace scb;
+int main() {
+    std::mt19937 rng(7);
+    long cases = 0;
+    for (int L1 : {16, 17, 31, 32, 33, 36, 47, 48, 64, 100, 150, 151, 250, 255, 256, 300, 2047}) {
+        const int PW = (L1 + 15) / 16, sz_meta = L1 > 255 ? 2 : 1;
+        for (int rep = 0; rep < 300; rep++) {
+            std::vector<int> base(L1);
+            for (auto &b : base) b = rng() & 3;
+            std::vector<uint32_t> row(PW + 2, 0);                    // the row + the two pad words the code may read
+            for (int q = 0; q < L1; q++) row[q >> 4] |= (uint32_t)base[q] << (30 - 2 * (q & 15));
+            int lv = rep %% 7 == 0 ? 0 : (int)(rng() %% (L1 < 32 ? L1 : 32)) + 1;
+            int end = lv == 0 ? 0 : lv + (int)(rng() %% (L1 - lv + 1));
+            if (rep %% 11 == 0 && lv) end = L1;
+            if (rep %% 13 == 0 && lv) end = lv;
+            std::vector<int> outb;
+            for (int q = end; q < L1; q++) outb.push_back(base[q]);          // output_read, reads.cpp:432-461
+            for (int q = 0; q < end - lv; q++) outb.push_back(base[q]);
+            const int total = L1 - lv, nbytes = (total + 3) / 4;
+            std::vector<uint8_t> want(nbytes + sz_meta, 0), got(nbytes + sz_meta + 8, 0xAA);
+            for (int j = 0; j < total; j++) want[j >> 2] |= outb[j] << (6 - 2 * (j & 3));
+            want[nbytes] = end & 0xff;
+            if (sz_meta > 1) want[nbytes + 1] = (end >> 8) & 0xff;
+            const int sz = emit_record(row.data(), L1, lv, end, sz_meta, got.data() + 3);
+            if (sz != nbytes + sz_meta || memcmp(want.data(), got.data() + 3, sz) != 0 || got[3 + sz] != 0xAA || got[2] != 0xAA) {
+                printf("MISMATCH L1 %%d lv %%d end %%d\n", L1, lv, end);
+                return 1;
+            }
+            cases++;
+        }
+    }
+    printf("ok %%ld\n", cases);
+    return 0;
+}
+''' % hdr)
+    exe = tmp_path / "er_test"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fsanitize=address,undefined", "-o", str(exe), str(src)], check=True)
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and r.stdout.startswith(b"ok"), (r.stdout + r.stderr).decode()
