@@ -156,6 +156,8 @@ struct scb_handle {
     const uint64_t *srt_keys = nullptr;                    // sorted keys of the chunk-major order
     int srt_seg_bits = 0;
     bool srt_keys_valid = false;   // scb_shard_finish_sort ran: scb_shard_finish only emits
+    // opt-in overlap of the flush-chunk pass with the tie-break (SCB_OVERLAP_CHUNKS): state between its two halves
+    bool chunks_begun = false; uint32_t *chk_cstart = nullptr; int chk_cap = 0; int *chk_nch_pinned = nullptr; cudaEvent_t ev_chk = nullptr;
     bool emit_early_done = false;  // scb_shard_finish_early ran: scb_shard_finish only runs the kernels that read quality / mate-2 rows
     Pending sh_local;          // the rank's own input after scb_shard_import replaced `cur` (phase-2 sends still read it)
     // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
@@ -761,6 +763,39 @@ static void stage_meta(scb_handle *h) {
 
 }
 
+// 3a. (opt-in, SCB_OVERLAP_CHUNKS=1; not yet measured) the size prefix sum and the chunk boundaries only need the scan's
+// levels, not the tie-break: enqueue them on a side stream BEFORE the resolve kernel is launched. That kernel holds
+// one CTA of 384 threads per SM and is latency bound; the small streaming kernels fit next to it. stage_chunks then only
+// reads the chunk count back and writes the per-read chunk ids.
+static void chunks_begin(scb_handle *h) {
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    const Pending &c = h->cur;
+    const int64_t n = c.n;
+    cudaStream_t sa = h->st_aux[0];
+    if (!h->ev_chk) SCB_CUDA(cudaEventCreateWithFlags(&h->ev_chk, cudaEventDisableTiming));
+    if (!h->chk_nch_pinned) SCB_CUDA(cudaHostAlloc((void **)&h->chk_nch_pinned, 64, cudaHostAllocDefault));
+    SCB_CUDA(cudaEventRecord(h->ev_fork, h->st));
+    SCB_CUDA(cudaStreamWaitEvent(sa, h->ev_fork, 0));
+    DevBuf ws64((size_t)scan_tiles(n) * 8, sa);
+    const int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
+    RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
+    DevBuf S((size_t)(n + 1) * 8, sa);
+    exclusive_scan<uint64_t>(rs, n, S.as<uint64_t>(), S.as<uint64_t>() + n, ws64.as<uint64_t>(), sa);
+    uint64_t max_rd = 256 + (uint64_t)sz_read(L1) + L1 + sz_read(L2) + L2 + 40;
+    uint64_t cap64 = (uint64_t)n * max_rd / cfg.bucket_set_bytes + 2;
+    if (cap64 > (uint64_t)n + 1) cap64 = (uint64_t)n + 1;
+    if (cap64 > (1u << 24)) throw CudaError{"bucket_set_bytes too small for this many reads (more than 2^24 flush chunks)"};
+    const int cap = (int)cap64;
+    DevBuf cstart((size_t)cap * 4, sa), dn(4, sa);
+    SCB_LAUNCH(chunk_bounds_k, 1, 1, 0, sa, S.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, cstart.as<uint32_t>(), cap, dn.as<int>());
+    SCB_CUDA(cudaMemcpyAsync(h->chk_nch_pinned, dn.p, 4, cudaMemcpyDeviceToHost, sa));
+    SCB_CUDA(cudaEventRecord(h->ev_chk, sa));
+    h->chk_cstart = cstart.as<uint32_t>();   // arena memory: stays valid until the flush ends
+    h->chk_cap = cap;
+    h->chunks_begun = true;
+}
+
 // 3. sizes -> flush chunks (compress.cpp:702, 708-713)
 static void stage_chunks(scb_handle *h) {
     cudaStream_t st = h->st;
@@ -770,6 +805,21 @@ static void stage_chunks(scb_handle *h) {
     const int64_t n = c.n;
     const int nb = h->tab.n_buckets;
     (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
+    if (h->chunks_begun) {   // second half of the overlapped variant
+        h->chunks_begun = false;
+        SCB_CUDA(cudaEventSynchronize(h->ev_chk));
+        SCB_CUDA(cudaStreamWaitEvent(st, h->ev_chk, 0));
+        const int nch = *h->chk_nch_pinned;
+        if (nch > h->chk_cap) throw CudaError{"internal: chunk capacity exceeded"};
+        h->n_chunks = nch;
+        if (nch > 1) {
+            h->chunk.alloc((size_t)n * 4, st);
+            SCB_LAUNCH(chunk_ids_k, (unsigned)cdiv(n, 256), 256, 0, st, h->chk_cstart, nch, n, h->chunk.as<uint32_t>());
+        } else {
+            h->chunk.release();
+        }
+        return;
+    }
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     {
         int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
@@ -1373,6 +1423,11 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
     stage_scan(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
+    h->chunks_begun = false;
+    {
+        const char *oc = getenv("SCB_OVERLAP_CHUNKS");
+        if (oc && atoi(oc) != 0 && h->cur.n > 0) chunks_begin(h);
+    }
     stage_resolve(h);
     stage_meta(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
@@ -1814,6 +1869,8 @@ void scb_destroy(scb_handle *h) {
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
     for (auto &a : h->st_aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_chk) cudaEventDestroy(h->ev_chk);
+    if (h->chk_nch_pinned) cudaFreeHost(h->chk_nch_pinned);
     for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);

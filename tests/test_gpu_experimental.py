@@ -7,6 +7,7 @@ SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GP
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
   SCB_EMIT_READS_V2=1      stream-1 writer with 8-byte row staging and branch-free record assembly (emit_reads_fast.cuh)
+  SCB_OVERLAP_CHUNKS=1     size prefix sum + flush-chunk boundaries on a side stream under the tie-break kernel
   SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
 
 Same bar as everywhere else: bit-exact against the oracle.
@@ -72,7 +73,7 @@ def test_early_emit_and_prerounds(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -109,7 +110,7 @@ def test_scan_v2_million_reads(monkeypatch):
 
 
 def test_all_single_gpu_variants_together_million_reads(monkeypatch):
-    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2"):
+    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS"):
         monkeypatch.setenv(var, "1")
     cores, b, q1, q2, _ = util.make_case(1000000, 150, seed=173, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)],
                                          paired=True, L2=100)
