@@ -5,7 +5,9 @@
 // the emit loop that walks the hit masks again, of ~3700 per tile): candidate space is reserved BEFORE the pick, by
 // hit count (an upper bound of the kept candidates; the candidate arrays have holes anyway), so that each candidate
 // can be written the moment it is kept; a hit of a higher level restarts the list and overwrites the slots.
-// Results (level, count, ordered candidates and positions per read) are identical; only cand_off differs.
+// The partial last word of a read is walked with the same compile-time shifts as the full words (the variable-shift
+// loop cost ~100 instructions per tile for 6 bases). Results (level, count, ordered candidates and positions per
+// read) are identical; only cand_off differs.
 #pragma once
 #include "scan_smem.cuh"
 
@@ -99,8 +101,11 @@ __global__ void __launch_bounds__(1024, 1) scan_smem2_k(ScanSmemParams p) {
                 else {
                     const uint32_t wv = row[full];
                     uint32_t m = 0;
-                    for (int j = 0; j < tail; j++) {
-                        const uint32_t c2 = ((wv >> (30 - 2 * j)) & 3u) * 2u;
+                    // same body as the full words (compile-time shifts), left through a warp-uniform exit
+#pragma unroll
+                    for (int j = 0; j < 15; j++) {
+                        if (j >= tail) break;
+                        const uint32_t c2 = (wv >> (29 - 2 * j)) & 6u;
                         e4 = *(const uint16_t *)(tb + (e4 * 2u + c2));
                         if (e4 >= H4) { m |= 1u << j; sts_u16(qp, e4); qp += 2; }
                     }
