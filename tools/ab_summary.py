@@ -50,7 +50,7 @@ def main():
     print("rounds".ljust(16) + "".join(str((runs[n].get("roofline") or {}).get("resolve_rounds")).rjust(w) for n in names))
     for n in names:
         e = runs[n].get("e2e")
-        if e:
+        if e and e.get('value'):
             print(f"e2e {n}: {e['value'] / 1e6:.1f} M reads/s, {e['ms_per_step']:.0f} ms/step, submit/flush/copy-out {e.get('ms_submit_flush_copyout')}, "
                   f"serial {e.get('serial')}, pipelined {e.get('pipelined')}")
 
