@@ -448,3 +448,38 @@ int main() {
     subprocess.run(["g++", "-O1", "-std=c++17", "-fsanitize=address,undefined", "-o", str(exe), str(src)], check=True)
     r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and r.stdout.startswith(b"ok"), (r.stdout + r.stderr).decode()
+
+
+def _bench_dry(*args):
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dry_run.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return json.loads(r.stdout.decode().strip().splitlines()[-1])
+
+
+def test_bench_native_arm_control_flow_and_json_contract():
+    """bench.py's native arm with the device and the library faked (tests/bench_dry_run.py): every key of the bench
+    contract is present and the end-to-end arm, its pipelined variant and the per-stage figures are assembled."""
+    d = _bench_dry("--reads", "20000", "--steps", "2", "--warmup", "1", "--no-cpu", "--e2e-depth", "2")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["config"]["workload"] and d["dtype"] == "u8" and d["vs_baseline"] is None and d["gpu_launches"] > 0
+    rf = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "per_stage", "stage_ms"):
+        assert k in rf, k
+    assert rf["bound"] == "hbm" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 20000 * 100 * 0 + 20000 * 150 * 2 + 20000 * 13 + 20001 * 8 and e["d2h_bytes_per_step"] == 20 + 60 + 200 + 16
+    assert e["pipelined"]["depth"] == 2 and e["pipelined"]["slots_agree"] and "serial" in e
+
+
+def test_bench_native_arm_cpu_baseline_fields():
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")):
+        pytest.skip("oracle/_ref not built")
+    d = _bench_dry("--reads", "20000", "--steps", "1", "--warmup", "1", "--no-e2e", "--cpu-sample", "20000")
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] >= c["value_1thread"] * 0.5 and c["unit"] == "reads/s" and c["sample"]
+    assert d["e2e"] is None
