@@ -1,6 +1,9 @@
 """Opt-in variants that were written without GPU access (end of round 1) and have NOT been measured or
-run on a B200 yet. They are off by default in the product path; these parity tests only run when
-SCB_TEST_EXPERIMENTAL=1 so that an unverified variant cannot turn the default GPU suite red.
+run on a B200 yet. They are off by default in the product path. This file is not collected by the default run
+(no test_ prefix): tests/test_zz_gpu_experimental.py runs it in ONE child process with a hard time limit and reports
+the outcome as pass / xfail, so that an unverified variant can neither turn the GPU suite red, nor poison its CUDA
+context, nor hang it. Run it directly with
+    SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q
 
   SCB_SHARD_PREROUNDS=k    later ranks iterate their shard from an estimate while rank 0 resolves alone
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel

@@ -1,12 +1,12 @@
 #!/bin/bash
 # ONE gpurun call (one GPU, ~6 min) that answers every open question the end of round 1 left behind:
-#   1. do the opt-in variants pass parity (tests/test_gpu_experimental.py)?
+#   1. do the opt-in variants pass parity (tests/experimental_cases.py)?
 #   2. what does each switch do to the headline step (50M x 150 bp, stage times from bench.py)?
 #   3. the pipelined end-to-end arm.
 # Usage:  gpurun --timeout 900 -- 'bash tools/round2_ab.sh'      results: gpurun_out/ab/ + a table on stdout
 mkdir -p gpurun_out/ab
 export PYTHONUNBUFFERED=1
-SCB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/ab/tests.log 2>&1
+SCB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/experimental_cases.py -q > gpurun_out/ab/tests.log 2>&1
 tail -n 15 gpurun_out/ab/tests.log
 run() {  # name ENV=... : kernel-only bench line of one configuration
   local name=$1; shift
