@@ -7,7 +7,10 @@ import sys
 
 import pytest
 
-pytestmark = pytest.mark.gpu
+# Off unless SCB_RUN_EXPERIMENTAL=1: the variants have never run on a B200, and the round-end suite shares its box with the
+# smoke run and the bench - not the place for a first run of unverified kernels. tools/round2_ab.sh runs the cases directly.
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SCB_RUN_EXPERIMENTAL", "0") in ("", "0"),
+                                                   reason="experimental variants: set SCB_RUN_EXPERIMENTAL=1 (or run tools/round2_ab.sh)")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
