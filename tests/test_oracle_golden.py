@@ -134,3 +134,41 @@ def test_reference_harness_thread_loop_conserves_payload(tmp_path):
     assert st[0] == mt[0] == int(off[n]) + n          # names: length byte + name per read
     assert st[2] == mt[2] == n * L                    # qualities
     assert st[1] == mt[1]                             # packed reads: the chosen core's LENGTH does not depend on the tie-break
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_cpp_host_stage_plus_oracle_matches_reference_cli(path, oracle_lib, tmp_path):
+    """The C++ host side (scalce_b200/host/scb_boost --dump-soa: FASTQ parse, phred offset, name and quality payloads)
+    feeding the oracle must give the files the UNMODIFIED reference CLI wrote for the same FASTQ: the host stages of the
+    drop-in are pinned to the reference without a GPU (the transform in between is what the -m gpu tests pin)."""
+    import subprocess
+    from scalce_b200 import build as bld
+    z, meta = _load(path)
+    cores, b = _inputs(z, meta)
+    tool = bld.build_host_tool()
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(b, f1, f2 if meta["paired"] else None)
+    d = tmp_path / "soa"
+    d.mkdir()
+    cmd = [tool, f1] + (["-r", f2] if meta["paired"] else []) + ["--dump-soa", str(d), "--batch", "1000"] + ([] if meta["use_names"] else ["-n"])
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    info = dict(line.split() for line in (d / "meta.txt").read_text().splitlines())
+    n, L, L2 = int(info["n"]), int(info["L1"]), int(info["L2"])
+    assert (n, L, L2) == (meta["n"] if "n" in meta else b.n, meta["L"], meta["L2"] or 0)
+    rd = lambda k, dt=np.uint8: np.fromfile(d / f"{k}.bin", dtype=dt)
+    seq, q1 = rd("seq1").reshape(n, L), rd("qual1").reshape(n, L)
+    seq2 = rd("seq2").reshape(n, L2) if meta["paired"] else None
+    q2 = rd("qual2").reshape(n, L2) if meta["paired"] else None
+    names, name_off = (rd("names"), rd("name_off", np.int64)) if meta["use_names"] else (b.names, b.name_off)
+    bucket = {"4G": 4 << 30, "1M": 1 << 20}[meta["bucket"]]
+    o = orc.Oracle(cores, L, L2, use_names=meta["use_names"], paired=meta["paired"], bucket_set_bytes=bucket)
+    o.submit(seq, q1, names, name_off, seq2, q2)
+    o.finish()
+    for mate in range(1 + int(meta["paired"])):
+        fn, fr, fq = orc.assemble_container(o.stream(3), o.stream(0), o.stream(1), o.stream(2), cores, L, int(info["offset1"]),
+                                            use_names=meta["use_names"], library=b"lib", paired=meta["paired"], mate=mate,
+                                            reads2=o.stream(4), quals2=o.stream(5), L2=L2)
+        for ext, data in (("n", fn), ("r", fr), ("q", fq)):
+            k = f"{mate + 1}{ext}"
+            assert hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{k}: bytes differ from the reference CLI output"
