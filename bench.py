@@ -515,7 +515,7 @@ def main():
         "emit": 2 * L + 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + L + 4, "merged": 0, "arrays": 16,
         # sharded run: pack + exchange move the payload once each (aux word, packed row, quality row, name)
         "finalize": 8, "hist": 4, "resolve_rounds": 16, "pack": 2 * (8 + 40 + L + NAME_BYTES), "exchange": 2 * (8 + 40 + NAME_BYTES), "exchange_rows": 2 * L, "import": 16, "sort": 24,
-        "prerounds": 16, "emit_early": 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + 40 + 8,   # opt-in stages of the sharded run
+        "emit_early": 2 * (NAME_BYTES + 1) + (L - mean_core + 3) // 4 + 1 + 40 + 8,   # opt-in stages of the sharded run
     }
     ach = N * stage_bytes.get(dom, 0) / (mean_st[dom] * 1e-3) / 1e9
     # DRAM bytes per read of each stage's kernels (dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list of this

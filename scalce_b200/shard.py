@@ -275,7 +275,6 @@ class ShardedTransform:
         self.on_torch_stream = bool(use_torch_stream)
         self.overlap = overlap      # row exchange overlapped with the receive side's sort (p2p only)
         import os
-        self.prerounds = int(os.environ.get("SCB_SHARD_PREROUNDS", "0") or 0)   # see flush(): 0 = off (default)
         self.early_emit = os.environ.get("SCB_SHARD_EARLY_EMIT", "0") not in ("", "0")
         self.stats = {}
         self._keep = None
@@ -326,30 +325,9 @@ class ShardedTransform:
         # ---- tie-break -------------------------------------------------------------------------------------
         tot = torch.zeros(ncols + 1, dtype=torch.int32, device=dev)   # u32 bit patterns
         sync = (lambda: None) if self.on_torch_stream else (lambda: torch.cuda.synchronize(dev))   # one stream orders everything
-        warm = self.prerounds > 0 and G > 1   # the switch must be the same on every rank
-        pre_ev = None
         if r == 0:
             _check(L.scb_shard_resolve_local(h, C.c_void_p(tot.data_ptr())))
             lap("resolve")
-        elif warm:
-            # Opt-in (SCB_SHARD_PREROUNDS=k): while rank 0 resolves its shard alone the later ranks would only wait, so
-            # they iterate their own shard from an ESTIMATE of what precedes it - first from nothing, then from their own
-            # bucket histogram scaled to the reads before the shard (shards of one input are statistically alike). The
-            # joint rounds then start from an almost converged assignment with fragile-read lists in place. Exactness is
-            # untouched: the estimate only picks the starting point of the fixed-point iteration below.
-            pre_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            pre_ev[0].record()
-            pre_keep = []
-            for k in range(self.prerounds):
-                if k == 0:
-                    bf = torch.zeros(ncols, dtype=torch.int32, device=dev)
-                else:
-                    bf = (tot[:ncols].to(torch.int64) * before[r] // max(ns[r], 1)).clamp_(max=0x7fffffff).to(torch.int32)
-                pre_keep.append(bf)   # referenced until the stream has run the round that reads it
-                sync()
-                _check(L.scb_shard_resolve_round(h, C.c_void_p(bf.data_ptr()), before[r], 1 if k == 0 else 0, C.c_void_p(tot.data_ptr())))
-                sync()
-            pre_ev[1].record()
         sync()
         allt = comm.allgather(tot)
         rounds = 0
@@ -363,10 +341,7 @@ class ShardedTransform:
             inflight = []          # (event, pinned changed count, was_first)
             if pipelined and not hasattr(self, "_pin"):
                 self._pin = [torch.empty(1, dtype=torch.int64, pin_memory=True) for _ in range(4)]   # allocated once: pinning is slow
-            # after pre-rounds every rank already holds an assignment and its histogram: the first joint round is an
-            # ordinary one (prefix counts of the current global assignment), so "nothing changed" already proves the
-            # fixed point and the kernel continues from the histograms the pre-rounds left
-            first = not warm
+            first = True
             done = False
             while not done:
                 if r > 0:
@@ -399,8 +374,6 @@ class ShardedTransform:
             e1.record()
             torch.cuda.synchronize(dev)
             ms["resolve_rounds"] = e0.elapsed_time(e1)
-            if pre_ev is not None:
-                ms["prerounds"] = pre_ev[0].elapsed_time(pre_ev[1])
         gtot = allt[:, :ncols].sum(0, dtype=torch.int64).to(torch.int32).contiguous()
         torch.cuda.synchronize(dev)
         _check(L.scb_shard_finalize(h, C.c_void_p(gtot.data_ptr()), n_global))

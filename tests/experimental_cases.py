@@ -5,7 +5,6 @@ the outcome as pass / xfail, so that an unverified variant can neither turn the 
 context, nor hang it. Run it directly with
     SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q
 
-  SCB_SHARD_PREROUNDS=k    later ranks iterate their shard from an estimate while rank 0 resolves alone
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
@@ -35,31 +34,6 @@ def _sharded(n, L, world, **kw):
     return o, ranks
 
 
-@pytest.mark.parametrize("k", [1, 2, 3])
-def test_prerounds_two_ranks(monkeypatch, k):
-    monkeypatch.setenv("SCB_SHARD_PREROUNDS", str(k))
-    _sharded(30000, 100, 2, seed=151)
-
-
-def test_prerounds_four_ranks_multi_chunk(monkeypatch):
-    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
-    _sharded(40000, 100, 4, seed=153, bucket_set_bytes=1 << 20)
-
-
-def test_prerounds_empty_ranks(monkeypatch):
-    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "2")
-    _sharded(9000, 64, 4, seed=156, bounds=[0, 0, 5000, 5000, 9000])
-
-
-def test_prerounds_larger_headline_cores(monkeypatch):
-    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
-    cores, b, q1, q2, _ = util.make_case(300000, 100, seed=159, plant=0.0,
-                                         spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
-    o = util.run_oracle(cores, b, q1, q2)
-    ranks = util.run_sharded_loopback(cores, b, q1, q2, 3)
-    util.assert_sharded_same(o, ranks)
-
-
 def test_early_emit_paired_multi_chunk(monkeypatch):
     monkeypatch.setenv("SCB_SHARD_EARLY_EMIT", "1")
     _sharded(20000, 100, 3, seed=154, paired=True, L2=75, bucket_set_bytes=1 << 20, bounds=[0, 1000, 13000, 20000])
@@ -70,9 +44,8 @@ def test_early_emit_no_names_short(monkeypatch):
     _sharded(40000, 36, 8, seed=155, use_names=False)
 
 
-def test_early_emit_and_prerounds(monkeypatch):
+def test_early_emit_four_ranks(monkeypatch):
     monkeypatch.setenv("SCB_SHARD_EARLY_EMIT", "1")
-    monkeypatch.setenv("SCB_SHARD_PREROUNDS", "3")
     _sharded(30000, 100, 4, seed=157)
 
 

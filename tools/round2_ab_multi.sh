@@ -1,5 +1,5 @@
 #!/bin/bash
-# The sharded run's opt-in switches at N GPUs (gpurun --gpus N): default, pre-rounds, early emit, both.
+# The sharded run's opt-in switch at N GPUs (gpurun --gpus N): default vs early emit.
 # Usage:  gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_ab_multi.sh 8'
 N=${1:-2}
 mkdir -p gpurun_out/ab
@@ -10,7 +10,5 @@ run() {
       bench.py --gpus $N --steps 3 --warmup 2 --no-e2e --no-cpu > gpurun_out/ab/n${N}_$name.json 2> gpurun_out/ab/n${N}_$name.err
 }
 run default
-run prerounds SCB_SHARD_PREROUNDS=3
 run early_emit SCB_SHARD_EARLY_EMIT=1
-run both SCB_SHARD_PREROUNDS=3 SCB_SHARD_EARLY_EMIT=1
 python tools/ab_summary.py gpurun_out/ab n${N}_

@@ -1,0 +1,175 @@
+// sim_resolve.c - CPU model of the tie-break's fixed-point SCHEDULES (not of the kernels): how many rounds do the
+// geometric-block schedule of one GPU and the joint rounds of the sharded run need, and what do estimate-driven
+// pre-rounds change? Used to choose what to measure on the GPU; nothing here is part of the product or of a test.
+//
+// Rule (reads.cpp:420-425, 246): read i goes to the FIRST of its candidates with the largest population so far.
+// Model of the headline workload (50M x 150 bp, 2048 cores: 1024 x 8 bp, 512 x 9, 256 x 10, 128 x 11, 128 x 12): per
+// read the number of hits of each core length is Poisson (positions x cores / 4^len), the read's candidates are that
+// many distinct uniformly random cores of the longest length that hit.
+// A round = every subtile (1776 per rank, as 148 CTAs x 12 warps) is swept sequentially from start counts derived
+// from the previous round's per-subtile histograms (Jacobi across subtiles) - DESIGN.md section 5.
+//
+//   gcc -O2 -fopenmp -o /tmp/sim_resolve tools/sim_resolve.c -lm
+//   /tmp/sim_resolve single 50000000            rounds of the one-GPU geometric schedule
+//   /tmp/sim_resolve shard 8 50000000 0         joint rounds at 8 ranks, no pre-rounds
+//   /tmp/sim_resolve shard 8 50000000 3         ... with 3 pre-rounds on ranks >= 1
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NB 2048
+#define MAXC 6
+#define SUB 1776
+
+static uint64_t rs;
+static inline uint64_t rnd(uint64_t *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return *s; }
+static inline double urnd(uint64_t *s) { return (rnd(s) >> 11) * (1.0 / 9007199254740992.0); }
+static int poisson(uint64_t *s, double lam) { double L = exp(-lam), p = 1; int k = 0; do { k++; p *= urnd(s); } while (p > L); return k - 1; }
+
+typedef struct { int64_t n; uint8_t *nc; uint16_t *c; uint8_t *sel; } Reads;
+
+static void gen(Reads *R, int64_t n, uint64_t seed) {
+    R->n = n; R->nc = malloc(n); R->c = malloc((size_t)n * MAXC * 2); R->sel = malloc(n);
+    memset(R->sel, 0xff, n);
+    const int L = 150, len[5] = {8, 9, 10, 11, 12}, cnt[5] = {1024, 512, 256, 128, 128}, first[5] = {0, 1024, 1536, 1792, 1920};
+    double lam[5];
+    for (int k = 0; k < 5; k++) lam[k] = (double)(L - len[k] + 1) * cnt[k] / pow(4.0, len[k]);
+#pragma omp parallel
+    {
+        uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345;
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            if ((i & 0xffff) == 0) s = (seed + (uint64_t)i) * 0x9E3779B97F4A7C15ull + 777;
+            int h[5], top = -1;
+            for (int k = 0; k < 5; k++) { h[k] = poisson(&s, lam[k]); if (h[k] > 0) top = k; }
+            int m = 0;
+            if (top >= 0) {
+                int want = h[top] > MAXC ? MAXC : h[top];
+                while (m < want) {
+                    uint16_t b = (uint16_t)(first[top] + rnd(&s) % cnt[top]);
+                    int dup = 0;
+                    for (int q = 0; q < m; q++) dup |= R->c[i * MAXC + q] == b;
+                    if (!dup) R->c[i * MAXC + m++] = b; else want--;     // a repeated core is one candidate
+                }
+            }
+            R->nc[i] = (uint8_t)m;
+        }
+    }
+}
+
+// one sweep of reads [lo, hi) from counts cnt[] (modified); returns the number of decisions that changed
+static int64_t sweep(Reads *R, int64_t lo, int64_t hi, uint32_t *cnt) {
+    int64_t ch = 0;
+    for (int64_t i = lo; i < hi; i++) {
+        const int nc = R->nc[i];
+        if (!nc) continue;
+        const uint16_t *c = R->c + i * MAXC;
+        int best = 0; uint32_t bc = cnt[c[0]];
+        for (int k = 1; k < nc; k++) if (cnt[c[k]] > bc) { bc = cnt[c[k]]; best = k; }
+        cnt[c[best]]++;
+        if (R->sel[i] != best) { R->sel[i] = (uint8_t)best; ch++; }
+    }
+    return ch;
+}
+
+// One round over block [n0, n1) of R split into SUB subtiles. H[t][b]: per-subtile histograms of the previous round
+// (updated). first: start counts extrapolated from base (g0 = reads before n0 in the job). Returns changed decisions.
+static int64_t round_block(Reads *R, int64_t n0, int64_t n1, const uint32_t *base, uint32_t *H, int first, int64_t g0, uint32_t *tot) {
+    const int64_t len = n1 - n0;
+    int64_t ts = (len + SUB - 1) / SUB; ts = (ts + 31) / 32 * 32; if (ts < 32) ts = 32;
+    const int ns = (int)((len + ts - 1) / ts);
+    uint32_t *start = malloc((size_t)ns * NB * 4);
+    if (first) {
+        for (int t = 0; t < ns; t++)
+            for (int b = 0; b < NB; b++)
+                start[(size_t)t * NB + b] = base[b] + (g0 + n0 > 0 ? (uint32_t)((uint64_t)base[b] * (uint64_t)(t * ts) / (uint64_t)(g0 + n0)) : 0);
+    } else {
+        for (int b = 0; b < NB; b++) { uint32_t run = base[b]; for (int t = 0; t < ns; t++) { start[(size_t)t * NB + b] = run; run += H[(size_t)t * NB + b]; } }
+    }
+    int64_t changed = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : changed)
+    for (int t = 0; t < ns; t++) {
+        uint32_t cnt[NB];
+        memcpy(cnt, start + (size_t)t * NB, sizeof cnt);
+        const int64_t lo = n0 + t * ts, hi = lo + ts < n1 ? lo + ts : n1;
+        changed += sweep(R, lo, hi, cnt);
+        for (int b = 0; b < NB; b++) H[(size_t)t * NB + b] = cnt[b] - start[(size_t)t * NB + b];
+    }
+    if (tot) { memset(tot, 0, NB * 4); for (int t = 0; t < ns; t++) for (int b = 0; b < NB; b++) tot[b] += H[(size_t)t * NB + b]; }
+    free(start);
+    return changed;
+}
+
+// geometric schedule of one GPU (api.cu dense_blocks): x4 until 1M reads precede, then x2. Returns total rounds.
+static int single(Reads *R, uint32_t *base) {
+    uint32_t *H = calloc((size_t)SUB * NB, 4), tot[NB];
+    int64_t n0 = 0; int rounds = 0, nblk = 0;
+    while (n0 < R->n) {
+        int64_t lenb = n0 < (1 << 20) ? 3 * n0 : n0; if (lenb < 4096) lenb = 4096;
+        int64_t n1 = n0 + lenb < R->n ? n0 + lenb : R->n;
+        int first = 1, r = 0;
+        char trace[512]; int tl = 0;
+        for (;;) {
+            int64_t ch = round_block(R, n0, n1, base, H, first, 0, tot); first = 0; r++;
+            if (tl < 480) tl += snprintf(trace + tl, sizeof trace - tl, " %ld", (long)ch);
+            if (!ch) break;
+        }
+        if (getenv("SIM_TRACE")) printf("    changed per round:%s\n", trace);
+        for (int b = 0; b < NB; b++) base[b] += tot[b];
+        printf("  block %2d [%9ld, %9ld): %d rounds\n", nblk, (long)n0, (long)n1, r);
+        rounds += r; nblk++; n0 = n1;
+    }
+    free(H);
+    return rounds;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: sim_resolve single N | shard G N_PER_RANK PREROUNDS\n"); return 2; }
+    if (!strcmp(argv[1], "single")) {
+        Reads R; gen(&R, atoll(argv[2]), 1);
+        uint32_t base[NB] = {0};
+        int r = single(&R, base);
+        printf("single GPU, %ld reads: %d rounds in total\n", (long)R.n, r);
+        return 0;
+    }
+    const int G = atoi(argv[2]); const int64_t n = atoll(argv[3]); const int pre = argc > 4 ? atoi(argv[4]) : 0;
+    Reads *R = malloc(sizeof(Reads) * G);
+    for (int g = 0; g < G; g++) gen(&R[g], n, 100 + g);
+    uint32_t (*hist)[NB] = calloc(G, sizeof *hist);        // per-rank bucket histogram of the current assignment
+    uint32_t **H = malloc(sizeof(void *) * G);
+    for (int g = 0; g < G; g++) H[g] = calloc((size_t)SUB * NB, 4);
+    // rank 0: exact (what its solo resolve produces)
+    { uint32_t cnt[NB] = {0}; sweep(&R[0], 0, n, cnt); memcpy(hist[0], cnt, sizeof cnt); }
+    // pre-rounds on ranks >= 1: first from nothing, then from the rank's own histogram scaled to the reads before it
+    for (int k = 0; k < pre; k++)
+        for (int g = 1; g < G; g++) {
+            uint32_t base[NB];
+            for (int b = 0; b < NB; b++) base[b] = k == 0 ? 0 : (uint32_t)((uint64_t)hist[g][b] * (uint64_t)g);
+            int64_t ch = round_block(&R[g], 0, n, base, H[g], k == 0, (int64_t)g * n, hist[g]);
+            if (g == 1 || g == G - 1) printf("  pre-round %d rank %d: %ld changed\n", k, g, (long)ch);
+        }
+    int rounds = 0, first = pre == 0;
+    for (;;) {
+        uint32_t (*nh)[NB] = calloc(G, sizeof *nh);
+        int64_t changed = 0;
+        for (int g = 1; g < G; g++) {
+            uint32_t base[NB];
+            for (int b = 0; b < NB; b++) {
+                if (first) base[b] = (uint32_t)((uint64_t)hist[0][b] * (uint64_t)g);           // rank 0's histogram scaled (exact for rank 1)
+                else { uint32_t s = 0; for (int q = 0; q < g; q++) s += hist[q][b]; base[b] = s; }
+            }
+            changed += round_block(&R[g], 0, n, base, H[g], first, (int64_t)g * n, nh[g]);
+        }
+        for (int g = 1; g < G; g++) memcpy(hist[g], nh[g], sizeof hist[g]);     // Jacobi across ranks: all see last round's histograms
+        free(nh);
+        rounds++;
+        printf("  joint round %2d: %ld decisions changed\n", rounds, (long)changed);
+        if (!first && changed == 0) break;
+        first = 0;
+        if (rounds > 200) break;
+    }
+    printf("%d ranks x %ld reads, %d pre-rounds: %d joint rounds\n", G, (long)n, pre, rounds);
+    return 0;
+}
