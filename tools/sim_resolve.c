@@ -107,7 +107,9 @@ static int single(Reads *R, uint32_t *base) {
     uint32_t *H = calloc((size_t)SUB * NB, 4), tot[NB];
     int64_t n0 = 0; int rounds = 0, nblk = 0;
     while (n0 < R->n) {
-        int64_t lenb = n0 < (1 << 20) ? 3 * n0 : n0; if (lenb < 4096) lenb = 4096;
+        const char *ge = getenv("SIM_GROWTH_LATE"), *gs = getenv("SIM_GROWTH_EARLY"), *sm = getenv("SIM_SMALL");   // api.cu: 2, 4, 1M
+        const int64_t g_late = ge ? atoi(ge) : 2, g_early = gs ? atoi(gs) : 4, small = sm ? atoll(sm) : (1 << 20);
+        int64_t lenb = n0 < small ? (g_early - 1) * n0 : (g_late - 1) * n0; if (lenb < 4096) lenb = 4096;
         int64_t n1 = n0 + lenb < R->n ? n0 + lenb : R->n;
         int first = 1, r = 0;
         char trace[512]; int tl = 0;
