@@ -204,6 +204,21 @@ int scb_shard_resolve_local(scb_handle *h, uint32_t *tot_dev);
 int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t reads_before, int32_t first, uint32_t *tot_dev);
 /* Commits the converged assignment. global_tot_dev: device u32[n_cols], bucket histogram summed over all
  * ranks (adds to the lifetime counts of EVERY rank's handle); n_global: reads of the whole flush. */
+/* Opt-in alternative to the host-driven loop of scb_shard_resolve_round + all-gather: ALL joint rounds inside one kernel
+ * per rank. The ranks exchange their histogram rows through peer memory (stores over NVLink into every rank's exchange
+ * buffer, system-scope flags) - no host and no NCCL in the loop. Needs one process per GPU with peer access.
+ *   scb_shard_joint_reserve  this rank's exchange buffer (device pointer; export it with scb_ipc_export, map the peers'
+ *                            with scb_ipc_open; *changed = 1 when it was (re)allocated and must be re-published)
+ *   scb_shard_resolve_joint  collective: every rank calls it once per flush, after rank 0's scb_shard_resolve_local.
+ *                            peers[g] = rank g's buffer as mapped in this process (peers[rank] = the own buffer);
+ *                            reads_before = reads of the lower ranks; n_rank0 = reads of rank 0; row0_dev = rank 0's
+ *                            histogram from scb_shard_resolve_local (rank 0 only). On return rows_out points at
+ *                            n_ranks rows of *row_words u32 (device): every rank's bucket histogram of the last round,
+ *                            entry n_cols = its changed count; *rounds_out = joint rounds run.
+ * Replaces the loop over scb_shard_resolve_round (compress.cpp has no counterpart: the reference is one process). */
+int scb_shard_joint_reserve(scb_handle *h, int32_t n_ranks, void **ptr, int32_t *changed);
+int scb_shard_resolve_joint(scb_handle *h, int32_t rank, int32_t n_ranks, void *const *peers, int64_t reads_before, int64_t n_rank0,
+                            const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *row_words, int32_t *rounds_out);
 int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global);
 /* Local bucket histogram in emission order, device u32[n_cols] (overwritten). */
 int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev);

@@ -176,6 +176,9 @@ struct scb_handle {
     std::vector<void *> rx_retired;
     DevBuf sh_name_off;        // import side: name offsets rebuilt from the lengths
     float sh_ms = 0;           // device time of the last scb_shard_* call
+    // joint tie-break rounds inside one kernel (opt-in): this rank's exchange buffer (plain cudaMalloc, exported over CUDA IPC)
+    void *jx = nullptr; size_t jx_cap = 0; int jx_G = 0; uint32_t j_epoch = 0;
+    std::vector<void *> jx_retired;
 };
 
 namespace scb {
@@ -589,9 +592,9 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
-    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k, W * 32, smem));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false>, W * 32, smem));
     if (occ < 1) return false;
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
@@ -614,7 +617,7 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
 }
 
 // one launch of the engine over blocks `blk` of the local reads; returns status (0 ok)
-static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<int64_t> &blk, uint32_t *tot_out) {
+static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<int64_t> &blk, uint32_t *tot_out, const RdJoint *joint = nullptr) {
     cudaStream_t st = h->st;
     const int nb1 = h->tab.n_buckets + 1;
     const int W = h->sh_W, grid = h->sh_grid;
@@ -625,7 +628,7 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
         SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
         SCB_CUDA(cudaMemsetAsync(h->sh_stat.p, 0, 8, st));
     }
-    SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)(mode == 0 ? kRdMaxRounds : 1) * 4, st));
+    SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)((mode == 0 || mode == 3) ? kRdMaxRounds : 1) * 4, st));
     RdParams rp;
     rp.n = h->cur.n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
     rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = nullptr;
@@ -643,10 +646,15 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
     rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
+    if (joint) rp.j = *joint; else memset(&rp.j, 0, sizeof rp.j);
     void *args[] = {&rp};
-    SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k, dim3(grid), dim3(W * 32), args, smem, st));
+    if (mode == 3) {   // all joint rounds of the sharded run in this launch (resolve_dense.cuh, JOINT)
+        SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k<true>, dim3(grid), dim3(W * 32), args, smem, st));
+    } else
+    SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k<false>, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
-    if (mode != 0) {
+    if (mode != 0 && mode != 3) {
         h->last_rounds++;
         if (getenv("SCB_RESOLVE_STAT")) {   // debugging aid: subtile sweeps of this round (synchronises)
             unsigned long long is[4] = {0, 0, 0, 0};
@@ -1158,6 +1166,71 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
     h->sh_ms = 0;   // asynchronous: the caller times the round loop on its stream
 }
 
+// ---- joint rounds inside one kernel per rank (opt-in; resolve_dense.cuh "joint mode") ------------------------------------
+static int joint_row_words(int nb1) { return (nb1 + 1 + 3) & ~3; }
+static size_t joint_bytes(int nb1, int G) { return ((size_t)2 * G * joint_row_words(nb1) + (size_t)G + 64) * 4; }
+
+static void shard_joint_reserve(scb_handle *h, int G, void **ptr, int32_t *changed) {
+    const int nb1 = h->tab.n_buckets + 1;
+    const size_t want = joint_bytes(nb1, G);
+    *changed = 0;
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    if (!h->jx || h->jx_cap < want || h->jx_G != G) {
+        if (h->jx) h->jx_retired.push_back(h->jx);   // peers may still map it: freed with the handle
+        SCB_CUDA(cudaMalloc(&h->jx, want));
+        SCB_CUDA(cudaMemset(h->jx, 0, want));          // flags start below every epoch
+        h->jx_cap = want; h->jx_G = G;
+        *changed = 1;
+    }
+    *ptr = h->jx;
+}
+
+static void shard_resolve_joint(scb_handle *h, int rank, int G, void *const *peers, int64_t reads_before, int64_t n_rank0,
+                                const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *rounds_out) {
+    cudaStream_t st = h->st;
+    ArenaScope arena_scope(&h->arena);
+    const int64_t n = h->cur.n;
+    const int nb1 = h->tab.n_buckets + 1;
+    if (!h->jx || h->jx_G != G || peers[rank] != h->jx) throw CudaError{"joint rounds: scb_shard_joint_reserve first, and peers[rank] must be this rank's buffer"};
+    h->j_epoch += 0x10000u;   // every rank makes the same sequence of calls, so the epochs agree without communication
+    RdJoint j;
+    memset(&j, 0, sizeof j);
+    for (int g = 0; g < G; g++) j.peer[g] = (uint32_t *)peers[g];
+    j.rank = rank; j.G = G; j.RW = joint_row_words(nb1); j.epoch = h->j_epoch;
+    j.life = h->d_life.as<unsigned long long>();
+    j.reads_before = reads_before; j.n_rank0 = n_rank0;
+    j.timeout_ns = 10ull * 1000000000ull;
+    ShardTimer tm(h);
+    int rounds = 0;
+    if (rank == 0 || n == 0) {
+        DevBuf dstat(8, st);
+        SCB_CUDA(cudaMemsetAsync(dstat.p, 0, 8, st));
+        SCB_LAUNCH(joint_follow_k, 1, 256, 0, st, j, rank == 0 ? row0_dev : (const uint32_t *)nullptr, nb1, dstat.as<int>() + 1, dstat.as<int>());
+        int stat[2] = {0, 0};
+        SCB_CUDA(cudaMemcpyAsync(stat, dstat.p, 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        if (stat[0] != 0) throw CudaError{stat[0] == 2 ? "joint rounds: timed out waiting for another rank" : "joint rounds: round cap hit"};
+        rounds = stat[1];
+    } else {
+        shard_need_dense(h);
+        if ((h->life_total + (uint64_t)reads_before + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
+        const int P = (nb1 + 3) & ~3;
+        DevBuf cta_base((size_t)h->sh_grid * P * 4, st);
+        j.cta_base = cta_base.as<uint32_t>();
+        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40) + reads_before;
+        std::vector<int64_t> blk{0, n};
+        h->last_rounds = 0;
+        const int rc = dense_launch(h, 3, g0, blk, h->sh_tot.as<uint32_t>(), &j);
+        if (rc != 0) throw CudaError{rc == 2 ? "joint rounds: timed out waiting for another rank" : "resolve: round cap hit"};
+        rounds = h->last_rounds;
+    }
+    tm.stop();
+    if (rounds < 2) throw CudaError{"joint rounds: internal (fewer than two rounds)"};
+    h->last_rounds = rounds;
+    *rounds_out = rounds;
+    *rows_out = (const uint32_t *)h->jx + (size_t)((rounds - 1) & 1) * G * j.RW;   // every rank's row of the last round
+}
+
 static void shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
     cudaStream_t st = h->st;
     ArenaScope arena_scope(&h->arena);
@@ -1661,6 +1734,23 @@ int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t r
     SCB_CATCH
     return SCB_OK;
 }
+int scb_shard_joint_reserve(scb_handle *h, int32_t n_ranks, void **ptr, int32_t *changed) {
+    if (!ptr || !changed || n_ranks < 2 || n_ranks > scb::kJointMaxRanks) { scb::g_last_error = "bad argument (2..16 ranks)"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(1)
+    scb::shard_joint_reserve(h, n_ranks, ptr, changed);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_resolve_joint(scb_handle *h, int32_t rank, int32_t n_ranks, void *const *peers, int64_t reads_before, int64_t n_rank0,
+                            const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *row_words, int32_t *rounds_out) {
+    if (!peers || !rows_out || !row_words || !rounds_out || n_ranks < 2 || n_ranks > scb::kJointMaxRanks || rank < 0 || rank >= n_ranks ||
+        (rank == 0 && !row0_dev)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    SCB_SHARD_ENTER(1)
+    scb::shard_resolve_joint(h, rank, n_ranks, peers, reads_before, n_rank0, row0_dev, rows_out, rounds_out);
+    *row_words = scb::joint_row_words(h->tab.n_buckets + 1);
+    SCB_CATCH
+    return SCB_OK;
+}
 int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
     SCB_SHARD_ENTER(1)
     if (!h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_finalize"; return SCB_ESTATE; }
@@ -1874,6 +1964,8 @@ void scb_destroy(scb_handle *h) {
     for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+    if (h->jx) cudaFree(h->jx);
+    for (void *r : h->jx_retired) cudaFree(r);
     for (auto &r : h->rx) if (r) cudaFree(r);
     for (void *r : h->rx_retired) cudaFree(r);
     h->arena.destroy();

@@ -5,6 +5,7 @@ the outcome as pass / xfail, so that an unverified variant can neither turn the 
 context, nor hang it. Run it directly with
     SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q
 
+  SCB_SHARD_JOINT_KERNEL=1 all joint tie-break rounds inside one kernel per rank, histograms exchanged through peer memory
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
@@ -130,3 +131,19 @@ def test_emit_reads_v2_odd_row_words_and_long_reads(monkeypatch):
         o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
         t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
         util.assert_same(o, t, r)
+
+
+# ---- joint tie-break rounds inside one kernel per rank (SCB_SHARD_JOINT_KERNEL=1): needs one PROCESS per GPU ----------------
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_joint_kernel_over_nvlink(world):
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(root, "tests", "sharded_nccl_worker.py"), "120000", "100", str(1 << 21)]
+    env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1")
+    r = subprocess.run(cmd, cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_NCCL_OK" in r.stdout, r.stdout[-4000:]

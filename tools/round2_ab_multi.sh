@@ -1,5 +1,6 @@
 #!/bin/bash
-# The sharded run's opt-in switch at N GPUs (gpurun --gpus N): default vs early emit.
+# The sharded run's opt-in switches at N GPUs (gpurun --gpus N): default, early emit, in-kernel joint rounds, both.
+# (parity of the joint kernel first: SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q -k joint_kernel)
 # Usage:  gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_ab_multi.sh 8'
 N=${1:-2}
 mkdir -p gpurun_out/ab
@@ -11,4 +12,6 @@ run() {
 }
 run default
 run early_emit SCB_SHARD_EARLY_EMIT=1
+run joint_kernel SCB_SHARD_JOINT_KERNEL=1
+run joint_early SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1
 python tools/ab_summary.py gpurun_out/ab n${N}_
