@@ -592,9 +592,9 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
-    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false>, W * 32, smem));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, false>, W * 32, smem));
     if (occ < 1) return false;
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
@@ -648,11 +648,14 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
     if (joint) rp.j = *joint; else memset(&rp.j, 0, sizeof rp.j);
     void *args[] = {&rp};
-    if (mode == 3) {   // all joint rounds of the sharded run in this launch (resolve_dense.cuh, JOINT)
-        SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k<true>, dim3(grid), dim3(W * 32), args, smem, st));
-    } else
-    SCB_CUDA(cudaLaunchCooperativeKernel((void *)resolve_dense_k<false>, dim3(grid), dim3(W * 32), args, smem, st));
+    // opt-in (not yet measured): the guess round of every block as a streaming pass (resolve_dense.cuh, CHEAP)
+    const char *cg = getenv("SCB_RESOLVE_CHEAP_GUESS");
+    const bool cheap = cg && atoi(cg) != 0;
+    void *kfn = (void *)resolve_dense_k<false, false>;
+    if (mode == 3) kfn = cheap ? (void *)resolve_dense_k<true, true> : (void *)resolve_dense_k<true, false>;   // all joint rounds in this launch (JOINT)
+    else if (cheap) kfn = (void *)resolve_dense_k<false, true>;
+    if (kfn != (void *)resolve_dense_k<false, false>) SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
     if (mode != 0 && mode != 3) {
         h->last_rounds++;

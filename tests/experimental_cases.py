@@ -10,6 +10,7 @@ context, nor hang it. Run it directly with
   SCB_SCAN_V2=1            scan kernel with pick + emit merged into one pass over the hits (scan_smem2.cuh)
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
   SCB_EMIT_READS_V2=1      stream-1 writer with 8-byte row staging and branch-free record assembly (emit_reads_fast.cuh)
+  SCB_RESOLVE_CHEAP_GUESS=1 the guess round of every tie-break block as a streaming pass (no sequential sweep)
   SCB_OVERLAP_CHUNKS=1     size prefix sum + flush-chunk boundaries on a side stream under the tie-break kernel
   SCB_EMIT_FUSED_SCAN=1    metadata gather + the three offset scans of the emit stage in 3 launches (emit_offsets.cuh)
 
@@ -50,7 +51,7 @@ def test_early_emit_four_ranks(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -87,7 +88,7 @@ def test_scan_v2_million_reads(monkeypatch):
 
 
 def test_all_single_gpu_variants_together_million_reads(monkeypatch):
-    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS"):
+    for var in ("SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_CORESIDENT", "SCB_EMIT_READS_V2", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS"):
         monkeypatch.setenv(var, "1")
     cores, b, q1, q2, _ = util.make_case(1000000, 150, seed=173, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)],
                                          paired=True, L2=100)
@@ -147,3 +148,27 @@ def test_joint_kernel_over_nvlink(world):
     env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1")
     r = subprocess.run(cmd, cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_NCCL_OK" in r.stdout, r.stdout[-4000:]
+
+
+def test_cheap_guess_round_sharded_and_tied(monkeypatch):
+    # the streaming guess round in the sharded run's first joint round, and on inputs where almost every read is tied
+    monkeypatch.setenv("SCB_RESOLVE_CHEAP_GUESS", "1")
+    _sharded(40000, 100, 4, seed=201, bucket_set_bytes=1 << 20)
+    _sharded(9000, 64, 4, seed=202, bounds=[0, 0, 5000, 5000, 9000])
+    import itertools
+    from scalce_b200 import synth
+    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]
+    b = synth.make_batch(20000, 80, seed=203)
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, None)
+    t, r = util.run_cuda(cores, b, q1, None)
+    util.assert_same(o, t, r)
+
+
+def test_cheap_guess_round_million_reads_second_flush(monkeypatch):
+    # two flushes on one handle: the second starts from large lifetime populations (g0 > 0 in the extrapolation)
+    monkeypatch.setenv("SCB_RESOLVE_CHEAP_GUESS", "1")
+    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=204, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2, splits=[600000])
+    t, r = util.run_cuda(cores, b, q1, q2, splits=[600000])
+    util.assert_same(o, t, r)

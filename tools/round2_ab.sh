@@ -19,10 +19,11 @@ run coresident SCB_EMIT_CORESIDENT=1
 run scan_v2 SCB_SCAN_V2=1
 run reads_v2 SCB_EMIT_READS_V2=1
 run overlap_chunks SCB_OVERLAP_CHUNKS=1
+run cheap_guess SCB_RESOLVE_CHEAP_GUESS=1
 # block schedule of the tie-break (tools/sim_resolve.c: x4 growth up to 4M / 16M reads -> 105 / 99 rounds instead of 111, larger blocks)
 run resolve_small_4M SCB_RESOLVE_SMALL=4194304
 run resolve_small_16M SCB_RESOLVE_SMALL=16777216
 run cores_reads_v2 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1
-run all_on SCB_EMIT_FUSED_SCAN=1 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1 SCB_SCAN_V2=1 SCB_OVERLAP_CHUNKS=1
+run all_on SCB_EMIT_FUSED_SCAN=1 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1 SCB_SCAN_V2=1 SCB_OVERLAP_CHUNKS=1 SCB_RESOLVE_CHEAP_GUESS=1
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-depth 2 > gpurun_out/ab/e2e_depth2.json 2> gpurun_out/ab/e2e_depth2.err
 python tools/ab_summary.py gpurun_out/ab

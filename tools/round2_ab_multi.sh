@@ -14,4 +14,6 @@ run default
 run early_emit SCB_SHARD_EARLY_EMIT=1
 run joint_kernel SCB_SHARD_JOINT_KERNEL=1
 run joint_early SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1
+run cheap_guess SCB_RESOLVE_CHEAP_GUESS=1
+run all_on SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1 SCB_RESOLVE_CHEAP_GUESS=1
 python tools/ab_summary.py gpurun_out/ab n${N}_

@@ -59,6 +59,22 @@ static void gen(Reads *R, int64_t n, uint64_t seed) {
     }
 }
 
+// SIM_CHEAP_FIRST=1: the guess round decides every read INDEPENDENTLY from its subtile's (extrapolated) start counts - a
+// data-parallel pass instead of a sequential sweep; hist[] receives the subtile's histogram under those decisions
+static int64_t sweep_static(Reads *R, int64_t lo, int64_t hi, const uint32_t *cnt, uint32_t *hist) {
+    int64_t ch = 0;
+    for (int64_t i = lo; i < hi; i++) {
+        const int nc = R->nc[i];
+        if (!nc) continue;
+        const uint16_t *c = R->c + i * MAXC;
+        int best = 0; uint32_t bc = cnt[c[0]];
+        for (int k = 1; k < nc; k++) if (cnt[c[k]] > bc) { bc = cnt[c[k]]; best = k; }
+        hist[c[best]]++;
+        if (R->sel[i] != best) { R->sel[i] = (uint8_t)best; ch++; }
+    }
+    return ch;
+}
+
 // one sweep of reads [lo, hi) from counts cnt[] (modified); returns the number of decisions that changed
 static int64_t sweep(Reads *R, int64_t lo, int64_t hi, uint32_t *cnt) {
     int64_t ch = 0;
@@ -89,11 +105,19 @@ static int64_t round_block(Reads *R, int64_t n0, int64_t n1, const uint32_t *bas
         for (int b = 0; b < NB; b++) { uint32_t run = base[b]; for (int t = 0; t < ns; t++) { start[(size_t)t * NB + b] = run; run += H[(size_t)t * NB + b]; } }
     }
     int64_t changed = 0;
+    const int cheap_first = getenv("SIM_CHEAP_FIRST") != NULL;
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : changed)
     for (int t = 0; t < ns; t++) {
         uint32_t cnt[NB];
         memcpy(cnt, start + (size_t)t * NB, sizeof cnt);
         const int64_t lo = n0 + t * ts, hi = lo + ts < n1 ? lo + ts : n1;
+        if (first && cheap_first) {
+            uint32_t hh[NB];
+            memset(hh, 0, sizeof hh);
+            changed += sweep_static(R, lo, hi, cnt, hh);
+            memcpy(H + (size_t)t * NB, hh, sizeof hh);
+            continue;
+        }
         changed += sweep(R, lo, hi, cnt);
         for (int b = 0; b < NB; b++) H[(size_t)t * NB + b] = cnt[b] - start[(size_t)t * NB + b];
     }
