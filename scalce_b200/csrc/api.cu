@@ -1181,7 +1181,8 @@ static void shard_joint_reserve(scb_handle *h, int G, void **ptr, int32_t *chang
     if (!h->jx || h->jx_cap < want || h->jx_G != G) {
         if (h->jx) h->jx_retired.push_back(h->jx);   // peers may still map it: freed with the handle
         SCB_CUDA(cudaMalloc(&h->jx, want));
-        SCB_CUDA(cudaMemset(h->jx, 0, want));          // flags start below every epoch
+        SCB_CUDA(cudaMemsetAsync(h->jx, 0, want, h->st));   // flags start below every epoch ...
+        SCB_CUDA(cudaStreamSynchronize(h->st));             // ... and the zeros are there before any peer can write (the caller's barrier follows)
         h->jx_cap = want; h->jx_G = G;
         *changed = 1;
     }
