@@ -25,5 +25,8 @@ run resolve_small_4M SCB_RESOLVE_SMALL=4194304
 run resolve_small_16M SCB_RESOLVE_SMALL=16777216
 run cores_reads_v2 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1
 run all_on SCB_EMIT_FUSED_SCAN=1 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1 SCB_SCAN_V2=1 SCB_OVERLAP_CHUNKS=1 SCB_RESOLVE_CHEAP_GUESS=1
+# per-round phase times of the tie-break kernel (P / D / E / sync / scan per round, to stderr): what a round's fixed cost consists of
+SCB_RESOLVE_PROF=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ab/resolve_prof.json 2> gpurun_out/ab/resolve_prof.err
+grep "resolve totals\|resolve subtile" gpurun_out/ab/resolve_prof.err | tail -4
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-depth 2 > gpurun_out/ab/e2e_depth2.json 2> gpurun_out/ab/e2e_depth2.err
 python tools/ab_summary.py gpurun_out/ab
