@@ -21,7 +21,7 @@
 
 #define NB 2048
 #define MAXC 6
-#define SUB 1776
+static int SUB = 1776;   // subtiles per block (148 CTAs x 12 warps); SIM_SUB overrides
 
 static uint64_t rs;
 static inline uint64_t rnd(uint64_t *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return *s; }
@@ -194,6 +194,7 @@ static int overlapped(Reads *R, uint32_t *base, int64_t thr) {
 }
 
 int main(int argc, char **argv) {
+    if (getenv("SIM_SUB")) SUB = atoi(getenv("SIM_SUB"));
     if (argc >= 4 && !strcmp(argv[1], "overlap")) {
         Reads R; gen(&R, atoll(argv[2]), 1);
         uint32_t base[NB] = {0};
