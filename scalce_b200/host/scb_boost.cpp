@@ -7,8 +7,11 @@
 //   quality payload  qualities.cpp:177-204 (q - offset, 0 under an 'N' base; lossy percentage 0)
 //   search/bucket    compress.cpp:673-706  -> scb_submit per batch of reads
 //   flush            compress.cpp:524-552, 708-715, 799-801 -> scb_flush, chunk c stream k -> t_%03d_<k>.tmp
+//   container        compress.cpp:262-379 (combine_and_compress_with_split in raw mode, -c no -A): the merged streams
+//                    -> PREFIX_<mate>.scalce{n,r,q}   (--container PREFIX; no entropy coding here - that stays the host's)
 //
 // It links libscalce_b200.so only; there is no CPU path for the transform (scb_create fails without a B200).
+// --assemble DIR reads merged_<k>.tmp from DIR instead of running the transform and only writes the container (no GPU).
 // --dump-soa DIR stops after the host stages and writes the batch arrays (what scb_submit would get): that mode
 // needs no GPU and is what the CPU tests check (tests/test_host_cpu.py).
 #include <cerrno>
@@ -28,6 +31,7 @@ namespace {
     exit(1);
 }
 void scb_check(int rc) { if (rc) die(scb_last_error()); }
+void write_file(const std::string &path, const void *p, size_t bytes);
 
 struct LineReader {   // plain-text FASTQ; lines without the terminator
     FILE *f = nullptr;
@@ -75,6 +79,69 @@ Sample sample_file(const char *path, int lines) {
     return s;
 }
 
+std::vector<uint8_t> read_file(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) die("cannot open " + path + ": " + strerror(errno));
+    std::vector<uint8_t> v;
+    uint8_t buf[1 << 16];
+    size_t r;
+    while ((r = fread(buf, 1, sizeof buf, f)) > 0) v.insert(v.end(), buf, buf + r);
+    fclose(f);
+    return v;
+}
+
+template <typename T> void put(std::vector<uint8_t> &o, T v) { const uint8_t *p = (const uint8_t *)&v; o.insert(o.end(), p, p + sizeof(T)); }
+
+// combine_and_compress_with_split, compress.cpp:262-379, raw mode (_no_ac = 1, IO_SYS): per mate three files.
+//   .scalcen  magic, use_names byte, [name index 0 + library name when names are off], then the name records
+//   .scalcer  magic, int32 no_ac, int32 read length, then per bucket [mate 1 only: int32 core, int64 reads] + its packed reads
+//   .scalceq  magic, int64 phred offset, then the quality bytes
+// streams: the merged (bucket-order) streams 0..5; meta records: int32 id, int32 core, int64 lN, lR, lQ [, lR2, lQ2].
+// core_len(core) = length of core `core` (patterns[core], compress.cpp:373); the root bucket has core = MAXBIN - 1.
+template <typename CoreLen>
+void write_containers(const std::string &prefix, const std::vector<uint8_t> *streams, CoreLen core_len, int L1, int L2, bool paired, bool use_names,
+                      int64_t phred_offset, const std::string &library) {
+    static const uint8_t magic[8] = {'s', 'c', 'a', 'l', 'c', 'e', '2', '2'};
+    const int nlen = 3 + 2 * (paired ? 1 : 0);
+    const size_t rsz = 8 + 8 * (size_t)nlen;
+    const int sz_meta = L1 > 255 ? 2 : 1;
+    const std::vector<uint8_t> &meta = streams[3];
+    if (meta.size() % rsz) die("meta stream is not a whole number of records");
+    for (int mate = 0; mate < (paired ? 2 : 1); mate++) {
+        std::vector<uint8_t> fn(magic, magic + 8), fr(magic, magic + 8), fq(magic, magic + 8);
+        fn.push_back(use_names ? 1 : 0);
+        if (!use_names) { put<int64_t>(fn, 0); fn.insert(fn.end(), library.begin(), library.end()); }
+        put<int32_t>(fr, 1);                                   // _no_ac
+        put<int32_t>(fr, mate ? L2 : L1);
+        put<int64_t>(fq, phred_offset);
+        const std::vector<uint8_t> &sr = streams[mate ? 4 : 1], &sq = streams[mate ? 5 : 2], &sn = streams[0];
+        size_t pn = 0, pr = 0, pq = 0;
+        for (size_t o = 0; o < meta.size(); o += rsz) {
+            int32_t core;
+            int64_t len[5] = {0, 0, 0, 0, 0};
+            memcpy(&core, &meta[o + 4], 4);
+            memcpy(len, &meta[o + 8], 8 * (size_t)nlen);
+            const int64_t lN = len[0];
+            int64_t lR = len[1], lQ = len[2];
+            if (mate) { lR = len[3]; lQ = len[4]; }
+            else {
+                const int clen = core == (1 << 30) - 1 ? 0 : core_len(core);
+                const int64_t per = (((L1 - clen) >> 2) + (((L1 - clen) & 3) != 0)) + sz_meta;
+                put<int32_t>(fr, core);
+                put<int64_t>(fr, lR / per);
+            }
+            if (pr + (size_t)lR > sr.size() || pq + (size_t)lQ > sq.size() || (use_names && pn + (size_t)lN > sn.size())) die("meta records run past the streams");
+            fr.insert(fr.end(), sr.begin() + pr, sr.begin() + pr + lR); pr += (size_t)lR;
+            fq.insert(fq.end(), sq.begin() + pq, sq.begin() + pq + lQ); pq += (size_t)lQ;
+            if (use_names) { fn.insert(fn.end(), sn.begin() + pn, sn.begin() + pn + lN); pn += (size_t)lN; }
+        }
+        const std::string m = std::to_string(mate + 1);
+        write_file(prefix + "_" + m + ".scalcen", fn.data(), fn.size());
+        write_file(prefix + "_" + m + ".scalcer", fr.data(), fr.size());
+        write_file(prefix + "_" + m + ".scalceq", fq.data(), fq.size());
+    }
+}
+
 void write_file(const std::string &path, const void *p, size_t bytes) {
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) die("cannot write " + path + ": " + strerror(errno));
@@ -85,7 +152,9 @@ void write_file(const std::string &path, const void *p, size_t bytes) {
 }  // namespace
 
 int main(int argc, char **argv) {
-    const char *in1 = nullptr, *in2 = nullptr, *cores = nullptr, *out = nullptr, *dump = nullptr;
+    const char *in1 = nullptr, *in2 = nullptr, *cores = nullptr, *out = nullptr, *dump = nullptr, *container = nullptr, *assemble = nullptr;
+    std::string library;
+    int asm_L1 = 0, asm_L2 = 0, asm_paired = 0; long long asm_offset = 33;
     uint64_t bucket_set = 4ull << 30;   // -B, main.cpp default
     int use_names = 1, use_quals = 1, merged = 0, device = 0, sample_lines = 100000;
     int64_t batch_reads = 4 << 20;
@@ -102,11 +171,32 @@ int main(int argc, char **argv) {
         else if (a == "--device") device = atoi(need("--device"));
         else if (a == "--batch") batch_reads = atoll(need("--batch"));
         else if (a == "--dump-soa") dump = need("--dump-soa");
+        else if (a == "--container") container = need("--container");
+        else if (a == "--library") library = need("--library");
+        else if (a == "--assemble") assemble = need("--assemble");
+        else if (a == "--L1") asm_L1 = atoi(need("--L1"));
+        else if (a == "--L2") { asm_L2 = atoi(need("--L2")); asm_paired = 1; }
+        else if (a == "--offset") asm_offset = atoll(need("--offset"));
         else if (a[0] == '-') die("unknown option " + a);
         else if (!in1) in1 = argv[i];
         else die("more than one input file (use -r for mate 2)");
     }
-    if (!in1 || (!out && !dump) || (!cores && !dump))
+    if (assemble) {   // container assembly alone, from merged_<k>.tmp in a directory (no GPU): scb_boost --assemble DIR --container PREFIX -P cores.txt --L1 n [--L2 n] [-n] [--offset o]
+        if (!container || !cores || asm_L1 <= 0) die("--assemble needs --container PREFIX, -P cores.txt and --L1");
+        std::vector<std::string> cv;
+        {
+            LineReader cr(cores);
+            std::string ln;
+            while (cr.next(ln)) if (!ln.empty()) cv.push_back(ln);
+        }
+        std::vector<uint8_t> st[6];
+        for (int k = 0; k < 4 + 2 * asm_paired; k++) st[k] = read_file(std::string(assemble) + "/merged_" + std::to_string(k) + ".tmp");
+        write_containers(container, st, [&](int32_t c) { if (c < 0 || (size_t)c >= cv.size()) die("core index out of range"); return (int)cv[(size_t)c].size(); },
+                         asm_L1, asm_L2, asm_paired != 0, use_names != 0, asm_offset, library);
+        return 0;
+    }
+    if (container) merged = 1;
+    if (!in1 || (!out && !dump && !container) || (!cores && !dump))
         die("usage: scb_boost in_1.fastq [-r in_2.fastq] -P cores.txt -o out_dir [-B bytes] [-n] [--no-quals] [--merged] [--batch reads] [--device d] | --dump-soa dir");
     if (batch_reads < 1) die("--batch must be positive");
 
@@ -212,7 +302,7 @@ int main(int argc, char **argv) {
     const int nf = 4 + 2 * (in2 ? 1 : 0);
     std::vector<uint8_t> buf;
     char path[4096];
-    for (int c = 0; c < res.n_chunks; c++)
+    for (int c = 0; out && c < res.n_chunks; c++)
         for (int k = 0; k < nf; k++) {
             const int64_t bytes = res.chunk_off[k][c + 1] - res.chunk_off[k][c];
             buf.resize(bytes > 0 ? (size_t)bytes : 1);
@@ -220,7 +310,7 @@ int main(int argc, char **argv) {
             snprintf(path, sizeof path, "%s/t_%03d_%d.tmp", out, c, k);
             write_file(path, buf.data(), (size_t)bytes);
         }
-    if (merged)   // what merge() leaves (compress.cpp:68-198): one set of streams in bucket order
+    if (merged && out)   // what merge() leaves (compress.cpp:68-198): one set of streams in bucket order
         for (int k = 0; k < nf; k++) {
             const int64_t bytes = res.merged_size[k];
             buf.resize(bytes > 0 ? (size_t)bytes : 1);
@@ -228,6 +318,15 @@ int main(int argc, char **argv) {
             snprintf(path, sizeof path, "%s/merged_%d.tmp", out, k);
             write_file(path, buf.data(), (size_t)bytes);
         }
+    if (container) {
+        std::vector<uint8_t> st[6];
+        for (int k = 0; k < nf; k++) {
+            st[k].resize(res.merged_size[k] > 0 ? (size_t)res.merged_size[k] : 0);
+            scb_check(scb_copy_stream(h, k, -1, st[k].empty() ? (void *)&st[k] : (void *)st[k].data(), res.merged_size[k]));
+        }
+        write_containers(container, st, [&](int32_t c) { const char *cs = scb_core(h, c); if (!cs) die("core index out of range"); return (int)strlen(cs); },
+                         L1, L2, in2 != nullptr, use_names != 0, s1.offset, library);
+    }
     fprintf(stderr, "scb_boost: %lld reads, L %d%s, phred offset %d, %d flush chunk(s), %lld unbucketed, device %.3f ms\n", (long long)n_total, L1,
             in2 ? (" + " + std::to_string(L2)).c_str() : "", s1.offset, res.n_chunks, (long long)scb_unbucketed(h), res.device_ms);
     scb_destroy(h);

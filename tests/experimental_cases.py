@@ -172,3 +172,32 @@ def test_cheap_guess_round_million_reads_second_flush(monkeypatch):
     o = util.run_oracle(cores, b, q1, q2, splits=[600000])
     t, r = util.run_cuda(cores, b, q1, q2, splits=[600000])
     util.assert_same(o, t, r)
+
+
+def test_host_tool_fastq_to_container_matches_reference_golden(tmp_path):
+    """FASTQ -> scb_boost --container (C++ host stages + the CUDA transform + container assembly) == the files the unmodified
+    reference CLI wrote (tests/golden), for every fixture."""
+    import glob
+    import hashlib
+    import subprocess
+    from scalce_b200 import build as bld, synth
+    from tests import test_oracle_golden as tg
+    tool = bld.build_host_tool()
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))):
+        z, meta = tg._load(path)
+        cores, b = tg._inputs(z, meta)
+        d = tmp_path / os.path.basename(path)[:-4]
+        d.mkdir()
+        f1, f2 = str(d / "in_1.fastq"), str(d / "in_2.fastq")
+        synth.write_fastq(b, f1, f2 if meta["paired"] else None)
+        (d / "cores.txt").write_text("\n".join(cores) + "\n")
+        bucket = {"4G": 4 << 30, "1M": 1 << 20}[meta["bucket"]]
+        cmd = [tool, f1] + (["-r", f2] if meta["paired"] else []) + ["-P", str(d / "cores.txt"), "-B", str(bucket), "--container", str(d / "out"),
+                                                                       "--library", "lib"] + ([] if meta["use_names"] else ["-n"])
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        for mate in range(1 + int(meta["paired"])):
+            for ext in "nrq":
+                k = f"{mate + 1}{ext}"
+                data = (d / f"out_{mate + 1}.scalce{ext}").read_bytes()
+                assert hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{os.path.basename(path)} {k}: differs from the reference CLI output"

@@ -172,3 +172,31 @@ def test_cpp_host_stage_plus_oracle_matches_reference_cli(path, oracle_lib, tmp_
         for ext, data in (("n", fn), ("r", fr), ("q", fq)):
             k = f"{mate + 1}{ext}"
             assert hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{k}: bytes differ from the reference CLI output"
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_cpp_container_assembly_matches_reference_cli(path, oracle_lib, tmp_path):
+    """The other host stage of the drop-in, after the transform: scb_boost --assemble writes .scalce{n,r,q} from the merged
+    streams as combine_and_compress_with_split does in raw mode (compress.cpp:262-379). Fed with the oracle's streams it must
+    reproduce the files of the unmodified reference CLI. No GPU involved."""
+    import subprocess
+    from scalce_b200 import build as bld
+    z, meta = _load(path)
+    cores, b = _inputs(z, meta)
+    o, _ = oracle_files(cores, b, meta)
+    tool = bld.build_host_tool()
+    d = tmp_path / "streams"
+    d.mkdir()
+    for k in range(6 if meta["paired"] else 4):
+        (d / f"merged_{k}.tmp").write_bytes(o.stream(k))
+    (tmp_path / "cores.txt").write_text("\n".join(cores) + "\n")
+    off = orc.detect_phred_offset(b.qual)
+    cmd = [tool, "--assemble", str(d), "--container", str(tmp_path / "out"), "-P", str(tmp_path / "cores.txt"), "--L1", str(meta["L"]),
+           "--offset", str(off), "--library", "lib"] + (["--L2", str(meta["L2"])] if meta["paired"] else []) + ([] if meta["use_names"] else ["-n"])
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    for mate in range(1 + int(meta["paired"])):
+        for ext in "nrq":
+            k = f"{mate + 1}{ext}"
+            data = (tmp_path / f"out_{mate + 1}.scalce{ext}").read_bytes()
+            assert len(data) == meta["sizes"][k] and hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{k}: differs from the reference CLI output"
