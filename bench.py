@@ -78,6 +78,13 @@ class ClockSampler:
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # both calls of a sample must work here, otherwise nvidia-smi does the sampling
+            self._reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            try:
+                self._reasons(self.h)
+            except Exception:
+                self._reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                self._reasons(self.h)
             self.nvml = pynvml
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
@@ -97,11 +104,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((mhz, rs))
+                self.samples.append((mhz, int(self._reasons(self.h))))
             except Exception:
                 pass
             time.sleep(0.01)
