@@ -231,6 +231,7 @@ int main(int argc, char **argv) {
             if (g == 1 || g == G - 1) printf("  pre-round %d rank %d: %ld changed\n", k, g, (long)ch);
         }
     int rounds = 0, first = pre == 0;
+    const int gs = getenv("SIM_GS") != NULL;
     for (;;) {
         uint32_t (*nh)[NB] = calloc(G, sizeof *nh);
         int64_t changed = 0;
@@ -238,7 +239,7 @@ int main(int argc, char **argv) {
             uint32_t base[NB];
             for (int b = 0; b < NB; b++) {
                 if (first) base[b] = (uint32_t)((uint64_t)hist[0][b] * (uint64_t)g);           // rank 0's histogram scaled (exact for rank 1)
-                else { uint32_t s = 0; for (int q = 0; q < g; q++) s += hist[q][b]; base[b] = s; }
+                else { uint32_t s = 0; for (int q = 0; q < g; q++) s += (gs && q >= 1) ? nh[q][b] : hist[q][b]; base[b] = s; }   // SIM_GS: Gauss-Seidel across ranks
             }
             changed += round_block(&R[g], 0, n, base, H[g], first, (int64_t)g * n, nh[g]);
         }
