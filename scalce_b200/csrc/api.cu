@@ -951,7 +951,7 @@ static void stage_sort(scb_handle *h) {
                     SCB_LAUNCH(tie_small_groups_k, (unsigned)cdiv((int64_t)G * 32, 256), 256, 0, st, h->packed.as<uint32_t>(), h->PW, L1, h->endv.as<uint16_t>(),
                                gstart.as<uint32_t>(), G, c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), consumed, h->perm.as<uint32_t>(), big.as<uint8_t>(),
                                mid_list.as<uint32_t>(), mid_count.as<uint32_t>(), (uint32_t)kTieMidMax);
-                    SCB_LAUNCH(tie_mid_groups_k, 148 * 4, 256, 0, st, h->packed.as<uint32_t>(), h->PW, L1, h->endv.as<uint16_t>(), gstart.as<uint32_t>(),
+                    SCB_LAUNCH(tie_mid_groups_k, 148 * 8, 256, 0, st,   /* grid-stride over the queued groups; 8 CTAs of 256 threads fit an SM (16 KB static smem, 48 registers) */ h->packed.as<uint32_t>(), h->PW, L1, h->endv.as<uint16_t>(), gstart.as<uint32_t>(),
                                mid_list.as<uint32_t>(), mid_count.as<uint32_t>(), c_pos.as<uint32_t>(), c_idx.as<uint32_t>(), consumed, h->perm.as<uint32_t>());
                     exclusive_scan<uint32_t>(LoadAs<uint8_t, uint32_t>{big.as<uint8_t>()}, t, bpos.as<uint32_t>(), bpos.as<uint32_t>() + t, w32b.as<uint32_t>(), st);
                     uint32_t t2 = 0;
