@@ -522,10 +522,12 @@ def main():
     }
     ach = N * stage_bytes.get(dom, 0) / (mean_st[dom] * 1e-3) / 1e9
     # DRAM bytes per read of each stage's kernels (dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list of this
-    # workload: profiles/r01_launches_summary.txt); only valid for the headline shape
+    # workload: profiles/r01_launches_summary.txt, taken before the 5-pass sort, scan_smem2_k, emit_reads_fast_k and the fused offset
+    # scans became the defaults - an upper bound for "sort" and "emit" now); only valid for the headline shape
     ncu_traffic_per_read = {"emit": 732, "resolve": 100, "scan": 212, "sort": 226, "ties": 22, "chunks": 28, "arrays": 22}
-    stage_kernels = {"emit": "gather_rows16_k + emit_reads_st_k + emit_names_st_k + gather_meta_k + offset scans", "resolve": "resolve_dense_k + resolve_finalize_k",
-                     "scan": "scan_smem_k", "sort": "build_keys_pk_k + 5 x (sort_hist_k, sort_scatter_k)", "exchange_rows": "gather_rows16_to_k (peer stores)"}
+    stage_kernels = {"emit": "gather_rows16_k + emit_reads_fast_k + emit_names_st_k + emit_off_reduce_k / emit_off_apply_k (metadata gather + offset scans)",
+                     "resolve": "resolve_dense_k + resolve_finalize_k", "scan": "scan_smem2_k", "sort": "build_keys_pk_k + 5 x (sort_hist_k, sort_scatter_k)",
+                     "exchange_rows": "gather_rows16_to_k (peer stores)"}
     traffic = float(ncu_traffic_per_read[dom]) * N if (L == 150 and world == 1 and dom in ncu_traffic_per_read) else None
     # every stage's own figure beside the dominant one (same definition: algorithmic bytes of the stage / its device time)
     per_stage = {k: {"ms": v, "bytes_per_read": stage_bytes.get(k), "achieved_gbs": (N * stage_bytes[k] / (v * 1e-3) / 1e9) if (v > 0 and stage_bytes.get(k)) else None}

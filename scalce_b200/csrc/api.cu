@@ -94,6 +94,12 @@ struct DevBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
+// kernel variants that became the default after an A/B run keep their switch: unset = on, "0" = the previous kernel
+static bool env_on(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) != 0 : dflt;
+}
+
 static int ceil_log2(uint64_t x) {  // bits needed to represent values in [0, x)
     int b = 0;
     while (b < 64 && (1ull << b) < x) b++;
@@ -347,10 +353,9 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     DevBuf ms((size_t)n * 8, st), offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st);
     KeyHead kh{keys, seg_shift, seg_bits};
     uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
-    const char *fs_env = getenv("SCB_EMIT_FUSED_SCAN");
-    const bool fused_scan = fs_env && atoi(fs_env) != 0;
+    const bool fused_scan = env_on("SCB_EMIT_FUSED_SCAN", true);
     if (fused_scan) {
-        // opt-in (not yet measured on a B200): metadata gather + the three prefix sums in 3 launches (emit_offsets.cuh)
+        // metadata gather + the three prefix sums in 3 launches (emit_offsets.cuh): emit 10.62 -> 10.26 ms at 50M x 150; "0" = the generic scans
         const int64_t nt = scan_tiles(n);
         DevBuf ts((size_t)3 * nt * 8, st), tot3(32, st);
         SCB_LAUNCH(emit_off_reduce_k, (unsigned)nt, kScanThreads, 0, st, h->meta_in.as<uint64_t>(), perm, kh, n, L1, sz_meta, (int)cfg.use_names,
@@ -415,8 +420,11 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         const int RPB = std::max(1, std::min(256, (40 * 1024) / per_read));
         const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
         const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
-        const char *rv2 = getenv("SCB_EMIT_READS_V2");   // opt-in (not yet measured): emit_reads_fast.cuh
-        if (rv2 && atoi(rv2) != 0) {
+        // emit_reads_fast.cuh: emit 10.62 -> 10.25 ms at 50M x 150. Rows of one or two words (reads of <= 32 bases) stay with
+        // emit_reads_st_k: that shape of the new kernel has not run on a GPU since its index fix. "0" = emit_reads_st_k
+        const char *rv2 = getenv("SCB_EMIT_READS_V2");
+        const int rv2_mode = rv2 && *rv2 ? atoi(rv2) : 1;            // 2 = also for one- and two-word rows (to test that shape)
+        if (rv2_mode != 0 && (h->PW >= 3 || rv2_mode >= 2)) {
             const uint32_t half = (uint32_t)((h->PW & 1) == 0 && (((uintptr_t)h->packed.p) & 7) == 0 ? h->PW / 2 : h->PW);
             const uint32_t inv_half = (uint32_t)(((1ull << 32) + half - 1) / half);
             const int64_t n_blk = cdiv(n, RPB);
@@ -528,8 +536,7 @@ static void stage_scan(scb_handle *h) {
         const int R = W * 32;
         if (W >= 2 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
             const size_t smem = scan_smem_total(h->tab.n_states, h->n_hit, nb, W, L1, PW);
-            const char *v2e = getenv("SCB_SCAN_V2");      // opt-in variant: pick + emit merged (scan_smem2.cuh), not yet measured
-            const bool scan_v2 = v2e && atoi(v2e) != 0;
+            const bool scan_v2 = env_on("SCB_SCAN_V2", true);   // pick + emit merged (scan_smem2.cuh): 8.07 -> 7.63 ms at 50M x 150; "0" = scan_smem_k
             SCB_CUDA(cudaFuncSetAttribute(scan_v2 ? scan_smem2_k : scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));

@@ -1,4 +1,5 @@
-// emit_offsets.cuh - the output side's three prefix sums in one pass (opt-in: SCB_EMIT_FUSED_SCAN=1).
+// emit_offsets.cuh - the output side's three prefix sums in one pass (default since the end of round 1: -0.36 ms at
+// 50M x 150 bp; SCB_EMIT_FUSED_SCAN=0 selects the generic scans).
 //
 // emit_order (api.cu) needs, per emitted read p: the segment number (running count of (chunk, bucket) heads), the
 // byte offset of its name record in stream 0 (names.cpp:48-62: length byte + name) and of its read record in

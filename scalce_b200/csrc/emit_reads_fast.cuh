@@ -1,5 +1,6 @@
 // emit_reads_fast.cuh - stream 1 (rotated 2-bit reads + end marker) with fewer instructions per read
-// (opt-in: SCB_EMIT_READS_V2=1; written without GPU access, not yet measured).
+// (default for reads of more than 32 bases since the end of round 1: 2.3 -> 1.9 ms at 50M x 150 bp; SCB_EMIT_READS_V2=0
+// selects emit_reads_st_k).
 //
 // ncu on emit_reads_st_k (gpurun_out/r01_top.raw.csv): issue bound - 83 % issue active, 44 warp instructions per read.
 // SASS: the row staging moves 4 bytes per ~21 instructions (13 items per read), and the record loop spends ~100
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) emit_reads_fast_k(EmitMParams e, int RPB,
         {   // rows: fetched once per read; the pad words are zeroed by the read's own thread below
             const uint32_t items = (uint32_t)np * half;
             for (uint32_t t = threadIdx.x; t < items; t += 256) {
-                const uint32_t pl = __umulhi(t, inv_half), k = t - pl * half;
+                const uint32_t pl = half == 1 ? t : __umulhi(t, inv_half), k = t - pl * half;   // ceil(2^32 / 1) does not fit 32 bits
                 const uint32_t *src = e.packed + (int64_t)e.perm[p0 + pl] * PW;
                 uint32_t *dst = s_rows + (size_t)pl * PWs;
                 if (wide) {

@@ -169,3 +169,11 @@ def test_mid_size_tie_groups():
     o = util.run_oracle(cores, b, q1, q2)
     t, r = util.run_cuda(cores, b, q1, q2)
     util.assert_same(o, t, r)
+
+
+@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_READS_V2"])
+def test_previous_kernels_still_selectable(monkeypatch, var):
+    # the kernels these switches replaced at the end of round 1 (scan_smem_k, the generic offset scans, emit_reads_st_k)
+    monkeypatch.setenv(var, "0")
+    _case(20000, 100, seed=71)
+    _case(6000, 150, seed=72, paired=True, L2=100, bucket_set_bytes=1 << 20)
