@@ -133,7 +133,8 @@ static int single(Reads *R, uint32_t *base) {
     while (n0 < R->n) {
         const char *ge = getenv("SIM_GROWTH_LATE"), *gs = getenv("SIM_GROWTH_EARLY"), *sm = getenv("SIM_SMALL");   // api.cu: 2, 4, 1M
         const int64_t g_late = ge ? atoi(ge) : 2, g_early = gs ? atoi(gs) : 4, small = sm ? atoll(sm) : (1 << 20);
-        int64_t lenb = n0 < small ? (g_early - 1) * n0 : (g_late - 1) * n0; if (lenb < 4096) lenb = 4096;
+        const int64_t first_len = getenv("SIM_FIRST") ? atoll(getenv("SIM_FIRST")) : 4096;   // api.cu: 4096
+        int64_t lenb = n0 < small ? (g_early - 1) * n0 : (g_late - 1) * n0; if (lenb < first_len) lenb = first_len;
         int64_t n1 = n0 + lenb < R->n ? n0 + lenb : R->n;
         int first = 1, r = 0;
         char trace[512]; int tl = 0;
