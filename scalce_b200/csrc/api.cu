@@ -19,6 +19,7 @@
 #include "emit_offsets.cuh"
 #include "emit_coresident.cuh"
 #include "emit_reads_fast.cuh"
+#include "emit_names_fast.cuh"
 #include "shard.cuh"
 
 namespace scb {
@@ -410,6 +411,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     if (cores_mode) SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
     if (cfg.use_names) {
         if (cores_mode) SCB_LAUNCH(emit_names_loop_k, (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)dev_sms * 2), 256, 0, sN, e, cdiv(n, 256));
+        else if (env_on("SCB_EMIT_NAMES_V2", false)) SCB_LAUNCH(emit_names_fast_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);   // opt-in, not yet measured
         else SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
     }
     {

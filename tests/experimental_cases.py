@@ -9,6 +9,7 @@ context, nor hang it. Run it directly with
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
   SCB_RESOLVE_CHEAP_GUESS=1 the guess round of every tie-break block as a streaming pass (no sequential sweep)
+  SCB_EMIT_NAMES_V2=1      stream-0 writer with word stores into the staging buffer (emit_names_fast.cuh, emit_name.h)
   SCB_OVERLAP_CHUNKS=1     size prefix sum + flush-chunk boundaries on a side stream under the tie-break kernel
   (SCB_SCAN_V2, SCB_EMIT_READS_V2 and SCB_EMIT_FUSED_SCAN passed these cases on a B200 at the end of round 1, won their A/B runs
   and are the default now; "=0" selects the previous kernels, tests/test_gpu_parity.py::test_previous_kernels_still_selectable)
@@ -50,7 +51,7 @@ def test_early_emit_four_ranks(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_EMIT_NAMES_V2", "SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -214,3 +215,21 @@ def test_emit_reads_v2_short_rows(monkeypatch):
         o = util.run_oracle(cores, b, q1, q2)
         t, r = util.run_cuda(cores, b, q1, q2)
         util.assert_same(o, t, r)
+
+
+def test_emit_names_v2_long_and_ragged_names(monkeypatch):
+    # names of 0..60 bytes (several 16-byte chunks, every alignment of the record in the staging buffer)
+    monkeypatch.setenv("SCB_EMIT_NAMES_V2", "1")
+    import numpy as np
+    from scalce_b200 import synth
+    cores, b, q1, q2, _ = util.make_case(12000, 100, seed=211)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 61, size=b.n)
+    lens[:50] = np.arange(50) % 34                       # every length around the 15 / 16 / 31 / 32 byte boundaries early in a tile
+    off = np.zeros(b.n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    b.names = rng.integers(33, 127, size=int(off[-1]), dtype=np.uint8)
+    b.name_off = off
+    o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    util.assert_same(o, t, r)

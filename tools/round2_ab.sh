@@ -14,20 +14,14 @@ run() {  # name ENV=... : kernel-only bench line of one configuration
 }
 run default
 run sort_per_bucket SCB_SORT_PER_BUCKET=1
-run fused_scan SCB_EMIT_FUSED_SCAN=1
-run coresident SCB_EMIT_CORESIDENT=1
-run scan_v2 SCB_SCAN_V2=1
-run reads_v2 SCB_EMIT_READS_V2=1
-run overlap_chunks SCB_OVERLAP_CHUNKS=1
-run cheap_guess SCB_RESOLVE_CHEAP_GUESS=1
+run names_v2 SCB_EMIT_NAMES_V2=1
 # block schedule of the tie-break (tools/sim_resolve.c: x4 growth up to 4M / 16M reads -> 105 / 99 rounds instead of 111, larger blocks)
 run resolve_small_4M SCB_RESOLVE_SMALL=4194304
 run resolve_small_16M SCB_RESOLVE_SMALL=16777216
 # early growth x8 / x16 up to 4M reads: 87 / 80 rounds in the model (a round costs ~35 us even on a tiny block)
 run resolve_g8_4M SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
 run resolve_g16_4M SCB_RESOLVE_GROWTH=16 SCB_RESOLVE_SMALL=4194304
-run cores_reads_v2 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1
-run all_on SCB_EMIT_FUSED_SCAN=1 SCB_EMIT_CORESIDENT=1 SCB_EMIT_READS_V2=1 SCB_SCAN_V2=1 SCB_OVERLAP_CHUNKS=1 SCB_RESOLVE_CHEAP_GUESS=1
+run best_guess SCB_EMIT_NAMES_V2=1 SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
 # per-round phase times of the tie-break kernel (P / D / E / sync / scan per round, to stderr): what a round's fixed cost consists of
 SCB_RESOLVE_PROF=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ab/resolve_prof.json 2> gpurun_out/ab/resolve_prof.err
 grep "resolve totals\|resolve subtile" gpurun_out/ab/resolve_prof.err | tail -4
