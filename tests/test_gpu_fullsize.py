@@ -131,6 +131,24 @@ def test_stream1_size_and_meta_totals(big):
     assert int(tR) == want and int(tQ) == N_FULL * L
 
 
+def test_stream1_content_windows(big):
+    """Stream 1 byte for byte on three 500k-read windows of the output: every record must be the rotated 2-bit read + end marker
+    that reads.cpp:432-461 / 128-130 define for (read, core level, end) - tests/util.py::stream1_window_matches, itself checked
+    against the oracle's stream on the CPU (tests/test_host_cpu.py)."""
+    import torch
+    from tests import util
+    res = big["res"]
+    perm = res.torch_view("perm").to(torch.int64)
+    core = res.torch_view("core").to(torch.int64)
+    lens = torch.tensor([len(c) for c in big["cores"]] + [0], device=core.device)
+    lv = lens[torch.where(core >= 0, core, torch.full_like(core, len(big["cores"])))]
+    end = res.torch_view("end").to(torch.int64)
+    s1 = res.torch_view(1)
+    m = min(500_000, N_FULL)
+    for start in (0, max(0, N_FULL // 2 - m // 2), N_FULL - m):
+        assert util.stream1_window_matches(s1, big["seq"], perm, lv, end, L, start, m), f"stream 1 differs in the window at output position {start}"
+
+
 def test_prefix_of_the_big_run_equals_oracle_on_the_prefix(big):
     """Sequential semantics: reads 0..m-1 are decided before anything later exists, so their bucket ids and end
     markers in the 50M-read run equal the oracle's on those m reads alone (flush chunks too: same byte budget)."""

@@ -523,3 +523,33 @@ int main() {
     subprocess.run(["g++", "-O1", "-std=c++17", "-fsanitize=address,undefined", "-o", str(exe), str(src)], check=True)
     r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and r.stdout.startswith(b"ok"), (r.stdout + r.stderr).decode()
+
+
+def test_stream1_checker_against_the_oracle():
+    """tests/util.py::stream1_window_matches (the torch check the full-size GPU test applies to stream 1 at 50M reads) must accept
+    the oracle's stream 1 and reject a corrupted one. Output order recovered from the (unique) names in the oracle's stream 0."""
+    import torch
+    from tests import util
+    cores, b, q1, q2, _ = util.make_case(6000, 100, seed=33)
+    o = util.run_oracle(cores, b, q1, q2)
+    assert o.n_chunks == 1
+    s0 = np.frombuffer(o.stream(0, 0), dtype=np.uint8)
+    name_to_idx = {b.names[b.name_off[i]:b.name_off[i + 1]].tobytes(): i for i in range(b.n)}
+    perm, p = [], 0
+    while p < s0.size:
+        nl = int(s0[p])
+        perm.append(name_to_idx[s0[p + 1:p + 1 + nl].tobytes()])
+        p += 1 + nl
+    perm = torch.tensor(perm, dtype=torch.int64)
+    assert sorted(perm.tolist()) == list(range(b.n))
+    d = o.debug()
+    lens = np.array([len(c) for c in cores] + [0])
+    lv = torch.from_numpy(lens[np.where(d["core"] >= 0, d["core"], len(cores))].astype(np.int64))
+    end = torch.from_numpy(d["end"].astype(np.int64))
+    s1 = torch.from_numpy(np.frombuffer(o.stream(1, 0), dtype=np.uint8).copy())
+    seq = torch.from_numpy(b.seq)
+    assert util.stream1_window_matches(s1, seq, perm, lv, end, 100, 0, b.n)
+    assert util.stream1_window_matches(s1, seq, perm, lv, end, 100, 2500, 1000)
+    bad = s1.clone()
+    bad[len(bad) // 2] ^= 0x10
+    assert not util.stream1_window_matches(bad, seq, perm, lv, end, 100, 0, b.n)

@@ -140,3 +140,44 @@ def assert_sharded_same(o, ranks, paired=False, check_merged=True):
             g = b"".join(res.stream(k, -1) for _, _, res in ranks)
             assert a == g, f"merged stream {k}: oracle {len(a)} B, sharded {len(g)} B, first diff {_first_diff(a, g)}"
     assert o.unbucketed == sum(t.unbucketed for t, _, _ in ranks)
+
+
+def expected_stream1_records(seq_rows, lv, end, L):
+    """torch (CPU or CUDA): the stream-1 records of the given reads in the given order - output_read(read, dest, end - level, level)
+    (reads.cpp:432-461: bases [end, L) then [0, end - level), 4 per byte MSB first, zero padded) followed by the 1-byte end marker
+    (L <= 255, reads.cpp:128-130). seq_rows uint8 [m, L] ASCII; lv, end int64 [m]. Returns (records uint8 [m, ceil(L/4) + 1] zero
+    padded, sizes int64 [m])."""
+    import torch
+    assert L <= 255
+    m, dev = seq_rows.shape[0], seq_rows.device
+    lo = seq_rows | 0x20
+    code = torch.zeros_like(seq_rows)
+    code[lo == ord("c")] = 1
+    code[lo == ord("g")] = 2
+    code[lo == ord("t")] = 3
+    j = torch.arange(L, device=dev)[None, :]
+    tail, total = (L - end)[:, None], (L - lv)[:, None]
+    src = torch.where(j < tail, end[:, None] + j, j - tail)
+    out_code = torch.where(j < total, torch.gather(code, 1, src.clamp(0, L - 1)), torch.zeros_like(code))
+    nbmax = (L + 3) // 4
+    q = torch.nn.functional.pad(out_code, (0, nbmax * 4 - L)).view(m, nbmax, 4).to(torch.int32)
+    by = ((q[:, :, 0] << 6) | (q[:, :, 1] << 4) | (q[:, :, 2] << 2) | q[:, :, 3]).to(torch.uint8)
+    nbytes = (L - lv + 3) // 4
+    rec = torch.zeros((m, nbmax + 1), dtype=torch.uint8, device=dev)
+    rec[:, :nbmax] = by
+    rec.scatter_(1, nbytes[:, None], (end & 0xff).to(torch.uint8)[:, None])
+    return rec, nbytes + 1
+
+
+def stream1_window_matches(stream1, seq, perm, lv_in, end_in, L, start, m):
+    """True if the records of output positions [start, start + m) in `stream1` (uint8 tensor, all chunks in output order) are what
+    expected_stream1_records says. perm int64 [n] output position -> input read; lv_in / end_in int64 [n] per INPUT read."""
+    import torch
+    sizes = (L - lv_in[perm] + 3) // 4 + 1
+    off = torch.cumsum(sizes, 0) - sizes
+    idx = perm[start:start + m]
+    want, sz = expected_stream1_records(seq.index_select(0, idx), lv_in[idx], end_in[idx], L)
+    col = torch.arange(want.shape[1], device=want.device)[None, :]
+    pos = (off[start:start + m, None] + col).clamp(max=stream1.numel() - 1)
+    got = torch.where(col < sz[:, None], stream1[pos], torch.zeros_like(want))
+    return bool(torch.equal(got, want)) and int(off[-1] + sizes[-1]) == stream1.numel()
