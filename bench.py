@@ -535,6 +535,7 @@ def main():
     for k, d_ in per_stage.items():
         d_["frac"] = (d_["achieved_gbs"] / peak) if d_["achieved_gbs"] else None
     roof = {"bound": "hbm", "kernel": dom, "kernels": stage_kernels.get(dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_source": "ncu launch list profiles/r01_launches_summary.txt, taken before scan_smem2_k / emit_reads_fast_k / the fused offset scans / the 5-pass sort became defaults: an upper bound for the emit and sort stages" if traffic else None,
             "peak_source": peak_src, "bytes_per_read": stage_bytes.get(dom), "stage_ms": mean_st, "per_stage": per_stage, "resolve_rounds": resolve_rounds}
     pipe = N * bpr / (ms_step * 1e-3) / 1e9
     pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
