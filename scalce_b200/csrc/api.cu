@@ -173,6 +173,7 @@ struct scb_handle {
     int64_t sh_n_local = 0;    // reads of this rank's input shard
     int sh_W = 0, sh_grid = 0; // dense-resolve geometry
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
+    DevBuf sh_stale, sh_nstale;   // deferred re-sweeps (resolve_dense_k<*, *, true>)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
@@ -601,9 +602,9 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
-    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, false>, W * 32, smem));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, false, false>, W * 32, smem));
     if (occ < 1) return false;
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
@@ -615,6 +616,8 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     h->sh_frbuf.alloc((size_t)n * 8 + 64, st);
     h->sh_fridx.alloc((size_t)n * 4 + 64, st);
     h->sh_incr_stat.alloc(32, st);
+    h->sh_stale.alloc(max_sub * 4, st); h->sh_nstale.alloc((size_t)kRdMaxRounds * 4, st);
+    SCB_CUDA(cudaMemsetAsync(h->sh_stale.p, 0, max_sub * 4, st));
     SCB_CUDA(cudaMemsetAsync(h->sh_frused.p, 0xff, max_sub * 4, st));
     SCB_CUDA(cudaMemsetAsync(h->sh_incr_stat.p, 0, 32, st));
     h->sh_Csum.alloc((size_t)grid * P * 4, st); h->sh_Cpre.alloc((size_t)grid * P * 4, st);
@@ -651,6 +654,8 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
         if (nb1 > 0xffff) rp.incr_T = 0;                 // records hold bucket ranks in 16 bits
     }
     rp.incr_stat = (getenv("SCB_RESOLVE_PROF") || getenv("SCB_RESOLVE_STAT")) ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
+    rp.stale = h->sh_stale.as<uint32_t>(); rp.n_stale = h->sh_nstale.as<uint32_t>();
+    if (mode == 0) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
@@ -660,10 +665,11 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     // opt-in (not yet measured): the guess round of every block as a streaming pass (resolve_dense.cuh, CHEAP)
     const char *cg = getenv("SCB_RESOLVE_CHEAP_GUESS");
     const bool cheap = cg && atoi(cg) != 0;
-    void *kfn = (void *)resolve_dense_k<false, false>;
-    if (mode == 3) kfn = cheap ? (void *)resolve_dense_k<true, true> : (void *)resolve_dense_k<true, false>;   // all joint rounds in this launch (JOINT)
-    else if (cheap) kfn = (void *)resolve_dense_k<false, true>;
-    if (kfn != (void *)resolve_dense_k<false, false>) SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *kfn = (void *)resolve_dense_k<false, false, false>;
+    if (mode == 3) kfn = cheap ? (void *)resolve_dense_k<true, true, false> : (void *)resolve_dense_k<true, false, false>;   // all joint rounds in this launch (JOINT)
+    else if (cheap) kfn = (void *)resolve_dense_k<false, true, false>;
+    else if (mode == 0 && env_on("SCB_RESOLVE_DEFER", false)) kfn = (void *)resolve_dense_k<false, false, true>;   // opt-in (not yet measured): deferred re-sweeps
+    if (kfn != (void *)resolve_dense_k<false, false, false>) SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SCB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
     if (mode != 0 && mode != 3) {

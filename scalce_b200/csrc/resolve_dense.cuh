@@ -93,6 +93,9 @@ struct RdParams {
     int incr_T;                   // decision-margin threshold
     unsigned long long *incr_stat;   // optional [4]: full sweeps, incremental sweeps, incremental sweeps redone in full, records visited
     RdJoint j;                       // joint mode only (mode 3)
+    // DEFER instances only (see resolve_dense_k): stale[t] = 1 while subtile t runs on replays although its margin bound failed;
+    // n_stale[round] = such subtiles after the round
+    uint32_t *stale, *n_stale;
 };
 
 __device__ __forceinline__ uint32_t lanemask_ge() {
@@ -377,7 +380,14 @@ __device__ __forceinline__ void rd_row_add(uint32_t *row, const uint32_t *g, int
 // rank's row of the previous round has arrived (system-scope flags in my exchange buffer), stop if no rank changed
 // anything, build the populations before my shard (lifetime + rows of the lower ranks) in this CTA's own copy, run
 // the round as in modes 1-2, then CTA 0 pushes my row into every rank's buffer and raises my flag there.
-template <bool JOINT, bool CHEAP>
+// DEFER = true (opt-in, mode 0): a subtile whose margin bound fails is NOT swept in full in the same round. Today it is, and the whole
+// round - two grid syncs, ~1775 other warps that only replay - waits for that one sequential sweep; tools/sim_resolve.c counts such
+// straggler sweeps in rounds 3-8 of every large block and, with a simple time model that reproduces the measured 9 ms, attributes ~15 %
+// of the kernel to them. Deferred: the subtile keeps the replay's result (fragile reads exact, the others possibly outdated) and is
+// marked stale; when a round changes nothing anywhere, the stale subtiles are swept in full in the next round (which rebuilds their
+// lists), and the block is finished by a quiet round without stale subtiles. A subtile whose bound holds again is not stale: the bound
+// only compares the current state with the last full sweep. Exactness as before: at termination every read was re-decided exactly.
+template <bool JOINT, bool CHEAP, bool DEFER>
 __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams p) {
     extern __shared__ __align__(16) uint32_t sm_cnt[];   // [W][pitch] populations, then [W][pitch] per-step lane tags
     const int W = p.W, nb1 = p.nb1, P = p.pitch, Q = p.pitch >> 2;   // Q = 128-bit quads per row
@@ -407,6 +417,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
         const int nact = (ns + k - 1) / k;                    // CTAs with work
         const int t_lo = c * k, t_hi = min(ns, t_lo + k);
         bool first = p.mode != 2;
+        bool verify = false;                     // DEFER: this round sweeps the stale subtiles in full
         while (true) {
             if constexpr (JOINT) {
                 // ---- joint mode prologue: rows of the previous round, termination, populations before my shard ----
@@ -507,14 +518,20 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                 if (incr_on) {
                     const uint32_t nrec = p.fr_used[t];
                     const uint32_t dmax = s_dmax[w];
-                    if (nrec != kFrNone && 2u * dmax <= (uint32_t)p.incr_T) {
+                    const bool sweep_now = DEFER && verify && p.stale[t] != 0;   // a quiet round was seen: stale subtiles are swept in full now
+                    if (nrec != kFrNone && !sweep_now && (DEFER || 2u * dmax <= (uint32_t)p.incr_T)) {
                         uint32_t E = 0;
                         rd_row_sub(cnt, S0row, Q);                               // row = new start - start of the full sweep
                         ch = rd_replay(p, lo, frw, fidx, nrec, cnt, &E);
                         visited = nrec;
-                        if (2u * (dmax + E) <= (uint32_t)p.incr_T) {
+                        const bool bound_ok = 2u * (dmax + E) <= (uint32_t)p.incr_T;
+                        if (bound_ok || DEFER) {
                             rd_row_add(cnt, S0row, Q);                           // back to new start + deviations (what the E phase expects)
                             replayed = true; stat_incr = 1;
+                            if (DEFER && l == 0) {
+                                p.stale[t] = bound_ok ? 0u : 1u;
+                                if (!bound_ok) atomicAdd(&p.n_stale[round], 1u);
+                            }
                         } else {
                             // the bound broke: sweep in full. First take the deviations out again: row -> new start counts
                             for (uint32_t r0 = l; r0 < nrec; r0 += 32) {
@@ -540,6 +557,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                     if (CHEAP && first) ch += rd_sweep_static(p, lo, hi, cnt, tagw);
                     else ch += rd_sweep(p, lo, hi, cnt, tagw, fr);
                     if (p.incr_T > 0 && l == 0) p.fr_used[t] = list ? fr.recs : kFrNone;
+                    if (DEFER && l == 0) p.stale[t] = 0u;
                     stat_full = 1;
                 }
                 if (l == 0) s_incr[w] = replayed ? 1 : 0;
@@ -591,7 +609,9 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             RD_STAMP(4);
             // ---- column scan over chunk totals; on convergence fold the block into base ---------------
             const uint32_t chg = *((volatile uint32_t *)&p.changed[round]);
-            const bool done = (chg == 0);
+            const uint32_t nst = DEFER ? *((volatile uint32_t *)&p.n_stale[round]) : 0u;
+            const bool done = (chg == 0) && nst == 0;
+            if (DEFER) verify = chg == 0 && nst != 0;
             {   // one warp per quad of columns; lanes stride over the chunks, shuffle scan across lanes
                 const int gw = blockIdx.x * W + w, tw = gridDim.x * W;
                 for (int q = gw; q < Q; q += tw) {

@@ -8,6 +8,7 @@ context, nor hang it. Run it directly with
   SCB_SHARD_JOINT_KERNEL=1 all joint tie-break rounds inside one kernel per rank, histograms exchanged through peer memory
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
   SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
+  SCB_RESOLVE_DEFER=1       tie-break: a subtile whose margin bound fails keeps replaying and is swept in full only after a quiet round
   SCB_RESOLVE_CHEAP_GUESS=1 the guess round of every tie-break block as a streaming pass (no sequential sweep)
   SCB_EMIT_NAMES_V2=1      stream-0 writer with word stores into the staging buffer (emit_names_fast.cuh, emit_name.h)
   SCB_OVERLAP_CHUNKS=1     size prefix sum + flush-chunk boundaries on a side stream under the tie-break kernel
@@ -51,7 +52,7 @@ def test_early_emit_four_ranks(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_EMIT_NAMES_V2", "SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
+@pytest.mark.parametrize("var", ["SCB_RESOLVE_DEFER", "SCB_EMIT_NAMES_V2", "SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
 def test_single_gpu_variants(monkeypatch, var):
     monkeypatch.setenv(var, "1")
     for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
@@ -232,4 +233,22 @@ def test_emit_names_v2_long_and_ragged_names(monkeypatch):
     b.name_off = off
     o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
     t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    util.assert_same(o, t, r)
+
+
+def test_resolve_defer_large_and_tied(monkeypatch):
+    # deferred re-sweeps on inputs where the margin bound fails often: 1M reads of the headline core set (blocks of up to 500k reads),
+    # a second flush on large lifetime populations, and a dense core set where almost every read is tied
+    monkeypatch.setenv("SCB_RESOLVE_DEFER", "1")
+    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=221, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2, splits=[400000])
+    t, r = util.run_cuda(cores, b, q1, q2, splits=[400000])
+    util.assert_same(o, t, r)
+    import itertools
+    from scalce_b200 import synth
+    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]
+    b = synth.make_batch(60000, 80, seed=222)
+    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
+    o = util.run_oracle(cores, b, q1, None)
+    t, r = util.run_cuda(cores, b, q1, None)
     util.assert_same(o, t, r)

@@ -15,13 +15,16 @@ run() {  # name ENV=... : kernel-only bench line of one configuration
 run default
 run sort_per_bucket SCB_SORT_PER_BUCKET=1
 run names_v2 SCB_EMIT_NAMES_V2=1
+# tie-break: deferred re-sweeps (model: 8.95 -> 7.7 ms), alone and with the faster-growing early blocks
+run resolve_defer SCB_RESOLVE_DEFER=1
+run resolve_defer_g8 SCB_RESOLVE_DEFER=1 SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
 # block schedule of the tie-break (tools/sim_resolve.c: x4 growth up to 4M / 16M reads -> 105 / 99 rounds instead of 111, larger blocks)
 run resolve_small_4M SCB_RESOLVE_SMALL=4194304
 run resolve_small_16M SCB_RESOLVE_SMALL=16777216
 # early growth x8 / x16 up to 4M reads: 87 / 80 rounds in the model (a round costs ~35 us even on a tiny block)
 run resolve_g8_4M SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
 run resolve_g16_4M SCB_RESOLVE_GROWTH=16 SCB_RESOLVE_SMALL=4194304
-run best_guess SCB_EMIT_NAMES_V2=1 SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
+run best_guess SCB_EMIT_NAMES_V2=1 SCB_RESOLVE_DEFER=1 SCB_RESOLVE_GROWTH=8 SCB_RESOLVE_SMALL=4194304
 # per-round phase times of the tie-break kernel (P / D / E / sync / scan per round, to stderr): what a round's fixed cost consists of
 SCB_RESOLVE_PROF=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ab/resolve_prof.json 2> gpurun_out/ab/resolve_prof.err
 grep "resolve totals\|resolve subtile" gpurun_out/ab/resolve_prof.err | tail -4

@@ -21,6 +21,11 @@
 
 #define NB 2048
 #define MAXC 6
+// bookkeeping of the incremental rounds (resolve_dense.cuh "fragile reads"): a subtile whose start counts moved by Dmax since its last
+// FULL sweep and whose decisions differ from that sweep in E reads must be swept in full again when 2 * (Dmax + E) > T; otherwise a
+// replay of its fragile list suffices. The model's sweeps are always exact - this only COUNTS which subtiles the kernel would re-sweep.
+static uint32_t *g_S0 = NULL; static uint8_t *g_sel0 = NULL; static int g_round_in_block = 0; static int64_t g_redo = 0, g_redo_reads = 0; static int g_T = 1024;
+static double g_model_us = 0;
 static int SUB = 1776;   // subtiles per block (148 CTAs x 12 warps); SIM_SUB overrides
 
 static uint64_t rs;
@@ -90,6 +95,46 @@ static int64_t sweep(Reads *R, int64_t lo, int64_t hi, uint32_t *cnt) {
     return ch;
 }
 
+// ---- model of the incremental rounds: fragile flags, replay, and the policy for subtiles whose margin bound fails -------------
+// g_frag[i] = 1 if read i's decision margin at its subtile's last FULL sweep was <= T (it is on the fragile list).
+// SIM_DEFER=1: a subtile whose bound fails is NOT re-swept at once (today: it is, and the whole round waits for it); it keeps
+// replaying - which may leave non-fragile reads with stale decisions - and is only swept in full in a later round, when the replay
+// rounds have gone quiet. Termination then needs a quiet round with no stale subtile left.
+static uint8_t *g_frag = NULL, *g_stale = NULL; static int g_defer = 0, g_verify = 0; static int64_t g_sweeps = 0, g_replays = 0;
+static int64_t sweep_margin(Reads *R, int64_t lo, int64_t hi, uint32_t *cnt, int T) {
+    int64_t ch = 0;
+    for (int64_t i = lo; i < hi; i++) {
+        const int nc = R->nc[i];
+        g_frag[i] = 0;
+        if (!nc) continue;
+        const uint16_t *c = R->c + i * MAXC;
+        int best = 0; uint32_t bc = cnt[c[0]];
+        for (int k = 1; k < nc; k++) if (cnt[c[k]] > bc) { bc = cnt[c[k]]; best = k; }
+        int64_t margin = 1 << 30;
+        for (int k = 0; k < nc; k++) if (k != best) { int64_t m = (int64_t)bc - cnt[c[k]] - (k < best ? 1 : 0); if (m < margin) margin = m; }
+        g_frag[i] = nc >= 2 && margin <= T;
+        cnt[c[best]]++;
+        if (R->sel[i] != best) { R->sel[i] = (uint8_t)best; ch++; }
+    }
+    return ch;
+}
+static int64_t replay(Reads *R, int64_t lo, int64_t hi, uint32_t *cnt) {   // fragile reads re-decided exactly, the others keep their decision
+    int64_t ch = 0;
+    for (int64_t i = lo; i < hi; i++) {
+        const int nc = R->nc[i];
+        if (!nc) continue;
+        const uint16_t *c = R->c + i * MAXC;
+        int best = R->sel[i];
+        if (g_frag[i]) {
+            best = 0; uint32_t bc = cnt[c[0]];
+            for (int k = 1; k < nc; k++) if (cnt[c[k]] > bc) { bc = cnt[c[k]]; best = k; }
+            if (R->sel[i] != best) { R->sel[i] = (uint8_t)best; ch++; }
+        }
+        cnt[c[best]]++;
+    }
+    return ch;
+}
+
 // One round over block [n0, n1) of R split into SUB subtiles. H[t][b]: per-subtile histograms of the previous round
 // (updated). first: start counts extrapolated from base (g0 = reads before n0 in the job). Returns changed decisions.
 static int64_t round_block(Reads *R, int64_t n0, int64_t n1, const uint32_t *base, uint32_t *H, int first, int64_t g0, uint32_t *tot) {
@@ -118,8 +163,54 @@ static int64_t round_block(Reads *R, int64_t n0, int64_t n1, const uint32_t *bas
             memcpy(H + (size_t)t * NB, hh, sizeof hh);
             continue;
         }
+        if (g_frag) {
+            int full = g_round_in_block < 2 || (g_verify && g_stale[t]);
+            int64_t ch_t = 0;
+            if (!full) {
+                uint32_t dmax = 0;
+                for (int b = 0; b < NB; b++) { int32_t d = (int32_t)(start[(size_t)t * NB + b] - g_S0[(size_t)t * NB + b]); uint32_t a = d < 0 ? -d : d; if (a > dmax) dmax = a; }
+                uint32_t save[NB]; memcpy(save, cnt, sizeof save);
+                ch_t = replay(R, lo, hi, cnt);
+                int64_t E = 0;
+                for (int64_t i = lo; i < hi; i++) E += R->sel[i] != g_sel0[i];
+                if (2 * ((int64_t)dmax + E) > g_T) {
+                    if (g_defer) g_stale[t] = 1;                              // keep the replay's result, sweep later
+                    else { memcpy(cnt, save, sizeof save); full = 1; }        // today's kernel: sweep in full in the same round
+                }
+            }
+            if (full) {
+                ch_t += sweep_margin(R, lo, hi, cnt, g_T);
+                memcpy(g_S0 + (size_t)t * NB, start + (size_t)t * NB, NB * 4); memcpy(g_sel0 + lo, R->sel + lo, hi - lo);
+                g_stale[t] = 0;
+#pragma omp atomic
+                g_sweeps++;
+            } else {
+#pragma omp atomic
+                g_replays++;
+            }
+            changed += ch_t;
+            for (int b = 0; b < NB; b++) H[(size_t)t * NB + b] = cnt[b] - start[(size_t)t * NB + b];
+            continue;
+        }
         changed += sweep(R, lo, hi, cnt);
         for (int b = 0; b < NB; b++) H[(size_t)t * NB + b] = cnt[b] - start[(size_t)t * NB + b];
+        if (g_S0) {
+            int full = g_round_in_block < 2;                       // guess round and the round after it always sweep in full
+            if (!full) {
+                uint32_t dmax = 0;
+                for (int b = 0; b < NB; b++) { int32_t d = (int32_t)(start[(size_t)t * NB + b] - g_S0[(size_t)t * NB + b]); uint32_t a = d < 0 ? -d : d; if (a > dmax) dmax = a; }
+                int64_t E = 0;
+                for (int64_t i = lo; i < hi; i++) E += R->sel[i] != g_sel0[i];
+                full = 2 * ((int64_t)dmax + E) > g_T;
+                if (full) {
+#pragma omp atomic
+                    g_redo++;
+#pragma omp atomic
+                    g_redo_reads += hi - lo;
+                }
+            }
+            if (full) { memcpy(g_S0 + (size_t)t * NB, start + (size_t)t * NB, NB * 4); memcpy(g_sel0 + lo, R->sel + lo, hi - lo); }
+        }
     }
     if (tot) { memset(tot, 0, NB * 4); for (int t = 0; t < ns; t++) for (int b = 0; b < NB; b++) tot[b] += H[(size_t)t * NB + b]; }
     free(start);
@@ -137,10 +228,41 @@ static int single(Reads *R, uint32_t *base) {
         int64_t lenb = n0 < small ? (g_early - 1) * n0 : (g_late - 1) * n0; if (lenb < first_len) lenb = first_len;
         int64_t n1 = n0 + lenb < R->n ? n0 + lenb : R->n;
         int first = 1, r = 0;
-        char trace[512]; int tl = 0;
+        char trace[768]; int tl = 0;
+        if (getenv("SIM_REDO")) { if (!g_S0) { g_S0 = calloc((size_t)SUB * NB, 4); g_sel0 = malloc(R->n); if (getenv("SIM_T")) g_T = atoi(getenv("SIM_T")); } }
+        g_round_in_block = 0;
+        if (getenv("SIM_POLICY")) {   // model the replay / re-sweep machinery: SIM_POLICY=now (today's kernel) or defer
+            if (!g_frag) { g_frag = calloc(R->n, 1); g_stale = calloc(SUB + 1, 1); if (!g_S0) { g_S0 = calloc((size_t)SUB * NB, 4); g_sel0 = malloc(R->n); } if (getenv("SIM_T")) g_T = atoi(getenv("SIM_T")); }
+            g_defer = !strcmp(getenv("SIM_POLICY"), "defer");
+            memset(g_stale, 0, SUB + 1);
+            const int64_t per = (n1 - n0 + SUB - 1) / SUB;
+            double us = 0;
+            for (;;) {
+                g_sweeps = g_replays = 0;
+                int64_t ch = round_block(R, n0, n1, base, H, first, 0, tot); first = 0; r++;
+                // time model: 35 us fixed; a round lasts as long as its slowest subtile: 25 ns per read swept, 5 ns per read replayed (5 % x 100 ns)
+                us += 35.0 + (g_sweeps ? per * 0.025 : per * 0.005);
+                if (tl < 700) tl += snprintf(trace + tl, sizeof trace - tl, " %ld(%ld)", (long)ch, (long)g_sweeps);
+                g_round_in_block++;
+                g_verify = 0;
+                if (!ch) {
+                    int any = 0; for (int t = 0; t < SUB; t++) any |= g_stale[t];
+                    if (!any) break;
+                    g_verify = 1;                                             // quiet, but stale subtiles remain: sweep them in the next round
+                }
+            }
+            g_model_us += us;
+            if (getenv("SIM_TRACE")) printf("    changed(subtiles swept in full) per round:%s   ~%.0f us\n", trace, us);
+            for (int b = 0; b < NB; b++) base[b] += tot[b];
+            printf("  block %2d [%9ld, %9ld): %d rounds\n", nblk, (long)n0, (long)n1, r);
+            rounds += r; nblk++; n0 = n1;
+            continue;
+        }
         for (;;) {
+            g_redo = 0; g_redo_reads = 0;
             int64_t ch = round_block(R, n0, n1, base, H, first, 0, tot); first = 0; r++;
-            if (tl < 480) tl += snprintf(trace + tl, sizeof trace - tl, " %ld", (long)ch);
+            if (tl < 700) tl += g_S0 ? snprintf(trace + tl, sizeof trace - tl, " %ld(%ld)", (long)ch, (long)g_redo) : snprintf(trace + tl, sizeof trace - tl, " %ld", (long)ch);
+            g_round_in_block++;
             if (!ch) break;
         }
         if (getenv("SIM_TRACE")) printf("    changed per round:%s\n", trace);
@@ -213,6 +335,11 @@ int main(int argc, char **argv) {
         uint32_t base[NB] = {0};
         int r = single(&R, base);
         printf("single GPU, %ld reads: %d rounds in total\n", (long)R.n, r);
+        if (getenv("SIM_POLICY")) {
+            uint32_t cnt[NB] = {0}; Reads S = R; S.sel = malloc(R.n); memset(S.sel, 0xff, R.n); sweep(&S, 0, R.n, cnt);
+            int64_t bad = 0; for (int64_t i = 0; i < R.n; i++) bad += R.nc[i] && R.sel[i] != S.sel[i];
+            printf("policy %s, T = %d: modelled time %.2f ms; decisions differing from the sequential answer: %ld\n", getenv("SIM_POLICY"), g_T, g_model_us * 1e-3, (long)bad);
+        }
         return 0;
     }
     const int G = atoi(argv[2]); const int64_t n = atoll(argv[3]); const int pre = argc > 4 ? atoi(argv[4]) : 0;
