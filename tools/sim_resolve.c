@@ -240,8 +240,11 @@ static int single(Reads *R, uint32_t *base) {
             for (;;) {
                 g_sweeps = g_replays = 0;
                 int64_t ch = round_block(R, n0, n1, base, H, first, 0, tot); first = 0; r++;
-                // time model: 35 us fixed; a round lasts as long as its slowest subtile: 25 ns per read swept, 5 ns per read replayed (5 % x 100 ns)
-                us += 35.0 + (g_sweeps ? per * 0.025 : per * 0.005);
+                // time model: 35 us fixed; a round lasts as long as its slowest subtile: 25 ns per read swept, 100 ns per fragile record replayed
+                // (replay cost from the block's actual fragile fraction, 100 ns per record: 32 records per ~3 us replay iteration)
+                int64_t nf = 0; for (int64_t i = n0; i < n1; i++) nf += g_frag[i];
+                const double frag = (double)nf / (double)(n1 - n0);
+                us += 35.0 + (g_sweeps ? per * 0.025 : per * frag * 0.1);
                 if (tl < 700) tl += snprintf(trace + tl, sizeof trace - tl, " %ld(%ld)", (long)ch, (long)g_sweeps);
                 g_round_in_block++;
                 g_verify = 0;
