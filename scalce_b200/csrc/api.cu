@@ -655,7 +655,7 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     }
     rp.incr_stat = (getenv("SCB_RESOLVE_PROF") || getenv("SCB_RESOLVE_STAT")) ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
     rp.stale = h->sh_stale.as<uint32_t>(); rp.n_stale = h->sh_nstale.as<uint32_t>();
-    if (mode == 0) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
+    if (mode == 0 || mode == 3) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
@@ -666,9 +666,11 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     const char *cg = getenv("SCB_RESOLVE_CHEAP_GUESS");
     const bool cheap = cg && atoi(cg) != 0;
     void *kfn = (void *)resolve_dense_k<false, false, false>;
-    if (mode == 3) kfn = cheap ? (void *)resolve_dense_k<true, true, false> : (void *)resolve_dense_k<true, false, false>;   // all joint rounds in this launch (JOINT)
+    const bool defer = env_on("SCB_RESOLVE_DEFER", false);   // opt-in (not yet measured): deferred re-sweeps
+    if (mode == 3) kfn = cheap ? (defer ? (void *)resolve_dense_k<true, true, true> : (void *)resolve_dense_k<true, true, false>)
+                               : (defer ? (void *)resolve_dense_k<true, false, true> : (void *)resolve_dense_k<true, false, false>);   // all joint rounds in this launch (JOINT)
     else if (cheap) kfn = (void *)resolve_dense_k<false, true, false>;
-    else if (mode == 0 && env_on("SCB_RESOLVE_DEFER", false)) kfn = (void *)resolve_dense_k<false, false, true>;   // opt-in (not yet measured): deferred re-sweeps
+    else if (mode == 0 && defer) kfn = (void *)resolve_dense_k<false, false, true>;
     if (kfn != (void *)resolve_dense_k<false, false, false>) SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SCB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
@@ -1185,7 +1187,7 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
 }
 
 // ---- joint rounds inside one kernel per rank (opt-in; resolve_dense.cuh "joint mode") ------------------------------------
-static int joint_row_words(int nb1) { return (nb1 + 1 + 3) & ~3; }
+static int joint_row_words(int nb1) { return (nb1 + 2 + 3) & ~3; }
 static size_t joint_bytes(int nb1, int G) { return ((size_t)2 * G * joint_row_words(nb1) + (size_t)G + 64) * 4; }
 
 static void shard_joint_reserve(scb_handle *h, int G, void **ptr, int32_t *changed) {

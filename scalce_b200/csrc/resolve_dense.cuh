@@ -34,7 +34,7 @@ constexpr int kRdBatch = 6;             // 128-bit histogram rows fetched togeth
 // Joint rounds of the sharded run inside ONE kernel per rank (opt-in, written without GPU access; see "joint mode" in
 // resolve_dense_k): the ranks exchange their histogram rows through peer memory instead of an NCCL all-gather per round.
 // Exchange buffer of a rank (plain cudaMalloc, mapped by the peers through CUDA IPC): rows[2][G][RW] u32 (parity of the
-// round, rank that produced the row; RW >= nb1 + 1: bucket histogram + changed count), then flags[G] u32 (slot s is
+// round, rank that produced the row; RW >= nb1 + 2: bucket histogram, changed count, stale subtiles), then flags[G] u32 (slot s is
 // written by rank s: epoch + number of rounds it has finished; 0xffff rounds = "my row is final").
 constexpr int kJointMaxRanks = 16;
 constexpr uint32_t kJointFinal = 0xffffu;
@@ -436,18 +436,23 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                             if (gtimer() - t0 > j.timeout_ns) { state = 2; break; }
                     }
                     if (state == 0 && round >= 2) {                                  // round - 1 was not the guess round: did anything change in it?
-                        uint32_t chg_all = 0;
-                        for (int s2 = 1; s2 < j.G; s2++) chg_all += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + nb1);
-                        if (chg_all == 0) state = 1;
+                        uint32_t chg_all = 0, stale_all = 0;                         // (DEFER: and is any subtile of any rank still stale?)
+                        for (int s2 = 1; s2 < j.G; s2++) {
+                            chg_all += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + nb1);
+                            stale_all += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + nb1 + 1);
+                        }
+                        if (chg_all == 0 && stale_all == 0) state = 1;
+                        else if (chg_all == 0) state = 4;                            // quiet but stale: this round sweeps the stale subtiles in full
                     }
                     s_joint = state;
                 }
                 __syncthreads();
                 const int state = s_joint;
-                if (state != 0) {
+                if (state != 0 && state != 4) {
                     if (blockIdx.x == 0 && threadIdx.x == 0) { *p.rounds_out = round; if (state == 2) *p.status = 2; }
                     return;
                 }
+                if (DEFER) verify = state == 4;
                 uint32_t *mine = p.j.cta_base + (size_t)blockIdx.x * P;
                 for (int i = threadIdx.x; i < P; i += blockDim.x) {
                     uint32_t v = 0;
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             const uint32_t chg = *((volatile uint32_t *)&p.changed[round]);
             const uint32_t nst = DEFER ? *((volatile uint32_t *)&p.n_stale[round]) : 0u;
             const bool done = (chg == 0) && nst == 0;
-            if (DEFER) verify = chg == 0 && nst != 0;
+            if (DEFER && !JOINT) verify = chg == 0 && nst != 0;   // joint mode decides from every rank's row (prologue)
             {   // one warp per quad of columns; lanes stride over the chunks, shuffle scan across lanes
                 const int gw = blockIdx.x * W + w, tw = gridDim.x * W;
                 for (int q = gw; q < Q; q += tw) {
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                     for (int g = 0; g < j.G; g++) {
                         uint32_t *dst = rdj_row(j, g, par, j.rank);
                         for (int i = threadIdx.x; i < nb1; i += blockDim.x) dst[i] = p.tot_out[i];
-                        if (threadIdx.x == 0) dst[nb1] = chg;
+                        if (threadIdx.x == 0) { dst[nb1] = chg; dst[nb1 + 1] = nst; }
                     }
                     __threadfence_system();
                     __syncthreads();
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(256) joint_follow_k(RdJoint j, const uint32_t 
         for (int g = 0; g < j.G; g++) {
             uint32_t *dst = rdj_row(j, g, par, j.rank);
             for (int i = threadIdx.x; i < nb1; i += blockDim.x) dst[i] = row ? row[i] : 0u;
-            if (threadIdx.x == 0) dst[nb1] = 0u;
+            if (threadIdx.x == 0) { dst[nb1] = 0u; dst[nb1 + 1] = 0u; }
         }
     __threadfence_system();
     __syncthreads();
@@ -704,8 +709,9 @@ __global__ void __launch_bounds__(256) joint_follow_k(RdJoint j, const uint32_t 
             }
             if (state) break;
             if (k >= 2) {
-                uint32_t chg_all = 0;
-                for (int s2 = 1; s2 < j.G; s2++) chg_all += ld_volatile_u32(rdj_row(j, j.rank, (k - 1) & 1, s2) + nb1);
+                uint32_t chg_all = 0;   // changed decisions + stale subtiles (the latter only with deferred re-sweeps): both must be zero
+                for (int s2 = 1; s2 < j.G; s2++)
+                    chg_all += ld_volatile_u32(rdj_row(j, j.rank, (k - 1) & 1, s2) + nb1) + ld_volatile_u32(rdj_row(j, j.rank, (k - 1) & 1, s2) + nb1 + 1);
                 if (chg_all == 0) { state = 1; break; }
             }
             if (k >= (int)kJointFinal - 1) { state = 3; break; }

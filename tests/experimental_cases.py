@@ -149,7 +149,7 @@ def test_joint_kernel_over_nvlink(world):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + world), os.path.join(root, "tests", "sharded_nccl_worker.py"), "120000", "100", str(1 << 21)]
-    env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1")
+    env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1", SCB_RESOLVE_DEFER="1" if world != 2 else "0")
     r = subprocess.run(cmd, cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_NCCL_OK" in r.stdout, r.stdout[-4000:]
 

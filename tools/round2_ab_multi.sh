@@ -14,8 +14,8 @@ run default
 run early_emit SCB_SHARD_EARLY_EMIT=1
 run joint_kernel SCB_SHARD_JOINT_KERNEL=1
 run joint_early SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1
-run cheap_guess SCB_RESOLVE_CHEAP_GUESS=1
-run all_on SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1 SCB_RESOLVE_CHEAP_GUESS=1
+run joint_defer SCB_SHARD_JOINT_KERNEL=1 SCB_RESOLVE_DEFER=1
+run all_on SCB_SHARD_JOINT_KERNEL=1 SCB_RESOLVE_DEFER=1 SCB_SHARD_EARLY_EMIT=1
 # per-round sweep statistics of the default joint rounds (full / incremental / redone subtiles per round and rank, to stderr)
 SCB_RESOLVE_STAT=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $N --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ab/n${N}_stat.json 2> gpurun_out/ab/n${N}_stat.err
