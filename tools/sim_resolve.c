@@ -176,7 +176,7 @@ static int64_t round_block(Reads *R, int64_t n0, int64_t n1, const uint32_t *bas
                 if (2 * ((int64_t)dmax + E) > g_T) {
                     if (g_defer) g_stale[t] = 1;                              // keep the replay's result, sweep later
                     else { memcpy(cnt, save, sizeof save); full = 1; }        // today's kernel: sweep in full in the same round
-                }
+                } else if (g_defer && !getenv("SIM_STICKY")) g_stale[t] = 0;  // the bound holds again: the replay was exact (as in the kernel)
             }
             if (full) {
                 ch_t += sweep_margin(R, lo, hi, cnt, g_T);
