@@ -134,7 +134,8 @@ int scb_copy_debug(scb_handle *h, int32_t *bucket_id, int32_t *core_idx, int32_t
 int64_t scb_unbucketed(const scb_handle *h);
 /* Lifetime count of a core's bucket (bin_size), -1 = root. */
 int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx);
-/* Number of this library's kernel launches since creation (bench.py's gpu_launches). */
+/* Number of this library's kernel launches in this PROCESS so far, over all handles (an atomic process-wide counter;
+ * the handle argument is ignored). bench.py's gpu_launches is a difference of two readings. */
 int64_t scb_kernel_launches(const scb_handle *h);
 /* Device time of each stage of the last flush, CUDA events on the handle's stream, milliseconds:
  * 0 scan, 1 resolve, 2 size accounting + chunk ids, 3 key build + sort, 4 tie refinement,
@@ -146,6 +147,14 @@ int scb_stage_ms(const scb_handle *h, float *out, int32_t cap);
 int scb_reset_counts(scb_handle *h);
 /* Fixed-point rounds the parallel tie-break needed in the last flush (0 = sequential engine used). */
 int scb_resolve_rounds(const scb_handle *h);
+/* High-water mark of the flush workspace (bytes of device memory handed out by the handle's slab in one flush, inputs
+ * copied by scb_submit not included): what to size a flush against the GPU's memory with. */
+int64_t scb_device_bytes(const scb_handle *h);
+/* Which tie-break engine serves this core set (all are exact, aho_search's population compare, reads.cpp:420-421):
+ * 0 dense (per-warp population rows in shared memory, <= ~6.4k buckets), 1 sparse (bucket-major candidate lists in
+ * global memory, core sets of production size: the reference sizes patterns[] for 5-10 M cores, reads.cpp:336, 385),
+ * 2 sequential (one warp; jobs of >= 2^32 - 1 reads). The sharded run works with 0 and 1; scb_shard_resolve_joint with 0. */
+int scb_resolve_engine(const scb_handle *h);
 
 /* =====================================================================================================
  * Sharded run: ONE flush whose input is the concatenation of the ranks' submissions in rank order
@@ -166,7 +175,7 @@ int scb_resolve_rounds(const scb_handle *h);
  *   scb_shard_bucket_hist -> all-reduce -> split of the bucket emission order into contiguous slices
  *   scb_shard_pack -> all-to-all -> scb_shard_import
  *   scb_shard_finish                                 stable sort + emit of the owned bucket slice
- * Restrictions: the shared-memory resolve engine must apply (<= ~25k buckets). Every rank owns ALL
+ * Restrictions: fewer than 2^24 buckets. Every rank owns ALL
  * flush chunks of its buckets, so emit_merged works per rank.
  * ===================================================================================================== */
 

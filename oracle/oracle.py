@@ -60,6 +60,7 @@ def lib():
         L.orc_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_core_node_id.restype = C.c_int32
         L.orc_core_node_id.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_assign.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.orc_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -91,6 +92,16 @@ class Oracle:
         name_off = None if name_off is None else np.ascontiguousarray(name_off, dtype=np.int64)
         lib().orc_submit(self.h, n, _ptr(seq), _ptr(qual), _ptr(names), _ptr(name_off), _ptr(seq2), _ptr(qual2))
         self.n += n
+
+    def assign(self, seq, name_off):
+        """Streaming form: bucket id / core / end marker / flush chunk of the next reads, nothing retained (orc_assign).
+        Use on a fresh oracle; do not mix with submit()."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n = seq.shape[0]
+        name_off = None if name_off is None else np.ascontiguousarray(name_off, dtype=np.int64)
+        out = [np.empty(n, dtype=np.int32) for _ in range(4)]
+        lib().orc_assign(self.h, n, _ptr(seq), _ptr(name_off), *[_ptr(a) for a in out])
+        return dict(node_id=out[0], core=out[1], end=out[2], chunk=out[3])
 
     def finish(self):
         lib().orc_finish(self.h)

@@ -67,6 +67,7 @@ typedef struct orc {
     obuf seq1, qual1, seq2, qual2, names; int64_t *name_off; int64_t cap_off;
     /* flushed chunks: 6 streams each (0 names,1 reads,2 quals,3 meta,4 reads2,5 quals2) */
     obuf (*chunk)[6]; int n_chunks, cap_chunks;
+    int as_chunks;            /* flush chunks closed so far by orc_assign (no streams behind them) */
     /* merged result (compress.cpp:488-522) */
     obuf merged[6]; int merged_valid;
     /* per-read debug */
@@ -313,6 +314,30 @@ void orc_submit(orc *o, int64_t n, const uint8_t *seq1, const uint8_t *qual1, co
         o->dbg_node_id[r] = bucket == 0 ? ORC_MAXBIN - 1 : b->id; o->dbg_core[r] = b->output; o->dbg_end[r] = end; o->dbg_chunk[r] = o->n_chunks;
         o->total_size += (uint64_t)sz + ORC_BIN_NODE_BYTES;                       /* compress.cpp:702 */
         if (o->total_size >= o->bucket_set_bytes) { flush_chunk(o); o->total_size = 0; } /* compress.cpp:708-713 */
+    }
+    o->n_reads += n;
+}
+
+/* The same per-read driver reduced to what DECIDES bucket, end marker and flush chunk (aho_search reads.cpp:413-429, the
+ * rd.sz accounting and flush trigger compress.cpp:675-715, bin_size++ reads.cpp:246): no payload is kept and nothing is
+ * emitted, so inputs of any size can be streamed through in pieces (tests/test_gpu_fullsize.py: all 50 M reads of the bench
+ * workload). name_off[n+1] gives the name lengths (ignored without names). Use a fresh oracle: do not mix with orc_submit. */
+void orc_assign(orc *o, int64_t n, const uint8_t *seq1, const int64_t *name_off, int32_t *node_id, int32_t *core, int32_t *end_out,
+                int32_t *chunk) {
+    for (int64_t i = 0; i < n; i++) {
+        int32_t bucket;
+        int bp = aho_search(o, seq1 + (size_t)i * o->L1, o->L1, &bucket);
+        onode *b = &o->nd[bucket];
+        int32_t sz = o->use_names ? (int32_t)(name_off[i + 1] - name_off[i]) + 1 : 1;
+        int end;
+        if (bp != -1) { sz += SZ_READ(o->L1 - b->level); end = bp + 1; } else { sz += SZ_READ(o->L1); end = 0; }
+        if (o->use_quals) sz += o->L1;
+        if (o->paired) { sz += SZ_READ(o->L2); if (o->use_quals) sz += o->L2; }
+        b->bin_size++;
+        if (bucket == 0) o->unbucketed++;
+        node_id[i] = bucket == 0 ? ORC_MAXBIN - 1 : b->id; core[i] = b->output; end_out[i] = end; chunk[i] = o->as_chunks;
+        o->total_size += (uint64_t)sz + ORC_BIN_NODE_BYTES;
+        if (o->total_size >= o->bucket_set_bytes) { o->as_chunks++; o->total_size = 0; }
     }
     o->n_reads += n;
 }

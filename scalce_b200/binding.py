@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_reset_counts", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_reset_counts", "scb_destroy",
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
     "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", "scb_shard_finish_early", "scb_shard_joint_reserve", "scb_shard_resolve_joint",
@@ -89,6 +89,9 @@ def load_library(path: str | None = None):
     L.scb_kernel_launches.argtypes = [C.c_void_p]
     L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_resolve_rounds.argtypes = [C.c_void_p]
+    L.scb_resolve_engine.argtypes = [C.c_void_p]
+    L.scb_device_bytes.restype = C.c_int64
+    L.scb_device_bytes.argtypes = [C.c_void_p]
     L.scb_reset_counts.argtypes = [C.c_void_p]
     L.scb_destroy.argtypes = [C.c_void_p]
     L.scb_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -280,6 +283,16 @@ class BoostTransform:
     @property
     def resolve_rounds(self):
         return load_library().scb_resolve_rounds(self._h)
+
+    @property
+    def device_bytes(self):
+        """High-water mark of the flush workspace in bytes."""
+        return load_library().scb_device_bytes(self._h)
+
+    @property
+    def resolve_engine(self):
+        """0 dense (shared-memory population rows), 1 sparse (bucket-major candidate lists), 2 sequential."""
+        return load_library().scb_resolve_engine(self._h)
 
     @property
     def kernel_launches(self):

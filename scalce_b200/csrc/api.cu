@@ -2,6 +2,7 @@
 #include "../../include/scalce_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -15,6 +16,8 @@
 #include "resolve_dense.cuh"
 #include "scan_smem.cuh"
 #include "scan_smem2.cuh"
+#include "scan_big.cuh"
+#include "resolve_sparse.cuh"
 #include "emit2.cuh"
 #include "emit_offsets.cuh"
 #include "emit_coresident.cuh"
@@ -23,7 +26,7 @@
 #include "shard.cuh"
 
 namespace scb {
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 static thread_local std::string g_last_error;
 
 // Flush-scoped device memory: one slab (grown on demand, kept across flushes) with bump allocation.
@@ -33,6 +36,8 @@ struct Arena {
     struct Slab { char *p; size_t cap; };
     std::vector<Slab> slabs;
     size_t cur = 0, off = 0;
+    size_t peak = 0;            // high-water mark of the bytes handed out in one flush (scb_device_bytes)
+    size_t used() const { size_t u = off; for (size_t k = 0; k < cur && k < slabs.size(); k++) u += slabs[k].cap; return u; }
     void reset() { cur = 0; off = 0; }
     void reserve(size_t bytes) {   // make the first slab at least this large (only ever called between flushes)
         if (!slabs.empty() && slabs[0].cap >= bytes) return;
@@ -47,7 +52,7 @@ struct Arena {
         bytes = (bytes + 511) & ~(size_t)511;
         if (bytes == 0) bytes = 512;
         while (true) {
-            if (cur < slabs.size() && off + bytes <= slabs[cur].cap) { void *r = slabs[cur].p + off; off += bytes; return r; }
+            if (cur < slabs.size() && off + bytes <= slabs[cur].cap) { void *r = slabs[cur].p + off; off += bytes; if (used() > peak) peak = used(); return r; }
             if (cur + 1 < slabs.size()) { cur++; off = 0; continue; }
             Slab s{nullptr, std::max(bytes, (size_t)1 << 30)};
             SCB_CUDA(cudaMalloc((void **)&s.p, s.cap));
@@ -141,6 +146,8 @@ struct scb_handle {
     DevBuf d_next, d_nto, d_rank_level, d_rank_node_id, d_rank_core;
     DevBuf d_life, d_claim;
     DevBuf d_trans16, d_hit_rank;   // shared-memory form of the automaton (scan_smem.cuh)
+    DevBuf d_trans32, d_hit_info;   // global-memory form for automata beyond shared memory (scan_big.cuh)
+    bool big_table = false;
     int H0 = 0, n_hit = 0;
     size_t smem_table_bytes = 0;
     std::vector<Pending> pending;
@@ -174,6 +181,11 @@ struct scb_handle {
     int sh_W = 0, sh_grid = 0; // dense-resolve geometry
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
     DevBuf sh_stale, sh_nstale;   // deferred re-sweeps (resolve_dense_k<*, *, true>)
+    // sparse resolve engine (resolve_sparse.cuh): bucket-major view of the candidate pairs, built once per flush
+    int engine = 0;            // engine of the current flush: 0 dense, 1 sparse, 2 sequential
+    bool sp_ready = false;
+    int64_t sp_M = 0;
+    DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2;
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
@@ -241,16 +253,21 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         upload(h->d_rank_level, h->tab.rank_level, h->st);
         upload(h->d_rank_node_id, h->tab.rank_node_id, h->st);
         upload(h->d_rank_core, h->tab.rank_core, h->st);
-        {   // shared-memory form: states renumbered so that states where some core ends come last
+        {   // scan tables: states renumbered so that states where some core ends come last (one compare per base finds a hit)
             const CoreTable &t = h->tab;
             const int ns = t.n_states;
             size_t nhit = 0;
             for (int u = 0; u < ns; u++) nhit += t.nto_rank[u] >= 0;
-            size_t bytes = (size_t)ns * 8 + nhit * 4 + (size_t)t.n_buckets;
-            if (ns <= 16383 && bytes <= 160 * 1024) {   // u16 entries hold next-state * 4
-                std::vector<uint32_t> newid(ns);
+            std::vector<uint32_t> newid(ns);
+            {
                 uint32_t a = 0, b = (uint32_t)(ns - nhit);
                 for (int u = 0; u < ns; u++) newid[u] = t.nto_rank[u] >= 0 ? b++ : a++;
+            }
+            h->H0 = (int)(ns - nhit); h->n_hit = (int)nhit;
+            const size_t bytes = (size_t)ns * 8 + nhit * 4 + (size_t)t.n_buckets;
+            const char *tf = getenv("SCB_TABLE");         // "global": keep even a small automaton in global memory (tests of scan_big_k)
+            const bool force_global = tf && !strcmp(tf, "global");
+            if (ns <= 16383 && bytes <= 160 * 1024 && !force_global) {   // shared-memory form: u16 entries hold next-state * 4
                 std::vector<uint16_t> tr((size_t)ns * 4);
                 std::vector<uint32_t> hr(nhit);
                 for (int u = 0; u < ns; u++) {
@@ -259,8 +276,19 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
                 }
                 upload(h->d_trans16, tr, h->st);
                 upload(h->d_hit_rank, hr, h->st);
-                h->H0 = (int)(ns - nhit); h->n_hit = (int)nhit; h->smem_table_bytes = bytes;
+                h->smem_table_bytes = bytes;
                 h->smem_resident = true;
+            } else if (t.n_buckets < (1 << 24) && (uint64_t)ns < (1ull << 30)) {   // global-memory form: u32 next state, hit_info = rank | level << 24
+                std::vector<uint32_t> tr((size_t)ns * 4);
+                std::vector<uint32_t> hi(nhit);
+                for (int u = 0; u < ns; u++) {
+                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + c] = newid[t.next[(size_t)u * 4 + c]];
+                    if (t.nto_rank[u] >= 0) hi[newid[u] - (ns - nhit)] = (uint32_t)t.nto_rank[u] | ((uint32_t)t.rank_level[(size_t)t.nto_rank[u]] << 24);
+                }
+                upload(h->d_trans32, tr, h->st);
+                upload(h->d_hit_info, hi, h->st);
+                SCB_CUDA(cudaStreamSynchronize(h->st));   // the host vectors go out of scope
+                h->big_table = true;
             }
         }
         size_t nb1 = (size_t)h->tab.n_buckets + 1;
@@ -503,6 +531,7 @@ static void flush_begin(scb_handle *h, double extra_factor) {
         est = (size_t)((double)est * extra_factor);
         h->arena.reserve(est);
         h->arena.reset();
+        h->arena.peak = 0;
     }
     gather_pending(h);
     const Pending &c = h->cur;
@@ -568,6 +597,40 @@ static void stage_scan(scb_handle *h) {
             }
         }
     }
+    if (!scanned && h->big_table && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(getenv("SCB_SCAN") && !strcmp(getenv("SCB_SCAN"), "global"))) {
+        // automaton in global memory / L2 (scan_big.cuh): same warp-tile pipeline, as many warps per SM as the staging allows
+        const size_t budget = 227 * 1024 - 64;
+        const int PW = h->PW, pitch = scan_smem_pitch(PW);
+        const size_t per_warp = scan_big_warp_bytes(L1, PW);
+        const int W = (int)std::min<size_t>(32, budget / per_warp);
+        if (W >= 1) {
+            const size_t smem = (size_t)W * per_warp;
+            SCB_CUDA(cudaFuncSetAttribute(scan_big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int dev_sms = 0;
+            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+            DevBuf dtot(8, st);
+            const uint64_t holes = (uint64_t)dev_sms * W * kCandChunk;
+            uint64_t cap = std::max<uint64_t>((uint64_t)n * 12, 1u << 20) + holes;
+            for (int attempt = 0; attempt < 2 && !scanned; attempt++) {
+                h->cand_rank.alloc((size_t)cap * 4, st);
+                h->cand_pos.alloc((size_t)cap * 2, st);
+                SCB_CUDA(cudaMemsetAsync(dtot.p, 0, 8, st));
+                ScanBigParams bp;
+                bp.seq = c.seq1; bp.n = n; bp.L = L1; bp.trans = h->d_trans32.as<uint32_t>(); bp.hit_info = h->d_hit_info.as<uint32_t>();
+                bp.H0 = (uint32_t)h->H0;
+                bp.lvl = h->lvl.as<uint8_t>(); bp.ncand = h->ncand.as<uint16_t>(); bp.cand_off = h->cand_off.as<uint64_t>();
+                bp.cand_rank = h->cand_rank.as<uint32_t>(); bp.cand_pos = h->cand_pos.as<uint16_t>();
+                bp.cand_total = dtot.as<unsigned long long>(); bp.cand_cap = cap; bp.n_tiles = cdiv(n, 32);
+                bp.packed = h->packed.as<uint32_t>(); bp.PW = PW;
+                bp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); bp.pitch = pitch;
+                const int grid = (int)std::min<int64_t>(dev_sms, cdiv(bp.n_tiles, W));
+                SCB_LAUNCH(scan_big_k, grid, W * 32, smem, st, bp);
+                SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                if (M <= cap) scanned = true; else cap = M;
+            }
+        }
+    }
     if (!scanned) {
         if (n > 0)
             SCB_LAUNCH((scan_k<false>), (unsigned)cdiv(n, 128), 128, 0, st, c.seq1, n, L1, dfa, h->lvl.as<uint8_t>(),
@@ -587,6 +650,124 @@ static void stage_scan(scb_handle *h) {
 
 }
 
+// ---- which tie-break engine serves this core set -------------------------------------------------------------
+// dense (resolve_dense.cuh): per-warp population rows in shared memory, needs >= 4 warps' rows to fit (<= ~6.4k buckets);
+// sparse (resolve_sparse.cuh): bucket-major pair lists in global memory, any bucket count < 2^24;
+// sequential (resolve_seq_k): exact fallback with 64-bit counters (jobs of >= 2^32 - 1 reads), and the cross-check of the tests.
+// SCB_RESOLVE=dense|sparse|seq forces one (tests run every engine on the same inputs).
+enum { kEngDense = 0, kEngSparse = 1, kEngSeq = 2 };
+static int dense_warps(const scb_handle *h) {
+    const int nb1 = h->tab.n_buckets + 1;
+    const int P = (nb1 + 3) & ~3;
+    return (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)P * 8));
+}
+static int pick_engine(const scb_handle *h, uint64_t reads_in_job) {
+    const char *force = getenv("SCB_RESOLVE");
+    if (force && !strcmp(force, "seq")) return kEngSeq;
+    if (reads_in_job >= 0xffffffffull) return kEngSeq;
+    const int W = dense_warps(h);
+    const bool sparse_ok = h->tab.n_buckets + 1 < (1 << 24);
+    if (force && !strcmp(force, "sparse") && sparse_ok) return kEngSparse;
+    if (force && !strcmp(force, "dense") && W >= 1) return kEngDense;
+    if (W >= 4) return kEngDense;
+    return sparse_ok ? kEngSparse : (W >= 1 ? kEngDense : kEngSeq);
+}
+
+// ---- sparse resolve engine (resolve_sparse.cuh) ------------------------------------------------------------------
+// builds the bucket-major view of the candidate pairs of h->cur (once per flush)
+static void sparse_setup(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n;
+    const int nb1 = h->tab.n_buckets + 1;
+    h->sp_ready = false;
+    h->sh_sel.alloc((size_t)std::max<int64_t>(n, 1) * 2, st);
+    h->sh_base.alloc((size_t)nb1 * 4, st);
+    h->sp_base2.alloc((size_t)nb1 * 4, st);
+    h->sp_hist.alloc((size_t)(nb1 + 1) * 4, st);
+    h->sp_changed.alloc(4, st);
+    h->sh_tot.alloc((size_t)(nb1 + 1) * 4, st);
+    h->sp_doff.alloc((size_t)(n + 1) * 8, st);
+    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+    uint64_t M = 0;
+    exclusive_scan<uint64_t>(LoadAs<uint16_t, uint64_t>{h->ncand.as<uint16_t>()}, n, h->sp_doff.as<uint64_t>(), h->sp_doff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+    SCB_CUDA(cudaMemcpyAsync(&M, h->sp_doff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    if (M >= 0xffffffffull) throw CudaError{"more than 2^32-1 candidate pairs in one flush: flush fewer reads at a time"};
+    h->sp_M = (int64_t)M;
+    const int64_t M1 = std::max<int64_t>((int64_t)M, 1);
+    const int64_t tiles = cdiv(M1, kSpTile);
+    h->sp_sb.alloc((size_t)M1 * 4, st); h->sp_sread.alloc((size_t)M1 * 4, st); h->sp_sk.alloc((size_t)M1 * 2, st); h->sp_sval.alloc((size_t)M1 * 4, st);
+    h->sp_cnt.alloc((size_t)M1 * 4, st); h->sp_fbyte.alloc((size_t)(M1 / 8 + 16), st);
+    h->sp_tail.alloc((size_t)tiles * 4, st); h->sp_treset.alloc((size_t)tiles * 4, st); h->sp_X.alloc((size_t)tiles * 4, st);
+    // temporaries of the sort: carved after the mark and handed back when the sorted view exists
+    const Arena::Mark mk = h->arena.mark();
+    {
+        DevBuf k0((size_t)M1 * 8, st), k1((size_t)M1 * 8, st), v0((size_t)M1 * 4, st), v1((size_t)M1 * 4, st), pread((size_t)M1 * 4, st);
+        DevBuf hist((size_t)SortWs::hist_elems(M1) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(M1)) * 4, st);
+        if (n > 0)
+            SCB_LAUNCH(sp_pairs_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
+                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>());
+        if (M > 0) {
+            SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
+            uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
+            uint32_t *va = v0.as<uint32_t>(), *vb = v1.as<uint32_t>();
+            radix_sort_pairs(&ka, &va, &kb, &vb, (int64_t)M, 0, std::max(1, ceil_log2((uint64_t)nb1)), ws, st);
+            SCB_LAUNCH(sp_post_k, (unsigned)cdiv((int64_t)M, 256), 256, 0, st, (int64_t)M, ka, va, pread.as<uint32_t>(), h->sp_doff.as<uint64_t>(),
+                       h->sp_sb.as<uint32_t>(), h->sp_sread.as<uint32_t>(), h->sp_sk.as<uint16_t>());
+            SCB_CUDA(cudaMemcpyAsync(h->sp_sval.p, va, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (g_arena) h->arena.rewind(mk);   // stream order keeps later users of this space behind the kernels above
+    h->sp_ready = true;
+}
+
+// one round: counts of the current assignment from `base`, then every read re-decides. hist_mode: 0 none, 1 rebuild the local
+// bucket histogram (sp_hist), 2 update it by the changes. The changed count lands in sp_changed.
+static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
+    cudaStream_t st = h->st;
+    const int64_t n = h->cur.n, M = h->sp_M;
+    const int nb1 = h->tab.n_buckets + 1;
+    SCB_CUDA(cudaMemsetAsync(h->sp_changed.p, 0, 4, st));
+    if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
+    if (M == 0 || n == 0) return;
+    const int64_t tiles = cdiv(M, kSpTile);
+    SpRound r;
+    r.M = M; r.sb = h->sp_sb.as<uint32_t>(); r.sread = h->sp_sread.as<uint32_t>(); r.sval = h->sp_sval.as<uint32_t>(); r.sk = h->sp_sk.as<uint16_t>();
+    r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>(); r.tail = h->sp_tail.as<uint32_t>(); r.treset = h->sp_treset.as<uint32_t>();
+    SCB_LAUNCH(sp_flags_k, (unsigned)tiles, kSpThreads, 0, st, r);
+    SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, h->sp_tail.as<uint32_t>(), h->sp_treset.as<uint32_t>(), tiles, h->sp_X.as<uint32_t>());
+    SpCounts c;
+    c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>(); c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
+    SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
+    SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->sp_doff.as<uint64_t>(), h->sp_cnt.as<uint32_t>(),
+               h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_changed.as<uint32_t>(),
+               hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0);
+}
+
+// iterates the local reads to their fixed point from the populations in sh_base, then folds them in: sp_base2 = populations after
+static void sparse_local(scb_handle *h) {
+    cudaStream_t st = h->st;
+    const int64_t M = h->sp_M;
+    const int nb1 = h->tab.n_buckets + 1;
+    h->last_rounds = 0;
+    SCB_CUDA(cudaMemcpyAsync(h->sp_base2.p, h->sh_base.p, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
+    if (M == 0 || h->cur.n == 0) return;
+    while (true) {
+        sparse_round(h, h->sh_base.as<uint32_t>(), 0);
+        h->last_rounds++;
+        uint32_t chg = 0;
+        SCB_CUDA(cudaMemcpyAsync(&chg, h->sp_changed.p, 4, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        if (chg == 0) break;
+        if (h->last_rounds >= kRdMaxRounds) throw CudaError{"resolve: round cap hit"};
+    }
+    // the last round changed nothing: its flags and tile scan describe the final assignment
+    SpCounts c;
+    c.M = M; c.sb = h->sp_sb.as<uint32_t>(); c.sval = h->sp_sval.as<uint32_t>(); c.fbyte = h->sp_fbyte.as<uint8_t>(); c.X = h->sp_X.as<uint32_t>();
+    c.base = h->sh_base.as<uint32_t>(); c.cnt = nullptr; c.fold = h->sp_base2.as<uint32_t>();
+    SCB_LAUNCH(sp_counts_k, (unsigned)cdiv(M, kSpTile), kSpThreads, 0, st, c);
+}
+
 // ---- dense resolve engine (resolve_dense.cuh): geometry, buffers, launches --------------------------------
 // Buffers live in the flush arena and are kept in the handle so that a sharded run can launch the kernel
 // once per global round. Returns false when the engine does not apply (too many buckets for shared
@@ -596,9 +777,8 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     const int64_t n = h->cur.n;
     const int nb1 = h->tab.n_buckets + 1;
     const int P = (nb1 + 3) & ~3;   // row pitch: 128-bit rows
-    int W = (int)std::min<size_t>(kRdMaxWarps, (200 * 1024) / ((size_t)P * 8));
-    const char *force = getenv("SCB_RESOLVE");
-    if (!(W >= 1 && n > 0 && reads_in_job < 0xffffffffull && !(force && !strcmp(force, "seq")))) return false;
+    int W = dense_warps(h);
+    if (!(W >= 1 && n > 0 && reads_in_job < 0xffffffffull)) return false;
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
@@ -746,7 +926,16 @@ static void stage_resolve(scb_handle *h) {
     SCB_CUDA(cudaMemcpyAsync(&root_before, h->d_life.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
     bool dense_done = false;
     h->last_rounds = 0;
-    if (dense_setup(h, h->life_total + (uint64_t)n)) {
+    h->engine = n > 0 ? pick_engine(h, h->life_total + (uint64_t)n) : kEngSeq;
+    if (h->engine == kEngSparse) {
+        sparse_setup(h);
+        SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
+        sparse_local(h);
+        SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->sp_base2.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
+        dense_finalize(h);
+        dense_done = true;
+    }
+    if (h->engine == kEngDense && dense_setup(h, h->life_total + (uint64_t)n)) {
         const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40);
         SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
         if (dense_launch(h, 0, g0, dense_blocks(n, g0), nullptr) == 0) {
@@ -1145,9 +1334,15 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
     *chunk_out = chunk_in + (int32_t)o[0];
 }
 
+// the engine of a sharded run depends on the core set alone, so that every rank takes the same one
+static int shard_engine(scb_handle *h) {
+    const int e = pick_engine(h, 0);
+    if (e == kEngSeq) throw CudaError{"the sharded run needs the dense or the sparse resolve engine (SCB_RESOLVE=seq, or >= 2^24 buckets)"};
+    return e;
+}
 static void shard_need_dense(scb_handle *h) {
     if (!dense_setup(h, h->life_total + (uint64_t)h->cur.n))
-        throw CudaError{"the sharded run needs the shared-memory resolve engine (core set too large, or SCB_RESOLVE=seq)"};
+        throw CudaError{"the sharded run's dense resolve engine does not apply (more than 2^32-1 reads in one job?)"};
 }
 
 static void shard_resolve_local(scb_handle *h, uint32_t *tot_dev) {
@@ -1159,11 +1354,20 @@ static void shard_resolve_local(scb_handle *h, uint32_t *tot_dev) {
     if (n == 0) {
         SCB_CUDA(cudaMemsetAsync(tot_dev, 0, (size_t)(nb1 + 1) * 4, st));
     } else {
-        shard_need_dense(h);
-        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40);
-        SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
-        if (dense_launch(h, 0, g0, dense_blocks(n, g0), nullptr) != 0) throw CudaError{"resolve: round cap hit"};
-        SCB_LAUNCH(sub_life_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sh_base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb1, tot_dev);
+        h->engine = shard_engine(h);
+        if ((h->life_total + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
+        if (h->engine == kEngSparse) {
+            sparse_setup(h);
+            SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
+            sparse_local(h);
+            SCB_LAUNCH(sub_life_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sp_base2.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb1, tot_dev);
+        } else {
+            shard_need_dense(h);
+            const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40);
+            SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
+            if (dense_launch(h, 0, g0, dense_blocks(n, g0), nullptr) != 0) throw CudaError{"resolve: round cap hit"};
+            SCB_LAUNCH(sub_life_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sh_base.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb1, tot_dev);
+        }
     }
     tm.stop();
 }
@@ -1176,12 +1380,23 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
     if (n == 0) {
         SCB_CUDA(cudaMemsetAsync(tot_dev, 0, (size_t)(nb1 + 1) * 4, st));
     } else {
-        if (first) shard_need_dense(h);
+        if (first) h->engine = shard_engine(h);
         if ((h->life_total + (uint64_t)reads_before + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
-        SCB_LAUNCH(add_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), before_dev, nb1, h->sh_base.as<uint32_t>());
-        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40) + reads_before;
-        std::vector<int64_t> blk{0, n};
-        if (dense_launch(h, first ? 1 : 2, g0, blk, tot_dev) != 0) throw CudaError{"resolve: round cap hit"};
+        if (h->engine == kEngSparse) {
+            // one global round on the bucket-major pair lists: base = lifetime counts + the lower ranks' histograms under the
+            // current assignment; the local histogram follows the decisions (rebuilt in the first round, then kept by differences)
+            if (first) sparse_setup(h);
+            SCB_LAUNCH(add_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), before_dev, nb1, h->sh_base.as<uint32_t>());
+            sparse_round(h, h->sh_base.as<uint32_t>(), first ? 1 : 2);
+            SCB_LAUNCH(sp_copy_tot_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sp_hist.as<uint32_t>(), h->sp_changed.as<uint32_t>(), nb1, tot_dev);
+            h->last_rounds++;
+        } else {
+            if (first) shard_need_dense(h);
+            SCB_LAUNCH(add_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), before_dev, nb1, h->sh_base.as<uint32_t>());
+            const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40) + reads_before;
+            std::vector<int64_t> blk{0, n};
+            if (dense_launch(h, first ? 1 : 2, g0, blk, tot_dev) != 0) throw CudaError{"resolve: round cap hit"};
+        }
     }
     h->sh_ms = 0;   // asynchronous: the caller times the round loop on its stream
 }
@@ -1233,6 +1448,8 @@ static void shard_resolve_joint(scb_handle *h, int rank, int G, void *const *pee
         if (stat[0] != 0) throw CudaError{stat[0] == 2 ? "joint rounds: timed out waiting for another rank" : "joint rounds: round cap hit"};
         rounds = stat[1];
     } else {
+        if (shard_engine(h) != kEngDense) throw CudaError{"joint rounds in one kernel need the dense resolve engine (scb_resolve_engine)"};
+        h->engine = kEngDense;
         shard_need_dense(h);
         if ((h->life_total + (uint64_t)reads_before + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
         const int P = (nb1 + 3) & ~3;
@@ -1949,7 +2166,7 @@ int64_t scb_lifetime_count(scb_handle *h, int32_t core_idx) {
     return (int64_t)v;
 }
 
-int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches; }
+int64_t scb_kernel_launches(const scb_handle *) { return scb::g_launches.load(); }
 
 int scb_reset_counts(scb_handle *h) {
     if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
@@ -1964,6 +2181,10 @@ int scb_reset_counts(scb_handle *h) {
 }
 
 int scb_resolve_rounds(const scb_handle *h) { return h ? h->last_rounds : -1; }
+
+int64_t scb_device_bytes(const scb_handle *h) { return h ? (int64_t)h->arena.peak : -1; }
+
+int scb_resolve_engine(const scb_handle *h) { return h ? scb::pick_engine(h, h->life_total) : -1; }
 
 int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
     if (!h || !out) return SCB_EINVAL;

@@ -1,6 +1,7 @@
 // common.cuh - shared device/host helpers for the sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -20,7 +21,7 @@ struct CudaError {
     } while (0)
 
 // every kernel launch goes through this so scb_kernel_launches() is an honest count
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 #define SCB_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                            \
         auto _kfn = kernel;                                                                         \

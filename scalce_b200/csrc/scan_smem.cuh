@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
             const uint32_t *tw = (const uint32_t *)s_tile;
             uint32_t *gp = p.packed + tile * (int64_t)32 * PW;
             for (uint32_t t = l; t < nwords; t += 32) {
-                const uint32_t r = __umulhi(t, p.inv_pw), k = t - r * (uint32_t)PW;
+                const uint32_t r = PW == 1 ? t : __umulhi(t, p.inv_pw), k = t - r * (uint32_t)PW;   // ceil(2^32 / 1) does not fit 32 bits
                 const uint32_t b = r * (uint32_t)L + 16u * k;
                 const uint32_t *a = tw + (b >> 2);
                 const uint32_t sh = (b & 3u) * 8u;

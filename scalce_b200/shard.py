@@ -312,7 +312,8 @@ class ShardedTransform:
         self.early_emit = os.environ.get("SCB_SHARD_EARLY_EMIT", "0") not in ("", "0")
         # opt-in (SCB_SHARD_JOINT_KERNEL=1, must be the same on every rank; one process per GPU only): all joint tie-break
         # rounds inside one kernel per rank, histograms exchanged through peer memory instead of an all-gather per round
-        self.joint_kernel = os.environ.get("SCB_SHARD_JOINT_KERNEL", "0") not in ("", "0") and hasattr(comm, "map_buffer")
+        self.joint_kernel = (os.environ.get("SCB_SHARD_JOINT_KERNEL", "0") not in ("", "0") and hasattr(comm, "map_buffer")
+                             and transform.resolve_engine == 0)   # the in-kernel joint rounds exist for the dense engine only
         self.stats = {}
         self._keep = None
         if use_torch_stream:

@@ -170,3 +170,24 @@ def make_batch_cuda(n, L, seed=1, paired=False, L2=None, n_frac=0.001, high_entr
     out["names"] = names.reshape(-1)
     out["name_off"] = torch.arange(n + 1, device=device, dtype=torch.int64) * W
     return out
+
+
+def make_core_set(spec, seed=7):
+    """Seeded synthetic core set of any size, vectorised: spec = [(length, count)], distinct cores per length, in a
+    deterministic (shuffled) order. The reference's patterns.bin is missing from its checkout (.MISSING_LARGE_BLOBS); its
+    loader sizes the set for 5-10 M cores (reads.cpp:336, 385). Returns list[str]."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for ln, cnt in spec:
+        cnt = int(min(cnt, 4 ** ln))
+        have = np.zeros(0, dtype=np.uint64)
+        while have.size < cnt:
+            need = cnt - have.size
+            x = rng.integers(0, 4 ** ln, size=need + need // 4 + 64, dtype=np.uint64)
+            have = np.unique(np.concatenate([have, x]))
+        have = rng.permutation(have)[:cnt]
+        shifts = (2 * (ln - 1 - np.arange(ln))).astype(np.uint64)
+        codes = ((have[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+        txt = _BASES[codes]                                   # uint8 [cnt, ln]
+        out.extend(txt.view(f"S{ln}").ravel().astype(str).tolist())
+    return out

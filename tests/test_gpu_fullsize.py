@@ -69,7 +69,7 @@ def test_quality_and_name_streams_are_row_gathers(big):
 
 def test_emission_order(big):
     """chunk-major, then bucket node id ascending with the no-core bucket last (reads.cpp:466-499), then the
-    suffix key, then input order (stable radix sort, reads.cpp:547-634) - the last two on a 2M-read window."""
+    suffix key, then input order (stable radix sort, reads.cpp:547-634) - over the whole output, 2M-read windows."""
     import torch
     res = big["res"]
     perm = res.torch_view("perm").to(torch.int64)
@@ -83,8 +83,11 @@ def test_emission_order(big):
     assert res.n_chunks == int(chunk.max()) + 1
     # inside segments: key = s[end..L) padded with A, N -> A; ties by input index
     m = min(2_000_000, N_FULL)
-    for start in (0, max(0, N_FULL // 2 - m // 2), N_FULL - m):
-        idx = perm[start:start + m]
+    for start in range(0, N_FULL, m - 1):              # every output position: windows overlap by one read
+        if start + 1 >= N_FULL:
+            break
+        mm = min(m, N_FULL - start)
+        idx = perm[start:start + mm]
         rows = big["seq"].index_select(0, idx)
         code = torch.zeros_like(rows)
         lo = rows | 0x20
@@ -94,7 +97,7 @@ def test_emission_order(big):
         e = end[idx]
         pos = e[:, None] + torch.arange(L, device=rows.device)[None, :]
         key = torch.where(pos < L, torch.gather(code, 1, pos.clamp(max=L - 1)), torch.zeros_like(code))
-        same_seg = seg[start + 1:start + m] == seg[start:start + m - 1]
+        same_seg = seg[start + 1:start + mm] == seg[start:start + mm - 1]
         a, z = key[:-1], key[1:]
         diff = a != z
         has = diff.any(dim=1)
@@ -167,6 +170,28 @@ def test_prefix_of_the_big_run_equals_oracle_on_the_prefix(big):
         got = res.torch_view(k)[:m].cpu().numpy()
         bad = np.nonzero(d[k] != got)[0]
         assert bad.size == 0, f"{k} differs from the oracle at reads {bad[:5]}"
+
+
+def test_every_read_of_the_big_run_equals_the_oracle(big):
+    """ALL reads of the full-size run (not a prefix): bucket id, core, end marker and flush chunk against the oracle's
+    streaming form (orc_assign: aho_search + size accounting + bin_size++, reads.cpp:413-429, compress.cpp:673-715; the same
+    code path as the full oracle, tests/test_host_cpu.py) - this covers the late geometric blocks of the tie-break (12.5 M
+    and 25 M reads), their replay rounds and the u32 population counters. ~80 s of one host core at 50 M reads."""
+    from oracle import oracle as orc
+    res = big["res"]
+    o = orc.Oracle(big["cores"], L)
+    step = 2_500_000
+    nbad = 0
+    for s in range(0, N_FULL, step):
+        e = min(N_FULL, s + step)
+        seq = big["seq"][s:e].cpu().numpy()
+        off = big["name_off"][s:e + 1].cpu().numpy()
+        d = o.assign(seq, off)
+        for k in ("node_id", "core", "end", "chunk"):
+            got = res.torch_view(k)[s:e].cpu().numpy()
+            bad = np.nonzero(d[k] != got)[0]
+            assert bad.size == 0, f"{k} differs from the oracle at reads {bad[:5] + s}: oracle {d[k][bad[:5]]} cuda {got[bad[:5]]}"
+    assert o.unbucketed == big["tr"].unbucketed
 
 
 def test_rerun_is_deterministic(big):

@@ -553,3 +553,37 @@ def test_stream1_checker_against_the_oracle():
     bad = s1.clone()
     bad[len(bad) // 2] ^= 0x10
     assert not util.stream1_window_matches(bad, seq, perm, lv, end, 100, 0, b.n)
+
+
+def test_oracle_streaming_assign_equals_full_oracle():
+    """orc_assign (the payload-free form used to check all 50 M reads of the bench workload) gives the full oracle's per-read
+    arrays, fed in pieces, multi-chunk, with and without names."""
+    from tests import util
+    from oracle import oracle as orc
+    for use_names in (True, False):
+        cores, b, q1, q2, _ = util.make_case(30000, 100, seed=401)
+        o = util.run_oracle(cores, b, q1, q2, use_names=use_names, bucket_set_bytes=1 << 20)
+        want = o.debug()
+        assert o.n_chunks > 3
+        s = orc.Oracle(cores, 100, use_names=use_names, bucket_set_bytes=1 << 20)
+        got = {k: [] for k in want}
+        for a, z in ((0, 7), (7, 12001), (12001, 30000)):
+            d = s.assign(b.seq[a:z], b.name_off[a:z + 1] if use_names else None)
+            for k in got:
+                got[k].append(d[k])
+        for k in want:
+            assert np.array_equal(want[k], np.concatenate(got[k])), k
+        assert s.unbucketed == o.unbucketed
+
+
+def test_vectorised_core_set_generator():
+    from scalce_b200 import synth
+    from scalce_b200.binding import table_dryrun
+    spec = [(8, 300), (10, 5000), (13, 20000)]
+    c = synth.make_core_set(spec, seed=3)
+    assert len(c) == 25300 and len(set(c)) == 25300
+    assert [len(x) for x in c[:300]] == [8] * 300 and len(c[-1]) == 13 and set("".join(c[:50])) <= set("ACGT")
+    assert c == synth.make_core_set(spec, seed=3) and c != synth.make_core_set(spec, seed=4)
+    d = table_dryrun(c)
+    assert d["n_buckets"] == 25300
+    assert synth.make_core_set([(3, 1000)], seed=1).__len__() == 64      # capped at 4^length
