@@ -280,6 +280,29 @@ int scb_shard_finish(scb_handle *h, scb_result *out);
 /* Device milliseconds of the last scb_shard_* call (CUDA events on the handle's stream). */
 float scb_shard_last_ms(const scb_handle *h);
 
+/* =====================================================================================================
+ * The transform's two neighbours that SURVEY.md 8(f) ranks next, on the device.
+ * ===================================================================================================== */
+/* (f3) Bucket-record assembly of the .scalcer body, replacing the per-bucket loop of combine_and_compress_with_split
+ * (compress.cpp:345-384) for mate 1: for every non-empty bucket `int32 core, int64 n_reads` (n_reads = tR / record size,
+ * compress.cpp:371-376) followed by that bucket's packed reads + end markers - everything the reference writes to
+ * <out>_1.scalcer after its 16 header bytes (magic, _no_ac, read_length; compress.cpp:289-291), as ONE contiguous
+ * buffer. chunk = -1: from the merged streams of the last flush (emit_merged, or a single flush chunk); chunk >= 0: from
+ * that flush chunk's streams. *body_dev (may be NULL) receives a device pointer owned by the handle, valid until the next
+ * scb_assemble_reads / scb_destroy. scb_copy_assembled copies the body and/or the segment table (core index - SCB_ROOT_ID
+ * for the no-core bucket - and reads per bucket record) to host; any pointer may be NULL. */
+int scb_assemble_reads(scb_handle *h, int32_t chunk, const uint8_t **body_dev, int64_t *body_bytes, int64_t *n_segments);
+int scb_copy_assembled(scb_handle *h, void *dst, int64_t dst_bytes, int32_t *seg_core, int64_t *seg_reads);
+/* (f4) The decompress-side inverse (decompress.cpp:331-352): bucket-ordered packed reads -> the ASCII rows the
+ * decompressor writes, in stream order. stream: mate 0 = packed reads + end markers WITHOUT the inline bucket headers
+ * (stream 1 / the .scalcer body minus its 12-byte records); mate 1 = stream 4 (mate-2 reads: unrotated, no end marker).
+ * seg_core / seg_reads [n_segments]: core index and reads of every bucket record, in stream order (what the inline headers
+ * hold). quals (may be NULL): the quality payload in the same order, n x L bytes; where it is 0 the base becomes 'N'
+ * (decompress.cpp:350-351) and qual_out (may be NULL) receives payload + phred_offset. seq_out / qual_out: n x L bytes,
+ * row pitch L, no newlines. location: 0 = all pointers host, 1 = all device (on cfg.device). */
+int scb_inverse_reads(scb_handle *h, const uint8_t *stream, const int32_t *seg_core, const int64_t *seg_reads, int64_t n_segments, const uint8_t *quals,
+                      int32_t mate, int32_t phred_offset, int32_t location, uint8_t *seq_out, uint8_t *qual_out, int64_t *n_reads_out);
+
 /* aho_trie_free (reads.cpp:505-535). */
 void scb_destroy(scb_handle *h);
 

@@ -61,6 +61,8 @@ def lib():
         L.orc_core_node_id.restype = C.c_int32
         L.orc_core_node_id.argtypes = [C.c_void_p, C.c_int32]
         L.orc_assign.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.orc_inverse.restype = C.c_int64
+        L.orc_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -102,6 +104,18 @@ class Oracle:
         out = [np.empty(n, dtype=np.int32) for _ in range(4)]
         lib().orc_assign(self.h, n, _ptr(seq), _ptr(name_off), *[_ptr(a) for a in out])
         return dict(node_id=out[0], core=out[1], end=out[2], chunk=out[3])
+
+    def inverse(self, stream, seg_core, seg_reads, quals=None, phred=33):
+        """decompress.cpp:331-352 for mate 1: (stream 1 without inline headers, bucket table) -> ASCII rows (+ qualities)."""
+        stream = np.ascontiguousarray(np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else stream)
+        seg_core = np.ascontiguousarray(seg_core, dtype=np.int32); seg_reads = np.ascontiguousarray(seg_reads, dtype=np.int64)
+        n = int(seg_reads.sum())
+        q = None if quals is None else np.ascontiguousarray(np.frombuffer(quals, dtype=np.uint8) if isinstance(quals, (bytes, bytearray)) else quals)
+        seq = np.empty((max(n, 1), self.L1), dtype=np.uint8)
+        qo = None if q is None else np.empty((max(n, 1), self.L1), dtype=np.uint8)
+        got = lib().orc_inverse(self.h, _ptr(stream), _ptr(seg_core), _ptr(seg_reads), len(seg_core), _ptr(q), phred, _ptr(seq), _ptr(qo))
+        assert got == n
+        return seq[:n], (None if qo is None else qo[:n])
 
     def finish(self):
         lib().orc_finish(self.h)
@@ -199,6 +213,35 @@ def assemble_container(meta: bytes, names: bytes, reads: bytes, quals: bytes, co
         if use_names:
             fn += names[pn:pn + lN]; pn += lN
     return bytes(fn), bytes(fr), bytes(fq)
+
+
+def segments_from_meta(meta: bytes, cores, L, paired=False):
+    """(core index, reads) of every bucket record, as combine_and_compress_with_split derives them (compress.cpp:364-379)."""
+    nlen = 3 + 2 * int(paired)
+    rsz = 8 + 8 * nlen
+    sz_meta = 2 if L > 255 else 1
+    sc, sr = [], []
+    for o in range(0, len(meta), rsz):
+        _id, core = struct.unpack_from("<ii", meta, o)
+        lR = struct.unpack_from("<q", meta, o + 16)[0]
+        clen = 0 if core == MAXBIN - 1 else len(cores[core])
+        sc.append(core); sr.append(lR // ((L - clen + 3) // 4 + sz_meta))
+    return np.array(sc, dtype=np.int32), np.array(sr, dtype=np.int64)
+
+
+def split_reads_container(body: bytes, cores, L):
+    """.scalcer after its 16 header bytes -> (stream 1 without the inline records, seg_core, seg_reads): the walk the
+    decompressor does over the bucket headers (decompress.cpp:262-272)."""
+    sz_meta = 2 if L > 255 else 1
+    pos, parts, sc, sr = 0, [], [], []
+    while pos < len(body):
+        core, cnt = struct.unpack_from("<iq", body, pos)
+        pos += 12
+        clen = 0 if core == MAXBIN - 1 else len(cores[core])
+        nb = cnt * ((L - clen + 3) // 4 + sz_meta)
+        parts.append(body[pos:pos + nb]); pos += nb
+        sc.append(core); sr.append(cnt)
+    return b"".join(parts), np.array(sc, dtype=np.int32), np.array(sr, dtype=np.int64)
 
 
 def run_reference_cli(fastq1, out_prefix, cores_txt=None, *, paired=False, bucket="4G", raw=True, no_names=None,

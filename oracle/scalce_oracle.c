@@ -437,6 +437,38 @@ int orc_candidates(orc *o, const uint8_t *text, int L, int cap, int32_t *cand_co
     *level = best; return n;
 }
 
+/* ---- decompress-side inverse, decompress.cpp:331-352 (mate 1) -------------------------------------
+ * stream: packed reads + end markers in bucket order WITHOUT the inline bucket headers; seg_core / seg_reads: what the
+ * headers (decompress.cpp:262-272) carry. Rebuilds every read around its core, restores 'N' where the quality byte is 0
+ * and adds the phred offset back. Returns the number of reads written (rows of L1 bytes, no newline). */
+int64_t orc_inverse(orc *o, const uint8_t *stream, const int32_t *seg_core, const int64_t *seg_reads, int64_t nseg,
+                    const uint8_t *quals, int phred, uint8_t *seq_out, uint8_t *qual_out) {
+    static const char alphabet[] = "ACGT";
+    const int L = o->L1, sz_meta = L > 255 ? 2 : 1;
+    int64_t K = 0; size_t pos = 0;
+    for (int64_t s = 0; s < nseg; s++) {
+        int32_t core = seg_core[s];
+        int corlen = (core == ORC_MAXBIN - 1) ? 0 : (int)strlen(o->cores[core]);      /* decompress.cpp:268 */
+        for (int64_t r = 0; r < seg_reads[s]; r++, K++) {
+            const uint8_t *p = stream + pos; pos += (size_t)SZ_READ(L - corlen);          /* :332 */
+            int64_t end = 0; memcpy(&end, stream + pos, (size_t)sz_meta); pos += (size_t)sz_meta;   /* :335 */
+            uint8_t *l = seq_out + (size_t)K * L; int lc = 0;
+            if (end) {
+                for (int i = L - (int)end; i < L - corlen; i++) l[lc++] = (uint8_t)alphabet[p[i >> 2] >> ((~i & 3) << 1) & 3];   /* :337-339 */
+                for (int i = 0; i < corlen; i++) l[lc++] = (uint8_t)o->cores[core][i];                                         /* :340-341 */
+            }
+            for (int i = 0; i < L - (int)end; i++) l[lc++] = (uint8_t)alphabet[p[i >> 2] >> ((~i & 3) << 1) & 3];              /* :344-345 */
+            if (quals)
+                for (int i = 0; i < L; i++) {                                                                                   /* :348-352 */
+                    uint8_t q = quals[(size_t)K * L + i];
+                    if (!q) l[i] = 'N';
+                    if (qual_out) qual_out[(size_t)K * L + i] = (uint8_t)(q + phred);
+                }
+        }
+    }
+    return K;
+}
+
 void orc_destroy(orc *o) {
     if (!o) return;
     for (int32_t i = 0; i < o->n_nodes; i++) free(o->nd[i].bin);

@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_reset_counts", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_assemble_reads", "scb_copy_assembled", "scb_inverse_reads", "scb_reset_counts", "scb_destroy",
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
     "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", "scb_shard_finish_early", "scb_shard_joint_reserve", "scb_shard_resolve_joint",
@@ -90,6 +90,10 @@ def load_library(path: str | None = None):
     L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_resolve_rounds.argtypes = [C.c_void_p]
     L.scb_resolve_engine.argtypes = [C.c_void_p]
+    L.scb_assemble_reads.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.scb_copy_assembled.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.scb_inverse_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     L.scb_device_bytes.restype = C.c_int64
     L.scb_device_bytes.argtypes = [C.c_void_p]
     L.scb_reset_counts.argtypes = [C.c_void_p]
@@ -262,6 +266,34 @@ class BoostTransform:
         res = ScbResult()
         _check(load_library().scb_flush(self._h, C.byref(res)))
         return FlushResult(self, res)
+
+    def assemble_reads(self, chunk=-1):
+        """(f3) .scalcer body of mate 1 (bucket records + packed reads, compress.cpp:345-384) from the last flush, assembled on
+        the device. Returns (body bytes, seg_core int32 [n_seg], seg_reads int64 [n_seg])."""
+        L = load_library()
+        nb, ns = C.c_int64(), C.c_int64()
+        _check(L.scb_assemble_reads(self._h, chunk, None, C.byref(nb), C.byref(ns)))
+        body = np.empty(max(nb.value, 1), dtype=np.uint8)
+        sc = np.empty(max(ns.value, 1), dtype=np.int32); sr = np.empty(max(ns.value, 1), dtype=np.int64)
+        _check(L.scb_copy_assembled(self._h, body.ctypes.data_as(C.c_void_p), nb.value, sc.ctypes.data_as(C.c_void_p), sr.ctypes.data_as(C.c_void_p)))
+        return body[:nb.value].tobytes(), sc[:ns.value], sr[:ns.value]
+
+    def inverse_reads(self, stream, seg_core, seg_reads, quals=None, mate=0, phred_offset=33):
+        """(f4) decompress-side inverse on the device (decompress.cpp:331-352), host buffers in and out.
+        Returns (seq uint8 [n, L], qual uint8 [n, L] or None)."""
+        L = load_library()
+        Lr = self.cfg.read_length[1 if mate else 0]
+        stream = np.ascontiguousarray(np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else stream, dtype=np.uint8)
+        seg_core = np.ascontiguousarray(seg_core, dtype=np.int32); seg_reads = np.ascontiguousarray(seg_reads, dtype=np.int64)
+        n = int(seg_reads.sum())
+        seq = np.empty((max(n, 1), Lr), dtype=np.uint8)
+        q_in = None if quals is None else np.ascontiguousarray(np.frombuffer(quals, dtype=np.uint8) if isinstance(quals, (bytes, bytearray)) else quals, dtype=np.uint8)
+        q_out = None if quals is None else np.empty((max(n, 1), Lr), dtype=np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        nn = C.c_int64()
+        _check(L.scb_inverse_reads(self._h, p(stream), p(seg_core), p(seg_reads), len(seg_core), p(q_in), mate, phred_offset, 0, p(seq), p(q_out), C.byref(nn)))
+        assert nn.value == n
+        return seq[:n], (None if q_out is None else q_out[:n])
 
     @property
     def unbucketed(self):

@@ -24,6 +24,7 @@
 #include "emit_reads_fast.cuh"
 #include "emit_names_fast.cuh"
 #include "shard.cuh"
+#include "container.cuh"
 
 namespace scb {
 std::atomic<long long> g_launches{0};
@@ -147,6 +148,9 @@ struct scb_handle {
     DevBuf d_life, d_claim;
     DevBuf d_trans16, d_hit_rank;   // shared-memory form of the automaton (scan_smem.cuh)
     DevBuf d_trans32, d_hit_info;   // global-memory form for automata beyond shared memory (scan_big.cuh)
+    DevBuf d_core_len, d_core_off, d_core_chars;   // the core set by core index (container.cuh: bucket records, inverse)
+    DevBuf as_body, as_seg_core, as_seg_reads, as_seg_bytes, as_in_start;   // last scb_assemble_reads
+    int64_t as_bytes = 0, as_nseg = 0;
     bool big_table = false;
     int H0 = 0, n_hit = 0;
     size_t smem_table_bytes = 0;
@@ -185,7 +189,8 @@ struct scb_handle {
     int engine = 0;            // engine of the current flush: 0 dense, 1 sparse, 2 sequential
     bool sp_ready = false;
     int64_t sp_M = 0;
-    DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2;
+    DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev;
+    uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
@@ -253,6 +258,16 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         upload(h->d_rank_level, h->tab.rank_level, h->st);
         upload(h->d_rank_node_id, h->tab.rank_node_id, h->st);
         upload(h->d_rank_core, h->tab.rank_core, h->st);
+        {
+            std::vector<int32_t> cl; std::vector<uint64_t> co; std::vector<uint8_t> cc;
+            cl.reserve(h->tab.cores.size()); co.reserve(h->tab.cores.size() + 1);
+            for (auto &c : h->tab.cores) { cl.push_back((int32_t)c.size()); co.push_back((uint64_t)cc.size()); cc.insert(cc.end(), c.begin(), c.end()); }
+            co.push_back((uint64_t)cc.size());
+            if (cl.empty()) cl.push_back(0);
+            if (cc.empty()) cc.push_back(0);
+            upload(h->d_core_len, cl, h->st); upload(h->d_core_off, co, h->st); upload(h->d_core_chars, cc, h->st);
+            SCB_CUDA(cudaStreamSynchronize(h->st));
+        }
         {   // scan tables: states renumbered so that states where some core ends come last (one compare per base finds a hit)
             const CoreTable &t = h->tab;
             const int ns = t.n_states;
@@ -605,7 +620,14 @@ static void stage_scan(scb_handle *h) {
         const int W = (int)std::min<size_t>(32, budget / per_warp);
         if (W >= 1) {
             const size_t smem = (size_t)W * per_warp;
-            SCB_CUDA(cudaFuncSetAttribute(scan_big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // L2 policy hints of scan_big_k (bit 0 table evict_last, bit 1 tiles evict_first, bit 2 streaming stores); SCB_BIG_HINTS picks a set for A/B runs
+            const char *he = getenv("SCB_BIG_HINTS");
+            // bit 1 is off by default: LDGSTS with a cache-policy descriptor raised "illegal instruction" on the B200 (compute-sanitizer: the
+            // cp.async.cg ... L2::cache_hint in stage_warp_tile_stream), profiles/r02_scan_big_hints.txt
+            const int hints = he && *he ? atoi(he) & 7 : 5;
+            void (*kbig)(ScanBigParams) = hints == 0 ? scan_big_k<0> : hints == 1 ? scan_big_k<1> : hints == 2 ? scan_big_k<2> : hints == 3 ? scan_big_k<3> :
+                                          hints == 4 ? scan_big_k<4> : hints == 5 ? scan_big_k<5> : hints == 6 ? scan_big_k<6> : scan_big_k<7>;
+            SCB_CUDA(cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
             DevBuf dtot(8, st);
@@ -624,7 +646,7 @@ static void stage_scan(scb_handle *h) {
                 bp.packed = h->packed.as<uint32_t>(); bp.PW = PW;
                 bp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); bp.pitch = pitch;
                 const int grid = (int)std::min<int64_t>(dev_sms, cdiv(bp.n_tiles, W));
-                SCB_LAUNCH(scan_big_k, grid, W * 32, smem, st, bp);
+                SCB_LAUNCH(kbig, grid, W * 32, smem, st, bp);
                 SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
                 SCB_CUDA(cudaStreamSynchronize(st));
                 if (M <= cap) scanned = true; else cap = M;
@@ -685,6 +707,10 @@ static void sparse_setup(scb_handle *h) {
     h->sp_base2.alloc((size_t)nb1 * 4, st);
     h->sp_hist.alloc((size_t)(nb1 + 1) * 4, st);
     h->sp_changed.alloc(4, st);
+    h->sp_dirty.alloc((size_t)nb1 * 4, st);
+    h->sp_base_prev.alloc((size_t)nb1 * 4, st);
+    SCB_CUDA(cudaMemsetAsync(h->sp_dirty.p, 0, (size_t)nb1 * 4, st));        // every bucket is dirty in round 0
+    h->sp_round = 0;
     h->sh_tot.alloc((size_t)(nb1 + 1) * 4, st);
     h->sp_doff.alloc((size_t)(n + 1) * 8, st);
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
@@ -731,17 +757,24 @@ static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
     if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
     if (M == 0 || n == 0) return;
     const int64_t tiles = cdiv(M, kSpTile);
+    const uint32_t round = h->sp_round++;
+    if (hist_mode != 0) {   // sharded rounds: `base` moves between rounds; buckets whose value moved are dirty (round 0: all are anyway)
+        if (round == 0) SCB_CUDA(cudaMemcpyAsync(h->sp_base_prev.p, base, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
+        else SCB_LAUNCH(sp_mark_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base, h->sp_base_prev.as<uint32_t>(), nb1, h->sp_dirty.as<uint32_t>(), round);
+    }
     SpRound r;
+    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round;
     r.M = M; r.sb = h->sp_sb.as<uint32_t>(); r.sread = h->sp_sread.as<uint32_t>(); r.sval = h->sp_sval.as<uint32_t>(); r.sk = h->sp_sk.as<uint16_t>();
     r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>(); r.tail = h->sp_tail.as<uint32_t>(); r.treset = h->sp_treset.as<uint32_t>();
     SCB_LAUNCH(sp_flags_k, (unsigned)tiles, kSpThreads, 0, st, r);
     SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, h->sp_tail.as<uint32_t>(), h->sp_treset.as<uint32_t>(), tiles, h->sp_X.as<uint32_t>());
     SpCounts c;
     c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>(); c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
+    c.dirty = r.dirty; c.round = round;
     SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
     SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->sp_doff.as<uint64_t>(), h->sp_cnt.as<uint32_t>(),
                h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_changed.as<uint32_t>(),
-               hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0);
+               hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0, h->sp_dirty.as<uint32_t>(), round + 1);
 }
 
 // iterates the local reads to their fixed point from the populations in sh_base, then folds them in: sp_base2 = populations after
@@ -765,6 +798,7 @@ static void sparse_local(scb_handle *h) {
     SpCounts c;
     c.M = M; c.sb = h->sp_sb.as<uint32_t>(); c.sval = h->sp_sval.as<uint32_t>(); c.fbyte = h->sp_fbyte.as<uint8_t>(); c.X = h->sp_X.as<uint32_t>();
     c.base = h->sh_base.as<uint32_t>(); c.cnt = nullptr; c.fold = h->sp_base2.as<uint32_t>();
+    c.dirty = h->sp_dirty.as<uint32_t>(); c.round = h->sp_round;
     SCB_LAUNCH(sp_counts_k, (unsigned)cdiv(M, kSpTile), kSpThreads, 0, st, c);
 }
 
@@ -1773,6 +1807,103 @@ static void fill_result(scb_handle *h, scb_result *out) {
     out->perm = h->perm.as<uint32_t>();
 }
 
+// ---- (f3) .scalcer body from merged meta + stream 1; (f4) the inverse (container.cuh) -----------------------------------
+static void segment_table(scb_handle *h, const uint8_t *meta_dev, int64_t nseg, DevBuf &seg_core, DevBuf &seg_reads, DevBuf &seg_bytes, DevBuf &in_start) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0];
+    const int rsz = 8 + 8 * (3 + 2 * cfg.paired);
+    const int64_t n1 = std::max<int64_t>(nseg, 1);
+    seg_core.alloc((size_t)n1 * 4, st); seg_reads.alloc((size_t)n1 * 8, st); seg_bytes.alloc((size_t)n1 * 8, st); in_start.alloc((size_t)(n1 + 1) * 8, st);
+    if (nseg > 0)
+        SCB_LAUNCH(ct_segments_k, (unsigned)cdiv(nseg, 256), 256, 0, st, MetaRecs{meta_dev, rsz}, nseg, h->d_core_len.as<int32_t>(), L1, L1 > 255 ? 2 : 1,
+                   seg_core.as<int32_t>(), seg_reads.as<int64_t>(), seg_bytes.as<int64_t>());
+    DevBuf ws64((size_t)scan_tiles(nseg) * 8, st);
+    exclusive_scan<uint64_t>(SegBytes{seg_bytes.as<int64_t>()}, nseg, in_start.as<uint64_t>(), in_start.as<uint64_t>() + nseg, ws64.as<uint64_t>(), st);
+}
+
+static void assemble_reads(scb_handle *h, int chunk) {
+    cudaStream_t st = h->st;
+    const int rsz = 8 + 8 * (3 + 2 * h->cfg.paired);
+    const uint8_t *s1, *meta; int64_t b1, bm;
+    if (chunk < 0) {
+        const EmitOut &m = (h->n_chunks > 1) ? h->merged : h->chunked;
+        s1 = m.data[1].as<uint8_t>(); b1 = m.size[1]; meta = m.data[3].as<uint8_t>(); bm = m.size[3];
+    } else {
+        const auto &c1 = h->chunked.chunk_off[1], &c3 = h->chunked.chunk_off[3];
+        s1 = h->chunked.data[1].as<uint8_t>() + c1[(size_t)chunk]; b1 = c1[(size_t)chunk + 1] - c1[(size_t)chunk];
+        meta = h->chunked.data[3].as<uint8_t>() + c3[(size_t)chunk]; bm = c3[(size_t)chunk + 1] - c3[(size_t)chunk];
+    }
+    const int64_t nseg = bm / rsz;
+    segment_table(h, meta, nseg, h->as_seg_core, h->as_seg_reads, h->as_seg_bytes, h->as_in_start);
+    const int64_t body = b1 + 12 * nseg;
+    h->as_body.alloc((size_t)body + 16, st);
+    if (body > 0)
+        SCB_LAUNCH(ct_assemble_k, (unsigned)cdiv(cdiv(body, 16), 256), 256, 0, st, s1, h->as_in_start.as<uint64_t>(), nseg, h->as_seg_core.as<int32_t>(),
+                   h->as_seg_reads.as<int64_t>(), h->as_body.as<uint8_t>(), body);
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->as_bytes = body; h->as_nseg = nseg;
+}
+
+static void inverse_reads(scb_handle *h, const uint8_t *stream, const int32_t *seg_core, const int64_t *seg_reads, int64_t nseg, const uint8_t *quals,
+                          int mate, int phred, int location, uint8_t *seq_out, uint8_t *qual_out, int64_t *n_out) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L = cfg.read_length[mate ? 1 : 0];
+    const int sz_meta = cfg.read_length[0] > 255 ? 2 : 1;
+    const int64_t n1 = std::max<int64_t>(nseg, 1);
+    // the segment table is small: always staged through the host (it is what the container's inline headers hold)
+    std::vector<int32_t> hc((size_t)n1, 0); std::vector<int64_t> hr((size_t)n1, 0);
+    if (nseg > 0) {
+        if (location == 1) {
+            SCB_CUDA(cudaMemcpyAsync(hc.data(), seg_core, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(hr.data(), seg_reads, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+        } else { memcpy(hc.data(), seg_core, (size_t)nseg * 4); memcpy(hr.data(), seg_reads, (size_t)nseg * 8); }
+    }
+    std::vector<uint64_t> in_start((size_t)n1 + 1, 0), read_start((size_t)n1 + 1, 0);
+    const int32_t ncores = (int32_t)h->tab.cores.size();
+    for (int64_t s2 = 0; s2 < nseg; s2++) {
+        const int32_t c = hc[(size_t)s2];
+        if (c != SCB_ROOT_ID && (c < 0 || c >= ncores)) throw CudaError{"inverse: core index out of range in the segment table"};
+        if (hr[(size_t)s2] < 0) throw CudaError{"inverse: negative read count in the segment table"};
+        const int lv = c == SCB_ROOT_ID ? 0 : (int)h->tab.cores[(size_t)c].size();
+        read_start[(size_t)s2 + 1] = read_start[(size_t)s2] + (uint64_t)hr[(size_t)s2];
+        in_start[(size_t)s2 + 1] = in_start[(size_t)s2] + (uint64_t)hr[(size_t)s2] * (uint64_t)(sz_read(cfg.read_length[0] - lv) + sz_meta);
+    }
+    const int64_t n = (int64_t)read_start[(size_t)nseg];
+    *n_out = n;
+    if (n == 0) return;
+    const int64_t sbytes = mate ? n * sz_read(L) : (int64_t)in_start[(size_t)nseg];
+    DevBuf d_stream, d_quals, d_seq, d_qual, d_core, d_is, d_rs;
+    const uint8_t *ps = stream, *pq = quals;
+    uint8_t *po = seq_out, *pqo = qual_out;
+    if (location == 0) {
+        d_stream.alloc((size_t)sbytes + 16, st);
+        SCB_CUDA(cudaMemcpyAsync(d_stream.p, stream, (size_t)sbytes, cudaMemcpyHostToDevice, st));
+        ps = d_stream.as<uint8_t>();
+        if (quals) { d_quals.alloc((size_t)n * L, st); SCB_CUDA(cudaMemcpyAsync(d_quals.p, quals, (size_t)n * L, cudaMemcpyHostToDevice, st)); pq = d_quals.as<uint8_t>(); }
+        d_seq.alloc((size_t)n * L, st); po = d_seq.as<uint8_t>();
+        if (quals && qual_out) { d_qual.alloc((size_t)n * L, st); pqo = d_qual.as<uint8_t>(); }
+    }
+    if (!quals) pqo = nullptr;
+    if (mate) {
+        SCB_LAUNCH(ct_inverse2_k, (unsigned)cdiv(n * ((L + 15) / 16), 256), 256, 0, st, ps, n, L, pq, phred, po, pqo);
+    } else {
+        upload(d_core, hc, st); upload(d_is, in_start, st); upload(d_rs, read_start, st);
+        InvParams ip;
+        ip.stream1 = ps; ip.in_start = d_is.as<uint64_t>(); ip.read_start = d_rs.as<uint64_t>(); ip.seg_core = d_core.as<int32_t>();
+        ip.core_len = h->d_core_len.as<int32_t>(); ip.core_off = h->d_core_off.as<uint64_t>(); ip.core_chars = h->d_core_chars.as<uint8_t>();
+        ip.nseg = nseg; ip.n = n; ip.L = L; ip.sz_meta = sz_meta; ip.quals = pq; ip.phred = phred; ip.seq_out = po; ip.qual_out = pqo;
+        SCB_LAUNCH(ct_inverse_k, (unsigned)cdiv(n * ((L + 15) / 16), 256), 256, 0, st, ip);
+    }
+    if (location == 0) {
+        SCB_CUDA(cudaMemcpyAsync(seq_out, po, (size_t)n * L, cudaMemcpyDeviceToHost, st));
+        if (pqo) SCB_CUDA(cudaMemcpyAsync(qual_out, pqo, (size_t)n * L, cudaMemcpyDeviceToHost, st));
+    }
+    SCB_CUDA(cudaStreamSynchronize(st));
+}
+
 }  // namespace scb
 
 // =====================================================================================================
@@ -2190,6 +2321,45 @@ int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
     if (!h || !out) return SCB_EINVAL;
     for (int k = 0; k < SCB_N_STAGES && k < cap; k++) out[k] = h->stage_ms[k];
     return SCB_N_STAGES;
+}
+
+int scb_assemble_reads(scb_handle *h, int32_t chunk, const uint8_t **body_dev, int64_t *body_bytes, int64_t *n_segments) {
+    if (!h || !body_bytes) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    if (chunk < 0 && !h->cfg.emit_merged && h->n_chunks > 1) { scb::g_last_error = "merged output was not requested (emit_merged = 0)"; return SCB_ESTATE; }
+    if (chunk >= h->n_chunks && !(chunk == 0 && h->n_chunks == 0)) { scb::g_last_error = "chunk out of range"; return SCB_EINVAL; }
+    if (h->chunked.chunk_off[1].empty()) { scb::g_last_error = "nothing was flushed yet"; return SCB_ESTATE; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::assemble_reads(h, chunk);
+    SCB_CATCH
+    if (body_dev) *body_dev = h->as_body.as<uint8_t>();
+    *body_bytes = h->as_bytes;
+    if (n_segments) *n_segments = h->as_nseg;
+    return SCB_OK;
+}
+
+int scb_copy_assembled(scb_handle *h, void *dst, int64_t dst_bytes, int32_t *seg_core, int64_t *seg_reads) {
+    if (!h) { scb::g_last_error = "null handle"; return SCB_EINVAL; }
+    if (dst && dst_bytes < h->as_bytes) { scb::g_last_error = "destination too small"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    if (dst && h->as_bytes > 0) SCB_CUDA(cudaMemcpyAsync(dst, h->as_body.p, (size_t)h->as_bytes, cudaMemcpyDeviceToHost, h->st));
+    if (seg_core && h->as_nseg > 0) SCB_CUDA(cudaMemcpyAsync(seg_core, h->as_seg_core.p, (size_t)h->as_nseg * 4, cudaMemcpyDeviceToHost, h->st));
+    if (seg_reads && h->as_nseg > 0) SCB_CUDA(cudaMemcpyAsync(seg_reads, h->as_seg_reads.p, (size_t)h->as_nseg * 8, cudaMemcpyDeviceToHost, h->st));
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    SCB_CATCH
+    return SCB_OK;
+}
+
+int scb_inverse_reads(scb_handle *h, const uint8_t *stream, const int32_t *seg_core, const int64_t *seg_reads, int64_t n_segments, const uint8_t *quals,
+                      int32_t mate, int32_t phred_offset, int32_t location, uint8_t *seq_out, uint8_t *qual_out, int64_t *n_reads_out) {
+    if (!h || !n_reads_out || n_segments < 0 || (n_segments > 0 && (!stream || !seg_core || !seg_reads || !seq_out)) || (mate != 0 && mate != 1) ||
+        (location != 0 && location != 1) || (mate == 1 && !h->cfg.paired)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::inverse_reads(h, stream, seg_core, seg_reads, n_segments, quals, mate, phred_offset, location, seq_out, qual_out, n_reads_out);
+    SCB_CATCH
+    return SCB_OK;
 }
 
 void scb_destroy(scb_handle *h) {

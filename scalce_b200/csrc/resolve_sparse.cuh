@@ -12,7 +12,10 @@
 // One round = flags + per-tile tails (sp_flags_k) -> segmented scan of the tile tails (sp_tilescan_k) ->
 // per-pair counts scattered back to read-major order (sp_counts_k) -> every read re-decides (sp_decide_k).
 // A round that changes nothing proves the assignment is the sequential one. All kernels stream; the two random
-// accesses per pair and round (flag gather, count scatter) are what bounds a round.
+// accesses per pair (flag gather, count scatter) are what a round costs, so they are only made for DIRTY buckets: a
+// bucket whose flags changed in the previous round, or whose population before the local reads changed (sharded
+// rounds). In a clean bucket neither the flags nor the counts its pairs see can have changed, and the set of dirty
+// buckets roughly halves per round (measured on the CPU model: 28 %, 14 %, 7 %, ... of the pairs).
 // The same round serves the sharded run (one global round per call, populations of the lower ranks supplied by
 // the caller) - include/scalce_b200.h "Sharded run".
 #pragma once
@@ -97,6 +100,8 @@ struct SpRound {
     const uint16_t *sel;
     uint8_t *fbyte;                  // [ceil(M / 8)] flags of 8 consecutive sorted pairs
     uint32_t *tail, *treset;         // [tiles]
+    const uint32_t *dirty;           // [nb1] round stamp: bucket b is dirty in round r iff dirty[b] == r (all zero before round 0)
+    uint32_t round;
 };
 
 // flags of the current assignment + per tile: flags in the tile's trailing segment, and whether that segment starts
@@ -115,13 +120,19 @@ __global__ void __launch_bounds__(kSpThreads) sp_flags_k(SpRound p) {
         kk[j] = ok ? (uint32_t)p.sk[base + j] : 0x10000u;    // never equals a slot
         b[j] = ok ? p.sb[base + j] : 0xffffffffu;
     }
+    // only pairs of dirty buckets look their read's selection up again (the random access of this kernel); the others keep
+    // the flag of the round before
+    uint32_t dm = 0;
+#pragma unroll
+    for (int j = 0; j < kSpItems; j++) dm |= ((base + j < p.M) && p.dirty[b[j] & kSpRankMask] == p.round) ? (1u << j) : 0u;
+    const uint32_t oldbits = (base < p.M && dm != 0xffu) ? (uint32_t)p.fbyte[base >> 3] : 0u;
     uint32_t s[kSpItems];
 #pragma unroll
-    for (int j = 0; j < kSpItems; j++) s[j] = (base + j < p.M) ? (uint32_t)p.sel[rd[j]] : 0x20000u;   // independent random 2-byte loads
+    for (int j = 0; j < kSpItems; j++) s[j] = ((dm >> j) & 1u) ? (uint32_t)p.sel[rd[j]] : 0x20000u;   // independent random 2-byte loads
     uint32_t bits = 0, cl = 0;
 #pragma unroll
     for (int j = 0; j < kSpItems; j++) {
-        const uint32_t f = s[j] == kk[j] ? 1u : 0u;
+        const uint32_t f = ((dm >> j) & 1u) ? (s[j] == kk[j] ? 1u : 0u) : ((oldbits >> j) & 1u);
         bits |= f << j;
         cl += (f && b[j] == klast) ? 1u : 0u;
     }
@@ -164,6 +175,7 @@ struct SpCounts {
     const uint32_t *base;            // [nb1] populations before the local reads
     uint32_t *cnt;                   // [M] read-major: what pair p sees
     uint32_t *fold;                  // != null: instead of scattering counts, write base + segment total at every segment end
+    const uint32_t *dirty; uint32_t round;   // counts are only scattered for dirty buckets (see SpRound)
 };
 
 __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
         const uint32_t c = p.base[b[j] & kSpRankMask] + ex[j] + (((lead >> j) & 1u) ? pre : 0u);
         if (p.fold) {
             if (b[j + 1] != b[j]) p.fold[b[j] & kSpRankMask] = c + ((bits >> j) & 1u);    // last pair of its bucket: every bucket at most once
-        } else {
+        } else if (p.dirty[b[j] & kSpRankMask] == p.round) {
             p.cnt[p.sval[base + j]] = c;
         }
     }
@@ -209,7 +221,8 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
 __global__ void __launch_bounds__(256) sp_decide_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ doff,
                                                    const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ cand_off,
                                                    const uint32_t *__restrict__ cand_rank, uint16_t *__restrict__ sel,
-                                                   uint32_t *__restrict__ changed, uint32_t *__restrict__ hist, int full) {
+                                                   uint32_t *__restrict__ changed, uint32_t *__restrict__ hist, int full,
+                                                   uint32_t *__restrict__ dirty, uint32_t next_round) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t chg = 0;
     if (i < n) {
@@ -222,9 +235,13 @@ __global__ void __launch_bounds__(256) sp_decide_k(int64_t n, const uint16_t *__
                 if (c > bc) { bc = c; bk = k; }
             }
             const int old = sel[i];
-            if (bk != old) { sel[i] = (uint16_t)bk; chg = 1; }
+            const uint64_t src = cand_off[i];
+            if (bk != old) {
+                sel[i] = (uint16_t)bk; chg = 1;
+                dirty[cand_rank[src + old]] = next_round;      // both buckets' flags changed (plain stores: every writer stores the same value)
+                dirty[cand_rank[src + bk]] = next_round;
+            }
             if (hist) {
-                const uint64_t src = cand_off[i];
                 if (full) atomicAdd(&hist[cand_rank[src + bk]], 1u);
                 else if (chg) { atomicSub(&hist[cand_rank[src + old]], 1u); atomicAdd(&hist[cand_rank[src + bk]], 1u); }
             }
@@ -232,6 +249,14 @@ __global__ void __launch_bounds__(256) sp_decide_k(int64_t n, const uint16_t *__
     }
     chg = __reduce_add_sync(0xffffffffu, chg);
     if (lane_id() == 0 && chg) atomicAdd(changed, chg);
+}
+
+// sharded rounds: the populations before the local reads change from round to round; a bucket whose value moved is dirty
+__global__ void sp_mark_base_k(const uint32_t *__restrict__ base, uint32_t *__restrict__ base_prev, int nb1, uint32_t *__restrict__ dirty, uint32_t round) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb1) return;
+    const uint32_t v = base[i];
+    if (v != base_prev[i]) { base_prev[i] = v; dirty[i] = round; }
 }
 
 __global__ void sp_copy_tot_k(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ changed, int nb1, uint32_t *__restrict__ tot) {

@@ -39,13 +39,56 @@ __host__ __device__ inline size_t scan_big_warp_bytes(int L, int PW) {
     return ((tile + pk + q + hm) + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t *p) {
+// L2 residency is what this kernel lives on: the transition table (tens of MB) is re-read 150 times per read while 7.5 GB of
+// ASCII, 2 GB of packed rows and the candidate lists stream through the same L2 once. Without hints the streams evict the
+// table (first B200 run: 48 G lookups/s = ~3 TB/s of 64-byte DRAM fetches, i.e. the table was served by HBM, not by L2).
+// So: table loads carry an evict_last policy, the ASCII tiles an evict_first policy, and the kernel's stores are streaming
+// (st.global.cs).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t *p, uint64_t pol) {
     uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, uint64_t pol) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol));
+}
+// stage_warp_tile (scan_smem.cuh) with the evict_first policy on the tile's 16-byte copies
+__device__ __forceinline__ void stage_warp_tile_stream(const uint8_t *seq, int64_t n, int L, int64_t tile, uint8_t *buf, uint64_t pol) {
+    const int64_t row0 = tile * 32;
+    int64_t rows = n - row0;
+    if (rows > 32) rows = 32;
+    if (rows <= 0) return;
+    const int bytes = (int)rows * L;
+    const uint8_t *src = seq + row0 * L;
+    const int n16 = bytes >> 4;
+    if (pol) { for (int k = lane_id(); k < n16; k += 32) cp_async16_hint(buf + (k << 4), src + ((int64_t)k << 4), pol); }
+    else { for (int k = lane_id(); k < n16; k += 32) cp_async16(buf + (k << 4), src + ((int64_t)k << 4)); }
+    for (int k = (n16 << 4) + lane_id(); k < bytes; k += 32) buf[k] = src[k];
+}
+template <int HINTS>
+__device__ __forceinline__ uint32_t big_ld(const uint32_t *p, uint64_t pol) {
+    if (HINTS & 1) return ldg_nc_u32(p, pol);
+    return __ldg(p);
+}
+template <int HINTS, typename T>
+__device__ __forceinline__ void big_st(T *p, T v) {
+    if (HINTS & 4) __stcs(p, v); else *p = v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(saddr), "r"(v) : "memory"); }
 
+// HINTS bit 0: evict_last policy on the table loads; bit 1: evict_first policy on the ASCII tile copies; bit 2: streaming stores
+template <int HINTS>
 __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
     extern __shared__ __align__(16) uint8_t sm[];
     // layout per warp: ASCII tile (+32) | packed tile | hit queues (u32) | hit masks
@@ -64,13 +107,11 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
     const uint32_t *__restrict__ tr = p.trans;
     uint64_t c_cur = 0, c_end = 0;
 
-    // stage_warp_tile takes the shared-memory kernels' parameter block: only seq / n / L are read
-    ScanSmemParams sp;
-    sp.seq = p.seq; sp.n = p.n; sp.L = p.L;
+    const uint64_t pol_keep = (HINTS & 1) ? l2_policy_evict_last() : 0ull, pol_stream = (HINTS & 2) ? l2_policy_evict_first() : 0ull;
 
     const int64_t stride = (int64_t)gridDim.x * W;
     int64_t tile = (int64_t)w * gridDim.x + blockIdx.x;
-    if (tile < p.n_tiles) stage_warp_tile(sp, tile, s_tile);
+    if (tile < p.n_tiles) stage_warp_tile_stream(p.seq, p.n, L, tile, s_tile, pol_stream);
     cp_async_commit();
     for (; tile < p.n_tiles; tile += stride) {
         cp_async_wait<0>();
@@ -95,13 +136,13 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
                 const int nv = L - 16 * (int)k;
                 if (nv < 16) wv &= ~(0xffffffffu >> (2 * nv));
                 s_pk[r * (uint32_t)pitch + k] = wv;
-                gp[t] = wv;
+                big_st<HINTS>(gp + t, wv);
             }
         }
         __syncwarp();
         {
             const int64_t nxt = tile + stride;
-            if (nxt < p.n_tiles) stage_warp_tile(sp, nxt, s_tile);
+            if (nxt < p.n_tiles) stage_warp_tile_stream(p.seq, p.n, L, nxt, s_tile, pol_stream);
             cp_async_commit();
         }
         // ---- B: walk, one L2 lookup per base ---------------------------------------------------------------
@@ -119,7 +160,7 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const uint32_t c = (wv >> (30 - 2 * j)) & 3u;
-                    e = ldg_nc_u32(tr + ((size_t)e * 4u + c));
+                    e = big_ld<HINTS>(tr + ((size_t)e * 4u + c), pol_keep);
                     if (e >= H0) { m |= 1u << j; sts_u32(qp, e); qp += 4; }
                 }
                 hm[k] = (uint16_t)m;
@@ -133,7 +174,7 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
                     for (int j = 0; j < 15; j++) {
                         if (j >= tail) break;
                         const uint32_t c = (wv >> (30 - 2 * j)) & 3u;
-                        e = ldg_nc_u32(tr + ((size_t)e * 4u + c));
+                        e = big_ld<HINTS>(tr + ((size_t)e * 4u + c), pol_keep);
                         if (e >= H0) { m |= 1u << j; sts_u32(qp, e); qp += 4; }
                     }
                     hm[full] = (uint16_t)m;
@@ -163,7 +204,7 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
                     while (m == 0) { k++; m = hm[k]; }
                     const int bpos = __ffs(m) - 1;
                     m &= m - 1;
-                    const uint32_t info = ldg_nc_u32(p.hit_info + (q[j] - H0));
+                    const uint32_t info = big_ld<HINTS>(p.hit_info + (q[j] - H0), pol_keep);
                     const uint32_t r = info & 0x00ffffffu;
                     const int lv = (int)(info >> 24);
                     if (lv > best) { best = lv; cnt = 0; first_kept = j; }
@@ -171,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
                     for (int kk = first_kept; kk < j && !drop; kk++) drop = (q[kk] == r);
                     q[j] = drop ? 0xffffffffu : r;
                     if (!drop) {
-                        if (room) { p.cand_rank[o + cnt] = r; p.cand_pos[o + cnt] = (uint16_t)(16 * k + bpos); }
+                        if (room) { big_st<HINTS>(p.cand_rank + o + cnt, r); big_st<HINTS>(p.cand_pos + o + cnt, (uint16_t)(16 * k + bpos)); }
                         cnt++;
                     }
                 }
@@ -180,9 +221,9 @@ __global__ void __launch_bounds__(1024, 1) scan_big_k(ScanBigParams p) {
                 // reserved). Without room the attempt is discarded by the host and rerun with the exact size.
                 uint32_t st2 = 0;
                 for (int qq = 0; qq < L; qq++) {
-                    st2 = ldg_nc_u32(tr + ((size_t)st2 * 4u + pk_code(row, qq)));
+                    st2 = big_ld<HINTS>(tr + ((size_t)st2 * 4u + pk_code(row, qq)), pol_keep);
                     if (st2 >= H0) {
-                        const uint32_t info = ldg_nc_u32(p.hit_info + (st2 - H0));
+                        const uint32_t info = big_ld<HINTS>(p.hit_info + (st2 - H0), pol_keep);
                         const uint32_t r = info & 0x00ffffffu;
                         const int lv = (int)(info >> 24);
                         if (lv > best) { best = lv; cnt = 0; }

@@ -474,6 +474,24 @@ def test_bench_native_arm_control_flow_and_json_contract():
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 20000 * 100 * 0 + 20000 * 150 * 2 + 20000 * 13 + 20001 * 8 and e["d2h_bytes_per_step"] == 20 + 60 + 200 + 16
     assert e["pipelined"]["depth"] == 2 and e["pipelined"]["slots_agree"] and "serial" in e
+    assert e["steps"] >= 2 and "ms_per_step_min" in e["serial"]
+    assert d["config"]["name"] == "c2" and d["config"]["core_set"]["cores"] == 2048 and d["scaling"] == "weak"
+
+
+def test_bench_named_configs():
+    """--config c3 / c4 / c5 (BASELINE configs[2..4]): paired input with both mates in the byte counts, the 36 bp shape with the
+    total split over the GPUs (strong scaling), 250 bp with high-entropy qualities."""
+    import bench
+    d = _bench_dry("--config", "c3", "--reads", "3000", "--steps", "1", "--warmup", "1", "--no-cpu", "--e2e-depth", "1", "--e2e-steps", "1")
+    assert d["config"]["paired"] and d["config"]["mate2_length"] == 150 and "paired-end" in d["config"]["workload"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 3000 * 150 * 4 + 3000 * 13 + 3001 * 8
+    assert d["e2e"]["d2h_bytes_per_step"] == 20 + 60 + 200 + 16 + 80 + 200
+    assert d["pipeline_roofline"]["bytes_per_read"] == bench.algorithmic_bytes_per_read(150, 13, 8, True, 150)
+    d = _bench_dry("--config", "c4", "--reads", "5000", "--steps", "1", "--warmup", "1", "--no-cpu", "--no-e2e")
+    assert d["config"]["read_length"] == 36 and d["scaling"] == "strong" and d["config"]["flushes_per_step"] == 1
+    d = _bench_dry("--config", "c5", "--reads", "2000", "--steps", "1", "--warmup", "1", "--no-cpu", "--no-e2e")
+    assert d["config"]["read_length"] == 250 and d["config"]["high_entropy_qualities"]
+    assert bench.CONFIGS["c4"]["total"] == 500_000_000 and bench.CONFIGS["c3"]["reads"] * 8 == 200_000_000 and bench.CONFIGS["c5"]["reads"] * 8 == 100_000_000
 
 
 def test_bench_native_arm_cpu_baseline_fields():

@@ -107,7 +107,7 @@ def test_reference_harness_thread_loop_conserves_payload(tmp_path):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     cores = bench.headline_cores()
     n, L = 20000, 100
-    seq, qual, names, off = bench.synth_host_sample(n, L, seed=3)
+    seq, qual, names, off, _, _ = bench.synth_host_sample(n, L, seed=3)
     H = C.CDLL(harness)
     H.refh_init.restype = C.c_double
     H.refh_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
@@ -200,3 +200,35 @@ def test_cpp_container_assembly_matches_reference_cli(path, oracle_lib, tmp_path
             k = f"{mate + 1}{ext}"
             data = (tmp_path / f"out_{mate + 1}.scalce{ext}").read_bytes()
             assert len(data) == meta["sizes"][k] and hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{k}: differs from the reference CLI output"
+
+
+def test_oracle_inverse_matches_reference_decompressor(tmp_path, oracle_lib):
+    """orc_inverse (oracle restatement of decompress.cpp:331-352, the checker of the device-side inverse scb_inverse_reads)
+    against the UNMODIFIED reference: compress with the CLI (-c no -A), decompress with the CLI, and the oracle must rebuild
+    the same read and quality lines, in the same order, from the .scalcer / .scalceq files."""
+    if not os.path.exists(orc.REF_CLI):
+        pytest.skip("reference CLI not built here")
+    from oracle.gen_cores import write_text
+    for seed, L, kw in ((931, 80, {}), (932, 300, {}), (933, 36, dict(lower_frac=0.05))):
+        cores = make_cores(seed, [(8, 128), (9, 64), (11, 32)])
+        b = synth.make_batch(2500, L, seed=seed, n_frac=0.01, **kw)
+        synth.plant_cores(b, cores, seed=seed + 1, frac=0.5)
+        d = str(tmp_path / f"c{seed}")
+        os.makedirs(d)
+        write_text(d + "/cores.txt", cores)
+        synth.write_fastq(b, d + "/in_1.fastq")
+        orc.run_reference_cli(d + "/in_1.fastq", d + "/ref", d + "/cores.txt", bucket="1M", tmpdir=d + "/tmp")
+        orc.run_reference_decompress(d + "/ref_1.scalcen", d + "/rt", d + "/cores.txt")
+        rt = open(d + "/rt_1.fastq", "rb").read().split(b"\n")
+        want_seq, want_q = rt[1::4], rt[3::4]
+        fr = open(d + "/ref_1.scalcer", "rb").read()
+        fq = open(d + "/ref_1.scalceq", "rb").read()
+        assert fr[:8] == orc.MAGIC and fq[:8] == orc.MAGIC
+        phred = int(np.frombuffer(fq[8:16], dtype=np.int64)[0])
+        stream, sc, sr = orc.split_reads_container(fr[16:], cores, L)
+        o = orc.Oracle(cores, L)
+        seq, q = o.inverse(stream, sc, sr, quals=fq[16:], phred=phred)
+        assert seq.shape[0] == b.n == len(want_seq) - (1 if want_seq[-1] == b"" else 0) or seq.shape[0] == b.n
+        for i in range(b.n):
+            assert seq[i].tobytes() == want_seq[i], f"read line {i}"
+            assert q[i].tobytes() == want_q[i], f"quality line {i}"
