@@ -189,7 +189,7 @@ struct scb_handle {
     int engine = 0;            // engine of the current flush: 0 dense, 1 sparse, 2 sequential
     bool sp_ready = false;
     int64_t sp_M = 0;
-    DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev;
+    DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev, sp_tile_clean, sp_ractive;
     uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
@@ -293,11 +293,16 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
                 upload(h->d_hit_rank, hr, h->st);
                 h->smem_table_bytes = bytes;
                 h->smem_resident = true;
-            } else if (t.n_buckets < (1 << 24) && (uint64_t)ns < (1ull << 30)) {   // global-memory form: u32 next state, hit_info = rank | level << 24
+            } else if (t.n_buckets < (1 << 24) && (uint64_t)ns < (1ull << kBigStateBits) && t.max_level < 64) {
+                // global-memory form (scan_big.cuh): entry = next state | level of the longest core ending there << 26; hit_info = rank | level << 24
                 std::vector<uint32_t> tr((size_t)ns * 4);
                 std::vector<uint32_t> hi(nhit);
                 for (int u = 0; u < ns; u++) {
-                    for (int c = 0; c < 4; c++) tr[(size_t)newid[u] * 4 + c] = newid[t.next[(size_t)u * 4 + c]];
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t v = t.next[(size_t)u * 4 + c];
+                        const uint32_t lv = t.nto_rank[v] >= 0 ? (uint32_t)t.rank_level[(size_t)t.nto_rank[v]] : 0u;
+                        tr[(size_t)newid[u] * 4 + c] = newid[v] | (lv << kBigStateBits);
+                    }
                     if (t.nto_rank[u] >= 0) hi[newid[u] - (ns - nhit)] = (uint32_t)t.nto_rank[u] | ((uint32_t)t.rank_level[(size_t)t.nto_rank[u]] << 24);
                 }
                 upload(h->d_trans32, tr, h->st);
@@ -612,45 +617,35 @@ static void stage_scan(scb_handle *h) {
             }
         }
     }
-    if (!scanned && h->big_table && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(getenv("SCB_SCAN") && !strcmp(getenv("SCB_SCAN"), "global"))) {
-        // automaton in global memory / L2 (scan_big.cuh): same warp-tile pipeline, as many warps per SM as the staging allows
-        const size_t budget = 227 * 1024 - 64;
-        const int PW = h->PW, pitch = scan_smem_pitch(PW);
-        const size_t per_warp = scan_big_warp_bytes(L1, PW);
-        const int W = (int)std::min<size_t>(32, budget / per_warp);
-        if (W >= 1) {
-            const size_t smem = (size_t)W * per_warp;
-            // L2 policy hints of scan_big_k (bit 0 table evict_last, bit 1 tiles evict_first, bit 2 streaming stores); SCB_BIG_HINTS picks a set for A/B runs
-            const char *he = getenv("SCB_BIG_HINTS");
-            // bit 1 is off by default: LDGSTS with a cache-policy descriptor raised "illegal instruction" on the B200 (compute-sanitizer: the
-            // cp.async.cg ... L2::cache_hint in stage_warp_tile_stream), profiles/r02_scan_big_hints.txt
-            const int hints = he && *he ? atoi(he) & 7 : 5;
-            void (*kbig)(ScanBigParams) = hints == 0 ? scan_big_k<0> : hints == 1 ? scan_big_k<1> : hints == 2 ? scan_big_k<2> : hints == 3 ? scan_big_k<3> :
-                                          hints == 4 ? scan_big_k<4> : hints == 5 ? scan_big_k<5> : hints == 6 ? scan_big_k<6> : scan_big_k<7>;
-            SCB_CUDA(cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int dev_sms = 0;
-            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
-            DevBuf dtot(8, st);
-            const uint64_t holes = (uint64_t)dev_sms * W * kCandChunk;
-            uint64_t cap = std::max<uint64_t>((uint64_t)n * 12, 1u << 20) + holes;
-            for (int attempt = 0; attempt < 2 && !scanned; attempt++) {
-                h->cand_rank.alloc((size_t)cap * 4, st);
-                h->cand_pos.alloc((size_t)cap * 2, st);
-                SCB_CUDA(cudaMemsetAsync(dtot.p, 0, 8, st));
-                ScanBigParams bp;
-                bp.seq = c.seq1; bp.n = n; bp.L = L1; bp.trans = h->d_trans32.as<uint32_t>(); bp.hit_info = h->d_hit_info.as<uint32_t>();
-                bp.H0 = (uint32_t)h->H0;
-                bp.lvl = h->lvl.as<uint8_t>(); bp.ncand = h->ncand.as<uint16_t>(); bp.cand_off = h->cand_off.as<uint64_t>();
-                bp.cand_rank = h->cand_rank.as<uint32_t>(); bp.cand_pos = h->cand_pos.as<uint16_t>();
-                bp.cand_total = dtot.as<unsigned long long>(); bp.cand_cap = cap; bp.n_tiles = cdiv(n, 32);
-                bp.packed = h->packed.as<uint32_t>(); bp.PW = PW;
-                bp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); bp.pitch = pitch;
-                const int grid = (int)std::min<int64_t>(dev_sms, cdiv(bp.n_tiles, W));
-                SCB_LAUNCH(kbig, grid, W * 32, smem, st, bp);
-                SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
-                SCB_CUDA(cudaStreamSynchronize(st));
-                if (M <= cap) scanned = true; else cap = M;
-            }
+    if (!scanned && h->big_table && n > 0 && ((uintptr_t)c.seq1 & 3) == 0 && !(getenv("SCB_SCAN") && !strcmp(getenv("SCB_SCAN"), "global"))) {
+        // automaton in global memory / L2 (scan_big.cuh): pack, then one lane per read walks with 32 warps per SM in flight
+        const int PW = h->PW;
+        const char *qe = getenv("SCB_BIG_Q");            // per-lane queue of max-level hits: 32 (default, 32 warps / SM) or 16 (64 warps / SM)
+        const int Q = qe && atoi(qe) == 16 ? 16 : 32;
+        const size_t smem = scan_big_smem_bytes(kBigThreads, Q);
+        void (*kbig)(ScanBigParams) = Q == 16 ? scan_big_k<16> : scan_big_k<32>;
+        SCB_CUDA(cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev_sms = 0;
+        SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+        SCB_LAUNCH(pack_reads16_k, (unsigned)cdiv(n * PW, 256), 256, 0, st, c.seq1, n, L1, PW, h->packed.as<uint32_t>());
+        DevBuf dtot(8, st);
+        const int grid = (int)std::min<int64_t>((int64_t)dev_sms * (Q == 16 ? 4 : 2), cdiv(cdiv(n, 32), kBigThreads / 32));
+        const uint64_t holes = (uint64_t)grid * (kBigThreads / 32) * kCandChunk;
+        uint64_t cap = std::max<uint64_t>((uint64_t)n * 6, 1u << 20) + holes;
+        for (int attempt = 0; attempt < 2 && !scanned; attempt++) {
+            h->cand_rank.alloc((size_t)cap * 4, st);
+            h->cand_pos.alloc((size_t)cap * 2, st);
+            SCB_CUDA(cudaMemsetAsync(dtot.p, 0, 8, st));
+            ScanBigParams bp;
+            bp.packed = h->packed.as<uint32_t>(); bp.n = n; bp.L = L1; bp.PW = PW;
+            bp.trans = h->d_trans32.as<uint32_t>(); bp.hit_info = h->d_hit_info.as<uint32_t>(); bp.H0 = (uint32_t)h->H0;
+            bp.lvl = h->lvl.as<uint8_t>(); bp.ncand = h->ncand.as<uint16_t>(); bp.cand_off = h->cand_off.as<uint64_t>();
+            bp.cand_rank = h->cand_rank.as<uint32_t>(); bp.cand_pos = h->cand_pos.as<uint16_t>();
+            bp.cand_total = dtot.as<unsigned long long>(); bp.cand_cap = cap;
+            SCB_LAUNCH(kbig, grid, kBigThreads, smem, st, bp);
+            SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            if (M <= cap) scanned = true; else cap = M;
         }
     }
     if (!scanned) {
@@ -725,6 +720,7 @@ static void sparse_setup(scb_handle *h) {
     h->sp_sb.alloc((size_t)M1 * 4, st); h->sp_sread.alloc((size_t)M1 * 4, st); h->sp_sk.alloc((size_t)M1 * 2, st); h->sp_sval.alloc((size_t)M1 * 4, st);
     h->sp_cnt.alloc((size_t)M1 * 4, st); h->sp_fbyte.alloc((size_t)(M1 / 8 + 16), st);
     h->sp_tail.alloc((size_t)tiles * 4, st); h->sp_treset.alloc((size_t)tiles * 4, st); h->sp_X.alloc((size_t)tiles * 4, st);
+    h->sp_tile_clean.alloc((size_t)tiles, st); h->sp_ractive.alloc((size_t)std::max<int64_t>(n, 1), st);
     // temporaries of the sort: carved after the mark and handed back when the sorted view exists
     const Arena::Mark mk = h->arena.mark();
     {
@@ -763,18 +759,19 @@ static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
         else SCB_LAUNCH(sp_mark_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base, h->sp_base_prev.as<uint32_t>(), nb1, h->sp_dirty.as<uint32_t>(), round);
     }
     SpRound r;
-    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round;
+    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round; r.tile_clean = h->sp_tile_clean.as<uint8_t>();
     r.M = M; r.sb = h->sp_sb.as<uint32_t>(); r.sread = h->sp_sread.as<uint32_t>(); r.sval = h->sp_sval.as<uint32_t>(); r.sk = h->sp_sk.as<uint16_t>();
     r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>(); r.tail = h->sp_tail.as<uint32_t>(); r.treset = h->sp_treset.as<uint32_t>();
     SCB_LAUNCH(sp_flags_k, (unsigned)tiles, kSpThreads, 0, st, r);
     SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, h->sp_tail.as<uint32_t>(), h->sp_treset.as<uint32_t>(), tiles, h->sp_X.as<uint32_t>());
     SpCounts c;
     c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>(); c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
-    c.dirty = r.dirty; c.round = round;
+    c.dirty = r.dirty; c.round = round; c.tile_clean = r.tile_clean; c.sread = r.sread; c.ractive = h->sp_ractive.as<uint8_t>(); c.stamp = (uint8_t)(round & 0xffu);
     SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
     SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->sp_doff.as<uint64_t>(), h->sp_cnt.as<uint32_t>(),
                h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_changed.as<uint32_t>(),
-               hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0, h->sp_dirty.as<uint32_t>(), round + 1);
+               hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0, h->sp_dirty.as<uint32_t>(), round + 1,
+               h->sp_ractive.as<uint8_t>(), round == 0 ? -1 : (int)(round & 0xffu));
 }
 
 // iterates the local reads to their fixed point from the populations in sh_base, then folds them in: sp_base2 = populations after
@@ -798,7 +795,7 @@ static void sparse_local(scb_handle *h) {
     SpCounts c;
     c.M = M; c.sb = h->sp_sb.as<uint32_t>(); c.sval = h->sp_sval.as<uint32_t>(); c.fbyte = h->sp_fbyte.as<uint8_t>(); c.X = h->sp_X.as<uint32_t>();
     c.base = h->sh_base.as<uint32_t>(); c.cnt = nullptr; c.fold = h->sp_base2.as<uint32_t>();
-    c.dirty = h->sp_dirty.as<uint32_t>(); c.round = h->sp_round;
+    c.dirty = h->sp_dirty.as<uint32_t>(); c.round = h->sp_round; c.tile_clean = nullptr; c.sread = nullptr; c.ractive = nullptr; c.stamp = 0;
     SCB_LAUNCH(sp_counts_k, (unsigned)cdiv(M, kSpTile), kSpThreads, 0, st, c);
 }
 

@@ -102,6 +102,7 @@ struct SpRound {
     uint32_t *tail, *treset;         // [tiles]
     const uint32_t *dirty;           // [nb1] round stamp: bucket b is dirty in round r iff dirty[b] == r (all zero before round 0)
     uint32_t round;
+    uint8_t *tile_clean;             // [tiles] 1 = no pair of the tile belongs to a dirty bucket this round: nothing of the tile changes
 };
 
 // flags of the current assignment + per tile: flags in the tile's trailing segment, and whether that segment starts
@@ -110,21 +111,30 @@ __global__ void __launch_bounds__(kSpThreads) sp_flags_k(SpRound p) {
     __shared__ uint32_t sm[kSpThreads / 32];
     const int64_t tbeg = (int64_t)blockIdx.x * kSpTile;
     const int64_t tend = tbeg + kSpTile < p.M ? tbeg + kSpTile : p.M;
-    const uint32_t klast = p.sb[tend - 1];
     const int64_t base = tbeg + (int64_t)threadIdx.x * kSpItems;
-    uint32_t rd[kSpItems], kk[kSpItems], b[kSpItems];
+    uint32_t b[kSpItems];
+#pragma unroll
+    for (int j = 0; j < kSpItems; j++) b[j] = (base + j < p.M) ? p.sb[base + j] : 0xffffffffu;
+    uint32_t dm0 = 0;
+#pragma unroll
+    for (int j = 0; j < kSpItems; j++) dm0 |= ((base + j < p.M) && p.dirty[b[j] & kSpRankMask] == p.round) ? (1u << j) : 0u;
+    // a tile without a pair of a dirty bucket keeps its flags, its tail and (sp_counts_k) its counts: late rounds touch few tiles
+    if (!__syncthreads_or(dm0 != 0)) {
+        if (threadIdx.x == 0) p.tile_clean[blockIdx.x] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) p.tile_clean[blockIdx.x] = 0;
+    const uint32_t klast = p.sb[tend - 1];
+    uint32_t rd[kSpItems], kk[kSpItems];
 #pragma unroll
     for (int j = 0; j < kSpItems; j++) {
-        const bool ok = base + j < p.M;
+        const bool ok = ((dm0 >> j) & 1u) != 0;
         rd[j] = ok ? p.sread[base + j] : 0u;
         kk[j] = ok ? (uint32_t)p.sk[base + j] : 0x10000u;    // never equals a slot
-        b[j] = ok ? p.sb[base + j] : 0xffffffffu;
     }
     // only pairs of dirty buckets look their read's selection up again (the random access of this kernel); the others keep
     // the flag of the round before
-    uint32_t dm = 0;
-#pragma unroll
-    for (int j = 0; j < kSpItems; j++) dm |= ((base + j < p.M) && p.dirty[b[j] & kSpRankMask] == p.round) ? (1u << j) : 0u;
+    const uint32_t dm = dm0;
     const uint32_t oldbits = (base < p.M && dm != 0xffu) ? (uint32_t)p.fbyte[base >> 3] : 0u;
     uint32_t s[kSpItems];
 #pragma unroll
@@ -176,10 +186,13 @@ struct SpCounts {
     uint32_t *cnt;                   // [M] read-major: what pair p sees
     uint32_t *fold;                  // != null: instead of scattering counts, write base + segment total at every segment end
     const uint32_t *dirty; uint32_t round;   // counts are only scattered for dirty buckets (see SpRound)
+    const uint8_t *tile_clean;               // tiles sp_flags_k found clean are skipped
+    const uint32_t *sread; uint8_t *ractive; uint8_t stamp;   // reads that receive a new count are marked for sp_decide_k
 };
 
 __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
     __shared__ uint32_t sm[64];
+    if (!p.fold && p.tile_clean[blockIdx.x]) return;        // block-uniform, before any barrier
     const int64_t tbeg = (int64_t)blockIdx.x * kSpTile;
     const int64_t base = tbeg + (int64_t)threadIdx.x * kSpItems;
     uint32_t b[kSpItems + 1];
@@ -212,6 +225,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
             if (b[j + 1] != b[j]) p.fold[b[j] & kSpRankMask] = c + ((bits >> j) & 1u);    // last pair of its bucket: every bucket at most once
         } else if (p.dirty[b[j] & kSpRankMask] == p.round) {
             p.cnt[p.sval[base + j]] = c;
+            p.ractive[p.sread[base + j]] = p.stamp;
         }
     }
 }
@@ -222,10 +236,11 @@ __global__ void __launch_bounds__(256) sp_decide_k(int64_t n, const uint16_t *__
                                                    const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ cand_off,
                                                    const uint32_t *__restrict__ cand_rank, uint16_t *__restrict__ sel,
                                                    uint32_t *__restrict__ changed, uint32_t *__restrict__ hist, int full,
-                                                   uint32_t *__restrict__ dirty, uint32_t next_round) {
+                                                   uint32_t *__restrict__ dirty, uint32_t next_round, const uint8_t *__restrict__ ractive, int stamp /* < 0: all reads */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t chg = 0;
-    if (i < n) {
+    // a read whose counts were not rewritten this round decides as before (a stale stamp from 256 rounds ago only costs a re-evaluation)
+    if (i < n && (stamp < 0 || ractive[i] == (uint8_t)stamp)) {
         const int nc = ncand[i];
         if (nc > 0) {
             const uint64_t d = doff[i];

@@ -51,6 +51,17 @@ def main():
         ok &= o.unbucketed == sum(g["unb"] for g in gathered)
         print("rounds", gathered[0]["stats"]["rounds"], "chunks", o.n_chunks, "split", gathered[0]["stats"]["split"])
         print("SHARDED_NCCL_OK" if ok else "SHARDED_NCCL_FAIL")
+        # a record the driver / the round's profiles can keep: what ran, on how many GPUs, and the verdict
+        import json
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        variant = "_".join(k for k in ("SCB_SHARD_JOINT_KERNEL", "SCB_SHARD_EARLY_EMIT", "SCB_RESOLVE") if os.environ.get(k, "0") not in ("", "0")) or "default"
+        rec = {"test": "tests/sharded_nccl_worker.py", "world_size": world, "gpus": torch.cuda.device_count(), "reads": n, "read_length": L,
+               "bucket_set_bytes": bsb, "flush_chunks": o.n_chunks, "joint_rounds": gathered[0]["stats"]["rounds"], "variant": variant,
+               "backend": "nccl + CUDA IPC peer stores, one process per GPU", "ok": bool(ok),
+               "compared": "per-read bucket / core / end / chunk arrays and streams 0-3 of every flush chunk and merged, rank-order concatenation vs the CPU oracle"}
+        with open(os.path.join(out_dir, f"sharded_nccl_w{world}_{variant}.json"), "w") as f:
+            json.dump(rec, f)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
