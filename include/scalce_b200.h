@@ -280,6 +280,36 @@ int scb_shard_finish(scb_handle *h, scb_result *out);
 /* Device milliseconds of the last scb_shard_* call (CUDA events on the handle's stream). */
 float scb_shard_last_ms(const scb_handle *h);
 
+/* ---- the whole sharded flush as ONE call (the C++ orchestrator; scalce_b200/shard.py is the same sequence in Python) ----
+ * Communication between the ranks is the caller's: MPI, NCCL (libscalce_b200_nccl.so wraps an ncclComm_t into this struct),
+ * or threads of one process. The library needs two collectives:
+ *   allgather  every rank contributes `bytes` from `send` and receives n_ranks * bytes in rank order in `recv`.
+ *              device = 1: both buffers are device memory of the calling rank's GPU and the operation must be ordered on
+ *              `stream` (a cudaStream_t: the handle's stream); device = 0: host memory, blocking.
+ *   barrier    all ranks arrive (host side); every rank has synchronised its stream before it calls this.
+ * same_process = 1: the ranks are threads of one process on GPUs with peer access (or one GPU): device pointers are
+ * exchanged as they are; otherwise the receive arrays are published through CUDA IPC (scb_ipc_export / scb_ipc_open).
+ * Both callbacks return 0 on success. */
+typedef struct scb_comm {
+    int32_t rank, n_ranks;
+    int32_t same_process;
+    int32_t reserved;
+    void *ctx;
+    int (*allgather)(void *ctx, const void *send, void *recv, int64_t bytes, int32_t device, void *stream);
+    int (*barrier)(void *ctx);
+} scb_comm;
+/* Everything between scb_submit of this rank's shard and the rank's slice of the output: scan, flush chunks along the global
+ * order, joint tie-break (one all-gather of the bucket histograms per round), bucket-range split, fused pack + exchange over
+ * peer memory with the row exchange overlapped by the sort, emit. Collective: every rank calls it once per flush with its own
+ * handle. Result as scb_shard_finish. scb_shard_flush_stats: device milliseconds of the phases of the last call, in the order
+ * scan, chunks, resolve (rank 0 alone), resolve_rounds (joint), finalize, hist, pack, exchange, import, sort, exchange_rows,
+ * emit; *rounds = joint rounds. */
+#define SCB_N_SHARD_PHASES 12
+int scb_shard_flush(scb_handle *h, const scb_comm *comm, scb_result *out);
+int scb_shard_flush_stats(const scb_handle *h, float *phase_ms, int32_t cap, int32_t *rounds);
+/* Reads of this rank's own input shard in the last sharded flush (the per-read arrays of scb_result refer to them). */
+int64_t scb_shard_n_local(const scb_handle *h);
+
 /* =====================================================================================================
  * The transform's two neighbours that SURVEY.md 8(f) ranks next, on the device.
  * ===================================================================================================== */

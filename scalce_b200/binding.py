@@ -23,7 +23,7 @@ EXPORTS = [
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
     "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", "scb_shard_finish_early", "scb_shard_joint_reserve", "scb_shard_resolve_joint",
-    "scb_ipc_export", "scb_ipc_open", "scb_ipc_close",
+    "scb_ipc_export", "scb_ipc_open", "scb_ipc_close", "scb_shard_flush", "scb_shard_flush_stats", "scb_shard_n_local",
 ]
 
 
@@ -54,6 +54,15 @@ class ScbShardXfer(C.Structure):
 class ScbShardPeer(C.Structure):
     _fields_ = [("aux", C.c_void_p), ("packed", C.c_void_p), ("qual1", C.c_void_p), ("names", C.c_void_p), ("seq2", C.c_void_p),
                 ("qual2", C.c_void_p), ("row_off", C.c_int64), ("name_off", C.c_int64)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class ScbComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("same_process", C.c_int32), ("reserved", C.c_int32), ("ctx", C.c_void_p),
+                ("allgather", ALLGATHER_FN), ("barrier", BARRIER_FN)]
 
 
 _lib = None
@@ -121,6 +130,10 @@ def load_library(path: str | None = None):
     L.scb_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.scb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     L.scb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.scb_shard_flush.argtypes = [C.c_void_p, C.POINTER(ScbComm), C.POINTER(ScbResult)]
+    L.scb_shard_n_local.restype = C.c_int64
+    L.scb_shard_n_local.argtypes = [C.c_void_p]
+    L.scb_shard_flush_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]
     L.scb_shard_last_ms.restype = C.c_float
     L.scb_shard_last_ms.argtypes = [C.c_void_p]
     if path is None:
@@ -315,6 +328,10 @@ class BoostTransform:
     @property
     def resolve_rounds(self):
         return load_library().scb_resolve_rounds(self._h)
+
+    def n_local_last(self):
+        """Reads of this rank's own input shard in the last sharded flush (the per-read arrays refer to them)."""
+        return int(load_library().scb_shard_n_local(self._h))
 
     @property
     def device_bytes(self):

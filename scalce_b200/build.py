@@ -39,6 +39,35 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+NCCL_LIB = os.path.join(HERE, "libscalce_b200_nccl.so")
+NCCL_SRC = os.path.join(CSRC, "comm_nccl.cpp")
+
+
+def build_nccl_comm(force: bool = False) -> str:
+    """nvcc -> scalce_b200/libscalce_b200_nccl.so: an ncclComm_t wrapped into the scb_comm of scb_shard_flush (csrc/comm_nccl.cpp).
+    Separate from the main library so that the transform itself carries no NCCL dependency."""
+    deps = [NCCL_SRC, os.path.join(HERE, "..", "include", "scalce_b200.h")]
+    if not force and os.path.exists(NCCL_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(NCCL_LIB) for d in deps):
+        return NCCL_LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    inc, libdirs = [], []
+    try:   # prefer the NCCL that ships with torch (the one the GPU box loads); fall back to the system one
+        import nvidia.nccl as _n
+        base = os.path.dirname(_n.__file__) if getattr(_n, "__file__", None) else list(_n.__path__)[0]
+        inc, libdirs = ["-I" + os.path.join(base, "include")], [os.path.join(base, "lib")]
+    except Exception:
+        pass
+    cmd = [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-shared", "-o", NCCL_LIB, NCCL_SRC] + inc
+    for d in libdirs:
+        cmd += ["-L" + d, "-Xlinker", "-rpath," + d]
+    cmd += ["-l:libnccl.so.2"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("libscalce_b200_nccl.so build failed")
+    return NCCL_LIB
+
+
 HOST_SRC = os.path.join(HERE, "host", "scb_boost.cpp")
 HOST_BIN = os.path.join(HERE, "host", "scb_boost")
 
@@ -62,3 +91,4 @@ def build_host_tool(force: bool = False) -> str:
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host_tool(force="--force" in sys.argv))
+    print(build_nccl_comm(force="--force" in sys.argv))

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -185,11 +186,17 @@ struct scb_handle {
     int sh_W = 0, sh_grid = 0; // dense-resolve geometry
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
     DevBuf sh_stale, sh_nstale;   // deferred re-sweeps (resolve_dense_k<*, *, true>)
+    // C++ orchestrator (scb_shard_flush): peers' receive arrays as mapped here, phase times of the last call
+    std::map<std::pair<int, int>, std::pair<std::vector<uint8_t>, void *>> fl_ipc;   // (rank, array) -> (IPC handle bytes, mapped pointer)
+    std::vector<std::vector<void *>> fl_table;                                       // [rank][array]
+    float fl_ms[SCB_N_SHARD_PHASES] = {};
+    int fl_rounds = 0;
     // sparse resolve engine (resolve_sparse.cuh): bucket-major view of the candidate pairs, built once per flush
     int engine = 0;            // engine of the current flush: 0 dense, 1 sparse, 2 sequential
     bool sp_ready = false;
     int64_t sp_M = 0;
     DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev, sp_tile_clean, sp_ractive;
+    bool sp_warm = false; uint32_t sp_dirty_tiles = 0;
     uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
@@ -701,7 +708,7 @@ static void sparse_setup(scb_handle *h) {
     h->sh_base.alloc((size_t)nb1 * 4, st);
     h->sp_base2.alloc((size_t)nb1 * 4, st);
     h->sp_hist.alloc((size_t)(nb1 + 1) * 4, st);
-    h->sp_changed.alloc(4, st);
+    h->sp_changed.alloc(16, st);
     h->sp_dirty.alloc((size_t)nb1 * 4, st);
     h->sp_base_prev.alloc((size_t)nb1 * 4, st);
     SCB_CUDA(cudaMemsetAsync(h->sp_dirty.p, 0, (size_t)nb1 * 4, st));        // every bucket is dirty in round 0
@@ -721,14 +728,19 @@ static void sparse_setup(scb_handle *h) {
     h->sp_cnt.alloc((size_t)M1 * 4, st); h->sp_fbyte.alloc((size_t)(M1 / 8 + 16), st);
     h->sp_tail.alloc((size_t)tiles * 4, st); h->sp_treset.alloc((size_t)tiles * 4, st); h->sp_X.alloc((size_t)tiles * 4, st);
     h->sp_tile_clean.alloc((size_t)tiles, st); h->sp_ractive.alloc((size_t)std::max<int64_t>(n, 1), st);
+    h->sp_dirty_tiles = (uint32_t)std::min<int64_t>(tiles, 0xffffffffll);   // "all dirty" until a round reports otherwise (the sharded rounds never do: no read-back per round)
     // temporaries of the sort: carved after the mark and handed back when the sorted view exists
     const Arena::Mark mk = h->arena.mark();
     {
         DevBuf k0((size_t)M1 * 8, st), k1((size_t)M1 * 8, st), v0((size_t)M1 * 4, st), v1((size_t)M1 * 4, st), pread((size_t)M1 * 4, st);
         DevBuf hist((size_t)SortWs::hist_elems(M1) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(M1)) * 4, st);
+        const bool warm = env_on("SCB_SPARSE_WARM", true);      // warm start of the iteration by candidate-pair populations (sp_warm_k); "0" = first candidate
+        h->sp_warm = warm;
+        if (warm) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));   // sp_hist doubles as the pair-population scratch until the rounds start
         if (n > 0)
             SCB_LAUNCH(sp_pairs_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
-                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>());
+                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>(),
+                       warm ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr);
         if (M > 0) {
             SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
             uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
@@ -749,29 +761,34 @@ static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
     cudaStream_t st = h->st;
     const int64_t n = h->cur.n, M = h->sp_M;
     const int nb1 = h->tab.n_buckets + 1;
-    SCB_CUDA(cudaMemsetAsync(h->sp_changed.p, 0, 4, st));
-    if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
-    if (M == 0 || n == 0) return;
+    SCB_CUDA(cudaMemsetAsync(h->sp_changed.p, 0, 16, st));
+    if (M == 0 || n == 0) { if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st)); return; }
     const int64_t tiles = cdiv(M, kSpTile);
     const uint32_t round = h->sp_round++;
+    if (round == 0 && h->sp_warm)     // sp_hist still holds the candidate-pair populations of sp_pairs_k
+        SCB_LAUNCH(sp_warm_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
+                   h->sp_hist.as<uint32_t>(), base, h->sh_sel.as<uint16_t>());
+    if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
+    // reads are marked active (one more random store per rewritten count) only once few tiles are dirty; before that every read re-decides
+    const bool use_active = round > 0 && (uint64_t)h->sp_dirty_tiles * 4 < (uint64_t)tiles;
     if (hist_mode != 0) {   // sharded rounds: `base` moves between rounds; buckets whose value moved are dirty (round 0: all are anyway)
         if (round == 0) SCB_CUDA(cudaMemcpyAsync(h->sp_base_prev.p, base, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
         else SCB_LAUNCH(sp_mark_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base, h->sp_base_prev.as<uint32_t>(), nb1, h->sp_dirty.as<uint32_t>(), round);
     }
     SpRound r;
-    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round; r.tile_clean = h->sp_tile_clean.as<uint8_t>();
+    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round; r.tile_clean = h->sp_tile_clean.as<uint8_t>(); r.n_dirty_tiles = h->sp_changed.as<uint32_t>() + 1;
     r.M = M; r.sb = h->sp_sb.as<uint32_t>(); r.sread = h->sp_sread.as<uint32_t>(); r.sval = h->sp_sval.as<uint32_t>(); r.sk = h->sp_sk.as<uint16_t>();
     r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>(); r.tail = h->sp_tail.as<uint32_t>(); r.treset = h->sp_treset.as<uint32_t>();
     SCB_LAUNCH(sp_flags_k, (unsigned)tiles, kSpThreads, 0, st, r);
     SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, h->sp_tail.as<uint32_t>(), h->sp_treset.as<uint32_t>(), tiles, h->sp_X.as<uint32_t>());
     SpCounts c;
     c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>(); c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
-    c.dirty = r.dirty; c.round = round; c.tile_clean = r.tile_clean; c.sread = r.sread; c.ractive = h->sp_ractive.as<uint8_t>(); c.stamp = (uint8_t)(round & 0xffu);
+    c.dirty = r.dirty; c.round = round; c.tile_clean = r.tile_clean; c.sread = r.sread; c.ractive = use_active ? h->sp_ractive.as<uint8_t>() : (uint8_t *)nullptr; c.stamp = (uint8_t)(round & 0xffu);
     SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
     SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->sp_doff.as<uint64_t>(), h->sp_cnt.as<uint32_t>(),
                h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_changed.as<uint32_t>(),
                hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0, h->sp_dirty.as<uint32_t>(), round + 1,
-               h->sp_ractive.as<uint8_t>(), round == 0 ? -1 : (int)(round & 0xffu));
+               h->sp_ractive.as<uint8_t>(), use_active ? (int)(round & 0xffu) : -1);
 }
 
 // iterates the local reads to their fixed point from the populations in sh_base, then folds them in: sp_base2 = populations after
@@ -782,12 +799,26 @@ static void sparse_local(scb_handle *h) {
     h->last_rounds = 0;
     SCB_CUDA(cudaMemcpyAsync(h->sp_base2.p, h->sh_base.p, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
     if (M == 0 || h->cur.n == 0) return;
+    const bool prof = getenv("SCB_SPARSE_PROF") != nullptr;      // per-round device time and changed decisions, to stderr
     while (true) {
+        if (prof) SCB_CUDA(cudaEventRecord(h->ev_s0, st));
         sparse_round(h, h->sh_base.as<uint32_t>(), 0);
+        if (prof) SCB_CUDA(cudaEventRecord(h->ev_s1, st));
         h->last_rounds++;
-        uint32_t chg = 0;
-        SCB_CUDA(cudaMemcpyAsync(&chg, h->sp_changed.p, 4, cudaMemcpyDeviceToHost, st));
+        uint32_t cc[2] = {0, 0};
+        SCB_CUDA(cudaMemcpyAsync(cc, h->sp_changed.p, 8, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));
+        const uint32_t chg = cc[0];
+        h->sp_dirty_tiles = cc[1];
+        if (prof) {
+            float rms = 0;
+            SCB_CUDA(cudaEventElapsedTime(&rms, h->ev_s0, h->ev_s1));
+            std::vector<uint8_t> tc((size_t)cdiv(M, kSpTile));
+            SCB_CUDA(cudaMemcpy(tc.data(), h->sp_tile_clean.p, tc.size(), cudaMemcpyDeviceToHost));
+            size_t dirty_tiles = 0;
+            for (uint8_t v : tc) dirty_tiles += v == 0;
+            fprintf(stderr, "sparse round %3d: %8.3f ms, %10u decisions changed, %zu of %zu tiles dirty\n", h->last_rounds, rms, chg, dirty_tiles, tc.size());
+        }
         if (chg == 0) break;
         if (h->last_rounds >= kRdMaxRounds) throw CudaError{"resolve: round cap hit"};
     }
@@ -2320,6 +2351,200 @@ int scb_stage_ms(const scb_handle *h, float *out, int32_t cap) {
     return SCB_N_STAGES;
 }
 
+// ---- the sharded flush as one call: scalce_b200/shard.py::ShardedTransform.flush in C++ ------------------------------------
+namespace scb {
+struct CommError { std::string msg; };
+static void comm_check(int rc, const char *what) { if (rc != 0) throw CommError{std::string("scb_comm ") + what + " failed"}; }
+static std::vector<int64_t> comm_allgather_i64(const scb_comm *cm, const std::vector<int64_t> &mine) {
+    std::vector<int64_t> all(mine.size() * (size_t)cm->n_ranks);
+    comm_check(cm->allgather(cm->ctx, mine.data(), all.data(), (int64_t)(mine.size() * 8), 0, nullptr), "allgather (host)");
+    return all;
+}
+// contiguous slices of the bucket emission order with about equal read counts (a bucket is never divided)
+static std::vector<int64_t> balanced_split(const std::vector<uint64_t> &hist, int G) {
+    const int64_t ncols = (int64_t)hist.size();
+    std::vector<uint64_t> cum(hist.size());
+    uint64_t run = 0;
+    for (size_t i = 0; i < hist.size(); i++) { run += hist[i]; cum[i] = run; }
+    std::vector<int64_t> split{0};
+    for (int g = 1; g < G; g++) {
+        const uint64_t target = run * (uint64_t)g / (uint64_t)G;
+        int64_t k = (int64_t)(std::upper_bound(cum.begin(), cum.end(), target) - cum.begin());   // first bucket whose inclusive count exceeds the target
+        k = std::min(std::max(k, split.back()), ncols);
+        split.push_back(k);
+    }
+    split.push_back(ncols);
+    return split;
+}
+}  // namespace scb
+
+#define SCB_FL(call) do { int _rc = (call); if (_rc != SCB_OK) return _rc; } while (0)
+
+int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
+    using namespace scb;
+    if (!h || !cm || !out || !cm->allgather || !cm->barrier || cm->n_ranks < 1 || cm->n_ranks > kMaxRanks || cm->rank < 0 || cm->rank >= cm->n_ranks) {
+        g_last_error = "bad argument"; return SCB_EINVAL;
+    }
+    const int G = cm->n_ranks, r = cm->rank;
+    const scb_config &cfg = h->cfg;
+    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+    float *ms = h->fl_ms;
+    for (int k = 0; k < SCB_N_SHARD_PHASES; k++) ms[k] = 0.f;
+    h->fl_rounds = 0;
+    enum { P_SCAN, P_CHUNKS, P_RESOLVE, P_ROUNDS, P_FINALIZE, P_HIST, P_PACK, P_EXCH, P_IMPORT, P_SORT, P_ROWS, P_EMIT };
+    auto lap = [&](int k) { ms[k] += scb_shard_last_ms(h); };
+    try {
+        SCB_CUDA(cudaSetDevice(cfg.device));
+        cudaStream_t st = h->st;
+        int32_t ncols = 0, rootpos = 0;
+        SCB_FL(scb_shard_info(h, &ncols, &rootpos));
+        // ---- scan ------------------------------------------------------------------------------------------------
+        int64_t n_local = 0;
+        SCB_FL(scb_shard_scan(h, &n_local)); lap(P_SCAN);
+        const std::vector<int64_t> ns = comm_allgather_i64(cm, {n_local});
+        std::vector<int64_t> before(1, 0);
+        for (int g = 0; g < G; g++) before.push_back(before.back() + ns[(size_t)g]);
+        const int64_t n_global = before.back();
+        // ---- flush chunks along the global order: the ranks take turns --------------------------------------------
+        uint64_t carry = 0; int32_t chunk = 0;
+        for (int g = 0; g < G; g++) {
+            if (g == r) { SCB_FL(scb_shard_sizes(h, carry, chunk, &carry, &chunk)); lap(P_CHUNKS); }
+            const std::vector<int64_t> cc = comm_allgather_i64(cm, {(int64_t)carry, (int64_t)chunk});
+            carry = (uint64_t)cc[(size_t)g * 2]; chunk = (int32_t)cc[(size_t)g * 2 + 1];
+        }
+        const int32_t n_chunks = chunk + (carry > 0 ? 1 : 0);
+        // ---- tie-break ------------------------------------------------------------------------------------------------
+        const int RW = ncols + 1;
+        DevBuf tot((size_t)RW * 4, st), all((size_t)G * RW * 4, st), bf((size_t)ncols * 4, st), gtot((size_t)ncols * 4, st), dchg(8, st);
+        SCB_CUDA(cudaMemsetAsync(tot.p, 0, (size_t)RW * 4, st));
+        if (r == 0) { SCB_FL(scb_shard_resolve_local(h, tot.as<uint32_t>())); lap(P_RESOLVE); }
+        comm_check(cm->allgather(cm->ctx, tot.p, all.p, (int64_t)RW * 4, 1, st), "allgather (device)");
+        int rounds = 0;
+        if (G > 1) {
+            cudaEvent_t e0, e1;
+            SCB_CUDA(cudaEventCreate(&e0)); SCB_CUDA(cudaEventCreate(&e1));
+            SCB_CUDA(cudaEventRecord(e0, st));
+            for (bool first = true;; first = false) {
+                if (r > 0) {
+                    if (first) SCB_LAUNCH(sh_guess_k, (unsigned)cdiv(ncols, 256), 256, 0, st, all.as<uint32_t>(), (unsigned long long)before[(size_t)r], (unsigned long long)ns[0], ncols, bf.as<uint32_t>());
+                    else SCB_LAUNCH(sh_sum_rows_k, (unsigned)cdiv(ncols, 256), 256, 0, st, all.as<uint32_t>(), RW, 0, r, ncols, bf.as<uint32_t>());
+                    SCB_FL(scb_shard_resolve_round(h, bf.as<uint32_t>(), before[(size_t)r], first ? 1 : 0, tot.as<uint32_t>()));
+                }
+                comm_check(cm->allgather(cm->ctx, tot.p, all.p, (int64_t)RW * 4, 1, st), "allgather (device)");
+                rounds++;
+                SCB_LAUNCH(sh_changed_k, 1, 1, 0, st, all.as<uint32_t>(), RW, G, ncols, dchg.as<unsigned long long>());
+                unsigned long long chg = 0;
+                SCB_CUDA(cudaMemcpyAsync(&chg, dchg.p, 8, cudaMemcpyDeviceToHost, st));
+                SCB_CUDA(cudaStreamSynchronize(st));
+                if (!first && chg == 0) break;            // a round other than the first that changed nothing anywhere: the sequential assignment
+                if (rounds >= kRdMaxRounds) throw CudaError{"joint rounds: round cap hit"};
+            }
+            SCB_CUDA(cudaEventRecord(e1, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            SCB_CUDA(cudaEventElapsedTime(&ms[P_ROUNDS], e0, e1));
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        h->fl_rounds = rounds;
+        SCB_LAUNCH(sh_sum_rows_k, (unsigned)cdiv(ncols, 256), 256, 0, st, all.as<uint32_t>(), RW, 0, G, ncols, gtot.as<uint32_t>());
+        SCB_CUDA(cudaStreamSynchronize(st));
+        SCB_FL(scb_shard_finalize(h, gtot.as<uint32_t>(), n_global)); lap(P_FINALIZE);
+        // ---- bucket-range split ----------------------------------------------------------------------------------------
+        DevBuf hist((size_t)ncols * 4, st), allh((size_t)G * ncols * 4, st), ghist((size_t)ncols * 4, st);
+        SCB_FL(scb_shard_bucket_hist(h, hist.as<uint32_t>())); lap(P_HIST);
+        comm_check(cm->allgather(cm->ctx, hist.p, allh.p, (int64_t)ncols * 4, 1, st), "allgather (device)");
+        // per-rank histograms fit u32; their sum over the ranks may not: add on the host in 64 bits
+        std::vector<uint32_t> hh((size_t)G * ncols);
+        SCB_CUDA(cudaMemcpyAsync(hh.data(), allh.p, hh.size() * 4, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint64_t> gh((size_t)ncols, 0);
+        for (int g = 0; g < G; g++) for (int c2 = 0; c2 < ncols; c2++) gh[(size_t)c2] += hh[(size_t)g * ncols + c2];
+        const std::vector<int64_t> split = balanced_split(gh, G);
+        scb_shard_xfer x;
+        SCB_FL(scb_shard_partition(h, split.data(), G, &x)); lap(P_PACK);
+        // ---- exchange: what every rank receives from every rank -----------------------------------------------------------
+        std::vector<int64_t> mine((size_t)2 * G);
+        for (int g = 0; g < G; g++) { mine[(size_t)g] = x.cnt_reads[g]; mine[(size_t)G + g] = x.cnt_name_bytes[g]; }
+        const std::vector<int64_t> mat = comm_allgather_i64(cm, mine);      // mat[s * 2G + g] = reads s -> g
+        int64_t n_recv = 0, nb_recv = 0;
+        for (int s2 = 0; s2 < G; s2++) { n_recv += mat[(size_t)s2 * 2 * G + r]; nb_recv += mat[(size_t)s2 * 2 * G + G + r]; }
+        const int prow = x.packed_row_bytes;
+        const int64_t need[6] = {n_recv * 8, n_recv * prow + 64, cfg.use_quals ? n_recv * L1 : 0, cfg.use_names ? nb_recv + 16 : 0,
+                                 cfg.paired ? n_recv * L2 : 0, (cfg.paired && cfg.use_quals) ? n_recv * L2 : 0};
+        void *ptrs[6]; int32_t changed = 0;
+        SCB_FL(scb_shard_recv_reserve(h, need, ptrs, &changed));
+        // publish the receive arrays: raw pointers between threads of one process, CUDA IPC handles between processes
+        const bool have_table = (int)h->fl_table.size() == G;
+        const std::vector<int64_t> anyc = comm_allgather_i64(cm, {(int64_t)((changed || !have_table) ? 1 : 0)});
+        bool any_changed = false;
+        for (int g = 0; g < G; g++) any_changed |= anyc[(size_t)g] != 0;
+        if (any_changed) {
+            h->fl_table.assign((size_t)G, std::vector<void *>(6, nullptr));
+            if (cm->same_process) {
+                std::vector<int64_t> pm(6);
+                for (int k = 0; k < 6; k++) pm[(size_t)k] = (int64_t)(uintptr_t)ptrs[k];
+                const std::vector<int64_t> pa = comm_allgather_i64(cm, pm);
+                for (int g = 0; g < G; g++) for (int k = 0; k < 6; k++) h->fl_table[(size_t)g][(size_t)k] = (void *)(uintptr_t)pa[(size_t)g * 6 + k];
+            } else {
+                std::vector<uint8_t> hb(6 * 72, 0), ha((size_t)G * 6 * 72);
+                for (int k = 0; k < 6; k++) if (ptrs[k]) { SCB_FL(scb_ipc_export(h, ptrs[k], &hb[(size_t)k * 72])); hb[(size_t)k * 72 + 64] = 1; }
+                comm_check(cm->allgather(cm->ctx, hb.data(), ha.data(), (int64_t)hb.size(), 0, nullptr), "allgather (host)");
+                for (int g = 0; g < G; g++)
+                    for (int k = 0; k < 6; k++) {
+                        const uint8_t *e = &ha[((size_t)g * 6 + k) * 72];
+                        if (g == r) { h->fl_table[(size_t)g][(size_t)k] = ptrs[k]; continue; }
+                        if (!e[64]) continue;
+                        auto key = std::make_pair(g, k);
+                        auto it = h->fl_ipc.find(key);
+                        if (it == h->fl_ipc.end() || memcmp(it->second.first.data(), e, 64) != 0) {
+                            if (it != h->fl_ipc.end()) scb_ipc_close(h, it->second.second);
+                            void *mp = nullptr;
+                            SCB_FL(scb_ipc_open(h, e, &mp));
+                            h->fl_ipc[key] = std::make_pair(std::vector<uint8_t>(e, e + 64), mp);
+                        }
+                        h->fl_table[(size_t)g][(size_t)k] = h->fl_ipc[key].second;
+                    }
+            }
+        } else {
+            for (int k = 0; k < 6; k++) h->fl_table[(size_t)r][(size_t)k] = ptrs[k];
+        }
+        std::vector<scb_shard_peer> peers((size_t)G);
+        for (int g = 0; g < G; g++) {
+            scb_shard_peer &pg = peers[(size_t)g];
+            void **t = h->fl_table[(size_t)g].data();
+            pg.aux = t[0]; pg.packed = t[1]; pg.qual1 = t[2]; pg.names = t[3]; pg.seq2 = t[4]; pg.qual2 = t[5];
+            pg.row_off = 0; pg.name_off = 0;
+            for (int s2 = 0; s2 < r; s2++) { pg.row_off += mat[(size_t)s2 * 2 * G + g]; pg.name_off += mat[(size_t)s2 * 2 * G + G + g]; }
+        }
+        scb_shard_xfer y;
+        memset(&y, 0, sizeof y);
+        y.n = n_recv; y.name_bytes = nb_recv; y.packed_row_bytes = prow;
+        y.aux = (const uint64_t *)ptrs[0]; y.packed = (const uint8_t *)ptrs[1]; y.qual1 = (const uint8_t *)ptrs[2]; y.names = (const uint8_t *)ptrs[3];
+        y.seq2 = (const uint8_t *)ptrs[4]; y.qual2 = (const uint8_t *)ptrs[5];
+        // what the receive side needs to SORT goes first; the quality / mate-2 rows cross NVLink on a side stream while the received
+        // reads are sorted and are only awaited before the emit
+        SCB_FL(scb_shard_send(h, r, G, peers.data(), 1, 0)); lap(P_EXCH);
+        comm_check(cm->barrier(cm->ctx), "barrier");
+        SCB_FL(scb_shard_import(h, &y, n_chunks)); lap(P_IMPORT);
+        SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+        SCB_FL(scb_shard_finish_sort(h)); lap(P_SORT);
+        SCB_FL(scb_shard_send_wait(h)); lap(P_ROWS);
+        comm_check(cm->barrier(cm->ctx), "barrier");           // every rank's row writes have landed
+        SCB_FL(scb_shard_finish(h, out)); lap(P_EMIT);
+    } catch (scb::CudaError &e) { scb::g_last_error = e.msg; return SCB_ECUDA; }
+    catch (scb::CommError &e) { scb::g_last_error = e.msg; return SCB_ECUDA; }
+    catch (std::bad_alloc &) { scb::g_last_error = "host allocation failed"; return SCB_ENOMEM; }
+    return SCB_OK;
+}
+
+int64_t scb_shard_n_local(const scb_handle *h) { return h ? h->sh_n_local : -1; }
+
+int scb_shard_flush_stats(const scb_handle *h, float *phase_ms, int32_t cap, int32_t *rounds) {
+    if (!h) return SCB_EINVAL;
+    for (int k = 0; k < SCB_N_SHARD_PHASES && k < cap; k++) if (phase_ms) phase_ms[k] = h->fl_ms[k];
+    if (rounds) *rounds = h->fl_rounds;
+    return SCB_N_SHARD_PHASES;
+}
+
 int scb_assemble_reads(scb_handle *h, int32_t chunk, const uint8_t **body_dev, int64_t *body_bytes, int64_t *n_segments) {
     if (!h || !body_bytes) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
     if (chunk < 0 && !h->cfg.emit_merged && h->n_chunks > 1) { scb::g_last_error = "merged output was not requested (emit_merged = 0)"; return SCB_ESTATE; }
@@ -2373,6 +2598,7 @@ void scb_destroy(scb_handle *h) {
     for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+    for (auto &kv : h->fl_ipc) cudaIpcCloseMemHandle(kv.second.second);
     if (h->jx) cudaFree(h->jx);
     for (void *r : h->jx_retired) cudaFree(r);
     for (auto &r : h->rx) if (r) cudaFree(r);

@@ -34,17 +34,39 @@ constexpr uint32_t kSpRankMask = 0x00ffffffu;     // bucket rank in the low 24 b
 __global__ void __launch_bounds__(256) sp_pairs_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
                                                   const uint32_t *__restrict__ cand_rank, const uint64_t *__restrict__ doff,
                                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ pread,
-                                                  uint16_t *__restrict__ sel) {
+                                                  uint16_t *__restrict__ sel, uint32_t *__restrict__ pop /* [nb1] candidate pairs per bucket, or null */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int nc = ncand[i];
-    sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;     // start of the iteration: the first candidate (any start converges)
+    sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;     // start of the iteration: the first candidate (any start converges); sp_warm_k refines it
     const uint64_t src = cand_off[i], d = doff[i];
     for (int k = 0; k < nc; k++) {
+        if (pop) atomicAdd(&pop[cand_rank[src + k]], 1u);
         key[d + k] = (uint64_t)cand_rank[src + k];
         val[d + k] = (uint32_t)(d + k);
         pread[d + k] = (uint32_t)i;
     }
+}
+
+// Warm start of the iteration: the candidate whose bucket is a candidate of the most reads of this flush (first one on ties),
+// plus what the bucket held before. The rule "largest population wins, populations feed on wins" makes the buckets that many
+// reads can choose the likely winners; the fixed point does not depend on where the iteration starts, only the number of
+// rounds does.
+__global__ void __launch_bounds__(256) sp_warm_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
+                                                 const uint32_t *__restrict__ cand_rank, const uint32_t *__restrict__ pop,
+                                                 const uint32_t *__restrict__ base, uint16_t *__restrict__ sel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nc = ncand[i];
+    if (nc < 2) return;
+    const uint64_t src = cand_off[i];
+    uint64_t best = 0; int bk = 0;
+    for (int k = 0; k < nc; k++) {
+        const uint32_t r = cand_rank[src + k];
+        const uint64_t v = (uint64_t)pop[r] + (uint64_t)base[r] * 4u;
+        if (k == 0 || v > best) { best = v; bk = k; }
+    }
+    sel[i] = (uint16_t)bk;
 }
 
 // sorted view: read and candidate slot of the pair at sorted position s, bucket as u32
@@ -103,6 +125,7 @@ struct SpRound {
     const uint32_t *dirty;           // [nb1] round stamp: bucket b is dirty in round r iff dirty[b] == r (all zero before round 0)
     uint32_t round;
     uint8_t *tile_clean;             // [tiles] 1 = no pair of the tile belongs to a dirty bucket this round: nothing of the tile changes
+    uint32_t *n_dirty_tiles;         // counter of the round
 };
 
 // flags of the current assignment + per tile: flags in the tile's trailing segment, and whether that segment starts
@@ -123,7 +146,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_flags_k(SpRound p) {
         if (threadIdx.x == 0) p.tile_clean[blockIdx.x] = 1;
         return;
     }
-    if (threadIdx.x == 0) p.tile_clean[blockIdx.x] = 0;
+    if (threadIdx.x == 0) { p.tile_clean[blockIdx.x] = 0; atomicAdd(p.n_dirty_tiles, 1u); }
     const uint32_t klast = p.sb[tend - 1];
     uint32_t rd[kSpItems], kk[kSpItems];
 #pragma unroll
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
             if (b[j + 1] != b[j]) p.fold[b[j] & kSpRankMask] = c + ((bits >> j) & 1u);    // last pair of its bucket: every bucket at most once
         } else if (p.dirty[b[j] & kSpRankMask] == p.round) {
             p.cnt[p.sval[base + j]] = c;
-            p.ractive[p.sread[base + j]] = p.stamp;
+            if (p.ractive) p.ractive[p.sread[base + j]] = p.stamp;     // late rounds only: one more random store per pair does not pay while most tiles are dirty
         }
     }
 }

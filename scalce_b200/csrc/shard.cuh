@@ -222,6 +222,27 @@ __global__ void sub_life_k(const uint32_t *__restrict__ base, const unsigned lon
     if (i < nb1) tot[i] = base[i] - (uint32_t)life[i];
     if (i == nb1) tot[i] = 0u;
 }
+// ---- helpers of the C++ orchestrator (scb_shard_flush): column sums over the ranks' histogram rows ------------------------
+// out[c] = sum over g in [g0, g1) of rows[g * RW + c]   (u32 wrap-around = the u32 sum)
+__global__ void sh_sum_rows_k(const uint32_t *__restrict__ rows, int RW, int g0, int g1, int ncols, uint32_t *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    uint32_t v = 0;
+    for (int g = g0; g < g1; g++) v += rows[(size_t)g * RW + c];
+    out[c] = v;
+}
+// first joint round: rank 0's histogram scaled to the reads before this shard (exact for rank 1)
+__global__ void sh_guess_k(const uint32_t *__restrict__ row0, unsigned long long before, unsigned long long n0, int ncols, uint32_t *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncols) out[c] = n0 ? (uint32_t)(((unsigned long long)row0[c] * before) / n0) : 0u;
+}
+// decisions that changed on the ranks >= 1 in this round
+__global__ void sh_changed_k(const uint32_t *__restrict__ rows, int RW, int G, int ncols, unsigned long long *__restrict__ out) {
+    unsigned long long v = 0;
+    for (int g = 1; g < G; g++) v += rows[(size_t)g * RW + ncols];
+    *out = v;
+}
+
 // life[col] += global histogram of this distributed flush (root, index nb, stays local: resolve_finalize_k)
 __global__ void life_add_k(unsigned long long *__restrict__ life, const uint32_t *__restrict__ tot, int nb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

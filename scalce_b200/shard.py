@@ -117,6 +117,13 @@ class TorchComm:
         self.dist.broadcast(t, src=src)
         return t.cpu().tolist()
 
+    def allgather_bytes(self, b: bytes):
+        import torch
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
+        return [bytes(x.cpu().numpy().tobytes()) for x in self.allgather(t)]
+
+    same_process = False
+
     def all_to_all_bytes(self, send, send_counts, recv_counts, slack=0):
         """send: uint8 tensor laid out destination-major; counts in bytes. Returns the receive tensor
         (source-major) with `slack` extra bytes allocated past the end."""
@@ -250,6 +257,11 @@ class LoopbackComm:
 
     def bcast_host(self, ints, src):
         return list(self._exchange(list(ints))[src])
+
+    def allgather_bytes(self, b: bytes):
+        return [bytes(x) for x in self._exchange(bytes(b))]
+
+    same_process = True
 
     def all_to_all_bytes(self, send, send_counts, recv_counts, slack=0):
         import torch
@@ -539,4 +551,103 @@ class ShardedTransform:
                                                           for g, c in enumerate(cr) if g != r) + sum(c for g, c in enumerate(cn) if g != r)))
         out = FlushResult(self.t, res)
         out.n_local = n_local.value
+        return out
+
+
+class NcclCComm:
+    """scb_comm over NCCL made by libscalce_b200_nccl.so (csrc/comm_nccl.cpp). The unique id travels through `dist`
+    (any initialised torch.distributed group; a file or MPI would do as well)."""
+
+    def __init__(self, dist, device_index):
+        import os
+        import torch
+        from .binding import ScbComm
+        here = os.path.dirname(os.path.abspath(__file__))
+        self.lib = C.CDLL(os.path.join(here, "libscalce_b200_nccl.so"))
+        self.lib.scb_nccl_unique_id.argtypes = [C.c_void_p]
+        self.lib.scb_nccl_comm_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.POINTER(ScbComm))]
+        self.lib.scb_nccl_comm_destroy.argtypes = [C.POINTER(ScbComm)]
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        idb = (C.c_uint8 * 128)()
+        if self.rank == 0 and self.lib.scb_nccl_unique_id(idb) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+        box = [bytes(idb)]
+        dist.broadcast_object_list(box, src=0)
+        idb = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self.ptr = C.POINTER(ScbComm)()
+        if self.lib.scb_nccl_comm_create(idb, self.rank, self.world, device_index, C.byref(self.ptr)) != 0:
+            raise RuntimeError("ncclCommInitRank failed")
+        self.same_process = False
+
+    def close(self):
+        if self.ptr:
+            self.lib.scb_nccl_comm_destroy(self.ptr)
+            self.ptr = None
+
+
+class CShardedTransform:
+    """The same sharded flush through the C++ orchestrator (scb_shard_flush): the sequence of ShardedTransform.flush lives in
+    the library; this class only lends it the two collectives it asks for (scb_comm: all-gather and barrier), served by any of the
+    comm back-ends above. With libscalce_b200_nccl.so (an ncclComm_t wrapped into an scb_comm) no Python is involved at all."""
+
+    PHASES = ("scan", "chunks", "resolve", "resolve_rounds", "finalize", "hist", "pack", "exchange", "import", "sort", "exchange_rows", "emit")
+
+    def __init__(self, transform, comm, use_torch_stream=True):
+        import torch
+        from .binding import ALLGATHER_FN, BARRIER_FN, ScbComm, _check, load_library
+        self.t, self.comm = transform, comm
+        self.stats = {}
+        if isinstance(comm, NcclCComm):        # a ready-made scb_comm (libscalce_b200_nccl.so): nothing of this class is on the path
+            self._c, self._err = comm.ptr.contents, None
+            return
+        dev = torch.device("cuda", transform.cfg.device)
+        if use_torch_stream:
+            with torch.cuda.device(transform.cfg.device):
+                s = torch.cuda.current_stream().cuda_stream
+            _check(load_library().scb_set_stream(transform._h, C.c_void_p(s), 1))
+        self._err = None
+
+        def allgather(ctx, send, recv, nbytes, device, stream):
+            try:
+                nbytes = int(nbytes)
+                if device:
+                    src = _dev_bytes(send, nbytes, dev)
+                    if isinstance(comm, LoopbackComm):
+                        torch.cuda.synchronize(dev)
+                    got = comm.allgather(src)                       # [G, nbytes] on the device, ordered on the current stream
+                    _dev_bytes(recv, nbytes * comm.world, dev).copy_(got.reshape(-1))
+                    if isinstance(comm, LoopbackComm):
+                        torch.cuda.synchronize(dev)
+                else:
+                    parts = comm.allgather_bytes(C.string_at(send, nbytes))
+                    C.memmove(recv, b"".join(parts), nbytes * comm.world)
+                return 0
+            except BaseException as ex:   # noqa: BLE001 - must not propagate through the C frames
+                self._err = ex
+                return 1
+
+        def barrier(ctx):
+            try:
+                comm.barrier()
+                return 0
+            except BaseException as ex:   # noqa: BLE001
+                self._err = ex
+                return 1
+        self._cb = (ALLGATHER_FN(allgather), BARRIER_FN(barrier))      # keep the thunks alive
+        self._c = ScbComm(comm.rank, comm.world, 1 if comm.same_process else 0, 0, None, self._cb[0], self._cb[1])
+
+    def flush(self):
+        from .binding import FlushResult, ScbResult, _check, load_library
+        L = load_library()
+        res = ScbResult()
+        rc = L.scb_shard_flush(self.t._h, C.byref(self._c), C.byref(res))
+        if rc != 0 and self._err is not None:
+            raise self._err
+        _check(rc)
+        ms = (C.c_float * 12)()
+        rounds = C.c_int32()
+        L.scb_shard_flush_stats(self.t._h, ms, 12, C.byref(rounds))
+        self.stats = dict(ms=dict(zip(self.PHASES, [float(x) for x in ms])), rounds=rounds.value)
+        out = FlushResult(self.t, res)
+        out.n_local = self.t.n_local_last()
         return out

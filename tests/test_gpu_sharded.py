@@ -132,3 +132,35 @@ def test_unoverlapped_p2p_exchange_path():
     finally:
         shard.ShardedTransform.__init__ = orig
     util.assert_sharded_same(o, ranks, paired=True)
+
+
+# ---- the same cases through the C++ orchestrator (scb_shard_flush): the library runs the whole sequence, Python only lends the
+# two collectives (all-gather, barrier) ------------------------------------------------------------------------------------------
+def _case_cpp(n, L, world, **kw):
+    run_kw = {k: kw.pop(k) for k in list(kw) if k in ("use_names", "use_quals", "bucket_set_bytes", "bounds")}
+    paired = kw.get("paired", False)
+    cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, **{k: v for k, v in run_kw.items() if k != "bounds"})
+    ranks = util.run_sharded_loopback(cores, b, q1, q2, world, paired=paired, cpp=True, **run_kw)
+    util.assert_sharded_same(o, ranks, paired=paired)
+    return o, ranks
+
+
+def test_cpp_orchestrator_two_ranks():
+    o, ranks = _case_cpp(30000, 100, 2, seed=51)
+    assert ranks[1][1].stats["rounds"] >= 2 and ranks[1][1].stats["ms"]["scan"] > 0
+
+
+def test_cpp_orchestrator_shapes():
+    _case_cpp(8000, 100, 1, seed=52)
+    _case_cpp(40000, 100, 4, seed=53, bucket_set_bytes=1 << 20)
+    _case_cpp(20000, 100, 3, seed=54, paired=True, L2=75, bucket_set_bytes=1 << 20, bounds=[0, 1000, 13000, 20000])
+    _case_cpp(40000, 36, 8, seed=55, use_names=False)
+    _case_cpp(9000, 64, 4, seed=56, bounds=[0, 0, 5000, 5000, 9000])
+    _case_cpp(6000, 300, 2, seed=57, use_quals=False, bucket_set_bytes=1 << 20)
+
+
+def test_cpp_orchestrator_sparse_engine(monkeypatch):
+    monkeypatch.setenv("SCB_TABLE", "global")
+    monkeypatch.setenv("SCB_RESOLVE", "sparse")
+    _case_cpp(30000, 100, 3, seed=59, bucket_set_bytes=1 << 20)

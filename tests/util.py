@@ -79,12 +79,12 @@ def _first_diff(a, b):
 
 
 def run_sharded_loopback(cores, b, q1, q2, world, *, use_names=True, paired=False, use_quals=True, bucket_set_bytes=4 << 30,
-                         emit_merged=True, bounds=None, device=0):
+                         emit_merged=True, bounds=None, device=0, cpp=False):
     """The sharded path with `world` ranks as threads of this process on ONE GPU (LoopbackComm).
     Returns [(transform, sharded, result)] per rank."""
     import threading
     from scalce_b200.binding import BoostTransform
-    from scalce_b200.shard import LoopbackComm, ShardedTransform, shard_bounds
+    from scalce_b200.shard import CShardedTransform, LoopbackComm, ShardedTransform, shard_bounds
     n = b.seq.shape[0]
     L1 = b.seq.shape[1]
     L2 = b.seq2.shape[1] if paired else 0
@@ -101,7 +101,7 @@ def run_sharded_loopback(cores, b, q1, q2, world, *, use_names=True, paired=Fals
             if z > a:
                 t.submit(b.seq[a:z], q1[a:z] if (use_quals and q1 is not None) else None, b.names, b.name_off[a:z + 1],
                          b.seq2[a:z] if paired else None, q2[a:z] if (paired and use_quals and q2 is not None) else None)
-            st = ShardedTransform(t, comms[r])
+            st = CShardedTransform(t, comms[r]) if cpp else ShardedTransform(t, comms[r])   # cpp: the sequence runs inside scb_shard_flush
             out[r] = (t, st, st.flush())
         except BaseException as e:   # noqa: BLE001 - unblock the other ranks, then re-raise in the caller
             errs.append(e)

@@ -7,6 +7,8 @@ export PYTHONUNBUFFERED=1
 tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 echo "== parity, default"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29501 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
 echo "== parity, joint kernel + early emit"; SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29502 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
+echo "== parity, C++ orchestrator + NCCL comm library"; SCB_ORCH=cpp_nccl timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29504 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
+echo "== parity, C++ orchestrator + torch collectives"; SCB_ORCH=cpp timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29505 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
 echo "== parity, sparse engine"; SCB_RESOLVE=sparse SCB_TABLE=global timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29503 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
 run() {
   local name=$1; shift
