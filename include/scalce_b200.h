@@ -87,7 +87,8 @@ typedef struct scb_batch {
 typedef struct scb_result {
     int64_t n_reads;
     int32_t n_chunks;
-    int32_t n_buckets_nonempty;       /* distinct non-empty buckets over the whole flush */
+    int32_t n_buckets_nonempty;       /* distinct non-empty buckets over the whole flush; filled when the flush has one chunk or
+                                         emit_merged is set (it is the number of merged meta records), 0 otherwise */
     const uint8_t *data[SCB_N_STREAMS];
     const int64_t *chunk_off[SCB_N_STREAMS];
     /* post-merge order (emit_merged): one set of streams, meta already merged */
@@ -212,7 +213,10 @@ int scb_shard_resolve_local(scb_handle *h, uint32_t *tot_dev);
  * count; first: 1 for the first round. tot_dev as above, last word = decisions that changed. */
 int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t reads_before, int32_t first, uint32_t *tot_dev);
 /* Commits the converged assignment. global_tot_dev: device u32[n_cols], bucket histogram summed over all
- * ranks (adds to the lifetime counts of EVERY rank's handle); n_global: reads of the whole flush. */
+ * ranks (adds to the lifetime counts of EVERY rank's handle); n_global: reads of the whole flush.
+ * Exception: the no-core (root) bucket is counted by every rank for its own shard only - nothing reads it for the
+ * tie-break - so after a sharded flush scb_unbucketed() and scb_lifetime_count(h, -1) are rank-local: sum them over
+ * the ranks for the value unbuck() (reads.cpp:502) would report. */
 /* Opt-in alternative to the host-driven loop of scb_shard_resolve_round + all-gather: ALL joint rounds inside one kernel
  * per rank. The ranks exchange their histogram rows through peer memory (stores over NVLink into every rank's exchange
  * buffer, system-scope flags) - no host and no NCCL in the loop. Needs one process per GPU with peer access.

@@ -15,15 +15,12 @@
 #include "pipeline.cuh"
 #include "prims.cuh"
 #include "resolve_dense.cuh"
-#include "scan_smem.cuh"
 #include "scan_smem2.cuh"
 #include "scan_big.cuh"
 #include "resolve_sparse.cuh"
 #include "emit2.cuh"
 #include "emit_offsets.cuh"
-#include "emit_coresident.cuh"
 #include "emit_reads_fast.cuh"
-#include "emit_names_fast.cuh"
 #include "shard.cuh"
 #include "container.cuh"
 
@@ -175,8 +172,6 @@ struct scb_handle {
     const uint64_t *srt_keys = nullptr;                    // sorted keys of the chunk-major order
     int srt_seg_bits = 0;
     bool srt_keys_valid = false;   // scb_shard_finish_sort ran: scb_shard_finish only emits
-    // opt-in overlap of the flush-chunk pass with the tie-break (SCB_OVERLAP_CHUNKS): state between its two halves
-    bool chunks_begun = false; uint32_t *chk_cstart = nullptr; int chk_cap = 0; int *chk_nch_pinned = nullptr; cudaEvent_t ev_chk = nullptr;
     bool emit_early_done = false;  // scb_shard_finish_early ran: scb_shard_finish only runs the kernels that read quality / mate-2 rows
     Pending sh_local;          // the rank's own input after scb_shard_import replaced `cur` (phase-2 sends still read it)
     // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
@@ -406,13 +401,11 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     o.n_seg = 0;
     if (n == 0) { for (int k = 0; k < SCB_N_STREAMS; k++) o.data[k].alloc(0, st); return; }
 
-    DevBuf hsum((size_t)(n + 1) * 4, st), ws32((size_t)scan_tiles(n) * 4, st), ws64((size_t)scan_tiles(n) * 8, st);
+    DevBuf hsum((size_t)(n + 1) * 4, st);
     DevBuf ms((size_t)n * 8, st), offN((size_t)(n + 1) * 8, st), offR((size_t)(n + 1) * 8, st);
     KeyHead kh{keys, seg_shift, seg_bits};
     uint64_t totN = 0, totR = 0; uint32_t nseg = 0;
-    const bool fused_scan = env_on("SCB_EMIT_FUSED_SCAN", true);
-    if (fused_scan) {
-        // metadata gather + the three prefix sums in 3 launches (emit_offsets.cuh): emit 10.62 -> 10.26 ms at 50M x 150; "0" = the generic scans
+    {   // metadata gather + the three prefix sums in 3 launches (emit_offsets.cuh)
         const int64_t nt = scan_tiles(n);
         DevBuf ts((size_t)3 * nt * 8, st), tot3(32, st);
         SCB_LAUNCH(emit_off_reduce_k, (unsigned)nt, kScanThreads, 0, st, h->meta_in.as<uint64_t>(), perm, kh, n, L1, sz_meta, (int)cfg.use_names,
@@ -421,15 +414,6 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         SCB_LAUNCH(emit_off_apply_k, (unsigned)nt, kScanThreads, 0, st, ms.as<uint64_t>(), kh, n, L1, sz_meta, (int)cfg.use_names, ts.as<uint64_t>(), nt,
                    tot3.as<uint64_t>(), hsum.as<uint32_t>(), offN.as<uint64_t>(), offR.as<uint64_t>());
         if (cfg.use_names) SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    } else {
-    // the one random small gather of the output side: per-read metadata into output order
-    SCB_LAUNCH(gather_meta_k, (unsigned)cdiv(n, 256), 256, 0, st, h->meta_in.as<uint64_t>(), perm, n, ms.as<uint64_t>());
-    exclusive_scan<uint32_t>(kh, n, hsum.as<uint32_t>(), hsum.as<uint32_t>() + n, ws32.as<uint32_t>(), st);
-    if (cfg.use_names) {
-        exclusive_scan<uint64_t>(NameRecM{ms.as<uint64_t>()}, n, offN.as<uint64_t>(), offN.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
-        SCB_CUDA(cudaMemcpyAsync(&totN, offN.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    }
-    exclusive_scan<uint64_t>(ReadRecM{ms.as<uint64_t>(), L1, sz_meta}, n, offR.as<uint64_t>(), offR.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
     }
     SCB_CUDA(cudaMemcpyAsync(&totR, offR.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(&nseg, hsum.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
@@ -460,51 +444,24 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     cudaStream_t sN = rows_now ? h->st_aux[0] : st, sR = h->st_aux[1];
     if (sN != st) SCB_CUDA(cudaStreamWaitEvent(sN, h->ev_fork, 0));
     SCB_CUDA(cudaStreamWaitEvent(sR, h->ev_fork, 0));
-    // opt-in (not yet measured): the three output kernels as co-resident persistent grids (emit_coresident.cuh)
-    const char *cr_env = getenv("SCB_EMIT_CORESIDENT");
-    const bool cores_mode = cr_env && atoi(cr_env) != 0 && rows_now && cfg.use_quals && L1 >= 16;
-    int dev_sms = kSMs;
-    if (cores_mode) SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
-    if (cfg.use_names) {
-        if (cores_mode) SCB_LAUNCH(emit_names_loop_k, (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)dev_sms * 2), 256, 0, sN, e, cdiv(n, 256));
-        else if (env_on("SCB_EMIT_NAMES_V2", false)) SCB_LAUNCH(emit_names_fast_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);   // opt-in, not yet measured
-        else SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
-    }
-    {
-        const uint32_t NW = (uint32_t)((sz_read(L1) + sz_meta + 3) / 4);
+    if (cfg.use_names) SCB_LAUNCH(emit_names_st_k, (unsigned)cdiv(n, 256), 256, 0, sN, e);
+    {   // packed reads + end markers (emit_reads_fast.cuh): rows staged per CTA, records assembled in shared memory
         const int recmax = sz_read(L1) + sz_meta;
         const int PWs = (h->PW + kEmitRowPad) | 1;
         const int per_read = recmax + PWs * 4;
         const int RPB = std::max(1, std::min(256, (40 * 1024) / per_read));
         const size_t smem = (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15) + (size_t)RPB * PWs * 4 + 16;
-        const uint32_t inv_pws = (uint32_t)(((1ull << 32) + PWs - 1) / PWs);
-        // emit_reads_fast.cuh: emit 10.62 -> 10.25 ms at 50M x 150. Rows of one or two words (reads of <= 32 bases) stay with
-        // emit_reads_st_k: that shape of the new kernel has not run on a GPU since its index fix. "0" = emit_reads_st_k
-        const char *rv2 = getenv("SCB_EMIT_READS_V2");
-        const int rv2_mode = rv2 && *rv2 ? atoi(rv2) : 1;            // 2 = also for one- and two-word rows (to test that shape)
-        if (rv2_mode != 0 && (h->PW >= 3 || rv2_mode >= 2)) {
-            const uint32_t half = (uint32_t)((h->PW & 1) == 0 && (((uintptr_t)h->packed.p) & 7) == 0 ? h->PW / 2 : h->PW);
-            const uint32_t inv_half = (uint32_t)(((1ull << 32) + half - 1) / half);
-            const int64_t n_blk = cdiv(n, RPB);
-            SCB_CUDA(cudaFuncSetAttribute(emit_reads_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SCB_LAUNCH(emit_reads_fast_k, (unsigned)(cores_mode ? std::min<int64_t>(n_blk, (int64_t)dev_sms * 2) : n_blk), 256, smem, sR, e, RPB, inv_half, recmax, n_blk);
-        } else if (cores_mode) {
-            SCB_CUDA(cudaFuncSetAttribute(emit_reads_loop_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SCB_LAUNCH(emit_reads_loop_k, (unsigned)std::min<int64_t>(cdiv(n, RPB), (int64_t)dev_sms * 2), 256, smem, sR, e, RPB, NW, inv_pws, recmax, cdiv(n, RPB));
-        } else {
-        SCB_CUDA(cudaFuncSetAttribute(emit_reads_st_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_LAUNCH(emit_reads_st_k, (unsigned)cdiv(n, RPB), 256, smem, sR, e, RPB, NW, inv_pws, recmax);
-        }
+        const uint32_t half = (uint32_t)((h->PW & 1) == 0 && (((uintptr_t)h->packed.p) & 7) == 0 ? h->PW / 2 : h->PW);
+        const uint32_t inv_half = (uint32_t)(((1ull << 32) + half - 1) / half);     // half == 1: the kernel does not use it
+        const int64_t n_blk = cdiv(n, RPB);
+        SCB_CUDA(cudaFuncSetAttribute(emit_reads_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_LAUNCH(emit_reads_fast_k, (unsigned)n_blk, 256, smem, sR, e, RPB, inv_half, recmax, n_blk);
     }
     if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
     if (sN != st) SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
     SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
-    auto gather_rows_loop = [&](const uint8_t *src, uint8_t *dst, int L) {
-        const int64_t n_blk = cdiv(cdiv(n * L, 16), 256 * kGatherChunks);   // < 2^31: n < 2^31 rows of <= 2047 bytes, 12 KB per block
-        SCB_LAUNCH(gather_rows16_loop_k, (unsigned)std::min<int64_t>(n_blk, (int64_t)dev_sms * 3), 256, 0, st, src, dst, perm, n, L, (int)n_blk);
-    };
-    if (cfg.use_quals && rows_now) { if (cores_mode) gather_rows_loop(c.qual1, oQ, L1); else gather_rows(c.qual1, oQ, L1); }
-    if (cfg.paired && cfg.use_quals && rows_now) { if (cores_mode && L2 >= 16) gather_rows_loop(c.qual2, oQ2, L2); else gather_rows(c.qual2, oQ2, L2); }
+    if (cfg.use_quals && rows_now) gather_rows(c.qual1, oQ, L1);
+    if (cfg.paired && cfg.use_quals && rows_now) gather_rows(c.qual2, oQ2, L2);
     if (sN != st) SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
     SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
@@ -595,8 +552,7 @@ static void stage_scan(scb_handle *h) {
         const int R = W * 32;
         if (W >= 2 && n > 0 && ((uintptr_t)c.seq1 & 15) == 0 && !(force && !strcmp(force, "global"))) {
             const size_t smem = scan_smem_total(h->tab.n_states, h->n_hit, nb, W, L1, PW);
-            const bool scan_v2 = env_on("SCB_SCAN_V2", true);   // pick + emit merged (scan_smem2.cuh): 8.07 -> 7.63 ms at 50M x 150; "0" = scan_smem_k
-            SCB_CUDA(cudaFuncSetAttribute(scan_v2 ? scan_smem2_k : scan_smem_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCB_CUDA(cudaFuncSetAttribute(scan_smem2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev_sms = 0;
             SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
             DevBuf dtot(8, st);
@@ -616,8 +572,7 @@ static void stage_scan(scb_handle *h) {
                 sp.packed = h->packed.as<uint32_t>(); sp.PW = PW;
                 sp.inv_pw = (uint32_t)(((1ull << 32) + (uint64_t)PW - 1) / (uint64_t)PW); sp.pitch = pitch;
                 int grid = (int)std::min<int64_t>(dev_sms, cdiv(sp.n_tiles, W));
-                if (scan_v2) SCB_LAUNCH(scan_smem2_k, grid, R, smem, st, sp);
-                else SCB_LAUNCH(scan_smem_k, grid, R, smem, st, sp);
+                SCB_LAUNCH(scan_smem2_k, grid, R, smem, st, sp);
                 SCB_CUDA(cudaMemcpyAsync(&M, dtot.p, 8, cudaMemcpyDeviceToHost, st));
                 SCB_CUDA(cudaStreamSynchronize(st));
                 if (M <= cap) scanned = true; else cap = M;   // list space was short: rerun with the exact size
@@ -627,8 +582,7 @@ static void stage_scan(scb_handle *h) {
     if (!scanned && h->big_table && n > 0 && ((uintptr_t)c.seq1 & 3) == 0 && !(getenv("SCB_SCAN") && !strcmp(getenv("SCB_SCAN"), "global"))) {
         // automaton in global memory / L2 (scan_big.cuh): pack, then one lane per read walks with 32 warps per SM in flight
         const int PW = h->PW;
-        const char *qe = getenv("SCB_BIG_Q");            // per-lane queue of max-level hits: 32 (default, 32 warps / SM) or 16 (64 warps / SM)
-        const int Q = qe && atoi(qe) == 16 ? 16 : 32;
+        const int Q = 32;            // per-lane queue of max-level hits; 16 (64 warps / SM instead of 32) measured no faster: the kernel is L2-rate bound
         const size_t smem = scan_big_smem_bytes(kBigThreads, Q);
         void (*kbig)(ScanBigParams) = Q == 16 ? scan_big_k<16> : scan_big_k<32>;
         SCB_CUDA(cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -844,9 +798,9 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
-    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, false, false>, W * 32, smem));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, true>, W * 32, smem));
     if (occ < 1) return false;
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
@@ -890,11 +844,7 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     rp.nblk = (int)blk.size() - 1; rp.nb1 = nb1; rp.W = W; rp.status = h->sh_stat.as<int>(); rp.rounds_out = h->sh_stat.as<int>() + 1;
     rp.g0 = g0; rp.mode = mode; rp.tot_out = tot_out; rp.pitch = P;
     rp.S0 = h->sh_S0.as<uint32_t>(); rp.H0 = h->sh_H0.as<uint32_t>(); rp.fr_buf = h->sh_frbuf.as<uint32_t>(); rp.fr_idx = h->sh_fridx.as<uint32_t>(); rp.fr_used = h->sh_frused.as<uint32_t>();
-    {
-        const char *e = getenv("SCB_RESOLVE_INCR");      // decision-margin threshold of the incremental rounds; 0 = every round sweeps in full
-        rp.incr_T = e ? atoi(e) : 1024;
-        if (nb1 > 0xffff) rp.incr_T = 0;                 // records hold bucket ranks in 16 bits
-    }
+    rp.incr_T = nb1 > 0xffff ? 0 : 1024;             // decision-margin threshold of the incremental rounds (records hold bucket ranks in 16 bits)
     rp.incr_stat = (getenv("SCB_RESOLVE_PROF") || getenv("SCB_RESOLVE_STAT")) ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
     rp.stale = h->sh_stale.as<uint32_t>(); rp.n_stale = h->sh_nstale.as<uint32_t>();
     if (mode == 0 || mode == 3) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
@@ -904,16 +854,9 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
     if (joint) rp.j = *joint; else memset(&rp.j, 0, sizeof rp.j);
     void *args[] = {&rp};
-    // opt-in (not yet measured): the guess round of every block as a streaming pass (resolve_dense.cuh, CHEAP)
-    const char *cg = getenv("SCB_RESOLVE_CHEAP_GUESS");
-    const bool cheap = cg && atoi(cg) != 0;
-    void *kfn = (void *)resolve_dense_k<false, false, false>;
-    const bool defer = env_on("SCB_RESOLVE_DEFER", false);   // opt-in (not yet measured): deferred re-sweeps
-    if (mode == 3) kfn = cheap ? (defer ? (void *)resolve_dense_k<true, true, true> : (void *)resolve_dense_k<true, true, false>)
-                               : (defer ? (void *)resolve_dense_k<true, false, true> : (void *)resolve_dense_k<true, false, false>);   // all joint rounds in this launch (JOINT)
-    else if (cheap) kfn = (void *)resolve_dense_k<false, true, false>;
-    else if (mode == 0 && defer) kfn = (void *)resolve_dense_k<false, false, true>;
-    if (kfn != (void *)resolve_dense_k<false, false, false>) SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // deferred re-sweeps (resolve_dense.cuh): 9.03 -> 8.43 ms at 50M x 150, profiles/r02_resolve_ab.txt
+    void *kfn = mode == 3 ? (void *)resolve_dense_k<true, true> : (void *)resolve_dense_k<false, true>;   // mode 3: all joint rounds in this launch
+    SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SCB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
     if (mode != 0 && mode != 3) {
@@ -956,8 +899,7 @@ static std::vector<int64_t> dense_blocks(int64_t n, int64_t g0) {
     const int64_t first = 4096;
     // early blocks are bound by the fixed cost of a round, not by their sweeps: they grow faster (x growth_small)
     // until the input before them reaches `small`
-    const char *e1 = getenv("SCB_RESOLVE_GROWTH"), *e2 = getenv("SCB_RESOLVE_SMALL");
-    const int64_t growth_small = e1 ? std::max(2, atoi(e1)) : 4, small = e2 ? atoll(e2) : (1 << 20);
+    const int64_t growth_small = 4, small = 1 << 20;     // x8 / x16 growth and later switch-over points were measured and lost (profiles/r02_resolve_ab.txt)
     while (blk.back() < n) {
         const int64_t n0 = blk.back(), before = n0 + g0;
         const int64_t len = before < small ? (growth_small - 1) * before : before;
@@ -1042,39 +984,6 @@ static void stage_meta(scb_handle *h) {
 
 }
 
-// 3a. (opt-in, SCB_OVERLAP_CHUNKS=1; not yet measured) the size prefix sum and the chunk boundaries only need the scan's
-// levels, not the tie-break: enqueue them on a side stream BEFORE the resolve kernel is launched. That kernel holds
-// one CTA of 384 threads per SM and is latency bound; the small streaming kernels fit next to it. stage_chunks then only
-// reads the chunk count back and writes the per-read chunk ids.
-static void chunks_begin(scb_handle *h) {
-    const scb_config &cfg = h->cfg;
-    const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
-    const Pending &c = h->cur;
-    const int64_t n = c.n;
-    cudaStream_t sa = h->st_aux[0];
-    if (!h->ev_chk) SCB_CUDA(cudaEventCreateWithFlags(&h->ev_chk, cudaEventDisableTiming));
-    if (!h->chk_nch_pinned) SCB_CUDA(cudaHostAlloc((void **)&h->chk_nch_pinned, 64, cudaHostAllocDefault));
-    SCB_CUDA(cudaEventRecord(h->ev_fork, h->st));
-    SCB_CUDA(cudaStreamWaitEvent(sa, h->ev_fork, 0));
-    DevBuf ws64((size_t)scan_tiles(n) * 8, sa);
-    const int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
-    RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
-    DevBuf S((size_t)(n + 1) * 8, sa);
-    exclusive_scan<uint64_t>(rs, n, S.as<uint64_t>(), S.as<uint64_t>() + n, ws64.as<uint64_t>(), sa);
-    uint64_t max_rd = 256 + (uint64_t)sz_read(L1) + L1 + sz_read(L2) + L2 + 40;
-    uint64_t cap64 = (uint64_t)n * max_rd / cfg.bucket_set_bytes + 2;
-    if (cap64 > (uint64_t)n + 1) cap64 = (uint64_t)n + 1;
-    if (cap64 > (1u << 24)) throw CudaError{"bucket_set_bytes too small for this many reads (more than 2^24 flush chunks)"};
-    const int cap = (int)cap64;
-    DevBuf cstart((size_t)cap * 4, sa), dn(4, sa);
-    SCB_LAUNCH(chunk_bounds_k, 1, 1, 0, sa, S.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, cstart.as<uint32_t>(), cap, dn.as<int>());
-    SCB_CUDA(cudaMemcpyAsync(h->chk_nch_pinned, dn.p, 4, cudaMemcpyDeviceToHost, sa));
-    SCB_CUDA(cudaEventRecord(h->ev_chk, sa));
-    h->chk_cstart = cstart.as<uint32_t>();   // arena memory: stays valid until the flush ends
-    h->chk_cap = cap;
-    h->chunks_begun = true;
-}
-
 // 3. sizes -> flush chunks (compress.cpp:702, 708-713)
 static void stage_chunks(scb_handle *h) {
     cudaStream_t st = h->st;
@@ -1084,21 +993,6 @@ static void stage_chunks(scb_handle *h) {
     const int64_t n = c.n;
     const int nb = h->tab.n_buckets;
     (void)st; (void)cfg; (void)L1; (void)L2; (void)c; (void)n; (void)nb;
-    if (h->chunks_begun) {   // second half of the overlapped variant
-        h->chunks_begun = false;
-        SCB_CUDA(cudaEventSynchronize(h->ev_chk));
-        SCB_CUDA(cudaStreamWaitEvent(st, h->ev_chk, 0));
-        const int nch = *h->chk_nch_pinned;
-        if (nch > h->chk_cap) throw CudaError{"internal: chunk capacity exceeded"};
-        h->n_chunks = nch;
-        if (nch > 1) {
-            h->chunk.alloc((size_t)n * 4, st);
-            SCB_LAUNCH(chunk_ids_k, (unsigned)cdiv(n, 256), 256, 0, st, h->chk_cstart, nch, n, h->chunk.as<uint32_t>());
-        } else {
-            h->chunk.release();
-        }
-        return;
-    }
     DevBuf ws64((size_t)scan_tiles(n) * 8, st);
     {
         int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
@@ -1149,12 +1043,10 @@ static void stage_sort(scb_handle *h) {
     int pb;
     {
         double per_bucket = (double)std::max<int64_t>(n, 1) / ((double)(nb + 1) * (double)nch);
-        if (getenv("SCB_SORT_PER_BUCKET")) per_bucket *= (double)nch;   // the old sizing, for A/B runs
         int need = 6;
         while (need < 32 && std::pow(4.0, need - 6) < per_bucket) need++;
         int total_bits = std::min(64, ((seg_bits + 2 * need + 7) / 8) * 8);
         pb = std::min(L1, (total_bits - seg_bits) / 2);
-        if (getenv("SCB_SORT_FULLKEY")) pb = std::min(L1, (64 - seg_bits) / 2);
     }
     DevBuf &k0 = h->srt_k0, &k1 = h->srt_k1, &v1 = h->srt_v1, &hist = h->srt_hist, &histws = h->srt_histws;
     k0.alloc((size_t)n * 8, st); k1.alloc((size_t)n * 8, st); v1.alloc((size_t)n * 4, st);
@@ -1796,11 +1688,6 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->stage_ev[0], st));
     stage_scan(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[1], st));
-    h->chunks_begun = false;
-    {
-        const char *oc = getenv("SCB_OVERLAP_CHUNKS");
-        if (oc && atoi(oc) != 0 && h->cur.n > 0) chunks_begin(h);
-    }
     stage_resolve(h);
     stage_meta(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
@@ -2023,6 +1910,14 @@ int scb_submit(scb_handle *h, const scb_batch *b) {
             SCB_CUDA(cudaStreamSynchronize(st));
             if (o[0] != 0) { scb::g_last_error = "device batches must have name_off[0] == 0"; return SCB_EINVAL; }
             p.name_bytes = o[1];
+            // the same contract as for host batches: every name 0..255 bytes (the reference's length byte, names.cpp:48-62)
+            scb::DevBuf rng(16, st);
+            SCB_CUDA(cudaMemsetAsync(rng.p, 0, 16, st));
+            SCB_LAUNCH(scb::name_len_range_k, (unsigned)scb::cdiv(b->n, 256), 256, 0, st, b->name_off, b->n, rng.as<long long>());
+            long long r2[2] = {0, 0};
+            SCB_CUDA(cudaMemcpyAsync(r2, rng.p, 16, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            if (r2[0] > 255 || r2[1] > 0) { scb::g_last_error = "name length outside 0..255"; return SCB_EINVAL; }
         }
     } else {
         auto up = [&](scb::DevBuf &d, const void *src, size_t bytes) {
@@ -2593,8 +2488,6 @@ void scb_destroy(scb_handle *h) {
     for (auto &e : h->stage_ev) if (e) cudaEventDestroy(e);
     for (auto &a : h->st_aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_chk) cudaEventDestroy(h->ev_chk);
-    if (h->chk_nch_pinned) cudaFreeHost(h->chk_nch_pinned);
     for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);

@@ -422,55 +422,6 @@ __device__ __forceinline__ uint32_t spk_bits32(const uint32_t *row, int b0) {
     const int k = b0 >> 4, sh = (b0 & 15) * 2;
     return __funnelshift_l(row[k + 1], row[k], sh);
 }
-__global__ void __launch_bounds__(256) emit_reads_st_k(EmitMParams e, int RPB, uint32_t NW, uint32_t inv_pws, int recmax) {
-    extern __shared__ __align__(16) uint8_t sbd[];
-    // layout: record bytes [RPB*recmax + 48] | rows [RPB][PW + pad] u32 (odd pitch)
-    const int PWs = (e.PW + kEmitRowPad) | 1;
-    uint32_t *s_rows = (uint32_t *)(sbd + (((size_t)RPB * recmax + 48 + 15) & ~(size_t)15));
-    const int64_t p0 = (int64_t)blockIdx.x * RPB, p1 = (p0 + RPB < e.n) ? p0 + RPB : e.n;
-    const int np = (int)(p1 - p0);
-    const uint64_t g0 = e.offR[p0];
-    const int len = (int)(e.offR[p1] - g0);
-    uint8_t *sb = sbd + (int)(g0 & 15);
-    {   // rows: PW words each (+ zero pad), fetched once per read
-        const uint32_t items = (uint32_t)np * (uint32_t)PWs;
-        for (uint32_t t = threadIdx.x; t < items; t += 256) {
-            const uint32_t pl = __umulhi(t, inv_pws), k = t - pl * (uint32_t)PWs;
-            s_rows[t] = k < (uint32_t)e.PW ? ldg_g64(e.packed + (int64_t)e.perm[p0 + pl] * e.PW + k) : 0u;
-        }
-    }
-    __syncthreads();
-    // one thread per read: decode the metadata once, then walk the record 16 bases (4 bytes) at a time
-    for (int pl = threadIdx.x; pl < np; pl += 256) {
-        const uint64_t m = e.ms[p0 + pl];
-        // output_read(read, dest, end-level, level): bases [end, L) then [0, end-level); reads.cpp:432-461
-        const int lv = meta_lvl(m), end = meta_end(m);
-        const int tail = e.L1 - end, total = e.L1 - lv;
-        const int nbytes = sz_read(total);
-        const int recsz = nbytes + e.sz_meta;
-        const uint32_t *row = s_rows + (size_t)pl * PWs;
-        uint8_t *d = sb + (int)(e.offR[p0 + pl] - g0);
-        for (int w = 0; 4 * w < recsz; w++) {
-            uint32_t v = 0;
-            const int j0 = 16 * w;
-            if (4 * w < nbytes) {
-                int a = tail - j0; a = a < 0 ? 0 : (a > 16 ? 16 : a);
-                int nv = total - j0; nv = nv > 16 ? 16 : nv;
-                if (a > 0) v = spk_bits32(row, end + j0) & (a == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * a)));
-                if (a < 16) v |= spk_bits32(row, j0 + a - tail) >> (2 * a);
-                if (nv < 16) v &= ~(0xffffffffu >> (2 * nv));
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int b = 4 * w + k;                           // byte index inside the record
-                if (b < nbytes) d[b] = (uint8_t)(v >> (24 - 8 * k));
-                else if (b < recsz) d[b] = (uint8_t)((uint32_t)end >> (8 * (b - nbytes)));   // low bytes of int16 end, reads.cpp:130
-            }
-        }
-    }
-    __syncthreads();
-    flush_staged(e.oR, g0, len, sbd);
-}
 
 // ---- stream 4: mate 2 is packed without rotation (output_read(read2, dest, 0, 0), compress.cpp:696) ----
 __global__ void emit_reads2_k(const uint8_t *__restrict__ seq2, const uint32_t *__restrict__ perm, int64_t n, int L2,

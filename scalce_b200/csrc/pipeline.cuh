@@ -142,6 +142,20 @@ struct RdSize {  // rd.sz + sizeof(bin_node), compress.cpp:675-702
     }
 };
 
+// name lengths of a device-resident batch: out[0] = max length, out[1] = max of -length (i.e. -min); out pre-set to 0
+__global__ void __launch_bounds__(256) name_len_range_k(const int64_t *__restrict__ name_off, int64_t n, long long *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long len = 0;
+    if (i < n) len = (long long)(name_off[i + 1] - name_off[i]);
+    long long mx = len, mn = -len;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mx, d), b = __shfl_xor_sync(0xffffffffu, mn, d);
+        mx = a > mx ? a : mx; mn = b > mn ? b : mn;
+    }
+    if (lane_id() == 0) { if (mx > 0) atomicMax(out, mx); if (mn > 0) atomicMax(out + 1, mn); }
+}
+
 // S[0..n] exclusive prefix of RdSize (S[n] = total). A chunk ends with the first read that brings
 // the running sum to >= B (compress.cpp:708-713). One thread; a binary search per chunk.
 __global__ void chunk_bounds_k(const uint64_t *__restrict__ S, int64_t n, uint64_t B, uint32_t *chunk_start, int cap,

@@ -261,43 +261,6 @@ __device__ __forceinline__ uint32_t rd_sweep(const RdParams &p, int64_t lo, int6
     return changed;
 }
 
-// Guess round of a block as a STREAMING pass (opt-in, template parameter CHEAP of resolve_dense_k): every read is decided
-// independently from its subtile's (extrapolated) start counts - no lane tags, no in-step iteration, several reads per
-// lane in flight. The guess only chooses where the fixed-point iteration starts; tools/sim_resolve.c shows the same
-// number of rounds per block and the same change counts from the second round on as with a sequential guess sweep
-// (111 rounds at 50M reads either way). acc = the warp's (all-zero) lane-tag row, used as the subtile's histogram and
-// folded into the counters at the end, because the E phase takes "counters - start counts" as the histogram.
-__device__ __forceinline__ uint32_t rd_sweep_static(const RdParams &p, int64_t lo, int64_t hi, uint32_t *cnt, uint32_t *acc) {
-    const uint32_t l = lane_id();
-    uint32_t changed = 0;
-    constexpr int U = 4;
-    for (int64_t g = lo; g < hi; g += 32 * U) {
-        int nc[U]; uint64_t off[U]; uint32_t so[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int64_t i = g + u * 32 + l;
-            nc[u] = 0; off[u] = 0; so[u] = kNoSel;
-            if (i < hi) { nc[u] = p.ncand[i]; off[u] = p.cand_off[i]; so[u] = p.sel[i]; }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (nc[u] > 0) {
-                uint32_t bc = 0, br = 0; int bk = 0;
-                for (int k = 0; k < nc[u]; k++) {
-                    const uint32_t r = p.cand_rank[off[u] + k];
-                    const uint32_t c = cnt[r];
-                    if (k == 0 || c > bc) { bc = c; bk = k; br = r; }   // first arg-max, strict > (reads.cpp:420-421)
-                }
-                atomicAdd(&acc[br], 1u);
-                if ((uint32_t)bk != so[u]) { p.sel[g + u * 32 + l] = (uint16_t)bk; changed++; }
-            }
-    }
-    __syncwarp();
-    for (int b = l; b < p.nb1; b += 32) { cnt[b] += acc[b]; acc[b] = 0; }
-    __syncwarp();
-    return changed;
-}
-
 // replay of a subtile's fragile list (see above), 32 records at a time, one per lane. row[] holds on entry
 // (new start count - start count of the full sweep) per bucket and accumulates the deviations of the reads replayed so
 // far, so a candidate's count now = count recorded at the full sweep + row[bucket]. Lanes evaluate in parallel; a lane
@@ -380,14 +343,15 @@ __device__ __forceinline__ void rd_row_add(uint32_t *row, const uint32_t *g, int
 // rank's row of the previous round has arrived (system-scope flags in my exchange buffer), stop if no rank changed
 // anything, build the populations before my shard (lifetime + rows of the lower ranks) in this CTA's own copy, run
 // the round as in modes 1-2, then CTA 0 pushes my row into every rank's buffer and raises my flag there.
-// DEFER = true (opt-in, mode 0): a subtile whose margin bound fails is NOT swept in full in the same round. Today it is, and the whole
+// DEFER = true (the default since it won its A/B run: 9.03 -> 8.43 ms at 50M x 150): a subtile whose margin bound fails is NOT swept
+// in full in the same round. Otherwise it is, and the whole
 // round - two grid syncs, ~1775 other warps that only replay - waits for that one sequential sweep; tools/sim_resolve.c counts such
 // straggler sweeps in rounds 3-8 of every large block and, with a simple time model that reproduces the measured 9 ms, attributes ~15 %
 // of the kernel to them. Deferred: the subtile keeps the replay's result (fragile reads exact, the others possibly outdated) and is
 // marked stale; when a round changes nothing anywhere, the stale subtiles are swept in full in the next round (which rebuilds their
 // lists), and the block is finished by a quiet round without stale subtiles. A subtile whose bound holds again is not stale: the bound
 // only compares the current state with the last full sweep. Exactness as before: at termination every read was re-decided exactly.
-template <bool JOINT, bool CHEAP, bool DEFER>
+template <bool JOINT, bool DEFER>
 __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams p) {
     extern __shared__ __align__(16) uint32_t sm_cnt[];   // [W][pitch] populations, then [W][pitch] per-step lane tags
     const int W = p.W, nb1 = p.nb1, P = p.pitch, Q = p.pitch >> 2;   // Q = 128-bit quads per row
@@ -559,8 +523,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
                         for (int q = l; q < Q; q += 32) ((uint4 *)S0row)[q] = ((const uint4 *)cnt)[q];
                         __syncwarp();
                     }
-                    if (CHEAP && first) ch += rd_sweep_static(p, lo, hi, cnt, tagw);
-                    else ch += rd_sweep(p, lo, hi, cnt, tagw, fr);
+                    ch += rd_sweep(p, lo, hi, cnt, tagw, fr);
                     if (p.incr_T > 0 && l == 0) p.fr_used[t] = list ? fr.recs : kFrNone;
                     if (DEFER && l == 0) p.stale[t] = 0u;
                     stat_full = 1;

@@ -1,4 +1,6 @@
-// scan_smem.cuh - core scan with the automaton resident in shared memory.
+// scan_smem.cuh - core scan with the automaton resident in shared memory: parameter block, shared-memory layout and the
+// device helpers (tile staging, SWAR 2-bit packing, the DFA step). The kernel is scan_smem2_k (scan_smem2.cuh); its
+// predecessor scan_smem_k, whose pipeline is described here, was removed after it lost its A/B run (8.07 vs 7.63 ms).
 //
 // Persistent kernel, one CTA per SM; every WARP runs its own pipeline over tiles of 32 reads and never
 // waits for another warp (no block barriers after the table is loaded), so the stalls of one warp's phase
@@ -118,176 +120,6 @@ __device__ __forceinline__ bool seen_before_smem(const uint32_t *row, int p, uin
         if (st >= (uint32_t)d.H0 && d.hit_rank[st - d.H0] == r) return true;
     }
     return false;
-}
-
-__global__ void __launch_bounds__(1024, 1) scan_smem_k(ScanSmemParams p) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    // layout: trans | hit_rank | rank_level | pad16 | per warp: ASCII tile (+32) | packed tile | hit queues | hit masks
-    uint16_t *s_trans = (uint16_t *)sm;
-    uint32_t *s_hit = (uint32_t *)(sm + (size_t)p.ns * 8);
-    uint8_t *s_lvl = (uint8_t *)(s_hit + p.n_hit);
-    const int L = p.L, PW = p.PW, pitch = p.pitch;
-    const int w = threadIdx.x >> 5, W = blockDim.x >> 5, l = lane_id();
-    uint8_t *s_tile = sm + scan_smem_table_bytes(p.ns, p.n_hit, p.nb) + (size_t)w * scan_smem_warp_bytes(L, PW);
-    uint32_t *s_pk = (uint32_t *)(s_tile + (size_t)32 * L + 32);
-    uint16_t *s_q = (uint16_t *)(s_pk + (size_t)32 * pitch);
-    uint16_t *s_hm = s_q + (size_t)32 * kHitQ;
-
-    for (int k = threadIdx.x; k < p.ns * 2; k += blockDim.x) ((uint32_t *)s_trans)[k] = ((const uint32_t *)p.trans)[k];
-    for (int k = threadIdx.x; k < p.n_hit; k += blockDim.x) s_hit[k] = p.hit_rank[k];
-    for (int k = threadIdx.x; k < p.nb; k += blockDim.x) s_lvl[k] = p.rank_level[k];
-    __syncthreads();                                  // the only block barrier: from here on warps run alone
-    const uint32_t H4 = (uint32_t)p.H0 * 4u;
-    const SmemDfa d{s_trans, s_hit, s_lvl, p.H0};
-    const int full = L >> 4, tail = L & 15;
-    const uint32_t *row = s_pk + (size_t)l * pitch;
-    uint16_t *q = s_q + (size_t)l * kHitQ;
-    uint16_t *hm = s_hm + (size_t)l * PW;
-    const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(q);
-    const uint8_t *tb = (const uint8_t *)s_trans;
-    uint64_t c_cur = 0, c_end = 0;                    // this warp's slice of the candidate arrays (uniform across lanes)
-
-    const int64_t stride = (int64_t)gridDim.x * W;
-    int64_t tile = (int64_t)w * gridDim.x + blockIdx.x;   // neighbouring CTAs take neighbouring tiles
-    if (tile < p.n_tiles) stage_warp_tile(p, tile, s_tile);
-    cp_async_commit();
-    for (; tile < p.n_tiles; tile += stride) {
-        cp_async_wait<0>();
-        __syncwarp();
-        int rows = (int)((p.n - tile * 32 < 32) ? (p.n - tile * 32) : 32);
-        // ---- A: pack ----------------------------------------------------------------------------------
-        {
-            const uint32_t nwords = (uint32_t)rows * (uint32_t)PW;
-            const uint32_t *tw = (const uint32_t *)s_tile;
-            uint32_t *gp = p.packed + tile * (int64_t)32 * PW;
-            for (uint32_t t = l; t < nwords; t += 32) {
-                const uint32_t r = PW == 1 ? t : __umulhi(t, p.inv_pw), k = t - r * (uint32_t)PW;   // ceil(2^32 / 1) does not fit 32 bits
-                const uint32_t b = r * (uint32_t)L + 16u * k;
-                const uint32_t *a = tw + (b >> 2);
-                const uint32_t sh = (b & 3u) * 8u;
-                const uint32_t x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3], x4 = a[4];   // the tile has 32 bytes of slack
-                const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
-                               y3 = __funnelshift_r(x3, x4, sh);
-                uint32_t bad = 0;
-                uint32_t wv = (pack4(y0, bad) << 24) | (pack4(y1, bad) << 16) | (pack4(y2, bad) << 8) | pack4(y3, bad);
-                if (bad) wv = (pack4_masked(y0) << 24) | (pack4_masked(y1) << 16) | (pack4_masked(y2) << 8) | pack4_masked(y3);
-                const int nv = L - 16 * (int)k;                   // valid bases of this word (>= 1)
-                if (nv < 16) wv &= ~(0xffffffffu >> (2 * nv));
-                s_pk[r * (uint32_t)pitch + k] = wv;
-                gp[t] = wv;
-            }
-        }
-        __syncwarp();
-        {   // the ASCII buffer is free again: the warp's next tile streams in under phases B-D
-            const int64_t nxt = tile + stride;
-            if (nxt < p.n_tiles) stage_warp_tile(p, nxt, s_tile);
-            cp_async_commit();
-        }
-        // ---- B: walk -----------------------------------------------------------------------------------
-        const int64_t i = tile * 32 + l;
-        const bool live = l < rows;
-        int nh = 0, best = 0, cnt = 0, first_kept = 0;
-        bool slow = false;
-        if (live) {
-            uint32_t e4 = 0;                                  // current state * 4
-            uint32_t qp = q0;                                 // 32-bit shared address of the queue's next slot
-            for (int k = 0; k < full && !slow; k++) {
-                if (qp - q0 > 2u * (kHitQ - kHitQGuard)) { slow = true; break; }
-                const uint32_t wv = row[k];
-                uint32_t m = 0;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const uint32_t c2 = (j < 15 ? (wv >> (29 - 2 * j)) : (wv << 1)) & 6u;      // code * 2
-                    e4 = *(const uint16_t *)(tb + (e4 * 2u + c2));
-                    if (e4 >= H4) { m |= 1u << j; sts_u16(qp, e4); qp += 2; }
-                }
-                hm[k] = (uint16_t)m;
-            }
-            if (tail && !slow) {
-                if (qp - q0 > 2u * (kHitQ - kHitQGuard)) slow = true;
-                else {
-                    const uint32_t wv = row[full];
-                    uint32_t m = 0;
-                    for (int j = 0; j < tail; j++) {
-                        const uint32_t c2 = ((wv >> (30 - 2 * j)) & 3u) * 2u;
-                        e4 = *(const uint16_t *)(tb + (e4 * 2u + c2));
-                        if (e4 >= H4) { m |= 1u << j; sts_u16(qp, e4); qp += 2; }
-                    }
-                    hm[full] = (uint16_t)m;
-                }
-            }
-            nh = (int)((qp - q0) >> 1);
-            // ---- C: pick ------------------------------------------------------------------------------
-            if (!slow) {
-                // one pass: a hit of a higher level restarts the list; within the level keep first occurrences.
-                // q[j] becomes the bucket rank (n_buckets < 2^14 here) or 0xffff for a dropped hit.
-                for (int j = 0; j < nh; j++) {
-                    const uint32_t r = s_hit[((uint32_t)q[j] >> 2) - p.H0];
-                    const int lv = s_lvl[r];
-                    if (lv > best) { best = lv; cnt = 0; first_kept = j; }
-                    bool drop = lv != best;
-                    for (int k = first_kept; k < j && !drop; k++) drop = (q[k] == r);
-                    q[j] = drop ? (uint16_t)0xffffu : (uint16_t)r;
-                    cnt += drop ? 0 : 1;
-                }
-            } else {
-                // more hits than the queue holds: full walk with inline dedupe
-                uint32_t st2 = 0;
-                for (int qq = 0; qq < L; qq++) {
-                    st2 = dfa_step(d, st2, pk_code(row, qq));
-                    if (st2 >= (uint32_t)p.H0) {
-                        const uint32_t r = s_hit[st2 - p.H0];
-                        const int lv = s_lvl[r];
-                        if (lv > best) { best = lv; cnt = 0; }
-                        if (lv == best && !seen_before_smem(row, qq, r, d)) cnt++;
-                    }
-                }
-            }
-        }
-        // ---- D: candidate space from the warp's slice (refilled in chunks from the global counter) -------
-        const uint32_t v = live ? (uint32_t)cnt : 0u;
-        const uint32_t inc = warp_incl_scan(v);
-        const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
-        if (c_cur + wtot > c_end) {
-            unsigned long long take = wtot > (uint32_t)kCandChunk ? wtot : (uint32_t)kCandChunk, got = 0;
-            if (l == 0) got = atomicAdd(p.cand_total, take);
-            got = __shfl_sync(0xffffffffu, got, 0);
-            c_cur = got; c_end = got + take;
-        }
-        const uint64_t o = c_cur + (inc - v);
-        c_cur += wtot;
-        if (live) {
-            p.lvl[i] = (uint8_t)best;
-            p.ncand[i] = (uint16_t)cnt;
-            p.cand_off[i] = o;
-            if (o + (uint64_t)cnt <= p.cand_cap) {
-                if (!slow) {
-                    int c2 = 0, j = 0;
-                    for (int k = 0; k < PW && c2 < cnt; k++) {
-                        uint32_t m = hm[k];
-                        while (m) {
-                            const int bpos = __ffs(m) - 1;
-                            m &= m - 1;
-                            const uint32_t r = (j >= first_kept) ? (uint32_t)q[j] : 0xffffu;
-                            j++;
-                            if (r != 0xffffu) { p.cand_rank[o + c2] = r; p.cand_pos[o + c2] = (uint16_t)(16 * k + bpos); c2++; }
-                        }
-                    }
-                } else {
-                    uint32_t st2 = 0; int c2 = 0;
-                    for (int qq = 0; qq < L; qq++) {
-                        st2 = dfa_step(d, st2, pk_code(row, qq));
-                        if (st2 >= (uint32_t)p.H0) {
-                            const uint32_t r = s_hit[st2 - p.H0];
-                            if ((int)s_lvl[r] == best && !seen_before_smem(row, qq, r, d)) { p.cand_rank[o + c2] = r; p.cand_pos[o + c2] = (uint16_t)qq; c2++; }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();   // packed tile, queues and masks are reused by the warp's next iteration
-    }
-    cp_async_wait<0>();
 }
 
 }  // namespace scb

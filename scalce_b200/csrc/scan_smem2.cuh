@@ -1,5 +1,5 @@
-// scan_smem2.cuh - the shared-memory scan kernel in use since the end of round 1 (8.07 -> 7.63 ms at 50M x 150 bp;
-// SCB_SCAN_V2=0 selects its predecessor scan_smem_k, whose pipeline description applies here too).
+// scan_smem2.cuh - the shared-memory scan kernel (8.07 -> 7.63 ms at 50M x 150 bp against its predecessor scan_smem_k,
+// since removed; the pipeline description in scan_smem.cuh applies).
 //
 // Same pipeline per warp tile (A pack, B walk: identical code), but the pick and emit phases are ONE pass over the
 // hits instead of two divergent loops (SASS of scan_smem_k: ~200 warp instructions per tile in the pick loop, ~380 in

@@ -1,19 +1,9 @@
-"""Opt-in variants that were written without GPU access (end of round 1) and have NOT been measured or
-run on a B200 yet. They are off by default in the product path. This file is not collected by the default run
-(no test_ prefix): tests/test_zz_gpu_experimental.py runs it in ONE child process with a hard time limit and reports
-the outcome as pass / xfail, so that an unverified variant can neither turn the GPU suite red, nor poison its CUDA
-context, nor hang it. Run it directly with
-    SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q
+"""Opt-in variants of the sharded run that are off by default until an 8-GPU run decides (see tools/r2_multi.sh), and the C++ host
+tool end to end. Not collected by the default run (no test_ prefix): tests/test_zz_gpu_experimental.py runs this file in a child
+process when SCB_RUN_EXPERIMENTAL=1. Run directly with  SCB_TEST_EXPERIMENTAL=1 python -m pytest tests/experimental_cases.py -q
 
   SCB_SHARD_JOINT_KERNEL=1 all joint tie-break rounds inside one kernel per rank, histograms exchanged through peer memory
   SCB_SHARD_EARLY_EMIT=1   names / packed reads / meta records are emitted while the quality rows still travel
-  SCB_EMIT_CORESIDENT=1    the three output kernels as co-resident persistent grids (emit_coresident.cuh)
-  SCB_RESOLVE_DEFER=1       tie-break: a subtile whose margin bound fails keeps replaying and is swept in full only after a quiet round
-  SCB_RESOLVE_CHEAP_GUESS=1 the guess round of every tie-break block as a streaming pass (no sequential sweep)
-  SCB_EMIT_NAMES_V2=1      stream-0 writer with word stores into the staging buffer (emit_names_fast.cuh, emit_name.h)
-  SCB_OVERLAP_CHUNKS=1     size prefix sum + flush-chunk boundaries on a side stream under the tie-break kernel
-  (SCB_SCAN_V2, SCB_EMIT_READS_V2 and SCB_EMIT_FUSED_SCAN passed these cases on a B200 at the end of round 1, won their A/B runs
-  and are the default now; "=0" selects the previous kernels, tests/test_gpu_parity.py::test_previous_kernels_still_selectable)
 
 Same bar as everywhere else: bit-exact against the oracle.
 """
@@ -52,93 +42,7 @@ def test_early_emit_four_ranks(monkeypatch):
     _sharded(30000, 100, 4, seed=157)
 
 
-@pytest.mark.parametrize("var", ["SCB_RESOLVE_DEFER", "SCB_EMIT_NAMES_V2", "SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS", "SCB_SORT_PER_BUCKET"])
-def test_single_gpu_variants(monkeypatch, var):
-    monkeypatch.setenv(var, "1")
-    for kw in (dict(n=20000, L=100, seed=161), dict(n=12000, L=150, seed=162, bucket_set_bytes=1 << 20),
-               dict(n=8000, L=36, seed=163, lower=0.3), dict(n=3000, L=300, seed=164), dict(n=10000, L=100, seed=165, paired=True, L2=75)):
-        run_kw = {k: kw.pop(k) for k in list(kw) if k in ("bucket_set_bytes",)}
-        n, L = kw.pop("n"), kw.pop("L")
-        paired = kw.get("paired", False)
-        cores, b, q1, q2, _ = util.make_case(n, L, **kw)
-        o = util.run_oracle(cores, b, q1, q2, paired=paired, **run_kw)
-        t, r = util.run_cuda(cores, b, q1, q2, paired=paired, **run_kw)
-        util.assert_same(o, t, r, paired=paired)
-
-
-def test_scan_v2_dense_core_set_and_queue_overflow(monkeypatch):
-    # (passed on a B200; the kernel is the default now - kept as a regression case) many hits per read: the queue overflows on some reads (slow path, L slots reserved) and the candidate arrays are
-    # re-sized by the second attempt
-    monkeypatch.setenv("SCB_SCAN_V2", "1")
-    import itertools
-    from scalce_b200 import synth
-    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]   # every position hits (tests/test_gpu_parity.py)
-    b = synth.make_batch(2000, 80, seed=171)
-    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
-    o = util.run_oracle(cores, b, q1, None)
-    t, r = util.run_cuda(cores, b, q1, None)
-    util.assert_same(o, t, r)
-
-
-def test_scan_v2_million_reads(monkeypatch):
-    monkeypatch.setenv("SCB_SCAN_V2", "1")
-    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=172, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
-    o = util.run_oracle(cores, b, q1, q2)
-    t, r = util.run_cuda(cores, b, q1, q2)
-    util.assert_same(o, t, r)
-
-
-def test_all_single_gpu_variants_together_million_reads(monkeypatch):
-    for var in ("SCB_EMIT_CORESIDENT", "SCB_OVERLAP_CHUNKS", "SCB_RESOLVE_CHEAP_GUESS"):
-        monkeypatch.setenv(var, "1")
-    cores, b, q1, q2, _ = util.make_case(1000000, 150, seed=173, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)],
-                                         paired=True, L2=100)
-    o = util.run_oracle(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
-    t, r = util.run_cuda(cores, b, q1, q2, paired=True, bucket_set_bytes=64 << 20)
-    util.assert_same(o, t, r, paired=True)
-
-
 # ---- the C++ host tool end to end (scalce_b200/host/scb_boost.cpp): FASTQ -> temp files == the oracle's chunk streams ----
-@pytest.mark.parametrize("paired", [False, True])
-def test_host_tool_temp_files_match_oracle(tmp_path, paired):
-    import subprocess
-    from scalce_b200 import build as bld, synth
-    tool = bld.build_host_tool()
-    cores, b, q1, q2, _ = util.make_case(30000, 100, seed=181, paired=paired, L2=75 if paired else None)
-    o = util.run_oracle(cores, b, q1, q2, paired=paired, bucket_set_bytes=1 << 21)
-    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
-    synth.write_fastq(b, f1, f2 if paired else None)
-    (tmp_path / "cores.txt").write_text("\n".join(cores) + "\n")
-    out = tmp_path / "out"
-    out.mkdir()
-    cmd = [tool, f1] + (["-r", f2] if paired else []) + ["-P", str(tmp_path / "cores.txt"), "-o", str(out), "-B", str(1 << 21), "--merged", "--batch", "7001"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode == 0, r.stderr.decode()
-    nf = 6 if paired else 4
-    assert o.n_chunks > 1
-    for c in range(o.n_chunks):
-        for k in range(nf):
-            assert (out / f"t_{c:03d}_{k}.tmp").read_bytes() == o.stream(k, c), f"chunk {c} stream {k}"
-    assert not (out / f"t_{o.n_chunks:03d}_0.tmp").exists()
-    for k in range(nf):
-        assert (out / f"merged_{k}.tmp").read_bytes() == o.stream(k, -1), f"merged stream {k}"
-
-
-def test_emit_reads_v2_odd_row_words_and_long_reads(monkeypatch):
-    # PW odd (4-byte staging path), 2-byte end markers, cores at the very start / end of reads (planted). On a B200 at the end of
-    # round 1: L = 40 and 300 passed, L = 17 (rows of two words, one 8-byte item per row) exposed an index bug (ceil(2^32 / 1) in
-    # 32 bits); fixed, not re-run - which is why reads of <= 32 bases still take the previous kernel by default.
-    monkeypatch.setenv("SCB_EMIT_READS_V2", "1")
-    for kw in (dict(n=9000, L=40, seed=191), dict(n=5000, L=300, seed=192), dict(n=4000, L=272, seed=194, plant=0.9), dict(n=6000, L=50, seed=195),
-               dict(n=3000, L=250, seed=196)):
-        n, L = kw.pop("n"), kw.pop("L")
-        cores, b, q1, q2, _ = util.make_case(n, L, **kw)
-        o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
-        t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
-        util.assert_same(o, t, r)
-
-
-# ---- joint tie-break rounds inside one kernel per rank (SCB_SHARD_JOINT_KERNEL=1): needs one PROCESS per GPU ----------------
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_joint_kernel_over_nvlink(world):
     import subprocess
@@ -149,106 +53,6 @@ def test_joint_kernel_over_nvlink(world):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + world), os.path.join(root, "tests", "sharded_nccl_worker.py"), "120000", "100", str(1 << 21)]
-    env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1", SCB_RESOLVE_DEFER="1" if world != 2 else "0")
+    env = dict(os.environ, SCB_SHARD_JOINT_KERNEL="1", SCB_SHARD_EARLY_EMIT="1")
     r = subprocess.run(cmd, cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_NCCL_OK" in r.stdout, r.stdout[-4000:]
-
-
-def test_cheap_guess_round_sharded_and_tied(monkeypatch):
-    # the streaming guess round in the sharded run's first joint round, and on inputs where almost every read is tied
-    monkeypatch.setenv("SCB_RESOLVE_CHEAP_GUESS", "1")
-    _sharded(40000, 100, 4, seed=201, bucket_set_bytes=1 << 20)
-    _sharded(9000, 64, 4, seed=202, bounds=[0, 0, 5000, 5000, 9000])
-    import itertools
-    from scalce_b200 import synth
-    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]
-    b = synth.make_batch(20000, 80, seed=203)
-    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
-    o = util.run_oracle(cores, b, q1, None)
-    t, r = util.run_cuda(cores, b, q1, None)
-    util.assert_same(o, t, r)
-
-
-def test_cheap_guess_round_million_reads_second_flush(monkeypatch):
-    # two flushes on one handle: the second starts from large lifetime populations (g0 > 0 in the extrapolation)
-    monkeypatch.setenv("SCB_RESOLVE_CHEAP_GUESS", "1")
-    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=204, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
-    o = util.run_oracle(cores, b, q1, q2, splits=[600000])
-    t, r = util.run_cuda(cores, b, q1, q2, splits=[600000])
-    util.assert_same(o, t, r)
-
-
-def test_host_tool_fastq_to_container_matches_reference_golden(tmp_path):
-    """FASTQ -> scb_boost --container (C++ host stages + the CUDA transform + container assembly) == the files the unmodified
-    reference CLI wrote (tests/golden), for every fixture."""
-    import glob
-    import hashlib
-    import subprocess
-    from scalce_b200 import build as bld, synth
-    from tests import test_oracle_golden as tg
-    tool = bld.build_host_tool()
-    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))):
-        z, meta = tg._load(path)
-        cores, b = tg._inputs(z, meta)
-        d = tmp_path / os.path.basename(path)[:-4]
-        d.mkdir()
-        f1, f2 = str(d / "in_1.fastq"), str(d / "in_2.fastq")
-        synth.write_fastq(b, f1, f2 if meta["paired"] else None)
-        (d / "cores.txt").write_text("\n".join(cores) + "\n")
-        bucket = {"4G": 4 << 30, "1M": 1 << 20}[meta["bucket"]]
-        cmd = [tool, f1] + (["-r", f2] if meta["paired"] else []) + ["-P", str(d / "cores.txt"), "-B", str(bucket), "--container", str(d / "out"),
-                                                                       "--library", "lib"] + ([] if meta["use_names"] else ["-n"])
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-        assert r.returncode == 0, r.stderr.decode()
-        for mate in range(1 + int(meta["paired"])):
-            for ext in "nrq":
-                k = f"{mate + 1}{ext}"
-                data = (d / f"out_{mate + 1}.scalce{ext}").read_bytes()
-                assert hashlib.sha256(data).hexdigest() == meta["sha"][k], f"{os.path.basename(path)} {k}: differs from the reference CLI output"
-
-
-def test_emit_reads_v2_short_rows(monkeypatch):
-    # rows of one or two words (reads of <= 32 bases): SCB_EMIT_READS_V2=2 forces the new stream-1 writer there too
-    monkeypatch.setenv("SCB_EMIT_READS_V2", "2")
-    for kw in (dict(n=7000, L=17, seed=193), dict(n=5000, L=32, seed=197), dict(n=4000, L=16, seed=198, spec=[(8, 200), (9, 100)])):
-        n, L = kw.pop("n"), kw.pop("L")
-        cores, b, q1, q2, _ = util.make_case(n, L, **kw)
-        o = util.run_oracle(cores, b, q1, q2)
-        t, r = util.run_cuda(cores, b, q1, q2)
-        util.assert_same(o, t, r)
-
-
-def test_emit_names_v2_long_and_ragged_names(monkeypatch):
-    # names of 0..60 bytes (several 16-byte chunks, every alignment of the record in the staging buffer)
-    monkeypatch.setenv("SCB_EMIT_NAMES_V2", "1")
-    import numpy as np
-    from scalce_b200 import synth
-    cores, b, q1, q2, _ = util.make_case(12000, 100, seed=211)
-    rng = np.random.default_rng(5)
-    lens = rng.integers(0, 61, size=b.n)
-    lens[:50] = np.arange(50) % 34                       # every length around the 15 / 16 / 31 / 32 byte boundaries early in a tile
-    off = np.zeros(b.n + 1, dtype=np.int64)
-    np.cumsum(lens, out=off[1:])
-    b.names = rng.integers(33, 127, size=int(off[-1]), dtype=np.uint8)
-    b.name_off = off
-    o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
-    t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
-    util.assert_same(o, t, r)
-
-
-def test_resolve_defer_large_and_tied(monkeypatch):
-    # deferred re-sweeps on inputs where the margin bound fails often: 1M reads of the headline core set (blocks of up to 500k reads),
-    # a second flush on large lifetime populations, and a dense core set where almost every read is tied
-    monkeypatch.setenv("SCB_RESOLVE_DEFER", "1")
-    cores, b, q1, q2, _ = util.make_case(1000000, 100, seed=221, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
-    o = util.run_oracle(cores, b, q1, q2, splits=[400000])
-    t, r = util.run_cuda(cores, b, q1, q2, splits=[400000])
-    util.assert_same(o, t, r)
-    import itertools
-    from scalce_b200 import synth
-    cores = ["".join(p) for p in itertools.product("ACGT", repeat=4)]
-    b = synth.make_batch(60000, 80, seed=222)
-    q1 = util.orc.quality_payload(b.qual, b.seq, 33)
-    o = util.run_oracle(cores, b, q1, None)
-    t, r = util.run_cuda(cores, b, q1, None)
-    util.assert_same(o, t, r)

@@ -171,9 +171,35 @@ def test_mid_size_tie_groups():
     util.assert_same(o, t, r)
 
 
-@pytest.mark.parametrize("var", ["SCB_SCAN_V2", "SCB_EMIT_FUSED_SCAN", "SCB_EMIT_READS_V2"])
-def test_previous_kernels_still_selectable(monkeypatch, var):
-    # the kernels these switches replaced at the end of round 1 (scan_smem_k, the generic offset scans, emit_reads_st_k)
-    monkeypatch.setenv(var, "0")
-    _case(20000, 100, seed=71)
-    _case(6000, 150, seed=72, paired=True, L2=100, bucket_set_bytes=1 << 20)
+def test_reads_of_16_32_and_odd_lengths():
+    # rows of one or two packed words (<= 32 bases): PW = 1 broke the reciprocal row index of the scan's pack phase in round 1
+    # (ceil(2^32 / 1) does not fit 32 bits); odd row words and 2-byte end markers take the 4-byte staging path of the stream-1 writer
+    _case(7000, 17, seed=193)
+    _case(5000, 32, seed=197)
+    _case(4000, 16, seed=198, spec=[(8, 200), (9, 100)])
+    _case(9000, 40, seed=191, bucket_set_bytes=1 << 20)
+    _case(4000, 272, seed=194, plant=0.9, bucket_set_bytes=1 << 20)
+    _case(3000, 250, seed=196)
+
+
+def test_long_and_ragged_names():
+    # names of 0..60 bytes: every alignment of the stream-0 record in the writer's staging buffer
+    cores, b, q1, q2, _ = util.make_case(12000, 100, seed=211)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 61, size=b.n)
+    lens[:50] = np.arange(50) % 34
+    off = np.zeros(b.n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    b.names = rng.integers(33, 127, size=int(off[-1]), dtype=np.uint8)
+    b.name_off = off
+    o = util.run_oracle(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    t, r = util.run_cuda(cores, b, q1, q2, bucket_set_bytes=1 << 20)
+    util.assert_same(o, t, r)
+
+
+def test_second_flush_with_large_populations_dense_engine():
+    # two flushes on one handle: the second starts from large lifetime populations (g0 > 0 in the dense engine's extrapolation)
+    cores, b, q1, q2, _ = util.make_case(600000, 100, seed=204, plant=0.0, spec=[(8, 1024), (9, 512), (10, 256), (11, 128), (12, 128)])
+    o = util.run_oracle(cores, b, q1, q2, splits=[350000])
+    t, r = util.run_cuda(cores, b, q1, q2, splits=[350000])
+    util.assert_same(o, t, r)

@@ -503,46 +503,6 @@ def test_bench_native_arm_cpu_baseline_fields():
     assert d["e2e"] is None
 
 
-def test_store_bytes16_every_alignment_and_length(tmp_path):
-    """scalce_b200/csrc/emit_name.h (compiled into the opt-in stream-0 writer): up to 16 bytes from four words to any byte
-    alignment with head bytes / word stores / tail bytes - checked for every (alignment, length) pair, neighbours untouched,
-    under the address and undefined-behaviour sanitizers."""
-    import subprocess
-    hdr = os.path.join(ROOT, "scalce_b200", "csrc", "emit_name.h")
-    src = tmp_path / "en_test.cpp"
-    src.write_text(r'''
-#include "%s"
-#include <cstdio>
-#include <cstring>
-#include <random>
-using namespace scb;
-int main() {
-    std::mt19937 rng(3);
-    alignas(16) uint8_t buf[64];
-    long cases = 0;
-    for (int rep = 0; rep < 100; rep++)
-        for (int s = 0; s < 8; s++)
-            for (int n = 0; n <= 16; n++) {
-                uint32_t w[4]; for (auto &x : w) x = rng();
-                uint8_t b[16]; memcpy(b, w, 16);
-                memset(buf, 0xAA, sizeof buf);
-                store_bytes16(buf + 8 + s, w[0], w[1], w[2], w[3], n);
-                for (int i = 0; i < 64; i++) {
-                    const int k = i - (8 + s);
-                    if (buf[i] != ((k >= 0 && k < n) ? b[k] : 0xAA)) { printf("MISMATCH s %%d n %%d at %%d\n", s, n, i); return 1; }
-                }
-                cases++;
-            }
-    printf("ok %%ld\n", cases);
-    return 0;
-}
-''' % hdr)
-    exe = tmp_path / "en_test"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fsanitize=address,undefined", "-o", str(exe), str(src)], check=True)
-    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode == 0 and r.stdout.startswith(b"ok"), (r.stdout + r.stderr).decode()
-
-
 def test_stream1_checker_against_the_oracle():
     """tests/util.py::stream1_window_matches (the torch check the full-size GPU test applies to stream 1 at 50M reads) must accept
     the oracle's stream 1 and reject a corrupted one. Output order recovered from the (unique) names in the oracle's stream 0."""
