@@ -191,7 +191,7 @@ struct scb_handle {
     bool sp_ready = false;
     int64_t sp_M = 0;
     DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev, sp_tile_clean, sp_ractive;
-    bool sp_warm = false; uint32_t sp_dirty_tiles = 0;
+    uint32_t sp_dirty_tiles = 0;
     uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
@@ -688,13 +688,9 @@ static void sparse_setup(scb_handle *h) {
     {
         DevBuf k0((size_t)M1 * 8, st), k1((size_t)M1 * 8, st), v0((size_t)M1 * 4, st), v1((size_t)M1 * 4, st), pread((size_t)M1 * 4, st);
         DevBuf hist((size_t)SortWs::hist_elems(M1) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(M1)) * 4, st);
-        const bool warm = env_on("SCB_SPARSE_WARM", true);      // warm start of the iteration by candidate-pair populations (sp_warm_k); "0" = first candidate
-        h->sp_warm = warm;
-        if (warm) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));   // sp_hist doubles as the pair-population scratch until the rounds start
         if (n > 0)
             SCB_LAUNCH(sp_pairs_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
-                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>(),
-                       warm ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr);
+                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>());
         if (M > 0) {
             SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
             uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
@@ -719,9 +715,6 @@ static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
     if (M == 0 || n == 0) { if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st)); return; }
     const int64_t tiles = cdiv(M, kSpTile);
     const uint32_t round = h->sp_round++;
-    if (round == 0 && h->sp_warm)     // sp_hist still holds the candidate-pair populations of sp_pairs_k
-        SCB_LAUNCH(sp_warm_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
-                   h->sp_hist.as<uint32_t>(), base, h->sh_sel.as<uint16_t>());
     if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
     // reads are marked active (one more random store per rewritten count) only once few tiles are dirty; before that every read re-decides
     const bool use_active = round > 0 && (uint64_t)h->sp_dirty_tiles * 4 < (uint64_t)tiles;

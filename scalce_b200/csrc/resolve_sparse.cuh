@@ -34,39 +34,19 @@ constexpr uint32_t kSpRankMask = 0x00ffffffu;     // bucket rank in the low 24 b
 __global__ void __launch_bounds__(256) sp_pairs_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
                                                   const uint32_t *__restrict__ cand_rank, const uint64_t *__restrict__ doff,
                                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ pread,
-                                                  uint16_t *__restrict__ sel, uint32_t *__restrict__ pop /* [nb1] candidate pairs per bucket, or null */) {
+                                                  uint16_t *__restrict__ sel) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int nc = ncand[i];
-    sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;     // start of the iteration: the first candidate (any start converges); sp_warm_k refines it
+    // start of the iteration: the first candidate. Any start converges to the same fixed point; a warm start by candidate-pair
+    // populations ("the bucket most reads can choose") was measured and needed MORE rounds (36 vs 30 at 50M reads x 1M cores).
+    sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;
     const uint64_t src = cand_off[i], d = doff[i];
     for (int k = 0; k < nc; k++) {
-        if (pop) atomicAdd(&pop[cand_rank[src + k]], 1u);
         key[d + k] = (uint64_t)cand_rank[src + k];
         val[d + k] = (uint32_t)(d + k);
         pread[d + k] = (uint32_t)i;
     }
-}
-
-// Warm start of the iteration: the candidate whose bucket is a candidate of the most reads of this flush (first one on ties),
-// plus what the bucket held before. The rule "largest population wins, populations feed on wins" makes the buckets that many
-// reads can choose the likely winners; the fixed point does not depend on where the iteration starts, only the number of
-// rounds does.
-__global__ void __launch_bounds__(256) sp_warm_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
-                                                 const uint32_t *__restrict__ cand_rank, const uint32_t *__restrict__ pop,
-                                                 const uint32_t *__restrict__ base, uint16_t *__restrict__ sel) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int nc = ncand[i];
-    if (nc < 2) return;
-    const uint64_t src = cand_off[i];
-    uint64_t best = 0; int bk = 0;
-    for (int k = 0; k < nc; k++) {
-        const uint32_t r = cand_rank[src + k];
-        const uint64_t v = (uint64_t)pop[r] + (uint64_t)base[r] * 4u;
-        if (k == 0 || v > best) { best = v; bk = k; }
-    }
-    sel[i] = (uint16_t)bk;
 }
 
 // sorted view: read and candidate slot of the pair at sorted position s, bucket as u32
