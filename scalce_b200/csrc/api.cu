@@ -1230,7 +1230,7 @@ static void shard_scan(scb_handle *h) {
     ArenaScope arena_scope(&h->arena);
     h->sh_phase = 0;
     h->emit_early_done = false;
-    flush_begin(h, 2.0);   // room for the send arrays; the receive side reuses the slab after the exchange
+    flush_begin(h, 1.25);  // room for the send side (owner sort, aux words, staged names: ~50 B per read); the receive side reuses the slab after the exchange
     const int64_t n = h->cur.n;
     h->sh_n_local = n;
     h->n_perm = 0;
