@@ -432,6 +432,9 @@ def main():
                          "threads, so step k+1's H2D runs while step k's result drains over the other PCIe direction (flushes serialised)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded parity check that precedes the timed steps")
+    ap.add_argument("--orchestrator", default="cpp", choices=["cpp", "python"],
+                    help="N > 1: who runs the sharded sequence - the library (scb_shard_flush over libscalce_b200_nccl.so, C++ + NCCL, the default) "
+                         "or scalce_b200/shard.py over torch.distributed")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -519,8 +522,11 @@ def main():
     if world > 1:
         # the global input is the concatenation of the ranks' batches in rank order; results are the single-GPU
         # (= reference -T 1) order of that input, each rank emitting a contiguous slice of the bucket order
-        from scalce_b200.shard import ShardedTransform, TorchComm
-        sharded = ShardedTransform(tr, TorchComm(dist, dev))
+        from scalce_b200.shard import CShardedTransform, NcclCComm, ShardedTransform, TorchComm
+        if a.orchestrator == "cpp":
+            sharded = CShardedTransform(tr, NcclCComm(dist, local), use_torch_stream=True)   # library work + NCCL on torch's current stream: the events below see it
+        else:
+            sharded = ShardedTransform(tr, TorchComm(dist, dev))
 
     # flushes per step: one, unless the flush workspace would not fit next to the resident inputs
     F = a.flushes
@@ -739,7 +745,8 @@ def main():
                                 "table": "shared memory (u16 transitions)" if info["smem_resident"] else "global memory / L2 (u32 transitions)", "tie_break_engine": engine},
                    "l2": f"inputs ({h2d / 1e9:.1f} GB per step) far exceed the 126 MB L2",
                    "timing": ("CUDA events on the library stream around scb_flush; one handle, bucket populations reset between steps" if world == 1 else
-                              "CUDA events on the rank's stream (library work and NCCL collectives are ordered on it) around submit + sharded flush, max over ranks"),
+                              "CUDA events on the rank's stream (library work and NCCL collectives are ordered on it; the side stream of the row exchange is joined before the emit) around submit + sharded flush, max over ranks"),
+                   "orchestrator": ("n/a" if world == 1 else ("scb_shard_flush (C++) + libscalce_b200_nccl.so" if a.orchestrator == "cpp" else "scalce_b200/shard.py + torch.distributed")),
                    "multi_gpu": ("n/a" if world == 1 else "contiguous input shards; joint exact tie-break (all-gather of bucket histograms per round), "
                                  "bucket-range exchange of packed reads + qualities + names by peer stores over NVLink (CUDA IPC); output = single-GPU order of the concatenated input")},
         "roofline": roof, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -154,7 +154,7 @@ int64_t scb_device_bytes(const scb_handle *h);
 /* Which tie-break engine serves this core set (all are exact, aho_search's population compare, reads.cpp:420-421):
  * 0 dense (per-warp population rows in shared memory, <= ~6.4k buckets), 1 sparse (bucket-major candidate lists in
  * global memory, core sets of production size: the reference sizes patterns[] for 5-10 M cores, reads.cpp:336, 385),
- * 2 sequential (one warp; jobs of >= 2^32 - 1 reads). The sharded run works with 0 and 1; scb_shard_resolve_joint with 0. */
+ * 2 sequential (one warp; jobs of >= 2^32 - 1 reads). The sharded run works with 0 and 1. */
 int scb_resolve_engine(const scb_handle *h);
 
 /* =====================================================================================================
@@ -217,21 +217,6 @@ int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t r
  * Exception: the no-core (root) bucket is counted by every rank for its own shard only - nothing reads it for the
  * tie-break - so after a sharded flush scb_unbucketed() and scb_lifetime_count(h, -1) are rank-local: sum them over
  * the ranks for the value unbuck() (reads.cpp:502) would report. */
-/* Opt-in alternative to the host-driven loop of scb_shard_resolve_round + all-gather: ALL joint rounds inside one kernel
- * per rank. The ranks exchange their histogram rows through peer memory (stores over NVLink into every rank's exchange
- * buffer, system-scope flags) - no host and no NCCL in the loop. Needs one process per GPU with peer access.
- *   scb_shard_joint_reserve  this rank's exchange buffer (device pointer; export it with scb_ipc_export, map the peers'
- *                            with scb_ipc_open; *changed = 1 when it was (re)allocated and must be re-published)
- *   scb_shard_resolve_joint  collective: every rank calls it once per flush, after rank 0's scb_shard_resolve_local.
- *                            peers[g] = rank g's buffer as mapped in this process (peers[rank] = the own buffer);
- *                            reads_before = reads of the lower ranks; n_rank0 = reads of rank 0; row0_dev = rank 0's
- *                            histogram from scb_shard_resolve_local (rank 0 only). On return rows_out points at
- *                            n_ranks rows of *row_words u32 (device): every rank's bucket histogram of the last round,
- *                            entry n_cols = its changed count; *rounds_out = joint rounds run.
- * Replaces the loop over scb_shard_resolve_round (compress.cpp has no counterpart: the reference is one process). */
-int scb_shard_joint_reserve(scb_handle *h, int32_t n_ranks, void **ptr, int32_t *changed);
-int scb_shard_resolve_joint(scb_handle *h, int32_t rank, int32_t n_ranks, void *const *peers, int64_t reads_before, int64_t n_rank0,
-                            const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *row_words, int32_t *rounds_out);
 int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global);
 /* Local bucket histogram in emission order, device u32[n_cols] (overwritten). */
 int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev);
@@ -267,11 +252,6 @@ int scb_shard_send_wait(scb_handle *h);
 /* Sort + tie refinement of the imported reads (needs aux, 2-bit rows and names only); optional: scb_shard_finish
  * runs it if it was not called. */
 int scb_shard_finish_sort(scb_handle *h);
-/* Optional, after scb_shard_finish_sort and BEFORE the row exchange has been awaited: emits everything that does not
- * read quality / mate-2 rows (stream offsets, names, packed reads, meta records = what bin_dump, reads.cpp:91-180,
- * writes to files 0, 1, 3), so that this work overlaps the tail of the row exchange; scb_shard_finish then only runs
- * the row gathers (files 2, 4, 5). */
-int scb_shard_finish_early(scb_handle *h);
 int scb_ipc_export(scb_handle *h, const void *dev_ptr, uint8_t *handle64);
 int scb_ipc_open(scb_handle *h, const uint8_t *handle64, void **out);
 int scb_ipc_close(scb_handle *h, void *peer_ptr);

@@ -22,7 +22,7 @@ EXPORTS = [
     "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_assemble_reads", "scb_copy_assembled", "scb_inverse_reads", "scb_reset_counts", "scb_destroy",
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
-    "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", "scb_shard_finish_early", "scb_shard_joint_reserve", "scb_shard_resolve_joint",
+    "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", 
     "scb_ipc_export", "scb_ipc_open", "scb_ipc_close", "scb_shard_flush", "scb_shard_flush_stats", "scb_shard_n_local",
 ]
 
@@ -123,10 +123,6 @@ def load_library(path: str | None = None):
     L.scb_shard_send.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ScbShardPeer), C.c_int32, C.c_int32]
     L.scb_shard_send_wait.argtypes = [C.c_void_p]
     L.scb_shard_finish_sort.argtypes = [C.c_void_p]
-    L.scb_shard_finish_early.argtypes = [C.c_void_p]
-    L.scb_shard_joint_reserve.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
-    L.scb_shard_resolve_joint.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_void_p,
-                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.scb_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.scb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     L.scb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]

@@ -172,7 +172,6 @@ struct scb_handle {
     const uint64_t *srt_keys = nullptr;                    // sorted keys of the chunk-major order
     int srt_seg_bits = 0;
     bool srt_keys_valid = false;   // scb_shard_finish_sort ran: scb_shard_finish only emits
-    bool emit_early_done = false;  // scb_shard_finish_early ran: scb_shard_finish only runs the kernels that read quality / mate-2 rows
     Pending sh_local;          // the rank's own input after scb_shard_import replaced `cur` (phase-2 sends still read it)
     // ---- sharded run (scb_shard_*): state between the phases of one distributed flush -------------------
     int sh_phase = 0;          // 0 idle, 1 scanned, 2 resolved (finalized), 3 sized, 4 packed, 5 imported
@@ -203,9 +202,6 @@ struct scb_handle {
     std::vector<void *> rx_retired;
     DevBuf sh_name_off;        // import side: name offsets rebuilt from the lengths
     float sh_ms = 0;           // device time of the last scb_shard_* call
-    // joint tie-break rounds inside one kernel (opt-in): this rank's exchange buffer (plain cudaMalloc, exported over CUDA IPC)
-    void *jx = nullptr; size_t jx_cap = 0; int jx_G = 0; uint32_t j_epoch = 0;
-    std::vector<void *> jx_retired;
 };
 
 namespace scb {
@@ -791,9 +787,9 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
     int dev_sms = 0;
     SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     const size_t smem = (size_t)W * P * 8;
-    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(resolve_dense_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<false, true>, W * 32, smem));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_dense_k<true>, W * 32, smem));
     if (occ < 1) return false;
     const int grid = std::min(dev_sms, 160);
     const size_t max_sub = (size_t)grid * W;
@@ -818,7 +814,7 @@ static bool dense_setup(scb_handle *h, uint64_t reads_in_job /* upper bound on a
 }
 
 // one launch of the engine over blocks `blk` of the local reads; returns status (0 ok)
-static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<int64_t> &blk, uint32_t *tot_out, const RdJoint *joint = nullptr) {
+static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<int64_t> &blk, uint32_t *tot_out) {
     cudaStream_t st = h->st;
     const int nb1 = h->tab.n_buckets + 1;
     const int W = h->sh_W, grid = h->sh_grid;
@@ -829,7 +825,7 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
         SCB_CUDA(cudaMemcpyAsync(h->sh_blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, st));
         SCB_CUDA(cudaMemsetAsync(h->sh_stat.p, 0, 8, st));
     }
-    SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)((mode == 0 || mode == 3) ? kRdMaxRounds : 1) * 4, st));
+    SCB_CUDA(cudaMemsetAsync(h->sh_changed.p, 0, (size_t)((mode == 0) ? kRdMaxRounds : 1) * 4, st));
     RdParams rp;
     rp.n = h->cur.n; rp.ncand = h->ncand.as<uint16_t>(); rp.cand_off = h->cand_off.as<uint64_t>(); rp.cand_rank = h->cand_rank.as<uint32_t>();
     rp.sel = h->sh_sel.as<uint16_t>(); rp.base = h->sh_base.as<uint32_t>(); rp.H = h->sh_H.as<uint32_t>(); rp.S = nullptr;
@@ -840,19 +836,18 @@ static int dense_launch(scb_handle *h, int mode, int64_t g0, const std::vector<i
     rp.incr_T = nb1 > 0xffff ? 0 : 1024;             // decision-margin threshold of the incremental rounds (records hold bucket ranks in 16 bits)
     rp.incr_stat = (getenv("SCB_RESOLVE_PROF") || getenv("SCB_RESOLVE_STAT")) ? h->sh_incr_stat.as<unsigned long long>() : nullptr;
     rp.stale = h->sh_stale.as<uint32_t>(); rp.n_stale = h->sh_nstale.as<uint32_t>();
-    if (mode == 0 || mode == 3) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
+    if (mode == 0) SCB_CUDA(cudaMemsetAsync(h->sh_nstale.p, 0, (size_t)kRdMaxRounds * 4, st));
     DevBuf dts;
     const bool prof = mode == 0 && getenv("SCB_RESOLVE_PROF") != nullptr;
     if (prof) { dts.alloc(4096 * 8 * 8, st); SCB_CUDA(cudaMemsetAsync(dts.p, 0, 4096 * 8 * 8, st)); }
     rp.tstamps = prof ? dts.as<unsigned long long>() : nullptr;
-    if (joint) rp.j = *joint; else memset(&rp.j, 0, sizeof rp.j);
     void *args[] = {&rp};
     // deferred re-sweeps (resolve_dense.cuh): 9.03 -> 8.43 ms at 50M x 150, profiles/r02_resolve_ab.txt
-    void *kfn = mode == 3 ? (void *)resolve_dense_k<true, true> : (void *)resolve_dense_k<false, true>;   // mode 3: all joint rounds in this launch
+    void *kfn = (void *)resolve_dense_k<true>;
     SCB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SCB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(W * 32), args, smem, st));
     g_launches++;
-    if (mode != 0 && mode != 3) {
+    if (mode != 0) {
         h->last_rounds++;
         if (getenv("SCB_RESOLVE_STAT")) {   // debugging aid: subtile sweeps of this round (synchronises)
             unsigned long long is[4] = {0, 0, 0, 0};
@@ -1229,7 +1224,6 @@ static void shard_scan(scb_handle *h) {
     cudaStream_t st = h->st;
     ArenaScope arena_scope(&h->arena);
     h->sh_phase = 0;
-    h->emit_early_done = false;
     flush_begin(h, 1.25);  // room for the send side (owner sort, aux words, staged names: ~50 B per read); the receive side reuses the slab after the exchange
     const int64_t n = h->cur.n;
     h->sh_n_local = n;
@@ -1346,74 +1340,6 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
         }
     }
     h->sh_ms = 0;   // asynchronous: the caller times the round loop on its stream
-}
-
-// ---- joint rounds inside one kernel per rank (opt-in; resolve_dense.cuh "joint mode") ------------------------------------
-static int joint_row_words(int nb1) { return (nb1 + 2 + 3) & ~3; }
-static size_t joint_bytes(int nb1, int G) { return ((size_t)2 * G * joint_row_words(nb1) + (size_t)G + 64) * 4; }
-
-static void shard_joint_reserve(scb_handle *h, int G, void **ptr, int32_t *changed) {
-    const int nb1 = h->tab.n_buckets + 1;
-    const size_t want = joint_bytes(nb1, G);
-    *changed = 0;
-    SCB_CUDA(cudaStreamSynchronize(h->st));
-    if (!h->jx || h->jx_cap < want || h->jx_G != G) {
-        if (h->jx) h->jx_retired.push_back(h->jx);   // peers may still map it: freed with the handle
-        SCB_CUDA(cudaMalloc(&h->jx, want));
-        SCB_CUDA(cudaMemsetAsync(h->jx, 0, want, h->st));   // flags start below every epoch ...
-        SCB_CUDA(cudaStreamSynchronize(h->st));             // ... and the zeros are there before any peer can write (the caller's barrier follows)
-        h->jx_cap = want; h->jx_G = G;
-        *changed = 1;
-    }
-    *ptr = h->jx;
-}
-
-static void shard_resolve_joint(scb_handle *h, int rank, int G, void *const *peers, int64_t reads_before, int64_t n_rank0,
-                                const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *rounds_out) {
-    cudaStream_t st = h->st;
-    ArenaScope arena_scope(&h->arena);
-    const int64_t n = h->cur.n;
-    const int nb1 = h->tab.n_buckets + 1;
-    if (!h->jx || h->jx_G != G || peers[rank] != h->jx) throw CudaError{"joint rounds: scb_shard_joint_reserve first, and peers[rank] must be this rank's buffer"};
-    h->j_epoch += 0x10000u;   // every rank makes the same sequence of calls, so the epochs agree without communication
-    RdJoint j;
-    memset(&j, 0, sizeof j);
-    for (int g = 0; g < G; g++) j.peer[g] = (uint32_t *)peers[g];
-    j.rank = rank; j.G = G; j.RW = joint_row_words(nb1); j.epoch = h->j_epoch;
-    j.life = h->d_life.as<unsigned long long>();
-    j.reads_before = reads_before; j.n_rank0 = n_rank0;
-    j.timeout_ns = 10ull * 1000000000ull;
-    ShardTimer tm(h);
-    int rounds = 0;
-    if (rank == 0 || n == 0) {
-        DevBuf dstat(8, st);
-        SCB_CUDA(cudaMemsetAsync(dstat.p, 0, 8, st));
-        SCB_LAUNCH(joint_follow_k, 1, 256, 0, st, j, rank == 0 ? row0_dev : (const uint32_t *)nullptr, nb1, dstat.as<int>() + 1, dstat.as<int>());
-        int stat[2] = {0, 0};
-        SCB_CUDA(cudaMemcpyAsync(stat, dstat.p, 8, cudaMemcpyDeviceToHost, st));
-        SCB_CUDA(cudaStreamSynchronize(st));
-        if (stat[0] != 0) throw CudaError{stat[0] == 2 ? "joint rounds: timed out waiting for another rank" : "joint rounds: round cap hit"};
-        rounds = stat[1];
-    } else {
-        if (shard_engine(h) != kEngDense) throw CudaError{"joint rounds in one kernel need the dense resolve engine (scb_resolve_engine)"};
-        h->engine = kEngDense;
-        shard_need_dense(h);
-        if ((h->life_total + (uint64_t)reads_before + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
-        const int P = (nb1 + 3) & ~3;
-        DevBuf cta_base((size_t)h->sh_grid * P * 4, st);
-        j.cta_base = cta_base.as<uint32_t>();
-        const int64_t g0 = (int64_t)std::min<uint64_t>(h->life_total, (uint64_t)1 << 40) + reads_before;
-        std::vector<int64_t> blk{0, n};
-        h->last_rounds = 0;
-        const int rc = dense_launch(h, 3, g0, blk, h->sh_tot.as<uint32_t>(), &j);
-        if (rc != 0) throw CudaError{rc == 2 ? "joint rounds: timed out waiting for another rank" : "resolve: round cap hit"};
-        rounds = h->last_rounds;
-    }
-    tm.stop();
-    if (rounds < 2) throw CudaError{"joint rounds: internal (fewer than two rounds)"};
-    h->last_rounds = rounds;
-    *rounds_out = rounds;
-    *rows_out = (const uint32_t *)h->jx + (size_t)((rounds - 1) & 1) * G * j.RW;   // every rank's row of the last round
 }
 
 static void shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
@@ -1563,7 +1489,9 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
     // async: on a side stream with a capped grid (NVLink-bound work needs few SMs), so that the receive side's sort
     // runs next to it; scb_shard_send_wait joins
     cudaStream_t st = async ? h->st_aux[0] : h->st;
-    const int cap = async ? 148 * 2 : 0;
+    // CTAs of the overlapped row sends: 4 per SM measured best next to the sort (2 GPUs, 50M x 150: step 59.0 / 55.6 / 54.4 / 55.9 ms
+    // at 1 / 2 / 4 per SM / uncapped; profiles/r02_multi_gpu_ab.txt)
+    const int cap = async ? 148 * 4 : 0;
     if (async) { SCB_CUDA(cudaEventRecord(h->ev_fork, h->st)); SCB_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0)); }
     cudaEventRecord(h->ev_s0, st);
     for (int k = 1; k <= G; k++) {
@@ -2019,23 +1947,6 @@ int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t r
     SCB_CATCH
     return SCB_OK;
 }
-int scb_shard_joint_reserve(scb_handle *h, int32_t n_ranks, void **ptr, int32_t *changed) {
-    if (!ptr || !changed || n_ranks < 2 || n_ranks > scb::kJointMaxRanks) { scb::g_last_error = "bad argument (2..16 ranks)"; return SCB_EINVAL; }
-    SCB_SHARD_ENTER(1)
-    scb::shard_joint_reserve(h, n_ranks, ptr, changed);
-    SCB_CATCH
-    return SCB_OK;
-}
-int scb_shard_resolve_joint(scb_handle *h, int32_t rank, int32_t n_ranks, void *const *peers, int64_t reads_before, int64_t n_rank0,
-                            const uint32_t *row0_dev, const uint32_t **rows_out, int32_t *row_words, int32_t *rounds_out) {
-    if (!peers || !rows_out || !row_words || !rounds_out || n_ranks < 2 || n_ranks > scb::kJointMaxRanks || rank < 0 || rank >= n_ranks ||
-        (rank == 0 && !row0_dev)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
-    SCB_SHARD_ENTER(1)
-    scb::shard_resolve_joint(h, rank, n_ranks, peers, reads_before, n_rank0, row0_dev, rows_out, rounds_out);
-    *row_words = scb::joint_row_words(h->tab.n_buckets + 1);
-    SCB_CATCH
-    return SCB_OK;
-}
 int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
     SCB_SHARD_ENTER(1)
     if (!h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_finalize"; return SCB_ESTATE; }
@@ -2137,22 +2048,12 @@ int scb_shard_finish_sort(scb_handle *h) {
     SCB_CATCH
     return SCB_OK;
 }
-int scb_shard_finish_early(scb_handle *h) {
-    SCB_SHARD_ENTER(5)
-    if (!h->srt_keys_valid) { scb::g_last_error = "sharded run: scb_shard_finish_early needs scb_shard_finish_sort first"; return SCB_ESTATE; }
-    if (h->emit_early_done) { scb::g_last_error = "sharded run: scb_shard_finish_early called twice"; return SCB_ESTATE; }
-    scb::shard_finish(h, 4);
-    h->emit_early_done = true;
-    SCB_CATCH
-    return SCB_OK;
-}
 int scb_shard_finish(scb_handle *h, scb_result *out) {
     if (!out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
     memset(out, 0, sizeof *out);
     SCB_SHARD_ENTER(5)
-    scb::shard_finish(h, h->emit_early_done ? 8 : (h->srt_keys_valid ? 2 : 3));
+    scb::shard_finish(h, h->srt_keys_valid ? 2 : 3);
     h->srt_keys_valid = false;
-    h->emit_early_done = false;
     out->device_ms = h->sh_ms;
     SCB_CATCH
     scb::fill_result(h, out);
@@ -2485,8 +2386,6 @@ void scb_destroy(scb_handle *h) {
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);
     for (auto &kv : h->fl_ipc) cudaIpcCloseMemHandle(kv.second.second);
-    if (h->jx) cudaFree(h->jx);
-    for (void *r : h->jx_retired) cudaFree(r);
     for (auto &r : h->rx) if (r) cudaFree(r);
     for (void *r : h->rx_retired) cudaFree(r);
     h->arena.destroy();

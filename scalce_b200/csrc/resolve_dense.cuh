@@ -31,36 +31,6 @@ constexpr uint32_t kNoSel = 0xffffu;
 constexpr int kRdMaxRounds = 1 << 16;
 constexpr int kRdBatch = 6;             // 128-bit histogram rows fetched together in the P / E phases
 
-// Joint rounds of the sharded run inside ONE kernel per rank (opt-in, written without GPU access; see "joint mode" in
-// resolve_dense_k): the ranks exchange their histogram rows through peer memory instead of an NCCL all-gather per round.
-// Exchange buffer of a rank (plain cudaMalloc, mapped by the peers through CUDA IPC): rows[2][G][RW] u32 (parity of the
-// round, rank that produced the row; RW >= nb1 + 2: bucket histogram, changed count, stale subtiles), then flags[G] u32 (slot s is
-// written by rank s: epoch + number of rounds it has finished; 0xffff rounds = "my row is final").
-constexpr int kJointMaxRanks = 16;
-constexpr uint32_t kJointFinal = 0xffffu;
-struct RdJoint {
-    uint32_t *peer[kJointMaxRanks];   // every rank's exchange buffer as mapped here (peer[rank] = my own)
-    int rank, G, RW;
-    uint32_t epoch;                   // flag values of this run start here (epochs never repeat: no resets, no stale flags)
-    const unsigned long long *life;   // lifetime populations before this flush
-    int64_t reads_before, n_rank0;    // for the first round's guess: rank 0's row scaled to the reads before this shard
-    uint32_t *cta_base;               // [grid][pitch] every CTA's own copy of the populations before the shard
-    unsigned long long timeout_ns;    // a rank that never shows up must not hang the others
-};
-__device__ __forceinline__ uint32_t *rdj_row(const RdJoint &j, int buf, int par, int s) { return j.peer[buf] + ((size_t)par * j.G + s) * j.RW; }
-__device__ __forceinline__ uint32_t *rdj_flags(const RdJoint &j, int buf) { return j.peer[buf] + (size_t)2 * j.G * j.RW; }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 struct RdParams {
     int64_t n;
     const uint16_t *ncand; const uint64_t *cand_off; const uint32_t *cand_rank;
@@ -92,7 +62,6 @@ struct RdParams {
     uint32_t *fr_used;            // [max_subtiles] records in the list; kFrNone = no valid list
     int incr_T;                   // decision-margin threshold
     unsigned long long *incr_stat;   // optional [4]: full sweeps, incremental sweeps, incremental sweeps redone in full, records visited
-    RdJoint j;                       // joint mode only (mode 3)
     // DEFER instances only (see resolve_dense_k): stale[t] = 1 while subtile t runs on replays although its margin bound failed;
     // n_stale[round] = such subtiles after the round
     uint32_t *stale, *n_stale;
@@ -339,10 +308,6 @@ __device__ __forceinline__ void rd_row_add(uint32_t *row, const uint32_t *g, int
     __syncwarp();
 }
 
-// JOINT = true (mode 3, ranks >= 1 of a sharded run): ALL joint rounds in this one launch. Per round: wait until every
-// rank's row of the previous round has arrived (system-scope flags in my exchange buffer), stop if no rank changed
-// anything, build the populations before my shard (lifetime + rows of the lower ranks) in this CTA's own copy, run
-// the round as in modes 1-2, then CTA 0 pushes my row into every rank's buffer and raises my flag there.
 // DEFER = true (the default since it won its A/B run: 9.03 -> 8.43 ms at 50M x 150): a subtile whose margin bound fails is NOT swept
 // in full in the same round. Otherwise it is, and the whole
 // round - two grid syncs, ~1775 other warps that only replay - waits for that one sequential sweep; tools/sim_resolve.c counts such
@@ -351,7 +316,7 @@ __device__ __forceinline__ void rd_row_add(uint32_t *row, const uint32_t *g, int
 // marked stale; when a round changes nothing anywhere, the stale subtiles are swept in full in the next round (which rebuilds their
 // lists), and the block is finished by a quiet round without stale subtiles. A subtile whose bound holds again is not stale: the bound
 // only compares the current state with the last full sweep. Exactness as before: at termination every read was re-decided exactly.
-template <bool JOINT, bool DEFER>
+template <bool DEFER>
 __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams p) {
     extern __shared__ __align__(16) uint32_t sm_cnt[];   // [W][pitch] populations, then [W][pitch] per-step lane tags
     const int W = p.W, nb1 = p.nb1, P = p.pitch, Q = p.pitch >> 2;   // Q = 128-bit quads per row
@@ -361,8 +326,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
     const int ncta = gridDim.x, c = blockIdx.x;
     const int total_warps = ncta * W;
     uint4 *sm_cnt4 = (uint4 *)sm_cnt;
-    const uint4 *base4 = JOINT ? (const uint4 *)(p.j.cta_base + (size_t)blockIdx.x * p.pitch) : (const uint4 *)p.base;
-    __shared__ int s_joint;                      // joint mode: 0 go on, 1 converged, 2 timed out
+    const uint4 *base4 = (const uint4 *)p.base;
     uint4 *H4 = (uint4 *)p.H, *Csum4 = (uint4 *)p.Csum, *Cpre4 = (uint4 *)p.Cpre;
     uint4 *S04 = (uint4 *)p.S0, *H04 = (uint4 *)p.H0;
     __shared__ uint32_t s_dmax[kRdMaxWarps];     // largest start-count change of each of my subtiles since its last full sweep
@@ -383,58 +347,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
         bool first = p.mode != 2;
         bool verify = false;                     // DEFER: this round sweeps the stale subtiles in full
         while (true) {
-            if constexpr (JOINT) {
-                // ---- joint mode prologue: rows of the previous round, termination, populations before my shard ----
-                const RdJoint &j = p.j;
-                const int prev = (round + 1) & 1;                                    // parity of round - 1
-                if (threadIdx.x == 0) {
-                    int state = 0;
-                    const unsigned long long t0 = gtimer();
-                    const uint32_t *fl = rdj_flags(j, j.rank);
-                    for (int s2 = 0; s2 < j.G && state == 0; s2++) {
-                        // the first round only needs rank 0's (final) row; later rounds need every rank's row of the round before,
-                        // MY OWN included: CTA 0 pushes it after the grid sync, the other CTAs must not run ahead of that push
-                        if (round == 0 && s2 != 0) continue;
-                        const uint32_t want = j.epoch + (round == 0 ? 1u : (uint32_t)round);
-                        while ((int32_t)(ld_acquire_sys(fl + s2) - want) < 0)
-                            if (gtimer() - t0 > j.timeout_ns) { state = 2; break; }
-                    }
-                    if (state == 0 && round >= 2) {                                  // round - 1 was not the guess round: did anything change in it?
-                        uint32_t chg_all = 0, stale_all = 0;                         // (DEFER: and is any subtile of any rank still stale?)
-                        for (int s2 = 1; s2 < j.G; s2++) {
-                            chg_all += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + nb1);
-                            stale_all += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + nb1 + 1);
-                        }
-                        if (chg_all == 0 && stale_all == 0) state = 1;
-                        else if (chg_all == 0) state = 4;                            // quiet but stale: this round sweeps the stale subtiles in full
-                    }
-                    s_joint = state;
-                }
-                __syncthreads();
-                const int state = s_joint;
-                if (state != 0 && state != 4) {
-                    if (blockIdx.x == 0 && threadIdx.x == 0) { *p.rounds_out = round; if (state == 2) *p.status = 2; }
-                    return;
-                }
-                if (DEFER) verify = state == 4;
-                uint32_t *mine = p.j.cta_base + (size_t)blockIdx.x * P;
-                for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                    uint32_t v = 0;
-                    if (i < nb1) {
-                        v = (uint32_t)j.life[i];
-                        if (round == 0) {
-                            if (j.n_rank0 > 0)
-                                v += (uint32_t)(((unsigned long long)ld_volatile_u32(rdj_row(j, j.rank, 0, 0) + i) * (unsigned long long)j.reads_before) /
-                                                (unsigned long long)j.n_rank0);
-                        } else {
-                            for (int s2 = 0; s2 < j.rank; s2++) v += ld_volatile_u32(rdj_row(j, j.rank, prev, s2) + i);
-                        }
-                    }
-                    mine[i] = v;
-                }
-                __syncthreads();
-            }
-            // ---- P: start counts of my subtiles, straight into the warps' shared-memory counters ----
+                        // ---- P: start counts of my subtiles, straight into the warps' shared-memory counters ----
             // first round of a block: no histogram of the block exists yet; start from the populations
             // before the block, extrapolated proportionally to the subtile's position (only a guess:
             // it shortens convergence, the fixed point does not depend on it). Four buckets per thread
@@ -579,7 +492,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             const uint32_t chg = *((volatile uint32_t *)&p.changed[round]);
             const uint32_t nst = DEFER ? *((volatile uint32_t *)&p.n_stale[round]) : 0u;
             const bool done = (chg == 0) && nst == 0;
-            if (DEFER && !JOINT) verify = chg == 0 && nst != 0;   // joint mode decides from every rank's row (prologue)
+            if (DEFER) verify = chg == 0 && nst != 0;
             {   // one warp per quad of columns; lanes stride over the chunks, shuffle scan across lanes
                 const int gw = blockIdx.x * W + w, tw = gridDim.x * W;
                 for (int q = gw; q < Q; q += tw) {
@@ -614,27 +527,7 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
             grid.sync();
             RD_STAMP(6);
             if (p.tstamps && blockIdx.x == 0 && threadIdx.x == 0 && round < 4096) p.tstamps[round * 8 + 7] = (unsigned long long)len;
-            if constexpr (JOINT) {
-                // my row of this round (tot_out, written by the column scan before the grid sync) goes into every rank's buffer
-                if (blockIdx.x == 0) {
-                    const RdJoint &j = p.j;
-                    const int par = round & 1;
-                    for (int g = 0; g < j.G; g++) {
-                        uint32_t *dst = rdj_row(j, g, par, j.rank);
-                        for (int i = threadIdx.x; i < nb1; i += blockDim.x) dst[i] = p.tot_out[i];
-                        if (threadIdx.x == 0) { dst[nb1] = chg; dst[nb1 + 1] = nst; }
-                    }
-                    __threadfence_system();
-                    __syncthreads();
-                    if (threadIdx.x == 0)
-                        for (int g = 0; g < j.G; g++) st_release_sys(rdj_flags(j, g) + j.rank, j.epoch + (uint32_t)round + 1u);
-                }
-                round++;
-                first = false;
-                if (round >= (int)kJointFinal - 1) { if (blockIdx.x == 0 && threadIdx.x == 0) *p.status = 1; return; }
-                continue;
-            }
-            if (p.mode != 0) {
+                        if (p.mode != 0) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) { p.tot_out[nb1] = chg; *p.rounds_out = 1; }
                 return;
             }
@@ -645,45 +538,6 @@ __global__ void __launch_bounds__(kRdMaxWarps * 32, 1) resolve_dense_k(RdParams 
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *p.rounds_out = round; }
-}
-
-// Joint mode, ranks whose row never changes (rank 0: its shard is resolved; a rank without reads: zeros): publish the row
-// as final in both parities of every rank's buffer, then follow the rounds of the others to the same exit.
-__global__ void __launch_bounds__(256) joint_follow_k(RdJoint j, const uint32_t *row /* [nb1] or null = zeros */, int nb1, int *rounds_out, int *status) {
-    __shared__ int s_state;
-    for (int par = 0; par < 2; par++)
-        for (int g = 0; g < j.G; g++) {
-            uint32_t *dst = rdj_row(j, g, par, j.rank);
-            for (int i = threadIdx.x; i < nb1; i += blockDim.x) dst[i] = row ? row[i] : 0u;
-            if (threadIdx.x == 0) { dst[nb1] = 0u; dst[nb1 + 1] = 0u; }
-        }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int g = 0; g < j.G; g++) st_release_sys(rdj_flags(j, g) + j.rank, j.epoch + kJointFinal);
-        int state = 0, k = 1;
-        const unsigned long long t0 = gtimer();
-        const uint32_t *fl = rdj_flags(j, j.rank);
-        for (;; k++) {                                   // k = number of rounds the iterating ranks have finished
-            for (int s2 = 1; s2 < j.G && state == 0; s2++) {
-                if (s2 == j.rank) continue;
-                while ((int32_t)(ld_acquire_sys(fl + s2) - (j.epoch + (uint32_t)k)) < 0)
-                    if (gtimer() - t0 > j.timeout_ns) { state = 2; break; }
-            }
-            if (state) break;
-            if (k >= 2) {
-                uint32_t chg_all = 0;   // changed decisions + stale subtiles (the latter only with deferred re-sweeps): both must be zero
-                for (int s2 = 1; s2 < j.G; s2++)
-                    chg_all += ld_volatile_u32(rdj_row(j, j.rank, (k - 1) & 1, s2) + nb1) + ld_volatile_u32(rdj_row(j, j.rank, (k - 1) & 1, s2) + nb1 + 1);
-                if (chg_all == 0) { state = 1; break; }
-            }
-            if (k >= (int)kJointFinal - 1) { state = 3; break; }
-        }
-        *rounds_out = k;
-        if (state != 1) *status = state;
-        s_state = state;
-    }
-    __syncthreads();
 }
 
 // asg / end from the converged slots; base -> lifetime counts

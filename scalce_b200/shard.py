@@ -180,40 +180,6 @@ class TorchComm:
             self._table[self.rank] = [int(p or 0) for p in ptrs]
         return self._table
 
-    def map_buffer(self, transform, tag, ptr, changed):
-        """One more persistent device buffer per rank (e.g. the joint rounds' exchange buffer): returns [G] pointers, rank
-        g's buffer as mapped into this process (own rank: the local pointer). Handles travel only when a buffer moved."""
-        import torch
-        from .binding import _check, load_library
-        L = load_library()
-        if not hasattr(self, "_bufs"):
-            self._bufs = {}
-        st = self._bufs.setdefault(tag, {"handles": {}, "table": None})
-        any_changed = max(x[0] for x in self.allgather_host([1 if (changed or st["table"] is None) else 0]))
-        if any_changed:
-            buf = (C.c_uint8 * 64)()
-            _check(L.scb_ipc_export(transform._h, C.c_void_p(ptr), buf))
-            hb = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy()).to(self.device)
-            allh = self.allgather(hb).cpu().numpy()
-            table = []
-            for g in range(self.world):
-                if g == self.rank:
-                    table.append(int(ptr))
-                    continue
-                hbytes = allh[g].tobytes()
-                old = st["handles"].get(g)
-                if old is None or old[0] != hbytes:
-                    if old is not None:
-                        _check(L.scb_ipc_close(transform._h, C.c_void_p(old[1])))
-                    out = C.c_void_p()
-                    _check(L.scb_ipc_open(transform._h, (C.c_uint8 * 64).from_buffer_copy(hbytes), C.byref(out)))
-                    st["handles"][g] = (hbytes, out.value)
-                table.append(st["handles"][g][1])
-            st["table"] = table
-        else:
-            st["table"][self.rank] = int(ptr)
-        return st["table"]
-
     def barrier(self):
         self.dist.barrier()
 
@@ -320,12 +286,6 @@ class ShardedTransform:
         self.p2p = p2p and hasattr(comm, "map_peers")
         self.on_torch_stream = bool(use_torch_stream)
         self.overlap = overlap      # row exchange overlapped with the receive side's sort (p2p only)
-        import os
-        self.early_emit = os.environ.get("SCB_SHARD_EARLY_EMIT", "0") not in ("", "0")
-        # opt-in (SCB_SHARD_JOINT_KERNEL=1, must be the same on every rank; one process per GPU only): all joint tie-break
-        # rounds inside one kernel per rank, histograms exchanged through peer memory instead of an all-gather per round
-        self.joint_kernel = (os.environ.get("SCB_SHARD_JOINT_KERNEL", "0") not in ("", "0") and hasattr(comm, "map_buffer")
-                             and transform.resolve_engine == 0)   # the in-kernel joint rounds exist for the dense engine only
         self.stats = {}
         self._keep = None
         if use_torch_stream:
@@ -379,28 +339,9 @@ class ShardedTransform:
             _check(L.scb_shard_resolve_local(h, C.c_void_p(tot.data_ptr())))
             lap("resolve")
         rounds = 0
-        joint_done = False
-        if G > 1 and self.joint_kernel:
-            # ---- all joint rounds in one kernel per rank (resolve_dense.cuh, joint mode) --------------------------------
-            jp, jchg = C.c_void_p(), C.c_int32()
-            _check(L.scb_shard_joint_reserve(h, G, C.byref(jp), C.byref(jchg)))
-            mapped = comm.map_buffer(self.t, "joint", jp.value, bool(jchg.value))       # rank g's buffer as mapped here
-            peers_j = (C.c_void_p * G)(*[C.c_void_p(int(x)) for x in mapped])
-            comm.barrier()                                                                # every buffer exists and is zero-initialised
-            rows_p, rw, jr = C.c_void_p(), C.c_int32(), C.c_int32()
-            torch.cuda.synchronize(dev)
-            _check(L.scb_shard_resolve_joint(h, r, G, peers_j, before[r], ns[0], C.c_void_p(tot.data_ptr()) if r == 0 else None,
-                                             C.byref(rows_p), C.byref(rw), C.byref(jr)))
-            ms["resolve_rounds"] = float(L.scb_shard_last_ms(h))
-            rounds = jr.value
-            rows = _dev_bytes(rows_p.value, G * rw.value * 4, dev).view(torch.int32).view(G, rw.value)
-            allt = rows[:, :ncols + 1].clone()
-            comm.barrier()                                                                # nobody reuses the rows before all have read them
-            joint_done = True
-        if not joint_done:
-            sync()
-            allt = comm.allgather(tot)
-        if G > 1 and not joint_done:
+        sync()
+        allt = comm.allgather(tot)
+        if G > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             # Rounds are enqueued one ahead of the convergence check: the "changed" count of round k is read back
@@ -500,9 +441,6 @@ class ShardedTransform:
                 _check(L.scb_shard_send(h, r, G, peers, 2, 1))
                 _check(L.scb_shard_finish_sort(h))
                 lap("sort")
-                if self.early_emit:   # opt-in (SCB_SHARD_EARLY_EMIT=1): names / packed reads / meta records while the rows still travel
-                    _check(L.scb_shard_finish_early(h))
-                    lap("emit_early")
                 _check(L.scb_shard_send_wait(h))
                 lap("exchange_rows")
                 comm.barrier()   # every rank's row writes have landed
@@ -599,6 +537,10 @@ class CShardedTransform:
         self.stats = {}
         if isinstance(comm, NcclCComm):        # a ready-made scb_comm (libscalce_b200_nccl.so): nothing of this class is on the path
             self._c, self._err = comm.ptr.contents, None
+            if use_torch_stream:               # the caller's events (bench.py) then bracket the library's work and the NCCL collectives
+                with torch.cuda.device(transform.cfg.device):
+                    s_ = torch.cuda.current_stream().cuda_stream
+                _check(load_library().scb_set_stream(transform._h, C.c_void_p(s_), 1))
             return
         dev = torch.device("cuda", transform.cfg.device)
         if use_torch_stream:

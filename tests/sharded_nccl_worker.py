@@ -63,7 +63,7 @@ def main():
         import json
         out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
         os.makedirs(out_dir, exist_ok=True)
-        variant = "_".join(k + ("-" + os.environ[k] if k in ("SCB_RESOLVE", "SCB_ORCH") else "") for k in ("SCB_SHARD_JOINT_KERNEL", "SCB_SHARD_EARLY_EMIT", "SCB_RESOLVE", "SCB_ORCH") if os.environ.get(k, "0") not in ("", "0")) or "default"
+        variant = "_".join(k + ("-" + os.environ[k] if k in ("SCB_RESOLVE", "SCB_ORCH") else "") for k in ("SCB_RESOLVE", "SCB_ORCH") if os.environ.get(k, "0") not in ("", "0")) or "default"
         rec = {"test": "tests/sharded_nccl_worker.py", "world_size": world, "gpus": torch.cuda.device_count(), "reads": n, "read_length": L,
                "bucket_set_bytes": bsb, "flush_chunks": o.n_chunks, "joint_rounds": gathered[0]["stats"]["rounds"], "variant": variant,
                "backend": "nccl + CUDA IPC peer stores, one process per GPU", "ok": bool(ok),

@@ -14,11 +14,15 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("orch", ["python", "cpp_nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_over_nccl(world):
+def test_sharded_over_nccl(world, orch):
+    """orch = python: scalce_b200/shard.py over torch.distributed; cpp_nccl: scb_shard_flush (the C++ orchestrator) over
+    libscalce_b200_nccl.so. Either way one process per GPU, NCCL + CUDA IPC peer stores, checked against the oracle; the worker
+    leaves a record under gpurun_out/ (copies of the round's runs: profiles/sharded_nccl_w*.json)."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "sharded_nccl_worker.py"), "60000", "100", str(1 << 21)]
-    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, SCB_ORCH=orch), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_NCCL_OK" in r.stdout, r.stdout[-4000:]

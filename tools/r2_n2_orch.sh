@@ -1,0 +1,15 @@
+#!/bin/bash
+N=${1:-2}
+mkdir -p gpurun_out/r2
+export PYTHONUNBUFFERED=1
+run() {
+  local name=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 \
+      bench.py --gpus $N --steps 3 --warmup 2 --no-cpu --no-e2e "$@" > gpurun_out/r2/n${N}_$name.json 2> gpurun_out/r2/n${N}_$name.err
+  echo "== $name rc=$?"; python tools/bench_brief.py gpurun_out/r2/n${N}_$name.json 2>/dev/null | head -3; tail -1 gpurun_out/r2/n${N}_$name.err | cut -c1-300
+}
+run orch_cpp --orchestrator cpp
+run orch_py --orchestrator python --no-parity
+SCB_ROWS_CAP=592 run cap592 --orchestrator cpp --no-parity
+SCB_ROWS_CAP=0 run cap0 --orchestrator cpp --no-parity
+SCB_ROWS_CAP=148 run cap148 --orchestrator cpp --no-parity
