@@ -297,6 +297,22 @@ int64_t scb_shard_n_local(const scb_handle *h);
 /* =====================================================================================================
  * The transform's two neighbours that SURVEY.md 8(f) ranks next, on the device.
  * ===================================================================================================== */
+/* (f2) The host front end on the device: FASTQ text -> one pending batch, replacing for a whole text at once the parse loop of
+ * thread() (compress.cpp:614-671: four lines per record, '@' name line, read and quality lines of read_length characters),
+ * output_name (names.cpp:48-62: the characters after '@' up to the first space) and output_quality at lossy percentage 0
+ * (qualities.cpp:177-204: quality - phred_offset, 0 under an upper-case 'N'), including output_quality's input-order context
+ * statistics ac_freq3 / ac_freq4 (what the arithmetic coder's model is built from, arithmetic.cpp) carried across calls.
+ * text1 / text2 (text2 only in a paired configuration; its name lines are skipped as the reference does): plain FASTQ, any
+ * number of whole records; location 0 = host, 1 = device. phred_offset[2]: per mate, what quality_mapping_init detected
+ * (qualities.cpp:99-104). Errors (SCB_ECUDA with the reason in scb_last_error): a record count that is not whole, a name line
+ * without '@', a read or quality line of another length (the reference exits on those, compress.cpp:629-636), a name longer
+ * than 255 bytes, a quality symbol outside [offset, offset + 80) (AC_DEPTH, arithmetic.h:47). A batch submitted this way and
+ * batches submitted through scb_submit may be mixed; only this entry point feeds the statistics.
+ * scb_quality_stats: ac_freq3 [80*80] and ac_freq4 [80*80*80] of a mate as the reference holds them after the same input
+ * (uint64 each; either pointer may be NULL); scb_reset_counts clears them. */
+int scb_submit_fastq(scb_handle *h, const uint8_t *text1, int64_t bytes1, const uint8_t *text2, int64_t bytes2, int32_t location,
+                     const int32_t *phred_offset, int64_t *n_records);
+int scb_quality_stats(scb_handle *h, int32_t mate, uint64_t *freq3, uint64_t *freq4);
 /* (f3) Bucket-record assembly of the .scalcer body, replacing the per-bucket loop of combine_and_compress_with_split
  * (compress.cpp:345-384) for mate 1: for every non-empty bucket `int32 core, int64 n_reads` (n_reads = tR / record size,
  * compress.cpp:371-376) followed by that bucket's packed reads + end markers - everything the reference writes to

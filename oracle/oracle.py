@@ -61,6 +61,8 @@ def lib():
         L.orc_core_node_id.restype = C.c_int32
         L.orc_core_node_id.argtypes = [C.c_void_p, C.c_int32]
         L.orc_assign.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.orc_parse_fastq.restype = C.c_int64
+        L.orc_parse_fastq.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.orc_inverse.restype = C.c_int64
         L.orc_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -213,6 +215,26 @@ def assemble_container(meta: bytes, names: bytes, reads: bytes, quals: bytes, co
         if use_names:
             fn += names[pn:pn + lN]; pn += lN
     return bytes(fn), bytes(fr), bytes(fq)
+
+
+def parse_fastq(text: bytes, L, phred=33, stats=None):
+    """The reference's host front end restated (compress.cpp:614-671, names.cpp:48-62, qualities.cpp:177-204): FASTQ text ->
+    (seq [n, L], qual payload [n, L], names, name_off). stats = dict(freq3, freq4, prev) carried across calls (None: off)."""
+    t = np.frombuffer(text, dtype=np.uint8)
+    cap = t.size // (2 * L + 4) + 2
+    seq = np.empty((cap, L), dtype=np.uint8); qual = np.empty((cap, L), dtype=np.uint8)
+    names = np.empty(t.size, dtype=np.uint8); off = np.zeros(cap + 1, dtype=np.int64)
+    f3 = f4 = pv = None
+    if stats is not None:
+        f3, f4, pv = stats["freq3"], stats["freq4"], stats["prev"]
+    n = lib().orc_parse_fastq(_ptr(t), t.size, L, phred, _ptr(seq), _ptr(qual), _ptr(names), _ptr(off), _ptr(f3), _ptr(f4), _ptr(pv))
+    if n < 0:
+        raise ValueError("malformed FASTQ")
+    return seq[:n], qual[:n], names[:off[n]], off[:n + 1]
+
+
+def new_quality_stats():
+    return dict(freq3=np.zeros(80 * 80, dtype=np.uint64), freq4=np.zeros(80 * 80 * 80, dtype=np.uint64), prev=np.array([500, 500], dtype=np.uint32))
 
 
 def segments_from_meta(meta: bytes, cores, L, paired=False):

@@ -67,6 +67,14 @@ static void dump(int fl, const char *dir, int nf) {  // dump_trie, compress.cpp:
 
 extern "C" {
 
+// output_quality's input-order statistics (qualities.cpp:186-199) are only kept with arithmetic coding on (_no_ac = 0): the
+// CPU test that pins the oracle's restatement of them switches it on, runs refh_run and reads the reference's globals back.
+void refh_set_no_ac(int v) { _no_ac = v; }
+void refh_get_stats(int mate, uint64_t *f3, uint64_t *f4) {
+    memcpy(f3, ac_freq3[mate], sizeof(uint64_t) * AC_DEPTH * AC_DEPTH);
+    memcpy(f4, ac_freq4[mate], sizeof(uint64_t) * AC_DEPTH * AC_DEPTH * AC_DEPTH);
+}
+
 // Loads the core set (text file, -P) and builds the automaton; returns seconds spent.
 double refh_init(const char *cores_path, int L1, int L2, int paired, int use_names, uint64_t bucket_set_bytes) {
     read_length[0] = L1;

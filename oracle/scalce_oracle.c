@@ -469,6 +469,52 @@ int64_t orc_inverse(orc *o, const uint8_t *stream, const int32_t *seg_core, cons
     return K;
 }
 
+/* ---- the host front end: parse loop compress.cpp:614-671, output_name names.cpp:48-62, output_quality
+ * qualities.cpp:177-204 at lossy percentage 0 (values[c] = c) with its input-order statistics. text: plain FASTQ, whole
+ * records. prev[2] = the two payload symbols before this text (500, 500 at the start of a job, qualities.cpp:179);
+ * freq3 [80*80] / freq4 [80*80*80] are updated in place (NULL: statistics off, as with -A). names: characters after '@' up to
+ * the first space; name_off[n+1]. Returns the number of records, -1 on a malformed record. */
+int64_t orc_parse_fastq(const uint8_t *text, int64_t bytes, int L, int phred, uint8_t *seq, uint8_t *qual, uint8_t *names,
+                        int64_t *name_off, uint64_t *freq3, uint64_t *freq4, uint32_t *prev) {
+    int64_t pos = 0, n = 0, nb = 0;
+    if (name_off) name_off[0] = 0;
+    while (pos < bytes) {
+        int64_t ls[4], le[4];
+        for (int k = 0; k < 4; k++) {                      /* f_gets x4, compress.cpp:615-642 */
+            if (pos > bytes) return -1;
+            ls[k] = pos;
+            while (pos < bytes && text[pos] != '\n') pos++;
+            le[k] = pos;
+            pos++;
+            if (k < 3 && le[k] >= bytes) return -1;
+        }
+        if (text[ls[0]] != '@' || le[1] - ls[1] != L || le[3] - ls[3] != L) return -1;
+        int64_t q = ls[0] + 1;
+        while (q < le[0] && text[q] != ' ') q++;           /* names.cpp:55 */
+        if (q - (ls[0] + 1) > 255) return -1;
+        if (names) { memcpy(names + nb, text + ls[0] + 1, (size_t)(q - (ls[0] + 1))); }
+        nb += q - (ls[0] + 1);
+        if (name_off) name_off[n + 1] = nb;
+        memcpy(seq + (size_t)n * L, text + ls[1], (size_t)L);
+        if (qual)
+            for (int i = 0; i < L; i++) {                   /* qualities.cpp:181-202 */
+                uint8_t d = (uint8_t)((text[ls[1] + i] == 'N' ? phred : text[ls[3] + i]) - phred);
+                qual[(size_t)n * L + i] = d;
+                if (freq3 && freq4) {
+                    if (prev[1] < 256) {
+                        freq3[prev[1] * 80 + d]++;
+                        if (prev[0] < 256) freq4[(prev[0] * 80 + prev[1]) * 80 + d]++;
+                    } else {
+                        for (int e = 0; e < 80 * 80 * 80; e++) freq4[e] = 1;
+                    }
+                    prev[0] = prev[1]; prev[1] = d;
+                }
+            }
+        n++;
+    }
+    return n;
+}
+
 void orc_destroy(orc *o) {
     if (!o) return;
     for (int32_t i = 0; i < o->n_nodes; i++) free(o->nd[i].bin);

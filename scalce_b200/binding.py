@@ -19,7 +19,7 @@ ROOT_ID = (1 << 30) - 1
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
     "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
-    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_assemble_reads", "scb_copy_assembled", "scb_inverse_reads", "scb_reset_counts", "scb_destroy",
+    "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_assemble_reads", "scb_copy_assembled", "scb_inverse_reads", "scb_submit_fastq", "scb_quality_stats", "scb_reset_counts", "scb_destroy",
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
     "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", 
@@ -99,6 +99,8 @@ def load_library(path: str | None = None):
     L.scb_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_resolve_rounds.argtypes = [C.c_void_p]
     L.scb_resolve_engine.argtypes = [C.c_void_p]
+    L.scb_submit_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.scb_quality_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.scb_assemble_reads.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.scb_copy_assembled.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.scb_inverse_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -275,6 +277,23 @@ class BoostTransform:
         res = ScbResult()
         _check(load_library().scb_flush(self._h, C.byref(res)))
         return FlushResult(self, res)
+
+    def submit_fastq(self, text1, text2=None, phred_offset=(33, 33)):
+        """(f2) FASTQ text (bytes / uint8 arrays on the host) parsed on the device into one pending batch. Returns the record count."""
+        L = load_library()
+        a1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
+        a2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
+        ph = (C.c_int32 * 2)(*phred_offset)
+        n = C.c_int64()
+        _check(L.scb_submit_fastq(self._h, a1.ctypes.data_as(C.c_void_p), a1.size, None if a2 is None else a2.ctypes.data_as(C.c_void_p),
+                                  0 if a2 is None else a2.size, 0, ph, C.byref(n)))
+        return n.value
+
+    def quality_stats(self, mate=0):
+        """ac_freq3 [80, 80] and ac_freq4 [80, 80, 80] (uint64) as output_quality accumulates them in input order."""
+        f3 = np.zeros(80 * 80, dtype=np.uint64); f4 = np.zeros(80 * 80 * 80, dtype=np.uint64)
+        _check(load_library().scb_quality_stats(self._h, mate, f3.ctypes.data_as(C.c_void_p), f4.ctypes.data_as(C.c_void_p)))
+        return f3.reshape(80, 80), f4.reshape(80, 80, 80)
 
     def assemble_reads(self, chunk=-1):
         """(f3) .scalcer body of mate 1 (bucket records + packed reads, compress.cpp:345-384) from the last flush, assembled on

@@ -23,6 +23,7 @@
 #include "emit_reads_fast.cuh"
 #include "shard.cuh"
 #include "container.cuh"
+#include "parse.cuh"
 
 namespace scb {
 std::atomic<long long> g_launches{0};
@@ -180,6 +181,10 @@ struct scb_handle {
     int sh_W = 0, sh_grid = 0; // dense-resolve geometry
     DevBuf sh_sel, sh_base, sh_H, sh_S, sh_Csum, sh_Cpre, sh_changed, sh_blk, sh_stat, sh_tot;
     DevBuf sh_stale, sh_nstale;   // deferred re-sweeps (resolve_dense_k<*, *, true>)
+    // (f2) input-order quality statistics of scb_submit_fastq: counts per mate, the two symbols before the next one (>= 256: none)
+    DevBuf q_freq3[2], q_freq4[2];
+    uint32_t q_prev[2][2] = {{500, 500}, {500, 500}};
+    uint64_t q_seen[2] = {0, 0};
     // C++ orchestrator (scb_shard_flush): peers' receive arrays as mapped here, phase times of the last call
     std::map<std::pair<int, int>, std::pair<std::vector<uint8_t>, void *>> fl_ipc;   // (rank, array) -> (IPC handle bytes, mapped pointer)
     std::vector<std::vector<void *>> fl_table;                                       // [rank][array]
@@ -1643,6 +1648,118 @@ static void fill_result(scb_handle *h, scb_result *out) {
     out->perm = h->perm.as<uint32_t>();
 }
 
+// ---- (f2) FASTQ text -> pending batch (parse.cuh) ----------------------------------------------------------------------------
+struct ParsedMate { DevBuf text, tile_cnt, tile_first, line_end, name_len, name_off, err; int64_t n = 0; const uint8_t *t = nullptr; int64_t bytes = 0; };
+
+static int64_t parse_lines(scb_handle *h, ParsedMate &m, const uint8_t *text, int64_t bytes, int location) {
+    cudaStream_t st = h->st;
+    m.bytes = bytes;
+    if (location == 0) {
+        m.text.alloc((size_t)bytes + 16, st);
+        SCB_CUDA(cudaMemcpyAsync(m.text.p, text, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        m.t = m.text.as<uint8_t>();
+    } else m.t = text;
+    if (bytes == 0) { m.n = 0; return 0; }
+    const int64_t tiles = cdiv(bytes, kParseTile);
+    m.tile_cnt.alloc((size_t)tiles * 4, st); m.tile_first.alloc((size_t)(tiles + 1) * 8, st);
+    SCB_LAUNCH(parse_count_nl_k, (unsigned)tiles, 256, 0, st, m.t, bytes, m.tile_cnt.as<uint32_t>());
+    DevBuf ws64((size_t)scan_tiles(tiles) * 8, st);
+    exclusive_scan<uint64_t>(NlCount{m.tile_cnt.as<uint32_t>()}, tiles, m.tile_first.as<uint64_t>(), m.tile_first.as<uint64_t>() + tiles, ws64.as<uint64_t>(), st);
+    uint64_t nl = 0; uint8_t last = 0;
+    SCB_CUDA(cudaMemcpyAsync(&nl, m.tile_first.as<uint64_t>() + tiles, 8, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(&last, m.t + bytes - 1, 1, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    const int64_t lines = (int64_t)nl + (last != '\n' ? 1 : 0);         // a last line without its newline still ends at the end of the text
+    if (lines % 4 != 0) throw CudaError{"FASTQ text does not hold a whole number of 4-line records"};
+    m.line_end.alloc((size_t)std::max<int64_t>(lines, 1) * 8, st);
+    SCB_LAUNCH(parse_line_ends_k, (unsigned)tiles, 256, 0, st, m.t, bytes, m.tile_first.as<uint64_t>(), m.line_end.as<int64_t>(), lines);
+    if (last != '\n') SCB_CUDA(cudaMemcpyAsync(m.line_end.as<int64_t>() + lines - 1, &bytes, 8, cudaMemcpyHostToDevice, st));
+    m.n = lines / 4;
+    return m.n;
+}
+
+static void submit_fastq(scb_handle *h, const uint8_t *text1, int64_t bytes1, const uint8_t *text2, int64_t bytes2, int location, const int32_t *phred, int64_t *n_out) {
+    cudaStream_t st = h->st;
+    const scb_config &cfg = h->cfg;
+    const int L[2] = {cfg.read_length[0], cfg.read_length[1]};
+    ParsedMate pm[2];
+    const int mates = cfg.paired ? 2 : 1;
+    for (int m = 0; m < mates; m++) parse_lines(h, pm[m], m ? text2 : text1, m ? bytes2 : bytes1, location);
+    const int64_t n = pm[0].n;
+    if (cfg.paired && pm[1].n != n) throw CudaError{"the two FASTQ texts hold different numbers of records"};
+    *n_out = n;
+    if (n == 0) return;
+    int64_t total = n;
+    for (auto &p : h->pending) total += p.n;
+    if (total >= (1ll << 31)) throw CudaError{"more than 2^31-1 reads pending; flush first"};
+    Pending p;
+    p.n = n;
+    DevBuf derr(4, st);
+    SCB_CUDA(cudaMemsetAsync(derr.p, 0, 4, st));
+    for (int m = 0; m < mates; m++) {
+        pm[m].name_len.alloc((size_t)n * 4, st);
+        ParseRec pr{pm[m].t, pm[m].bytes, pm[m].line_end.as<int64_t>(), n, L[m], pm[m].name_len.as<uint32_t>(), derr.as<uint32_t>()};
+        SCB_LAUNCH(parse_records_k, (unsigned)cdiv(n, 256), 256, 0, st, pr);
+    }
+    if (cfg.use_names) {
+        p.b_off.alloc((size_t)(n + 1) * 8, st);
+        DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+        exclusive_scan<uint64_t>(NameLenU{pm[0].name_len.as<uint32_t>()}, n, p.b_off.as<uint64_t>(), p.b_off.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        uint64_t nb = 0;
+        SCB_CUDA(cudaMemcpyAsync(&nb, p.b_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        p.name_bytes = (int64_t)nb;
+        p.b_names.alloc((size_t)nb + 16, st);
+    }
+    p.b_seq1.alloc((size_t)n * L[0], st);
+    if (cfg.use_quals) p.b_qual1.alloc((size_t)n * L[0], st);
+    if (cfg.paired) { p.b_seq2.alloc((size_t)n * L[1], st); if (cfg.use_quals) p.b_qual2.alloc((size_t)n * L[1], st); }
+    for (int m = 0; m < mates; m++) {
+        ParseCopy pc;
+        pc.text = pm[m].t; pc.line_end = pm[m].line_end.as<int64_t>(); pc.n = n; pc.L = L[m]; pc.phred = phred[m];
+        pc.name_off = (m == 0 && cfg.use_names) ? p.b_off.as<uint64_t>() : nullptr;
+        pc.seq = m ? p.b_seq2.as<uint8_t>() : p.b_seq1.as<uint8_t>();
+        pc.qual = cfg.use_quals ? (m ? p.b_qual2.as<uint8_t>() : p.b_qual1.as<uint8_t>()) : nullptr;
+        pc.names = (m == 0 && cfg.use_names) ? p.b_names.as<uint8_t>() : nullptr;
+        pc.err = derr.as<uint32_t>();
+        SCB_LAUNCH(parse_copy_k, (unsigned)cdiv(n * 32, 256), 256, 0, st, pc);
+    }
+    uint32_t err = 0;
+    SCB_CUDA(cudaMemcpyAsync(&err, derr.p, 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    if (err) {
+        throw CudaError{std::string("FASTQ text rejected:") + ((err & 1) ? " a name line does not start with '@';" : "") + ((err & 2) ? " a read line does not have the configured length;" : "") +
+                        ((err & 4) ? " a quality line does not have the configured length;" : "") + ((err & 8) ? " a name is longer than 255 bytes;" : "") +
+                        ((err & 16) ? " a quality symbol lies outside [offset, offset + 80);" : "")};
+    }
+    if (cfg.use_quals) {   // output_quality's input-order statistics (qualities.cpp:186-199), per mate
+        for (int m = 0; m < mates; m++) {
+            if (!h->q_freq3[m].p) {
+                h->q_freq3[m].alloc((size_t)kAcDepth * kAcDepth * 8, st); h->q_freq4[m].alloc((size_t)kAcDepth * kAcDepth * kAcDepth * 8, st);
+                SCB_CUDA(cudaMemsetAsync(h->q_freq3[m].p, 0, h->q_freq3[m].bytes, st));
+                SCB_CUDA(cudaMemsetAsync(h->q_freq4[m].p, 0, h->q_freq4[m].bytes, st));
+            }
+            const uint8_t *sym = m ? p.b_qual2.as<uint8_t>() : p.b_qual1.as<uint8_t>();
+            const int64_t tot = n * L[m];
+            int dev_sms = kSMs;
+            SCB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device));
+            const int grid = (int)std::min<int64_t>((int64_t)dev_sms * 4, cdiv(cdiv(tot, kStatRun), 256));
+            SCB_LAUNCH(parse_qstats_k, grid, 256, 0, st, sym, tot, h->q_prev[m][0], h->q_prev[m][1], h->q_freq3[m].as<unsigned long long>(), h->q_freq4[m].as<unsigned long long>());
+            uint8_t lastq[2] = {0, 0};
+            if (tot >= 2) SCB_CUDA(cudaMemcpyAsync(lastq, sym + tot - 2, 2, cudaMemcpyDeviceToHost, st));
+            else SCB_CUDA(cudaMemcpyAsync(lastq + 1, sym + tot - 1, 1, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            if (tot >= 2) { h->q_prev[m][0] = lastq[0]; h->q_prev[m][1] = lastq[1]; }
+            else { h->q_prev[m][0] = h->q_prev[m][1]; h->q_prev[m][1] = lastq[1]; }
+            h->q_seen[m] += (uint64_t)tot;
+        }
+    }
+    p.seq1 = p.b_seq1.as<uint8_t>(); p.qual1 = p.b_qual1.as<uint8_t>(); p.seq2 = p.b_seq2.as<uint8_t>(); p.qual2 = p.b_qual2.as<uint8_t>();
+    p.names = p.b_names.as<uint8_t>(); p.name_off = p.b_off.as<int64_t>();
+    SCB_CUDA(cudaStreamSynchronize(st));
+    h->pending.push_back(std::move(p));
+}
+
 // ---- (f3) .scalcer body from merged meta + stream 1; (f4) the inverse (container.cuh) -----------------------------------
 static void segment_table(scb_handle *h, const uint8_t *meta_dev, int64_t nseg, DevBuf &seg_core, DevBuf &seg_reads, DevBuf &seg_bytes, DevBuf &in_start) {
     cudaStream_t st = h->st;
@@ -2125,6 +2242,11 @@ int scb_reset_counts(scb_handle *h) {
     SCB_CATCH
     h->life_total = 0;
     h->unbucketed = 0;
+    for (int m = 0; m < 2; m++) {
+        if (h->q_freq3[m].p) { cudaMemsetAsync(h->q_freq3[m].p, 0, h->q_freq3[m].bytes, h->st); cudaMemsetAsync(h->q_freq4[m].p, 0, h->q_freq4[m].bytes, h->st); }
+        h->q_prev[m][0] = h->q_prev[m][1] = 500; h->q_seen[m] = 0;
+    }
+    cudaStreamSynchronize(h->st);
     return SCB_OK;
 }
 
@@ -2332,6 +2454,36 @@ int scb_shard_flush_stats(const scb_handle *h, float *phase_ms, int32_t cap, int
     for (int k = 0; k < SCB_N_SHARD_PHASES && k < cap; k++) if (phase_ms) phase_ms[k] = h->fl_ms[k];
     if (rounds) *rounds = h->fl_rounds;
     return SCB_N_SHARD_PHASES;
+}
+
+int scb_submit_fastq(scb_handle *h, const uint8_t *text1, int64_t bytes1, const uint8_t *text2, int64_t bytes2, int32_t location,
+                     const int32_t *phred_offset, int64_t *n_records) {
+    if (!h || !phred_offset || !n_records || bytes1 < 0 || (bytes1 > 0 && !text1) || (location != 0 && location != 1)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    if (h->cfg.paired && (bytes2 < 0 || (bytes2 > 0 && !text2))) { scb::g_last_error = "paired configuration: the second FASTQ text is missing"; return SCB_EINVAL; }
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::submit_fastq(h, text1, bytes1, text2, bytes2, location, phred_offset, n_records);
+    SCB_CATCH
+    return SCB_OK;
+}
+
+int scb_quality_stats(scb_handle *h, int32_t mate, uint64_t *freq3, uint64_t *freq4) {
+    if (!h || (mate != 0 && mate != 1)) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    const size_t n3 = (size_t)scb::kAcDepth * scb::kAcDepth, n4 = n3 * scb::kAcDepth;
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->q_freq3[mate].p) {
+        if (freq3) memset(freq3, 0, n3 * 8);
+        if (freq4) memset(freq4, 0, n4 * 8);
+        return SCB_OK;
+    }
+    if (freq3) SCB_CUDA(cudaMemcpyAsync(freq3, h->q_freq3[mate].p, n3 * 8, cudaMemcpyDeviceToHost, h->st));
+    if (freq4) SCB_CUDA(cudaMemcpyAsync(freq4, h->q_freq4[mate].p, n4 * 8, cudaMemcpyDeviceToHost, h->st));
+    SCB_CUDA(cudaStreamSynchronize(h->st));
+    // the first symbol of a job sets every ac_freq4 entry to 1 (qualities.cpp:192-197); the counts come on top
+    if (freq4 && h->q_seen[mate] > 0) for (size_t i = 0; i < n4; i++) freq4[i] += 1;
+    SCB_CATCH
+    return SCB_OK;
 }
 
 int scb_assemble_reads(scb_handle *h, int32_t chunk, const uint8_t **body_dev, int64_t *body_bytes, int64_t *n_segments) {

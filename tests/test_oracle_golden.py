@@ -232,3 +232,56 @@ def test_oracle_inverse_matches_reference_decompressor(tmp_path, oracle_lib):
         for i in range(b.n):
             assert seq[i].tobytes() == want_seq[i], f"read line {i}"
             assert q[i].tobytes() == want_q[i], f"quality line {i}"
+
+
+def test_oracle_parse_and_quality_stats_match_reference(tmp_path, oracle_lib):
+    """orc_parse_fastq (the checker of scb_submit_fastq) against the UNMODIFIED reference: the harness feeds the same reads to the
+    reference's output_quality with arithmetic coding on (_no_ac = 0) in a fresh process (its `prev` is a function-static) and its
+    ac_freq3 / ac_freq4 globals must equal the oracle's input-order statistics; names and payload must equal what the SoA holds."""
+    import subprocess
+    import sys
+    harness = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_harness.so")
+    if not os.path.exists(harness):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cores = make_cores(941, [(8, 64), (9, 32)])
+    b = synth.make_batch(3000, 70, seed=941, n_frac=0.02, high_entropy=True)
+    b2 = synth.make_batch(2000, 70, seed=942, n_frac=0.0)
+    d = str(tmp_path)
+    synth.write_fastq(b, d + "/a.fastq")
+    synth.write_fastq(b2, d + "/b.fastq")
+    ta, tb = open(d + "/a.fastq", "rb").read(), open(d + "/b.fastq", "rb").read()
+    # oracle: two texts one after the other (statistics and prev carried across)
+    st = orc.new_quality_stats()
+    seq_a, q_a, nm_a, off_a = orc.parse_fastq(ta, 70, 33, st)
+    seq_b, q_b, nm_b, off_b = orc.parse_fastq(tb[:-1], 70, 33, st)          # last line without its newline
+    assert np.array_equal(seq_a, b.seq) and np.array_equal(seq_b, b2.seq)
+    assert np.array_equal(q_a, orc.quality_payload(b.qual, b.seq, 33)) and np.array_equal(q_b, orc.quality_payload(b2.qual, b2.seq, 33))
+    assert nm_a.tobytes() == b.names.tobytes() and np.array_equal(off_a, b.name_off) and nm_b.tobytes() == b2.names.tobytes()
+    np.savez(d + "/in.npz", seq=np.concatenate([b.seq, b2.seq]), qual=np.concatenate([b.qual, b2.qual]),
+             names=np.concatenate([b.names, b2.names]), off=np.concatenate([b.name_off, b2.name_off[1:] + b.name_off[-1]]))
+    open(d + "/cores.txt", "w").write("\n".join(cores) + "\n")
+    code = f"""
+import ctypes as C, numpy as np
+H = C.CDLL({harness!r})
+H.refh_init.restype = C.c_double; H.refh_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
+H.refh_run.restype = C.c_double; H.refh_run.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+H.refh_set_no_ac.argtypes = [C.c_int]; H.refh_get_stats.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+z = np.load({d + '/in.npz'!r})
+H.refh_set_no_ac(0)
+H.refh_init({d + '/cores.txt'!r}.encode(), 70, 0, 0, 1, 4 << 30)
+p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+seq, qual, names, off = [np.ascontiguousarray(z[k]) for k in ('seq', 'qual', 'names', 'off')]
+nch = C.c_int()
+H.refh_run(seq.shape[0], p(seq), p(qual), p(names), p(off), None, None, 33, {d!r}.encode(), C.byref(nch), None, None)
+f3 = np.zeros(6400, dtype=np.uint64); f4 = np.zeros(512000, dtype=np.uint64)
+H.refh_get_stats(0, p(f3), p(f4))
+np.savez({d + '/ref_stats.npz'!r}, f3=f3, f4=f4)
+"""
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    ref = np.load(d + "/ref_stats.npz")
+    assert np.array_equal(ref["f3"], st["freq3"]), "ac_freq3 differs from the reference's output_quality"
+    assert np.array_equal(ref["f4"], st["freq4"]), "ac_freq4 differs from the reference's output_quality"
+    assert int(st["freq3"].sum()) == 5000 * 70 - 1 and int(st["freq4"].sum()) == 512000 + 5000 * 70 - 2
+    with pytest.raises(ValueError):
+        orc.parse_fastq(ta[:len(ta) // 2 + 7], 70, 33)
