@@ -566,7 +566,9 @@ def main():
             a0, a1 = edges[k], edges[k + 1]
             tr.submit_device(a1 - a0, seq[a0:a1].data_ptr(), qual[a0:a1].data_ptr(), names[a0 * NAME_BYTES:].data_ptr(), off0.data_ptr(),
                              seq2[a0:a1].data_ptr() if paired else None, qual2[a0:a1].data_ptr() if paired else None)
-            r = tr.flush()
+            # several flushes per step (a job beyond one GPU's memory): all but the last are streaming flushes - complete flush chunks
+            # only, the open chunk's reads stay pending - so the step's chunks are those of ONE flush over the whole input
+            r = tr.flush() if k == F - 1 else tr.flush_closed()
             ms += r.device_ms
             for kk, v in tr.stage_ms().items():
                 st[kk] = st.get(kk, 0.0) + v

@@ -127,6 +127,15 @@ int scb_submit(scb_handle *h, const scb_batch *batch);
  * reads.cpp:466-499, 600-634, 91-180) for everything pending; lifetime bucket counts
  * (aho_trie::bin_size, reads.h:82) persist in the handle across flushes. */
 int scb_flush(scb_handle *h, scb_result *out);
+/* Streaming form for jobs that do not fit one flush (inputs beyond HBM, or more than 2^31-1 reads): emits only the flush chunks
+ * that are COMPLETE and keeps the reads of the open chunk pending - they are taken out of the bucket populations again and are
+ * decided anew by the next flush, together with what is submitted in between. Chunk boundaries, chunk contents, in-chunk order
+ * and lifetime counts of a job fed through any sequence of scb_submit / scb_flush_closed calls and one final scb_flush are
+ * therefore those of one scb_flush over the whole input, i.e. the reference's (compress.cpp:702-713 carries total_size across
+ * reads and input files; a caller cannot align plain flushes with chunk boundaries because rd.sz depends on the core picked on
+ * the device). out->n_reads = reads emitted (0 when no chunk closed yet); chunk numbers restart at 0 in every result: the caller
+ * numbers its temp files consecutively. Needs emit_merged = 0. Not part of the sharded run (scb_shard_sizes carries the sum). */
+int scb_flush_closed(scb_handle *h, scb_result *out);
 /* Device-to-host copy of one stream slice (chunk >= 0) or of the merged stream (chunk = -1). */
 int scb_copy_stream(scb_handle *h, int32_t stream, int32_t chunk, void *dst, int64_t dst_bytes);
 /* Copies per-read arrays of the last flush to host; any pointer may be NULL. */

@@ -18,7 +18,7 @@ ROOT_ID = (1 << 30) - 1
 
 EXPORTS = [
     "scb_abi_version", "scb_last_error", "scb_table_dryrun", "scb_create", "scb_create_from_file", "scb_table_info", "scb_core",
-    "scb_submit", "scb_flush", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
+    "scb_submit", "scb_flush", "scb_flush_closed", "scb_copy_stream", "scb_copy_debug", "scb_unbucketed", "scb_lifetime_count",
     "scb_kernel_launches", "scb_stage_ms", "scb_resolve_rounds", "scb_resolve_engine", "scb_device_bytes", "scb_assemble_reads", "scb_copy_assembled", "scb_inverse_reads", "scb_submit_fastq", "scb_quality_stats", "scb_reset_counts", "scb_destroy",
     "scb_set_stream", "scb_shard_info", "scb_shard_scan", "scb_shard_sizes", "scb_shard_resolve_local", "scb_shard_resolve_round",
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
@@ -88,6 +88,7 @@ def load_library(path: str | None = None):
     L.scb_core.argtypes = [C.c_void_p, C.c_int32]
     L.scb_submit.argtypes = [C.c_void_p, C.POINTER(ScbBatch)]
     L.scb_flush.argtypes = [C.c_void_p, C.POINTER(ScbResult)]
+    L.scb_flush_closed.argtypes = [C.c_void_p, C.POINTER(ScbResult)]
     L.scb_copy_stream.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
     L.scb_copy_debug.argtypes = [C.c_void_p] * 6
     L.scb_unbucketed.restype = C.c_int64
@@ -322,6 +323,12 @@ class BoostTransform:
         _check(L.scb_inverse_reads(self._h, p(stream), p(seg_core), p(seg_reads), len(seg_core), p(q_in), mate, phred_offset, 0, p(seq), p(q_out), C.byref(nn)))
         assert nn.value == n
         return seq[:n], (None if q_out is None else q_out[:n])
+
+    def flush_closed(self) -> FlushResult:
+        """Streaming flush: only the complete flush chunks; the open chunk's reads stay pending (scb_flush_closed)."""
+        res = ScbResult()
+        _check(load_library().scb_flush_closed(self._h, C.byref(res)))
+        return FlushResult(self, res)
 
     @property
     def unbucketed(self):

@@ -163,6 +163,7 @@ struct scb_handle {
     DevBuf dbg_bucket, dbg_core, dbg_end, dbg_chunk;
     EmitOut chunked, merged;
     int32_t n_chunks = 0;
+    int64_t open_from = 0;        // first read of the last flush's open chunk (streaming flush)
     int64_t n_last = 0;
     int64_t unbucketed = 0;
     bool smem_resident = false;
@@ -1001,9 +1002,15 @@ static void stage_chunks(scb_handle *h) {
         DevBuf cstart((size_t)cap * 4, st), dn(4, st);
         SCB_LAUNCH(chunk_bounds_k, 1, 1, 0, st, S.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, cstart.as<uint32_t>(), cap, dn.as<int>());
         int nch = 0;
+        long long open_from = 0;
+        DevBuf dof(8, st);
         SCB_CUDA(cudaMemcpyAsync(&nch, dn.p, 4, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));
         if (nch > cap) throw CudaError{"internal: chunk capacity exceeded"};
+        SCB_LAUNCH(chunk_open_from_k, 1, 1, 0, st, S.as<uint64_t>(), n, (uint64_t)cfg.bucket_set_bytes, cstart.as<uint32_t>(), nch, dof.as<long long>());
+        SCB_CUDA(cudaMemcpyAsync(&open_from, dof.p, 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        h->open_from = open_from;
         h->n_chunks = nch;
         if (nch > 1) {
             h->chunk.alloc((size_t)n * 4, st);
@@ -1604,8 +1611,14 @@ static void shard_finish(scb_handle *h, int what /* 1 = sort, 2 = emit, 3 = both
 }
 
 // ---- the transform on one GPU ------------------------------------------------------------------------------
-static void run_flush(scb_handle *h) {
+// closed_only (scb_flush_closed): only the flush chunks that are complete are emitted; the reads of the open chunk are taken out
+// of the populations again and stay pending, so that the next flush decides them exactly as if nothing had happened - the chunk
+// boundaries, chunk contents and lifetime counts of a job fed in pieces are those of the reference fed the whole input
+// (compress.cpp:702-713 carries total_size across reads and input files).
+static void run_flush(scb_handle *h, bool closed_only = false) {
     cudaStream_t st = h->st;
+    Pending tail;                 // reads of the open chunk, copied out of the flush workspace (pooled memory)
+    {
     ArenaScope arena_scope(&h->arena);
     h->sh_phase = 0;
     flush_begin(h, 1.0);
@@ -1618,6 +1631,25 @@ static void run_flush(scb_handle *h) {
     stage_meta(h);
     SCB_CUDA(cudaEventRecord(h->stage_ev[2], st));
     stage_chunks(h);
+    const int64_t n_all = h->cur.n;
+    int64_t keep = n_all;
+    if (closed_only && h->open_from < n_all) {
+        keep = h->open_from;
+        const int64_t m = n_all - keep;
+        const int nb = h->tab.n_buckets;
+        DevBuf droots(8, st);
+        SCB_CUDA(cudaMemsetAsync(droots.p, 0, 8, st));
+        SCB_LAUNCH(uncommit_tail_k, (unsigned)cdiv(m, 256), 256, 0, st, h->asg.as<uint32_t>(), keep, n_all, h->d_life.as<unsigned long long>(), nb, droots.as<unsigned long long>());
+        unsigned long long roots = 0;
+        SCB_CUDA(cudaMemcpyAsync(&roots, droots.p, 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        h->life_total -= (uint64_t)m;
+        if (h->tab.root_counts_unbucketed) h->unbucketed -= (int64_t)roots;
+        h->n_chunks -= 1;
+        h->cur.n = keep;              // everything below works on the closed chunks only
+        h->n_perm = keep;
+        h->n_last = keep;
+    }
     SCB_CUDA(cudaEventRecord(h->stage_ev[3], st));
     stage_sort(h);
     stage_emit(h);
@@ -1627,6 +1659,34 @@ static void run_flush(scb_handle *h) {
     SCB_CUDA(cudaEventRecord(h->ev1, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k < SCB_N_STAGES; k++) SCB_CUDA(cudaEventElapsedTime(&h->stage_ms[k], h->stage_ev[k], h->stage_ev[k + 1]));
+    if (keep < n_all) {
+        // the open chunk's reads leave the flush workspace (the next flush re-uses it from the start) as an owned pending batch
+        const scb_config &cfg = h->cfg;
+        const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+        const Pending &c = h->cur;
+        const int64_t m = n_all - keep;
+        g_arena = nullptr;            // pooled allocations from here on
+        tail.n = m;
+        auto cp = [&](DevBuf &d, const uint8_t *src, size_t bytes) { d.alloc(bytes, st); SCB_CUDA(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyDeviceToDevice, st)); };
+        cp(tail.b_seq1, c.seq1 + keep * L1, (size_t)m * L1);
+        if (cfg.use_quals) cp(tail.b_qual1, c.qual1 + keep * L1, (size_t)m * L1);
+        if (cfg.paired) { cp(tail.b_seq2, c.seq2 + keep * L2, (size_t)m * L2); if (cfg.use_quals) cp(tail.b_qual2, c.qual2 + keep * L2, (size_t)m * L2); }
+        if (cfg.use_names) {
+            int64_t o2[2] = {0, 0};
+            SCB_CUDA(cudaMemcpyAsync(&o2[0], c.name_off + keep, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&o2[1], c.name_off + n_all, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            tail.name_bytes = o2[1] - o2[0];
+            cp(tail.b_names, c.names + o2[0], (size_t)tail.name_bytes);
+            tail.b_off.alloc((size_t)(m + 1) * 8, st);
+            SCB_LAUNCH(rebase_off_k, (unsigned)cdiv(m + 1, 256), 256, 0, st, c.name_off + keep, m + 1, tail.b_off.as<int64_t>());
+        }
+        SCB_CUDA(cudaStreamSynchronize(st));
+        tail.seq1 = tail.b_seq1.as<uint8_t>(); tail.qual1 = tail.b_qual1.as<uint8_t>(); tail.seq2 = tail.b_seq2.as<uint8_t>(); tail.qual2 = tail.b_qual2.as<uint8_t>();
+        tail.names = tail.b_names.as<uint8_t>(); tail.name_off = tail.b_off.as<int64_t>();
+    }
+    }   // arena scope
+    if (tail.n > 0) h->pending.insert(h->pending.begin(), std::move(tail));
 }
 
 static void fill_result(scb_handle *h, scb_result *out) {
@@ -2005,6 +2065,22 @@ int scb_flush(scb_handle *h, scb_result *out) {
     SCB_TRY
     SCB_CUDA(cudaSetDevice(h->cfg.device));
     scb::run_flush(h);
+    float ms = 0;
+    SCB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    out->device_ms = ms;
+    SCB_CATCH
+    scb::fill_result(h, out);
+    return SCB_OK;
+}
+
+int scb_flush_closed(scb_handle *h, scb_result *out) {
+    if (!h || !out) { scb::g_last_error = "null argument"; return SCB_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (h->cfg.emit_merged) { scb::g_last_error = "scb_flush_closed emits flush chunks only (emit_merged = 0): the merge across flushes is merge()'s (compress.cpp:488-522)"; return SCB_ESTATE; }
+    if (h->pending.empty()) h->pending.emplace_back();
+    SCB_TRY
+    SCB_CUDA(cudaSetDevice(h->cfg.device));
+    scb::run_flush(h, true);
     float ms = 0;
     SCB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     out->device_ms = ms;

@@ -177,6 +177,26 @@ __global__ void chunk_bounds_k(const uint64_t *__restrict__ S, int64_t n, uint64
     *n_chunks = c;
 }
 
+// streaming flush: first read of the flush's OPEN chunk (n if the last chunk closed with the last read) - compress.cpp:708-713
+__global__ void chunk_open_from_k(const uint64_t *__restrict__ S, int64_t n, uint64_t B, const uint32_t *__restrict__ chunk_start, int n_chunks, long long *out) {
+    if (n_chunks <= 0 || n == 0) { *out = 0; return; }
+    const int64_t s = chunk_start[n_chunks - 1];
+    *out = (S[n] - S[s] >= B) ? (long long)n : (long long)s;
+}
+// takes the reads [from, n) out of the lifetime populations again (they stay pending); roots = how many of them had no core
+__global__ void uncommit_tail_k(const uint32_t *__restrict__ asg, int64_t from, int64_t n, unsigned long long *__restrict__ life, int nb,
+                                unsigned long long *__restrict__ roots) {
+    const int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t a = asg[i];
+    atomicAdd(&life[a], ~0ull);              // - 1
+    if (a == (uint32_t)nb) atomicAdd(roots, 1ull);
+}
+__global__ void rebase_off_k(const int64_t *__restrict__ off, int64_t m1, int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m1) out[i] = off[i] - off[0];
+}
+
 __global__ void chunk_ids_k(const uint32_t *__restrict__ chunk_start, int n_chunks, int64_t n, uint32_t *__restrict__ chunk) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

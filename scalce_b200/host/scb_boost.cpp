@@ -156,7 +156,7 @@ int main(int argc, char **argv) {
     std::string library;
     int asm_L1 = 0, asm_L2 = 0, asm_paired = 0; long long asm_offset = 33;
     uint64_t bucket_set = 4ull << 30;   // -B, main.cpp default
-    int use_names = 1, use_quals = 1, merged = 0, device = 0, sample_lines = 100000;
+    int use_names = 1, use_quals = 1, merged = 0, device = 0, sample_lines = 100000, device_parse = 0;
     int64_t batch_reads = 4 << 20;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -168,6 +168,7 @@ int main(int argc, char **argv) {
         else if (a == "-n") use_names = 0;
         else if (a == "--no-quals") use_quals = 0;
         else if (a == "--merged") merged = 1;
+        else if (a == "--device-parse") device_parse = 1;   // the parse loop / output_name / output_quality on the GPU (scb_submit_fastq)
         else if (a == "--device") device = atoi(need("--device"));
         else if (a == "--batch") batch_reads = atoll(need("--batch"));
         else if (a == "--dump-soa") dump = need("--dump-soa");
@@ -197,7 +198,7 @@ int main(int argc, char **argv) {
     }
     if (container) merged = 1;
     if (!in1 || (!out && !dump && !container) || (!cores && !dump))
-        die("usage: scb_boost in_1.fastq [-r in_2.fastq] -P cores.txt -o out_dir [-B bytes] [-n] [--no-quals] [--merged] [--batch reads] [--device d] | --dump-soa dir");
+        die("usage: scb_boost in_1.fastq [-r in_2.fastq] -P cores.txt -o out_dir [-B bytes] [-n] [--no-quals] [--merged] [--batch reads] [--device d] [--device-parse] | --dump-soa dir");
     if (batch_reads < 1) die("--batch must be positive");
 
     const Sample s1 = sample_file(in1, sample_lines);
@@ -216,6 +217,39 @@ int main(int argc, char **argv) {
         scb_check(scb_create_from_file(cores, &cfg, &h));
     }
 
+    if (device_parse && !dump) {
+        // the file goes to the device as text, in pieces of whole records; the library does the parse loop
+        // (compress.cpp:614-671), output_name and output_quality. Everything after the submit is the same as below.
+        auto slurp = [](const char *path) {
+            FILE *f = fopen(path, "rb");
+            if (!f) die(std::string("cannot open ") + path + ": " + strerror(errno));
+            std::vector<uint8_t> v;
+            std::vector<uint8_t> tmp(8 << 20);
+            size_t r;
+            while ((r = fread(tmp.data(), 1, tmp.size(), f)) > 0) v.insert(v.end(), tmp.begin(), tmp.begin() + r);
+            fclose(f);
+            return v;
+        };
+        const std::vector<uint8_t> t1 = slurp(in1), t2 = in2 ? slurp(in2) : std::vector<uint8_t>();
+        // pieces of `batch_reads` records: advance 4 * batch_reads line ends in each text
+        auto advance = [](const std::vector<uint8_t> &t, size_t from, int64_t records) {
+            int64_t lines = 4 * records;
+            size_t p = from;
+            while (p < t.size() && lines > 0) { if (t[p] == '\n') lines--; p++; }
+            return p;
+        };
+        const int32_t ph[2] = {s1.offset, in2 ? s2.offset : s1.offset};
+        size_t p1 = 0, p2 = 0;
+        int64_t n_total_dev = 0;
+        while (p1 < t1.size()) {
+            const size_t e1 = advance(t1, p1, batch_reads), e2 = in2 ? advance(t2, p2, batch_reads) : 0;
+            int64_t got = 0;
+            scb_check(scb_submit_fastq(h, t1.data() + p1, (int64_t)(e1 - p1), in2 ? t2.data() + p2 : nullptr, in2 ? (int64_t)(e2 - p2) : 0, 0, ph, &got));
+            n_total_dev += got;
+            p1 = e1; p2 = e2;
+        }
+        fprintf(stderr, "scb_boost: %lld records parsed on the device\n", (long long)n_total_dev);
+    }
     LineReader r1(in1);
     LineReader *r2 = in2 ? new LineReader(in2) : nullptr;
     Soa soa, all;   // `all` only in --dump-soa mode
@@ -243,7 +277,7 @@ int main(int argc, char **argv) {
         }
         soa.clear();
     };
-    while (r1.next(name)) {
+    while (!(device_parse && !dump) && r1.next(name)) {
         if (!r1.next(read)) break;
         if (read.empty()) {   // compress.cpp:620-625 (the reference has not consumed the '+' / quality lines at that point either)
             fprintf(stderr, "Whooops... %s is empty, skipping it!\n", name.c_str());

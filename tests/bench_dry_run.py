@@ -81,6 +81,8 @@ class _FakeTransform:
     def flush(self):
         return _Res(self.n, self.paired)
 
+    flush_closed = flush
+
     def stage_ms(self):
         return dict(zip(self.STAGES, [1.0, 2.0, 0.1, 0.5, 0.1, 3.0, 0.0, 0.05]))
 

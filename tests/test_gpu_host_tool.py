@@ -10,8 +10,9 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("device_parse", [False, True], ids=["host_parse", "device_parse"])
 @pytest.mark.parametrize("paired", [False, True])
-def test_host_tool_temp_files_match_oracle(tmp_path, paired):
+def test_host_tool_temp_files_match_oracle(tmp_path, paired, device_parse):
     import subprocess
     from scalce_b200 import build as bld, synth
     tool = bld.build_host_tool()
@@ -22,7 +23,7 @@ def test_host_tool_temp_files_match_oracle(tmp_path, paired):
     (tmp_path / "cores.txt").write_text("\n".join(cores) + "\n")
     out = tmp_path / "out"
     out.mkdir()
-    cmd = [tool, f1] + (["-r", f2] if paired else []) + ["-P", str(tmp_path / "cores.txt"), "-o", str(out), "-B", str(1 << 21), "--merged", "--batch", "7001"]
+    cmd = [tool, f1] + (["-r", f2] if paired else []) + ["-P", str(tmp_path / "cores.txt"), "-o", str(out), "-B", str(1 << 21), "--merged", "--batch", "7001"] + (["--device-parse"] if device_parse else [])
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()
     nf = 6 if paired else 4

@@ -203,3 +203,37 @@ def test_second_flush_with_large_populations_dense_engine():
     o = util.run_oracle(cores, b, q1, q2, splits=[350000])
     t, r = util.run_cuda(cores, b, q1, q2, splits=[350000])
     util.assert_same(o, t, r)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_streaming_flush_equals_one_flush(paired):
+    """scb_flush_closed: a job fed in pieces, with only the complete flush chunks emitted after every piece and the open chunk's
+    reads kept pending, produces exactly the chunks of ONE flush over the whole input (= the reference, which carries total_size
+    across reads, compress.cpp:702-713): same boundaries, same bytes, same lifetime counts."""
+    from scalce_b200.binding import BoostTransform
+    B = 1 << 20
+    cores, b, q1, q2, _ = util.make_case(60000, 100, seed=701 + int(paired), paired=paired, L2=75 if paired else None)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, bucket_set_bytes=B)
+    L2 = 75 if paired else 0
+    t = BoostTransform(cores, 100, L2, paired=paired, bucket_set_bytes=B, emit_merged=False)
+    nstream = 6 if paired else 4
+    chunks, emitted = [], 0
+    cuts = [0, 300, 7000, 7001, 30000, 30500, 60000]      # the first piece is smaller than a chunk: nothing closes
+    for a, z in zip(cuts[:-1], cuts[1:]):
+        t.submit(b.seq[a:z], q1[a:z], b.names, b.name_off[a:z + 1], b.seq2[a:z] if paired else None, q2[a:z] if paired else None)
+        r = t.flush_closed()
+        emitted += r.n_reads
+        assert emitted <= z
+        for c in range(r.n_chunks):
+            chunks.append([r.stream(k, c) for k in range(nstream)])
+    r = t.flush()
+    emitted += r.n_reads
+    for c in range(r.n_chunks):
+        chunks.append([r.stream(k, c) for k in range(nstream)])
+    assert emitted == b.n and len(chunks) == o.n_chunks and o.n_chunks > 8
+    for c in range(o.n_chunks):
+        for k in range(nstream):
+            assert chunks[c][k] == o.stream(k, c), f"chunk {c} stream {k}"
+    for ci in (0, 5, 17, 100):
+        assert o.lifetime_count(ci) == t.lifetime_count(ci)
+    assert o.unbucketed == t.unbucketed
