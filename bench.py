@@ -514,6 +514,7 @@ def main():
         qual2 = torch.where(seq2 == ord("N"), torch.zeros_like(d["qual2"]), d["qual2"] - 33)
     del d
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()          # the generator's temporaries go back to the driver: the library allocates with cudaMalloc, not through torch
 
     tr = BoostTransform(cores, L, L2, paired=paired, device=local, emit_merged=False)
     info = tr.table_info()
@@ -533,7 +534,7 @@ def main():
     if F <= 0:
         F = 1
         free_b, _ = torch.cuda.mem_get_info(dev)
-        per_read = 300 + 2 * L + (L // 4) + ((3 * L2) if paired else 0)     # workspace + output streams, generous
+        per_read = 360 + 3 * L + (L // 4) + ((3 * L2) if paired else 0)     # workspace + output streams + the concatenation copy of a multi-batch flush, generous
         while F < 16 and (N / F) * per_read > 0.85 * free_b:
             F += 1
         if world > 1:
