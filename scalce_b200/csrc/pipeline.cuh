@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(256) name_len_range_k(const int64_t *__restric
         const long long a = __shfl_xor_sync(0xffffffffu, mx, d), b = __shfl_xor_sync(0xffffffffu, mn, d);
         mx = a > mx ? a : mx; mn = b > mn ? b : mn;
     }
-    if (lane_id() == 0) { if (mx > 0) atomicMax(out, mx); if (mn > 0) atomicMax(out + 1, mn); }
+    // a racy read first: the maxima only grow, so a stale value can only cause a redundant atomic, never a missed one
+    if (lane_id() == 0) { if (mx > ((volatile long long *)out)[0]) atomicMax(out, mx); if (mn > ((volatile long long *)out)[1]) atomicMax(out + 1, mn); }
 }
 
 // S[0..n] exclusive prefix of RdSize (S[n] = total). A chunk ends with the first read that brings
