@@ -289,7 +289,10 @@ def e2e_pipelined(depth, steps_per_slot, cores, L, device, N, host_in, lib, L2=0
     handles = [BoostTransform(cores, L, L2, paired=paired, device=device, emit_merged=False) for _ in range(depth)]
     outbufs = [None] * depth
     sizes_seen = [None] * depth
-    gpu_lock = threading.Lock()
+    # one slot at a time per resource: the host->device direction (submit), the GPU (flush), the device->host direction
+    # (copy-out). Without the two copy locks the slots drift into lock step - both submitting, then both copying out - and each
+    # direction of the link is shared instead of the two directions being used at the same time.
+    gpu_lock, h2d_lock, d2h_lock = threading.Lock(), threading.Lock(), threading.Lock()
     errors = []
     nstream = 6 if paired else 4
 
@@ -298,18 +301,20 @@ def e2e_pipelined(depth, steps_per_slot, cores, L, device, N, host_in, lib, L2=0
             t = handles[slot]
             for _ in range(nsteps):
                 t.reset_counts()
-                t.submit(h_seq.reshape(N, L), h_qual.reshape(N, L), h_names, h_off, h_seq2, h_qual2)
+                with h2d_lock:
+                    t.submit(h_seq.reshape(N, L), h_qual.reshape(N, L), h_names, h_off, h_seq2, h_qual2)
                 with gpu_lock:
                     r = t.flush()
                 sizes = [r.chunk_off[k][-1] for k in range(6)]
                 if outbufs[slot] is None:
                     outbufs[slot] = [torch.empty(max(int(sz * 1.02), 1), dtype=torch.uint8).pin_memory() for sz in sizes]
-                for k in range(nstream):
-                    for c in range(r.n_chunks):
-                        o0, o1 = r.chunk_off[k][c], r.chunk_off[k][c + 1]
-                        rc = lib.scb_copy_stream(t._h, k, c, C.c_void_p(outbufs[slot][k].data_ptr() + o0), o1 - o0)
-                        if rc != 0:
-                            raise RuntimeError(f"scb_copy_stream -> {rc}")
+                with d2h_lock:
+                    for k in range(nstream):
+                        for c in range(r.n_chunks):
+                            o0, o1 = r.chunk_off[k][c], r.chunk_off[k][c + 1]
+                            rc = lib.scb_copy_stream(t._h, k, c, C.c_void_p(outbufs[slot][k].data_ptr() + o0), o1 - o0)
+                            if rc != 0:
+                                raise RuntimeError(f"scb_copy_stream -> {rc}")
                 sizes_seen[slot] = sizes
         except BaseException as ex:  # noqa: BLE001 - reported by the caller
             errors.append(ex)

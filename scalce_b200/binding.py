@@ -73,7 +73,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SCB_LIB_PATH") or LIB_PATH     # SCB_LIB_PATH: a differently built library for A/B runs of compile-time choices
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: build it with `python -m scalce_b200.build` (nvcc, sm_100a). "
                            "scalce_b200 has no CPU fallback.")
