@@ -197,6 +197,8 @@ struct scb_handle {
     int64_t sp_M = 0;
     DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev, sp_tile_clean, sp_ractive;
     uint32_t sp_dirty_tiles = 0;
+    int sp_rank_bits = 24; int64_t sp_blk_reads = 0; int sp_nblk = 1;   // (block, bucket) keys of the sorted view
+    std::vector<int64_t> sp_blk_pair, sp_blk_tile;                         // [nblk + 1] first pair / first tile slot of every block
     uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
@@ -655,7 +657,7 @@ static int pick_engine(const scb_handle *h, uint64_t reads_in_job) {
 
 // ---- sparse resolve engine (resolve_sparse.cuh) ------------------------------------------------------------------
 // builds the bucket-major view of the candidate pairs of h->cur (once per flush)
-static void sparse_setup(scb_handle *h) {
+static void sparse_setup(scb_handle *h, bool blocked) {
     cudaStream_t st = h->st;
     const int64_t n = h->cur.n;
     const int nb1 = h->tab.n_buckets + 1;
@@ -679,9 +681,35 @@ static void sparse_setup(scb_handle *h) {
     if (M >= 0xffffffffull) throw CudaError{"more than 2^32-1 candidate pairs in one flush: flush fewer reads at a time"};
     h->sp_M = (int64_t)M;
     const int64_t M1 = std::max<int64_t>((int64_t)M, 1);
-    const int64_t tiles = cdiv(M1, kSpTile);
+    // input-order blocks (one GPU owning the order): ~1 M reads each. The sharded rounds use one block.
+    h->sp_rank_bits = std::max(1, ceil_log2((uint64_t)nb1));
+    int64_t want = 1 << 20;
+    if (const char *e = getenv("SCB_SPARSE_BLOCK")) want = std::max<int64_t>(1024, atoll(e));      // reads per block (experiments)
+    h->sp_nblk = blocked ? (int)std::min<int64_t>(4096, std::max<int64_t>(1, n / want)) : 1;
+    h->sp_blk_reads = std::max<int64_t>(1, cdiv(std::max<int64_t>(n, 1), h->sp_nblk));
+    h->sp_nblk = (int)cdiv(std::max<int64_t>(n, 1), h->sp_blk_reads);
+    const int blk_bits = ceil_log2((uint64_t)h->sp_nblk);
+    if (h->sp_rank_bits + blk_bits > 31) { h->sp_nblk = 1; h->sp_blk_reads = std::max<int64_t>(n, 1); }
+    h->sp_blk_pair.assign((size_t)h->sp_nblk + 1, 0);
+    {
+        std::vector<int64_t> idx((size_t)h->sp_nblk + 1);
+        for (int k = 0; k <= h->sp_nblk; k++) idx[(size_t)k] = std::min<int64_t>(n, (int64_t)k * h->sp_blk_reads);
+        DevBuf didx(idx.size() * 8, st), dout(idx.size() * 8, st);
+        SCB_CUDA(cudaMemcpyAsync(didx.p, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, st));
+        SCB_LAUNCH(gather_u64_k, (unsigned)cdiv((int64_t)idx.size(), 64), 64, 0, st, h->sp_doff.as<uint64_t>(), didx.as<int64_t>(), (int)idx.size(), dout.as<int64_t>());
+        SCB_CUDA(cudaMemcpyAsync(h->sp_blk_pair.data(), dout.p, idx.size() * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+    }
+    // per-block tiles: every block's tile-indexed arrays (flag bytes, tails, clean marks) start at their own slot
+    int64_t tiles = 0;
+    h->sp_blk_tile.assign((size_t)h->sp_nblk + 1, 0);
+    for (int k = 0; k < h->sp_nblk; k++) {
+        h->sp_blk_tile[(size_t)k] = tiles;
+        tiles += cdiv(std::max<int64_t>(h->sp_blk_pair[(size_t)k + 1] - h->sp_blk_pair[(size_t)k], 1), kSpTile);
+    }
+    h->sp_blk_tile[(size_t)h->sp_nblk] = tiles;
     h->sp_sb.alloc((size_t)M1 * 4, st); h->sp_sread.alloc((size_t)M1 * 4, st); h->sp_sk.alloc((size_t)M1 * 2, st); h->sp_sval.alloc((size_t)M1 * 4, st);
-    h->sp_cnt.alloc((size_t)M1 * 4, st); h->sp_fbyte.alloc((size_t)(M1 / 8 + 16), st);
+    h->sp_cnt.alloc((size_t)M1 * 4, st); h->sp_fbyte.alloc((size_t)tiles * (kSpTile / 8) + 16, st);
     h->sp_tail.alloc((size_t)tiles * 4, st); h->sp_treset.alloc((size_t)tiles * 4, st); h->sp_X.alloc((size_t)tiles * 4, st);
     h->sp_tile_clean.alloc((size_t)tiles, st); h->sp_ractive.alloc((size_t)std::max<int64_t>(n, 1), st);
     h->sp_dirty_tiles = (uint32_t)std::min<int64_t>(tiles, 0xffffffffll);   // "all dirty" until a round reports otherwise (the sharded rounds never do: no read-back per round)
@@ -692,12 +720,12 @@ static void sparse_setup(scb_handle *h) {
         DevBuf hist((size_t)SortWs::hist_elems(M1) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(M1)) * 4, st);
         if (n > 0)
             SCB_LAUNCH(sp_pairs_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
-                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>());
+                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_blk_reads, h->sp_rank_bits);
         if (M > 0) {
             SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
             uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
             uint32_t *va = v0.as<uint32_t>(), *vb = v1.as<uint32_t>();
-            radix_sort_pairs(&ka, &va, &kb, &vb, (int64_t)M, 0, std::max(1, ceil_log2((uint64_t)nb1)), ws, st);
+            radix_sort_pairs(&ka, &va, &kb, &vb, (int64_t)M, 0, h->sp_rank_bits + ceil_log2((uint64_t)h->sp_nblk), ws, st);
             SCB_LAUNCH(sp_post_k, (unsigned)cdiv((int64_t)M, 256), 256, 0, st, (int64_t)M, ka, va, pread.as<uint32_t>(), h->sp_doff.as<uint64_t>(),
                        h->sp_sb.as<uint32_t>(), h->sp_sread.as<uint32_t>(), h->sp_sk.as<uint16_t>());
             SCB_CUDA(cudaMemcpyAsync(h->sp_sval.p, va, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
@@ -707,76 +735,92 @@ static void sparse_setup(scb_handle *h) {
     h->sp_ready = true;
 }
 
-// one round: counts of the current assignment from `base`, then every read re-decides. hist_mode: 0 none, 1 rebuild the local
-// bucket histogram (sp_hist), 2 update it by the changes. The changed count lands in sp_changed.
-static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode) {
+// one round over input-order block `blk`: counts of the current assignment from `base` (the populations before the block's
+// first read), then every read of the block re-decides. hist_mode: 0 none, 1 rebuild the local bucket histogram (sp_hist),
+// 2 update it by the changes (sharded rounds: one block). The changed count lands in sp_changed.
+static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode, int blk, bool first_of_block) {
     cudaStream_t st = h->st;
-    const int64_t n = h->cur.n, M = h->sp_M;
+    const int64_t n = h->cur.n;
     const int nb1 = h->tab.n_buckets + 1;
     SCB_CUDA(cudaMemsetAsync(h->sp_changed.p, 0, 16, st));
-    if (M == 0 || n == 0) { if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st)); return; }
-    const int64_t tiles = cdiv(M, kSpTile);
+    if (h->sp_M == 0 || n == 0) { if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st)); return; }
+    const int64_t p0 = h->sp_blk_pair[(size_t)blk], M = h->sp_blk_pair[(size_t)blk + 1] - p0;
+    const int64_t i0 = std::min<int64_t>(n, (int64_t)blk * h->sp_blk_reads), nr = std::min<int64_t>(n, (int64_t)(blk + 1) * h->sp_blk_reads) - i0;
+    const int64_t t0 = h->sp_blk_tile[(size_t)blk];
     const uint32_t round = h->sp_round++;
     if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
+    if (M == 0) return;                                        // no read of the block has a candidate: nothing to decide
+    const int64_t tiles = cdiv(M, kSpTile);
     // reads are marked active (one more random store per rewritten count) only once few tiles are dirty; before that every read re-decides
-    const bool use_active = round > 0 && (uint64_t)h->sp_dirty_tiles * 4 < (uint64_t)tiles;
-    if (hist_mode != 0) {   // sharded rounds: `base` moves between rounds; buckets whose value moved are dirty (round 0: all are anyway)
-        if (round == 0) SCB_CUDA(cudaMemcpyAsync(h->sp_base_prev.p, base, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
+    const bool use_active = !first_of_block && (uint64_t)h->sp_dirty_tiles * 4 < (uint64_t)tiles;
+    if (hist_mode != 0) {   // sharded rounds: `base` moves between rounds; buckets whose value moved are dirty (first round: all are anyway)
+        if (first_of_block) SCB_CUDA(cudaMemcpyAsync(h->sp_base_prev.p, base, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
         else SCB_LAUNCH(sp_mark_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, base, h->sp_base_prev.as<uint32_t>(), nb1, h->sp_dirty.as<uint32_t>(), round);
     }
     SpRound r;
-    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round; r.tile_clean = h->sp_tile_clean.as<uint8_t>(); r.n_dirty_tiles = h->sp_changed.as<uint32_t>() + 1;
-    r.M = M; r.sb = h->sp_sb.as<uint32_t>(); r.sread = h->sp_sread.as<uint32_t>(); r.sval = h->sp_sval.as<uint32_t>(); r.sk = h->sp_sk.as<uint16_t>();
-    r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>(); r.tail = h->sp_tail.as<uint32_t>(); r.treset = h->sp_treset.as<uint32_t>();
+    r.dirty = h->sp_dirty.as<uint32_t>(); r.round = round; r.all = first_of_block ? 1u : 0u; r.rank_mask = (1u << h->sp_rank_bits) - 1u;
+    r.tile_clean = h->sp_tile_clean.as<uint8_t>() + t0; r.n_dirty_tiles = h->sp_changed.as<uint32_t>() + 1;
+    r.M = M; r.sb = h->sp_sb.as<uint32_t>() + p0; r.sread = h->sp_sread.as<uint32_t>() + p0; r.sval = h->sp_sval.as<uint32_t>() + p0; r.sk = h->sp_sk.as<uint16_t>() + p0;
+    r.sel = h->sh_sel.as<uint16_t>(); r.fbyte = h->sp_fbyte.as<uint8_t>() + t0 * (kSpTile / 8); r.tail = h->sp_tail.as<uint32_t>() + t0; r.treset = h->sp_treset.as<uint32_t>() + t0;
     SCB_LAUNCH(sp_flags_k, (unsigned)tiles, kSpThreads, 0, st, r);
-    SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, h->sp_tail.as<uint32_t>(), h->sp_treset.as<uint32_t>(), tiles, h->sp_X.as<uint32_t>());
+    SCB_LAUNCH(sp_tilescan_k, 1, 1024, 0, st, r.tail, r.treset, tiles, h->sp_X.as<uint32_t>() + t0);
     SpCounts c;
-    c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>(); c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
-    c.dirty = r.dirty; c.round = round; c.tile_clean = r.tile_clean; c.sread = r.sread; c.ractive = use_active ? h->sp_ractive.as<uint8_t>() : (uint8_t *)nullptr; c.stamp = (uint8_t)(round & 0xffu);
+    c.M = M; c.sb = r.sb; c.sval = r.sval; c.fbyte = r.fbyte; c.X = h->sp_X.as<uint32_t>() + t0; c.base = base; c.cnt = h->sp_cnt.as<uint32_t>(); c.fold = nullptr;
+    c.dirty = r.dirty; c.round = round; c.all = r.all; c.rank_mask = r.rank_mask; c.tile_clean = r.tile_clean; c.sread = r.sread;
+    c.ractive = use_active ? h->sp_ractive.as<uint8_t>() : (uint8_t *)nullptr; c.stamp = (uint8_t)(round & 0xffu);
     SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
-    SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->sp_doff.as<uint64_t>(), h->sp_cnt.as<uint32_t>(),
-               h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_changed.as<uint32_t>(),
+    SCB_LAUNCH(sp_decide_k, (unsigned)cdiv(nr, 256), 256, 0, st, nr, h->ncand.as<uint16_t>() + i0, h->sp_doff.as<uint64_t>() + i0, h->sp_cnt.as<uint32_t>(),
+               h->cand_off.as<uint64_t>() + i0, h->cand_rank.as<uint32_t>(), h->sh_sel.as<uint16_t>() + i0, h->sp_changed.as<uint32_t>(),
                hist_mode ? h->sp_hist.as<uint32_t>() : (uint32_t *)nullptr, hist_mode == 1 ? 1 : 0, h->sp_dirty.as<uint32_t>(), round + 1,
-               h->sp_ractive.as<uint8_t>(), use_active ? (int)(round & 0xffu) : -1);
+               h->sp_ractive.as<uint8_t>() + i0, use_active ? (int)(round & 0xffu) : -1);
 }
 
-// iterates the local reads to their fixed point from the populations in sh_base, then folds them in: sp_base2 = populations after
+// iterates the local reads to their fixed point from the populations in sh_base, block after block in input order, folding every
+// finished block into the populations the next one starts from: sp_base2 = populations after the last read
 static void sparse_local(scb_handle *h) {
     cudaStream_t st = h->st;
-    const int64_t M = h->sp_M;
     const int nb1 = h->tab.n_buckets + 1;
     h->last_rounds = 0;
     SCB_CUDA(cudaMemcpyAsync(h->sp_base2.p, h->sh_base.p, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
-    if (M == 0 || h->cur.n == 0) return;
-    const bool prof = getenv("SCB_SPARSE_PROF") != nullptr;      // per-round device time and changed decisions, to stderr
-    while (true) {
+    if (h->sp_M == 0 || h->cur.n == 0) return;
+    const bool prof = getenv("SCB_SPARSE_PROF") != nullptr;      // per-block rounds and device time, to stderr
+    uint32_t *cur = h->sh_base.as<uint32_t>(), *nxt = h->sp_base2.as<uint32_t>();     // both hold the populations before block 0 here
+    for (int blk = 0; blk < h->sp_nblk; blk++) {
+        const int64_t p0 = h->sp_blk_pair[(size_t)blk], M = h->sp_blk_pair[(size_t)blk + 1] - p0;
+        if (M == 0) continue;
+        const int64_t tiles = cdiv(M, kSpTile), t0 = h->sp_blk_tile[(size_t)blk];
+        h->sp_dirty_tiles = (uint32_t)std::min<int64_t>(tiles, 0xffffffffll);
         if (prof) SCB_CUDA(cudaEventRecord(h->ev_s0, st));
-        sparse_round(h, h->sh_base.as<uint32_t>(), 0);
-        if (prof) SCB_CUDA(cudaEventRecord(h->ev_s1, st));
-        h->last_rounds++;
-        uint32_t cc[2] = {0, 0};
-        SCB_CUDA(cudaMemcpyAsync(cc, h->sp_changed.p, 8, cudaMemcpyDeviceToHost, st));
-        SCB_CUDA(cudaStreamSynchronize(st));
-        const uint32_t chg = cc[0];
-        h->sp_dirty_tiles = cc[1];
+        int rounds = 0;
+        while (true) {
+            sparse_round(h, cur, 0, blk, rounds == 0);
+            rounds++; h->last_rounds++;
+            uint32_t cc[2] = {0, 0};
+            SCB_CUDA(cudaMemcpyAsync(cc, h->sp_changed.p, 8, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            h->sp_dirty_tiles = cc[1];
+            if (cc[0] == 0) break;
+            if (rounds >= kRdMaxRounds) throw CudaError{"resolve: round cap hit"};
+        }
+        // the last round changed nothing: its flags and tile scan describe the block's final assignment. Populations after the
+        // block = populations before it, with the buckets the block touches overwritten (each once, at its segment's last pair)
+        SpCounts c;
+        c.M = M; c.sb = h->sp_sb.as<uint32_t>() + p0; c.sval = h->sp_sval.as<uint32_t>() + p0; c.fbyte = h->sp_fbyte.as<uint8_t>() + t0 * (kSpTile / 8);
+        c.X = h->sp_X.as<uint32_t>() + t0; c.base = cur; c.cnt = nullptr; c.fold = nxt;
+        c.dirty = h->sp_dirty.as<uint32_t>(); c.round = h->sp_round; c.all = 0; c.rank_mask = (1u << h->sp_rank_bits) - 1u;
+        c.tile_clean = nullptr; c.sread = nullptr; c.ractive = nullptr; c.stamp = 0;
+        SCB_LAUNCH(sp_counts_k, (unsigned)tiles, kSpThreads, 0, st, c);
+        if (blk + 1 < h->sp_nblk) {   // ping-pong: the next block reads what this one folded
+            SCB_CUDA(cudaMemcpyAsync(cur, nxt, (size_t)nb1 * 4, cudaMemcpyDeviceToDevice, st));
+        }
         if (prof) {
             float rms = 0;
+            SCB_CUDA(cudaEventRecord(h->ev_s1, st));
+            SCB_CUDA(cudaEventSynchronize(h->ev_s1));
             SCB_CUDA(cudaEventElapsedTime(&rms, h->ev_s0, h->ev_s1));
-            std::vector<uint8_t> tc((size_t)cdiv(M, kSpTile));
-            SCB_CUDA(cudaMemcpy(tc.data(), h->sp_tile_clean.p, tc.size(), cudaMemcpyDeviceToHost));
-            size_t dirty_tiles = 0;
-            for (uint8_t v : tc) dirty_tiles += v == 0;
-            fprintf(stderr, "sparse round %3d: %8.3f ms, %10u decisions changed, %zu of %zu tiles dirty\n", h->last_rounds, rms, chg, dirty_tiles, tc.size());
+            fprintf(stderr, "sparse block %3d of %d: %9lld pairs, %3d rounds, %8.3f ms\n", blk, h->sp_nblk, (long long)M, rounds, rms);
         }
-        if (chg == 0) break;
-        if (h->last_rounds >= kRdMaxRounds) throw CudaError{"resolve: round cap hit"};
     }
-    // the last round changed nothing: its flags and tile scan describe the final assignment
-    SpCounts c;
-    c.M = M; c.sb = h->sp_sb.as<uint32_t>(); c.sval = h->sp_sval.as<uint32_t>(); c.fbyte = h->sp_fbyte.as<uint8_t>(); c.X = h->sp_X.as<uint32_t>();
-    c.base = h->sh_base.as<uint32_t>(); c.cnt = nullptr; c.fold = h->sp_base2.as<uint32_t>();
-    c.dirty = h->sp_dirty.as<uint32_t>(); c.round = h->sp_round; c.tile_clean = nullptr; c.sread = nullptr; c.ractive = nullptr; c.stamp = 0;
-    SCB_LAUNCH(sp_counts_k, (unsigned)cdiv(M, kSpTile), kSpThreads, 0, st, c);
 }
 
 // ---- dense resolve engine (resolve_dense.cuh): geometry, buffers, launches --------------------------------
@@ -926,7 +970,7 @@ static void stage_resolve(scb_handle *h) {
     h->last_rounds = 0;
     h->engine = n > 0 ? pick_engine(h, h->life_total + (uint64_t)n) : kEngSeq;
     if (h->engine == kEngSparse) {
-        sparse_setup(h);
+        sparse_setup(h, true);
         SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
         sparse_local(h);
         SCB_LAUNCH(base_to_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->sp_base2.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb);
@@ -1310,7 +1354,7 @@ static void shard_resolve_local(scb_handle *h, uint32_t *tot_dev) {
         h->engine = shard_engine(h);
         if ((h->life_total + (uint64_t)n) >= 0xffffffffull) throw CudaError{"more than 2^32-1 reads in one job: u32 resolve counters would overflow"};
         if (h->engine == kEngSparse) {
-            sparse_setup(h);
+            sparse_setup(h, true);
             SCB_LAUNCH(life_to_base_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), h->sh_base.as<uint32_t>(), nb1);
             sparse_local(h);
             SCB_LAUNCH(sub_life_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sp_base2.as<uint32_t>(), h->d_life.as<unsigned long long>(), nb1, tot_dev);
@@ -1338,9 +1382,9 @@ static void shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64
         if (h->engine == kEngSparse) {
             // one global round on the bucket-major pair lists: base = lifetime counts + the lower ranks' histograms under the
             // current assignment; the local histogram follows the decisions (rebuilt in the first round, then kept by differences)
-            if (first) sparse_setup(h);
+            if (first) sparse_setup(h, false);
             SCB_LAUNCH(add_life_k, (unsigned)cdiv(nb1, 256), 256, 0, st, h->d_life.as<unsigned long long>(), before_dev, nb1, h->sh_base.as<uint32_t>());
-            sparse_round(h, h->sh_base.as<uint32_t>(), first ? 1 : 2);
+            sparse_round(h, h->sh_base.as<uint32_t>(), first ? 1 : 2, 0, first != 0);
             SCB_LAUNCH(sp_copy_tot_k, (unsigned)cdiv(nb1 + 1, 256), 256, 0, st, h->sp_hist.as<uint32_t>(), h->sp_changed.as<uint32_t>(), nb1, tot_dev);
             h->last_rounds++;
         } else {

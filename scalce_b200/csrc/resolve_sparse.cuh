@@ -16,6 +16,11 @@
 // bucket whose flags changed in the previous round, or whose population before the local reads changed (sharded
 // rounds). In a clean bucket neither the flags nor the counts its pairs see can have changed, and the set of dirty
 // buckets roughly halves per round (measured on the CPU model: 28 %, 14 %, 7 %, ... of the pairs).
+// One GPU owning the input order walks it in BLOCKS of reads (Gauss-Seidel across blocks, Jacobi inside): the sort key is
+// (block, bucket), a block's pairs are one contiguous range of the sorted view, and a block is iterated to its fixed point from
+// the populations every earlier block left behind. A decision depends on earlier reads only, so chains of dependent decisions
+// are cut at the block boundaries: a block of ~1 M reads needs far fewer rounds than the whole flush, and its late rounds
+// touch only that block's pairs.
 // The same round serves the sharded run (one global round per call, populations of the lower ranks supplied by
 // the caller) - include/scalce_b200.h "Sharded run".
 #pragma once
@@ -27,23 +32,23 @@ namespace scb {
 constexpr int kSpThreads = 256;
 constexpr int kSpItems = 8;                       // consecutive sorted pairs per thread
 constexpr int kSpTile = kSpThreads * kSpItems;    // 2048 pairs per CTA
-constexpr uint32_t kSpRankMask = 0x00ffffffu;     // bucket rank in the low 24 bits of a sort key
 
 // ---- set-up: read-major pair arrays ----------------------------------------------------------------------------
 // doff[i] = exclusive prefix of ncand (dense numbering: the scan's candidate arrays have holes)
 __global__ void __launch_bounds__(256) sp_pairs_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
                                                   const uint32_t *__restrict__ cand_rank, const uint64_t *__restrict__ doff,
                                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ pread,
-                                                  uint16_t *__restrict__ sel) {
+                                                  uint16_t *__restrict__ sel, int64_t blk_reads, int rank_bits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint64_t blk = (uint64_t)(i / blk_reads) << rank_bits;      // input-order block of the read: the sort groups (block, bucket)
     const int nc = ncand[i];
     // start of the iteration: the first candidate. Any start converges to the same fixed point; a warm start by candidate-pair
     // populations ("the bucket most reads can choose") was measured and needed MORE rounds (36 vs 30 at 50M reads x 1M cores).
     sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;
     const uint64_t src = cand_off[i], d = doff[i];
     for (int k = 0; k < nc; k++) {
-        key[d + k] = (uint64_t)cand_rank[src + k];
+        key[d + k] = blk | (uint64_t)cand_rank[src + k];
         val[d + k] = (uint32_t)(d + k);
         pread[d + k] = (uint32_t)i;
     }
@@ -102,8 +107,10 @@ struct SpRound {
     const uint16_t *sel;
     uint8_t *fbyte;                  // [ceil(M / 8)] flags of 8 consecutive sorted pairs
     uint32_t *tail, *treset;         // [tiles]
-    const uint32_t *dirty;           // [nb1] round stamp: bucket b is dirty in round r iff dirty[b] == r (all zero before round 0)
+    const uint32_t *dirty;           // [nb1] round stamp: bucket b is dirty in round r iff dirty[b] == r
     uint32_t round;
+    uint32_t all;                    // 1: first round over these pairs, every bucket counts as dirty
+    uint32_t rank_mask;              // sb = input block << rank_bits | bucket rank
     uint8_t *tile_clean;             // [tiles] 1 = no pair of the tile belongs to a dirty bucket this round: nothing of the tile changes
     uint32_t *n_dirty_tiles;         // counter of the round
 };
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_flags_k(SpRound p) {
     for (int j = 0; j < kSpItems; j++) b[j] = (base + j < p.M) ? p.sb[base + j] : 0xffffffffu;
     uint32_t dm0 = 0;
 #pragma unroll
-    for (int j = 0; j < kSpItems; j++) dm0 |= ((base + j < p.M) && p.dirty[b[j] & kSpRankMask] == p.round) ? (1u << j) : 0u;
+    for (int j = 0; j < kSpItems; j++) dm0 |= ((base + j < p.M) && (p.all || p.dirty[b[j] & p.rank_mask] == p.round)) ? (1u << j) : 0u;
     // a tile without a pair of a dirty bucket keeps its flags, its tail and (sp_counts_k) its counts: late rounds touch few tiles
     if (!__syncthreads_or(dm0 != 0)) {
         if (threadIdx.x == 0) p.tile_clean[blockIdx.x] = 1;
@@ -188,7 +195,7 @@ struct SpCounts {
     const uint32_t *base;            // [nb1] populations before the local reads
     uint32_t *cnt;                   // [M] read-major: what pair p sees
     uint32_t *fold;                  // != null: instead of scattering counts, write base + segment total at every segment end
-    const uint32_t *dirty; uint32_t round;   // counts are only scattered for dirty buckets (see SpRound)
+    const uint32_t *dirty; uint32_t round, all, rank_mask;   // counts are only scattered for dirty buckets (see SpRound)
     const uint8_t *tile_clean;               // tiles sp_flags_k found clean are skipped
     const uint32_t *sread; uint8_t *ractive; uint8_t stamp;   // reads that receive a new count are marked for sp_decide_k
 };
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
     uint32_t b[kSpItems + 1];
 #pragma unroll
     for (int j = 0; j <= kSpItems; j++) b[j] = (base + j < p.M) ? p.sb[base + j] : 0xffffffffu;
-    const uint32_t prevkey = base > 0 && base < p.M ? p.sb[base - 1] : 0xfffffffeu;       // differs from every key (ranks < 2^24)
+    const uint32_t prevkey = base > 0 && base < p.M ? p.sb[base - 1] : 0xfffffffeu;       // differs from every key (keys < 2^31)
     const uint32_t bits = base < p.M ? (uint32_t)p.fbyte[base >> 3] : 0u;
     uint32_t ex[kSpItems];
     uint32_t run = 0, lead = 0xffu, any = 0;       // lead bit j: no segment start in [0, j]
@@ -223,10 +230,10 @@ __global__ void __launch_bounds__(kSpThreads) sp_counts_k(SpCounts p) {
 #pragma unroll
     for (int j = 0; j < kSpItems; j++) {
         if (base + j >= p.M) break;
-        const uint32_t c = p.base[b[j] & kSpRankMask] + ex[j] + (((lead >> j) & 1u) ? pre : 0u);
+        const uint32_t c = p.base[b[j] & p.rank_mask] + ex[j] + (((lead >> j) & 1u) ? pre : 0u);
         if (p.fold) {
-            if (b[j + 1] != b[j]) p.fold[b[j] & kSpRankMask] = c + ((bits >> j) & 1u);    // last pair of its bucket: every bucket at most once
-        } else if (p.dirty[b[j] & kSpRankMask] == p.round) {
+            if (b[j + 1] != b[j]) p.fold[b[j] & p.rank_mask] = c + ((bits >> j) & 1u);    // last pair of its (block, bucket) segment: every bucket at most once per range
+        } else if (p.all || p.dirty[b[j] & p.rank_mask] == p.round) {
             p.cnt[p.sval[base + j]] = c;
             if (p.ractive) p.ractive[p.sread[base + j]] = p.stamp;     // late rounds only: one more random store per pair does not pay while most tiles are dirty
         }

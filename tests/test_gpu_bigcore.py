@@ -101,6 +101,24 @@ def test_forced_identical_reads(big_engines):
     util.assert_same(o, t, r)
 
 
+def test_forced_many_input_blocks(big_engines, monkeypatch):
+    """The one-GPU sparse engine walks the input in blocks of reads (resolve_sparse.cuh); blocks of 1024 reads here, so that the
+    standard shapes cross dozens of block boundaries, including blocks without a candidate and a ragged last block."""
+    monkeypatch.setenv("SCB_SPARSE_BLOCK", "1024")
+    o, t, r = _case(20000, 100, seed=351)
+    assert t.resolve_engine == 1 and t.resolve_rounds > 19          # at least one round per block
+    _case(12000, 100, seed=352, paired=True, L2=75, bucket_set_bytes=1 << 20)
+    _case(20500, 36, seed=353, lower=0.05)
+    _case(9000, 100, seed=354, spec=[(8, 100), (14, 50), (20, 30), (32, 10)])
+    _case(3000, 24, seed=355, spec=[(12, 3)])                     # almost no read has a candidate: empty blocks
+    for n in (1023, 1024, 1025, 2049):
+        _case(n, 50, seed=360 + n)
+    cores, b, q1, q2, _ = util.make_case(12000, 100, seed=356)
+    o = util.run_oracle(cores, b, q1, q2, splits=[5000])
+    t, r = util.run_cuda(cores, b, q1, q2, splits=[100, 5000])
+    util.assert_same(o, t, r)
+
+
 def test_sharded_sparse_engine(big_engines):
     for world, kw in ((2, dict(n=30000, L=100, seed=321)), (4, dict(n=40000, L=100, seed=322, bucket_set_bytes=1 << 20)),
                       (3, dict(n=20000, L=100, seed=323, paired=True, L2=75, bounds=[0, 1000, 13000, 20000]))):
