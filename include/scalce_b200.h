@@ -41,6 +41,9 @@ extern "C" {
 /* id/core written for the "no core" (root) bucket: MAXBIN-1, const.h:94, reads.cpp:161-164 */
 #define SCB_ROOT_ID ((1 << 30) - 1)
 
+/* longest read: what the reference's line buffer holds (fgets into MAXLINE = 2500 bytes: text + newline + NUL, const.h:87) */
+#define SCB_MAX_READ_LENGTH 2498
+
 /* stream numbering = temp-file numbering t_%03d_<k>.tmp (compress.cpp:527-533, reads.cpp:91-180) */
 enum { SCB_S_NAMES = 0, SCB_S_READS = 1, SCB_S_QUALS = 2, SCB_S_META = 3, SCB_S_READS2 = 4, SCB_S_QUALS2 = 5, SCB_N_STREAMS = 6 };
 
@@ -49,7 +52,7 @@ typedef struct scb_handle scb_handle;
 /* Replaces the globals the path reads: read_length[2], _use_names, _use_second_file,
  * _compress_qualities, _max_bucket_set_size (const.h:100-119, main.cpp:62-80). */
 typedef struct scb_config {
-    int32_t read_length[2];    /* L of mate 1, mate 2 (0 when single-end); fixed-length build only */
+    int32_t read_length[2];    /* L of mate 1, mate 2 (0 when single-end), 1..SCB_MAX_READ_LENGTH; fixed-length build only */
     int32_t use_names;         /* 1: names are payload (stream 0); 0: -n mode, one 0 byte per read in size accounting */
     int32_t paired;            /* _use_second_file */
     int32_t use_quals;         /* _compress_qualities (0 with -Q / -f) */

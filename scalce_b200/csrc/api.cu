@@ -100,12 +100,6 @@ struct DevBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
-// kernel variants that became the default after an A/B run keep their switch: unset = on, "0" = the previous kernel
-static bool env_on(const char *name, bool dflt) {
-    const char *e = getenv(name);
-    return e && *e ? atoi(e) != 0 : dflt;
-}
-
 static int ceil_log2(uint64_t x) {  // bits needed to represent values in [0, x)
     int b = 0;
     while (b < 64 && (1ull << b) < x) b++;
@@ -197,8 +191,9 @@ struct scb_handle {
     int64_t sp_M = 0;
     DevBuf sp_doff, sp_sb, sp_sread, sp_sk, sp_sval, sp_cnt, sp_fbyte, sp_tail, sp_treset, sp_X, sp_hist, sp_changed, sp_base2, sp_dirty, sp_base_prev, sp_tile_clean, sp_ractive;
     uint32_t sp_dirty_tiles = 0;
-    int sp_rank_bits = 24; int64_t sp_blk_reads = 0; int sp_nblk = 1;   // (block, bucket) keys of the sorted view
-    std::vector<int64_t> sp_blk_pair, sp_blk_tile;                         // [nblk + 1] first pair / first tile slot of every block
+    int sp_rank_bits = 24; int sp_nblk = 1;   // (block, bucket) keys of the sorted view
+    std::vector<int64_t> sp_blk_first, sp_blk_pair, sp_blk_tile;           // [nblk + 1] first read / first pair / first tile slot of every block
+    DevBuf sp_dblk_first;
     uint32_t sp_round = 0;      // rounds of the sparse engine since its set-up (the stamps in sp_dirty refer to it)
     DevBuf sh_S0, sh_H0, sh_frused, sh_frbuf, sh_fridx, sh_incr_stat;   // incremental resolve rounds (resolve_dense.cuh "fragile reads")
     DevBuf sh_sizes;           // u64 [n+1] exclusive prefix of rd.sz + 40 over the local shard
@@ -227,7 +222,8 @@ static void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
 static int create_common(const std::vector<std::string> &cores, const scb_config *cfg, scb_handle **out) {
     if (!cfg || !out) { g_last_error = "null argument"; return SCB_EINVAL; }
     int L1 = cfg->read_length[0], L2 = cfg->read_length[1];
-    if (L1 <= 0 || L1 > 2047 || (cfg->paired && (L2 <= 0 || L2 > 2047))) { g_last_error = "read length out of range (1..2047)"; return SCB_EINVAL; }
+    // 2498 = the longest read the reference's line buffer holds (fgets into MAXLINE = 2500 bytes: text + newline + NUL, const.h:87)
+    if (L1 <= 0 || L1 > SCB_MAX_READ_LENGTH || (cfg->paired && (L2 <= 0 || L2 > SCB_MAX_READ_LENGTH))) { g_last_error = "read length out of range (1..2498)"; return SCB_EINVAL; }
     if (cfg->bucket_set_bytes == 0) { g_last_error = "bucket_set_bytes must be > 0"; return SCB_EINVAL; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
@@ -525,6 +521,7 @@ static void flush_begin(scb_handle *h, double extra_factor) {
     const Pending &c = h->cur;
     const int64_t n = c.n;
     h->n_last = n;
+    if (c.name_bytes >= (1ll << 36)) throw CudaError{"more than 64 GiB of names in one flush (the per-read metadata word keeps 36 bits of name offset)"};
 }
 
 // 1. scan: max level + ordered distinct candidates per read (+ the 2-bit packed copy of the reads)
@@ -681,23 +678,30 @@ static void sparse_setup(scb_handle *h, bool blocked) {
     if (M >= 0xffffffffull) throw CudaError{"more than 2^32-1 candidate pairs in one flush: flush fewer reads at a time"};
     h->sp_M = (int64_t)M;
     const int64_t M1 = std::max<int64_t>((int64_t)M, 1);
-    // input-order blocks (one GPU owning the order): ~1 M reads each. The sharded rounds use one block.
+    // input-order blocks (one GPU owning the order). The first blocks see (nearly) empty populations, where almost every
+    // decision is a tie broken by the reads just before it and a block needs many rounds, so they start small and double up
+    // to the steady size (measured at 50M reads x 1M cores: 19 rounds for a first block of 4.5M reads, 6-7 for the later
+    // ones). The sharded rounds use one block.
     h->sp_rank_bits = std::max(1, ceil_log2((uint64_t)nb1));
-    int64_t want = 1 << 20;
-    if (const char *e = getenv("SCB_SPARSE_BLOCK")) want = std::max<int64_t>(1024, atoll(e));      // reads per block (experiments)
-    h->sp_nblk = blocked ? (int)std::min<int64_t>(4096, std::max<int64_t>(1, n / want)) : 1;
-    h->sp_blk_reads = std::max<int64_t>(1, cdiv(std::max<int64_t>(n, 1), h->sp_nblk));
-    h->sp_nblk = (int)cdiv(std::max<int64_t>(n, 1), h->sp_blk_reads);
-    const int blk_bits = ceil_log2((uint64_t)h->sp_nblk);
-    if (h->sp_rank_bits + blk_bits > 31) { h->sp_nblk = 1; h->sp_blk_reads = std::max<int64_t>(n, 1); }
+    int64_t blk_max = 4 << 20, blk0 = 128 << 10;
+    if (const char *e = getenv("SCB_SPARSE_BLOCK")) blk_max = std::max<int64_t>(256, atoll(e));      // reads per block (tests, experiments)
+    if (const char *e = getenv("SCB_SPARSE_BLOCK0")) blk0 = std::max<int64_t>(256, atoll(e));
+    blk0 = std::min(blk0, blk_max);
+    std::vector<int64_t> first{0};
+    if (blocked) {
+        const int max_blocks = 1 << std::min(12, 31 - h->sp_rank_bits);      // block and bucket share a 31-bit key
+        for (int64_t sz = blk0, at = sz; at < n && (int)first.size() < max_blocks; sz = std::min(sz * 2, blk_max), at += sz) first.push_back(at);
+    }
+    h->sp_nblk = (int)first.size();
+    first.push_back(std::max<int64_t>(n, 0));
+    h->sp_blk_first = first;
     h->sp_blk_pair.assign((size_t)h->sp_nblk + 1, 0);
+    h->sp_dblk_first.alloc(first.size() * 8, st);
     {
-        std::vector<int64_t> idx((size_t)h->sp_nblk + 1);
-        for (int k = 0; k <= h->sp_nblk; k++) idx[(size_t)k] = std::min<int64_t>(n, (int64_t)k * h->sp_blk_reads);
-        DevBuf didx(idx.size() * 8, st), dout(idx.size() * 8, st);
-        SCB_CUDA(cudaMemcpyAsync(didx.p, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, st));
-        SCB_LAUNCH(gather_u64_k, (unsigned)cdiv((int64_t)idx.size(), 64), 64, 0, st, h->sp_doff.as<uint64_t>(), didx.as<int64_t>(), (int)idx.size(), dout.as<int64_t>());
-        SCB_CUDA(cudaMemcpyAsync(h->sp_blk_pair.data(), dout.p, idx.size() * 8, cudaMemcpyDeviceToHost, st));
+        DevBuf dout(first.size() * 8, st);
+        SCB_CUDA(cudaMemcpyAsync(h->sp_dblk_first.p, h->sp_blk_first.data(), first.size() * 8, cudaMemcpyHostToDevice, st));   // sp_blk_first outlives the copy
+        SCB_LAUNCH(gather_u64_k, (unsigned)cdiv((int64_t)first.size(), 64), 64, 0, st, h->sp_doff.as<uint64_t>(), h->sp_dblk_first.as<int64_t>(), (int)first.size(), dout.as<int64_t>());
+        SCB_CUDA(cudaMemcpyAsync(h->sp_blk_pair.data(), dout.p, first.size() * 8, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));
     }
     // per-block tiles: every block's tile-indexed arrays (flag bytes, tails, clean marks) start at their own slot
@@ -716,19 +720,22 @@ static void sparse_setup(scb_handle *h, bool blocked) {
     // temporaries of the sort: carved after the mark and handed back when the sorted view exists
     const Arena::Mark mk = h->arena.mark();
     {
-        DevBuf k0((size_t)M1 * 8, st), k1((size_t)M1 * 8, st), v0((size_t)M1 * 4, st), v1((size_t)M1 * 4, st), pread((size_t)M1 * 4, st);
+        const int key_bits = h->sp_rank_bits + ceil_log2((uint64_t)h->sp_nblk);
+        const int passes = M > 1 ? (key_bits + 7) / 8 : 0;      // radix_sort_pairs leaves 0 or 1 pairs where they are
+        DevBuf k1((size_t)M1 * 4, st), v1((size_t)M1 * 4, st), pread((size_t)M1 * 4, st);
         DevBuf hist((size_t)SortWs::hist_elems(M1) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(M1)) * 4, st);
+        // the ping-pong starts on the side that makes the last pass land in sp_sb / sp_sval
+        uint32_t *ka = (passes & 1) ? k1.as<uint32_t>() : h->sp_sb.as<uint32_t>(), *kb = (passes & 1) ? h->sp_sb.as<uint32_t>() : k1.as<uint32_t>();
+        uint32_t *va = (passes & 1) ? v1.as<uint32_t>() : h->sp_sval.as<uint32_t>(), *vb = (passes & 1) ? h->sp_sval.as<uint32_t>() : v1.as<uint32_t>();
         if (n > 0)
             SCB_LAUNCH(sp_pairs_k, (unsigned)cdiv(n, 256), 256, 0, st, n, h->ncand.as<uint16_t>(), h->cand_off.as<uint64_t>(), h->cand_rank.as<uint32_t>(),
-                       h->sp_doff.as<uint64_t>(), k0.as<uint64_t>(), v0.as<uint32_t>(), pread.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_blk_reads, h->sp_rank_bits);
+                       h->sp_doff.as<uint64_t>(), ka, va, pread.as<uint32_t>(), h->sh_sel.as<uint16_t>(), h->sp_dblk_first.as<int64_t>(), h->sp_nblk, h->sp_rank_bits);
         if (M > 0) {
             SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
-            uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
-            uint32_t *va = v0.as<uint32_t>(), *vb = v1.as<uint32_t>();
-            radix_sort_pairs(&ka, &va, &kb, &vb, (int64_t)M, 0, h->sp_rank_bits + ceil_log2((uint64_t)h->sp_nblk), ws, st);
-            SCB_LAUNCH(sp_post_k, (unsigned)cdiv((int64_t)M, 256), 256, 0, st, (int64_t)M, ka, va, pread.as<uint32_t>(), h->sp_doff.as<uint64_t>(),
-                       h->sp_sb.as<uint32_t>(), h->sp_sread.as<uint32_t>(), h->sp_sk.as<uint16_t>());
-            SCB_CUDA(cudaMemcpyAsync(h->sp_sval.p, va, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+            radix_sort_pairs(&ka, &va, &kb, &vb, (int64_t)M, 0, key_bits, ws, st);
+            if (ka != h->sp_sb.as<uint32_t>() || va != h->sp_sval.as<uint32_t>()) throw CudaError{"sparse set-up: sorted view landed in the wrong buffer"};
+            SCB_LAUNCH(sp_post_k, (unsigned)cdiv((int64_t)M, 256), 256, 0, st, (int64_t)M, va, pread.as<uint32_t>(), h->sp_doff.as<uint64_t>(),
+                       h->sp_sread.as<uint32_t>(), h->sp_sk.as<uint16_t>());
         }
     }
     if (g_arena) h->arena.rewind(mk);   // stream order keeps later users of this space behind the kernels above
@@ -745,7 +752,7 @@ static void sparse_round(scb_handle *h, const uint32_t *base, int hist_mode, int
     SCB_CUDA(cudaMemsetAsync(h->sp_changed.p, 0, 16, st));
     if (h->sp_M == 0 || n == 0) { if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st)); return; }
     const int64_t p0 = h->sp_blk_pair[(size_t)blk], M = h->sp_blk_pair[(size_t)blk + 1] - p0;
-    const int64_t i0 = std::min<int64_t>(n, (int64_t)blk * h->sp_blk_reads), nr = std::min<int64_t>(n, (int64_t)(blk + 1) * h->sp_blk_reads) - i0;
+    const int64_t i0 = h->sp_blk_first[(size_t)blk], nr = h->sp_blk_first[(size_t)blk + 1] - i0;
     const int64_t t0 = h->sp_blk_tile[(size_t)blk];
     const uint32_t round = h->sp_round++;
     if (hist_mode == 1) SCB_CUDA(cudaMemsetAsync(h->sp_hist.p, 0, (size_t)(nb1 + 1) * 4, st));
@@ -1323,7 +1330,7 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
     SCB_CUDA(cudaMemcpyAsync(o, dout.p, 16, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     if ((int64_t)o[0] > cap) throw CudaError{"internal: chunk capacity exceeded"};
-    if ((uint64_t)chunk_in + o[0] >= kAuxMaxChunks) throw CudaError{"too many flush chunks for the sharded run (>= 2^21)"};
+    if ((uint64_t)chunk_in + o[0] >= kAuxMaxChunks) throw CudaError{"too many flush chunks for the sharded run (>= 2^20)"};
     h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
     if (n > 0) SCB_LAUNCH(chunk_ids_global_k, (unsigned)cdiv(n, 256), 256, 0, st, bounds.as<uint32_t>(), (int)o[0], (uint32_t)chunk_in, n, h->chunk.as<uint32_t>());
     tm.stop();

@@ -327,14 +327,15 @@ __global__ void gather_rows_small_k(const uint8_t *__restrict__ src, uint8_t *__
 
 // ---- per-read metadata word ---------------------------------------------------------------------------
 // Everything small the output side needs about a read, in one u64 so that output order costs ONE random
-// 8-byte gather per read: bits 0-36 name offset, 37-44 name length, 45-52 core level, 53-63 end marker.
+// 8-byte gather per read: bits 0-35 name offset (64 GiB of names per flush), 36-43 name length, 44-51 core level,
+// 52-63 end marker (reads up to the reference's line cap, const.h:87).
 __host__ __device__ __forceinline__ uint64_t meta_pack(uint64_t name_off, uint32_t namelen, uint32_t lvl, uint32_t end) {
-    return (name_off & ((1ull << 37) - 1)) | ((uint64_t)(namelen & 0xffu) << 37) | ((uint64_t)(lvl & 0xffu) << 45) | ((uint64_t)(end & 0x7ffu) << 53);
+    return (name_off & ((1ull << 36) - 1)) | ((uint64_t)(namelen & 0xffu) << 36) | ((uint64_t)(lvl & 0xffu) << 44) | ((uint64_t)(end & 0xfffu) << 52);
 }
-__device__ __forceinline__ int64_t meta_name_off(uint64_t m) { return (int64_t)(m & ((1ull << 37) - 1)); }
-__device__ __forceinline__ int meta_namelen(uint64_t m) { return (int)((m >> 37) & 0xffu); }
-__device__ __forceinline__ int meta_lvl(uint64_t m) { return (int)((m >> 45) & 0xffu); }
-__device__ __forceinline__ int meta_end(uint64_t m) { return (int)(m >> 53); }
+__device__ __forceinline__ int64_t meta_name_off(uint64_t m) { return (int64_t)(m & ((1ull << 36) - 1)); }
+__device__ __forceinline__ int meta_namelen(uint64_t m) { return (int)((m >> 36) & 0xffu); }
+__device__ __forceinline__ int meta_lvl(uint64_t m) { return (int)((m >> 44) & 0xffu); }
+__device__ __forceinline__ int meta_end(uint64_t m) { return (int)(m >> 52); }
 
 __global__ void build_meta_k(int64_t n, const int64_t *__restrict__ name_off, const uint8_t *__restrict__ lvl,
                              const uint16_t *__restrict__ endv, uint64_t *__restrict__ meta_in) {

@@ -112,7 +112,7 @@ struct LoadAs {
 };
 
 // =================================================================================================
-// stable LSD radix sort of (u64 key, u32 val), 8-bit digits over key bits [bit_lo, bit_hi)
+// stable LSD radix sort of (u64 or u32 key, u32 val), 8-bit digits over key bits [bit_lo, bit_hi)
 //   pass = digit histogram per tile -> exclusive scan (digit-major) -> stable scatter
 // Each warp owns a contiguous run of kSortItems*32 elements and ranks them 32 at a time with
 // match.any, so order inside a digit is input order (stability).
@@ -125,7 +125,8 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = SCB_SORT_ITEMS;   // tile = 3072 elements: 36 KB of staging + 10 KB of counters stays under 48 KB static smem
 constexpr int kSortTile = kSortThreads * kSortItems;
 
-__global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys, int64_t n, int shift, uint32_t mask,
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads) sort_hist_k(const K *keys, int64_t n, int shift, uint32_t mask,
                                                             uint32_t *hist /*[256][tiles]*/, int64_t tiles) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
@@ -145,26 +146,27 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_k(const uint64_t *keys
 #ifndef SCB_SORT_MINBLOCKS
 #define SCB_SORT_MINBLOCKS 4   // 64 registers (8 bytes of spill), 4 CTAs per SM: sort 3.94 -> 3.44 ms at 50M x 150 (3 CTAs at 80 registers before; 8-item tiles with 4 or 5 CTAs: 3.72 / 3.64)
 #endif
-__global__ void __launch_bounds__(kSortThreads, SCB_SORT_MINBLOCKS) sort_scatter_k(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                               uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads, SCB_SORT_MINBLOCKS) sort_scatter_k(const K *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                               K *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
                                                                int shift, uint32_t mask, const uint32_t *__restrict__ hist_scanned, int64_t tiles) {
     __shared__ uint32_t cnt[kSortWarps][256];
     __shared__ uint32_t gbase[256];     // global start of this tile's run of digit d, minus its start inside the tile
     __shared__ uint32_t tbase[256];     // start of digit d inside the digit-ordered tile
     __shared__ uint32_t sc[kSortThreads / 32 + 1];
-    __shared__ uint64_t skey[kSortTile];
+    __shared__ K skey[kSortTile];
     __shared__ uint32_t sval[kSortTile];
     const int w = threadIdx.x >> 5, l = lane_id();
     for (int d = l; d < 256; d += 32) cnt[w][d] = 0;
     __syncwarp();
     const int64_t tbeg = (int64_t)blockIdx.x * kSortTile;
     const int64_t wbase = tbeg + (int64_t)w * (kSortItems * 32);
-    uint64_t key[kSortItems];
+    K key[kSortItems];
     uint32_t rank[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
         int64_t i = wbase + k * 32 + l;
-        key[k] = i < n ? keys[i] : ~0ull;
+        key[k] = i < n ? keys[i] : (K)~(K)0;
     }
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kSortThreads, SCB_SORT_MINBLOCKS) sort_scatter
     const int64_t rem = n - tbeg;
     const int cntTile = (int)(rem < (int64_t)kSortTile ? rem : (int64_t)kSortTile);
     for (int t = threadIdx.x; t < cntTile; t += kSortThreads) {
-        uint64_t kk = skey[t];
+        const K kk = skey[t];
         uint32_t d = (uint32_t)(kk >> shift) & mask;
         uint32_t p = gbase[d] + (uint32_t)t;
         keys_out[p] = kk;
@@ -226,18 +228,19 @@ struct SortWs {
 
 // Sorts in place logically: on return *keys / *vals point at the buffer holding the result
 // (ping-pong with *keys_alt / *vals_alt).
-inline void radix_sort_pairs(uint64_t **keys, uint32_t **vals, uint64_t **keys_alt, uint32_t **vals_alt, int64_t n,
+template <typename K>
+inline void radix_sort_pairs(K **keys, uint32_t **vals, K **keys_alt, uint32_t **vals_alt, int64_t n,
                              int bit_lo, int bit_hi, const SortWs &ws, cudaStream_t st) {
     if (n <= 1) return;
     int64_t tiles = cdiv(n, kSortTile);
     for (int lo = bit_lo; lo < bit_hi; lo += 8) {
         int bits = bit_hi - lo < 8 ? bit_hi - lo : 8;
         uint32_t mask = (1u << bits) - 1u;
-        SCB_LAUNCH(sort_hist_k, (unsigned)tiles, kSortThreads, 0, st, *keys, n, lo, mask, ws.hist, tiles);
+        SCB_LAUNCH(sort_hist_k<K>, (unsigned)tiles, kSortThreads, 0, st, *keys, n, lo, mask, ws.hist, tiles);
         exclusive_scan<uint32_t>(LoadAs<uint32_t, uint32_t>{ws.hist}, 256 * tiles, ws.hist, (uint32_t *)nullptr, ws.tile_ws, st);
-        SCB_LAUNCH(sort_scatter_k, (unsigned)tiles, kSortThreads, 0, st, *keys, *vals, *keys_alt, *vals_alt, n, lo, mask,
+        SCB_LAUNCH(sort_scatter_k<K>, (unsigned)tiles, kSortThreads, 0, st, *keys, *vals, *keys_alt, *vals_alt, n, lo, mask,
                    ws.hist, tiles);
-        uint64_t *tk = *keys; *keys = *keys_alt; *keys_alt = tk;
+        K *tk = *keys; *keys = *keys_alt; *keys_alt = tk;
         uint32_t *tv = *vals; *vals = *vals_alt; *vals_alt = tv;
     }
 }

@@ -37,31 +37,32 @@ constexpr int kSpTile = kSpThreads * kSpItems;    // 2048 pairs per CTA
 // doff[i] = exclusive prefix of ncand (dense numbering: the scan's candidate arrays have holes)
 __global__ void __launch_bounds__(256) sp_pairs_k(int64_t n, const uint16_t *__restrict__ ncand, const uint64_t *__restrict__ cand_off,
                                                   const uint32_t *__restrict__ cand_rank, const uint64_t *__restrict__ doff,
-                                                  uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ pread,
-                                                  uint16_t *__restrict__ sel, int64_t blk_reads, int rank_bits) {
+                                                  uint32_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ pread,
+                                                  uint16_t *__restrict__ sel, const int64_t *__restrict__ blk_first, int nblk, int rank_bits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t blk = (uint64_t)(i / blk_reads) << rank_bits;      // input-order block of the read: the sort groups (block, bucket)
+    int lo = 0, hi = nblk - 1;                                         // last block whose first read is <= i
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_first[mid] <= i) lo = mid; else hi = mid - 1; }
+    const uint32_t blk = (uint32_t)lo << rank_bits;                    // input-order block of the read: the sort groups (block, bucket)
     const int nc = ncand[i];
     // start of the iteration: the first candidate. Any start converges to the same fixed point; a warm start by candidate-pair
     // populations ("the bucket most reads can choose") was measured and needed MORE rounds (36 vs 30 at 50M reads x 1M cores).
     sel[i] = nc > 0 ? (uint16_t)0 : (uint16_t)0xffffu;
     const uint64_t src = cand_off[i], d = doff[i];
     for (int k = 0; k < nc; k++) {
-        key[d + k] = blk | (uint64_t)cand_rank[src + k];
+        key[d + k] = blk | cand_rank[src + k];
         val[d + k] = (uint32_t)(d + k);
         pread[d + k] = (uint32_t)i;
     }
 }
 
-// sorted view: read and candidate slot of the pair at sorted position s, bucket as u32
-__global__ void __launch_bounds__(256) sp_post_k(int64_t M, const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
+// sorted view: read and candidate slot of the pair at sorted position s (the sorted keys are sb, the sorted values sval)
+__global__ void __launch_bounds__(256) sp_post_k(int64_t M, const uint32_t *__restrict__ sval,
                                                  const uint32_t *__restrict__ pread, const uint64_t *__restrict__ doff,
-                                                 uint32_t *__restrict__ sb, uint32_t *__restrict__ sread, uint16_t *__restrict__ sk) {
+                                                 uint32_t *__restrict__ sread, uint16_t *__restrict__ sk) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= M) return;
     const uint32_t p = sval[s], i = pread[p];
-    sb[s] = (uint32_t)skey[s];
     sread[s] = i;
     sk[s] = (uint16_t)((uint64_t)p - doff[i]);
 }

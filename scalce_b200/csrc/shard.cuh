@@ -15,16 +15,16 @@
 
 namespace scb {
 
-// ---- aux word: bits 0-23 bucket rank, 24-34 end marker, 35-42 name length, 43-63 flush chunk ------------
+// ---- aux word: bits 0-23 bucket rank, 24-35 end marker, 36-43 name length, 44-63 flush chunk ------------
 constexpr uint32_t kAuxMaxBuckets = 1u << 24;
-constexpr uint32_t kAuxMaxChunks = 1u << 21;
+constexpr uint32_t kAuxMaxChunks = 1u << 20;
 __host__ __device__ __forceinline__ uint64_t aux_pack(uint32_t asg, uint32_t end, uint32_t namelen, uint32_t chunk) {
-    return (uint64_t)(asg & 0xffffffu) | ((uint64_t)(end & 0x7ffu) << 24) | ((uint64_t)(namelen & 0xffu) << 35) | ((uint64_t)(chunk & 0x1fffffu) << 43);
+    return (uint64_t)(asg & 0xffffffu) | ((uint64_t)(end & 0xfffu) << 24) | ((uint64_t)(namelen & 0xffu) << 36) | ((uint64_t)(chunk & 0xfffffu) << 44);
 }
 __host__ __device__ __forceinline__ uint32_t aux_asg(uint64_t a) { return (uint32_t)(a & 0xffffffu); }
-__host__ __device__ __forceinline__ uint32_t aux_end(uint64_t a) { return (uint32_t)((a >> 24) & 0x7ffu); }
-__host__ __device__ __forceinline__ uint32_t aux_namelen(uint64_t a) { return (uint32_t)((a >> 35) & 0xffu); }
-__host__ __device__ __forceinline__ uint32_t aux_chunk(uint64_t a) { return (uint32_t)(a >> 43); }
+__host__ __device__ __forceinline__ uint32_t aux_end(uint64_t a) { return (uint32_t)((a >> 24) & 0xfffu); }
+__host__ __device__ __forceinline__ uint32_t aux_namelen(uint64_t a) { return (uint32_t)((a >> 36) & 0xffu); }
+__host__ __device__ __forceinline__ uint32_t aux_chunk(uint64_t a) { return (uint32_t)(a >> 44); }
 
 // ---- flush chunks along the GLOBAL order ---------------------------------------------------------------
 // S[0..n] = exclusive prefix of rd.sz + 40 over the local shard. The running sum enters the shard at

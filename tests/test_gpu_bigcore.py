@@ -113,6 +113,9 @@ def test_forced_many_input_blocks(big_engines, monkeypatch):
     _case(3000, 24, seed=355, spec=[(12, 3)])                     # almost no read has a candidate: empty blocks
     for n in (1023, 1024, 1025, 2049):
         _case(n, 50, seed=360 + n)
+    monkeypatch.setenv("SCB_SPARSE_BLOCK0", "256")                 # growing blocks: 256, 512, 1024, 2048, 2048, ...
+    monkeypatch.setenv("SCB_SPARSE_BLOCK", "2048")
+    _case(20000, 100, seed=357)
     cores, b, q1, q2, _ = util.make_case(12000, 100, seed=356)
     o = util.run_oracle(cores, b, q1, q2, splits=[5000])
     t, r = util.run_cuda(cores, b, q1, q2, splits=[100, 5000])

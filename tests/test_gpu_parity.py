@@ -46,6 +46,18 @@ def test_long_reads_two_byte_end():
     _case(5000, 300, seed=6, bucket_set_bytes=1 << 20)
 
 
+def test_reads_at_the_reference_line_cap():
+    """2498 bases = the longest read the reference's line buffer holds (const.h:87); the oracle is pinned against the reference
+    CLI at this length (test_oracle_golden.py). End markers up to 2498 need 12 bits in the per-read metadata words."""
+    _case(600, 2498, seed=401, plant=0.9, bucket_set_bytes=1 << 20)
+    _case(500, 2047, seed=402)
+    _case(400, 2498, seed=403, paired=True, L2=2498, bucket_set_bytes=1 << 20)
+    _case(700, 1000, seed=404, use_names=False)
+    from scalce_b200.binding import BoostTransform, ScbError
+    with pytest.raises(ScbError):
+        BoostTransform(util.make_cores(1, util.DEFAULT_SPEC), 2499, 0)
+
+
 def test_short_reads_lowercase():
     _case(20000, 36, seed=7, lower=0.05)
 

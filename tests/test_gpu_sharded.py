@@ -158,6 +158,7 @@ def test_cpp_orchestrator_shapes():
     _case_cpp(40000, 36, 8, seed=55, use_names=False)
     _case_cpp(9000, 64, 4, seed=56, bounds=[0, 0, 5000, 5000, 9000])
     _case_cpp(6000, 300, 2, seed=57, use_quals=False, bucket_set_bytes=1 << 20)
+    _case_cpp(900, 2498, 3, seed=58, bucket_set_bytes=1 << 20, plant=0.9)      # the reference's line cap: 12-bit end markers in the aux word
 
 
 def test_cpp_orchestrator_sparse_engine(monkeypatch):

@@ -76,20 +76,22 @@ def test_oracle_matches_reference_cli(path, oracle_lib):
         assert o.n_chunks > 1   # the multi-chunk merge path (compress.cpp:68-198) is what these fixtures pin
 
 
-def test_oracle_against_live_reference_cli(tmp_path, oracle_lib):
-    """When oracle/_ref/scalce exists (build container), run it now on a fresh seed."""
+@pytest.mark.parametrize("n,L", [(3000, 80), (300, 2047), (300, 2498)])
+def test_oracle_against_live_reference_cli(tmp_path, oracle_lib, n, L):
+    """When oracle/_ref/scalce exists (build container), run it now on a fresh seed. 2498 bases is the longest read the
+    reference's line buffer holds (fgets into MAXLINE = 2500 bytes, const.h:87): the 2-byte end marker at its largest."""
     if not os.path.exists(orc.REF_CLI):
         pytest.skip("reference CLI not built here")
     from oracle.gen_cores import write_text
     spec = [(8, 128), (9, 64), (11, 32)]
     cores = make_cores(911, spec)
-    b = synth.make_batch(3000, 80, seed=911, lower_frac=0.02)
+    b = synth.make_batch(n, L, seed=911, lower_frac=0.02)
     synth.plant_cores(b, cores, seed=912, frac=0.5)
     d = str(tmp_path)
     write_text(d + "/cores.txt", cores)
     synth.write_fastq(b, d + "/in_1.fastq")
     orc.run_reference_cli(d + "/in_1.fastq", d + "/ref", d + "/cores.txt", tmpdir=d + "/tmp")
-    meta = dict(L=80, L2=0, paired=False, use_names=True, bucket="4G")
+    meta = dict(L=L, L2=0, paired=False, use_names=True, bucket="4G")
     _, files = oracle_files(cores, b, meta)
     for ext in "nrq":
         assert files["1" + ext] == open(f"{d}/ref_1.scalce{ext}", "rb").read()
