@@ -418,6 +418,39 @@ def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
     return out
 
 
+def bind_host_to_gpu(local):
+    """N > 1: run this rank's host threads on the CPUs next to its GPU (NVML's ideal CPU affinity), before any pinned buffer
+    exists, so that first-touch places the pinned pages on the GPU's NUMA node: eight ranks copying 26 GB per step through one
+    socket's memory controllers and the inter-socket link is what the end-to-end arm measured in round 1 (H2D 22 GB/s and D2H
+    11 GB/s per GPU instead of 55). Returns a description for the JSON line; never fails the run. SCB_BENCH_BIND=0 disables."""
+    if os.environ.get("SCB_BENCH_BIND", "1") == "0":
+        return {"bound": False, "why": "SCB_BENCH_BIND=0"}
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = ideal & allowed
+        node = None
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:  # noqa: BLE001  (older NVML)
+            pass
+        if not target:
+            return {"bound": False, "why": "NVML's ideal CPUs are outside this process's allowed set", "ideal_cpus": len(ideal), "allowed_cpus": len(allowed)}
+        if target != allowed:
+            os.sched_setaffinity(0, target)
+        return {"bound": target != allowed, "cpus": len(target), "allowed_cpus": len(allowed), "numa_node": node,
+                "first_cpu": min(target), "last_cpu": max(target)}
+    except Exception as ex:  # noqa: BLE001
+        return {"bound": False, "why": f"{type(ex).__name__}: {ex}"[:160]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -498,6 +531,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    # N = 1 keeps the whole host (the CPU baseline leg uses every core, and one GPU's copies already run at the PCIe rate)
+    host_binding = bind_host_to_gpu(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -661,6 +696,8 @@ def main():
                    "ms_submit_flush_copyout": [float(np.median([p[i] for p in e_parts])) for i in range(3)],
                    "note": "pinned host buffers -> scb_submit (H2D) -> scb_flush -> scb_copy_stream of every stream (D2H); one handle" +
                            (" and one sharded transform (receive arrays, IPC mappings)" if world > 1 else "") + " reused across steps"}
+            if host_binding is not None:
+                e2e["host_binding_rank0"] = host_binding
             tr.close()
             tr = None
             if a.e2e_depth > 1 and world == 1:

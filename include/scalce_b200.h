@@ -194,7 +194,7 @@ int scb_resolve_engine(const scb_handle *h);
 
 /* Device arrays of one side of the exchange, destination-major (send) or source-major (receive); rows keep
  * input order inside a destination/source. aux: one u64 per read (bucket rank | end << 24 | name length
- * << 35 | flush chunk << 43); packed: 2-bit rows of packed_row_bytes; names: name bytes without length
+ * << 36 | flush chunk << 44); packed: 2-bit rows of packed_row_bytes; names: name bytes without length
  * bytes. cnt_* are host arrays [n_ranks] owned by the handle (send side only). */
 typedef struct scb_shard_xfer {
     int64_t n;

@@ -501,7 +501,6 @@ struct ArenaScope { ArenaScope(Arena *a) { g_arena = a; } ~ArenaScope() { g_aren
 
 // sizes the flush slab and concatenates the pending batches into h->cur (call with the arena scope open)
 static void flush_begin(scb_handle *h, double extra_factor) {
-    cudaStream_t st = h->st;
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
     {   // size the slab for this flush before anything is carved from it

@@ -5,8 +5,8 @@
 // Persistent kernel, one CTA per SM; every WARP runs its own pipeline over tiles of 32 reads and never
 // waits for another warp (no block barriers after the table is loaded), so the stalls of one warp's phase
 // are covered by the other warps' phases. Per warp tile:
-//   A  pack   the tile's 32 ASCII rows arrive by 16-byte cp.async (the warp's NEXT tile streams in while this
-//             one is walked); the lanes turn them into 2-bit packed words, 16 bases per word, SWAR on four
+//   A  pack   the tile's 32 ASCII rows arrive as one bulk copy (cp.async.bulk + the warp's mbarrier; 16-byte cp.async
+//             per lane with -DSCB_SCAN_BULK=0) - the warp's NEXT tile streams in while this one is walked; the lanes turn them into 2-bit packed words, 16 bases per word, SWAR on four
 //             bytes at a time (bytes that are not ACGT/acgt become A, const.cpp:47-49). The words go to
 //             global memory (coalesced: a tile's packed rows are one contiguous run) and to a shared-memory
 //             copy with an odd row pitch (conflict-free for phase B).
@@ -51,7 +51,7 @@ __host__ __device__ inline int scan_smem_pitch(int PW) { return PW | 1; }
 __host__ __device__ inline size_t scan_smem_warp_bytes(int L, int PW) {
     const size_t tile = (size_t)32 * L + 32;                        // 32*L is a multiple of 16
     const size_t pk = (size_t)32 * scan_smem_pitch(PW) * 4, q = (size_t)32 * kHitQ * 2, hm = (((size_t)32 * PW * 2) + 15) & ~(size_t)15;
-    return ((tile + pk + q + hm) + 15) & ~(size_t)15;
+    return ((tile + pk + q + hm) + 15 + 16) & ~(size_t)15;          // + the warp's mbarrier (last 16 bytes)
 }
 __host__ __device__ inline size_t scan_smem_total(int ns, int n_hit, int nb, int W, int L, int PW) {
     return scan_smem_table_bytes(ns, n_hit, nb) + (size_t)W * scan_smem_warp_bytes(L, PW);
@@ -76,6 +76,44 @@ __device__ __forceinline__ void stage_warp_tile(const ScanSmemParams &p, int64_t
     const int n16 = bytes >> 4;
     for (int k = lane_id(); k < n16; k += 32) cp_async16(buf + (k << 4), src + ((int64_t)k << 4));
     for (int k = (n16 << 4) + lane_id(); k < bytes; k += 32) buf[k] = src[k];
+}
+
+// ---- the same staging as ONE bulk copy per warp tile (TMA engine, SASS UBLKCP): a tile's rows are one contiguous,
+// 16-byte aligned run of global memory. Lane 0 arms the warp's mbarrier with the byte count and issues the copy; the
+// warp waits on the barrier's phase before packing. The (< 16) bytes a ragged last tile leaves over are copied by hand.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// returns true if a copy was issued (the caller then owes one mbar_wait)
+__device__ __forceinline__ bool stage_warp_tile_bulk(const ScanSmemParams &p, int64_t tile, uint8_t *buf, uint64_t *bar) {
+    const int64_t row0 = tile * 32;
+    int64_t rows = p.n - row0;
+    if (rows > 32) rows = 32;
+    if (rows <= 0) return false;
+    const int bytes = (int)rows * p.L;
+    const uint8_t *src = p.seq + row0 * p.L;
+    const int b16 = bytes & ~15;
+    for (int k = b16 + lane_id(); k < bytes; k += 32) buf[k] = src[k];
+    if (b16 == 0) return false;
+    if (lane_id() == 0) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(buf), b = (uint32_t)__cvta_generic_to_shared(bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"((uint32_t)b16) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(d), "l"(src), "r"((uint32_t)b16), "r"(b) : "memory");
+    }
+    return true;
 }
 
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {

@@ -12,6 +12,10 @@
 #pragma once
 #include "scan_smem.cuh"
 
+#ifndef SCB_SCAN_BULK
+#define SCB_SCAN_BULK 1    // tile staging by cp.async.bulk + mbarrier (0: per-lane 16-byte cp.async)
+#endif
+
 namespace scb {
 
 __global__ void __launch_bounds__(1024, 1) scan_smem2_k(ScanSmemParams p) {
@@ -26,6 +30,13 @@ __global__ void __launch_bounds__(1024, 1) scan_smem2_k(ScanSmemParams p) {
     uint32_t *s_pk = (uint32_t *)(s_tile + (size_t)32 * L + 32);
     uint16_t *s_q = (uint16_t *)(s_pk + (size_t)32 * pitch);
     uint16_t *s_hm = s_q + (size_t)32 * kHitQ;
+#if SCB_SCAN_BULK
+    uint64_t *bar = (uint64_t *)(s_tile + scan_smem_warp_bytes(L, PW) - 16);
+    if (l == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    uint32_t phase = 0;
+    bool pending = false;
+#endif
 
     for (int k = threadIdx.x; k < p.ns * 2; k += blockDim.x) ((uint32_t *)s_trans)[k] = ((const uint32_t *)p.trans)[k];
     for (int k = threadIdx.x; k < p.n_hit; k += blockDim.x) s_hit[k] = p.hit_rank[k];
@@ -43,10 +54,18 @@ __global__ void __launch_bounds__(1024, 1) scan_smem2_k(ScanSmemParams p) {
 
     const int64_t stride = (int64_t)gridDim.x * W;
     int64_t tile = (int64_t)w * gridDim.x + blockIdx.x;   // neighbouring CTAs take neighbouring tiles
+#if SCB_SCAN_BULK
+    if (tile < p.n_tiles) pending = stage_warp_tile_bulk(p, tile, s_tile, bar);
+#else
     if (tile < p.n_tiles) stage_warp_tile(p, tile, s_tile);
     cp_async_commit();
+#endif
     for (; tile < p.n_tiles; tile += stride) {
+#if SCB_SCAN_BULK
+        if (pending) { mbar_wait(bar, phase); phase ^= 1u; }
+#else
         cp_async_wait<0>();
+#endif
         __syncwarp();
         int rows = (int)((p.n - tile * 32 < 32) ? (p.n - tile * 32) : 32);
         // ---- A: pack ----------------------------------------------------------------------------------
@@ -74,8 +93,12 @@ __global__ void __launch_bounds__(1024, 1) scan_smem2_k(ScanSmemParams p) {
         __syncwarp();
         {   // the ASCII buffer is free again: the warp's next tile streams in under phases B-D
             const int64_t nxt = tile + stride;
+#if SCB_SCAN_BULK
+            pending = nxt < p.n_tiles && stage_warp_tile_bulk(p, nxt, s_tile, bar);
+#else
             if (nxt < p.n_tiles) stage_warp_tile(p, nxt, s_tile);
             cp_async_commit();
+#endif
         }
         // ---- B: walk -----------------------------------------------------------------------------------
         const int64_t i = tile * 32 + l;

@@ -291,11 +291,11 @@ def test_two_rank_gloo_shard_plumbing(tmp_path):
 
 
 def test_aux_word_layout_matches_header():
-    # include/scalce_b200.h documents the exchange word: rank | end << 24 | name length << 35 | chunk << 43
+    # include/scalce_b200.h documents the exchange word: rank | end << 24 (12 bits) | name length << 36 | chunk << 44
     hdr = open(os.path.join(ROOT, "include", "scalce_b200.h")).read()
     cuh = open(os.path.join(ROOT, "scalce_b200", "csrc", "shard.cuh")).read()
-    assert "end << 24" in hdr and "<< 35" in hdr and "<< 43" in hdr
-    assert "<< 24" in cuh and "<< 35" in cuh and "<< 43" in cuh
+    assert "end << 24" in hdr and "<< 36" in hdr and "<< 44" in hdr
+    assert "<< 24" in cuh and "<< 36" in cuh and "<< 44" in cuh
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):

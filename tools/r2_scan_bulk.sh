@@ -1,0 +1,12 @@
+#!/bin/bash
+# scan tile staging: cp.async.bulk + mbarrier (default) against per-lane 16-byte cp.async (build/variants/lib_scan_ldgsts.so)
+mkdir -p gpurun_out/r2
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q 2>&1 | tail -4
+for rep in 1 2; do
+  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null > gpurun_out/r2/scan_bulk_$rep.json
+  SCB_LIB_PATH=$PWD/build/variants/lib_scan_ldgsts.so python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null > gpurun_out/r2/scan_ldgsts_$rep.json
+done
+python tools/bench_brief.py gpurun_out/r2/scan_bulk_*.json gpurun_out/r2/scan_ldgsts_*.json | grep -v clocks
+python bench.py --config c3 --steps 3 --warmup 2 --no-e2e --no-cpu 2>/dev/null > gpurun_out/r2/scan_bulk_c3.json
+SCB_LIB_PATH=$PWD/build/variants/lib_scan_ldgsts.so python bench.py --config c3 --steps 3 --warmup 2 --no-e2e --no-cpu 2>/dev/null > gpurun_out/r2/scan_ldgsts_c3.json
+python tools/bench_brief.py gpurun_out/r2/scan_bulk_c3.json gpurun_out/r2/scan_ldgsts_c3.json | grep -v clocks
