@@ -347,18 +347,21 @@ def e2e_pipelined(depth, steps_per_slot, cores, L, device, N, host_in, lib, L2=0
             t.close()
 
 
-def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
+def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000, by_chunk=False):
     """Run before the timed steps at N > 1: a small sharded case (n_per reads per rank, a byte budget small enough for many flush
     chunks) against the SAME concatenated input through ONE handle on rank 0's GPU (the single-GPU path, itself checked bit for
     bit against the oracle and the reference CLI fixtures by tests/). Compared: SHA-256 of every rank's slice of every stream of
     every flush chunk and of the merged streams, and of the per-read arrays. This exercises what the loopback tests cannot:
-    cross-process CUDA-IPC peer stores, the side-stream row exchange and the NCCL ordering. Returns the "parity" object (rank 0)."""
+    cross-process CUDA-IPC peer stores, the side-stream row exchange and the NCCL ordering. Returns the "parity" object (rank 0).
+    by_chunk: the same through scb_shard_flush (C++ orchestrator + NCCL comm library) with flush-chunk ownership, which applies
+    when no merged stream is requested - the configuration of the timed steps."""
     import hashlib
     import torch
     from scalce_b200 import synth
     from scalce_b200.binding import BoostTransform
-    from scalce_b200.shard import ShardedTransform, TorchComm
+    from scalce_b200.shard import CShardedTransform, NcclCComm, ShardedTransform, TorchComm
     bsb = 16 << 20
+    merged = not by_chunk
 
     def batch(r):
         b = synth.make_batch(n_per, L, seed=9000 + r, name_start=r * n_per)
@@ -367,13 +370,20 @@ def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
         return b, q
     sha = lambda x: hashlib.sha256(x).hexdigest()
     b, q = batch(rank)
-    t = BoostTransform(cores, L, device=local, bucket_set_bytes=bsb, emit_merged=True)
+    t = BoostTransform(cores, L, device=local, bucket_set_bytes=bsb, emit_merged=merged)
     t.submit(b.seq, q, b.names, b.name_off)
-    st = ShardedTransform(t, TorchComm(dist, torch.device("cuda", local)))
-    res = st.flush()
+    if by_chunk:
+        os.environ["SCB_SHARD_SPLIT"] = "chunks"
+        st = CShardedTransform(t, NcclCComm(dist, local), use_torch_stream=True)
+    else:
+        st = ShardedTransform(t, TorchComm(dist, torch.device("cuda", local)))
+    try:
+        res = st.flush()
+    finally:
+        os.environ.pop("SCB_SHARD_SPLIT", None)
     dbg = res.debug(res.n_local)
-    chunks = list(range(res.n_chunks)) + [-1]
-    mine = {"n_chunks": res.n_chunks, "n_local": res.n_local, "rounds": st.stats["rounds"],
+    chunks = list(range(res.n_chunks)) + ([-1] if merged else [])
+    mine = {"n_chunks": res.n_chunks, "n_local": res.n_local, "rounds": st.stats["rounds"], "split": st.stats.get("split", "bucket ranges"),
             "arr": {k: sha(dbg[k].tobytes()) for k in ("node_id", "core", "end", "chunk")}, "streams": {}}
     for k in range(4):
         for c in chunks:
@@ -384,7 +394,7 @@ def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
     dist.gather_object(mine, gathered, dst=0)
     out = None
     if rank == 0:
-        t1 = BoostTransform(cores, L, device=local, bucket_set_bytes=bsb, emit_merged=True)
+        t1 = BoostTransform(cores, L, device=local, bucket_set_bytes=bsb, emit_merged=merged)
         for r in range(world):
             bb, qq = batch(r)
             t1.submit(bb.seq, qq, bb.names, bb.name_off)
@@ -399,7 +409,7 @@ def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
                 if sha(d1[k][o:o + g["n_local"]].tobytes()) != g["arr"][k]:
                     bad.append(f"per-read {k} of rank {gi}")
             o += g["n_local"]
-        for c in list(range(r1.n_chunks)) + [-1]:
+        for c in list(range(r1.n_chunks)) + ([-1] if merged else []):
             for k in range(4):
                 whole = r1.stream(k, c)
                 pos = 0
@@ -412,8 +422,9 @@ def sharded_parity_check(dist, rank, world, local, cores, L=150, n_per=150_000):
                     bad.append(f"stream {k} chunk {c} length")
         t1.close()
         out = {"n_ranks": world, "ok": not bad, "reads": world * n_per, "read_length": L, "flush_chunks": r1.n_chunks,
-               "joint_rounds": gathered[0]["rounds"], "mismatches": bad[:8],
-               "what": "rank-order concatenation of the ranks' streams 0-3 (every flush chunk + merged) and per-read bucket / core / end / "
+               "joint_rounds": gathered[0]["rounds"], "mismatches": bad[:8], "ownership": gathered[0]["split"],
+               "orchestrator": "scb_shard_flush (C++) + libscalce_b200_nccl.so" if by_chunk else "scalce_b200/shard.py + torch.distributed",
+               "what": "rank-order concatenation of the ranks' streams 0-3 (every flush chunk" + (" + merged" if merged else "") + ") and per-read bucket / core / end / "
                        "chunk arrays == ONE handle fed the concatenated input, SHA-256 per rank slice; NCCL + CUDA IPC, one process per GPU"}
     return out
 
@@ -543,6 +554,12 @@ def main():
         parity = sharded_parity_check(dist, rank, world, local, cores)
         torch.cuda.synchronize()
         dist.barrier()
+        if a.orchestrator == "cpp":
+            p2 = sharded_parity_check(dist, rank, world, local, cores, by_chunk=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                parity = {"ok": bool(parity["ok"] and p2["ok"]), "bucket_ranges": parity, "flush_chunks": p2}
 
     d = synth.make_batch_cuda(N, L, seed=1 + rank, paired=paired, L2=L2 or None, high_entropy=high_entropy, device=f"cuda:{local}")
     seq, qual, names, name_off = d["seq"], d["qual"], d["names"], d["name_off"]
@@ -595,6 +612,7 @@ def main():
         torch.cuda.synchronize()
         st = dict(sharded.stats["ms"])
         st["_rounds"] = sharded.stats["rounds"]
+        st["_split"] = sharded.stats.get("split", "bucket ranges")
         return e0.elapsed_time(e1), st
 
     def one_step():
@@ -729,7 +747,8 @@ def main():
 
     # ---- roofline of the dominant stage + whole-path figure --------------------------------------
     peak, peak_src = measured_peak_gbs()
-    mean_st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    split_mode = stages[-1].get("_split") if isinstance(stages[-1], dict) else None
+    mean_st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0] if k != "_split"}
     resolve_rounds = mean_st.pop("_rounds", None)
     dom = max(mean_st, key=mean_st.get)
     packed = (L - mean_core + 3) // 4 + (2 if L > 255 else 1)
@@ -792,8 +811,11 @@ def main():
                    "timing": ("CUDA events on the library stream around scb_flush; one handle, bucket populations reset between steps" if world == 1 else
                               "CUDA events on the rank's stream (library work and NCCL collectives are ordered on it; the side stream of the row exchange is joined before the emit) around submit + sharded flush, max over ranks"),
                    "orchestrator": ("n/a" if world == 1 else ("scb_shard_flush (C++) + libscalce_b200_nccl.so" if a.orchestrator == "cpp" else "scalce_b200/shard.py + torch.distributed")),
-                   "multi_gpu": ("n/a" if world == 1 else "contiguous input shards; joint exact tie-break (all-gather of bucket histograms per round), "
-                                 "bucket-range exchange of packed reads + qualities + names by peer stores over NVLink (CUDA IPC); output = single-GPU order of the concatenated input")},
+                   "multi_gpu": ("n/a" if world == 1 else "contiguous input shards; joint exact tie-break (all-gather of bucket histograms per round), " +
+                                 ("whole flush chunks handed to the ranks next to them: only the reads of chunks at shard edges move" if split_mode == "flush chunks"
+                                  else "bucket-range exchange of packed reads + qualities + names") +
+                                 " by peer stores over NVLink (CUDA IPC); output = single-GPU order of the concatenated input"),
+                   "ownership": None if world == 1 else (split_mode or "bucket ranges")},
         "roofline": roof, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "workspace_bytes_per_flush": int(workspace_bytes),
     }

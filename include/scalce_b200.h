@@ -253,6 +253,26 @@ typedef struct scb_shard_peer {
     int64_t row_off, name_off;
 } scb_shard_peer;
 int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out);
+/* The other way to hand out the emit work: whole FLUSH CHUNKS instead of bucket ranges. The output of the transform is
+ * chunk-major (one set of temp files per flush chunk, compress.cpp:708-713), chunks and shards are both contiguous pieces of
+ * the input, so a rank that is handed the chunks lying in (or mostly in) its own shard keeps most of its reads and only the
+ * reads of the chunks at shard edges cross NVLink - against (n_ranks-1)/n_ranks of all reads for bucket ranges. After the
+ * exchange a rank holds every read of its chunks and emits them exactly as one handle would; the other ranks' pieces of those
+ * chunks are empty, so "rank-order concatenation per chunk" still describes the job's output.
+ *   scb_shard_chunk_layout      after scb_shard_sizes: out5 = {first chunk id of this shard, chunks that START in it, reads,
+ *                               reads belonging to the first chunk id, reads belonging to the last started chunk}
+ *   scb_shard_partition_chunks  replaces scb_shard_partition; chunk_owner[n_chunks] (host) = rank that emits each chunk,
+ *                               non-decreasing (then the send order is the input order and no owner sort is needed)
+ * The bucket-major merged stream (emit_merged) has no contiguous per-rank piece under this ownership: orchestrators keep
+ * bucket ranges when it is requested. scb_shard_split_mode: ownership used by the handle's last sharded flush (0 bucket
+ * ranges, 1 flush chunks). scb_shard_flush picks chunks when emit_merged = 0 and the chunks balance the ranks within 1.6x. */
+int scb_shard_chunk_layout(const scb_handle *h, int64_t *out5);
+int scb_shard_partition_chunks(scb_handle *h, const int32_t *chunk_owner, int32_t n_chunks, int32_t n_ranks, scb_shard_xfer *out);
+int scb_shard_split_mode(const scb_handle *h);
+/* The owner rule scb_shard_flush applies (host arithmetic, no device): layouts = the ranks' scb_shard_chunk_layout outputs in
+ * rank order [n_ranks x 5]. A chunk inside one shard stays with that rank; a chunk spanning shards goes to the least loaded rank
+ * it touches (ties: the one holding most of it). *max_load = reads of the busiest rank. */
+int scb_shard_chunk_owners(const int64_t *layouts, int32_t n_ranks, int32_t n_chunks, int32_t *chunk_owner, int64_t *max_load);
 int scb_shard_recv_reserve(scb_handle *h, const int64_t *need_bytes, void **ptrs, int32_t *changed);
 /* what: 1 = aux words + 2-bit rows + names (all the receive side needs to SORT), 2 = quality / mate-2 rows, 3 = both.
  * async = 0: returns when this rank's writes are complete. async = 1: the writes run on a side stream with a small

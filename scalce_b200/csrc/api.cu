@@ -200,6 +200,8 @@ struct scb_handle {
     DevBuf sh_perm, sh_aux, sh_packed, sh_qual1, sh_names, sh_seq2, sh_qual2, sh_noff;   // send side, destination-major
     std::vector<int64_t> sh_cnt_reads, sh_cnt_name_bytes, sh_first, sh_nbytes;
     int sh_G = 0;
+    int64_t sh_layout[5] = {0, 0, 0, 0, 0};   // flush chunks of the local shard: first chunk id, new chunks, reads, reads of the first chunk, reads of the last
+    int sh_split_mode = 0;                   // ownership of the last sharded flush: 0 bucket ranges, 1 flush chunks
     void *rx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // receive buffers: aux, packed, qual1, names, seq2, qual2
     size_t rx_cap[6] = {0, 0, 0, 0, 0, 0};
     std::vector<void *> rx_retired;
@@ -1332,6 +1334,17 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
     if ((uint64_t)chunk_in + o[0] >= kAuxMaxChunks) throw CudaError{"too many flush chunks for the sharded run (>= 2^20)"};
     h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
     if (n > 0) SCB_LAUNCH(chunk_ids_global_k, (unsigned)cdiv(n, 256), 256, 0, st, bounds.as<uint32_t>(), (int)o[0], (uint32_t)chunk_in, n, h->chunk.as<uint32_t>());
+    {   // what an orchestrator needs to hand whole chunks to ranks (scb_shard_chunk_layout)
+        uint32_t b2[2] = {0, 0};
+        if (o[0] > 0) {
+            SCB_CUDA(cudaMemcpyAsync(&b2[0], bounds.as<uint32_t>(), 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaMemcpyAsync(&b2[1], bounds.as<uint32_t>() + (o[0] - 1), 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+        }
+        h->sh_layout[0] = chunk_in; h->sh_layout[1] = (int64_t)o[0]; h->sh_layout[2] = n;
+        h->sh_layout[3] = o[0] > 0 ? (int64_t)b2[0] : n;
+        h->sh_layout[4] = o[0] > 0 ? n - (int64_t)b2[1] : 0;
+    }
     tm.stop();
     *carry_out = o[1];
     *chunk_out = chunk_in + (int32_t)o[0];
@@ -1457,7 +1470,9 @@ static void gather_rows_to(cudaStream_t st, const uint8_t *src, uint8_t *dst, co
 }
 
 // stable partition of the local reads by owner + what the owners need to size their receive buffers
-static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shard_xfer *out) {
+// split != null: owner = the rank whose slice of the bucket emission order holds the read's bucket; else chunk_owner[n_chunks]
+// (host): owner = the rank that was handed the read's flush chunk
+static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shard_xfer *out, const int32_t *chunk_owner = nullptr, int n_chunks = 0) {
     cudaStream_t st = h->st;
     ArenaScope arena_scope(&h->arena);
     const scb_config &cfg = h->cfg;
@@ -1468,18 +1483,27 @@ static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shar
     ShardTimer tm(h);
     SplitTab t;
     t.G = G;
-    for (int g = 0; g <= G; g++) t.s[g] = (uint32_t)split[g];
+    if (split) for (int g = 0; g <= G; g++) t.s[g] = (uint32_t)split[g];
     // one 8-bit radix pass over the destination keeps input order inside every destination
     DevBuf k0((size_t)n1 * 8, st), k1((size_t)n1 * 8, st), v0((size_t)n1 * 4, st);
     DevBuf hist((size_t)SortWs::hist_elems(n) * 4, st), histws((size_t)scan_tiles(SortWs::hist_elems(n)) * 4, st);
     SortWs ws; ws.hist = hist.as<uint32_t>(); ws.tile_ws = histws.as<uint32_t>();
     uint64_t *ka = k0.as<uint64_t>(), *kb = k1.as<uint64_t>();
     uint32_t *va = v0.as<uint32_t>(), *vb = h->sh_perm.as<uint32_t>();   // one pass: the result lands in sh_perm
-    if (n > 0) {
+    if (n > 0 && !split) {
+        // whole chunks: owners are non-decreasing along the input, the send order is the input order
+        std::vector<uint8_t> ow((size_t)std::max(n_chunks, 1), 0);
+        for (int c2 = 0; c2 < n_chunks; c2++) ow[(size_t)c2] = (uint8_t)chunk_owner[c2];
+        DevBuf dow(ow.size(), st);
+        SCB_CUDA(cudaMemcpyAsync(dow.p, ow.data(), ow.size(), cudaMemcpyHostToDevice, st));
+        SCB_LAUNCH(dest_keys_chunk_k, (unsigned)cdiv(n, 256), 256, 0, st, h->chunk.as<uint32_t>(), n, dow.as<uint8_t>(), ka, h->sh_perm.as<uint32_t>());
+        SCB_CUDA(cudaStreamSynchronize(st));          // `ow` leaves scope
+    } else if (n > 0) {
         SCB_LAUNCH(dest_keys_k, (unsigned)cdiv(n, 256), 256, 0, st, h->asg.as<uint32_t>(), n, nb, h->tab.root_order_pos, t, ka, va);
         radix_sort_pairs(&ka, &va, &kb, &vb, n, 0, std::max(1, ceil_log2((uint64_t)G)), ws, st);
         if (va != h->sh_perm.as<uint32_t>()) SCB_CUDA(cudaMemcpyAsync(h->sh_perm.p, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     }
+    h->sh_split_mode = split ? 0 : 1;
     const uint32_t *perm = h->sh_perm.as<uint32_t>();
     DevBuf dfirst((size_t)(G + 1) * 8, st), dnb((size_t)(G + 1) * 8, st);
     SCB_LAUNCH(dest_bounds_k, 1, kMaxRanks + 1, 0, st, ka, n, G, dfirst.as<int64_t>());
@@ -2216,6 +2240,38 @@ int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, sc
     SCB_CATCH
     return SCB_OK;
 }
+int scb_shard_partition_chunks(scb_handle *h, const int32_t *chunk_owner, int32_t n_chunks, int32_t n_ranks, scb_shard_xfer *out) {
+    if (!chunk_owner || !out || n_chunks < 1 || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks, >= 1 chunk)"; return SCB_EINVAL; }
+    for (int c = 0; c < n_chunks; c++)
+        if (chunk_owner[c] < 0 || chunk_owner[c] >= n_ranks || (c > 0 && chunk_owner[c] < chunk_owner[c - 1])) {
+            scb::g_last_error = "chunk owners must be ranks and must not decrease along the chunk order"; return SCB_EINVAL;
+        }
+    SCB_SHARD_ENTER(2)
+    {
+        const int64_t c0 = h->sh_layout[0], nn = h->sh_layout[1], n = h->sh_layout[2], tail = h->sh_layout[4];
+        const int64_t last = nn > 0 ? (tail > 0 ? c0 + nn : c0 + nn - 1) : c0;          // largest chunk id a local read carries
+        if (n > 0 && last >= n_chunks) { scb::g_last_error = "chunk owners do not cover this rank's chunks"; return SCB_EINVAL; }
+    }
+    scb::shard_partition(h, nullptr, n_ranks, out, chunk_owner, n_chunks);
+    SCB_CATCH
+    return SCB_OK;
+}
+int scb_shard_chunk_layout(const scb_handle *h, int64_t *out5) {
+    if (!h || !out5) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
+    if (h->sh_phase < 1 || !h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_chunk_layout"; return SCB_ESTATE; }
+    for (int k = 0; k < 5; k++) out5[k] = h->sh_layout[k];
+    return SCB_OK;
+}
+int scb_shard_split_mode(const scb_handle *h) { return h ? h->sh_split_mode : -1; }
+namespace scb { static int64_t chunk_owners(const std::vector<int64_t> &lay, int G, int n_chunks, std::vector<int32_t> &owner); }
+int scb_shard_chunk_owners(const int64_t *layouts, int32_t n_ranks, int32_t n_chunks, int32_t *chunk_owner, int64_t *max_load) {
+    if (!layouts || !chunk_owner || n_ranks < 1 || n_ranks > scb::kMaxRanks || n_chunks < 1) { scb::g_last_error = "bad argument (1..64 ranks, >= 1 chunk)"; return SCB_EINVAL; }
+    std::vector<int32_t> ow;
+    const int64_t ml = scb::chunk_owners(std::vector<int64_t>(layouts, layouts + (size_t)n_ranks * 5), n_ranks, n_chunks, ow);
+    for (int c = 0; c < n_chunks; c++) chunk_owner[c] = ow[(size_t)c];
+    if (max_load) *max_load = ml;
+    return SCB_OK;
+}
 int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
     if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(2)
@@ -2413,6 +2469,40 @@ static std::vector<int64_t> balanced_split(const std::vector<uint64_t> &hist, in
     split.push_back(ncols);
     return split;
 }
+// Whole flush chunks to ranks. lay[g] = scb_shard_chunk_layout of rank g. A chunk that lies inside one rank stays there; a
+// chunk that spans ranks goes to the least loaded rank it touches (ties: the rank holding most of it). Chunks and shards are
+// both contiguous in the input, so owners never decrease along the chunk order. Returns the largest load (reads).
+static int64_t chunk_owners(const std::vector<int64_t> &lay, int G, int n_chunks, std::vector<int32_t> &owner) {
+    owner.assign((size_t)std::max(n_chunks, 1), 0);
+    std::vector<int64_t> load((size_t)G, 0);
+    std::vector<std::vector<std::pair<int, int64_t>>> touch((size_t)n_chunks);      // (rank, reads) of the chunks at shard edges
+    for (int g = 0; g < G; g++) {
+        const int64_t c0 = lay[(size_t)g * 5], nn = lay[(size_t)g * 5 + 1], n = lay[(size_t)g * 5 + 2], head = lay[(size_t)g * 5 + 3], tail = lay[(size_t)g * 5 + 4];
+        if (c0 < n_chunks && head > 0) touch[(size_t)c0].push_back({g, head});
+        if (nn > 0 && c0 + nn < n_chunks && tail > 0) touch[(size_t)(c0 + nn)].push_back({g, tail});
+        for (int64_t c = c0 + 1; c < c0 + nn && c < n_chunks; c++) owner[(size_t)c] = g;                 // chunks that start and end inside the shard
+        load[(size_t)g] += n - head - (nn > 0 ? tail : 0);
+    }
+    int prev = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        auto &t = touch[(size_t)c];
+        if (!t.empty()) {
+            int best = -1; int64_t best_cnt = 0, total = 0;
+            for (auto &e : t) {
+                total += e.second;
+                if (e.first < prev) continue;                  // keeps the owners monotone whatever the loads say
+                if (best < 0 || load[(size_t)e.first] < load[(size_t)best] || (load[(size_t)e.first] == load[(size_t)best] && e.second > best_cnt)) { best = e.first; best_cnt = e.second; }
+            }
+            if (best < 0) best = t.back().first;
+            owner[(size_t)c] = best;
+            load[(size_t)best] += total;
+        } else if (owner[(size_t)c] < prev) {
+            owner[(size_t)c] = prev;                           // a chunk without reads (cannot happen below n_chunks): anywhere monotone
+        }
+        prev = owner[(size_t)c];
+    }
+    return *std::max_element(load.begin(), load.end());
+}
 }  // namespace scb
 
 #define SCB_FL(call) do { int _rc = (call); if (_rc != SCB_OK) return _rc; } while (0)
@@ -2450,6 +2540,23 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
             carry = (uint64_t)cc[(size_t)g * 2]; chunk = (int32_t)cc[(size_t)g * 2 + 1];
         }
         const int32_t n_chunks = chunk + (carry > 0 ? 1 : 0);
+        // ---- who emits what. Chunk-major output shards by flush chunk: a rank is handed whole chunks, near its own shard, and
+        //      only the reads of the chunks at shard edges cross NVLink. That needs enough chunks to balance the ranks, and it
+        //      leaves no rank a contiguous piece of the bucket-major merged stream - so with emit_merged, or with few chunks, the
+        //      bucket emission order is cut into ranges instead and (G-1)/G of the reads move. SCB_SHARD_SPLIT=chunks|buckets forces.
+        std::vector<int32_t> owner;
+        bool by_chunk = false;
+        {
+            int64_t lay5[5] = {0, 0, 0, 0, 0};
+            SCB_FL(scb_shard_chunk_layout(h, lay5));
+            const std::vector<int64_t> lay = comm_allgather_i64(cm, std::vector<int64_t>(lay5, lay5 + 5));
+            const int64_t max_load = n_chunks > 0 ? chunk_owners(lay, G, n_chunks, owner) : 0;
+            by_chunk = G > 1 && n_chunks >= 2 && !cfg.emit_merged && (double)max_load * G <= 1.6 * (double)n_global;
+            if (const char *e = getenv("SCB_SHARD_SPLIT")) {
+                if (!strcmp(e, "chunks") && n_chunks >= 1 && !cfg.emit_merged) by_chunk = true;
+                if (!strcmp(e, "buckets")) by_chunk = false;
+            }
+        }
         // ---- tie-break ------------------------------------------------------------------------------------------------
         const int RW = ncols + 1;
         DevBuf tot((size_t)RW * 4, st), all((size_t)G * RW * 4, st), bf((size_t)ncols * 4, st), gtot((size_t)ncols * 4, st), dchg(8, st);
@@ -2485,19 +2592,23 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
         SCB_LAUNCH(sh_sum_rows_k, (unsigned)cdiv(ncols, 256), 256, 0, st, all.as<uint32_t>(), RW, 0, G, ncols, gtot.as<uint32_t>());
         SCB_CUDA(cudaStreamSynchronize(st));
         SCB_FL(scb_shard_finalize(h, gtot.as<uint32_t>(), n_global)); lap(P_FINALIZE);
-        // ---- bucket-range split ----------------------------------------------------------------------------------------
-        DevBuf hist((size_t)ncols * 4, st), allh((size_t)G * ncols * 4, st), ghist((size_t)ncols * 4, st);
-        SCB_FL(scb_shard_bucket_hist(h, hist.as<uint32_t>())); lap(P_HIST);
-        comm_check(cm->allgather(cm->ctx, hist.p, allh.p, (int64_t)ncols * 4, 1, st), "allgather (device)");
-        // per-rank histograms fit u32; their sum over the ranks may not: add on the host in 64 bits
-        std::vector<uint32_t> hh((size_t)G * ncols);
-        SCB_CUDA(cudaMemcpyAsync(hh.data(), allh.p, hh.size() * 4, cudaMemcpyDeviceToHost, st));
-        SCB_CUDA(cudaStreamSynchronize(st));
-        std::vector<uint64_t> gh((size_t)ncols, 0);
-        for (int g = 0; g < G; g++) for (int c2 = 0; c2 < ncols; c2++) gh[(size_t)c2] += hh[(size_t)g * ncols + c2];
-        const std::vector<int64_t> split = balanced_split(gh, G);
+        // ---- partition by owner --------------------------------------------------------------------------------------------
         scb_shard_xfer x;
-        SCB_FL(scb_shard_partition(h, split.data(), G, &x)); lap(P_PACK);
+        if (by_chunk) {
+            SCB_FL(scb_shard_partition_chunks(h, owner.data(), n_chunks, G, &x)); lap(P_PACK);
+        } else {
+            DevBuf hist((size_t)ncols * 4, st), allh((size_t)G * ncols * 4, st);
+            SCB_FL(scb_shard_bucket_hist(h, hist.as<uint32_t>())); lap(P_HIST);
+            comm_check(cm->allgather(cm->ctx, hist.p, allh.p, (int64_t)ncols * 4, 1, st), "allgather (device)");
+            // per-rank histograms fit u32; their sum over the ranks may not: add on the host in 64 bits
+            std::vector<uint32_t> hh((size_t)G * ncols);
+            SCB_CUDA(cudaMemcpyAsync(hh.data(), allh.p, hh.size() * 4, cudaMemcpyDeviceToHost, st));
+            SCB_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint64_t> gh((size_t)ncols, 0);
+            for (int g = 0; g < G; g++) for (int c2 = 0; c2 < ncols; c2++) gh[(size_t)c2] += hh[(size_t)g * ncols + c2];
+            const std::vector<int64_t> split = balanced_split(gh, G);
+            SCB_FL(scb_shard_partition(h, split.data(), G, &x)); lap(P_PACK);
+        }
         // ---- exchange: what every rank receives from every rank -----------------------------------------------------------
         std::vector<int64_t> mine((size_t)2 * G);
         for (int g = 0; g < G; g++) { mine[(size_t)g] = x.cnt_reads[g]; mine[(size_t)G + g] = x.cnt_name_bytes[g]; }

@@ -95,6 +95,15 @@ __global__ void dest_keys_k(const uint32_t *__restrict__ asg, int64_t n, int nb,
     keys[i] = (uint64_t)g;
     vals[i] = (uint32_t)i;
 }
+// chunk ownership: destination = owner of the read's flush chunk. Owners never decrease along the input order, so the keys
+// come out sorted and the send order is the input order (no sort pass).
+__global__ void dest_keys_chunk_k(const uint32_t *__restrict__ chunk, int64_t n, const uint8_t *__restrict__ owner,
+                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint64_t)owner[chunk[i]];
+    vals[i] = (uint32_t)i;
+}
 // first[g] = first position of the sorted destination keys holding a value >= g, g = 0..G
 __global__ void dest_bounds_k(const uint64_t *__restrict__ keys, int64_t n, int G, int64_t *__restrict__ first) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;

@@ -589,7 +589,8 @@ class CShardedTransform:
         ms = (C.c_float * 12)()
         rounds = C.c_int32()
         L.scb_shard_flush_stats(self.t._h, ms, 12, C.byref(rounds))
-        self.stats = dict(ms=dict(zip(self.PHASES, [float(x) for x in ms])), rounds=rounds.value)
+        self.stats = dict(ms=dict(zip(self.PHASES, [float(x) for x in ms])), rounds=rounds.value,
+                          split=("flush chunks" if L.scb_shard_split_mode(self.t._h) == 1 else "bucket ranges"))
         out = FlushResult(self.t, res)
         out.n_local = self.t.n_local_last()
         return out

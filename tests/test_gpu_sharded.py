@@ -165,3 +165,56 @@ def test_cpp_orchestrator_sparse_engine(monkeypatch):
     monkeypatch.setenv("SCB_TABLE", "global")
     monkeypatch.setenv("SCB_RESOLVE", "sparse")
     _case_cpp(30000, 100, 3, seed=59, bucket_set_bytes=1 << 20)
+
+
+# ---- flush-chunk ownership (scb_shard_partition_chunks): whole chunks to the ranks next to them ------------------------------
+def _case_chunks(n, L, world, **kw):
+    """C++ orchestrator, no merged stream (bucket-major output keeps bucket-range ownership): per-chunk streams and per-read
+    arrays against the oracle. Returns (oracle, ranks)."""
+    run_kw = {k: kw.pop(k) for k in list(kw) if k in ("use_names", "use_quals", "bucket_set_bytes", "bounds")}
+    paired = kw.get("paired", False)
+    cores, b, q1, q2, _ = util.make_case(n, L, **kw)
+    o = util.run_oracle(cores, b, q1, q2, paired=paired, **{k: v for k, v in run_kw.items() if k != "bounds"})
+    ranks = util.run_sharded_loopback(cores, b, q1, q2, world, paired=paired, cpp=True, emit_merged=False, **run_kw)
+    util.assert_sharded_same(o, ranks, paired=paired, check_merged=False)
+    return o, ranks
+
+
+def test_chunk_ownership_is_picked_when_chunks_balance_the_ranks():
+    o, ranks = _case_chunks(40000, 100, 4, seed=61, bucket_set_bytes=1 << 19)
+    assert o.n_chunks >= 12
+    assert all(st.stats["split"] == "flush chunks" for _, st, _ in ranks)
+    # every chunk lives on exactly one rank, owners do not decrease, and every rank got work
+    owners = []
+    for c in range(o.n_chunks):
+        have = [r for r, (_, _, res) in enumerate(ranks) if len(res.stream(1, c)) > 0]
+        assert len(have) == 1, (c, have)
+        owners.append(have[0])
+    assert owners == sorted(owners) and set(owners) == set(range(4))
+
+
+def test_chunk_ownership_shapes(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_SPLIT", "chunks")
+    _case_chunks(30000, 100, 2, seed=62, bucket_set_bytes=1 << 20)
+    _case_chunks(20000, 100, 3, seed=63, paired=True, L2=75, bucket_set_bytes=1 << 20, bounds=[0, 1000, 13000, 20000])
+    _case_chunks(40000, 36, 8, seed=64, use_names=False, bucket_set_bytes=1 << 19)
+    _case_chunks(9000, 64, 4, seed=65, bounds=[0, 0, 5000, 5000, 9000], bucket_set_bytes=1 << 18)      # empty ranks
+    _case_chunks(6000, 300, 2, seed=66, use_quals=False, bucket_set_bytes=1 << 20)
+    _case_chunks(8000, 100, 4, seed=67)                              # ONE chunk (4 GiB budget): everything goes to one rank
+    _case_chunks(12000, 100, 5, seed=68, bucket_set_bytes=3 << 20)   # a chunk spanning several ranks
+    o, ranks = _case_chunks(900, 2498, 3, seed=69, bucket_set_bytes=1 << 20, plant=0.9)
+    assert all(st.stats["split"] == "flush chunks" for _, st, _ in ranks)
+
+
+def test_few_chunks_or_merged_output_keep_bucket_ranges():
+    o, ranks = _case_chunks(8000, 100, 4, seed=70)                   # one chunk cannot balance four ranks
+    assert all(st.stats["split"] == "bucket ranges" for _, st, _ in ranks)
+    o, ranks = _case_cpp(40000, 100, 4, seed=71, bucket_set_bytes=1 << 20)     # emit_merged: each rank holds a contiguous piece of the merged stream
+    assert all(st.stats["split"] == "bucket ranges" for _, st, _ in ranks)
+
+
+def test_chunk_ownership_second_flush_and_sparse_engine(monkeypatch):
+    monkeypatch.setenv("SCB_SHARD_SPLIT", "chunks")
+    monkeypatch.setenv("SCB_RESOLVE", "sparse")
+    monkeypatch.setenv("SCB_TABLE", "global")
+    _case_chunks(30000, 100, 3, seed=72, bucket_set_bytes=1 << 20)

@@ -565,3 +565,52 @@ def test_vectorised_core_set_generator():
     d = table_dryrun(c)
     assert d["n_buckets"] == 25300
     assert synth.make_core_set([(3, 1000)], seed=1).__len__() == 64      # capped at 4^length
+
+
+def test_chunk_owner_rule_on_simulated_shards():
+    """scb_shard_chunk_owners (host arithmetic of the sharded flush): whole flush chunks to ranks. Random shard and chunk
+    boundaries; the owners must not decrease, must touch their chunk, and the loads must add up to the input."""
+    import ctypes as C
+    from scalce_b200.binding import load_library
+    L = load_library()
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        G = int(rng.integers(1, 9))
+        n = int(rng.integers(1, 5000))
+        n_chunks = int(rng.integers(1, 40))
+        sb = np.sort(rng.integers(0, n + 1, size=G - 1)) if G > 1 else np.zeros(0, dtype=np.int64)
+        shard = np.concatenate([[0], sb, [n]]).astype(np.int64)                      # shard g = [shard[g], shard[g+1])
+        cb = np.sort(rng.choice(np.arange(1, n), size=min(n_chunks - 1, n - 1), replace=False)) if n > 1 else np.zeros(0, dtype=np.int64)
+        chunk_start = np.concatenate([[0], cb]).astype(np.int64)                      # chunk c = [chunk_start[c], chunk_start[c+1])
+        n_chunks = len(chunk_start)
+        chunk_of = np.searchsorted(chunk_start, np.arange(n), side="right") - 1
+        lay = np.zeros((G, 5), dtype=np.int64)
+        cur_chunk = 0
+        for g in range(G):
+            a, z = int(shard[g]), int(shard[g + 1])
+            # chunk id the shard starts in (a chunk starting exactly at the shard's first read was announced by the rank before:
+            # its flush fell on its last read)
+            cin = int(chunk_of[a]) if a < n else n_chunks - 1
+            if a == z:
+                lay[g] = [cin, 0, 0, 0, 0]
+                continue
+            starts = [int(x) - a for x in chunk_start if a < x < z]                # chunks that start inside the shard, local indices
+            # a chunk starting exactly at z (the shard's end) is announced by this rank as a boundary at local index n
+            if z < n and z in chunk_start:
+                starts.append(z - a)
+            head = starts[0] if starts else z - a
+            tail = (z - a) - starts[-1] if starts else 0
+            lay[g] = [cin, len(starts), z - a, head, tail]
+        owner = (C.c_int32 * n_chunks)()
+        ml = C.c_int64()
+        assert L.scb_shard_chunk_owners(lay.ctypes.data_as(C.POINTER(C.c_int64)), G, n_chunks, owner, C.byref(ml)) == 0
+        ow = np.array(owner[:])
+        assert (np.diff(ow) >= 0).all(), (trial, ow)
+        load = np.zeros(G, dtype=np.int64)
+        rank_of = np.searchsorted(shard, np.arange(n), side="right") - 1
+        rank_of = np.minimum(rank_of, G - 1)
+        for c in range(n_chunks):
+            members = np.nonzero(chunk_of == c)[0]
+            assert ow[c] in set(rank_of[members].tolist()), (trial, c, ow[c])    # the owner holds part of its chunk
+            load[ow[c]] += len(members)
+        assert load.sum() == n and load.max() == ml.value, (trial, load, ml.value)
