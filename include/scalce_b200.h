@@ -262,7 +262,12 @@ int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, sc
  *   scb_shard_chunk_layout      after scb_shard_sizes: out5 = {first chunk id of this shard, chunks that START in it, reads,
  *                               reads belonging to the first chunk id, reads belonging to the last started chunk}
  *   scb_shard_partition_chunks  replaces scb_shard_partition; chunk_owner[n_chunks] (host) = rank that emits each chunk,
- *                               non-decreasing (then the send order is the input order and no owner sort is needed)
+ *                               non-decreasing (then the send order is the input order, every array of a destination is one
+ *                               contiguous copy and no owner sort is needed). Nothing of it depends on the tie-break: it may
+ *                               be called right after scb_shard_sizes, and scb_shard_send(what = 2) - the quality / mate-2
+ *                               rows, most of the bytes - may then run UNDER the tie-break. The aux words (bucket, end
+ *                               marker) are packed by the first scb_shard_send that carries them (what & 1), which
+ *                               therefore needs scb_shard_finalize before it.
  * The bucket-major merged stream (emit_merged) has no contiguous per-rank piece under this ownership: orchestrators keep
  * bucket ranges when it is requested. scb_shard_split_mode: ownership used by the handle's last sharded flush (0 bucket
  * ranges, 1 flush chunks). scb_shard_flush picks chunks when emit_merged = 0 and the chunks balance the ranks within 1.6x. */

@@ -132,7 +132,8 @@ struct scb_handle {
     cudaStream_t st = nullptr, st_own = nullptr;
     cudaStream_t st_aux[2] = {nullptr, nullptr};   // side streams: independent output kernels run next to the quality gather
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;   // around the rows of a sharded send (possibly on the side stream)
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;   // around a sharded send on the main stream
+    cudaEvent_t ev_a0 = nullptr, ev_a1 = nullptr;   // around the row sends on the side stream (they may bracket a main-stream send)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t stage_ev[SCB_N_STAGES + 1] = {};
     float stage_ms[SCB_N_STAGES] = {};
@@ -202,6 +203,9 @@ struct scb_handle {
     int sh_G = 0;
     int64_t sh_layout[5] = {0, 0, 0, 0, 0};   // flush chunks of the local shard: first chunk id, new chunks, reads, reads of the first chunk, reads of the last
     int sh_split_mode = 0;                   // ownership of the last sharded flush: 0 bucket ranges, 1 flush chunks
+    bool sh_resolved = false;                // scb_shard_finalize has run for the current shard
+    bool sh_aux_pending = false;             // chunk ownership, partitioned before the tie-break: the aux words are packed by the first send that carries them
+    const uint8_t *sh_names_src = nullptr;   // names in send order: the staged copy (bucket ranges) or the input itself (flush chunks: send order = input order)
     void *rx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // receive buffers: aux, packed, qual1, names, seq2, qual2
     size_t rx_cap[6] = {0, 0, 0, 0, 0, 0};
     std::vector<void *> rx_retired;
@@ -250,6 +254,8 @@ static int create_common(const std::vector<std::string> &cores, const scb_config
         for (auto &e : h->ev_join) SCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         SCB_CUDA(cudaEventCreate(&h->ev_s0));
         SCB_CUDA(cudaEventCreate(&h->ev_s1));
+        SCB_CUDA(cudaEventCreate(&h->ev_a0));
+        SCB_CUDA(cudaEventCreate(&h->ev_a1));
         SCB_CUDA(cudaEventCreate(&h->ev0));
         SCB_CUDA(cudaEventCreate(&h->ev1));
         for (auto &e : h->stage_ev) SCB_CUDA(cudaEventCreate(&e));
@@ -1303,6 +1309,7 @@ static void shard_scan(scb_handle *h) {
     h->endv.alloc((size_t)n * 2, st);
     tm.stop();
     h->last_rounds = 0;
+    h->sh_resolved = false; h->sh_aux_pending = false; h->sh_names_src = nullptr;
     h->sh_phase = 1;
 }
 
@@ -1432,7 +1439,8 @@ static void shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_
     stage_debug(h);   // per-read arrays of the input shard (chunk ids are the global ones)
     tm.stop();
     if (h->tab.root_counts_unbucketed) h->unbucketed += (int64_t)(root_after - root_before);
-    h->sh_phase = 2;
+    h->sh_resolved = true;
+    h->sh_phase = std::max(h->sh_phase, 2);     // chunk ownership may have partitioned (3) and started its row sends (4) already
 }
 
 static void shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
@@ -1508,33 +1516,55 @@ static void shard_partition(scb_handle *h, const int64_t *split, int G, scb_shar
     DevBuf dfirst((size_t)(G + 1) * 8, st), dnb((size_t)(G + 1) * 8, st);
     SCB_LAUNCH(dest_bounds_k, 1, kMaxRanks + 1, 0, st, ka, n, G, dfirst.as<int64_t>());
     h->sh_aux.alloc((size_t)n1 * 8, st);
-    if (n > 0)
-        SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
-                   cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
-    h->sh_noff.alloc((size_t)(n + 1) * 8, st);
-    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
-    exclusive_scan<uint64_t>(AuxNameLen{h->sh_aux.as<uint64_t>()}, n, h->sh_noff.as<uint64_t>(), h->sh_noff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
-    SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, h->sh_noff.as<uint64_t>(), dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
     h->sh_first.assign((size_t)G + 1, 0); h->sh_nbytes.assign((size_t)G + 1, 0);
-    SCB_CUDA(cudaMemcpyAsync(h->sh_first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaMemcpyAsync(h->sh_nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
-    SCB_CUDA(cudaStreamSynchronize(st));
+    int64_t name_bytes = 0;
+    if (!split) {
+        // send order = input order: the names of a destination are one contiguous piece of the input's name array, nothing is
+        // staged; and nothing here depends on the tie-break, so this may run (and the row sends may start) before it. The aux
+        // words need bucket and end marker: packed now if the tie-break is done, else by the first send that carries them.
+        if (cfg.use_names && n > 0) SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, (const uint64_t *)c.name_off, dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
+        else SCB_CUDA(cudaMemsetAsync(dnb.p, 0, (size_t)(G + 1) * 8, st));
+        SCB_CUDA(cudaMemcpyAsync(h->sh_first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaMemcpyAsync(h->sh_nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        const int64_t nb0 = h->sh_nbytes[0];
+        for (int g = 0; g <= G; g++) h->sh_nbytes[(size_t)g] -= nb0;
+        h->sh_names_src = cfg.use_names ? c.names + nb0 : nullptr;
+        h->sh_aux_pending = true;
+        if (h->sh_resolved && n > 0) {
+            SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+                       cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
+            h->sh_aux_pending = false;
+        }
+    } else {
+        if (n > 0)
+            SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+                       cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
+        h->sh_noff.alloc((size_t)(n + 1) * 8, st);
+        DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+        exclusive_scan<uint64_t>(AuxNameLen{h->sh_aux.as<uint64_t>()}, n, h->sh_noff.as<uint64_t>(), h->sh_noff.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        SCB_LAUNCH(gather_u64_k, 1, kMaxRanks + 1, 0, st, h->sh_noff.as<uint64_t>(), dfirst.as<int64_t>(), G + 1, dnb.as<int64_t>());
+        SCB_CUDA(cudaMemcpyAsync(h->sh_first.data(), dfirst.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaMemcpyAsync(h->sh_nbytes.data(), dnb.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+    }
     h->sh_cnt_reads.assign((size_t)G, 0); h->sh_cnt_name_bytes.assign((size_t)G, 0);
     for (int g = 0; g < G; g++) { h->sh_cnt_reads[g] = h->sh_first[g + 1] - h->sh_first[g]; h->sh_cnt_name_bytes[g] = h->sh_nbytes[g + 1] - h->sh_nbytes[g]; }
-    const int64_t name_bytes = h->sh_nbytes[(size_t)G];
-    if (cfg.use_names) {   // names are staged contiguously per destination (variable length: bulk copies move them)
+    name_bytes = h->sh_nbytes[(size_t)G];
+    if (cfg.use_names && split) {   // names are staged contiguously per destination (variable length: bulk copies move them)
         h->sh_names.alloc((size_t)name_bytes + 16, st);
         if (n > 0) SCB_LAUNCH(pack_names_k, (unsigned)cdiv(n, 256), 256, 0, st, perm, n, c.name_off, c.names, h->sh_noff.as<uint64_t>(), h->sh_names.as<uint8_t>());
+        h->sh_names_src = h->sh_names.as<uint8_t>();
     }
     tm.stop();
     memset(out, 0, sizeof *out);
     out->n = n; out->name_bytes = cfg.use_names ? name_bytes : 0;
     out->aux = h->sh_aux.as<uint64_t>();
-    out->names = cfg.use_names ? h->sh_names.as<uint8_t>() : nullptr;
+    out->names = cfg.use_names ? h->sh_names_src : nullptr;
     out->cnt_reads = h->sh_cnt_reads.data(); out->cnt_name_bytes = h->sh_cnt_name_bytes.data();
     out->packed_row_bytes = h->PW * 4;
     h->sh_G = G;
-    h->sh_phase = 3;
+    h->sh_phase = std::max(h->sh_phase, 3);
 }
 
 // staged variant: rows gathered into local send arrays (the caller moves them, e.g. NCCL all-to-all)
@@ -1579,30 +1609,44 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
     // at 1 / 2 / 4 per SM / uncapped; profiles/r02_multi_gpu_ab.txt)
     const int cap = async ? 148 * 4 : 0;
     if (async) { SCB_CUDA(cudaEventRecord(h->ev_fork, h->st)); SCB_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0)); }
-    cudaEventRecord(h->ev_s0, st);
+    cudaEventRecord(async ? h->ev_a0 : h->ev_s0, st);
+    if ((what & 1) && h->sh_aux_pending) {     // partitioned before the tie-break (chunk ownership): bucket and end marker exist only now
+        if (!h->sh_resolved) throw CudaError{"sharded run: the aux words need scb_shard_finalize before they are sent"};
+        const int64_t n = c.n;
+        if (n > 0)
+            SCB_LAUNCH(pack_aux_k, (unsigned)cdiv(n, 256), 256, 0, st, h->sh_perm.as<uint32_t>(), n, h->asg.as<uint32_t>(), h->endv.as<uint16_t>(),
+                       cfg.use_names ? c.name_off : (const int64_t *)nullptr, h->chunk.as<uint32_t>(), h->sh_aux.as<uint64_t>());
+        h->sh_aux_pending = false;
+    }
+    // chunk ownership: a destination's reads are one contiguous range of the input, every array moves as one copy (copy engines,
+    // no SMs); bucket ranges: row gathers by the owner-sorted order
+    const bool contiguous = h->sh_split_mode == 1;
+    auto rows = [&](const uint8_t *src, void *dst_base, int64_t row_off, int64_t f, int64_t ng, int L) {
+        if (contiguous) SCB_CUDA(cudaMemcpyAsync((uint8_t *)dst_base + row_off * L, src + f * (int64_t)L, (size_t)ng * L, cudaMemcpyDeviceToDevice, st));
+        else gather_rows_to(st, src, (uint8_t *)dst_base + row_off * L, h->sh_perm.as<uint32_t>() + f, ng, L, cap);
+    };
     for (int k = 1; k <= G; k++) {
         const int g = (rank + k) % G;
         const int64_t ng = h->sh_cnt_reads[g];
         if (ng == 0) continue;
         const scb_shard_peer &pp = peers[g];
         const int64_t f = h->sh_first[g];
-        const uint32_t *perm = h->sh_perm.as<uint32_t>() + f;
         if (what & 1) {
             SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.aux + pp.row_off * 8, h->sh_aux.as<uint64_t>() + f, (size_t)ng * 8, cudaMemcpyDeviceToDevice, st));
-            gather_rows_to(st, h->packed.as<uint8_t>(), (uint8_t *)pp.packed + pp.row_off * prow, perm, ng, prow, cap);
+            rows(h->packed.as<uint8_t>(), pp.packed, pp.row_off, f, ng, prow);
             if (cfg.use_names && h->sh_cnt_name_bytes[g] > 0)
-                SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names.as<uint8_t>() + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
+                SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names_src + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
                                          cudaMemcpyDeviceToDevice, st));
         }
         if (what & 2) {
-            if (cfg.use_quals) gather_rows_to(st, c.qual1, (uint8_t *)pp.qual1 + pp.row_off * L1, perm, ng, L1, cap);
+            if (cfg.use_quals) rows(c.qual1, pp.qual1, pp.row_off, f, ng, L1);
             if (cfg.paired) {
-                gather_rows_to(st, c.seq2, (uint8_t *)pp.seq2 + pp.row_off * L2, perm, ng, L2, cap);
-                if (cfg.use_quals) gather_rows_to(st, c.qual2, (uint8_t *)pp.qual2 + pp.row_off * L2, perm, ng, L2, cap);
+                rows(c.seq2, pp.seq2, pp.row_off, f, ng, L2);
+                if (cfg.use_quals) rows(c.qual2, pp.qual2, pp.row_off, f, ng, L2);
             }
         }
     }
-    SCB_CUDA(cudaEventRecord(h->ev_s1, st));
+    SCB_CUDA(cudaEventRecord(async ? h->ev_a1 : h->ev_s1, st));
     if (!async) {
         SCB_CUDA(cudaStreamSynchronize(st));
         SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_s0, h->ev_s1));
@@ -1611,7 +1655,7 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
 }
 static void shard_send_wait(scb_handle *h) {
     SCB_CUDA(cudaStreamSynchronize(h->st_aux[0]));
-    SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_s0, h->ev_s1));
+    SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_a0, h->ev_a1));
     h->sh_local = Pending();
 }
 
@@ -2223,6 +2267,7 @@ int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_
 }
 int scb_shard_bucket_hist(scb_handle *h, uint32_t *hist_dev) {
     SCB_SHARD_ENTER(2)
+    if (!h->sh_resolved) { scb::g_last_error = "sharded run: call order violated (scb_shard_finalize first)"; return SCB_ESTATE; }
     scb::shard_bucket_hist(h, hist_dev);
     SCB_CATCH
     return SCB_OK;
@@ -2235,18 +2280,21 @@ static int shard_split_ok(const scb_handle *h, const int64_t *split, int32_t n_r
 int scb_shard_partition(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
     if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(2)
+    if (!h->sh_resolved) { scb::g_last_error = "sharded run: call order violated (scb_shard_finalize first)"; return SCB_ESTATE; }
     if (!shard_split_ok(h, split, n_ranks)) return SCB_EINVAL;
     scb::shard_partition(h, split, n_ranks, out);
     SCB_CATCH
     return SCB_OK;
 }
+// callable from scb_shard_sizes on: ownership by flush chunk does not depend on the tie-break
 int scb_shard_partition_chunks(scb_handle *h, const int32_t *chunk_owner, int32_t n_chunks, int32_t n_ranks, scb_shard_xfer *out) {
     if (!chunk_owner || !out || n_chunks < 1 || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks, >= 1 chunk)"; return SCB_EINVAL; }
     for (int c = 0; c < n_chunks; c++)
         if (chunk_owner[c] < 0 || chunk_owner[c] >= n_ranks || (c > 0 && chunk_owner[c] < chunk_owner[c - 1])) {
             scb::g_last_error = "chunk owners must be ranks and must not decrease along the chunk order"; return SCB_EINVAL;
         }
-    SCB_SHARD_ENTER(2)
+    SCB_SHARD_ENTER(1)
+    if (!h->chunk.p || h->sh_phase >= 5) { scb::g_last_error = "sharded run: scb_shard_partition_chunks belongs between scb_shard_sizes and the import"; return SCB_ESTATE; }
     {
         const int64_t c0 = h->sh_layout[0], nn = h->sh_layout[1], n = h->sh_layout[2], tail = h->sh_layout[4];
         const int64_t last = nn > 0 ? (tail > 0 ? c0 + nn : c0 + nn - 1) : c0;          // largest chunk id a local read carries
@@ -2275,6 +2323,7 @@ int scb_shard_chunk_owners(const int64_t *layouts, int32_t n_ranks, int32_t n_ch
 int scb_shard_pack(scb_handle *h, const int64_t *split, int32_t n_ranks, scb_shard_xfer *out) {
     if (!split || !out || n_ranks < 1 || n_ranks > scb::kMaxRanks) { scb::g_last_error = "bad argument (1..64 ranks)"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(2)
+    if (!h->sh_resolved) { scb::g_last_error = "sharded run: call order violated (scb_shard_finalize first)"; return SCB_ESTATE; }
     if (!shard_split_ok(h, split, n_ranks)) return SCB_EINVAL;
     scb::shard_partition(h, split, n_ranks, out);
     const float ms = h->sh_ms;
@@ -2337,6 +2386,7 @@ int scb_ipc_close(scb_handle *h, void *peer_ptr) {
 int scb_shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chunks_global) {
     if (!in || in->n < 0 || n_chunks_global < 0) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
     SCB_SHARD_ENTER(4)
+    if (!h->sh_resolved || h->sh_aux_pending) { scb::g_last_error = "sharded run: call order violated (the tie-break and the aux-word send precede the import)"; return SCB_ESTATE; }
     scb::shard_import(h, in, n_chunks_global);
     SCB_CATCH
     return SCB_OK;
@@ -2557,6 +2607,77 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
                 if (!strcmp(e, "buckets")) by_chunk = false;
             }
         }
+        // ---- chunk ownership: nothing of the partition depends on the tie-break, so the receive arrays are sized and published and
+        //      the quality / mate-2 rows start crossing NVLink (copy engines) now, under the tie-break ---------------------------------
+        scb_shard_xfer x;
+        memset(&x, 0, sizeof x);
+        std::vector<scb_shard_peer> peers((size_t)G);
+        scb_shard_xfer y;
+        memset(&y, 0, sizeof y);
+        auto setup_exchange = [&]() -> int {
+            // ---- exchange: what every rank receives from every rank -----------------------------------------------------------
+            std::vector<int64_t> mine((size_t)2 * G);
+            for (int g = 0; g < G; g++) { mine[(size_t)g] = x.cnt_reads[g]; mine[(size_t)G + g] = x.cnt_name_bytes[g]; }
+            const std::vector<int64_t> mat = comm_allgather_i64(cm, mine);      // mat[s * 2G + g] = reads s -> g
+            int64_t n_recv = 0, nb_recv = 0;
+            for (int s2 = 0; s2 < G; s2++) { n_recv += mat[(size_t)s2 * 2 * G + r]; nb_recv += mat[(size_t)s2 * 2 * G + G + r]; }
+            const int prow = x.packed_row_bytes;
+            const int64_t need[6] = {n_recv * 8, n_recv * prow + 64, cfg.use_quals ? n_recv * L1 : 0, cfg.use_names ? nb_recv + 16 : 0,
+                                     cfg.paired ? n_recv * L2 : 0, (cfg.paired && cfg.use_quals) ? n_recv * L2 : 0};
+            void *ptrs[6]; int32_t changed = 0;
+            SCB_FL(scb_shard_recv_reserve(h, need, ptrs, &changed));
+            // publish the receive arrays: raw pointers between threads of one process, CUDA IPC handles between processes
+            const bool have_table = (int)h->fl_table.size() == G;
+            const std::vector<int64_t> anyc = comm_allgather_i64(cm, {(int64_t)((changed || !have_table) ? 1 : 0)});
+            bool any_changed = false;
+            for (int g = 0; g < G; g++) any_changed |= anyc[(size_t)g] != 0;
+            if (any_changed) {
+                h->fl_table.assign((size_t)G, std::vector<void *>(6, nullptr));
+                if (cm->same_process) {
+                    std::vector<int64_t> pm(6);
+                    for (int k = 0; k < 6; k++) pm[(size_t)k] = (int64_t)(uintptr_t)ptrs[k];
+                    const std::vector<int64_t> pa = comm_allgather_i64(cm, pm);
+                    for (int g = 0; g < G; g++) for (int k = 0; k < 6; k++) h->fl_table[(size_t)g][(size_t)k] = (void *)(uintptr_t)pa[(size_t)g * 6 + k];
+                } else {
+                    std::vector<uint8_t> hb(6 * 72, 0), ha((size_t)G * 6 * 72);
+                    for (int k = 0; k < 6; k++) if (ptrs[k]) { SCB_FL(scb_ipc_export(h, ptrs[k], &hb[(size_t)k * 72])); hb[(size_t)k * 72 + 64] = 1; }
+                    comm_check(cm->allgather(cm->ctx, hb.data(), ha.data(), (int64_t)hb.size(), 0, nullptr), "allgather (host)");
+                    for (int g = 0; g < G; g++)
+                        for (int k = 0; k < 6; k++) {
+                            const uint8_t *e = &ha[((size_t)g * 6 + k) * 72];
+                            if (g == r) { h->fl_table[(size_t)g][(size_t)k] = ptrs[k]; continue; }
+                            if (!e[64]) continue;
+                            auto key = std::make_pair(g, k);
+                            auto it = h->fl_ipc.find(key);
+                            if (it == h->fl_ipc.end() || memcmp(it->second.first.data(), e, 64) != 0) {
+                                if (it != h->fl_ipc.end()) scb_ipc_close(h, it->second.second);
+                                void *mp = nullptr;
+                                SCB_FL(scb_ipc_open(h, e, &mp));
+                                h->fl_ipc[key] = std::make_pair(std::vector<uint8_t>(e, e + 64), mp);
+                            }
+                            h->fl_table[(size_t)g][(size_t)k] = h->fl_ipc[key].second;
+                        }
+                }
+            } else {
+                for (int k = 0; k < 6; k++) h->fl_table[(size_t)r][(size_t)k] = ptrs[k];
+            }
+            for (int g = 0; g < G; g++) {
+                scb_shard_peer &pg = peers[(size_t)g];
+                void **t = h->fl_table[(size_t)g].data();
+                pg.aux = t[0]; pg.packed = t[1]; pg.qual1 = t[2]; pg.names = t[3]; pg.seq2 = t[4]; pg.qual2 = t[5];
+                pg.row_off = 0; pg.name_off = 0;
+                for (int s2 = 0; s2 < r; s2++) { pg.row_off += mat[(size_t)s2 * 2 * G + g]; pg.name_off += mat[(size_t)s2 * 2 * G + G + g]; }
+            }
+            y.n = n_recv; y.name_bytes = nb_recv; y.packed_row_bytes = prow;
+            y.aux = (const uint64_t *)ptrs[0]; y.packed = (const uint8_t *)ptrs[1]; y.qual1 = (const uint8_t *)ptrs[2]; y.names = (const uint8_t *)ptrs[3];
+            y.seq2 = (const uint8_t *)ptrs[4]; y.qual2 = (const uint8_t *)ptrs[5];
+            return SCB_OK;
+        };
+        if (by_chunk) {
+            SCB_FL(scb_shard_partition_chunks(h, owner.data(), n_chunks, G, &x)); lap(P_PACK);
+            SCB_FL(setup_exchange());
+            SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+        }
         // ---- tie-break ------------------------------------------------------------------------------------------------
         const int RW = ncols + 1;
         DevBuf tot((size_t)RW * 4, st), all((size_t)G * RW * 4, st), bf((size_t)ncols * 4, st), gtot((size_t)ncols * 4, st), dchg(8, st);
@@ -2592,11 +2713,8 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
         SCB_LAUNCH(sh_sum_rows_k, (unsigned)cdiv(ncols, 256), 256, 0, st, all.as<uint32_t>(), RW, 0, G, ncols, gtot.as<uint32_t>());
         SCB_CUDA(cudaStreamSynchronize(st));
         SCB_FL(scb_shard_finalize(h, gtot.as<uint32_t>(), n_global)); lap(P_FINALIZE);
-        // ---- partition by owner --------------------------------------------------------------------------------------------
-        scb_shard_xfer x;
-        if (by_chunk) {
-            SCB_FL(scb_shard_partition_chunks(h, owner.data(), n_chunks, G, &x)); lap(P_PACK);
-        } else {
+        if (!by_chunk) {
+            // ---- bucket ranges: owners follow from the global bucket histogram ---------------------------------------------------------
             DevBuf hist((size_t)ncols * 4, st), allh((size_t)G * ncols * 4, st);
             SCB_FL(scb_shard_bucket_hist(h, hist.as<uint32_t>())); lap(P_HIST);
             comm_check(cm->allgather(cm->ctx, hist.p, allh.p, (int64_t)ncols * 4, 1, st), "allgather (device)");
@@ -2608,72 +2726,14 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
             for (int g = 0; g < G; g++) for (int c2 = 0; c2 < ncols; c2++) gh[(size_t)c2] += hh[(size_t)g * ncols + c2];
             const std::vector<int64_t> split = balanced_split(gh, G);
             SCB_FL(scb_shard_partition(h, split.data(), G, &x)); lap(P_PACK);
+            SCB_FL(setup_exchange());
         }
-        // ---- exchange: what every rank receives from every rank -----------------------------------------------------------
-        std::vector<int64_t> mine((size_t)2 * G);
-        for (int g = 0; g < G; g++) { mine[(size_t)g] = x.cnt_reads[g]; mine[(size_t)G + g] = x.cnt_name_bytes[g]; }
-        const std::vector<int64_t> mat = comm_allgather_i64(cm, mine);      // mat[s * 2G + g] = reads s -> g
-        int64_t n_recv = 0, nb_recv = 0;
-        for (int s2 = 0; s2 < G; s2++) { n_recv += mat[(size_t)s2 * 2 * G + r]; nb_recv += mat[(size_t)s2 * 2 * G + G + r]; }
-        const int prow = x.packed_row_bytes;
-        const int64_t need[6] = {n_recv * 8, n_recv * prow + 64, cfg.use_quals ? n_recv * L1 : 0, cfg.use_names ? nb_recv + 16 : 0,
-                                 cfg.paired ? n_recv * L2 : 0, (cfg.paired && cfg.use_quals) ? n_recv * L2 : 0};
-        void *ptrs[6]; int32_t changed = 0;
-        SCB_FL(scb_shard_recv_reserve(h, need, ptrs, &changed));
-        // publish the receive arrays: raw pointers between threads of one process, CUDA IPC handles between processes
-        const bool have_table = (int)h->fl_table.size() == G;
-        const std::vector<int64_t> anyc = comm_allgather_i64(cm, {(int64_t)((changed || !have_table) ? 1 : 0)});
-        bool any_changed = false;
-        for (int g = 0; g < G; g++) any_changed |= anyc[(size_t)g] != 0;
-        if (any_changed) {
-            h->fl_table.assign((size_t)G, std::vector<void *>(6, nullptr));
-            if (cm->same_process) {
-                std::vector<int64_t> pm(6);
-                for (int k = 0; k < 6; k++) pm[(size_t)k] = (int64_t)(uintptr_t)ptrs[k];
-                const std::vector<int64_t> pa = comm_allgather_i64(cm, pm);
-                for (int g = 0; g < G; g++) for (int k = 0; k < 6; k++) h->fl_table[(size_t)g][(size_t)k] = (void *)(uintptr_t)pa[(size_t)g * 6 + k];
-            } else {
-                std::vector<uint8_t> hb(6 * 72, 0), ha((size_t)G * 6 * 72);
-                for (int k = 0; k < 6; k++) if (ptrs[k]) { SCB_FL(scb_ipc_export(h, ptrs[k], &hb[(size_t)k * 72])); hb[(size_t)k * 72 + 64] = 1; }
-                comm_check(cm->allgather(cm->ctx, hb.data(), ha.data(), (int64_t)hb.size(), 0, nullptr), "allgather (host)");
-                for (int g = 0; g < G; g++)
-                    for (int k = 0; k < 6; k++) {
-                        const uint8_t *e = &ha[((size_t)g * 6 + k) * 72];
-                        if (g == r) { h->fl_table[(size_t)g][(size_t)k] = ptrs[k]; continue; }
-                        if (!e[64]) continue;
-                        auto key = std::make_pair(g, k);
-                        auto it = h->fl_ipc.find(key);
-                        if (it == h->fl_ipc.end() || memcmp(it->second.first.data(), e, 64) != 0) {
-                            if (it != h->fl_ipc.end()) scb_ipc_close(h, it->second.second);
-                            void *mp = nullptr;
-                            SCB_FL(scb_ipc_open(h, e, &mp));
-                            h->fl_ipc[key] = std::make_pair(std::vector<uint8_t>(e, e + 64), mp);
-                        }
-                        h->fl_table[(size_t)g][(size_t)k] = h->fl_ipc[key].second;
-                    }
-            }
-        } else {
-            for (int k = 0; k < 6; k++) h->fl_table[(size_t)r][(size_t)k] = ptrs[k];
-        }
-        std::vector<scb_shard_peer> peers((size_t)G);
-        for (int g = 0; g < G; g++) {
-            scb_shard_peer &pg = peers[(size_t)g];
-            void **t = h->fl_table[(size_t)g].data();
-            pg.aux = t[0]; pg.packed = t[1]; pg.qual1 = t[2]; pg.names = t[3]; pg.seq2 = t[4]; pg.qual2 = t[5];
-            pg.row_off = 0; pg.name_off = 0;
-            for (int s2 = 0; s2 < r; s2++) { pg.row_off += mat[(size_t)s2 * 2 * G + g]; pg.name_off += mat[(size_t)s2 * 2 * G + G + g]; }
-        }
-        scb_shard_xfer y;
-        memset(&y, 0, sizeof y);
-        y.n = n_recv; y.name_bytes = nb_recv; y.packed_row_bytes = prow;
-        y.aux = (const uint64_t *)ptrs[0]; y.packed = (const uint8_t *)ptrs[1]; y.qual1 = (const uint8_t *)ptrs[2]; y.names = (const uint8_t *)ptrs[3];
-        y.seq2 = (const uint8_t *)ptrs[4]; y.qual2 = (const uint8_t *)ptrs[5];
-        // what the receive side needs to SORT goes first; the quality / mate-2 rows cross NVLink on a side stream while the received
-        // reads are sorted and are only awaited before the emit
+        // what the receive side needs to SORT goes first; the quality / mate-2 rows cross NVLink on a side stream (bucket ranges: while
+        // the received reads are sorted; chunk ownership: since before the tie-break) and are only awaited before the emit
         SCB_FL(scb_shard_send(h, r, G, peers.data(), 1, 0)); lap(P_EXCH);
         comm_check(cm->barrier(cm->ctx), "barrier");
         SCB_FL(scb_shard_import(h, &y, n_chunks)); lap(P_IMPORT);
-        SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+        if (!by_chunk) SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
         SCB_FL(scb_shard_finish_sort(h)); lap(P_SORT);
         SCB_FL(scb_shard_send_wait(h)); lap(P_ROWS);
         comm_check(cm->barrier(cm->ctx), "barrier");           // every rank's row writes have landed
@@ -2774,6 +2834,8 @@ void scb_destroy(scb_handle *h) {
     for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+    if (h->ev_a0) cudaEventDestroy(h->ev_a0);
+    if (h->ev_a1) cudaEventDestroy(h->ev_a1);
     for (auto &kv : h->fl_ipc) cudaIpcCloseMemHandle(kv.second.second);
     for (auto &r : h->rx) if (r) cudaFree(r);
     for (void *r : h->rx_retired) cudaFree(r);

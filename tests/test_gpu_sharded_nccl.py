@@ -14,11 +14,12 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("orch", ["python", "cpp_nccl"])
+@pytest.mark.parametrize("orch", ["python", "cpp_nccl", "cpp_nccl_chunks"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_over_nccl(world, orch):
     """orch = python: scalce_b200/shard.py over torch.distributed; cpp_nccl: scb_shard_flush (the C++ orchestrator) over
-    libscalce_b200_nccl.so. Either way one process per GPU, NCCL + CUDA IPC peer stores, checked against the oracle; the worker
+    libscalce_b200_nccl.so; cpp_nccl_chunks: the same without a merged stream, i.e. with whole flush chunks handed to the ranks
+    instead of bucket ranges. Either way one process per GPU, NCCL + CUDA IPC peer stores, checked against the oracle; the worker
     leaves a record under gpurun_out/ (copies of the round's runs: profiles/sharded_nccl_w*.json)."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -1,22 +1,30 @@
 #!/bin/bash
-# N GPUs (gpurun --gpus N): parity over NCCL + CUDA IPC first (default path, then the in-kernel joint rounds + early emit), then the
-# bench line per switch. Usage: gpurun --gpus 2 --timeout 1500 -- 'bash tools/r2_multi.sh 2'
+# N GPUs (gpurun --gpus N): parity over NCCL + CUDA IPC (C++ orchestrator: bucket ranges, flush chunks), host<->device copy rates of
+# all ranks at once with and without CPU binding, then the bench lines. Usage: gpurun --gpus 2 --timeout 1500 -- 'bash tools/r2_multi.sh 2'
 N=${1:-2}
 mkdir -p gpurun_out/r2
 export PYTHONUNBUFFERED=1
-tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
-echo "== parity, default"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29501 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
-echo "== parity, joint kernel + early emit"; SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29502 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
-echo "== parity, C++ orchestrator + NCCL comm library"; SCB_ORCH=cpp_nccl timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29504 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
-echo "== parity, C++ orchestrator + torch collectives"; SCB_ORCH=cpp timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29505 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
-echo "== parity, sparse engine"; SCB_RESOLVE=sparse SCB_TABLE=global timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29503 tests/sharded_nccl_worker.py 120000 100 2097152 2>&1 | tail -3
+nvidia-smi topo -m > gpurun_out/r2/n${N}_topo.txt 2>&1
+for o in cpp_nccl cpp_nccl_chunks; do
+  echo "== parity, $o"; SCB_ORCH=$o timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29504 tests/sharded_nccl_worker.py 120000 100 1048576 2>&1 | tail -2
+done
+for b in 0 1; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29506 tools/pcie_multi.py --bind $b 2>/dev/null | grep '^{' > gpurun_out/r2/n${N}_pcie_bind$b.json
+  python - <<PY
+import json
+d = json.load(open("gpurun_out/r2/n${N}_pcie_bind$b.json"))
+print("pcie bind=$b slowest rank GB/s", {k: round(v, 1) for k, v in d["slowest_rank_GBps"].items()}, "sum", {k: round(v, 1) for k, v in d["sum_GBps"].items()}, d["binding"][0])
+PY
+done
 run() {
   local name=$1; shift
-  env "$@" timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $N --steps 3 --warmup 2 --no-cpu $EXTRA > gpurun_out/r2/n${N}_$name.json 2> gpurun_out/r2/n${N}_$name.err
   echo "== $name rc=$?"; python tools/bench_brief.py gpurun_out/r2/n${N}_$name.json; tail -2 gpurun_out/r2/n${N}_$name.err | cut -c1-300
 }
-EXTRA="--e2e-steps 3" run default
-EXTRA="--no-e2e --no-parity" run early_emit SCB_SHARD_EARLY_EMIT=1
-EXTRA="--no-e2e --no-parity" run joint_kernel SCB_SHARD_JOINT_KERNEL=1
-EXTRA="--no-e2e --no-parity" run joint_early SCB_SHARD_JOINT_KERNEL=1 SCB_SHARD_EARLY_EMIT=1
+EXTRA="--e2e-steps 3" run chunks
+EXTRA="--no-e2e --no-parity" run buckets SCB_SHARD_SPLIT=buckets
+if [ -n "$MORE" ]; then
+  EXTRA="--no-e2e --no-parity --cores 1000000" run 1Mcores
+  EXTRA="--no-e2e --no-parity --config c3" run c3
+fi
