@@ -613,6 +613,8 @@ def main():
         st = dict(sharded.stats["ms"])
         st["_rounds"] = sharded.stats["rounds"]
         st["_split"] = sharded.stats.get("split", "bucket ranges")
+        for k, v in (sharded.stats.get("wall_ms") or {}).items():
+            st["wall:" + k] = v
         return e0.elapsed_time(e1), st
 
     def one_step():
@@ -750,6 +752,8 @@ def main():
     split_mode = stages[-1].get("_split") if isinstance(stages[-1], dict) else None
     mean_st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0] if k != "_split"}
     resolve_rounds = mean_st.pop("_rounds", None)
+    # N > 1: host wall time per phase of scb_shard_flush on rank 0 (device work + collectives + waiting for the other ranks)
+    phase_wall = {k[5:]: mean_st.pop(k) for k in list(mean_st) if k.startswith("wall:")} or None
     dom = max(mean_st, key=mean_st.get)
     packed = (L - mean_core + 3) // 4 + (2 if L > 255 else 1)
     PWB = (L + 15) // 16 * 4                       # bytes of a 2-bit packed row
@@ -774,7 +778,8 @@ def main():
         d_["frac"] = (d_["achieved_gbs"] / peak) if d_["achieved_gbs"] else None
     roof = {"bound": "hbm", "kernel": dom, "kernels": STAGE_KERNELS.get(dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
-            "peak_source": peak_src, "bytes_per_read": stage_bytes.get(dom), "stage_ms": mean_st, "per_stage": per_stage, "resolve_rounds": resolve_rounds}
+            "peak_source": peak_src, "bytes_per_read": stage_bytes.get(dom), "stage_ms": mean_st, "per_stage": per_stage, "resolve_rounds": resolve_rounds,
+            **({"phase_wall_ms_rank0": phase_wall} if phase_wall else {})}
     pipe = N * bpr / (ms_step * 1e-3) / 1e9
     pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
 

@@ -328,6 +328,9 @@ typedef struct scb_comm {
 #define SCB_N_SHARD_PHASES 12
 int scb_shard_flush(scb_handle *h, const scb_comm *comm, scb_result *out);
 int scb_shard_flush_stats(const scb_handle *h, float *phase_ms, int32_t cap, int32_t *rounds);
+/* Host wall time per phase of the last scb_shard_flush, same order: from the end of the phase before to the end of the phase,
+ * i.e. device work + collectives + waiting for the other ranks. Their sum is the duration of the call. */
+int scb_shard_flush_wall(const scb_handle *h, float *wall_ms, int32_t cap);
 /* Reads of this rank's own input shard in the last sharded flush (the per-read arrays of scb_result refer to them). */
 int64_t scb_shard_n_local(const scb_handle *h);
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "scb_shard_finalize", "scb_shard_bucket_hist", "scb_shard_pack", "scb_shard_import", "scb_shard_finish", "scb_shard_last_ms",
     "scb_shard_partition", "scb_shard_recv_reserve", "scb_shard_send", "scb_shard_send_wait", "scb_shard_finish_sort", 
     "scb_ipc_export", "scb_ipc_open", "scb_ipc_close", "scb_shard_flush", "scb_shard_flush_stats", "scb_shard_n_local",
-    "scb_shard_chunk_layout", "scb_shard_partition_chunks", "scb_shard_split_mode", "scb_shard_chunk_owners",
+    "scb_shard_chunk_layout", "scb_shard_partition_chunks", "scb_shard_split_mode", "scb_shard_chunk_owners", "scb_shard_flush_wall",
 ]
 
 
@@ -139,6 +139,7 @@ def load_library(path: str | None = None):
     L.scb_shard_chunk_layout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.scb_shard_partition_chunks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(ScbShardXfer)]
     L.scb_shard_split_mode.argtypes = [C.c_void_p]
+    L.scb_shard_flush_wall.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     L.scb_shard_chunk_owners.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     if path is None:
         _lib = L

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -185,6 +186,7 @@ struct scb_handle {
     std::map<std::pair<int, int>, std::pair<std::vector<uint8_t>, void *>> fl_ipc;   // (rank, array) -> (IPC handle bytes, mapped pointer)
     std::vector<std::vector<void *>> fl_table;                                       // [rank][array]
     float fl_ms[SCB_N_SHARD_PHASES] = {};
+    float fl_wall[SCB_N_SHARD_PHASES] = {};   // host wall time per phase of the last scb_shard_flush (includes collectives and waiting)
     int fl_rounds = 0;
     // sparse resolve engine (resolve_sparse.cuh): bucket-major view of the candidate pairs, built once per flush
     int engine = 0;            // engine of the current flush: 0 dense, 1 sparse, 2 sequential
@@ -204,6 +206,7 @@ struct scb_handle {
     int64_t sh_layout[5] = {0, 0, 0, 0, 0};   // flush chunks of the local shard: first chunk id, new chunks, reads, reads of the first chunk, reads of the last
     int sh_split_mode = 0;                   // ownership of the last sharded flush: 0 bucket ranges, 1 flush chunks
     bool sh_resolved = false;                // scb_shard_finalize has run for the current shard
+    bool sh_sized = false;                   // scb_shard_sizes has run for the current shard (global chunk ids exist)
     bool sh_aux_pending = false;             // chunk ownership, partitioned before the tie-break: the aux words are packed by the first send that carries them
     const uint8_t *sh_names_src = nullptr;   // names in send order: the staged copy (bucket ranges) or the input itself (flush chunks: send order = input order)
     void *rx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // receive buffers: aux, packed, qual1, names, seq2, qual2
@@ -1307,9 +1310,20 @@ static void shard_scan(scb_handle *h) {
     stage_scan(h);
     h->asg.alloc((size_t)n * 4, st);
     h->endv.alloc((size_t)n * 2, st);
+    {   // rd.sz prefix sums of the shard (compress.cpp:702): every rank at once, here; only the walk along the chunk boundaries
+        // (scb_shard_sizes) has to wait for the ranks before it
+        const scb_config &cfg = h->cfg;
+        const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
+        const int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
+        RdSize rs{h->cur.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
+        DevBuf ws64((size_t)scan_tiles(n) * 8, st);
+        h->sh_sizes.alloc((size_t)(n + 1) * 8, st);
+        exclusive_scan<uint64_t>(rs, n, h->sh_sizes.as<uint64_t>(), h->sh_sizes.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
+        h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
+    }
     tm.stop();
     h->last_rounds = 0;
-    h->sh_resolved = false; h->sh_aux_pending = false; h->sh_names_src = nullptr;
+    h->sh_resolved = false; h->sh_sized = false; h->sh_aux_pending = false; h->sh_names_src = nullptr;
     h->sh_phase = 1;
 }
 
@@ -1321,11 +1335,6 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
     const Pending &c = h->cur;
     const int64_t n = c.n;
     ShardTimer tm(h);
-    const int fixed = (cfg.use_quals ? L1 : 0) + (cfg.paired ? sz_read(L2) + (cfg.use_quals ? L2 : 0) : 0) + 40;
-    RdSize rs{c.name_off, h->lvl.as<uint8_t>(), L1, fixed, cfg.use_names};
-    DevBuf ws64((size_t)scan_tiles(n) * 8, st);
-    h->sh_sizes.alloc((size_t)(n + 1) * 8, st);
-    exclusive_scan<uint64_t>(rs, n, h->sh_sizes.as<uint64_t>(), h->sh_sizes.as<uint64_t>() + n, ws64.as<uint64_t>(), st);
     const uint64_t max_rd = 256 + (uint64_t)sz_read(L1) + L1 + sz_read(L2) + L2 + 40;
     uint64_t cap64 = (uint64_t)n * max_rd / cfg.bucket_set_bytes + 2;
     if (cap64 > (uint64_t)n + 1) cap64 = (uint64_t)n + 1;
@@ -1339,7 +1348,6 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
     SCB_CUDA(cudaStreamSynchronize(st));
     if ((int64_t)o[0] > cap) throw CudaError{"internal: chunk capacity exceeded"};
     if ((uint64_t)chunk_in + o[0] >= kAuxMaxChunks) throw CudaError{"too many flush chunks for the sharded run (>= 2^20)"};
-    h->chunk.alloc((size_t)std::max<int64_t>(n, 1) * 4, st);
     if (n > 0) SCB_LAUNCH(chunk_ids_global_k, (unsigned)cdiv(n, 256), 256, 0, st, bounds.as<uint32_t>(), (int)o[0], (uint32_t)chunk_in, n, h->chunk.as<uint32_t>());
     {   // what an orchestrator needs to hand whole chunks to ranks (scb_shard_chunk_layout)
         uint32_t b2[2] = {0, 0};
@@ -1353,6 +1361,7 @@ static void shard_sizes(scb_handle *h, uint64_t carry_in, int32_t chunk_in, uint
         h->sh_layout[4] = o[0] > 0 ? n - (int64_t)b2[1] : 0;
     }
     tm.stop();
+    h->sh_sized = true;
     *carry_out = o[1];
     *chunk_out = chunk_in + (int32_t)o[0];
 }
@@ -2260,7 +2269,7 @@ int scb_shard_resolve_round(scb_handle *h, const uint32_t *before_dev, int64_t r
 }
 int scb_shard_finalize(scb_handle *h, const uint32_t *global_tot_dev, int64_t n_global) {
     SCB_SHARD_ENTER(1)
-    if (!h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_finalize"; return SCB_ESTATE; }
+    if (!h->sh_sized) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_finalize"; return SCB_ESTATE; }
     scb::shard_finalize(h, global_tot_dev, n_global);
     SCB_CATCH
     return SCB_OK;
@@ -2294,7 +2303,7 @@ int scb_shard_partition_chunks(scb_handle *h, const int32_t *chunk_owner, int32_
             scb::g_last_error = "chunk owners must be ranks and must not decrease along the chunk order"; return SCB_EINVAL;
         }
     SCB_SHARD_ENTER(1)
-    if (!h->chunk.p || h->sh_phase >= 5) { scb::g_last_error = "sharded run: scb_shard_partition_chunks belongs between scb_shard_sizes and the import"; return SCB_ESTATE; }
+    if (!h->sh_sized || h->sh_phase >= 5) { scb::g_last_error = "sharded run: scb_shard_partition_chunks belongs between scb_shard_sizes and the import"; return SCB_ESTATE; }
     {
         const int64_t c0 = h->sh_layout[0], nn = h->sh_layout[1], n = h->sh_layout[2], tail = h->sh_layout[4];
         const int64_t last = nn > 0 ? (tail > 0 ? c0 + nn : c0 + nn - 1) : c0;          // largest chunk id a local read carries
@@ -2306,7 +2315,7 @@ int scb_shard_partition_chunks(scb_handle *h, const int32_t *chunk_owner, int32_
 }
 int scb_shard_chunk_layout(const scb_handle *h, int64_t *out5) {
     if (!h || !out5) { scb::g_last_error = "bad argument"; return SCB_EINVAL; }
-    if (h->sh_phase < 1 || !h->chunk.p) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_chunk_layout"; return SCB_ESTATE; }
+    if (h->sh_phase < 1 || !h->sh_sized) { scb::g_last_error = "sharded run: scb_shard_sizes must precede scb_shard_chunk_layout"; return SCB_ESTATE; }
     for (int k = 0; k < 5; k++) out5[k] = h->sh_layout[k];
     return SCB_OK;
 }
@@ -2566,10 +2575,13 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
     const scb_config &cfg = h->cfg;
     const int L1 = cfg.read_length[0], L2 = cfg.read_length[1];
     float *ms = h->fl_ms;
-    for (int k = 0; k < SCB_N_SHARD_PHASES; k++) ms[k] = 0.f;
+    for (int k = 0; k < SCB_N_SHARD_PHASES; k++) { ms[k] = 0.f; h->fl_wall[k] = 0.f; }
+    auto wall_last = std::chrono::steady_clock::now();
+    // wall[k]: host time from the end of the phase before to the end of phase k (device work + collectives + waiting for other ranks)
+    auto wall = [&](int k) { const auto now = std::chrono::steady_clock::now(); h->fl_wall[k] += std::chrono::duration<float, std::milli>(now - wall_last).count(); wall_last = now; };
     h->fl_rounds = 0;
     enum { P_SCAN, P_CHUNKS, P_RESOLVE, P_ROUNDS, P_FINALIZE, P_HIST, P_PACK, P_EXCH, P_IMPORT, P_SORT, P_ROWS, P_EMIT };
-    auto lap = [&](int k) { ms[k] += scb_shard_last_ms(h); };
+    auto lap = [&](int k) { ms[k] += scb_shard_last_ms(h); wall(k); };
     try {
         SCB_CUDA(cudaSetDevice(cfg.device));
         cudaStream_t st = h->st;
@@ -2677,6 +2689,7 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
             SCB_FL(scb_shard_partition_chunks(h, owner.data(), n_chunks, G, &x)); lap(P_PACK);
             SCB_FL(setup_exchange());
             SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+            wall(P_PACK);          // wall time of the partition phase includes the exchange set-up (counts, receive arrays, IPC handles)
         }
         // ---- tie-break ------------------------------------------------------------------------------------------------
         const int RW = ncols + 1;
@@ -2707,6 +2720,7 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
             SCB_CUDA(cudaEventRecord(e1, st));
             SCB_CUDA(cudaStreamSynchronize(st));
             SCB_CUDA(cudaEventElapsedTime(&ms[P_ROUNDS], e0, e1));
+            wall(P_ROUNDS);
             cudaEventDestroy(e0); cudaEventDestroy(e1);
         }
         h->fl_rounds = rounds;
@@ -2727,6 +2741,7 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
             const std::vector<int64_t> split = balanced_split(gh, G);
             SCB_FL(scb_shard_partition(h, split.data(), G, &x)); lap(P_PACK);
             SCB_FL(setup_exchange());
+            wall(P_PACK);
         }
         // what the receive side needs to SORT goes first; the quality / mate-2 rows cross NVLink on a side stream (bucket ranges: while
         // the received reads are sorted; chunk ownership: since before the tie-break) and are only awaited before the emit
@@ -2745,6 +2760,12 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
 }
 
 int64_t scb_shard_n_local(const scb_handle *h) { return h ? h->sh_n_local : -1; }
+
+int scb_shard_flush_wall(const scb_handle *h, float *wall_ms, int32_t cap) {
+    if (!h || !wall_ms) return SCB_EINVAL;
+    for (int k = 0; k < SCB_N_SHARD_PHASES && k < cap; k++) wall_ms[k] = h->fl_wall[k];
+    return SCB_N_SHARD_PHASES;
+}
 
 int scb_shard_flush_stats(const scb_handle *h, float *phase_ms, int32_t cap, int32_t *rounds) {
     if (!h) return SCB_EINVAL;

@@ -589,7 +589,9 @@ class CShardedTransform:
         ms = (C.c_float * 12)()
         rounds = C.c_int32()
         L.scb_shard_flush_stats(self.t._h, ms, 12, C.byref(rounds))
-        self.stats = dict(ms=dict(zip(self.PHASES, [float(x) for x in ms])), rounds=rounds.value,
+        wall = (C.c_float * 12)()
+        L.scb_shard_flush_wall(self.t._h, wall, 12)
+        self.stats = dict(ms=dict(zip(self.PHASES, [float(x) for x in ms])), rounds=rounds.value, wall_ms=dict(zip(self.PHASES, [float(x) for x in wall])),
                           split=("flush chunks" if L.scb_shard_split_mode(self.t._h) == 1 else "bucket ranges"))
         out = FlushResult(self.t, res)
         out.n_local = self.t.n_local_last()

@@ -15,6 +15,9 @@ for p in sys.argv[1:]:
     print(f"{p}: {d['value'] / 1e9:.3f} G reads/s, {d['ms_per_step']:.2f} ms/step, n_gpus {d['n_gpus']}, launches {d.get('gpu_launches')}, "
           f"path {d['pipeline_roofline']['frac_of_peak']:.3f} of HBM peak, workspace {d.get('workspace_bytes_per_flush', 0) / 2**30:.1f} GiB")
     print("   stages ms:", {k: round(v, 2) for k, v in (r.get("stage_ms") or {}).items()}, "rounds", r.get("resolve_rounds"))
+    if r.get("phase_wall_ms_rank0"):
+        w = r["phase_wall_ms_rank0"]
+        print("   wall ms (rank 0):", {k: round(v, 2) for k, v in w.items()}, "sum", round(sum(w.values()), 2))
     if e:
         print("   e2e:", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in e.items() if k in ("value", "ms_per_step", "ms_per_step_min", "ms_submit_flush_copyout", "error", "skipped")},
               "serial", e.get("serial"), "piped", (e.get("pipelined") or {}).get("ms_per_step"))
