@@ -110,7 +110,6 @@ class ClockSampler:
                 self._reasons(self.h)
             self.nvml = pynvml
             self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
             return
         except Exception:
             self.nvml = None
@@ -118,9 +117,16 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
         except Exception:
             self.proc = None
+
+    def start(self):
+        """Sampling starts here; construction (NVML initialisation: ~0.1 s) belongs before the barrier that opens the timed region -
+        at N > 1 a rank 0 that enters its first timed step late makes every other rank wait inside that step."""
+        if self.nvml is not None or self.proc is not None:
+            self.samples.clear(); self.lines.clear()
+            self.t.start()
+        return self
 
     def _poll(self):
         nv = self.nvml
@@ -602,15 +608,24 @@ def main():
     off0 = name_off
 
     def one_step_sharded():
+        hr = time.perf_counter()
         tr.reset_counts()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         tr.submit_device(N, seq.data_ptr(), qual.data_ptr(), names.data_ptr(), name_off.data_ptr(),
                          seq2.data_ptr() if paired else None, qual2.data_ptr() if paired else None)
+        h1 = time.perf_counter()
         sharded.flush()
+        h2 = time.perf_counter()
         e1.record()
         torch.cuda.synchronize()
+        h3 = time.perf_counter()
         st = dict(sharded.stats["ms"])
+        st["wall:_reset"] = (h0 - hr) * 1e3
+        st["wall:_sync_after"] = (h3 - h2) * 1e3
+        st["wall:_submit"] = (h1 - h0) * 1e3
+        st["wall:_flush_call"] = (h2 - h1) * 1e3
         st["_rounds"] = sharded.stats["rounds"]
         st["_split"] = sharded.stats.get("split", "bucket ranges")
         for k, v in (sharded.stats.get("wall_ms") or {}).items():
@@ -644,8 +659,10 @@ def main():
 
     for _ in range(a.warmup):
         one_step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
     launches0 = lib.scb_kernel_launches(None)
     t0 = time.perf_counter()
     dev_ms, stages = [], []
@@ -659,7 +676,14 @@ def main():
     launches = lib.scb_kernel_launches(None) - launches0
     clocks = sampler.stop() if sampler else None
     ms_step = float(np.mean(dev_ms))
+    by_rank = None
     if dist is not None:
+        # every rank's own view of the step: device time, host wall per phase of scb_shard_flush (collectives and waiting included)
+        mine = {"rank": rank, "ms_per_step": ms_step,
+                "wall_ms": {k[5:]: round(float(np.mean([s_[k] for s_ in stages])), 3) for k in stages[0] if k.startswith("wall:")}}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        by_rank = gathered
         tt = torch.tensor([ms_step, wall_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_step, wall_ms = float(tt[0]), float(tt[1])
@@ -779,7 +803,7 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "kernels": STAGE_KERNELS.get(dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
             "peak_source": peak_src, "bytes_per_read": stage_bytes.get(dom), "stage_ms": mean_st, "per_stage": per_stage, "resolve_rounds": resolve_rounds,
-            **({"phase_wall_ms_rank0": phase_wall} if phase_wall else {})}
+            **({"phase_wall_ms_rank0": phase_wall} if phase_wall else {}), **({"by_rank": by_rank} if by_rank else {})}
     pipe = N * bpr / (ms_step * 1e-3) / 1e9
     pipeline = {"achieved": pipe, "unit": "GB/s", "frac_of_peak": pipe / peak, "frac_of_nominal_8TBs": pipe / 8000.0, "bytes_per_read": bpr}
 

@@ -18,6 +18,9 @@ for p in sys.argv[1:]:
     if r.get("phase_wall_ms_rank0"):
         w = r["phase_wall_ms_rank0"]
         print("   wall ms (rank 0):", {k: round(v, 2) for k, v in w.items()}, "sum", round(sum(w.values()), 2))
+    for br in (r.get("by_rank") or []):
+        w = br.get("wall_ms") or {}
+        print(f"   rank {br['rank']}: {br['ms_per_step']:.2f} ms/step; wall", {k: round(v, 1) for k, v in w.items()})
     if e:
         print("   e2e:", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in e.items() if k in ("value", "ms_per_step", "ms_per_step_min", "ms_submit_flush_copyout", "error", "skipped")},
               "serial", e.get("serial"), "piped", (e.get("pipelined") or {}).get("ms_per_step"))
