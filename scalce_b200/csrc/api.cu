@@ -2138,7 +2138,7 @@ int scb_submit(scb_handle *h, const scb_batch *b) {
             // the same contract as for host batches: every name 0..255 bytes (the reference's length byte, names.cpp:48-62)
             scb::DevBuf rng(16, st);
             SCB_CUDA(cudaMemsetAsync(rng.p, 0, 16, st));
-            SCB_LAUNCH(scb::name_len_range_k, (unsigned)scb::cdiv(b->n, 256), 256, 0, st, b->name_off, b->n, rng.as<long long>());
+            SCB_LAUNCH(scb::name_len_range_k, (unsigned)std::max<int64_t>(1, std::min<int64_t>(scb::cdiv(b->n, 256), 148 * 8)), 256, 0, st, b->name_off, b->n, rng.as<long long>());
             long long r2[2] = {0, 0};
             SCB_CUDA(cudaMemcpyAsync(r2, rng.p, 16, cudaMemcpyDeviceToHost, st));
             SCB_CUDA(cudaStreamSynchronize(st));
