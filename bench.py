@@ -49,9 +49,9 @@ CONFIGS = {
 
 
 # DRAM bytes per read of each stage's kernels at the headline shape: dram__bytes_read.sum + dram__bytes_write.sum, summed over
-# the stage's launches of one ncu pass over a headline step (profiles/r02_launches_summary.txt)
-NCU_TRAFFIC_PER_READ = {"emit": 718, "resolve": 114, "scan": 227, "sort": 226, "ties": 20, "chunks": 28, "arrays": 22}
-NCU_TRAFFIC_SOURCE = "ncu launch list of the headline step with this round's kernels (profiles/r02_launches_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's launches"
+# the stage's launches of one ncu pass over a headline step (profiles/r02_final_launches_summary.txt)
+NCU_TRAFFIC_PER_READ = {"emit": 736, "resolve": 108, "scan": 227, "sort": 226, "ties": 15, "chunks": 28, "arrays": 16}
+NCU_TRAFFIC_SOURCE = "ncu launch list of the headline step with this round's kernels (profiles/r02_final_launches_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's launches"
 STAGE_KERNELS = {"emit": "gather_rows16_k + emit_reads_fast_k + emit_names_st_k + emit_off_reduce_k / emit_off_apply_k (metadata gather + offset scans)",
                  "resolve": "resolve_dense_k + resolve_finalize_k (dense) or sp_flags_k / sp_tilescan_k / sp_counts_k / sp_decide_k per round (sparse)",
                  "scan": "scan_smem2_k (table in shared memory) or scan_big_k (table in global memory / L2)",
