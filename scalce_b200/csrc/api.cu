@@ -113,6 +113,10 @@ struct Pending {
     const uint8_t *seq1 = nullptr, *qual1 = nullptr, *names = nullptr, *seq2 = nullptr, *qual2 = nullptr;
     const int64_t *name_off = nullptr;
     int64_t name_bytes = 0;
+    // sharded run, chunk ownership: rows [own_lo, own_hi) of qual1 / seq2 / qual2 are not in those arrays but in the rank's own
+    // input (own_* pre-offset: row r at own_x + r * L); see RowSrc
+    int64_t own_lo = 0, own_hi = 0;
+    const uint8_t *own_qual1 = nullptr, *own_seq2 = nullptr, *own_qual2 = nullptr;
     DevBuf b_seq1, b_qual1, b_names, b_off, b_seq2, b_qual2;
 };
 
@@ -208,6 +212,8 @@ struct scb_handle {
     bool sh_resolved = false;                // scb_shard_finalize has run for the current shard
     bool sh_sized = false;                   // scb_shard_sizes has run for the current shard (global chunk ids exist)
     bool sh_aux_pending = false;             // chunk ownership, partitioned before the tie-break: the aux words are packed by the first send that carries them
+    bool sh_rows_in_place = false;           // chunk ownership: this rank's own quality / mate-2 rows were not copied into its receive arrays
+    int64_t sh_self_lo = 0; int sh_rank = 0;  // where this rank's reads start in its own receive numbering; its rank
     const uint8_t *sh_names_src = nullptr;   // names in send order: the staged copy (bucket ranges) or the input itself (flush chunks: send order = input order)
     void *rx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // receive buffers: aux, packed, qual1, names, seq2, qual2
     size_t rx_cap[6] = {0, 0, 0, 0, 0, 0};
@@ -378,7 +384,7 @@ static void gather_pending(scb_handle *h) {
 }
 
 // dst row p <- src row perm[p], rows of L bytes (dst dense and 16-byte aligned)
-static void gather_rows_any(cudaStream_t st, const uint8_t *src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
+static void gather_rows_any(cudaStream_t st, const RowSrc src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
     if (n <= 0 || L <= 0) return;
     if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
     else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
@@ -402,9 +408,9 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     const int nch = merged ? 1 : h->n_chunks;
     if (part == 2) {   // the row-dependent kernels alone, into the streams part 1 allocated
         if (n == 0) return;
-        if (cfg.use_quals) gather_rows_any(st, c.qual1, o.data[2].as<uint8_t>(), perm, n, L1);
-        if (cfg.paired && cfg.use_quals) gather_rows_any(st, c.qual2, o.data[5].as<uint8_t>(), perm, n, L2);
-        if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, c.seq2, perm, n, L2, o.data[4].as<uint8_t>());
+        if (cfg.use_quals) gather_rows_any(st, RowSrc{c.qual1, c.own_qual1, c.own_lo, c.own_hi}, o.data[2].as<uint8_t>(), perm, n, L1);
+        if (cfg.paired && cfg.use_quals) gather_rows_any(st, RowSrc{c.qual2, c.own_qual2, c.own_lo, c.own_hi}, o.data[5].as<uint8_t>(), perm, n, L2);
+        if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, RowSrc{c.seq2, c.own_seq2, c.own_lo, c.own_hi}, perm, n, L2, o.data[4].as<uint8_t>());
         return;
     }
     const bool rows_now = (part & 2) != 0;
@@ -447,7 +453,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
     e.offN = offN.as<uint64_t>(); e.offR = offR.as<uint64_t>(); e.n = n; e.L1 = L1; e.sz_meta = sz_meta;
     e.oN = o.data[0].as<uint8_t>(); e.oR = o.data[1].as<uint8_t>();
     uint8_t *oQ = o.data[2].as<uint8_t>(), *oR2 = o.data[4].as<uint8_t>(), *oQ2 = o.data[5].as<uint8_t>();
-    auto gather_rows = [&](const uint8_t *src, uint8_t *dst, int L) { gather_rows_any(st, src, dst, perm, n, L); };
+    auto gather_rows = [&](const RowSrc src, uint8_t *dst, int L) { gather_rows_any(st, src, dst, perm, n, L); };
     // The output kernels are independent of each other: names and packed reads (latency / issue bound) run on side
     // streams next to the quality-row gather (HBM bound) instead of one after the other.
     SCB_CUDA(cudaEventRecord(h->ev_fork, st));
@@ -468,11 +474,11 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         SCB_CUDA(cudaFuncSetAttribute(emit_reads_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_LAUNCH(emit_reads_fast_k, (unsigned)n_blk, 256, smem, sR, e, RPB, inv_half, recmax, n_blk);
     }
-    if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, c.seq2, perm, n, L2, oR2);
+    if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, RowSrc{c.seq2, c.own_seq2, c.own_lo, c.own_hi}, perm, n, L2, oR2);
     if (sN != st) SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
     SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
-    if (cfg.use_quals && rows_now) gather_rows(c.qual1, oQ, L1);
-    if (cfg.paired && cfg.use_quals && rows_now) gather_rows(c.qual2, oQ2, L2);
+    if (cfg.use_quals && rows_now) gather_rows(RowSrc{c.qual1, c.own_qual1, c.own_lo, c.own_hi}, oQ, L1);
+    if (cfg.paired && cfg.use_quals && rows_now) gather_rows(RowSrc{c.qual2, c.own_qual2, c.own_lo, c.own_hi}, oQ2, L2);
     if (sN != st) SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
     SCB_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     DevBuf cfirst((size_t)2 * std::max(nch, 1) * 8, st);
@@ -1323,7 +1329,7 @@ static void shard_scan(scb_handle *h) {
     }
     tm.stop();
     h->last_rounds = 0;
-    h->sh_resolved = false; h->sh_sized = false; h->sh_aux_pending = false; h->sh_names_src = nullptr;
+    h->sh_resolved = false; h->sh_sized = false; h->sh_aux_pending = false; h->sh_names_src = nullptr; h->sh_rows_in_place = false;
     h->sh_phase = 1;
 }
 
@@ -1482,7 +1488,7 @@ static void gather_rows_to(cudaStream_t st, const uint8_t *src, uint8_t *dst, co
     } else if ((L & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
         SCB_LAUNCH(gather_words_to_k, (unsigned)cdiv(n * (L / 4), 256), 256, 0, st, (const uint32_t *)src, (uint32_t *)dst, perm, n, L / 4);
     } else {
-        SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
+        SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, RowSrc{src, nullptr, 0, 0}, dst, perm, n, L);
     }
 }
 
@@ -1647,7 +1653,11 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
                 SCB_CUDA(cudaMemcpyAsync((uint8_t *)pp.names + pp.name_off, h->sh_names_src + h->sh_nbytes[g], (size_t)h->sh_cnt_name_bytes[g],
                                          cudaMemcpyDeviceToDevice, st));
         }
-        if (what & 2) {
+        if ((what & 2) && contiguous && g == rank) {
+            // the rank's own rows stay where they are: the emit reads them from the input (RowSrc), so most of the "exchange" of
+            // chunk ownership - a local copy of ~80-90 % of the quality / mate-2 bytes - does not happen at all
+            h->sh_rows_in_place = true; h->sh_self_lo = pp.row_off; h->sh_rank = rank;
+        } else if (what & 2) {
             if (cfg.use_quals) rows(c.qual1, pp.qual1, pp.row_off, f, ng, L1);
             if (cfg.paired) {
                 rows(c.seq2, pp.seq2, pp.row_off, f, ng, L2);
@@ -1665,7 +1675,7 @@ static void shard_send(scb_handle *h, int rank, const scb_shard_peer *peers, int
 static void shard_send_wait(scb_handle *h) {
     SCB_CUDA(cudaStreamSynchronize(h->st_aux[0]));
     SCB_CUDA(cudaEventElapsedTime(&h->sh_ms, h->ev_a0, h->ev_a1));
-    h->sh_local = Pending();
+    if (!h->sh_rows_in_place) h->sh_local = Pending();     // else the emit still reads the rank's own rows from it
 }
 
 // persistent receive buffers (plain cudaMalloc so that they can be exported over CUDA IPC), grown with headroom
@@ -1706,6 +1716,15 @@ static void shard_import(scb_handle *h, const scb_shard_xfer *in, int32_t n_chun
     Pending imp;
     imp.n = n; imp.borrowed = true;
     imp.qual1 = in->qual1; imp.names = in->names; imp.seq2 = in->seq2; imp.qual2 = in->qual2; imp.name_bytes = in->name_bytes;
+    if (h->sh_rows_in_place) {
+        // received rows [lo, hi) are this rank's own reads [first, first + cnt) of its input: row r there is input row r - lo + first
+        const int L2 = cfg.read_length[1];
+        const int64_t lo = h->sh_self_lo, cnt = h->sh_cnt_reads[(size_t)h->sh_rank], first = h->sh_first[(size_t)h->sh_rank];
+        const Pending &own = h->cur;
+        imp.own_lo = lo; imp.own_hi = lo + cnt;
+        auto shifted = [&](const uint8_t *p, int L) { return p ? (const uint8_t *)((intptr_t)p + (intptr_t)(first - lo) * L) : nullptr; };
+        imp.own_qual1 = shifted(own.qual1, L1); imp.own_seq2 = shifted(own.seq2, L2); imp.own_qual2 = shifted(own.qual2, L2);
+    }
     h->packed.borrow((void *)in->packed, (size_t)n * h->PW * 4);
     h->asg.alloc((size_t)std::max<int64_t>(n, 1) * 4, st); h->endv.alloc((size_t)std::max<int64_t>(n, 1) * 2, st); h->lvl.alloc((size_t)std::max<int64_t>(n, 1), st);
     h->n_chunks = n_chunks_global;
@@ -1734,7 +1753,10 @@ static void shard_finish(scb_handle *h, int what /* 1 = sort, 2 = emit, 3 = both
     if (what & 4) stage_emit(h, 1);
     if (what & 8) stage_emit(h, 2);
     tm.stop();
-    if (what & (2 | 8)) h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
+    if (what & (2 | 8)) {
+        h->sh_phase = 6;   // stage_debug keys on != 0; reset by the next flush / scan
+        if (h->sh_rows_in_place) { SCB_CUDA(cudaStreamSynchronize(h->st)); h->sh_local = Pending(); h->sh_rows_in_place = false; }
+    }
 }
 
 // ---- the transform on one GPU ------------------------------------------------------------------------------
@@ -2688,14 +2710,20 @@ int scb_shard_flush(scb_handle *h, const scb_comm *cm, scb_result *out) {
         if (by_chunk) {
             SCB_FL(scb_shard_partition_chunks(h, owner.data(), n_chunks, G, &x)); lap(P_PACK);
             SCB_FL(setup_exchange());
-            SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+            // rank 0 is about to resolve its shard alone: its small memsets and copies would queue behind 2.3 ms of row copies on the
+            // copy engines (measured: the stream sat idle that long before the tie-break kernel), so ITS rows leave after that, under
+            // the joint rounds; every other rank only waits for rank 0 now and sends at once
+            if (r != 0) SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
             wall(P_PACK);          // wall time of the partition phase includes the exchange set-up (counts, receive arrays, IPC handles)
         }
         // ---- tie-break ------------------------------------------------------------------------------------------------
         const int RW = ncols + 1;
         DevBuf tot((size_t)RW * 4, st), all((size_t)G * RW * 4, st), bf((size_t)ncols * 4, st), gtot((size_t)ncols * 4, st), dchg(8, st);
         SCB_CUDA(cudaMemsetAsync(tot.p, 0, (size_t)RW * 4, st));
-        if (r == 0) { SCB_FL(scb_shard_resolve_local(h, tot.as<uint32_t>())); lap(P_RESOLVE); }
+        if (r == 0) {
+            SCB_FL(scb_shard_resolve_local(h, tot.as<uint32_t>())); lap(P_RESOLVE);
+            if (by_chunk) SCB_FL(scb_shard_send(h, r, G, peers.data(), 2, 1));
+        }
         comm_check(cm->allgather(cm->ctx, tot.p, all.p, (int64_t)RW * 4, 1, st), "allgather (device)");
         int rounds = 0;
         if (G > 1) {
