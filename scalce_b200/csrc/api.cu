@@ -386,7 +386,8 @@ static void gather_pending(scb_handle *h) {
 // dst row p <- src row perm[p], rows of L bytes (dst dense and 16-byte aligned)
 static void gather_rows_any(cudaStream_t st, const RowSrc src, uint8_t *dst, const uint32_t *perm, int64_t n, int L) {
     if (n <= 0 || L <= 0) return;
-    if (L >= 16) SCB_LAUNCH(gather_rows16_k, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
+    if (L >= 16 && src.split()) SCB_LAUNCH(gather_rows16_k<true>, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
+    else if (L >= 16) SCB_LAUNCH(gather_rows16_k<false>, (unsigned)cdiv(cdiv(n * L, 16), 256 * kGatherChunks), 256, 0, st, src, dst, perm, n, L);
     else SCB_LAUNCH(gather_rows_small_k, (unsigned)cdiv(n * L, 256), 256, 0, st, src, dst, perm, n, L);
 }
 
@@ -410,7 +411,7 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         if (n == 0) return;
         if (cfg.use_quals) gather_rows_any(st, RowSrc{c.qual1, c.own_qual1, c.own_lo, c.own_hi}, o.data[2].as<uint8_t>(), perm, n, L1);
         if (cfg.paired && cfg.use_quals) gather_rows_any(st, RowSrc{c.qual2, c.own_qual2, c.own_lo, c.own_hi}, o.data[5].as<uint8_t>(), perm, n, L2);
-        if (cfg.paired) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, RowSrc{c.seq2, c.own_seq2, c.own_lo, c.own_hi}, perm, n, L2, o.data[4].as<uint8_t>());
+        if (cfg.paired) { const RowSrc rs{c.seq2, c.own_seq2, c.own_lo, c.own_hi}; if (rs.split()) SCB_LAUNCH(emit_reads2_k<true>, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, rs, perm, n, L2, o.data[4].as<uint8_t>()); else SCB_LAUNCH(emit_reads2_k<false>, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, st, rs, perm, n, L2, o.data[4].as<uint8_t>()); }
         return;
     }
     const bool rows_now = (part & 2) != 0;
@@ -474,7 +475,11 @@ static void emit_order(scb_handle *h, const uint32_t *perm, const uint64_t *keys
         SCB_CUDA(cudaFuncSetAttribute(emit_reads_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_LAUNCH(emit_reads_fast_k, (unsigned)n_blk, 256, smem, sR, e, RPB, inv_half, recmax, n_blk);
     }
-    if (cfg.paired && rows_now) SCB_LAUNCH(emit_reads2_k, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, RowSrc{c.seq2, c.own_seq2, c.own_lo, c.own_hi}, perm, n, L2, oR2);
+    if (cfg.paired && rows_now) {
+        const RowSrc rs{c.seq2, c.own_seq2, c.own_lo, c.own_hi};
+        if (rs.split()) SCB_LAUNCH(emit_reads2_k<true>, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, rs, perm, n, L2, oR2);
+        else SCB_LAUNCH(emit_reads2_k<false>, (unsigned)cdiv(n * ((sz_read(L2) + 3) / 4), 256), 256, 0, sN, rs, perm, n, L2, oR2);
+    }
     if (sN != st) SCB_CUDA(cudaEventRecord(h->ev_join[0], sN));
     SCB_CUDA(cudaEventRecord(h->ev_join[1], sR));
     if (cfg.use_quals && rows_now) gather_rows(RowSrc{c.qual1, c.own_qual1, c.own_lo, c.own_hi}, oQ, L1);

@@ -280,12 +280,17 @@ __device__ __forceinline__ uint4 splice16(uint4 x, uint4 y, int k) {
 struct RowSrc {
     const uint8_t *p, *own;
     int64_t lo, hi;
-    __host__ __device__ __forceinline__ const uint8_t *row(int64_t r, int L) const { return ((r >= lo && r < hi) ? own : p) + r * (int64_t)L; }
+    // SEG = false: the caller knows lo == hi (one GPU, bucket ranges) and the two compares per row lookup are compiled out
+    // (they cost the one-GPU emit 0.15 ms of 9.85 when they were unconditional)
+    template <bool SEG>
+    __host__ __device__ __forceinline__ const uint8_t *row(int64_t r, int L) const { return ((SEG && r >= lo && r < hi) ? own : p) + r * (int64_t)L; }
+    bool split() const { return hi > lo; }
 };
 #ifndef SCB_GATHER_CHUNKS
 #define SCB_GATHER_CHUNKS 3
 #endif
 constexpr int kGatherChunks = SCB_GATHER_CHUNKS;   // independent 16-byte chunks per thread; 3 measured best (4: 11.7 ms emit, 3: 10.6, 2: 10.8)   // independent 16-byte chunks per thread (memory-level parallelism)
+template <bool SEG>
 __global__ void __launch_bounds__(256) gather_rows16_k(const RowSrc src, uint8_t *__restrict__ dst,
                                                        const uint32_t *__restrict__ perm, int64_t n, int L) {
     const int64_t total = n * (int64_t)L;
@@ -304,8 +309,8 @@ __global__ void __launch_bounds__(256) gather_rows16_k(const RowSrc src, uint8_t
             const int64_t p0 = pblk + dp;
             const int r0 = (int)(x - dp * (uint32_t)L);
             n0[q] = min(16, L - r0);
-            a0[q] = src.row(perm[p0], L) + r0;
-            if (n0[q] < 16 && p0 + 1 < n) a1[q] = src.row(perm[p0 + 1], L);
+            a0[q] = src.row<SEG>(perm[p0], L) + r0;
+            if (n0[q] < 16 && p0 + 1 < n) a1[q] = src.row<SEG>(perm[p0 + 1], L);
         }
     }
     uint4 v[kGatherChunks];
@@ -331,7 +336,7 @@ __global__ void gather_rows_small_k(const RowSrc src, uint8_t *__restrict__ dst,
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n * (int64_t)L) return;
     const int64_t p = o / L;
-    dst[o] = src.row(perm[p], L)[o - p * L];
+    dst[o] = src.row<true>(perm[p], L)[o - p * L];
 }
 
 // ---- per-read metadata word ---------------------------------------------------------------------------
@@ -439,6 +444,7 @@ __device__ __forceinline__ uint32_t spk_bits32(const uint32_t *row, int b0) {
 // SWAR packer, same code table as base_code); the byte-wise path only serves the last few bytes of the input array
 // (an aligned fetch would cross its end). Before: sixteen byte loads + base_code per thread, 12 ms of the 16.6 ms emit stage
 // of the paired 25M x 2 x 150 bp configuration.
+template <bool SEG>
 __global__ void __launch_bounds__(256) emit_reads2_k(const RowSrc seq2, const uint32_t *__restrict__ perm, int64_t n, int L2,
                                                      uint8_t *__restrict__ oR2) {
     const int nb2 = sz_read(L2), nw = (nb2 + 3) >> 2;
@@ -447,8 +453,8 @@ __global__ void __launch_bounds__(256) emit_reads2_k(const RowSrc seq2, const ui
     const int64_t p = t / nw;
     const int w = (int)(t - p * nw);
     const uint32_t src_row = perm[p];
-    const uint8_t *s = seq2.row(src_row, L2) + 16 * w;
-    const bool in_own = (int64_t)src_row >= seq2.lo && (int64_t)src_row < seq2.hi;
+    const uint8_t *s = seq2.row<SEG>(src_row, L2) + 16 * w;
+    const bool in_own = SEG && (int64_t)src_row >= seq2.lo && (int64_t)src_row < seq2.hi;
     const uint8_t *arr_end = in_own ? seq2.own + seq2.hi * (int64_t)L2 : seq2.p + n * (int64_t)L2;   // last byte + 1 of the array the row lives in
     const int nv = L2 - 16 * w < 16 ? L2 - 16 * w : 16;            // bases of this word (>= 1)
     uint32_t v = 0;
