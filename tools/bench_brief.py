@@ -17,7 +17,7 @@ for p in sys.argv[1:]:
     print("   stages ms:", {k: round(v, 2) for k, v in (r.get("stage_ms") or {}).items()}, "rounds", r.get("resolve_rounds"))
     if r.get("phase_wall_ms_rank0"):
         w = r["phase_wall_ms_rank0"]
-        print("   wall ms (rank 0):", {k: round(v, 2) for k, v in w.items()}, "sum", round(sum(w.values()), 2))
+        print("   wall ms (rank 0):", {k: round(v, 2) for k, v in w.items()}, "sum", round(sum(v for k, v in w.items() if not k.startswith("_")), 2))
     for br in (r.get("by_rank") or []):
         w = br.get("wall_ms") or {}
         print(f"   rank {br['rank']}: {br['ms_per_step']:.2f} ms/step; wall", {k: round(v, 1) for k, v in w.items()})
