@@ -245,12 +245,40 @@ assert comm.bcast_host([7 * (rank + 1), 3], src=1) == [14, 3]
 rng = np.random.default_rng(11)
 sizes = rng.integers(100, 400, size=600).tolist(); B = 5000
 bd = shard_bounds(len(sizes), world)
+lay = {{}}
 def sizes_fn(carry, chunk):
-    for s in sizes[bd[rank]:bd[rank + 1]]:
+    mine = sizes[bd[rank]:bd[rank + 1]]
+    starts = []                                   # local indices at which a new chunk starts (may equal len(mine))
+    c0 = chunk
+    for i, s in enumerate(mine):
         carry += s
-        if carry >= B: chunk += 1; carry = 0
+        if carry >= B: chunk += 1; carry = 0; starts.append(i + 1)
+    n = len(mine)
+    lay["v"] = [c0, len(starts), n, starts[0] if starts else n, (n - starts[-1]) if starts else 0]   # = scb_shard_chunk_layout
     return carry, chunk
 n_chunks = chain_chunks(sizes_fn, comm)
+# flush-chunk ownership: every rank derives the same owners from the all-gathered layouts (scb_shard_chunk_owners: host arithmetic)
+import ctypes as C
+from scalce_b200.binding import load_library
+L = load_library()
+lays = np.array(comm.allgather_host(lay["v"]), dtype=np.int64)
+owner = (C.c_int32 * n_chunks)(); ml = C.c_int64()
+assert L.scb_shard_chunk_owners(lays.ctypes.data_as(C.POINTER(C.c_int64)), world, n_chunks, owner, C.byref(ml)) == 0
+owners = list(owner)
+assert owners == sorted(owners) and set(owners) <= {{0, 1}}
+assert comm.allgather_host(owners) == [owners, owners]          # identical on both ranks
+# the owner of a chunk holds part of it, and the loads add up
+chunk_of, c, tot_ = [], 0, 0
+for s_ in sizes:
+    chunk_of.append(c); tot_ += s_
+    if tot_ >= B: c += 1; tot_ = 0
+load = [0, 0]
+for i, c_ in enumerate(chunk_of):
+    load[owners[c_]] += 1
+for c_ in range(n_chunks):
+    members = [i for i, x in enumerate(chunk_of) if x == c_]
+    assert any(bd[owners[c_]] <= i < bd[owners[c_] + 1] for i in members), (c_, owners[c_])
+assert sum(load) == len(sizes) and max(load) == ml.value, (load, ml.value)
 tot, c = 0, 0
 for s in sizes:
     tot += s
