@@ -218,3 +218,59 @@ def test_chunk_ownership_second_flush_and_sparse_engine(monkeypatch):
     monkeypatch.setenv("SCB_RESOLVE", "sparse")
     monkeypatch.setenv("SCB_TABLE", "global")
     _case_chunks(30000, 100, 3, seed=72, bucket_set_bytes=1 << 20)
+
+
+def test_chunk_ownership_two_flushes_on_the_same_handles(monkeypatch):
+    """What bench.py's timed steps and its e2e arm do: the same handles (receive arrays, lifetime counts, the rank's own rows left
+    in place) serve one sharded flush after the other. Reference: ONE handle flushing the same two inputs (itself pinned to the
+    oracle by the parity tests)."""
+    import threading
+    from scalce_b200.binding import BoostTransform
+    from scalce_b200.shard import CShardedTransform, LoopbackComm, shard_bounds
+    monkeypatch.setenv("SCB_SHARD_SPLIT", "chunks")
+    cores, b, q1, q2, _ = util.make_case(30000, 100, seed=73, paired=True, L2=60)
+    parts = ((0, 14000), (14000, 30000))
+    kw = dict(use_names=True, paired=True, use_quals=True, bucket_set_bytes=1 << 20, emit_merged=False)
+    streams = [0, 1, 2, 3, 4, 5]
+
+    def collect(r, n=None):
+        return dict(n_chunks=r.n_chunks, dbg=r.debug(n), streams={(k, c): r.stream(k, c) for k in streams for c in range(r.n_chunks)})
+
+    t1 = BoostTransform(cores, 100, 60, **kw)
+    want = []
+    for lo, hi in parts:
+        t1.submit(b.seq[lo:hi], q1[lo:hi], b.names, b.name_off[lo:hi + 1], b.seq2[lo:hi], q2[lo:hi])
+        want.append(collect(t1.flush()))
+    world = 3
+    comms = LoopbackComm.make(world, 0)
+    got = [[None] * world for _ in parts]
+    errs = []
+
+    def worker(r):
+        try:
+            t = BoostTransform(cores, 100, 60, **kw)
+            st = CShardedTransform(t, comms[r])
+            for f, (lo, hi) in enumerate(parts):
+                bd = shard_bounds(hi - lo, world)
+                a, z = lo + bd[r], lo + bd[r + 1]
+                t.submit(b.seq[a:z], q1[a:z], b.names, b.name_off[a:z + 1], b.seq2[a:z], q2[a:z])
+                res = st.flush()
+                assert st.stats["split"] == "flush chunks"
+                got[f][r] = collect(res, res.n_local)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            comms[r].s.barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    if errs:
+        real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    for f in range(len(parts)):
+        assert all(g["n_chunks"] == want[f]["n_chunks"] for g in got[f])
+        for k in ("node_id", "core", "end", "chunk"):
+            assert np.array_equal(np.concatenate([g["dbg"][k] for g in got[f]]), want[f]["dbg"][k]), (f, k)
+        for c in range(want[f]["n_chunks"]):
+            for k in streams:
+                assert b"".join(g["streams"][(k, c)] for g in got[f]) == want[f]["streams"][(k, c)], (f, c, k)
