@@ -1,5 +1,8 @@
 #!/bin/bash
-# scan tile staging: cp.async.bulk + mbarrier (default) against per-lane 16-byte cp.async (build/variants/lib_scan_ldgsts.so)
+# scan tile staging: cp.async.bulk + mbarrier (default) against per-lane 16-byte cp.async (build/variants/lib_scan_ldgsts.so).
+# The variant library is not kept in the tree; build it first (here, nvcc cross-compiles):
+#   mkdir -p build/variants && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 -shared \
+#     --expt-relaxed-constexpr -DSCB_SCAN_BULK=0 -o build/variants/lib_scan_ldgsts.so scalce_b200/csrc/api.cu scalce_b200/csrc/core_table.cpp
 mkdir -p gpurun_out/r2
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q 2>&1 | tail -4
 for rep in 1 2; do
