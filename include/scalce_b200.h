@@ -72,7 +72,9 @@ typedef struct scb_config {
  *          space; names.cpp:48-62) WITHOUT the length byte; name_off[n+1] byte offsets into it.
  *          A name longer than 255 bytes is an error (the reference's length byte wraps).
  *          NULL when use_names == 0.
- * location: 0 = host memory (pageable or pinned), 1 = device memory on cfg.device. */
+ * location: 0 = host memory (pageable or pinned), 1 = device memory on cfg.device. Device arrays are read in whole 16-byte
+ * granules: each must be readable up to the next 16-byte boundary past its last byte (true of anything cudaMalloc or a
+ * framework's caching allocator returns; a sub-range ending in the middle of a larger array is fine too). */
 typedef struct scb_batch {
     int64_t n;
     const uint8_t *seq1, *qual1;

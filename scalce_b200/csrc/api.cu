@@ -88,7 +88,9 @@ struct DevBuf {
         release();
         st = s; bytes = b;
         if (g_arena) { p = g_arena->alloc(b); pooled = false; return; }
-        if (b == 0) b = 16;
+        // the row / name gathers fetch whole 16-byte granules (load16_unaligned): the granule holding an array's last byte must
+        // belong to the allocation too - exact-size requests left up to 15 bytes of it outside (compute-sanitizer, emit_names_st_k)
+        b = (b + 16 + 255) & ~(size_t)255;
         SCB_CUDA(cudaMallocAsync(&p, b, s));
         pooled = true;
     }
